@@ -1,0 +1,214 @@
+"""Generate the golden fixtures in this directory by running the REFERENCE'S OWN CODE.
+
+Run in the build container only (``python tests/golden/make_golden.py``): it imports
+``neusky`` / ``reni`` from /root/reference through ``oracle/ref_shim`` (stand-ins for the
+absent nerfstudio / tinycudann / nerfacc packages).  /root/reference does not exist on the
+GPU box, so the resulting ``*.npz`` files are committed and tests only read those.
+
+Weights are NOT stored: every fixture records the seed, and ``neusky_b200.init`` regenerates
+the identical tensors (a checksum of the weights is stored to catch RNG drift).
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_shim  # noqa: E402
+
+ref_shim.install()
+
+from neusky_b200 import init as nb_init  # noqa: E402
+
+
+def checksum(params) -> str:
+    h = hashlib.sha256()
+    for k in sorted(params):
+        h.update(k.encode())
+        h.update(params[k].detach().contiguous().numpy().tobytes())
+    return h.hexdigest()
+
+
+def save(name, **arrays):
+    out = {}
+    for k, v in arrays.items():
+        if isinstance(v, torch.Tensor):
+            v = v.detach().cpu().numpy()
+        out[k] = v
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(f"wrote {path}: " + ", ".join(f"{k}{tuple(np.shape(v))}" for k, v in out.items()))
+
+
+# ------------------------------------------------------------------------------ icosphere
+def golden_icosphere():
+    from reni.model_components.illumination_samplers import IcosahedronSampler, IcosahedronSamplerConfig
+
+    out = {}
+    for n in (100, 256, 512):
+        s = IcosahedronSampler(IcosahedronSamplerConfig(num_directions=n))
+        out[f"dirs_{n}"] = s.directions
+    save("icosphere", **out)
+
+
+# ------------------------------------------------------------------------------ DDF + visibility
+DDF_SEED = 1234
+DDF_FINAL_GAIN = 8.0
+
+
+def build_reference_ddf():
+    from neusky.fields.directional_distance_field import DirectionalDistanceField, DirectionalDistanceFieldConfig
+
+    cfg = DirectionalDistanceFieldConfig(
+        ddf_type="ddf", position_encoding_type="hash", direction_encoding_type="nerf", conditioning="FiLM",
+        termination_output_activation="sigmoid", probability_of_hit_output_activation="sigmoid",
+        hidden_layers=5, hidden_features=256, mapping_layers=5, mapping_features=256,
+        num_attention_heads=8, num_attention_layers=6, predict_probability_of_hit=False,
+    )  # neusky/configs/neusky_config.py:162-177
+    field = DirectionalDistanceField(cfg, ddf_radius=1.0)
+    params = nb_init.init_ddf_params(DDF_SEED, final_gain=DDF_FINAL_GAIN)
+    missing, unexpected = field.load_state_dict(params, strict=True), None
+    field.eval()
+    return field, params
+
+
+def golden_ddf_and_visibility():
+    from nerfstudio.cameras.rays import RayBundle
+    from neusky.models.ddf_model import DDFModel
+    from neusky.models.neusky_model import NeuSkyFactoModel
+
+    field, params = build_reference_ddf()
+    g = torch.Generator().manual_seed(77)
+
+    # --- DDFModel.get_outputs on sphere points / inward directions (ddf_model.py:183-219)
+    ddf_self = types.SimpleNamespace(
+        field=field, training=False,
+        config=types.SimpleNamespace(
+            compute_normals=False, include_depth_loss_scene_center_weight=True,
+            loss_inclusions={"sdf_l1_loss": False, "sdf_l2_loss": True, "multi_view_loss": True, "sky_ray_loss": True},
+        ),
+    )
+    ddf_self.get_localised_transforms = lambda pos: DDFModel.get_localised_transforms(ddf_self, pos)
+    N = 512
+    q = torch.nn.functional.normalize(torch.randn(N, 3, generator=g), dim=-1)
+    q[:, 2] = q[:, 2].abs()
+    tgt = torch.randn(N, 3, generator=g) * 0.3
+    d = torch.nn.functional.normalize(tgt - q, dim=-1)
+    with torch.no_grad():
+        out = DDFModel.get_outputs(ddf_self, RayBundle(origins=q, directions=d, pixel_area=torch.ones(N)), None, None, True)
+    save("ddf_model", seed=DDF_SEED, final_gain=DDF_FINAL_GAIN, weights_sha256=checksum(params),
+         positions=q, directions=d, expected_termination_dist=out["expected_termination_dist"])
+
+    # --- NeuSkyFactoModel.compute_visibility (neusky_model.py:1624-1778) incl. outside-sphere rays
+    from reni.model_components.illumination_samplers import IcosahedronSampler, IcosahedronSamplerConfig
+
+    dirs = IcosahedronSampler(IcosahedronSamplerConfig(num_directions=100)).directions  # D=162
+    R, S, D = 48, 3, dirs.shape[0]
+    origins = torch.tensor([0.0, -0.9, 0.25]).expand(R, 3).clone() + 0.05 * torch.randn(R, 3, generator=g)
+    rdirs = torch.nn.functional.normalize(-origins + 0.6 * torch.randn(R, 3, generator=g), dim=-1)
+    p2p = 0.2 + 1.2 * torch.rand(R, 1, generator=g)
+    p2p[:6] = 2.5  # these land outside the DDF sphere -> the "hack" branch (:1674-1683)
+    model_self = types.SimpleNamespace(
+        ddf_radius=1.0,
+        config=types.SimpleNamespace(only_upperhemisphere_visibility=True, lower_hermisphere_visibility=True,
+                                     sdf_to_visibility_stop_gradients="depth"),
+        visibility_field=lambda rb, batch, neusky, stop_gradients: DDFModel.get_outputs(ddf_self, rb, batch, None, stop_gradients),
+    )
+    model_self.ray_sphere_intersection = lambda p, d_, r: NeuSkyFactoModel.ray_sphere_intersection(model_self, p, d_, r)
+    from nerfstudio.cameras.rays import Frustums, RaySamples
+
+    rs = RaySamples(frustums=Frustums(origins=origins[:, None].expand(R, S, 3).contiguous(),
+                                      directions=rdirs[:, None].expand(R, S, 3).contiguous(),
+                                      starts=torch.zeros(R, S, 1), ends=torch.ones(R, S, 1), pixel_area=torch.ones(R, S, 1)))
+    illum = dirs[None].expand(R * S, D, 3)
+    thr, scale = 0.1, 25.0
+    with torch.no_grad():
+        vd = NeuSkyFactoModel.compute_visibility(model_self, rs, p2p.clone(), illum, thr, scale)
+    vis = vd["visibility"].reshape(R, S, D)
+    assert torch.equal(vis[:, 0], vis[:, 1])
+    save("visibility", seed=DDF_SEED, final_gain=DDF_FINAL_GAIN, weights_sha256=checksum(params),
+         origins=origins, ray_dirs=rdirs, p2p=p2p, dirs=dirs, threshold=thr, sigmoid_scale=scale,
+         visibility=vis[:, 0], expected_termination_dist=vd["expected_termination_dist"],
+         termination_dist=vd["visibility_batch"]["termination_dist"])
+
+
+# ------------------------------------------------------------------------------ RENI++
+RENI_SEED = 4321
+
+
+def golden_reni():
+    from reni.illumination_fields.reni_illumination_field import RENIField, RENIFieldConfig
+    from reni.field_components.field_heads import RENIFieldHeadNames
+    from nerfstudio.cameras.rays import Frustums, RaySamples
+
+    cfg = RENIFieldConfig(
+        conditioning="Attention", invariant_function="VN", equivariance="SO2", axis_of_invariance="z",
+        positional_encoding="NeRF", encoded_input="Directions", latent_dim=100, hidden_features=128, hidden_layers=9,
+        mapping_layers=5, mapping_features=128, num_attention_heads=8, num_attention_layers=6,
+        output_activation="None", last_layer_linear=True, fixed_decoder=True, trainable_scale=True,
+    )  # neusky/configs/neusky_config.py:78-96
+    field = RENIField(cfg, num_train_data=None, num_eval_data=None, normalisations={"min_max": None, "log_domain": True})
+    params = nb_init.init_reni_params(RENI_SEED)
+    sd = field.state_dict()
+    for k, v in params.items():
+        assert k in sd and sd[k].shape == v.shape, (k, v.shape, sd.get(k, torch.zeros(0)).shape)
+    field.load_state_dict({**sd, **params}, strict=True)
+    field.eval()
+    g = torch.Generator().manual_seed(99)
+    K, D = 3, 40
+    dirs = torch.nn.functional.normalize(torch.randn(D, 3, generator=g), dim=-1)
+    Z = torch.randn(K, 100, 3, generator=g)
+    scale = 0.3 * torch.randn(K, generator=g)
+    rot = torch.tensor([[0.8, -0.6, 0.0], [0.6, 0.8, 0.0], [0.0, 0.0, 1.0]])
+    outs = {}
+    for tag, R in (("", None), ("_rot", rot)):
+        rows = []
+        for k in range(K):
+            rs = RaySamples(frustums=Frustums(origins=torch.zeros(D, 3), directions=dirs, starts=torch.zeros(D), ends=torch.ones(D), pixel_area=torch.ones(D)),
+                            camera_indices=torch.full((D,), k))
+            with torch.no_grad():
+                o = field.forward(rs, rotation=R, latent_codes=Z[k : k + 1].expand(D, -1, -1), scale=scale[k : k + 1].expand(D))
+            rows.append(field.unnormalise(o[RENIFieldHeadNames.RGB]))
+        outs["radiance" + tag] = torch.stack(rows, 0)
+    save("reni", seed=RENI_SEED, weights_sha256=checksum(params), dirs=dirs, latents=Z, scale=scale, rotation=rot, **outs)
+
+
+# ------------------------------------------------------------------------------ Lambertian renderer
+def golden_lambert():
+    from neusky.model_components.renderers import RGBLambertianRendererWithVisibility
+
+    g = torch.Generator().manual_seed(5)
+    R, S, D = 16, 4, 37
+    albedo = torch.rand(R, S, 3, generator=g)
+    normals = torch.nn.functional.normalize(torch.randn(R, S, 3, generator=g), dim=-1)
+    dirs = torch.nn.functional.normalize(torch.randn(D, 3, generator=g), dim=-1)
+    light = torch.exp(torch.randn(R, D, 3, generator=g))
+    vis = torch.rand(R, D, generator=g)
+    bg = torch.rand(R, 3, generator=g)
+    w = torch.rand(R, S, 1, generator=g) / S
+    ren = RGBLambertianRendererWithVisibility()
+    ren.eval()
+    rgb = ren(
+        albedos=albedo, normals=normals,
+        light_directions=dirs[None].expand(R * S, D, 3),
+        light_colors=light[:, None].expand(R, S, D, 3).reshape(R * S, D, 3),
+        visibility=vis[:, None].expand(R, S, D).reshape(R * S, D, 1),
+        background_illumination=bg, weights=w,
+    )
+    save("lambert", albedo=albedo, normals=normals, dirs=dirs, light=light, visibility=vis, bg=bg, weights=w, rgb=rgb)
+
+
+if __name__ == "__main__":
+    torch.manual_seed(0)
+    golden_icosphere()
+    golden_lambert()
+    golden_reni()
+    golden_ddf_and_visibility()
