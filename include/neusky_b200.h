@@ -1,0 +1,149 @@
+/*
+ * neusky_b200 -- C ABI of the B200-native NeuSky render-and-shade hot path.
+ *
+ * The reference (JADGardner/neusky) is 100% Python and has no FFI of its own; its boundary
+ * for this path is the nerfstudio Field/Model plugin API.  These are the
+ * entry points a drop-in plugin binds instead of the reference's torch/tcnn calls.  Each
+ * function names the reference code it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer on the current CUDA device unless marked "host";
+ *     tensors are dense, row-major, fp32 unless stated;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - the callee never allocates, frees or retains caller memory; outputs are caller-allocated;
+ *   - return value: 0 on success, non-zero on error; nsk_last_error() then returns a
+ *     thread-local, NUL-terminated description.  There is no CPU fallback.
+ *   - all entry points are re-entrant and keep no global mutable state (the nerfstudio viewer
+ *     thread may render while the trainer thread trains: neusky/models/neusky_model.py:1388-1403).
+ */
+#ifndef NEUSKY_B200_H
+#define NEUSKY_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NSK_ABI_VERSION 1
+
+int nsk_version(void);
+const char* nsk_last_error(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * K1  multiresolution hash-grid encode (nerfstudio HashEncoding.pytorch_fwd semantics)
+ * replaces tcnn.Encoding at neusky/fields/sdf_albedo_field.py:117-130 and
+ * neusky/fields/directional_distance_field.py:139-156.
+ *   x        [n,3]        positions (any range; negative coordinates are legal)
+ *   table    [L*T, 2]     T = 1<<log2_T, level-major
+ *   scalings [L]          per-level scale (floor(min_res*growth^l), computed by the host)
+ *   out      [n, 2L]      level-major features
+ * ------------------------------------------------------------------------------------------- */
+int nsk_hash_encode_fwd(const float* x, int64_t n, const float* table, const float* scalings,
+                        int num_levels, int log2_T, float* out, void* stream);
+
+/* d(table) += scatter of grad_out through the trilinear weights.  grad_table [L*T,2] must be
+ * zero-filled (or hold a running sum) by the caller. */
+int nsk_hash_encode_bwd(const float* x, int64_t n, const float* scalings, int num_levels, int log2_T,
+                        const float* grad_out, float* grad_table, void* stream);
+
+/* Integer part only, for bit-exact index parity tests: idx [n,L,8] int64 (including the l*T level
+ * offset, corner order of SURVEY A.3), offsets [n,L,3]. */
+int nsk_hash_indices(const float* x, int64_t n, const float* scalings, int num_levels, int log2_T,
+                     int64_t* idx, float* offsets, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K3  NeuS logistic-CDF alpha + transmittance + compositing, one warp per ray.
+ * replaces SDFField.get_alpha (called neusky/fields/sdf_albedo_field.py:266),
+ * RaySamples.get_weights_and_transmittance_from_alphas (neusky/models/neusky_model.py:565) and the
+ * depth / accumulation / normal / albedo renderers (neusky_model.py:591-595, 806-813).
+ *   sdf [R,S], grad [R,S,3], albedo [R,S,3], ray_dirs [R,3], starts/ends/deltas [R,S], dnorm [R]
+ *   outputs: weights [R,S], wa [R,S,3] = weights*albedo, normals [R,S,3] = normalize(grad),
+ *            acc [R], p2p_raw [R] (unclipped expected distance), normal_out [R,3],
+ *            albedo_out [R,3] (white background, clamped to [0,1] unless training), bg_T [R],
+ *            steps_minmax [2] (global min / max of (start+end)/2; caller pre-fills {+inf,-inf})
+ * nsk_neus_finalize_depth clips p2p to the batch-global [min,max] (nerfstudio DepthRenderer) and
+ * divides by directions_norm:  p2p [R], depth [R].
+ * ------------------------------------------------------------------------------------------- */
+int nsk_neus_composite_fwd(const float* sdf, const float* grad, const float* albedo, const float* ray_dirs,
+                           const float* starts, const float* ends, const float* deltas,
+                           int64_t R, int S, float inv_s, float cos_anneal_ratio, int training,
+                           float* weights, float* wa, float* normals, float* acc, float* p2p_raw,
+                           float* normal_out, float* albedo_out, float* bg_T, float* steps_minmax, void* stream);
+int nsk_neus_finalize_depth(const float* p2p_raw, const float* dnorm, const float* steps_minmax, int64_t R,
+                            float* p2p, float* depth, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * RENI++ radiance table: HDR radiance of K latent codes in D directions.
+ * replaces RENIField.get_outputs + unnormalise as driven by NeuSkyFactoModel.sample_illumination
+ * (ns_reni/reni/illumination_fields/reni_illumination_field.py:493-573, base_spherical_field.py:143-154,
+ *  ns_reni/reni/field_components/transformer_decoder.py:21-155, vn_layers.py:191-246,404-419;
+ *  neusky/models/neusky_model.py:445-551).
+ *   dirs [D,3], latents [K,Ld,3], scale [K] (NULL = no scale), rotation [3,3] (NULL = none; applied
+ *   to the latent, Z@R), weights = packed fp32 blob (layout: nsk_reni_weights_floats / python
+ *   neusky_b200.packing.pack_reni), workspace [K*6*H] floats, out [K,D,3] = exp(log-HDR) when log_domain.
+ * ------------------------------------------------------------------------------------------- */
+int64_t nsk_reni_weights_floats(int latent_dim, int hidden, int num_layers);
+int nsk_reni_decode_fwd(const float* dirs, int64_t D, const float* latents, const float* scale, int64_t K,
+                        const float* rotation, const float* weights, int latent_dim, int hidden, int num_layers,
+                        int log_domain, float* workspace, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Lambertian pre-pass and finalisation.
+ * replaces the count / un-occluded part of RGBLambertianRendererWithVisibility.render_and_combine_rgb
+ * (neusky/model_components/renderers.py:93-113) and its background blend + sRGB (:122-128, :173-174).
+ *   normals [R,S,3], wa [R,S,3] (= weight*albedo), dirs [D,3], ddf_mask [D] (uint8: 1 = this
+ *   direction is shaded through the DDF by nsk_sky_shade_*, 0 = visibility is the constant
+ *   `unoccluded_vis`), radiance [K,D,3], cam [R] int32 row of the radiance table (NULL = row 0).
+ *   outputs: inv_count [R,S] = 1/max(1,#{j: n.l_j>0}); rgb_lin [R,3] = sum over samples and over
+ *   un-masked directions of wa * clamp(n.l) * inv_count * unoccluded_vis * radiance (OVERWRITTEN).
+ * nsk_shade_finalize: rgb = clamp(sRGB(rgb_lin + bg*(1-acc))) (no final clamp when training).
+ * ------------------------------------------------------------------------------------------- */
+int nsk_lambert_prep(const float* normals, const float* wa, int64_t R, int S, const float* dirs,
+                     const uint8_t* ddf_mask, int D, const float* radiance, const int32_t* cam,
+                     float unoccluded_vis, float* inv_count, float* rgb_lin, void* stream);
+int nsk_shade_finalize(const float* rgb_lin, const float* bg, const float* acc, int64_t R, int training,
+                       float* rgb, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K4  outside-in sky visibility + cosine-weighted Lambertian sum, fused.
+ * replaces NeuSkyFactoModel.compute_visibility (neusky/models/neusky_model.py:1624-1778),
+ * DDFModel.get_outputs (neusky/models/ddf_model.py:158-219), DirectionalDistanceField.get_outputs
+ * (neusky/fields/directional_distance_field.py:261-306), FiLMSiren (ns_reni/reni/field_components/
+ * film_siren.py:45-156) and the visibility-weighted part of the Lambertian renderer
+ * (neusky/model_components/renderers.py:93-113) for every (ray, direction) pair.
+ *   points   [R,3]     surface points (already pulled inside the sphere, neusky_model.py:1667-1683)
+ *   normals  [R,S,3], wa [R,S,3], inv_count [R,S]   per-sample shading inputs (from K3 / lambert_prep)
+ *   dirs     [Dp,3]    the directions with ddf_mask==1, radiance [K,Dp,3] their HDR radiance
+ *   cam      [R] int32 radiance row per ray (NULL = row 0)
+ *   rgb_lin  [R,3]     ACCUMULATED INTO (atomics): += sum_s wa*clamp(n.l)*inv_count*vis*radiance
+ *   vis_out  [R,Dp]    optional (NULL to skip): the visibility tensor; never written when NULL
+ *   ddf_out  [R*Dp]    optional: expected termination distance; term_out [R*Dp] optional: |p-q|
+ * nsk_sky_shade_simt_fwd : exact fp32 CUDA-core path.   ddf_weights = nsk pack "simt" blob (fp32).
+ * nsk_sky_shade_tc_fwd   : tcgen05/TMEM tensor-core path, fp16 operands, fp32 accumulate.
+ *                          ddf_weights = nsk pack "tc" blob (pre-tiled fp16 operand images + fp32 biases).
+ * ------------------------------------------------------------------------------------------- */
+int nsk_sky_shade_simt_fwd(const float* points, int64_t R, const float* normals, const float* wa,
+                           const float* inv_count, int S, const float* dirs, int Dp, const float* radiance,
+                           const int32_t* cam, const float* ddf_weights, const float* hash_table,
+                           const float* scalings, int num_levels, int log2_T, float radius, float threshold,
+                           float sigmoid_scale, float* rgb_lin, float* vis_out, float* ddf_out, float* term_out,
+                           void* stream);
+int nsk_sky_shade_tc_fwd(const float* points, int64_t R, const float* normals, const float* wa,
+                         const float* inv_count, int S, const float* dirs, int Dp, const float* radiance,
+                         const int32_t* cam, const void* ddf_weights, const float* hash_table,
+                         const float* scalings, int num_levels, int log2_T, float radius, float threshold,
+                         float sigmoid_scale, float* rgb_lin, float* vis_out, float* ddf_out, float* term_out,
+                         void* stream);
+int64_t nsk_ddf_simt_weights_floats(void);
+int64_t nsk_ddf_tc_weights_bytes(void);
+
+/* Surface points for visibility incl. the outside-sphere replacement (neusky_model.py:1667-1683):
+ * origins [R,3], ray_dirs [R,3], p2p [R] -> points [R,3]. */
+int nsk_surface_points(const float* origins, const float* ray_dirs, const float* p2p, int64_t R, float radius,
+                       float* points, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NEUSKY_B200_H */

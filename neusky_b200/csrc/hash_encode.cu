@@ -1,0 +1,137 @@
+// K1: multiresolution hash-grid encode, forward / backward / index dump.
+// Semantics: nerfstudio HashEncoding.pytorch_fwd [NS-mem, SURVEY A.3] -- the substitution for
+// tcnn.Encoding at neusky/fields/sdf_albedo_field.py:117-130 and
+// neusky/fields/directional_distance_field.py:139-156.
+//
+// Layout / mapping: a warp owns 32 consecutive points (lane = point) and walks the levels, so all
+// 32 lanes gather from the same level's table slice at once (coarse levels stay L1/L2 resident).
+// Each lane issues the 8 corner gathers of a level as independent 8-byte loads (two levels in
+// flight = 16 outstanding loads per lane).  Results are staged in shared memory and written back
+// as one contiguous 4 KB run per warp (32 points x 128 B) with 16-byte stores.
+// HBM-bound roofline: 12 B in + 16*8*8 B gathers + 128 B out = 1164 B per point.
+#include "nsk_common.cuh"
+
+namespace nsk {
+
+constexpr int HE_WARPS = 8;
+constexpr int HE_MAX_LEVELS = 16;
+
+__global__ void __launch_bounds__(HE_WARPS * 32)
+hash_encode_fwd_kernel(const float* __restrict__ x, int64_t n, const float2* __restrict__ table,
+                       const float* __restrict__ scalings, int L, int log2_T, float* __restrict__ out) {
+  __shared__ float s_scale[HE_MAX_LEVELS];
+  __shared__ __align__(16) float stage[HE_WARPS][32][2 * HE_MAX_LEVELS + 1];  // +1: conflict-free column reads
+  if (threadIdx.x < L) s_scale[threadIdx.x] = scalings[threadIdx.x];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t mask = (1u << log2_T) - 1u;
+  const int64_t warps_total = (int64_t)gridDim.x * HE_WARPS;
+  const int F = 2 * L;
+  for (int64_t base = ((int64_t)blockIdx.x * HE_WARPS + warp) * 32; base < n; base += warps_total * 32) {
+    const int64_t p = base + lane;
+    float px = 0.f, py = 0.f, pz = 0.f;
+    if (p < n) { px = x[p * 3 + 0]; py = x[p * 3 + 1]; pz = x[p * 3 + 2]; }
+    for (int l = 0; l < L; l += 2) {
+      float2 f[2][8];
+      float ox[2], oy[2], oz[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int lev = min(l + u, L - 1);
+        const float s = s_scale[lev];
+        uint32_t idx[8];
+        hash_corners(__fmul_rn(px, s), __fmul_rn(py, s), __fmul_rn(pz, s), mask, idx, ox[u], oy[u], oz[u]);
+        const float2* tl = table + ((size_t)lev << log2_T);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) f[u][c] = __ldg(tl + idx[c]);
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (l + u < L) {
+          const float2 r = hash_interp(f[u], ox[u], oy[u], oz[u]);
+          stage[warp][lane][2 * (l + u) + 0] = r.x;
+          stage[warp][lane][2 * (l + u) + 1] = r.y;
+        }
+      }
+    }
+    __syncwarp();
+    // coalesced write-back: the warp's 32 x F floats are contiguous in `out`
+    const int64_t valid = min((int64_t)32, n - base);
+    float* dst = out + base * F;
+    for (int i = lane; i < (int)valid * F; i += 32) dst[i] = stage[warp][i / F][i % F];
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(256)
+hash_encode_bwd_kernel(const float* __restrict__ x, int64_t n, const float* __restrict__ scalings, int L,
+                       int log2_T, const float* __restrict__ grad_out, float* __restrict__ grad_table) {
+  // one thread per (point, level); d out / d table[corner] = trilinear weight of that corner
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lev = blockIdx.y;
+  if (i >= n) return;
+  const uint32_t mask = (1u << log2_T) - 1u;
+  const float s = scalings[lev];
+  uint32_t idx[8];
+  float ox, oy, oz;
+  hash_corners(__fmul_rn(x[i * 3], s), __fmul_rn(x[i * 3 + 1], s), __fmul_rn(x[i * 3 + 2], s), mask, idx, ox, oy, oz);
+  const float gx = grad_out[i * 2 * L + 2 * lev], gy = grad_out[i * 2 * L + 2 * lev + 1];
+  const float wx[2] = {ox, 1.f - ox}, wy[2] = {oy, 1.f - oy}, wz[2] = {oz, 1.f - oz};
+  // corner c uses (x: c or f, y: c or f, z: c or f) -> weight index 0 for "c" (offset), 1 for "f"
+  const int ux[8] = {0, 0, 1, 1, 0, 0, 1, 1}, uy[8] = {0, 1, 1, 0, 0, 1, 1, 0}, uz[8] = {0, 0, 0, 0, 1, 1, 1, 1};
+  float2* tl = reinterpret_cast<float2*>(grad_table) + ((size_t)lev << log2_T);
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const float w = wx[ux[c]] * wy[uy[c]] * wz[uz[c]];
+    atomicAdd(tl + idx[c], make_float2(w * gx, w * gy));
+  }
+}
+
+__global__ void hash_indices_kernel(const float* __restrict__ x, int64_t n, const float* __restrict__ scalings, int L,
+                                    int log2_T, int64_t* __restrict__ idx_out, float* __restrict__ off_out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * L) return;
+  const int64_t p = i / L;
+  const int lev = (int)(i % L);
+  const uint32_t mask = (1u << log2_T) - 1u;
+  const float s = scalings[lev];
+  uint32_t idx[8];
+  float ox, oy, oz;
+  hash_corners(__fmul_rn(x[p * 3], s), __fmul_rn(x[p * 3 + 1], s), __fmul_rn(x[p * 3 + 2], s), mask, idx, ox, oy, oz);
+  for (int c = 0; c < 8; ++c) idx_out[i * 8 + c] = (int64_t)idx[c] + ((int64_t)lev << log2_T);
+  off_out[i * 3 + 0] = ox; off_out[i * 3 + 1] = oy; off_out[i * 3 + 2] = oz;
+}
+
+}  // namespace nsk
+
+extern "C" int nsk_hash_encode_fwd(const float* x, int64_t n, const float* table, const float* scalings,
+                                   int num_levels, int log2_T, float* out, void* stream) {
+  NSK_REQUIRE(num_levels >= 1 && num_levels <= nsk::HE_MAX_LEVELS, "nsk_hash_encode_fwd: num_levels out of range");
+  NSK_REQUIRE(log2_T >= 1 && log2_T <= 28, "nsk_hash_encode_fwd: log2_T out of range");
+  if (n == 0) return 0;
+  NSK_REQUIRE(x && table && scalings && out, "nsk_hash_encode_fwd: null pointer");
+  int64_t blocks = (n + nsk::HE_WARPS * 32 - 1) / (nsk::HE_WARPS * 32);
+  const int64_t cap = 148 * 8 * 4;  // multiple of the SM count; grid-stride beyond that
+  if (blocks > cap) blocks = cap;
+  nsk::hash_encode_fwd_kernel<<<(unsigned)blocks, nsk::HE_WARPS * 32, 0, nsk::as_stream(stream)>>>(
+      x, n, reinterpret_cast<const float2*>(table), scalings, num_levels, log2_T, out);
+  return nsk::check_launch("hash_encode_fwd_kernel");
+}
+
+extern "C" int nsk_hash_encode_bwd(const float* x, int64_t n, const float* scalings, int num_levels, int log2_T,
+                                   const float* grad_out, float* grad_table, void* stream) {
+  NSK_REQUIRE(num_levels >= 1 && num_levels <= nsk::HE_MAX_LEVELS, "nsk_hash_encode_bwd: num_levels out of range");
+  if (n == 0) return 0;
+  NSK_REQUIRE(x && scalings && grad_out && grad_table, "nsk_hash_encode_bwd: null pointer");
+  dim3 grid((unsigned)((n + 255) / 256), num_levels);
+  nsk::hash_encode_bwd_kernel<<<grid, 256, 0, nsk::as_stream(stream)>>>(x, n, scalings, num_levels, log2_T, grad_out, grad_table);
+  return nsk::check_launch("hash_encode_bwd_kernel");
+}
+
+extern "C" int nsk_hash_indices(const float* x, int64_t n, const float* scalings, int num_levels, int log2_T,
+                                int64_t* idx, float* offsets, void* stream) {
+  if (n == 0) return 0;
+  NSK_REQUIRE(x && scalings && idx && offsets, "nsk_hash_indices: null pointer");
+  const int64_t total = n * num_levels;
+  nsk::hash_indices_kernel<<<(unsigned)((total + 255) / 256), 256, 0, nsk::as_stream(stream)>>>(x, n, scalings, num_levels, log2_T, idx, offsets);
+  return nsk::check_launch("hash_indices_kernel");
+}

@@ -1,0 +1,190 @@
+"""Thin, validated Python wrappers over the C ABI (include/neusky_b200.h).
+
+Every op takes CUDA fp32 contiguous tensors, allocates its outputs with torch's caching
+allocator, launches on torch's current stream and raises ``ValueError`` / ``RuntimeError`` on
+misuse -- there is no CPU path and no silent fallback (north_star).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _lib
+
+Tensor = torch.Tensor
+c_void_p, c_int, c_int64, c_float = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float
+
+
+def _ptr(t: Optional[Tensor]):
+    return c_void_p(0 if t is None else t.data_ptr())
+
+
+def _stream(t: Tensor):
+    return c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _chk(name: str, t: Tensor, dtype=torch.float32, shape: Optional[Tuple] = None) -> Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise ValueError(f"{name}: expected a tensor")
+    if not t.is_cuda:
+        raise ValueError(f"{name}: must be a CUDA tensor (neusky_b200 has no CPU path)")
+    if t.dtype != dtype:
+        raise ValueError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if shape is not None:
+        if t.dim() != len(shape) or any(s is not None and s != d for s, d in zip(shape, t.shape)):
+            raise ValueError(f"{name}: expected shape {shape}, got {tuple(t.shape)}")
+    return t.contiguous()
+
+
+# ------------------------------------------------------------------------------------------- K1
+def hash_encode(x: Tensor, table: Tensor, scalings: Tensor, log2_T: int) -> Tensor:
+    """x [...,3] -> [..., 2L]; nerfstudio torch hash-grid semantics."""
+    lead = x.shape[:-1]
+    x2 = _chk("x", x.reshape(-1, 3), shape=(None, 3))
+    L = scalings.numel()
+    table = _chk("table", table, shape=(L << log2_T, 2))
+    scalings = _chk("scalings", scalings)
+    out = torch.empty((x2.shape[0], 2 * L), device=x.device, dtype=torch.float32)
+    lib = _lib.load()
+    _lib.check(lib.nsk_hash_encode_fwd(_ptr(x2), c_int64(x2.shape[0]), _ptr(table), _ptr(scalings), c_int(L), c_int(log2_T), _ptr(out), _stream(x)), "nsk_hash_encode_fwd")
+    return out.reshape(*lead, 2 * L)
+
+
+def hash_encode_bwd(x: Tensor, scalings: Tensor, log2_T: int, grad_out: Tensor, grad_table: Optional[Tensor] = None) -> Tensor:
+    x2 = _chk("x", x.reshape(-1, 3), shape=(None, 3))
+    L = scalings.numel()
+    g = _chk("grad_out", grad_out.reshape(-1, 2 * L), shape=(x2.shape[0], 2 * L))
+    if grad_table is None:
+        grad_table = torch.zeros((L << log2_T, 2), device=x.device, dtype=torch.float32)
+    grad_table = _chk("grad_table", grad_table, shape=(L << log2_T, 2))
+    lib = _lib.load()
+    _lib.check(lib.nsk_hash_encode_bwd(_ptr(x2), c_int64(x2.shape[0]), _ptr(_chk("scalings", scalings)), c_int(L), c_int(log2_T), _ptr(g), _ptr(grad_table), _stream(x)), "nsk_hash_encode_bwd")
+    return grad_table
+
+
+def hash_indices(x: Tensor, scalings: Tensor, log2_T: int) -> Tuple[Tensor, Tensor]:
+    x2 = _chk("x", x.reshape(-1, 3), shape=(None, 3))
+    L = scalings.numel()
+    idx = torch.empty((x2.shape[0], L, 8), device=x.device, dtype=torch.int64)
+    off = torch.empty((x2.shape[0], L, 3), device=x.device, dtype=torch.float32)
+    lib = _lib.load()
+    _lib.check(lib.nsk_hash_indices(_ptr(x2), c_int64(x2.shape[0]), _ptr(_chk("scalings", scalings)), c_int(L), c_int(log2_T), _ptr(idx), _ptr(off), _stream(x)), "nsk_hash_indices")
+    return idx, off
+
+
+# ------------------------------------------------------------------------------------------- K3
+def neus_composite(sdf, grad, albedo, ray_dirs, starts, ends, deltas, dnorm, inv_s: float, cos_anneal_ratio: float = 1.0, training: bool = False) -> Dict[str, Tensor]:
+    """sdf/starts/ends/deltas [R,S(,1)], grad/albedo [R,S,3], ray_dirs [R,3], dnorm [R(,1)]."""
+    R, S = sdf.shape[0], sdf.shape[1]
+    dev = sdf.device
+    sdf = _chk("sdf", sdf.reshape(R, S))
+    grad = _chk("grad", grad, shape=(R, S, 3))
+    albedo = _chk("albedo", albedo, shape=(R, S, 3))
+    ray_dirs = _chk("ray_dirs", ray_dirs, shape=(R, 3))
+    starts, ends, deltas = (_chk(n, t.reshape(R, S)) for n, t in (("starts", starts), ("ends", ends), ("deltas", deltas)))
+    dnorm = _chk("dnorm", dnorm.reshape(R))
+    f = dict(device=dev, dtype=torch.float32)
+    out = {
+        "weights": torch.empty((R, S), **f), "wa": torch.empty((R, S, 3), **f), "normals": torch.empty((R, S, 3), **f),
+        "accumulation": torch.empty((R,), **f), "p2p_raw": torch.empty((R,), **f), "normal": torch.empty((R, 3), **f),
+        "albedo": torch.empty((R, 3), **f), "bg_transmittance": torch.empty((R,), **f),
+        "p2p_dist": torch.empty((R,), **f), "depth": torch.empty((R,), **f),
+    }
+    mm = torch.tensor([float("inf"), float("-inf")], **f)
+    lib = _lib.load()
+    st = _stream(sdf)
+    _lib.check(lib.nsk_neus_composite_fwd(_ptr(sdf), _ptr(grad), _ptr(albedo), _ptr(ray_dirs), _ptr(starts), _ptr(ends), _ptr(deltas), c_int64(R), c_int(S), c_float(inv_s), c_float(cos_anneal_ratio), c_int(int(training)), _ptr(out["weights"]), _ptr(out["wa"]), _ptr(out["normals"]), _ptr(out["accumulation"]), _ptr(out["p2p_raw"]), _ptr(out["normal"]), _ptr(out["albedo"]), _ptr(out["bg_transmittance"]), _ptr(mm), st), "nsk_neus_composite_fwd")
+    _lib.check(lib.nsk_neus_finalize_depth(_ptr(out["p2p_raw"]), _ptr(dnorm), _ptr(mm), c_int64(R), _ptr(out["p2p_dist"]), _ptr(out["depth"]), st), "nsk_neus_finalize_depth")
+    out["steps_minmax"] = mm
+    return out
+
+
+def surface_points(origins: Tensor, ray_dirs: Tensor, p2p: Tensor, radius: float) -> Tensor:
+    R = origins.shape[0]
+    origins, ray_dirs = _chk("origins", origins, shape=(R, 3)), _chk("ray_dirs", ray_dirs, shape=(R, 3))
+    p2p = _chk("p2p", p2p.reshape(R))
+    out = torch.empty((R, 3), device=origins.device, dtype=torch.float32)
+    _lib.check(_lib.load().nsk_surface_points(_ptr(origins), _ptr(ray_dirs), _ptr(p2p), c_int64(R), c_float(radius), _ptr(out), _stream(origins)), "nsk_surface_points")
+    return out
+
+
+# ------------------------------------------------------------------------------------------- RENI++
+def reni_radiance_table(dirs: Tensor, latents: Tensor, scale: Optional[Tensor], packed: Tensor, rotation: Optional[Tensor] = None, hidden: int = 128, num_layers: int = 6, log_domain: bool = True) -> Tensor:
+    """dirs [D,3], latents [K,L,3], scale [K] -> HDR radiance [K,D,3]."""
+    D = dirs.shape[0]
+    K, L = latents.shape[0], latents.shape[1]
+    dirs = _chk("dirs", dirs, shape=(D, 3))
+    latents = _chk("latents", latents, shape=(K, L, 3))
+    if scale is not None:
+        scale = _chk("scale", scale, shape=(K,))
+    if rotation is not None:
+        if rotation.dim() == 3:
+            raise NotImplementedError("Batched rotation not implemented yet")  # reni_illumination_field.py:520-521
+        rotation = _chk("rotation", rotation, shape=(3, 3))
+    lib = _lib.load()
+    need = lib.nsk_reni_weights_floats(c_int(L), c_int(hidden), c_int(num_layers))
+    packed = _chk("packed", packed, shape=(need,))
+    ws = torch.empty((K * num_layers * hidden + K * L * 2,), device=dirs.device, dtype=torch.float32)
+    out = torch.empty((K, D, 3), device=dirs.device, dtype=torch.float32)
+    _lib.check(lib.nsk_reni_decode_fwd(_ptr(dirs), c_int64(D), _ptr(latents), _ptr(scale), c_int64(K), _ptr(rotation), _ptr(packed), c_int(L), c_int(hidden), c_int(num_layers), c_int(int(log_domain)), _ptr(ws), _ptr(out), _stream(dirs)), "nsk_reni_decode_fwd")
+    return out
+
+
+# ------------------------------------------------------------------------------------------- Lambert / K4
+def lambert_prep(normals, wa, dirs, ddf_mask, radiance, cam=None, unoccluded_vis: float = 1.0):
+    R, S = normals.shape[0], normals.shape[1]
+    D = dirs.shape[0]
+    normals, wa = _chk("normals", normals, shape=(R, S, 3)), _chk("wa", wa, shape=(R, S, 3))
+    dirs = _chk("dirs", dirs, shape=(D, 3))
+    ddf_mask = _chk("ddf_mask", ddf_mask, dtype=torch.uint8, shape=(D,))
+    radiance = _chk("radiance", radiance, shape=(None, D, 3))
+    if cam is not None:
+        cam = _chk("cam", cam, dtype=torch.int32, shape=(R,))
+    inv_count = torch.empty((R, S), device=normals.device, dtype=torch.float32)
+    rgb_lin = torch.empty((R, 3), device=normals.device, dtype=torch.float32)
+    _lib.check(_lib.load().nsk_lambert_prep(_ptr(normals), _ptr(wa), c_int64(R), c_int(S), _ptr(dirs), _ptr(ddf_mask), c_int(D), _ptr(radiance), _ptr(cam), c_float(unoccluded_vis), _ptr(inv_count), _ptr(rgb_lin), _stream(normals)), "nsk_lambert_prep")
+    return inv_count, rgb_lin
+
+
+def shade_finalize(rgb_lin, bg, acc, training: bool = False) -> Tensor:
+    R = rgb_lin.shape[0]
+    rgb_lin, bg = _chk("rgb_lin", rgb_lin, shape=(R, 3)), _chk("bg", bg, shape=(R, 3))
+    acc = _chk("acc", acc.reshape(R))
+    out = torch.empty((R, 3), device=rgb_lin.device, dtype=torch.float32)
+    _lib.check(_lib.load().nsk_shade_finalize(_ptr(rgb_lin), _ptr(bg), _ptr(acc), c_int64(R), c_int(int(training)), _ptr(out), _stream(rgb_lin)), "nsk_shade_finalize")
+    return out
+
+
+def sky_shade(points, normals, wa, inv_count, dirs_sel, radiance_sel, ddf_blob, hash_table, scalings, log2_T: int, radius: float, threshold: float, sigmoid_scale: float, rgb_lin: Tensor, cam=None, want_vis: bool = False, want_ddf: bool = False, impl: str = "tc"):
+    """K4.  Accumulates into ``rgb_lin`` [R,3]; returns (vis [R,Dp] | None, ddf [R*Dp] | None, term | None)."""
+    R, S = normals.shape[0], normals.shape[1]
+    Dp = dirs_sel.shape[0]
+    points = _chk("points", points, shape=(R, 3))
+    normals, wa = _chk("normals", normals, shape=(R, S, 3)), _chk("wa", wa, shape=(R, S, 3))
+    inv_count = _chk("inv_count", inv_count, shape=(R, S))
+    dirs_sel = _chk("dirs_sel", dirs_sel, shape=(Dp, 3))
+    radiance_sel = _chk("radiance_sel", radiance_sel, shape=(None, Dp, 3))
+    if cam is not None:
+        cam = _chk("cam", cam, dtype=torch.int32, shape=(R,))
+    L = scalings.numel()
+    hash_table = _chk("hash_table", hash_table, shape=(L << log2_T, 2))
+    scalings = _chk("scalings", scalings)
+    if not (rgb_lin.is_cuda and rgb_lin.dtype == torch.float32 and rgb_lin.is_contiguous() and tuple(rgb_lin.shape) == (R, 3)):
+        raise ValueError("rgb_lin: expected a contiguous CUDA fp32 [R,3] accumulator")
+    dev = points.device
+    vis = torch.empty((R, Dp), device=dev, dtype=torch.float32) if want_vis else None
+    ddf = torch.empty((R * Dp,), device=dev, dtype=torch.float32) if want_ddf else None
+    term = torch.empty((R * Dp,), device=dev, dtype=torch.float32) if want_ddf else None
+    lib = _lib.load()
+    if impl == "simt":
+        blob = _chk("ddf_blob", ddf_blob, shape=(lib.nsk_ddf_simt_weights_floats(),))
+        fn, name = lib.nsk_sky_shade_simt_fwd, "nsk_sky_shade_simt_fwd"
+    elif impl == "tc":
+        blob = _chk("ddf_blob", ddf_blob, dtype=torch.uint8, shape=(lib.nsk_ddf_tc_weights_bytes(),))
+        fn, name = lib.nsk_sky_shade_tc_fwd, "nsk_sky_shade_tc_fwd"
+    else:
+        raise ValueError(f"impl must be 'tc' or 'simt', got {impl!r}")
+    _lib.check(fn(_ptr(points), c_int64(R), _ptr(normals), _ptr(wa), _ptr(inv_count), c_int(S), _ptr(dirs_sel), c_int(Dp), _ptr(radiance_sel), _ptr(cam), _ptr(blob), _ptr(hash_table), _ptr(scalings), c_int(L), c_int(log2_T), c_float(radius), c_float(threshold), c_float(sigmoid_scale), _ptr(rgb_lin), _ptr(vis), _ptr(ddf), _ptr(term), _stream(points)), name)
+    return vis, ddf, term

@@ -1,0 +1,76 @@
+"""Host-side orchestration of the shading hot path: RENI++ radiance table -> Lambert pre-pass ->
+fused DDF visibility + cosine-weighted sum (K4) -> background blend + sRGB.
+
+Mirrors what NeuSkyFactoModel.sample_illumination / compute_visibility / lambertian_renderer do
+between them (neusky/models/neusky_model.py:445-551, 1624-1778, 797-805) without materialising the
+[R*S, D, 3] direction / colour tensors or the [R*S, D] visibility tensor.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+
+from . import ops, packing
+from .init import hash_scalings
+
+Tensor = torch.Tensor
+
+
+class SkyShader:
+    """Holds device-resident packed weights for the DDF visibility field and the RENI++ decoder."""
+
+    def __init__(self, ddf_params: Dict[str, Tensor], reni_params: Optional[Dict[str, Tensor]], device="cuda", ddf_radius: float = 1.0,
+                 log2_T: int = 19, num_levels: int = 16, only_upper_hemisphere: bool = True, lower_hemisphere_visibility: float = 1.0,
+                 impl: str = "tc"):
+        self.device = torch.device(device)
+        self.radius = float(ddf_radius)
+        self.log2_T = log2_T
+        self.only_upper = only_upper_hemisphere
+        self.lower_vis = float(lower_hemisphere_visibility)
+        self.impl = impl
+        self.scalings = hash_scalings(num_levels).to(self.device)
+        self.hash_table = ddf_params["position_encoding.hash_table"].to(self.device, torch.float32).contiguous()
+        self.set_ddf_weights(ddf_params)
+        self.reni_blob = packing.pack_reni({k: v.to(self.device) for k, v in reni_params.items()}) if reni_params is not None else None
+
+    def set_ddf_weights(self, ddf_params: Dict[str, Tensor]) -> None:
+        p = {k: v.to(self.device) for k, v in ddf_params.items() if k.startswith("ddf.")}
+        self.ddf_blob_simt = packing.pack_ddf_simt(p)
+        self.ddf_blob_tc = packing.pack_ddf_tc(p) if hasattr(packing, "pack_ddf_tc") else None
+
+    # -- direction set -------------------------------------------------------------------------
+    def set_directions(self, dirs: Tensor) -> None:
+        """dirs [D,3] (unit).  Mask = upper hemisphere (neusky_model.py:1650-1657)."""
+        self.dirs = dirs.to(self.device, torch.float32).contiguous()
+        if self.only_upper:
+            m = self.dirs[:, 2] > 0
+        else:
+            m = torch.ones(self.dirs.shape[0], dtype=torch.bool, device=self.device)
+        self.mask = m
+        self.mask_u8 = m.to(torch.uint8).contiguous()
+        self.dirs_sel = self.dirs[m].contiguous()
+
+    def radiance_table(self, latents: Tensor, scale: Optional[Tensor], rotation: Optional[Tensor] = None) -> Tensor:
+        return ops.reni_radiance_table(self.dirs, latents, scale, self.reni_blob, rotation)
+
+    # -- shading ---------------------------------------------------------------------------------
+    def shade(self, points: Tensor, normals: Tensor, wa: Tensor, radiance: Tensor, cam: Optional[Tensor] = None,
+              want_vis: bool = False, want_ddf: bool = False, threshold: float = 0.1, sigmoid_scale: float = 25.0,
+              impl: Optional[str] = None) -> Dict[str, Tensor]:
+        """points [R,3]; normals, wa [R,S,3]; radiance [K,D,3] -> linear radiance sum [R,3]
+        (sum_s w_s * albedo_s * sum_j c_sj vis_rj L_j) and, on request, the per-pair tensors."""
+        impl = impl or self.impl
+        inv_count, rgb_lin = ops.lambert_prep(normals, wa, self.dirs, self.mask_u8, radiance, cam, self.lower_vis)
+        rad_sel = radiance[:, self.mask].contiguous()
+        blob = self.ddf_blob_tc if impl == "tc" else self.ddf_blob_simt
+        vis, ddf, term = ops.sky_shade(points, normals, wa, inv_count, self.dirs_sel, rad_sel, blob, self.hash_table, self.scalings,
+                                       self.log2_T, self.radius, threshold, sigmoid_scale, rgb_lin, cam, want_vis, want_ddf, impl)
+        out = {"rgb_lin": rgb_lin, "inv_count": inv_count}
+        if vis is not None:
+            full = torch.full((points.shape[0], self.dirs.shape[0]), self.lower_vis, device=self.device)
+            full[:, self.mask] = vis
+            out["visibility"] = full
+        if ddf is not None:
+            out["expected_termination_dist"], out["termination_dist"] = ddf, term
+        return out

@@ -1,0 +1,213 @@
+"""GPU parity tests: the CUDA path (through the C ABI) vs the CPU oracle and the golden fixtures
+generated from the reference's own code.  Run on the B200 box:  pytest -m gpu"""
+import numpy as np
+import pytest
+import torch
+
+from neusky_b200 import init as nb_init
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from neusky_b200 import _lib
+
+    _lib.load()  # fail loudly if the native library is missing
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import neusky_oracle
+
+    return neusky_oracle
+
+
+# ----------------------------------------------------------------------------------------- K1
+def _hash_points(n, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    x = (torch.rand(n, 3, generator=g) * 2.6 - 1.3).float()
+    # edge cases: exact grid integers (c == f, o == 0), zero, negatives, > 1, tiny values
+    edge = torch.tensor([[0.0, 0.0, 0.0], [1.0, 1.0, 1.0], [-1.0, 0.5, 0.25], [0.0625, -0.0625, 1.5], [1e-30, -1e-30, 3.0],
+                         [0.999999, -0.999999, 0.5], [2.0, -2.0, 0.125]])
+    return torch.cat([edge, x], 0)
+
+
+@pytest.mark.parametrize("log2_T,L", [(19, 16), (17, 5), (4, 3)])
+def test_hash_indices_bit_exact(dev, O, log2_T, L):
+    from neusky_b200 import ops
+
+    x = _hash_points(5000)
+    sc = O.hash_scalings(L, 16, 2048 if L == 16 else 64)
+    idx_ref, off_ref = O.hash_corner_indices(x, sc, log2_T)
+    idx, off = ops.hash_indices(x.to(dev), sc.to(dev), log2_T)
+    assert torch.equal(idx.cpu(), idx_ref), "hash indices must match bit-exactly"
+    assert torch.equal(off.cpu().view(torch.int32), off_ref.view(torch.int32)), "interpolation offsets must match bit-exactly"
+
+
+@pytest.mark.parametrize("n", [0, 1, 31, 33, 4097])
+def test_hash_encode_forward(dev, O, n):
+    from neusky_b200 import ops
+
+    log2_T, L = 19, 16
+    table = nb_init.init_hash_table(3, L, log2_T)
+    sc = O.hash_scalings(L)
+    x = _hash_points(n)[:n] if n else torch.zeros(0, 3)
+    ref = O.hash_encode(x, table, sc, log2_T)
+    out = ops.hash_encode(x.to(dev), table.to(dev), sc.to(dev), log2_T).cpu()
+    assert out.shape == ref.shape
+    assert torch.equal(out, ref), (out - ref).abs().max()  # same op order, no FMA contraction: bit-exact
+
+
+def test_hash_encode_backward(dev, O):
+    from neusky_b200 import ops
+
+    log2_T, L = 12, 16
+    table = nb_init.init_hash_table(4, L, log2_T).requires_grad_(True)
+    sc = O.hash_scalings(L)
+    x = _hash_points(3000)
+    g = torch.randn(x.shape[0], 2 * L, generator=torch.Generator().manual_seed(1))
+    O.hash_encode(x, table, sc, log2_T).backward(g)
+    got = ops.hash_encode_bwd(x.to(dev), sc.to(dev), log2_T, g.to(dev)).cpu()
+    assert torch.allclose(got, table.grad, rtol=1e-4, atol=1e-5), (got - table.grad).abs().max()
+
+
+def test_hash_rejects_cpu_tensor(dev, O):
+    from neusky_b200 import ops
+
+    with pytest.raises(ValueError):
+        ops.hash_encode(torch.zeros(4, 3), torch.zeros(16 << 4, 2), O.hash_scalings(16), 4)
+
+
+# ----------------------------------------------------------------------------------------- K3
+@pytest.mark.parametrize("R,S", [(1, 1), (7, 48), (33, 128), (5, 200)])
+def test_neus_composite(dev, O, R, S):
+    from neusky_b200 import ops
+
+    g = torch.Generator().manual_seed(R * 1000 + S)
+    t = torch.sort(torch.rand(R, S + 1, generator=g) * 2.0 + 0.05, dim=1).values
+    starts, ends = t[:, :-1, None].contiguous(), t[:, 1:, None].contiguous()
+    deltas = ends - starts
+    ray_dirs = torch.nn.functional.normalize(torch.randn(R, 3, generator=g), dim=-1)
+    sdf = (1.0 - (starts + ends) / 2) * 0.3 + 0.02 * torch.randn(R, S, 1, generator=g)
+    grad = -ray_dirs[:, None, :] * (0.7 + 0.6 * torch.rand(R, S, 1, generator=g)) + 0.3 * torch.randn(R, S, 3, generator=g)
+    albedo = torch.rand(R, S, 3, generator=g)
+    dnorm = 1.0 + torch.rand(R, 1, generator=g)
+    inv_s = float(np.exp(10 * 0.3))
+    radiance = torch.zeros(R, S, 3)
+    ref = O.neus_composite(sdf, grad, albedo, radiance, ray_dirs, starts, ends, deltas, torch.zeros(R, 3), dnorm, inv_s, 1.0, False)
+    out = ops.neus_composite(*(a.to(dev) for a in (sdf, grad, albedo, ray_dirs, starts, ends, deltas, dnorm)), inv_s, 1.0, False)
+    tol = dict(rtol=1e-4, atol=2e-6)
+    assert torch.allclose(out["weights"].cpu(), ref["weights"][..., 0], **tol)
+    assert torch.allclose(out["accumulation"].cpu(), ref["accumulation"][:, 0], **tol)
+    assert torch.allclose(out["bg_transmittance"].cpu(), ref["bg_transmittance"][:, 0], **tol)
+    assert torch.allclose(out["p2p_dist"].cpu(), ref["p2p_dist"][:, 0], **tol)
+    assert torch.allclose(out["depth"].cpu(), ref["depth"][:, 0], **tol)
+    assert torch.allclose(out["normal"].cpu(), ref["normal"], rtol=1e-4, atol=1e-5)
+    assert torch.allclose(out["albedo"].cpu(), ref["albedo"], rtol=1e-4, atol=1e-5)
+    assert torch.allclose(out["wa"].cpu(), ref["weights"] * albedo, rtol=1e-4, atol=1e-6)
+    assert float(ref["accumulation"].max()) > 0.5  # the case actually renders a surface
+
+
+def test_surface_points_hack_branch(dev, O, golden):
+    from neusky_b200 import ops
+
+    g = golden("visibility")
+    o, d, p2p = (torch.from_numpy(g[k]) for k in ("origins", "ray_dirs", "p2p"))
+    ref = O.surface_points(o, d, p2p, 1.0)
+    out = ops.surface_points(o.to(dev), d.to(dev), p2p.to(dev), 1.0).cpu()
+    assert torch.allclose(out, ref, rtol=1e-5, atol=1e-6)
+
+
+# ----------------------------------------------------------------------------------------- RENI++
+def test_reni_radiance_table(dev, O, golden):
+    from neusky_b200 import ops, packing
+
+    g = golden("reni")
+    p = nb_init.init_reni_params(int(g["seed"]))
+    blob = packing.pack_reni({k: v.to(dev) for k, v in p.items()})
+    dirs, Z, sc, rot = (torch.from_numpy(g[k]).to(dev) for k in ("dirs", "latents", "scale", "rotation"))
+    rad = ops.reni_radiance_table(dirs, Z, sc, blob).cpu()
+    ref = torch.from_numpy(g["radiance"])
+    assert torch.allclose(rad, ref, rtol=1e-3, atol=1e-6), ((rad - ref).abs() / ref.abs()).max()
+    rad_r = ops.reni_radiance_table(dirs, Z, sc, blob, rotation=rot).cpu()
+    assert torch.allclose(rad_r, torch.from_numpy(g["radiance_rot"]), rtol=1e-3, atol=1e-6)
+    with pytest.raises(NotImplementedError):
+        ops.reni_radiance_table(dirs, Z, sc, blob, rotation=rot[None].expand(3, 3, 3))
+    # D not a multiple of the row tile, K = 1, no scale
+    rad1 = ops.reni_radiance_table(dirs[:13], Z[:1], None, blob).cpu()
+    ref1 = O.reni_radiance_table(dirs[:13].cpu(), Z[:1].cpu(), torch.zeros(1), p)
+    assert torch.allclose(rad1, ref1, rtol=1e-3, atol=1e-6)
+
+
+# ----------------------------------------------------------------------------------------- Lambert + K4 (exact path)
+def _shader(dev, g, impl):
+    from neusky_b200.render import SkyShader
+
+    p = nb_init.init_ddf_params(int(g["seed"]), final_gain=float(g["final_gain"]))
+    return SkyShader(p, None, device=dev, impl=impl), p
+
+
+def test_lambert_golden(dev, golden):
+    """lambert_prep (all directions un-occluded) + finalize == the reference renderer with vis=1."""
+    from neusky_b200 import ops
+    from oracle import neusky_oracle as O
+
+    g = golden("lambert")
+    t = {k: torch.from_numpy(g[k]) for k in g.files}
+    R, S, _ = t["albedo"].shape
+    D = t["dirs"].shape[0]
+    wa = (t["weights"] * t["albedo"]).to(dev)
+    ref = O.lambertian_render(t["albedo"], t["normals"], t["dirs"], t["light"], None, t["bg"], t["weights"], False)
+    cam = torch.arange(R, dtype=torch.int32, device=dev)
+    inv_count, rgb_lin = ops.lambert_prep(t["normals"].to(dev), wa, t["dirs"].to(dev), torch.zeros(D, dtype=torch.uint8, device=dev), t["light"].to(dev), cam, 1.0)
+    rgb = ops.shade_finalize(rgb_lin, t["bg"].to(dev), t["weights"].sum(1)[:, 0].to(dev)).cpu()
+    assert torch.allclose(rgb, ref, rtol=1e-4, atol=1e-5), (rgb - ref).abs().max()
+
+
+def test_visibility_simt_vs_reference_golden(dev, O, golden):
+    from neusky_b200 import ops
+
+    g = golden("visibility")
+    sh, p = _shader(dev, g, "simt")
+    o, d, p2p, dirs = (torch.from_numpy(g[k]).to(dev) for k in ("origins", "ray_dirs", "p2p", "dirs"))
+    pts = ops.surface_points(o, d, p2p, 1.0)
+    sh.set_directions(dirs)
+    R, D = pts.shape[0], dirs.shape[0]
+    normals = torch.nn.functional.normalize(torch.randn(R, 2, 3, generator=torch.Generator().manual_seed(3)), dim=-1).to(dev)
+    wa = torch.rand(R, 2, 3, generator=torch.Generator().manual_seed(4)).to(dev) * 0.5
+    radiance = torch.exp(torch.randn(1, D, 3, generator=torch.Generator().manual_seed(5))).to(dev)
+    out = sh.shade(pts, normals, wa, radiance, want_vis=True, want_ddf=True, threshold=float(g["threshold"]), sigmoid_scale=float(g["sigmoid_scale"]))
+    torch.cuda.synchronize()
+    ref_vis = torch.from_numpy(g["visibility"])
+    assert torch.allclose(out["termination_dist"].cpu(), torch.from_numpy(g["termination_dist"]), rtol=1e-5, atol=2e-6)
+    assert torch.allclose(out["expected_termination_dist"].cpu(), torch.from_numpy(g["expected_termination_dist"]), rtol=1e-4, atol=5e-5)
+    assert torch.allclose(out["visibility"].cpu(), ref_vis, rtol=0, atol=5e-4), (out["visibility"].cpu() - ref_vis).abs().max()
+    # fused Lambertian sum vs the oracle renderer fed with the REFERENCE visibility
+    N = R * 2
+    rad_ref = O.lambertian_radiance(torch.ones(N, 3), normals.cpu().reshape(N, 3), dirs.cpu(), radiance[0].cpu(), ref_vis[:, None].expand(R, 2, D).reshape(N, D))
+    ref_lin = (wa.cpu().reshape(N, 3) * rad_ref).reshape(R, 2, 3).sum(1)
+    assert torch.allclose(out["rgb_lin"].cpu(), ref_lin, rtol=1e-3, atol=1e-5), (out["rgb_lin"].cpu() - ref_lin).abs().max()
+
+
+@pytest.mark.parametrize("R,D", [(1, 1), (5, 37), (64, 162)])
+def test_shade_points_simt_vs_oracle(dev, O, R, D):
+    """Config-2 shape: one sample per point, weight 1, ragged pair counts (R*D' not a tile multiple)."""
+    from neusky_b200.render import SkyShader
+
+    p = nb_init.init_ddf_params(11, final_gain=8.0, log2_T=19)
+    g = torch.Generator().manual_seed(R * 100 + D)
+    pts = torch.nn.functional.normalize(torch.randn(R, 3, generator=g), dim=-1) * torch.rand(R, 1, generator=g) ** (1 / 3) * 0.95
+    normals = torch.nn.functional.normalize(torch.randn(R, 3, generator=g), dim=-1)
+    albedo = torch.rand(R, 3, generator=g)
+    dirs = torch.nn.functional.normalize(torch.randn(D, 3, generator=g), dim=-1)
+    radiance = torch.exp(torch.randn(D, 3, generator=g))
+    ref_rad, ref_v = O.shade_points(pts, normals, albedo, dirs, radiance, p, O.hash_scalings(), 19, 1.0, 0.1, 25.0)
+    sh = SkyShader(p, None, device=dev, impl="simt")
+    sh.set_directions(dirs)
+    out = sh.shade(pts.to(dev), normals[:, None].to(dev), albedo[:, None].to(dev), radiance[None].to(dev), want_vis=True)
+    assert torch.allclose(out["visibility"].cpu(), ref_v["visibility"], rtol=0, atol=5e-4)
+    assert torch.allclose(out["rgb_lin"].cpu(), ref_rad, rtol=1e-3, atol=1e-5), (out["rgb_lin"].cpu() - ref_rad).abs().max()

@@ -1,0 +1,326 @@
+// Stand-alone probes of the Blackwell primitives the tensor-core shading kernel is built from.
+// Each probe validates one mechanism against a CPU result and/or measures its throughput, so the
+// kernel design rests on measured facts (B200, sm_100a) rather than assumptions.
+//   build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -o tc_probe tools/tc_probe.cu
+//   run  : ./tc_probe <probe> [args]     (see main())
+#include <cuda_fp16.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+#include <math.h>
+
+#include "../neusky_b200/csrc/tc_util.cuh"
+
+using namespace nsk::tc;
+
+#define CK(x)                                                                          \
+  do {                                                                                 \
+    cudaError_t e_ = (x);                                                              \
+    if (e_ != cudaSuccess) {                                                           \
+      printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); \
+      exit(2);                                                                         \
+    }                                                                                  \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// probe 1/2: one tile D[128 x N] = A[128 x K] * B[N x K]^T, A from smem (SS) or TMEM (TS)
+// ------------------------------------------------------------------------------------------------
+template <bool A_IN_TMEM>
+__global__ void __launch_bounds__(128) mma_tile_kernel(const __half* __restrict__ A, const __half* __restrict__ B, float* __restrict__ D,
+                                                       int N, int K) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  uint8_t* sA = smem;                  // 128 x K fp16, canonical layout
+  uint8_t* sB = smem + 128 * K * 2;    // N x K fp16
+  const int t = threadIdx.x, warp = t >> 5;
+  for (int e = t; e < 128 * K; e += 128) {
+    const int r = e / K, k = e % K;
+    *reinterpret_cast<__half*>(sA + tile_off(128, r, k)) = A[e];
+  }
+  for (int e = t; e < N * K; e += 128) {
+    const int r = e / K, k = e % K;
+    *reinterpret_cast<__half*>(sB + tile_off(N, r, k)) = B[e];
+  }
+  if (t == 0) { mbar_init(smem_u32(&bar), 1); fence_barrier_init(); }
+  if (warp == 0) tmem_alloc<512>(smem_u32(&tmem_base_s));
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t acc = tmem;            // columns [0, N)
+  const uint32_t a_tm = tmem + 256;     // columns [256, 256 + K/2): A as packed fp16 pairs
+  if (A_IN_TMEM) {
+    // thread t owns row t (TMEM lane t): column c holds elements (2c, 2c+1)
+    for (int c0 = 0; c0 < K / 2; c0 += 8) {
+      uint32_t v[8];
+      for (int j = 0; j < 8; ++j) {
+        const __half2 h = __halves2half2(A[t * K + 2 * (c0 + j)], A[t * K + 2 * (c0 + j) + 1]);
+        v[j] = *reinterpret_cast<const uint32_t*>(&h);
+      }
+      tmem_st8(a_tm + ((uint32_t)(warp * 32) << 16) + c0, v);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
+  if (t == 0) {
+    const uint32_t idesc = make_idesc_f16(128, N);
+    for (int k0 = 0; k0 < K; k0 += 16) {
+      const uint64_t bd = make_smem_desc(smem_u32(sB) + (k0 / 8) * N * 16, N * 16, 128);
+      if (A_IN_TMEM) {
+        umma_ts(acc, a_tm + k0 / 2, bd, idesc, k0 > 0);
+      } else {
+        const uint64_t ad = make_smem_desc(smem_u32(sA) + (k0 / 8) * 128 * 16, 128 * 16, 128);
+        umma_ss(acc, ad, bd, idesc, k0 > 0);
+      }
+    }
+    umma_commit(smem_u32(&bar));
+  }
+  mbar_wait(smem_u32(&bar), 0);
+  tc_fence_after();
+  for (int c0 = 0; c0 < N; c0 += 32) {
+    uint32_t v[32];
+    tmem_ld32(acc + ((uint32_t)(warp * 32) << 16) + c0, v);
+    tmem_ld_wait();
+    for (int j = 0; j < 32; ++j)
+      if (c0 + j < N) D[(size_t)t * N + c0 + j] = __uint_as_float(v[j]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
+static int probe_mma(bool ts, int N, int K) {
+  std::vector<__half> hA(128 * K), hB((size_t)N * K);
+  std::vector<float> fA(128 * K), fB((size_t)N * K), ref((size_t)128 * N), got((size_t)128 * N);
+  srand(1234 + N + K);
+  for (size_t i = 0; i < hA.size(); ++i) { fA[i] = (float)((rand() % 9) - 4) / 4.0f; hA[i] = __float2half(fA[i]); }
+  for (size_t i = 0; i < hB.size(); ++i) { fB[i] = (float)((rand() % 9) - 4) / 8.0f; hB[i] = __float2half(fB[i]); }
+  for (int m = 0; m < 128; ++m)
+    for (int n = 0; n < N; ++n) {
+      float s = 0;
+      for (int k = 0; k < K; ++k) s += fA[m * K + k] * fB[(size_t)n * K + k];
+      ref[(size_t)m * N + n] = s;
+    }
+  __half *dA, *dB; float* dD;
+  CK(cudaMalloc(&dA, hA.size() * 2)); CK(cudaMalloc(&dB, hB.size() * 2)); CK(cudaMalloc(&dD, got.size() * 4));
+  CK(cudaMemcpy(dA, hA.data(), hA.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dB, hB.data(), hB.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemset(dD, 0xff, got.size() * 4));
+  const size_t smem = (size_t)(128 + N) * K * 2 + 1024;
+  if (ts) {
+    CK(cudaFuncSetAttribute(mma_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    mma_tile_kernel<true><<<1, 128, smem>>>(dA, dB, dD, N, K);
+  } else {
+    CK(cudaFuncSetAttribute(mma_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    mma_tile_kernel<false><<<1, 128, smem>>>(dA, dB, dD, N, K);
+  }
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(got.data(), dD, got.size() * 4, cudaMemcpyDeviceToHost));
+  double maxerr = 0; int bad = 0;
+  for (size_t i = 0; i < got.size(); ++i) {
+    const double e = fabs((double)got[i] - ref[i]);
+    if (!(e <= 1e-5)) { if (bad < 5) printf("  mismatch at m=%zu n=%zu got %f ref %f\n", i / N, i % N, got[i], ref[i]); ++bad; }
+    if (e > maxerr) maxerr = e;
+  }
+  printf("probe mma_%s N=%d K=%d : %s (max err %.3g, %d bad)\n", ts ? "ts" : "ss", N, K, bad ? "FAIL" : "PASS", maxerr, bad);
+  return bad != 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// probe 3: MMA issue throughput on every SM (cycles per 128xNx16 MMA), SS vs TS, with or without
+// concurrent shared-memory traffic from 4 "epilogue" warps.
+// ------------------------------------------------------------------------------------------------
+template <bool A_IN_TMEM>
+__global__ void __launch_bounds__(256) mma_rate_kernel(int N, int iters, int smem_noise, long long* __restrict__ cycles, float* sink) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int t = threadIdx.x, warp = t >> 5;
+  // operands: A 128x256, B 256x256 (zeros are fine for timing)
+  for (int e = t; e < (128 + 256) * 256 * 2 / 16; e += blockDim.x) reinterpret_cast<uint4*>(smem)[e] = make_uint4(0, 0, 0, 0);
+  if (t == 0) { mbar_init(smem_u32(&bar), 1); fence_barrier_init(); }
+  if (warp == 0) tmem_alloc<512>(smem_u32(&tmem_base_s));
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t sA = smem_u32(smem), sB = smem_u32(smem) + 128 * 256 * 2;
+  if (t == 0) {
+    const uint32_t idesc = make_idesc_f16(128, N);
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+      const int k0 = (i & 15) * 16;
+      const uint64_t bd = make_smem_desc(sB + (k0 / 8) * N * 16, N * 16, 128);
+      if (A_IN_TMEM) umma_ts(tmem, tmem + 256 + k0 / 2, bd, idesc, 1);
+      else umma_ss(tmem, make_smem_desc(sA + (k0 / 8) * 128 * 16, 128 * 16, 128), bd, idesc, 1);
+    }
+    umma_commit(smem_u32(&bar));
+    mbar_wait(smem_u32(&bar), 0);
+    cycles[blockIdx.x] = clock64() - t0;
+  } else if (warp >= 4 && smem_noise) {
+    // emulate epilogue traffic: 16-byte stores + loads on a scratch region while the MMAs run
+    uint8_t* scratch = smem + (128 + 256) * 256 * 2;
+    float acc = 0.f;
+    const int lt = t - 128;
+    for (int i = 0; i < iters * smem_noise; ++i) {
+      uint4* p = reinterpret_cast<uint4*>(scratch) + ((i * 128 + lt) & 1023);
+      *p = make_uint4(i, t, 0, 0);
+      acc += (float)p->x;
+    }
+    if (acc == 12345.f) *sink = acc;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
+static void probe_rate(bool ts, int N, int noise) {
+  const int iters = 4096, grid = 148;
+  long long* d; float* sink;
+  CK(cudaMalloc(&d, grid * sizeof(long long))); CK(cudaMalloc(&sink, 4));
+  const size_t smem = (size_t)(128 + 256) * 256 * 2 + 16384 + 1024;
+  auto k = ts ? mma_rate_kernel<true> : mma_rate_kernel<false>;
+  CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  for (int rep = 0; rep < 2; ++rep) k<<<grid, 256, smem>>>(N, iters, noise, d, sink);
+  CK(cudaDeviceSynchronize());
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaEventRecord(e0);
+  k<<<grid, 256, smem>>>(N, iters, noise, d, sink);
+  cudaEventRecord(e1);
+  CK(cudaDeviceSynchronize());
+  float ms; cudaEventElapsedTime(&ms, e0, e1);
+  std::vector<long long> h(grid);
+  CK(cudaMemcpy(h.data(), d, grid * sizeof(long long), cudaMemcpyDeviceToHost));
+  double mean = 0; for (auto v : h) mean += (double)v; mean /= grid;
+  const double flops = 2.0 * 128 * N * 16 * (double)iters * grid;
+  printf("probe rate_%s N=%d noise=%d : %.1f cycles/MMA (ideal %d), kernel %.3f ms -> %.0f TFLOP/s\n", ts ? "ts" : "ss", N, noise,
+         mean / iters, N / 2, ms, flops / (ms * 1e-3) / 1e12);
+}
+
+// ------------------------------------------------------------------------------------------------
+// probe 4: bulk-copy (TMA engine) streaming of an L2-resident weight blob through a smem ring:
+// every CTA streams the same `blob_bytes` region `passes` times -- the access pattern of the
+// per-tile weight stream.  Reports aggregate L2->SM bandwidth.
+// ------------------------------------------------------------------------------------------------
+constexpr int RING = 3;
+__global__ void __launch_bounds__(128) stream_kernel(const uint8_t* __restrict__ blob, int stages_per_pass, int passes, int stage_bytes,
+                                                     unsigned* __restrict__ check) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t full[RING], empty[RING];
+  const int t = threadIdx.x;
+  if (t == 0) {
+    for (int i = 0; i < RING; ++i) { mbar_init(smem_u32(&full[i]), 1); mbar_init(smem_u32(&empty[i]), 1); }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  const int total = stages_per_pass * passes;
+  if (t == 0) {  // producer
+    const uint64_t pol = l2_policy_evict_last();
+    for (int i = 0; i < total; ++i) {
+      const int s = i % RING, ph = (i / RING) & 1;
+      mbar_wait(smem_u32(&empty[s]), ph ^ 1);
+      mbar_arrive_expect_tx(smem_u32(&full[s]), stage_bytes);
+      bulk_g2s_hint(smem_u32(smem + (size_t)s * stage_bytes), blob + (size_t)(i % stages_per_pass) * stage_bytes, stage_bytes,
+                    smem_u32(&full[s]), pol);
+    }
+  } else if (t == 32) {  // consumer: touch one word per stage, release
+    unsigned acc = 0;
+    for (int i = 0; i < total; ++i) {
+      const int s = i % RING, ph = (i / RING) & 1;
+      mbar_wait(smem_u32(&full[s]), ph);
+      acc += *reinterpret_cast<volatile unsigned*>(smem + (size_t)s * stage_bytes + 4 * (i & 63));
+      mbar_arrive(smem_u32(&empty[s]));
+    }
+    check[blockIdx.x] = acc;
+  }
+}
+
+static int probe_stream(int stage_kb, int grid) {
+  const int stage_bytes = stage_kb * 1024;
+  const int blob_bytes = 2400 * 1024 / stage_bytes * stage_bytes;
+  const int stages_per_pass = blob_bytes / stage_bytes, passes = 40;
+  std::vector<unsigned> h(blob_bytes / 4);
+  for (size_t i = 0; i < h.size(); ++i) h[i] = (unsigned)i * 2654435761u;
+  uint8_t* d; unsigned* chk;
+  CK(cudaMalloc(&d, blob_bytes)); CK(cudaMalloc(&chk, grid * 4));
+  CK(cudaMemcpy(d, h.data(), blob_bytes, cudaMemcpyHostToDevice));
+  const size_t smem = (size_t)RING * stage_bytes + 1024;
+  CK(cudaFuncSetAttribute(stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  stream_kernel<<<grid, 128, smem>>>(d, stages_per_pass, 2, stage_bytes, chk);
+  CK(cudaDeviceSynchronize());
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaEventRecord(e0);
+  stream_kernel<<<grid, 128, smem>>>(d, stages_per_pass, passes, stage_bytes, chk);
+  cudaEventRecord(e1);
+  CK(cudaDeviceSynchronize());
+  float ms; cudaEventElapsedTime(&ms, e0, e1);
+  std::vector<unsigned> got(grid);
+  CK(cudaMemcpy(got.data(), chk, grid * 4, cudaMemcpyDeviceToHost));
+  unsigned ref = 0;
+  for (int i = 0; i < stages_per_pass * passes; ++i) ref += h[((size_t)(i % stages_per_pass) * stage_bytes + 4 * (i & 63)) / 4];
+  int bad = 0; for (auto v : got) bad += (v != ref);
+  const double bytes = (double)blob_bytes * passes * grid;
+  printf("probe stream stage=%dKB grid=%d : %s, %.3f ms, %.2f TB/s aggregate (%.1f GB/s per CTA)\n", stage_kb, grid, bad ? "FAIL" : "PASS", ms,
+         bytes / (ms * 1e-3) / 1e12, bytes / grid / (ms * 1e-3) / 1e9);
+  return bad != 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// probe 5: TMEM load throughput (4 warps x 32x32b.x32) and a sin/FMA epilogue cost estimate
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) ldtm_kernel(int iters, long long* cycles, float* sink) {
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) tmem_alloc<512>(smem_u32(&tmem_base_s));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s + ((uint32_t)(warp * 32) << 16);
+  float acc = 0.f;
+  const long long t0 = clock64();
+  for (int i = 0; i < iters; ++i) {
+    uint32_t v[32];
+    tmem_ld32(tmem + (i & 7) * 32, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc += __sinf(__uint_as_float(v[j]) * 0.001f + 1.0f);
+  }
+  const long long t1 = clock64();
+  if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+  if (acc == 1234.5f) *sink = acc;
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tmem_base_s);
+}
+
+static void probe_ldtm() {
+  long long* d; float* sink; CK(cudaMalloc(&d, 148 * 8)); CK(cudaMalloc(&sink, 4));
+  const int iters = 2000;
+  ldtm_kernel<<<148, 128>>>(iters, d, sink);
+  CK(cudaDeviceSynchronize());
+  std::vector<long long> h(148);
+  CK(cudaMemcpy(h.data(), d, 148 * 8, cudaMemcpyDeviceToHost));
+  double mean = 0; for (auto v : h) mean += (double)v; mean /= 148;
+  printf("probe ldtm : %.1f cycles per (4 warps x [32 lanes x 32 cols] load + 32 sin/FMA per thread) -> %.2f cycles per 128x32 element block\n",
+         mean / iters, mean / iters);
+}
+
+int main(int argc, char** argv) {
+  const char* what = argc > 1 ? argv[1] : "all";
+  int fails = 0;
+  cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
+  printf("device: %s, %d SMs, cc %d.%d, smem/block optin %zu\n", prop.name, prop.multiProcessorCount, prop.major, prop.minor, prop.sharedMemPerBlockOptin);
+  if (!strcmp(what, "mma_ss")) { fails += probe_mma(false, atoi(argv[2]), atoi(argv[3])); }
+  else if (!strcmp(what, "mma_ts")) { fails += probe_mma(true, atoi(argv[2]), atoi(argv[3])); }
+  else if (!strcmp(what, "rate")) { probe_rate(atoi(argv[2]) != 0, atoi(argv[3]), atoi(argv[4])); }
+  else if (!strcmp(what, "stream")) { fails += probe_stream(atoi(argv[2]), atoi(argv[3])); }
+  else if (!strcmp(what, "ldtm")) { probe_ldtm(); }
+  else { printf("unknown probe %s\n", what); return 2; }
+  return fails ? 1 : 0;
+}
