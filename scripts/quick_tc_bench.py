@@ -32,4 +32,4 @@ e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / n
 pairs = R * Dp
-print(f"R={R} D={dirs.shape[0]} Dp={Dp}: {ms:.2f} ms/step, {pairs/ms*1e-3/1e6:.1f} M pairs/s, {pairs*2385408/ms*1e-3/1e12:.0f} TFLOP/s algorithmic, {R/ms*1e3:.0f} points/s")
+print(f"R={R} D={dirs.shape[0]} Dp={Dp}: {ms:.2f} ms/step, {pairs/(ms*1e-3)/1e6:.1f} M pairs/s, {pairs*2385408/(ms*1e-3)/1e12:.0f} TFLOP/s algorithmic, {R/ms*1e3:.0f} points/s")

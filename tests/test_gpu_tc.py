@@ -26,6 +26,8 @@ def _scene(R, D, S, seed):
     normals = torch.nn.functional.normalize(torch.randn(R, S, 3, generator=g), dim=-1)
     wa = torch.rand(R, S, 3, generator=g) / S
     dirs = torch.nn.functional.normalize(torch.randn(D, 3, generator=g), dim=-1)
+    dirs[: max(1, D // 2), 2] = dirs[: max(1, D // 2), 2].abs() + 1e-3  # at least half the set is in the upper hemisphere
+    dirs = torch.nn.functional.normalize(dirs, dim=-1)
     radiance = torch.exp(torch.randn(1, D, 3, generator=g))
     return pts, normals, wa, dirs, radiance
 
