@@ -17,9 +17,11 @@
 //   TMEM (512 columns)  ACC_A = cols [0,256)   mapping layers 1,3,5 / trunk pre-activation Z_l
 //                       ACC_B = cols [256,512) mapping layers 2,4 ; in the trunk phase split into
 //                       FP0 = [256,384), FP1 = [384,512): double-buffered FiLM chunks [freq 64 | phase 64]
-//   SMEM   ACT_M 64 KB  mapping activations / m5 (A operand, fp16, K-major no-swizzle canonical layout)
+//   SMEM   ACT_M 68 KB  mapping activations / m5 (A operand, fp16, K-major no-swizzle canonical layout),
+//                       K = 256 + a 16-wide "ones" block: columns 256,257 hold 1.0 so that every bias is
+//                       a pair of extra weight columns (fp16 hi + lo) and the epilogues add nothing
 //          ACT_H 64 KB  trunk activations h_l
-//          IN_M 16 KB, IN_H 8 KB  first-layer inputs of the NEXT tile (written by the prologue warps)
+//          IN_M 12 KB, IN_H 4 KB  first-layer inputs of the NEXT tile (written by the prologue warps)
 //          ring  4 x 16 KB  weight stages, filled by cp.async.bulk from the pre-tiled fp16 blob (L2 resident)
 //
 //   warp 0      weight producer (one lane): walks the 147-stage stream once per tile
@@ -36,6 +38,7 @@
 // phase' = phase + freq' * b (linear in m5, so it is one more row block of the same GEMM).
 #include "nsk_common.cuh"
 #include "tc_util.cuh"
+#include <stdlib.h>
 
 namespace nsk {
 namespace tcs {
@@ -49,17 +52,23 @@ constexpr int NUM_THREADS = 512;
 constexpr int EPI_WARP0 = 4, PRO_WARP0 = 12;
 constexpr int EPI_THREADS = 256, PRO_THREADS = 128;
 
-// stream: M1 (2 stages) | M2..M5 (8 each) | per layer: FP(l,0) 4, Z_l (1 or 8), FP(l,1..3) 4 each
-constexpr int STAGES_PER_TILE = 2 + 4 * 8 + (1 + 4 * 8) + 20 * 4;  // 147
-constexpr int BIAS_FLOATS = 5 * 256 /*map*/ + 5 * 256 /*freq'*/ + 5 * 256 /*phase'*/ + 256 /*w_final*/ + 4;
-constexpr int64_t BLOB_BYTES = (int64_t)STAGES_PER_TILE * STAGE_BYTES + (int64_t)BIAS_FLOATS * 4;
+// Weight stream per tile, in MMA issue order.  A stage is an [N][kps] fp16 operand tile:
+//   M1: [256][32] [256][16]        (K = 35 features + bias hi/lo columns, padded to 48)
+//   M2..M5: 8 x [256][32] + [256][16] (the 16-wide tail carries the bias hi/lo columns)
+//   FP(l,c): 4 x [128][64] + [128][16]   rows 0..63 freq', rows 64..127 phase' of columns c*64..c*64+63
+//   Z_0: [256][16] ; Z_1..Z_4: 8 x [256][32]  (trunk biases are folded into phase')
+constexpr int STAGES_PER_TILE = 2 + 4 * 9 + 20 * 5 + 1 + 4 * 8;  // 171
+constexpr int64_t STREAM_BYTES = (16384 + 8192) + 4ll * (8 * 16384 + 8192) + 20ll * (4 * 16384 + 4096) + 8192 + 4ll * 8 * 16384;
+constexpr int TAIL_FLOATS = 256 /*w_final*/ + 4 /*b_final*/;
+constexpr int64_t BLOB_BYTES = STREAM_BYTES + (int64_t)TAIL_FLOATS * 4;
+constexpr int KM = 272;                            // ACT_M K extent (256 + ones block)
 
 // shared memory carve-up (bytes)
-constexpr uint32_t OFF_ACT_M = 0;
-constexpr uint32_t OFF_ACT_H = 65536;
-constexpr uint32_t OFF_IN_M = 131072;              // [128][64] fp16
-constexpr uint32_t OFF_IN_H = OFF_IN_M + 16384;    // [128][32] fp16
-constexpr uint32_t OFF_RING = OFF_IN_H + 8192;
+constexpr uint32_t OFF_ACT_M = 0;                  // [128][272] fp16
+constexpr uint32_t OFF_ACT_H = TM * KM * 2;        // [128][256] fp16
+constexpr uint32_t OFF_IN_M = OFF_ACT_H + 65536;   // [128][48] fp16
+constexpr uint32_t OFF_IN_H = OFF_IN_M + 12288;    // [128][16] fp16
+constexpr uint32_t OFF_RING = OFF_IN_H + 4096;
 constexpr uint32_t OFF_GEO = OFF_RING + NSTAGE * STAGE_BYTES;   // [2][128] x {term, pad} + fin[128]
 constexpr uint32_t OFF_BAR = OFF_GEO + 2 * 128 * 4 + 128 * 4;
 constexpr uint32_t SMEM_BYTES = OFF_BAR + 32 * 8 + 16;
@@ -78,6 +87,7 @@ struct Params {
   float radius, thr, sig_scale;
   float* rgb_lin; float* vis_out; float* ddf_out; float* term_out;
   int64_t n_pairs, n_tiles;
+  float* dbg;   // diagnostics: [10][128][256] activations of the first tile of CTA 0 (NULL = off)
 };
 
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
@@ -85,37 +95,67 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   return *reinterpret_cast<const uint32_t*>(&h);
 }
 
-// Issue the MMAs of one GEMM op: D[tmem_d, 128 x N] (+)= A[smem a_base, 128 x K] * W^T, with W arriving
-// in `nst` ring stages of `kps` K-columns each ([N][kps] canonical tiles).
-__device__ __forceinline__ void issue_op(uint32_t smem_base, uint32_t bars, uint32_t a_off, int N, int nst, int kps,
-                                         uint32_t tmem_d, uint32_t& wstage, uint32_t& wphase) {
-  const uint32_t idesc = make_idesc_f16(TM, N);
-  uint32_t acc = 0;
-  for (int s = 0; s < nst; ++s) {
-    mbar_wait(bars + 8 * (B_WFULL + wstage), wphase);
-    tc_fence_after();
-    const uint32_t b_base = smem_base + OFF_RING + wstage * STAGE_BYTES;
-    for (int j = 0; j < kps / 16; ++j) {
-      const int k0 = s * kps + j * 16;
-      const uint64_t ad = make_smem_desc(smem_base + a_off + (uint32_t)(k0 / 8) * (TM * 16), TM * 16, 128);
-      const uint64_t bd = make_smem_desc(b_base + (uint32_t)(j * 2) * (uint32_t)(N * 16), (uint32_t)(N * 16), 128);
-      umma_ss(tmem_d, ad, bd, idesc, acc);
-      acc = 1;
-    }
-    umma_commit(bars + 8 * (B_WEMPTY + wstage));   // stage free once these MMAs have read it
-    if (++wstage == NSTAGE) { wstage = 0; wphase ^= 1; }
-  }
-}
+// ---- static per-tile schedule ------------------------------------------------------------------
+// One entry per GEMM op in MMA issue order.  `wait` is the mbarrier the issuer must see complete
+// before the op (0xff = none), `commit0/1` the barriers that a tcgen05.commit arrives on after it.
+struct Op {
+  uint8_t wait, a_sel, shape, dst, commit0, commit1, pad0, pad1;
+  uint32_t a_off;   // byte offset of the A operand tile in shared memory
+  uint32_t d_col;   // first TMEM column of the accumulator
+};
 
+enum { A_IN_M = 0, A_ACT_M = 1, A_IN_H = 2, A_ACT_H = 3 };
+enum { SH_M1 = 0, SH_MAP = 1, SH_FP = 2, SH_Z0 = 3, SH_Z = 4, SH_NONE = 5 };
+enum { D_ACC_A = 0, D_ACC_B = 1, D_FP0 = 2, D_FP1 = 3 };
+constexpr uint8_t NOB = 0xff;
+constexpr int NUM_OPS = 32;
+
+struct Schedule {
+  Op ops[NUM_OPS];
+  constexpr Schedule() : ops{} {
+    int n = 0;
+    ops[n++] = Op{B_INFULL, A_IN_M, SH_M1, D_ACC_A, B_ACCA, NOB, 0, 0, 0, 0};
+    for (int i = 2; i <= 5; ++i)
+      ops[n++] = Op{B_MACT, A_ACT_M, SH_MAP, (uint8_t)((i & 1) ? D_ACC_A : D_ACC_B), (uint8_t)((i & 1) ? B_ACCA : B_MAPB), NOB, 0, 0, 0, 0};
+    ops[n++] = Op{B_MACT, A_ACT_M, SH_FP, D_FP0, B_FPFULL + 0, NOB, 0, 0, 0, 0};      // FP(0,0): m5 ready
+    ops[n++] = Op{NOB, A_IN_H, SH_Z0, D_ACC_A, B_ACCA, B_INEMPTY, 0, 0, 0, 0};        // Z_0 ; IN buffers consumed
+    ops[n++] = Op{NOB, A_ACT_M, SH_FP, D_FP1, B_FPFULL + 1, NOB, 0, 0, 0, 0};         // FP(0,1)
+    for (int l = 0; l < 5; ++l) {
+      ops[n++] = Op{B_FPFREE + 0, A_ACT_M, SH_FP, D_FP0, B_FPFULL + 0, NOB, 0, 0, 0, 0};   // FP(l,2) after C(l,0)
+      ops[n++] = Op{B_FPFREE + 1, A_ACT_M, SH_FP, D_FP1, B_FPFULL + 1, NOB, 0, 0, 0, 0};   // FP(l,3) after C(l,1)
+      if (l < 4) {
+        ops[n++] = Op{B_FPFREE + 0, A_ACT_M, SH_FP, D_FP0, B_FPFULL + 0, NOB, 0, 0, 0, 0}; // FP(l+1,0) after C(l,2)
+        ops[n++] = Op{B_FPFREE + 1, A_ACT_H, SH_Z, D_ACC_A, B_ACCA, NOB, 0, 0, 0, 0};      // Z_{l+1} after C(l,3): h_l complete
+        ops[n++] = Op{NOB, A_ACT_M, SH_FP, D_FP1, B_FPFULL + 1, NOB, 0, 0, 0, 0};          // FP(l+1,1)
+      } else {
+        ops[n++] = Op{B_FPFREE + 0, 0, SH_NONE, 0, NOB, NOB, 0, 0, 0, 0};                  // drain C(4,2)
+        ops[n++] = Op{B_FPFREE + 1, 0, SH_NONE, 0, NOB, NOB, 0, 0, 0, 0};                  // drain C(4,3): TMEM free
+      }
+    }
+    for (int i = 0; i < NUM_OPS; ++i) {
+      ops[i].a_off = ops[i].a_sel == A_IN_M ? OFF_IN_M : ops[i].a_sel == A_ACT_M ? OFF_ACT_M : ops[i].a_sel == A_IN_H ? OFF_IN_H : OFF_ACT_H;
+      ops[i].d_col = ops[i].dst == D_ACC_A ? TM_ACC_A : ops[i].dst == D_ACC_B ? TM_ACC_B : ops[i].dst == D_FP0 ? TM_FP0 : TM_FP1;
+    }
+  }
+};
+__constant__ Schedule c_sched = Schedule();
+// shape -> (N, number of full stages, K columns per full stage, K columns of the tail stage)
+__constant__ int c_shape_N[6] = {256, 256, 128, 256, 256, 0};
+__constant__ int c_shape_nfull[6] = {1, 8, 4, 0, 8, 0};
+__constant__ int c_shape_kps[6] = {32, 32, 64, 32, 32, 0};
+__constant__ int c_shape_ktail[6] = {16, 16, 16, 16, 0, 0};
+
+template <int VARIANT>
 __global__ void __launch_bounds__(NUM_THREADS, 1) sky_shade_tc_kernel(const Params P) {
+  // VARIANT bit0: epilogue math stripped (diagnostic), bit1: MMAs not issued (diagnostic)
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bars = sbase + OFF_BAR;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 32 * 8);
-  float* geo_term = reinterpret_cast<float*>(smem + OFF_GEO);           // [2][128]
+  float* geo_term = reinterpret_cast<float*>(smem + OFF_GEO);                 // [2][128]
   float* fin_part = reinterpret_cast<float*>(smem + OFF_GEO + 2 * 128 * 4);  // [128]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const float* bias = reinterpret_cast<const float*>(P.blob + (size_t)STAGES_PER_TILE * STAGE_BYTES);
+  const float* tailw = reinterpret_cast<const float*>(P.blob + STREAM_BYTES);  // w_final[256], b_final
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NSTAGE; ++i) { mbar_init(bars + 8 * (B_WFULL + i), 1); mbar_init(bars + 8 * (B_WEMPTY + i), 1); }
@@ -128,7 +168,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sky_shade_tc_kernel(const Para
     mbar_init(bars + 8 * (B_FPFREE + 0), EPI_THREADS); mbar_init(bars + 8 * (B_FPFREE + 1), EPI_THREADS);
     fence_barrier_init();
   }
+  // the "ones" block of ACT_M (k = 256..271): columns 256 and 257 are 1.0, written once
+  if (threadIdx.x < TM) {
+    uint8_t* d = smem + OFF_ACT_M + (uint32_t)(256 / 8) * (TM * 16) + threadIdx.x * 16;
+    *reinterpret_cast<uint4*>(d) = make_uint4(0x3C003C00u, 0u, 0u, 0u);   // fp16 1.0, 1.0, 0...
+    *reinterpret_cast<uint4*>(d + TM * 16) = make_uint4(0u, 0u, 0u, 0u);
+  }
   if (warp == 2) tmem_alloc<512>(smem_u32(tmem_slot));
+  fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -140,65 +187,81 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sky_shade_tc_kernel(const Para
       const uint64_t pol = l2_policy_evict_last();
       uint32_t st = 0, ph = 0;
       for (int64_t tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
-        for (int i = 0; i < STAGES_PER_TILE; ++i) {
-          mbar_wait(bars + 8 * (B_WEMPTY + st), ph ^ 1);
-          mbar_arrive_expect_tx(bars + 8 * (B_WFULL + st), STAGE_BYTES);
-          bulk_g2s_hint(sbase + OFF_RING + st * STAGE_BYTES, P.blob + (size_t)i * STAGE_BYTES, STAGE_BYTES, bars + 8 * (B_WFULL + st), pol);
-          if (++st == NSTAGE) { st = 0; ph ^= 1; }
+        const uint8_t* src = P.blob;
+#pragma unroll 1
+        for (int o = 0; o < NUM_OPS; ++o) {
+          const int sh = c_sched.ops[o].shape;
+          const int N = c_shape_N[sh], nfull = c_shape_nfull[sh], kps = c_shape_kps[sh], ktail = c_shape_ktail[sh];
+          const int nst = nfull + (ktail ? 1 : 0);
+#pragma unroll 1
+          for (int sg = 0; sg < nst; ++sg) {
+            const uint32_t bytes = (uint32_t)N * (uint32_t)(sg < nfull ? kps : ktail) * 2u;
+            mbar_wait(bars + 8 * (B_WEMPTY + st), ph ^ 1);
+            mbar_arrive_expect_tx(bars + 8 * (B_WFULL + st), bytes);
+            bulk_g2s_hint(sbase + OFF_RING + st * STAGE_BYTES, src, bytes, bars + 8 * (B_WFULL + st), pol);
+            src += bytes;
+            if (++st == NSTAGE) { st = 0; ph ^= 1; }
+          }
         }
       }
     }
+    __syncwarp();
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
-    if (lane == 0) {
-      uint32_t wst = 0, wph = 0;
-      uint32_t ph_in = 0, ph_mact = 0, ph_free0 = 0, ph_free1 = 0;
-      for (int64_t tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
-        mbar_wait(bars + 8 * B_INFULL, ph_in); ph_in ^= 1;
-        tc_fence_after();
-        // ---- mapping network ----
-        issue_op(sbase, bars, OFF_IN_M, 256, 2, 32, tmem + TM_ACC_A, wst, wph);
-        umma_commit(bars + 8 * B_ACCA);
-        for (int i = 2; i <= 5; ++i) {
-          mbar_wait(bars + 8 * B_MACT, ph_mact); ph_mact ^= 1;
+    // The whole warp walks the schedule (warp-uniform control flow); one elected lane issues the
+    // tcgen05.mma / tcgen05.commit instructions.  Descriptors are advanced by adding to their low words.
+    uint32_t wst = 0, wph = 0, phases = 0;
+    #define NSK_LEADER() ((VARIANT & 2) ? (lane == 0) : elect_one())
+    const uint64_t desc_hi = ((uint64_t)1 << 46) | ((uint64_t)(128 >> 4) << 32);   // version 1, SBO = 128 B
+    for (int64_t tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+#pragma unroll 1
+      for (int o = 0; o < NUM_OPS; ++o) {
+        const Op op = c_sched.ops[o];
+        if (op.wait != NOB) {
+          mbar_wait(bars + 8 * op.wait, (phases >> op.wait) & 1u);
+          phases ^= 1u << op.wait;
           tc_fence_after();
-          const bool toB = (i & 1) == 0;
-          issue_op(sbase, bars, OFF_ACT_M, 256, 8, 32, tmem + (toB ? TM_ACC_B : TM_ACC_A), wst, wph);
-          umma_commit(bars + 8 * (toB ? B_MAPB : B_ACCA));
         }
-        mbar_wait(bars + 8 * B_MACT, ph_mact); ph_mact ^= 1;   // m5 ready, ACC_A / ACC_B free
-        tc_fence_after();
-        // ---- trunk ----
-        issue_op(sbase, bars, OFF_ACT_M, 128, 4, 64, tmem + TM_FP0, wst, wph);       // FP(0,0)
-        umma_commit(bars + 8 * (B_FPFULL + 0));
-        issue_op(sbase, bars, OFF_IN_H, 256, 1, 32, tmem + TM_ACC_A, wst, wph);      // Z_0
-        umma_commit(bars + 8 * B_ACCA);
-        umma_commit(bars + 8 * B_INEMPTY);                                           // IN_M / IN_H consumed
-        issue_op(sbase, bars, OFF_ACT_M, 128, 4, 64, tmem + TM_FP1, wst, wph);       // FP(0,1)
-        umma_commit(bars + 8 * (B_FPFULL + 1));
-        for (int l = 0; l < DDF_LAYERS; ++l) {
-          mbar_wait(bars + 8 * (B_FPFREE + 0), ph_free0); ph_free0 ^= 1;             // C(l,0) done
-          tc_fence_after();
-          issue_op(sbase, bars, OFF_ACT_M, 128, 4, 64, tmem + TM_FP0, wst, wph);     // FP(l,2)
-          umma_commit(bars + 8 * (B_FPFULL + 0));
-          mbar_wait(bars + 8 * (B_FPFREE + 1), ph_free1); ph_free1 ^= 1;             // C(l,1) done
-          tc_fence_after();
-          issue_op(sbase, bars, OFF_ACT_M, 128, 4, 64, tmem + TM_FP1, wst, wph);     // FP(l,3)
-          umma_commit(bars + 8 * (B_FPFULL + 1));
-          mbar_wait(bars + 8 * (B_FPFREE + 0), ph_free0); ph_free0 ^= 1;             // C(l,2) done
-          tc_fence_after();
-          if (l + 1 < DDF_LAYERS) {
-            issue_op(sbase, bars, OFF_ACT_M, 128, 4, 64, tmem + TM_FP0, wst, wph);   // FP(l+1,0)
-            umma_commit(bars + 8 * (B_FPFULL + 0));
+        const int sh = op.shape;
+        if (sh != SH_NONE) {
+          const int N = c_shape_N[sh], nfull = c_shape_nfull[sh], kps = c_shape_kps[sh], ktail = c_shape_ktail[sh];
+          const int nst = nfull + (ktail ? 1 : 0);
+          const uint32_t idesc = make_idesc_f16(TM, N);
+          const uint32_t tmem_d = tmem + op.d_col;
+          // A descriptor: LBO = 128 rows * 16 B; advancing one K=16 step moves 2 chunks = 4096 B
+          const uint64_t ad0 = desc_hi | ((uint64_t)((TM * 16) >> 4) << 16) | (uint64_t)(((sbase + op.a_off) >> 4) & 0x3FFF);
+          uint32_t kstep = 0;   // K=16 steps issued so far in this op (warp-uniform)
+          const uint64_t bd0 = desc_hi | ((uint64_t)((N * 16) >> 4) << 16);
+          const uint32_t b_step = (uint32_t)(2 * N * 16) >> 4;
+          uint32_t acc = 0;
+#pragma unroll 1
+          for (int sg = 0; sg < nst; ++sg) {
+            const int nmma = (sg < nfull ? kps : ktail) >> 4;
+            mbar_wait(bars + 8 * (B_WFULL + wst), wph);
+            tc_fence_after();
+            if (NSK_LEADER()) {
+              uint64_t ad = ad0 + (uint64_t)kstep * 256u;   // one K=16 step = 2 chunks = 4096 B >> 4
+              uint64_t bd = bd0 | (uint64_t)(((sbase + OFF_RING + wst * STAGE_BYTES) >> 4) & 0x3FFF);
+              uint32_t a = acc;
+#pragma unroll 1
+              for (int j = 0; j < nmma; ++j) {
+                umma_ss(tmem_d, ad, bd, idesc, a);
+                a = 1;
+                ad += 256;
+                bd += b_step;
+              }
+              umma_commit(bars + 8 * (B_WEMPTY + wst));   // stage reusable once these MMAs have read it
+            }
+            __syncwarp();
+            kstep += nmma;
+            acc = 1;
+            if (++wst == NSTAGE) { wst = 0; wph ^= 1; }
           }
-          mbar_wait(bars + 8 * (B_FPFREE + 1), ph_free1); ph_free1 ^= 1;             // C(l,3) done: h_l complete
-          tc_fence_after();
-          if (l + 1 < DDF_LAYERS) {
-            issue_op(sbase, bars, OFF_ACT_H, 256, 8, 32, tmem + TM_ACC_A, wst, wph); // Z_{l+1}
-            umma_commit(bars + 8 * B_ACCA);
-            issue_op(sbase, bars, OFF_ACT_M, 128, 4, 64, tmem + TM_FP1, wst, wph);   // FP(l+1,1)
-            umma_commit(bars + 8 * (B_FPFULL + 1));
+          if (NSK_LEADER()) {
+            umma_commit(bars + 8 * op.commit0);
+            if (op.commit1 != NOB) umma_commit(bars + 8 * op.commit1);
           }
+          __syncwarp();
         }
       }
     }
@@ -211,32 +274,35 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sky_shade_tc_kernel(const Para
     uint32_t ph_acca = 0, ph_mapb = 0, ph_fp0 = 0, ph_fp1 = 0;
     int par = 0;
     for (int64_t tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, par ^= 1) {
-      // ---- mapping layers: LeakyReLU(acc + b) -> ACT_M ----
+      // ---- mapping layers: LeakyReLU(acc) -> ACT_M (bias already inside the accumulator) ----
       for (int i = 1; i <= 5; ++i) {
         const bool fromB = (i & 1) == 0;
         if (fromB) { mbar_wait(bars + 8 * B_MAPB, ph_mapb); ph_mapb ^= 1; }
         else { mbar_wait(bars + 8 * B_ACCA, ph_acca); ph_acca ^= 1; }
         tc_fence_after();
-        const float* b = bias + (i - 1) * 256;
         const uint32_t src = tmem + (fromB ? TM_ACC_B : TM_ACC_A) + lane_off + hsel * 128;
-#pragma unroll 1
+        uint8_t* dst = smem + OFF_ACT_M + (uint32_t)(hsel * 16) * (TM * 16) + row * 16;
+        uint32_t v[2][16];
+        tmem_ld16(src, v[0]);
+#pragma unroll
         for (int cb = 0; cb < 8; ++cb) {
-          uint32_t v[16];
-          tmem_ld16(src + cb * 16, v);
           tmem_ld_wait();
-          const int col0 = hsel * 128 + cb * 16;
+          if (cb + 1 < 8) tmem_ld16(src + (cb + 1) * 16, v[(cb + 1) & 1]);   // prefetch the next 16 columns
           uint32_t pk[8];
 #pragma unroll
           for (int j = 0; j < 16; j += 2) {
-            float a0 = __uint_as_float(v[j]) + __ldg(b + col0 + j);
-            float a1 = __uint_as_float(v[j + 1]) + __ldg(b + col0 + j + 1);
-            a0 = a0 > 0.f ? a0 : 0.2f * a0;
-            a1 = a1 > 0.f ? a1 : 0.2f * a1;
-            pk[j >> 1] = pack_h2(a0, a1);
+            const float a0 = __uint_as_float(v[cb & 1][j]), a1 = __uint_as_float(v[cb & 1][j + 1]);
+            pk[j >> 1] = pack_h2(fmaxf(a0, 0.2f * a0), fmaxf(a1, 0.2f * a1));   // LeakyReLU(0.2)
           }
-          uint8_t* dst = smem + OFF_ACT_M + (uint32_t)(col0 >> 3) * (TM * 16) + row * 16;
-          *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          *reinterpret_cast<uint4*>(dst + TM * 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          if (P.dbg && tile == 0) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float a0 = __uint_as_float(v[cb & 1][j]);
+              P.dbg[((i - 1) * 128 + row) * 256 + hsel * 128 + cb * 16 + j] = fmaxf(a0, 0.2f * a0);
+            }
+          }
+          *reinterpret_cast<uint4*>(dst + (cb * 2) * (TM * 16)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          *reinterpret_cast<uint4*>(dst + (cb * 2 + 1) * (TM * 16)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
         }
         fence_proxy_async_smem();
         tc_fence_before();
@@ -246,37 +312,41 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sky_shade_tc_kernel(const Para
       float fin = 0.f;
       for (int l = 0; l < DDF_LAYERS; ++l) {
         mbar_wait(bars + 8 * B_ACCA, ph_acca); ph_acca ^= 1;   // Z_l
-        const float* bf = bias + 5 * 256 + l * 256;
-        const float* bp = bias + 10 * 256 + l * 256;
         for (int c = 0; c < 4; ++c) {
           if (c & 1) { mbar_wait(bars + 8 * (B_FPFULL + 1), ph_fp1); ph_fp1 ^= 1; }
           else { mbar_wait(bars + 8 * (B_FPFULL + 0), ph_fp0); ph_fp0 ^= 1; }
           tc_fence_after();
-          const uint32_t fp = tmem + ((c & 1) ? TM_FP1 : TM_FP0) + lane_off;
-#pragma unroll 1
-          for (int sb = 0; sb < 2; ++sb) {
-            const int cc = hsel * 32 + sb * 16;          // column inside the 64-wide chunk
-            const int col0 = c * 64 + cc;                // column inside the layer
-            uint32_t z[16], f[16], p[16];
-            tmem_ld16(tmem + TM_ACC_A + lane_off + col0, z);
-            tmem_ld16(fp + cc, f);
-            tmem_ld16(fp + 64 + cc, p);
-            tmem_ld_wait();
-            float h[16];
+          const uint32_t fp = tmem + ((c & 1) ? TM_FP1 : TM_FP0) + lane_off + hsel * 32;
+          const uint32_t zz = tmem + TM_ACC_A + lane_off + c * 64 + hsel * 32;
+          const int colw = c * 64 + hsel * 32;   // first layer column handled by this warp in this chunk
+          uint32_t z[2][8], f[2][8], p[2][8];
+          tmem_ld8(zz, z[0]); tmem_ld8(fp, f[0]); tmem_ld8(fp + 64, p[0]);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float fr = __uint_as_float(f[j]) + __ldg(bf + col0 + j);
-              const float ph = __uint_as_float(p[j]) + __ldg(bp + col0 + j);
-              h[j] = __sinf(fmaf(fr, __uint_as_float(z[j]), ph));
+          for (int pc = 0; pc < 4; ++pc) {
+            tmem_ld_wait();
+            if (pc + 1 < 4) {
+              tmem_ld8(zz + (pc + 1) * 8, z[(pc + 1) & 1]);
+              tmem_ld8(fp + (pc + 1) * 8, f[(pc + 1) & 1]);
+              tmem_ld8(fp + 64 + (pc + 1) * 8, p[(pc + 1) & 1]);
+            }
+            float h[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float arg = fmaf(__uint_as_float(f[pc & 1][j]), __uint_as_float(z[pc & 1][j]), __uint_as_float(p[pc & 1][j]));
+              h[j] = (VARIANT & 1) ? arg : __sinf(arg);
+            }
+            if (P.dbg && tile == 0) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) P.dbg[((5 + l) * 128 + row) * 256 + colw + pc * 8 + j] = h[j];
             }
             if (l + 1 < DDF_LAYERS) {
-              uint8_t* dst = smem + OFF_ACT_H + (uint32_t)(col0 >> 3) * (TM * 16) + row * 16;
+              uint8_t* dst = smem + OFF_ACT_H + (uint32_t)((colw >> 3) + pc) * (TM * 16) + row * 16;
               *reinterpret_cast<uint4*>(dst) = make_uint4(pack_h2(h[0], h[1]), pack_h2(h[2], h[3]), pack_h2(h[4], h[5]), pack_h2(h[6], h[7]));
-              *reinterpret_cast<uint4*>(dst + TM * 16) = make_uint4(pack_h2(h[8], h[9]), pack_h2(h[10], h[11]), pack_h2(h[12], h[13]), pack_h2(h[14], h[15]));
             } else {
-              const float* wf = bias + 15 * 256;
-#pragma unroll
-              for (int j = 0; j < 16; ++j) fin = fmaf(h[j], __ldg(wf + col0 + j), fin);   // final 256 -> 1 (film_siren.py:147)
+              const float4 w0 = __ldg(reinterpret_cast<const float4*>(tailw + colw + pc * 8));
+              const float4 w1 = __ldg(reinterpret_cast<const float4*>(tailw + colw + pc * 8 + 4));
+              fin = fmaf(h[0], w0.x, fin); fin = fmaf(h[1], w0.y, fin); fin = fmaf(h[2], w0.z, fin); fin = fmaf(h[3], w0.w, fin);
+              fin = fmaf(h[4], w1.x, fin); fin = fmaf(h[5], w1.y, fin); fin = fmaf(h[6], w1.z, fin); fin = fmaf(h[7], w1.w, fin);  // film_siren.py:147
             }
           }
           if (l + 1 < DDF_LAYERS) fence_proxy_async_smem();
@@ -293,7 +363,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sky_shade_tc_kernel(const Para
         const int64_t prc = valid ? pr : P.n_pairs - 1;
         const int64_t ray = prc / P.Dp;
         const int j = (int)(prc % P.Dp);
-        const float o = fin + fin_part[row] + __ldg(bias + 16 * 256);
+        const float o = fin + fin_part[row] + __ldg(tailw + 256);
         const float ddf = sigmoidf_(o) * (2.0f * P.radius);       // directional_distance_field.py:297-299
         const float term = geo_term[par * 128 + row];
         const float vis = visibility_from_ddf(ddf, term, P.radius, P.thr, P.sig_scale);
@@ -345,10 +415,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sky_shade_tc_kernel(const Para
       ddf_local_dir(qv, dneg, dl);                                           // ddf_model.py:158-200
       ddf_dir_features(dl, feat);                                            // directional_distance_field.py:270-271
       feat[15] = 0.f;
-      // mapping input: [q (3) | hash(q) (32) | zero pad] = 64 halves
-      float mi[40];
-      mi[0] = qv[0]; mi[1] = qv[1]; mi[2] = qv[2];
-#pragma unroll 1
+      // mapping input: [q (3) | hash(q) (32) | 1, 1 (bias columns) | zero pad] = 48 halves
+      uint32_t mp[24];
+      float carry = qv[2];   // element 2 pairs with the first hash feature
+      mp[0] = pack_h2(qv[0], qv[1]);
+#pragma unroll
       for (int lev = 0; lev < DDF_LEVELS; lev += 2) {
         float2 f[2][8];
         float ox[2], oy[2], oz[2];
@@ -361,31 +432,28 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sky_shade_tc_kernel(const Para
 #pragma unroll
           for (int c = 0; c < 8; ++c) f[u][c] = __ldg(tl + idx[c]);
         }
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const float2 r = hash_interp(f[u], ox[u], oy[u], oz[u]);
-          mi[3 + 2 * (lev + u)] = r.x;
-          mi[3 + 2 * (lev + u) + 1] = r.y;
-        }
+        const float2 r0 = hash_interp(f[0], ox[0], oy[0], oz[0]);
+        const float2 r1 = hash_interp(f[1], ox[1], oy[1], oz[1]);
+        // elements 3+2*lev .. 3+2*lev+3 ; packed pairs start at odd element indices
+        mp[1 + lev] = pack_h2(carry, r0.x);
+        mp[2 + lev] = pack_h2(r0.y, r1.x);
+        carry = r1.y;
       }
-      mi[35] = mi[36] = mi[37] = mi[38] = mi[39] = 0.f;
+      mp[17] = pack_h2(carry, 1.0f);     // elements 34, 35 (35 = bias hi column)
+      mp[18] = pack_h2(1.0f, 0.0f);      // element 36 = bias lo column
+      mp[19] = mp[20] = mp[21] = mp[22] = mp[23] = 0u;
       // wait until the MMAs of the previous tile have consumed IN_M / IN_H
       mbar_wait(bars + 8 * B_INEMPTY, ph_empty ^ 1); ph_empty ^= 1;
       {
         uint8_t* dm = smem + OFF_IN_M + row * 16;
 #pragma unroll
-        for (int kc = 0; kc < 5; ++kc)
-          *reinterpret_cast<uint4*>(dm + kc * (TM * 16)) = make_uint4(pack_h2(mi[kc * 8], mi[kc * 8 + 1]), pack_h2(mi[kc * 8 + 2], mi[kc * 8 + 3]),
-                                                                       pack_h2(mi[kc * 8 + 4], mi[kc * 8 + 5]), pack_h2(mi[kc * 8 + 6], mi[kc * 8 + 7]));
-#pragma unroll
-        for (int kc = 5; kc < 8; ++kc) *reinterpret_cast<uint4*>(dm + kc * (TM * 16)) = make_uint4(0, 0, 0, 0);
+        for (int kc = 0; kc < 6; ++kc)
+          *reinterpret_cast<uint4*>(dm + kc * (TM * 16)) = make_uint4(mp[kc * 4], mp[kc * 4 + 1], mp[kc * 4 + 2], mp[kc * 4 + 3]);
         uint8_t* dh = smem + OFF_IN_H + row * 16;
 #pragma unroll
         for (int kc = 0; kc < 2; ++kc)
           *reinterpret_cast<uint4*>(dh + kc * (TM * 16)) = make_uint4(pack_h2(feat[kc * 8], feat[kc * 8 + 1]), pack_h2(feat[kc * 8 + 2], feat[kc * 8 + 3]),
                                                                        pack_h2(feat[kc * 8 + 4], feat[kc * 8 + 5]), pack_h2(feat[kc * 8 + 6], feat[kc * 8 + 7]));
-#pragma unroll
-        for (int kc = 2; kc < 4; ++kc) *reinterpret_cast<uint4*>(dh + kc * (TM * 16)) = make_uint4(0, 0, 0, 0);
       }
       geo_term[par * 128 + row] = term;
       fence_proxy_async_smem();
@@ -403,6 +471,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sky_shade_tc_kernel(const Para
 }  // namespace nsk
 
 extern "C" int64_t nsk_ddf_tc_weights_bytes(void) { return nsk::tcs::BLOB_BYTES; }
+
+// Diagnostics only (not part of the public ABI): when set, the first tile of CTA 0 dumps its
+// post-activation values [10][128][256] (5 mapping layers, 5 trunk layers) into this device buffer.
+static float* g_nsk_tc_debug_dump = nullptr;
+extern "C" void nsk_debug_set_tc_dump(float* buf) { g_nsk_tc_debug_dump = buf; }
 
 extern "C" int nsk_sky_shade_tc_fwd(const float* points, int64_t R, const float* normals, const float* wa,
                                     const float* inv_count, int S, const float* dirs, int Dp, const float* radiance,
@@ -422,7 +495,9 @@ extern "C" int nsk_sky_shade_tc_fwd(const float* points, int64_t R, const float*
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(sky_shade_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(sky_shade_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(sky_shade_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(sky_shade_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
     if (e != cudaSuccess) { num_sms = 0; return nsk::fail("nsk_sky_shade_tc_fwd: device setup", cudaGetErrorString(e)); }
   }
   Params P;
@@ -432,9 +507,13 @@ extern "C" int nsk_sky_shade_tc_fwd(const float* points, int64_t R, const float*
   P.table = reinterpret_cast<const float2*>(hash_table); P.scalings = scalings; P.log2_T = log2_T;
   P.radius = radius; P.thr = threshold; P.sig_scale = sigmoid_scale;
   P.rgb_lin = rgb_lin; P.vis_out = vis_out; P.ddf_out = ddf_out; P.term_out = term_out;
+  P.dbg = g_nsk_tc_debug_dump;
   P.n_pairs = R * (int64_t)Dp;
   P.n_tiles = (P.n_pairs + TM - 1) / TM;
   const int64_t grid = P.n_tiles < num_sms ? P.n_tiles : num_sms;
-  sky_shade_tc_kernel<<<(unsigned)grid, NUM_THREADS, SMEM_BYTES, nsk::as_stream(stream)>>>(P);
+  const char* dbg = getenv("NSK_TC_VARIANT");   // diagnostics only: 1 = epilogue without sin
+  if (dbg && dbg[0] == '1') sky_shade_tc_kernel<1><<<(unsigned)grid, NUM_THREADS, SMEM_BYTES, nsk::as_stream(stream)>>>(P);
+  else if (dbg && dbg[0] == '2') sky_shade_tc_kernel<2><<<(unsigned)grid, NUM_THREADS, SMEM_BYTES, nsk::as_stream(stream)>>>(P);
+  else sky_shade_tc_kernel<0><<<(unsigned)grid, NUM_THREADS, SMEM_BYTES, nsk::as_stream(stream)>>>(P);
   return nsk::check_launch("sky_shade_tc_kernel");
 }

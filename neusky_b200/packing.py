@@ -53,27 +53,38 @@ def pack_reni(p: Dict[str, Tensor], num_layers: int = 6) -> Tensor:
 
 
 # ------------------------------------------------------------------------------------------------
-# Tensor-core blob for csrc/sky_shade_tc.cu: the per-tile weight STREAM (147 stages x 16 KB of fp16
-# operand tiles in the exact order the MMA issuer consumes them) followed by the fp32 epilogue vectors.
+# Tensor-core blob for csrc/sky_shade_tc.cu: the per-tile weight STREAM (fp16 operand tiles in the exact
+# order the MMA issuer consumes them, see the stage table in the kernel header) followed by the fp32
+# final-layer vector.  Every bias rides inside the GEMMs as two extra K columns (fp16 hi + lo) that
+# multiply the constant-1 columns of the activation tiles.
 # ------------------------------------------------------------------------------------------------
-TC_STAGE_BYTES = 16384
-TC_STAGES_PER_TILE = 147
-TC_BIAS_FLOATS = 15 * 256 + 256 + 4
+TC_STREAM_BYTES = (16384 + 8192) + 4 * (8 * 16384 + 8192) + 20 * (4 * 16384 + 4096) + 8192 + 4 * 8 * 16384
+TC_TAIL_FLOATS = 256 + 4
 
 
-def _stage_images(W: Tensor, kps: int):
-    """W [N][K] (K multiple of kps) -> list of fp16 [kps/8][N][8] images (no-swizzle K-major canonical layout)."""
-    N, K = W.shape
+def _image(W: Tensor) -> Tensor:
+    """W [N][kc] fp16 (kc multiple of 8) -> [kc/8][N][8] flattened: no-swizzle K-major canonical tile."""
+    N, kc = W.shape
+    return W.reshape(N, kc // 8, 8).permute(1, 0, 2).contiguous().flatten()
+
+
+def _stages(W: Tensor, nfull: int, kps: int, ktail: int):
     Wh = W.to(torch.float16)
-    out = []
-    for k0 in range(0, K, kps):
-        out.append(Wh[:, k0 : k0 + kps].reshape(N, kps // 8, 8).permute(1, 0, 2).contiguous().flatten())
+    out = [_image(Wh[:, i * kps : (i + 1) * kps]) for i in range(nfull)]
+    if ktail:
+        out.append(_image(Wh[:, nfull * kps : nfull * kps + ktail]))
+    assert nfull * kps + ktail == W.shape[1]
     return out
 
 
-def _pad_k(W: Tensor, K: int) -> Tensor:
-    out = torch.zeros((W.shape[0], K), dtype=W.dtype, device=W.device)
-    out[:, : W.shape[1]] = W
+def _with_bias_cols(W: Tensor, b: Tensor, K: int) -> Tensor:
+    """[N][K]: W, then bias split into fp16 hi and lo columns, zero padded."""
+    N, k = W.shape
+    out = torch.zeros((N, K), dtype=torch.float32, device=W.device)
+    out[:, :k] = W
+    hi = b.to(torch.float16).to(torch.float32)
+    out[:, k] = hi
+    out[:, k + 1] = b.to(torch.float32) - hi
     return out
 
 
@@ -92,36 +103,36 @@ def fold_film(p: Dict[str, Tensor]):
 
 
 def pack_ddf_tc(p: Dict[str, Tensor]) -> Tensor:
-    """uint8 blob [147*16384 + 4100*4] for nsk_sky_shade_tc_fwd."""
+    """uint8 blob [TC_STREAM_BYTES + 260*4] for nsk_sky_shade_tc_fwd."""
     dev = p["ddf.final_layer.weight"].device
+    f32 = lambda k: p[k].to(torch.float32)
     Wf, bf, Wp, bp = fold_film(p)
-    stages = []
-    # mapping network: M1 (K 35 -> 64), M2..M5
-    stages += _stage_images(_pad_k(p["ddf.mapping_network.network.0.weight"].to(torch.float32), 64), 32)
+    st = []
+    st += _stages(_with_bias_cols(f32("ddf.mapping_network.network.0.weight"), f32("ddf.mapping_network.network.0.bias"), 48), 1, 32, 16)
     for i in range(1, DDF_LAYERS):
-        stages += _stage_images(p[f"ddf.mapping_network.network.{2 * i}.weight"].to(torch.float32), 32)
+        st += _stages(_with_bias_cols(f32(f"ddf.mapping_network.network.{2 * i}.weight"), f32(f"ddf.mapping_network.network.{2 * i}.bias"), 272), 8, 32, 16)
 
     def fp(l, c):
         rows = slice(l * DDF_HID + c * 64, l * DDF_HID + c * 64 + 64)
-        return _stage_images(torch.cat([Wf[rows], Wp[rows]], 0), 64)
+        W = torch.cat([_with_bias_cols(Wf[rows], bf[rows], 272), _with_bias_cols(Wp[rows], bp[rows], 272)], 0)
+        return _stages(W, 4, 64, 16)
 
     def z(l):
-        W = p[f"ddf.net.{l}.layer.weight"].to(torch.float32)
-        return _stage_images(_pad_k(W, 32) if l == 0 else W, 32)
+        W = f32(f"ddf.net.{l}.layer.weight")
+        if l == 0:
+            W0 = torch.zeros((DDF_HID, 16), dtype=torch.float32, device=dev)
+            W0[:, :15] = W
+            return _stages(W0, 0, 32, 16)
+        return _stages(W, 8, 32, 0)
 
-    stages += fp(0, 0) + z(0) + fp(0, 1)
+    st += fp(0, 0) + z(0) + fp(0, 1)
     for l in range(DDF_LAYERS):
-        stages += fp(l, 2) + fp(l, 3)
+        st += fp(l, 2) + fp(l, 3)
         if l + 1 < DDF_LAYERS:
-            stages += fp(l + 1, 0) + z(l + 1) + fp(l + 1, 1)
-    assert len(stages) == TC_STAGES_PER_TILE, len(stages)
-    assert all(s.numel() * 2 == TC_STAGE_BYTES for s in stages)
-    stream = torch.cat(stages).contiguous().view(torch.uint8)
-    vec = torch.zeros(TC_BIAS_FLOATS, dtype=torch.float32, device=dev)
-    for i in range(DDF_LAYERS):
-        vec[i * 256 : (i + 1) * 256] = p[f"ddf.mapping_network.network.{2 * i}.bias"]
-    vec[5 * 256 : 10 * 256] = bf
-    vec[10 * 256 : 15 * 256] = bp
-    vec[15 * 256 : 16 * 256] = p["ddf.final_layer.weight"].flatten()
-    vec[16 * 256] = p["ddf.final_layer.bias"].flatten()[0]
+            st += fp(l + 1, 0) + z(l + 1) + fp(l + 1, 1)
+    stream = torch.cat(st).contiguous().view(torch.uint8)
+    assert stream.numel() == TC_STREAM_BYTES, (stream.numel(), TC_STREAM_BYTES)
+    vec = torch.zeros(TC_TAIL_FLOATS, dtype=torch.float32, device=dev)
+    vec[:256] = f32("ddf.final_layer.weight").flatten()
+    vec[256] = f32("ddf.final_layer.bias").flatten()[0]
     return torch.cat([stream, vec.view(torch.uint8)]).contiguous()
