@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py -- shaded rays/s of the NeuSky shading hot path (BASELINE.json config 2).
+
+Workload (N = 1, `config.workload`): 1,000,000 synthetic surface points x 2048 RENI++ directions
+(32x64 equirectangular grid, `EquirectangularSampler(width=64)`), DDF sky visibility on the 1024
+upper-hemisphere directions (`only_upperhemisphere_visibility=True`, neusky_config.py:157), fused
+forward.  One step = RENI++ radiance decode -> Lambert pre-pass -> fused DDF visibility + cosine-weighted
+sum (K4, tcgen05) -> sRGB, for every point.  N > 1: every rank shades its own 1M points with replicated
+weights (weak scaling, no data-path collective -- SURVEY.md 8e).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--points P] [--impl ours|reference]
+
+Prints ONE JSON line (rank 0).  `value` = points of all ranks / device time (max over ranks), inputs
+resident in HBM; `e2e` = the same through `SkyShader.shade_points_host` with pinned HOST buffers,
+H2D + D2H inside the timed region; `roofline` = the K4 kernel's algorithmic FLOP/s (2,385,408 FLOP per
+(point, direction) pair) against the measured dense tensor peak; `cpu_baseline` = the CPU
+oracle (a port of the reference algorithm: `oracle/`) on a bounded sample on this box's host cores.
+`--impl reference` times that CPU implementation alone (rank 0 only).
+
+Nothing here reads /root/reference.  The oracle is used only for the cpu_baseline / reference arm.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_PAIR = 2_385_408          # DDF network, SURVEY.md 8(d): 1,192,704 MAC per (point, direction) pair
+METRIC = "shaded rays/s (NeuS+RENI+++DDF visibility)"
+UNIT = "rays/s"
+WIDTH = 64                         # equirect 32 x 64 = 2048 directions
+SEED_W, SEED_P = 0, 1
+
+
+# ------------------------------------------------------------------------------------------ helpers
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return {"hbm_gbs": float(d.get("hbm_gbs", 6650.0)), "tf_burst": float(d.get("bf16_tflops", 1590.0)),
+                "tf_sustained": float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1590.0))), "source": "measured"}
+    # /opt/skills/guides/B200_PROFILING.md fallback (earlier measurement on this pool)
+    return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "source": "fallback"}
+
+
+def _ncu_traffic():
+    """dram bytes per launch of the K4 kernel from the committed `ncu --set full` summary, if any."""
+    path = os.path.join(ROOT, "profiles", "k4_ncu_summary.json")
+    if os.path.exists(path):
+        try:
+            with open(path) as f:
+                return json.load(f).get("dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+class ClockSampler:
+    """nvidia-smi sampling of SM clocks / throttle reasons during the timed region."""
+
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.idx)],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is not None:
+            self.p.terminate()
+            try:
+                self.p.wait(timeout=5)
+            except Exception:
+                self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, pw, reasons = [], [], [], set()
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 8:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2])); pw.append(float(c[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        self.f.close()
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w": round(statistics.median(pw), 1),
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def _inputs(P: int, seed: int):
+    """points uniform in the ball |p| < 0.95, unit normals uniform on S^2, albedo U(0,1)."""
+    g = torch.Generator().manual_seed(seed)
+    pts = torch.nn.functional.normalize(torch.randn(P, 3, generator=g), dim=-1) * torch.rand(P, 1, generator=g) ** (1.0 / 3.0) * 0.95
+    g2 = torch.Generator().manual_seed(seed + 1)
+    nrm = torch.nn.functional.normalize(torch.randn(P, 3, generator=g2), dim=-1)
+    alb = torch.rand(P, 3, generator=torch.Generator().manual_seed(seed + 2))
+    return pts.contiguous(), nrm.contiguous(), alb.contiguous()
+
+
+def _latents():
+    return torch.randn(1, 100, 3, generator=torch.Generator().manual_seed(3)), torch.zeros(1)
+
+
+def _equirect_directions(width: int):
+    """EquirectangularSampler(width) directions, z-up (ns_reni illumination_samplers.py:373-432 through nerfstudio's
+    equirectangular ray generation)."""
+    H, W = width // 2, width
+    ys, xs = torch.meshgrid(torch.arange(H, dtype=torch.float32) + 0.5, torch.arange(W, dtype=torch.float32) + 0.5, indexing="ij")
+    u = (xs - float(W // 2)) / float(H)
+    v = -(ys - float(H // 2)) / float(H)
+    theta, phi = -torch.pi * u, torch.pi * (0.5 - v)
+    d_cam = torch.stack([-torch.sin(theta) * torch.sin(phi), torch.cos(phi), -torch.cos(theta) * torch.sin(phi)], -1).reshape(-1, 3)
+    d = d_cam @ torch.tensor([[1.0, 0, 0], [0, 0, 1.0], [0, 1.0, 0]]).T
+    return d / d.norm(dim=-1, keepdim=True)
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def cpu_oracle_rate(target_s: float = 15.0, max_points: int = 8192, chunk: int = 64):
+    """Points/s of the CPU oracle (reference algorithm, torch fp32 on all host threads) on a bounded
+    sample of the config-2 workload.  Returns (rate, cores, sample description, seconds)."""
+    from oracle import neusky_oracle as O
+    from neusky_b200 import init as nb_init
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    ddf = nb_init.init_ddf_params(SEED_W)
+    reni = nb_init.init_reni_params(SEED_W + 1)
+    dirs = O.equirect_directions(WIDTH)
+    Z, sc = _latents()
+    sca = O.hash_scalings()
+
+    def run(P, seed):
+        pts, nrm, alb = _inputs(P, seed)
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            rad = O.reni_radiance_table(dirs, Z, sc, reni)[0]
+            for i in range(0, P, chunk):
+                lin, _ = O.shade_points(pts[i:i + chunk], nrm[i:i + chunk], alb[i:i + chunk], dirs, rad, ddf, sca, 19, 1.0, 0.1, 25.0)
+                O.linear_to_srgb(lin)
+        return time.perf_counter() - t0
+
+    run(chunk, 100)                       # warm-up (thread pool, allocator)
+    t_cal = run(chunk, 101)
+    P = int(max(chunk, min(max_points, (target_s / max(t_cal, 1e-6)) * chunk)))
+    P = (P // chunk) * chunk
+    t = run(P, SEED_P)
+    return P / t, cores, f"{P} of the 1,000,000 points x 2048 directions (D'=1024 through the DDF), fp32 torch CPU, one pass", t
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    rates, secs, desc, cores = [], [], "", 1
+    per_step = max(5.0, min(30.0, 120.0 / max(1, args.steps + args.warmup)))
+    for i in range(args.warmup + args.steps):
+        r, cores, desc, t = cpu_oracle_rate(target_s=per_step)
+        if i >= args.warmup:
+            rates.append(r); secs.append(t)
+    v = sum(rates) / len(rates)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * sum(secs) / len(secs), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": _config(args, 1),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def _config(args, world):
+    return {"workload": f"BASELINE.json configs[1]: shading microbench, {args.points:,} synthetic surface points/GPU x 2048 RENI++ directions "
+                        f"(32x64 equirect; D'=1024 upper-hemisphere directions through the DDF visibility field), fused forward",
+            "points_per_gpu": args.points, "directions": 2048, "ddf_directions": 1024, "latent_codes": 1,
+            "parallelism": f"ray-sharded x{world}, weights replicated, no collective",
+            "l2": "256 MiB scratch write between timed steps (L2 flush); the 1.7 MB fp16 weight stream is L2-resident by design",
+            "k4_numerics": "fp16 operands, fp32 accumulate (tcgen05 kind::f16), fp32 epilogues"}
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--points", type=int, default=1_000_000)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+        return
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    from neusky_b200 import _lib, init as nb_init
+    from neusky_b200.render import SkyShader
+
+    _lib.load()
+    shader = SkyShader(nb_init.init_ddf_params(SEED_W), nb_init.init_reni_params(SEED_W + 1), device=dev)
+    shader.set_directions(_equirect_directions(WIDTH))
+    Dp = int(shader.mask.sum())
+    P = args.points
+    pts_h, nrm_h, alb_h = (t.pin_memory() for t in _inputs(P, SEED_P + 10 * rank))
+    pts, nrm, alb = (t.to(dev) for t in (pts_h, nrm_h, alb_h))
+    Z, sc = (t.to(dev) for t in _latents())
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if dist is None:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(fn, steps):
+        evs = []
+        for _ in range(steps):
+            flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record()
+            evs.append((e0, e1))
+        torch.cuda.synchronize()
+        return sum(a.elapsed_time(b) for a, b in evs) / 1e3
+
+    # ---- device-resident throughput --------------------------------------------------------------
+    step = lambda: shader.shade_points(pts, nrm, alb, Z, sc)
+    for _ in range(args.warmup):
+        flush.fill_(1); step()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    shader.k4_events = []
+    l0 = _lib.launches
+    wall0 = time.perf_counter()
+    t_dev = timed(step, args.steps)
+    barrier()
+    wall = time.perf_counter() - wall0
+    launches = _lib.launches - l0
+    k4_s = sum(a.elapsed_time(b) for a, b in shader.k4_events) / 1e3 / max(1, len(shader.k4_events))
+    shader.k4_events = None
+    clocks = sampler.stop() if sampler else None
+    t_dev = max_over_ranks(t_dev)
+
+    # ---- end to end from pinned host buffers -----------------------------------------------------
+    out_h = torch.empty(P, 3, dtype=torch.float32).pin_memory()
+    e2e_step = lambda: shader.shade_points_host(pts_h, nrm_h, alb_h, Z, sc, out_h=out_h)
+    e2e_steps = max(1, min(args.steps, 2))
+    e2e_step()
+    barrier()
+    t_e2e = max_over_ranks(timed(e2e_step, e2e_steps))
+    barrier()
+
+    if rank == 0:
+        peaks = _peaks()
+        pairs = P * Dp
+        achieved = pairs * FLOP_PER_PAIR / k4_s / 1e12
+        peak = peaks["tf_sustained"]       # K4 runs for seconds inside the step: the sustained (power-capped) figure applies
+        line = {
+            "metric": METRIC, "value": world * P * args.steps / t_dev, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16xf16->f32",
+            "data": "synthetic", "config": _config(args, world),
+            "e2e": {"value": world * P * e2e_steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": 3 * P * 12, "d2h_bytes_per_step": P * 12,
+                    "api": "neusky_b200.render.SkyShader.shade_points_host", "steps": e2e_steps},
+            "gpu_launches": launches,
+            "roofline": {"kernel": "sky_shade_tc_kernel", "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                         "traffic": _ncu_traffic(), "peak_source": f"{peaks['source']} dense bf16/fp16 cuBLAS, sustained ({peaks['tf_burst']:.0f} burst)",
+                         "frac_of_burst": achieved / peaks["tf_burst"], "pairs_per_launch": pairs, "flop_per_pair": FLOP_PER_PAIR,
+                         "ms_per_launch": 1e3 * k4_s, "k4_share_of_step": k4_s * args.steps / t_dev if world == 1 else None},
+            "clocks": clocks, "wall_s_timed_region": wall,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            r, cores, desc, t = cpu_oracle_rate()
+            line["cpu_baseline"] = {"value": r, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc, "seconds": t}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

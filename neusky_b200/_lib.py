@@ -40,6 +40,14 @@ def load() -> ctypes.CDLL:
     return _lib
 
 
+# CUDA kernels launched per successful ABI call (1 unless listed); bench.py reports the running total
+# as ``gpu_launches``.
+KERNELS_PER_CALL = {"nsk_reni_decode_fwd": 2}
+launches = 0
+
+
 def check(status: int, what: str) -> None:
+    global launches
     if status != 0:
         raise RuntimeError(f"{what} failed: {load().nsk_last_error().decode()}")
+    launches += KERNELS_PER_CALL.get(what, 1)

@@ -33,6 +33,7 @@ class SkyShader:
         self.hash_table = ddf_params["position_encoding.hash_table"].to(self.device, torch.float32).contiguous()
         self.set_ddf_weights(ddf_params)
         self.reni_blob = packing.pack_reni({k: v.to(self.device) for k, v in reni_params.items()}) if reni_params is not None else None
+        self.k4_events = None   # bench hook: when a list, (start, end) CUDA events are recorded around every K4 launch
 
     def set_ddf_weights(self, ddf_params: Dict[str, Tensor]) -> None:
         p = {k: v.to(self.device) for k, v in ddf_params.items() if k.startswith("ddf.")}
@@ -64,8 +65,14 @@ class SkyShader:
         inv_count, rgb_lin = ops.lambert_prep(normals, wa, self.dirs, self.mask_u8, radiance, cam, self.lower_vis)
         rad_sel = radiance[:, self.mask].contiguous()
         blob = self.ddf_blob_tc if impl == "tc" else self.ddf_blob_simt
+        if self.k4_events is not None:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
         vis, ddf, term = ops.sky_shade(points, normals, wa, inv_count, self.dirs_sel, rad_sel, blob, self.hash_table, self.scalings,
                                        self.log2_T, self.radius, threshold, sigmoid_scale, rgb_lin, cam, want_vis, want_ddf, impl)
+        if self.k4_events is not None:
+            ev[1].record()
+            self.k4_events.append(ev)
         out = {"rgb_lin": rgb_lin, "inv_count": inv_count}
         if vis is not None:
             full = torch.full((points.shape[0], self.dirs.shape[0]), self.lower_vis, device=self.device)
@@ -74,3 +81,29 @@ class SkyShader:
         if ddf is not None:
             out["expected_termination_dist"], out["termination_dist"] = ddf, term
         return out
+
+    # -- config-2 entry points (BASELINE.json: surface points x RENI++ directions) ------------------
+    def shade_points(self, points: Tensor, normals: Tensor, albedo: Tensor, latents: Tensor, scale: Optional[Tensor] = None,
+                     rotation: Optional[Tensor] = None, threshold: float = 0.1, sigmoid_scale: float = 25.0) -> Tensor:
+        """Device-resident inputs: points/normals/albedo [N,3] (one sample per point, weight 1), latents [1,L,3]
+        -> sRGB [N,3].  RENI++ decode -> Lambert pre-pass -> fused DDF visibility + cosine sum -> sRGB."""
+        N = points.shape[0]
+        radiance = self.radiance_table(latents, scale, rotation)
+        out = self.shade(points, normals.reshape(N, 1, 3), albedo.reshape(N, 1, 3), radiance, threshold=threshold, sigmoid_scale=sigmoid_scale)
+        ones = torch.ones(N, device=self.device)
+        return ops.shade_finalize(out["rgb_lin"], torch.zeros(N, 3, device=self.device), ones)
+
+    def shade_points_host(self, points_h: Tensor, normals_h: Tensor, albedo_h: Tensor, latents: Tensor, scale: Optional[Tensor] = None,
+                          out_h: Optional[Tensor] = None, **kw) -> Tensor:
+        """Same, from (pinned) HOST buffers to a (pinned) host result: the call a user with CPU-side
+        G-buffers makes.  Copies ride the current stream; returns after the result has landed."""
+        for n, t in (("points_h", points_h), ("normals_h", normals_h), ("albedo_h", albedo_h)):
+            if t.is_cuda or t.dtype != torch.float32 or t.dim() != 2 or t.shape[1] != 3:
+                raise ValueError(f"{n}: expected a host fp32 [N,3] tensor")
+        pts, nrm, alb = (t.to(self.device, non_blocking=True) for t in (points_h, normals_h, albedo_h))
+        rgb = self.shade_points(pts, nrm, alb, latents, scale, **kw)
+        if out_h is None:
+            out_h = torch.empty(rgb.shape, dtype=torch.float32, pin_memory=True)
+        out_h.copy_(rgb, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return out_h
