@@ -53,6 +53,21 @@ int nsk_hash_indices(const float* x, int64_t n, const float* scalings, int num_l
                      int64_t* idx, float* offsets, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * K2  SDF / albedo field of a sample, fused with its hash encode and the ANALYTIC gradient d sdf / d x.
+ * replaces SDFAlbedoField.get_outputs and get_sdf_at_pos (neusky/fields/sdf_albedo_field.py:169-174, 211-269):
+ * nerfstudio SDFField.forward_geonetwork [SURVEY A.4] (L-inf scene contraction, (p+2)/4, hash grid, [x | PE6(x) | feat]
+ * -> 256 -> 256 -> 1+256, softplus beta=100), torch.autograd.grad(sdf, x) (:235-238) and get_colors (:185-209).
+ *   x [n,3]; sdf_weights = packed fp32 blob (python neusky_b200.packing.pack_sdf_simt, weight_norm folded);
+ *   hash_table [L*T,2]; outputs sdf [n], grad [n,3] (NULL = skip the reverse pass), albedo [n,3] (NULL = skip the
+ *   colour network), geo [n,256] (NULL = do not write the geometry feature).
+ * nsk_sdf_field_simt_fwd: exact fp32 CUDA-core path.
+ * ------------------------------------------------------------------------------------------- */
+int64_t nsk_sdf_simt_weights_floats(void);
+int nsk_sdf_field_simt_fwd(const float* x, int64_t n, const float* sdf_weights, const float* hash_table,
+                           const float* scalings, int num_levels, int log2_T, float* sdf, float* grad, float* albedo,
+                           float* geo, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * K3  NeuS logistic-CDF alpha + transmittance + compositing, one warp per ray.
  * replaces SDFField.get_alpha (called neusky/fields/sdf_albedo_field.py:266),
  * RaySamples.get_weights_and_transmittance_from_alphas (neusky/models/neusky_model.py:565) and the

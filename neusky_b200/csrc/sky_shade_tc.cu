@@ -87,6 +87,7 @@ struct Params {
   float radius, thr, sig_scale;
   float* rgb_lin; float* vis_out; float* ddf_out; float* term_out;
   int64_t n_pairs, n_tiles;
+  unsigned long long* prof;   // diagnostics: [grid][16] cycle counters (NULL = off)
   float* dbg;   // diagnostics: [10][128][256] activations of the first tile of CTA 0 (NULL = off)
 };
 
@@ -186,6 +187,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sky_shade_tc_kernel(const Para
     if (lane == 0) {
       const uint64_t pol = l2_policy_evict_last();
       uint32_t st = 0, ph = 0;
+      long long t_wait = 0;
+      const long long t_begin = clock64();
       for (int64_t tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
         const uint8_t* src = P.blob;
 #pragma unroll 1
@@ -196,7 +199,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sky_shade_tc_kernel(const Para
 #pragma unroll 1
           for (int sg = 0; sg < nst; ++sg) {
             const uint32_t bytes = (uint32_t)N * (uint32_t)(sg < nfull ? kps : ktail) * 2u;
+            const long long c0 = clock64();
             mbar_wait(bars + 8 * (B_WEMPTY + st), ph ^ 1);
+            t_wait += clock64() - c0;
             mbar_arrive_expect_tx(bars + 8 * (B_WFULL + st), bytes);
             bulk_g2s_hint(sbase + OFF_RING + st * STAGE_BYTES, src, bytes, bars + 8 * (B_WFULL + st), pol);
             src += bytes;
@@ -204,6 +209,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sky_shade_tc_kernel(const Para
           }
         }
       }
+      if (P.prof) { P.prof[blockIdx.x * 16 + 0] = clock64() - t_begin; P.prof[blockIdx.x * 16 + 1] = t_wait; }
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -211,6 +217,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sky_shade_tc_kernel(const Para
     // The whole warp walks the schedule (warp-uniform control flow); one elected lane issues the
     // tcgen05.mma / tcgen05.commit instructions.  Descriptors are advanced by adding to their low words.
     uint32_t wst = 0, wph = 0, phases = 0;
+    long long t_dep = 0, t_w = 0, t_dep_map = 0;
+    const long long t_begin = clock64();
     #define NSK_LEADER() ((VARIANT & 2) ? (lane == 0) : elect_one())
     const uint64_t desc_hi = ((uint64_t)1 << 46) | ((uint64_t)(128 >> 4) << 32);   // version 1, SBO = 128 B
     for (int64_t tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
@@ -218,7 +226,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sky_shade_tc_kernel(const Para
       for (int o = 0; o < NUM_OPS; ++o) {
         const Op op = c_sched.ops[o];
         if (op.wait != NOB) {
+          const long long c0 = clock64();
           mbar_wait(bars + 8 * op.wait, (phases >> op.wait) & 1u);
+          const long long dt = clock64() - c0;
+          t_dep += dt;
+          if (o < 6) t_dep_map += dt;
           phases ^= 1u << op.wait;
           tc_fence_after();
         }
@@ -237,7 +249,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sky_shade_tc_kernel(const Para
 #pragma unroll 1
           for (int sg = 0; sg < nst; ++sg) {
             const int nmma = (sg < nfull ? kps : ktail) >> 4;
-            mbar_wait(bars + 8 * (B_WFULL + wst), wph);
+            {
+              const long long c0 = clock64();
+              mbar_wait(bars + 8 * (B_WFULL + wst), wph);
+              t_w += clock64() - c0;
+            }
             tc_fence_after();
             if (NSK_LEADER()) {
               uint64_t ad = ad0 + (uint64_t)kstep * 256u;   // one K=16 step = 2 chunks = 4096 B >> 4
@@ -265,6 +281,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sky_shade_tc_kernel(const Para
         }
       }
     }
+    if (P.prof && lane == 0) {
+      P.prof[blockIdx.x * 16 + 2] = clock64() - t_begin; P.prof[blockIdx.x * 16 + 3] = t_dep; P.prof[blockIdx.x * 16 + 4] = t_w;
+      P.prof[blockIdx.x * 16 + 5] = t_dep_map;
+    }
   } else if (warp >= EPI_WARP0 && warp < PRO_WARP0) {
     // ================================ epilogue ================================
     const int e = warp - EPI_WARP0;
@@ -272,13 +292,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sky_shade_tc_kernel(const Para
     const int row = q * 32 + lane;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     uint32_t ph_acca = 0, ph_mapb = 0, ph_fp0 = 0, ph_fp1 = 0;
+    long long t_wmap = 0, t_wz = 0, t_wfp = 0, t_tail = 0;
+    const long long t_begin = clock64();
     int par = 0;
     for (int64_t tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, par ^= 1) {
       // ---- mapping layers: LeakyReLU(acc) -> ACT_M (bias already inside the accumulator) ----
       for (int i = 1; i <= 5; ++i) {
         const bool fromB = (i & 1) == 0;
+        const long long c0 = clock64();
         if (fromB) { mbar_wait(bars + 8 * B_MAPB, ph_mapb); ph_mapb ^= 1; }
         else { mbar_wait(bars + 8 * B_ACCA, ph_acca); ph_acca ^= 1; }
+        t_wmap += clock64() - c0;
         tc_fence_after();
         const uint32_t src = tmem + (fromB ? TM_ACC_B : TM_ACC_A) + lane_off + hsel * 128;
         uint8_t* dst = smem + OFF_ACT_M + (uint32_t)(hsel * 16) * (TM * 16) + row * 16;
@@ -311,10 +335,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sky_shade_tc_kernel(const Para
       // ---- trunk: h = sin(freq' * z + phase') ----
       float fin = 0.f;
       for (int l = 0; l < DDF_LAYERS; ++l) {
+        long long c0 = clock64();
         mbar_wait(bars + 8 * B_ACCA, ph_acca); ph_acca ^= 1;   // Z_l
+        t_wz += clock64() - c0;
         for (int c = 0; c < 4; ++c) {
+          c0 = clock64();
           if (c & 1) { mbar_wait(bars + 8 * (B_FPFULL + 1), ph_fp1); ph_fp1 ^= 1; }
           else { mbar_wait(bars + 8 * (B_FPFULL + 0), ph_fp0); ph_fp0 ^= 1; }
+          t_wfp += clock64() - c0;
           tc_fence_after();
           const uint32_t fp = tmem + ((c & 1) ? TM_FP1 : TM_FP0) + lane_off + hsel * 32;
           const uint32_t zz = tmem + TM_ACC_A + lane_off + c * 64 + hsel * 32;
@@ -355,6 +383,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sky_shade_tc_kernel(const Para
         }
       }
       // ---- tail: sigmoid, visibility, Lambertian accumulation ----
+      const long long c_tail = clock64();
       if (hsel == 1) fin_part[row] = fin;
       asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
       if (hsel == 0) {
@@ -393,6 +422,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sky_shade_tc_kernel(const Para
         }
       }
       asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");   // fin_part reusable
+      t_tail += clock64() - c_tail;
+    }
+    if (P.prof && e == 0 && lane == 0) {
+      P.prof[blockIdx.x * 16 + 6] = clock64() - t_begin; P.prof[blockIdx.x * 16 + 7] = t_wmap; P.prof[blockIdx.x * 16 + 8] = t_wz;
+      P.prof[blockIdx.x * 16 + 9] = t_wfp; P.prof[blockIdx.x * 16 + 10] = t_tail;
     }
   } else if (warp >= PRO_WARP0) {
     // ================================ prologue ================================
@@ -400,6 +434,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sky_shade_tc_kernel(const Para
     const uint32_t mask = (1u << P.log2_T) - 1u;
     uint32_t ph_empty = 0;
     int par = 0;
+    long long t_wempty = 0;
+    const long long t_begin = clock64();
     for (int64_t tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, par ^= 1) {
       const int64_t pr = min(tile * TM + row, P.n_pairs - 1);
       const int64_t ray = pr / P.Dp;
@@ -443,7 +479,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sky_shade_tc_kernel(const Para
       mp[18] = pack_h2(1.0f, 0.0f);      // element 36 = bias lo column
       mp[19] = mp[20] = mp[21] = mp[22] = mp[23] = 0u;
       // wait until the MMAs of the previous tile have consumed IN_M / IN_H
-      mbar_wait(bars + 8 * B_INEMPTY, ph_empty ^ 1); ph_empty ^= 1;
+      {
+        const long long c0 = clock64();
+        mbar_wait(bars + 8 * B_INEMPTY, ph_empty ^ 1); ph_empty ^= 1;
+        t_wempty += clock64() - c0;
+      }
       {
         uint8_t* dm = smem + OFF_IN_M + row * 16;
 #pragma unroll
@@ -459,6 +499,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sky_shade_tc_kernel(const Para
       fence_proxy_async_smem();
       mbar_arrive(bars + 8 * B_INFULL);
     }
+    if (P.prof && row == 0) { P.prof[blockIdx.x * 16 + 11] = clock64() - t_begin; P.prof[blockIdx.x * 16 + 12] = t_wempty; }
   }
 
   __syncwarp();
@@ -476,6 +517,9 @@ extern "C" int64_t nsk_ddf_tc_weights_bytes(void) { return nsk::tcs::BLOB_BYTES;
 // post-activation values [10][128][256] (5 mapping layers, 5 trunk layers) into this device buffer.
 static float* g_nsk_tc_debug_dump = nullptr;
 extern "C" void nsk_debug_set_tc_dump(float* buf) { g_nsk_tc_debug_dump = buf; }
+// Diagnostics only: per-CTA cycle counters [grid][16] (see scripts/k4_phase_profile.py for the slot meaning).
+static unsigned long long* g_nsk_tc_prof = nullptr;
+extern "C" void nsk_debug_set_tc_prof(unsigned long long* buf) { g_nsk_tc_prof = buf; }
 
 extern "C" int nsk_sky_shade_tc_fwd(const float* points, int64_t R, const float* normals, const float* wa,
                                     const float* inv_count, int S, const float* dirs, int Dp, const float* radiance,
@@ -508,6 +552,7 @@ extern "C" int nsk_sky_shade_tc_fwd(const float* points, int64_t R, const float*
   P.radius = radius; P.thr = threshold; P.sig_scale = sigmoid_scale;
   P.rgb_lin = rgb_lin; P.vis_out = vis_out; P.ddf_out = ddf_out; P.term_out = term_out;
   P.dbg = g_nsk_tc_debug_dump;
+  P.prof = g_nsk_tc_prof;
   P.n_pairs = R * (int64_t)Dp;
   P.n_tiles = (P.n_pairs + TM - 1) / TM;
   const int64_t grid = P.n_tiles < num_sms ? P.n_tiles : num_sms;

@@ -74,9 +74,44 @@ def hash_indices(x: Tensor, scalings: Tensor, log2_T: int) -> Tuple[Tensor, Tens
     return idx, off
 
 
+# ------------------------------------------------------------------------------------------- K2
+def sdf_field(x: Tensor, blob: Tensor, hash_table: Tensor, scalings: Tensor, log2_T: int, want_grad: bool = True, want_albedo: bool = True,
+              want_geo: bool = False, impl: str = "simt") -> Dict[str, Tensor]:
+    """x [...,3] -> {"sdf" [...,1], "gradient" [...,3], "albedo" [...,3], "geo" [...,256]} (SDFAlbedoField.get_outputs
+    without alpha, neusky/fields/sdf_albedo_field.py:211-269; the gradient is analytic, not autograd)."""
+    lead = x.shape[:-1]
+    x2 = _chk("x", x.reshape(-1, 3), shape=(None, 3))
+    n = x2.shape[0]
+    L = scalings.numel()
+    hash_table = _chk("hash_table", hash_table, shape=(L << log2_T, 2))
+    scalings = _chk("scalings", scalings)
+    lib = _lib.load()
+    if impl != "simt":
+        raise ValueError(f"impl must be 'simt', got {impl!r}")
+    blob = _chk("blob", blob, shape=(lib.nsk_sdf_simt_weights_floats(),))
+    f = dict(device=x.device, dtype=torch.float32)
+    sdf = torch.empty((n,), **f)
+    grad = torch.empty((n, 3), **f) if want_grad else None
+    alb = torch.empty((n, 3), **f) if want_albedo else None
+    geo = torch.empty((n, 256), **f) if want_geo else None
+    _lib.check(lib.nsk_sdf_field_simt_fwd(_ptr(x2), c_int64(n), _ptr(blob), _ptr(hash_table), _ptr(scalings), c_int(L), c_int(log2_T), _ptr(sdf), _ptr(grad), _ptr(alb), _ptr(geo), _stream(x)), "nsk_sdf_field_simt_fwd")
+    out = {"sdf": sdf.reshape(*lead, 1)}
+    if grad is not None:
+        out["gradient"] = grad.reshape(*lead, 3)
+    if alb is not None:
+        out["albedo"] = alb.reshape(*lead, 3)
+    if geo is not None:
+        out["geo"] = geo.reshape(*lead, 256)
+    return out
+
+
 # ------------------------------------------------------------------------------------------- K3
-def neus_composite(sdf, grad, albedo, ray_dirs, starts, ends, deltas, dnorm, inv_s: float, cos_anneal_ratio: float = 1.0, training: bool = False) -> Dict[str, Tensor]:
-    """sdf/starts/ends/deltas [R,S(,1)], grad/albedo [R,S,3], ray_dirs [R,3], dnorm [R(,1)]."""
+def neus_composite(sdf, grad, albedo, ray_dirs, starts, ends, deltas, dnorm, inv_s: float, cos_anneal_ratio: float = 1.0, training: bool = False,
+                   steps_minmax: Optional[Tensor] = None) -> Dict[str, Tensor]:
+    """sdf/starts/ends/deltas [R,S(,1)], grad/albedo [R,S,3], ray_dirs [R,3], dnorm [R(,1)].
+    The expected depth is clipped to [min, max] of the sample mid-points like nerfstudio's DepthRenderer: over THIS
+    batch by default (the reference renders 256-ray chunks, so its clip range is per chunk), or to the caller's
+    ``steps_minmax`` [2] when given (tile- and rank-invariant eval renders)."""
     R, S = sdf.shape[0], sdf.shape[1]
     dev = sdf.device
     sdf = _chk("sdf", sdf.reshape(R, S))
@@ -96,6 +131,8 @@ def neus_composite(sdf, grad, albedo, ray_dirs, starts, ends, deltas, dnorm, inv
     lib = _lib.load()
     st = _stream(sdf)
     _lib.check(lib.nsk_neus_composite_fwd(_ptr(sdf), _ptr(grad), _ptr(albedo), _ptr(ray_dirs), _ptr(starts), _ptr(ends), _ptr(deltas), c_int64(R), c_int(S), c_float(inv_s), c_float(cos_anneal_ratio), c_int(int(training)), _ptr(out["weights"]), _ptr(out["wa"]), _ptr(out["normals"]), _ptr(out["accumulation"]), _ptr(out["p2p_raw"]), _ptr(out["normal"]), _ptr(out["albedo"]), _ptr(out["bg_transmittance"]), _ptr(mm), st), "nsk_neus_composite_fwd")
+    if steps_minmax is not None:
+        mm = _chk("steps_minmax", steps_minmax, shape=(2,))
     _lib.check(lib.nsk_neus_finalize_depth(_ptr(out["p2p_raw"]), _ptr(dnorm), _ptr(mm), c_int64(R), _ptr(out["p2p_dist"]), _ptr(out["depth"]), st), "nsk_neus_finalize_depth")
     out["steps_minmax"] = mm
     return out

@@ -52,6 +52,37 @@ def pack_reni(p: Dict[str, Tensor], num_layers: int = 6) -> Tensor:
     return torch.cat([x.to(torch.float32).flatten() for x in parts]).contiguous()
 
 
+def fold_weight_norm(p: Dict[str, Tensor], name: str) -> Tensor:
+    """nn.utils.weight_norm(dim=0) fold W = g * v / ||v||_row (SDFFieldConfig.weight_norm=True [NS-mem A.4];
+    neusky/fields/sdf_albedo_field.py:159-160); plain ``.weight`` is accepted too."""
+    if name + ".weight" in p:
+        return p[name + ".weight"].to(torch.float32)
+    v, g = p[name + ".weight_v"].to(torch.float32), p[name + ".weight_g"].to(torch.float32)
+    return v * (g / v.norm(dim=1, keepdim=True))
+
+
+def pack_sdf_simt(p: Dict[str, Tensor]) -> Tensor:
+    """fp32 blob for nsk_sdf_field_simt_fwd (see sdf_layout() in csrc/sdf_field_simt.cu): forward weights
+    transposed to [K][N], reverse-pass weights in torch's [out][in] layout.  NeuSky shape only
+    (neusky_config.py:66-77: 2 hidden geo layers, 2 hidden colour layers, width 256, geo feature 256)."""
+    W0, W1, W2 = (fold_weight_norm(p, f"glin{l}") for l in range(3))
+    C0, C1, C2 = (fold_weight_norm(p, f"clin{l}") for l in range(3))
+    if tuple(W0.shape) != (256, 71) or tuple(W1.shape) != (256, 256) or tuple(W2.shape) != (257, 256) or tuple(C0.shape) != (256, 295) or tuple(C2.shape) != (3, 256):
+        raise ValueError("pack_sdf_simt: expected the NeuSky SDFAlbedoField shape (71->256->256->257, 295->256->256->3)")
+    f32 = lambda k: p[k].to(torch.float32).flatten()
+    dev = W0.device
+    pad4 = lambda v: torch.cat([v.flatten(), torch.zeros(4 - v.numel(), dtype=torch.float32, device=dev)])
+    b2 = f32("glin2.bias")
+    parts = [
+        W0.t().contiguous().flatten(), f32("glin0.bias"), W1.t().contiguous().flatten(), f32("glin1.bias"),
+        W2[1:].t().contiguous().flatten(), b2[1:], W2[0].contiguous(), pad4(b2[:1]),
+        W1.contiguous().flatten(), W0.contiguous().flatten(),
+        C0.t().contiguous().flatten(), f32("clin0.bias"), C1.t().contiguous().flatten(), f32("clin1.bias"),
+        C2.contiguous().flatten(), pad4(f32("clin2.bias")),
+    ]
+    return torch.cat(parts).contiguous()
+
+
 # ------------------------------------------------------------------------------------------------
 # Tensor-core blob for csrc/sky_shade_tc.cu: the per-tile weight STREAM (fp16 operand tiles in the exact
 # order the MMA issuer consumes them, see the stage table in the kernel header) followed by the fp32

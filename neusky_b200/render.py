@@ -107,3 +107,96 @@ class SkyShader:
         out_h.copy_(rgb, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
         return out_h
+
+
+# ==================================================================================================
+# Full per-ray eval render (BASELINE.json configs 1 and 3)
+# ==================================================================================================
+def pinhole_rays(H: int, W: int, fx: float, fy: float, cx: float, cy: float, c2w: Tensor, device) -> tuple:
+    """Camera rays exactly as nerfstudio Cameras.generate_rays builds them for a perspective camera [SURVEY A.8]:
+    pixel centres at +0.5, d_cam = ((x-cx)/fx, -(y-cy)/fy, -1).  Returns origins, unit directions [H*W,3] and
+    directions_norm [H*W,1], row-major, on `device`."""
+    ys, xs = torch.meshgrid(torch.arange(H, dtype=torch.float32, device=device) + 0.5, torch.arange(W, dtype=torch.float32, device=device) + 0.5, indexing="ij")
+    d_cam = torch.stack([(xs - cx) / fx, -(ys - cy) / fy, -torch.ones_like(xs)], -1).reshape(-1, 3)
+    c2w = c2w.to(device, torch.float32)
+    d = d_cam @ c2w[:3, :3].T
+    dn = d.norm(dim=-1, keepdim=True)
+    return c2w[:3, 3].expand(H * W, 3).contiguous(), (d / dn).contiguous(), dn.contiguous()
+
+
+def sphere_collider(origins: Tensor, directions: Tensor, radius: float = 1.0, near_plane: float = 0.05, training: bool = False):
+    """nerfstudio SphereCollider [SURVEY A.6], set at neusky/models/neusky_model.py:440."""
+    ox, oy, oz = origins[..., 0:1], origins[..., 1:2], origins[..., 2:3]
+    dx, dy, dz = directions[..., 0:1], directions[..., 1:2], directions[..., 2:3]
+    # explicit component arithmetic (no reductions): every op is a correctly rounded fp32 elementwise op, so the CPU
+    # oracle and the GPU host mirror produce bit-identical near / far
+    a = dx * dx + dy * dy + dz * dz
+    b = 2 * (ox * dx + oy * dy + oz * dz)
+    c = (ox * ox + oy * oy + oz * oz) - radius**2
+    disc = b * b - 4 * a * c
+    t0 = (-b - torch.sqrt(disc)) / (2 * a)
+    t1 = (-b + torch.sqrt(disc)) / (2 * a)
+    near = torch.clamp(t0, min=near_plane if training else 0.0)
+    far = torch.maximum(t1, near + 1e-6)
+    return torch.nan_to_num(near, nan=0.0), torch.nan_to_num(far, nan=0.0)
+
+
+def uniform_samples(near: Tensor, far: Tensor, S: int):
+    """nerfstudio UniformSampler eval placement [SURVEY A.6]: same op sequence as the oracle so that starts / ends
+    are bit-identical to the CPU reference."""
+    bins = torch.linspace(0.0, 1.0, S + 1, dtype=near.dtype)[None].to(near.device)   # built on the host: CPU linspace rounding
+    e = bins * far + (1 - bins) * near
+    return e[:, :-1].contiguous(), e[:, 1:].contiguous()
+
+
+class RayRenderer:
+    """Eval render of a ray bundle: sample placement -> K2 (SDF/albedo field + analytic normals) -> K3 (NeuS alpha,
+    transmittance, composites) -> RENI++ radiance -> K4 (DDF sky visibility + Lambertian sum) -> sRGB.
+    Mirrors NeuSkyFactoModel.forward / get_outputs in eval mode (neusky/models/neusky_model.py:425-443, 553-931) for
+    one camera (one latent code) per call; outputs use the reference's keys (:881-931)."""
+
+    def __init__(self, sdf_params: Dict[str, Tensor], ddf_params: Dict[str, Tensor], reni_params: Dict[str, Tensor], device="cuda",
+                 log2_T: int = 19, num_levels: int = 16, ddf_radius: float = 1.0, impl: str = "tc", sdf_impl: str = "simt"):
+        self.device = torch.device(device)
+        self.log2_T = log2_T
+        self.sdf_impl = sdf_impl
+        self.shader = SkyShader(ddf_params, reni_params, device=device, ddf_radius=ddf_radius, log2_T=log2_T, num_levels=num_levels, impl=impl)
+        self.scalings = self.shader.scalings
+        self.sdf_table = sdf_params["encoding.hash_table"].to(self.device, torch.float32).contiguous()
+        self.set_sdf_weights(sdf_params)
+
+    def set_sdf_weights(self, sdf_params: Dict[str, Tensor]) -> None:
+        p = {k: v.to(self.device) for k, v in sdf_params.items() if k.startswith(("glin", "clin"))}
+        self.sdf_blob = packing.pack_sdf_simt(p)
+        var = sdf_params["deviation_network.variance"]
+        self.inv_s = float(torch.exp(10.0 * var.detach().float().cpu()).clip(1e-6, 1e6))   # LearnedVariance.get_variance [SURVEY A.4]
+
+    def set_directions(self, dirs: Tensor) -> None:
+        self.shader.set_directions(dirs)
+
+    @torch.no_grad()
+    def render(self, origins: Tensor, directions: Tensor, dnorm: Tensor, S: int, latent: Tensor, scale: Tensor, rotation: Optional[Tensor] = None,
+               threshold: float = 0.1, sigmoid_scale: float = 25.0, cos_anneal_ratio: float = 1.0, want_vis: bool = False,
+               steps_minmax: Optional[Tensor] = None) -> Dict[str, Tensor]:
+        """origins/directions [R,3], dnorm [R,1]; latent [L,3]; scale scalar tensor.  All rays belong to one camera."""
+        R = origins.shape[0]
+        sh = self.shader
+        near, far = sphere_collider(origins, directions)
+        starts, ends = uniform_samples(near, far, S)
+        x = origins[:, None, :] + directions[:, None, :] * starts[..., None]          # get_start_positions
+        f = ops.sdf_field(x, self.sdf_blob, self.sdf_table, self.scalings, self.log2_T, impl=self.sdf_impl)
+        c = ops.neus_composite(f["sdf"], f["gradient"], f["albedo"], directions, starts, ends, ends - starts, dnorm, self.inv_s, cos_anneal_ratio, False,
+                               steps_minmax=steps_minmax)
+        Z = latent.reshape(1, -1, 3).to(self.device, torch.float32)
+        sc = scale.reshape(1).to(self.device, torch.float32)
+        radiance = sh.radiance_table(Z, sc, rotation)                                    # [1,D,3]
+        bg = ops.reni_radiance_table(directions, Z, sc, sh.reni_blob, rotation)[0]      # per-ray background (neusky_model.py:535-549)
+        pts = ops.surface_points(origins, directions, c["p2p_dist"], sh.radius)
+        s = sh.shade(pts, c["normals"], c["wa"], radiance, want_vis=want_vis, threshold=threshold, sigmoid_scale=sigmoid_scale)
+        rgb = ops.shade_finalize(s["rgb_lin"], bg, c["accumulation"])
+        out = {"rgb": rgb, "albedo": c["albedo"], "accumulation": c["accumulation"][:, None], "depth": c["depth"][:, None], "p2p_dist": c["p2p_dist"][:, None],
+               "normal": c["normal"], "weights": c["weights"][..., None], "hdr_background_colours": bg, "directions_norm": dnorm,
+               "starts": starts, "ends": ends}
+        if want_vis:
+            out["visibility"] = s["visibility"]
+        return out

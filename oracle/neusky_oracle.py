@@ -532,3 +532,86 @@ def shade_points(points, normals, albedo, dirs, radiance, ddf_p, scalings, log2_
     v = compute_visibility(points, dirs, ddf_p, scalings, log2_T, ddf_radius, threshold, sigmoid_scale, only_upper)
     rad = lambertian_radiance(albedo, normals, dirs, radiance, v["visibility"])
     return rad, v
+
+
+# --------------------------------------------------------------------------------------
+# End-to-end eval render of a ray bundle (BASELINE.json configs 1 and 3)
+# NeuSkyFactoModel.forward -> get_outputs (neusky/models/neusky_model.py:425-443, 738-931), eval mode
+# --------------------------------------------------------------------------------------
+
+
+def pinhole_rays(H: int, W: int, fx: float, fy: float, cx: float, cy: float, c2w: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
+    """nerfstudio Cameras.generate_rays, perspective [NS-mem A.8]: pixel centres at +0.5,
+    d_cam = ((x-cx)/fx, -(y-cy)/fy, -1), d_world = R d_cam, directions_norm = |d_world|.
+    Returns origins [H*W,3], unit directions [H*W,3], directions_norm [H*W,1] (row-major)."""
+    ys, xs = torch.meshgrid(torch.arange(H, dtype=torch.float32) + 0.5, torch.arange(W, dtype=torch.float32) + 0.5, indexing="ij")
+    d_cam = torch.stack([(xs - cx) / fx, -(ys - cy) / fy, -torch.ones_like(xs)], -1).reshape(-1, 3)
+    d = d_cam @ c2w[:3, :3].T
+    dn = d.norm(dim=-1, keepdim=True)
+    return c2w[:3, 3].expand(H * W, 3).contiguous(), d / dn, dn
+
+
+def look_at_camera(eye, target=(0.0, 0.0, 0.0), up=(0.0, 0.0, 1.0)) -> Tensor:
+    """c2w [3,4] of a camera at `eye` looking at `target` (OpenGL convention: -z forward, +y up), z-up world."""
+    eye, target, up = (torch.tensor(v, dtype=torch.float32) for v in (eye, target, up))
+    f = torch.nn.functional.normalize(target - eye, dim=0)
+    r = torch.nn.functional.normalize(torch.linalg.cross(f, up), dim=0)
+    u = torch.linalg.cross(r, f)
+    return torch.cat([torch.stack([r, u, -f], 1), eye[:, None]], 1)
+
+
+def sphere_collider(origins: Tensor, directions: Tensor, radius: float = 1.0, near_plane: float = 0.05, training: bool = False) -> Tuple[Tensor, Tensor]:
+    """nerfstudio SphereCollider (centre 0) [NS-mem A.6] set at neusky_model.py:440."""
+    ox, oy, oz = origins[..., 0:1], origins[..., 1:2], origins[..., 2:3]
+    dx, dy, dz = directions[..., 0:1], directions[..., 1:2], directions[..., 2:3]
+    # explicit component arithmetic (no reductions): every op is a correctly rounded fp32 elementwise op, so the CPU
+    # oracle and the GPU host mirror produce bit-identical near / far
+    a = dx * dx + dy * dy + dz * dz
+    b = 2 * (ox * dx + oy * dy + oz * dz)
+    c = (ox * ox + oy * oy + oz * oz) - radius**2
+    disc = b * b - 4 * a * c
+    t0 = (-b - torch.sqrt(disc)) / (2 * a)
+    t1 = (-b + torch.sqrt(disc)) / (2 * a)
+    near = torch.clamp(t0, min=near_plane if training else 0.0)
+    far = torch.maximum(t1, near + 1e-6)
+    return torch.nan_to_num(near, nan=0.0), torch.nan_to_num(far, nan=0.0)
+
+
+def uniform_samples(near: Tensor, far: Tensor, S: int) -> Tuple[Tensor, Tensor]:
+    """nerfstudio UniformSampler, eval placement (no jitter) [NS-mem A.6]:
+    bins = linspace(0,1,S+1); euclid = bins*far + (1-bins)*near.  Returns starts, ends [R,S,1]."""
+    bins = torch.linspace(0.0, 1.0, S + 1, dtype=near.dtype, device=near.device)[None]
+    e = bins * far + (1 - bins) * near
+    return e[:, :-1, None], e[:, 1:, None]
+
+
+def render_rays(origins, directions, dnorm, S, sdf_p, ddf_p, reni_p, latent, scale, dirs, inv_s, log2_T=19,
+                ddf_radius=1.0, threshold=0.1, sigmoid_scale=25.0, rotation=None, chunk=256):
+    """Eval render of R rays of ONE camera with uniform sample placement.  Returns the outputs dict of
+    neusky_model.py:881-931 (rgb, albedo, accumulation, depth, p2p_dist, normal) plus visibility [R,D]."""
+    sca = hash_scalings()
+    radiance = reni_radiance_table(dirs, latent[None], scale.reshape(1), reni_p, rotation)[0]  # [D,3] (:488-518)
+    out = {k: [] for k in ("rgb", "albedo", "accumulation", "depth", "p2p_dist", "normal", "visibility", "weights")}
+    R = origins.shape[0]
+    near, far = sphere_collider(origins, directions)
+    starts_all, ends_all = uniform_samples(near, far, S)
+    mids = (starts_all + ends_all) / 2
+    smin, smax = mids.min(), mids.max()
+    for s in range(0, R, chunk):
+        o, d, dn = origins[s:s + chunk], directions[s:s + chunk], dnorm[s:s + chunk]
+        starts, ends = starts_all[s:s + chunk], ends_all[s:s + chunk]
+        r = o.shape[0]
+        x = o[:, None, :] + d[:, None, :] * starts  # get_start_positions (sdf_albedo_field.py:225)
+        f = sdf_field(x.reshape(-1, 3), sdf_p, sca, log2_T)
+        sdf, grad, alb = f["sdf"].reshape(r, S, 1), f["gradient"].reshape(r, S, 3), f["albedo"].reshape(r, S, 3)
+        bg = reni_radiance_table(d, latent[None], scale.reshape(1), reni_p, rotation)[0]  # :535-549
+        c = neus_composite(sdf, grad, alb, torch.zeros(r, S, 3), d, starts, ends, ends - starts, bg, dn, inv_s, 1.0, False)
+        p2p = torch.clip(c["p2p_raw"], smin, smax)   # DepthRenderer clips to the batch-global range [A.7]; here: the whole bundle
+        pts = surface_points(o, d, p2p, ddf_radius)
+        v = compute_visibility(pts, dirs, ddf_p, sca, log2_T, ddf_radius, threshold, sigmoid_scale)
+        normals = torch.nn.functional.normalize(grad, dim=-1)
+        rgb = lambertian_render(alb, normals, dirs, radiance, v["visibility"], bg, c["weights"], False)
+        for k, t in (("rgb", rgb), ("albedo", c["albedo"]), ("accumulation", c["accumulation"]), ("depth", p2p / dn), ("p2p_dist", p2p),
+                     ("normal", c["normal"]), ("visibility", v["visibility"]), ("weights", c["weights"])):
+            out[k].append(t)
+    return {k: torch.cat(v, 0) for k, v in out.items()}

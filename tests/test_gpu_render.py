@@ -1,0 +1,88 @@
+"""End-to-end eval render (BASELINE.json config 1 shape, reduced): sample placement -> K2 -> K3 -> RENI++ -> K4 -> sRGB
+on the GPU vs the CPU oracle's render_rays on the same seeded weights and camera.
+fp32 path (impl="simt" for K4): rgb / depth / normal / visibility within 1e-3 (north_star).  Tensor-core K4 path:
+stated separately (fp16 operands): rgb within 5e-3 absolute."""
+import pytest
+import torch
+
+from neusky_b200 import init as nb_init
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from neusky_b200 import _lib
+
+    _lib.load()
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def scene():
+    from oracle import neusky_oracle as O
+
+    log2_T = 15
+    sdf_p = nb_init.init_sdf_params(0, log2_T=log2_T, bias=0.45)      # a sphere of radius ~0.45 so that most rays hit a surface
+    sdf_p["deviation_network.variance"] = torch.tensor(0.3)           # inv_s = e^3
+    ddf_p = nb_init.init_ddf_params(1, final_gain=8.0, log2_T=log2_T)
+    reni_p = nb_init.init_reni_params(2)
+    H = W = 12
+    c2w = O.look_at_camera((0.0, -0.9, 0.25))
+    o, d, dn = O.pinhole_rays(H, W, float(W), float(W), W / 2, H / 2, c2w)
+    dirs = O.icosphere_directions(100)
+    Z = torch.randn(100, 3, generator=torch.Generator().manual_seed(3))
+    S = 40
+    with torch.no_grad():
+        ref = O.render_rays(o, d, dn, S, sdf_p, ddf_p, reni_p, Z, torch.zeros(()), dirs, float(torch.exp(torch.tensor(3.0))), log2_T=log2_T)
+    return dict(log2_T=log2_T, sdf_p=sdf_p, ddf_p=ddf_p, reni_p=reni_p, H=H, W=W, c2w=c2w, dirs=dirs, Z=Z, S=S, ref=ref, o=o, d=d, dn=dn)
+
+
+def _render(dev, sc, impl):
+    from neusky_b200.render import RayRenderer
+
+    r = RayRenderer(sc["sdf_p"], sc["ddf_p"], sc["reni_p"], device=dev, log2_T=sc["log2_T"], impl=impl)
+    r.set_directions(sc["dirs"])
+    o, d, dn = (t.to(dev) for t in (sc["o"], sc["d"], sc["dn"]))   # the ray bundle is an INPUT of the path (neusky_model.py:425)
+    out = r.render(o, d, dn, sc["S"], sc["Z"].to(dev), torch.zeros((), device=dev), want_vis=True)
+    torch.cuda.synchronize()
+    return o, d, dn, {k: v.cpu() for k, v in out.items()}
+
+
+def test_sample_placement_bit_exact(dev, scene):
+    from oracle import neusky_oracle as O
+
+    o, d, dn, out = _render(dev, scene, "simt")
+    near, far = O.sphere_collider(scene["o"], scene["d"])
+    st, en = O.uniform_samples(near, far, scene["S"])
+    assert torch.equal(out["starts"], st[..., 0]) and torch.equal(out["ends"], en[..., 0]), "sample placement must be bit-exact"
+
+
+def test_pinhole_rays_match_oracle(dev, scene):
+    from neusky_b200.render import pinhole_rays
+
+    o, d, dn = pinhole_rays(scene["H"], scene["W"], float(scene["W"]), float(scene["W"]), scene["W"] / 2, scene["H"] / 2, scene["c2w"], dev)
+    assert torch.equal(o.cpu(), scene["o"])
+    assert torch.allclose(d.cpu(), scene["d"], rtol=0, atol=1e-6) and torch.allclose(dn.cpu(), scene["dn"], rtol=1e-6, atol=0)
+
+
+def test_render_fp32_path_vs_oracle(dev, scene):
+    _, _, _, out = _render(dev, scene, "simt")
+    ref = scene["ref"]
+    assert float(ref["accumulation"].max()) > 0.9 and float(ref["accumulation"].min()) < 0.1   # the camera sees surface and sky
+    for k, tol in (("accumulation", 1e-3), ("p2p_dist", 1e-3), ("depth", 1e-3), ("normal", 1e-3), ("albedo", 1e-3), ("visibility", 1e-3), ("rgb", 1e-3)):
+        err = (out[k] - ref[k]).abs().max() / ref[k].abs().max().clamp_min(1e-6)
+        assert float(err) <= tol, (k, float(err))
+    assert torch.allclose(out["weights"], ref["weights"], rtol=1e-3, atol=1e-5)
+
+
+def test_render_tensor_core_path_vs_oracle(dev, scene):
+    _, _, _, out = _render(dev, scene, "tc")
+    ref = scene["ref"]
+    assert float((out["rgb"] - ref["rgb"]).abs().max()) <= 5e-3
+    assert float((out["visibility"] - ref["visibility"]).abs().max()) <= 2e-2
+    for k in ("accumulation", "depth", "normal", "albedo"):     # these do not go through the fp16 kernel
+        err = (out[k] - ref[k]).abs().max() / ref[k].abs().max().clamp_min(1e-6)
+        assert float(err) <= 1e-3, (k, float(err))
