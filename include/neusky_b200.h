@@ -61,7 +61,14 @@ int nsk_hash_indices(const float* x, int64_t n, const float* scalings, int num_l
  *   hash_table [L*T,2]; outputs sdf [n], grad [n,3] (NULL = skip the reverse pass), albedo [n,3] (NULL = skip the
  *   colour network), geo [n,256] (NULL = do not write the geometry feature).
  * nsk_sdf_field_simt_fwd: exact fp32 CUDA-core path.
+ * nsk_sdf_field_tc_fwd  : tcgen05/TMEM tensor-core path (fp16 operands, fp32 accumulate; x enters as fp16 hi+lo, the sdf
+ *                         row of the last layer is an fp32 dot product).  sdf_weights = nsk pack "sdf tc" blob
+ *                         (neusky_b200.packing.pack_sdf_tc); always writes sdf, grad and albedo.
  * ------------------------------------------------------------------------------------------- */
+int64_t nsk_sdf_tc_weights_bytes(void);
+int nsk_sdf_field_tc_fwd(const float* x, int64_t n, const void* sdf_weights, const float* hash_table,
+                         const float* scalings, int num_levels, int log2_T, float* sdf, float* grad, float* albedo,
+                         void* stream);
 int64_t nsk_sdf_simt_weights_floats(void);
 int nsk_sdf_field_simt_fwd(const float* x, int64_t n, const float* sdf_weights, const float* hash_table,
                            const float* scalings, int num_levels, int log2_T, float* sdf, float* grad, float* albedo,

@@ -86,11 +86,18 @@ def sdf_field(x: Tensor, blob: Tensor, hash_table: Tensor, scalings: Tensor, log
     hash_table = _chk("hash_table", hash_table, shape=(L << log2_T, 2))
     scalings = _chk("scalings", scalings)
     lib = _lib.load()
-    if impl != "simt":
-        raise ValueError(f"impl must be 'simt', got {impl!r}")
-    blob = _chk("blob", blob, shape=(lib.nsk_sdf_simt_weights_floats(),))
     f = dict(device=x.device, dtype=torch.float32)
     sdf = torch.empty((n,), **f)
+    if impl == "tc":
+        if want_geo:
+            raise ValueError("sdf_field: the tensor-core path keeps the geometry feature on chip (want_geo needs impl='simt')")
+        blob = _chk("blob", blob, dtype=torch.uint8, shape=(lib.nsk_sdf_tc_weights_bytes(),))
+        grad, alb = torch.empty((n, 3), **f), torch.empty((n, 3), **f)
+        _lib.check(lib.nsk_sdf_field_tc_fwd(_ptr(x2), c_int64(n), _ptr(blob), _ptr(hash_table), _ptr(scalings), c_int(L), c_int(log2_T), _ptr(sdf), _ptr(grad), _ptr(alb), _stream(x)), "nsk_sdf_field_tc_fwd")
+        return {"sdf": sdf.reshape(*lead, 1), "gradient": grad.reshape(*lead, 3), "albedo": alb.reshape(*lead, 3)}
+    if impl != "simt":
+        raise ValueError(f"impl must be 'tc' or 'simt', got {impl!r}")
+    blob = _chk("blob", blob, shape=(lib.nsk_sdf_simt_weights_floats(),))
     grad = torch.empty((n, 3), **f) if want_grad else None
     alb = torch.empty((n, 3), **f) if want_albedo else None
     geo = torch.empty((n, 256), **f) if want_geo else None

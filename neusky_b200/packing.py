@@ -167,3 +167,48 @@ def pack_ddf_tc(p: Dict[str, Tensor]) -> Tensor:
     vec[:256] = f32("ddf.final_layer.weight").flatten()
     vec[256] = f32("ddf.final_layer.bias").flatten()[0]
     return torch.cat([stream, vec.view(torch.uint8)]).contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# Tensor-core blob for csrc/sdf_field_tc.cu: one region of fp16 operand stages per GEMM (the order and the stage
+# shapes of the segment table in the kernel), then the fp32 sdf row of the last geo layer.
+# ------------------------------------------------------------------------------------------------
+SDF_TC_STREAM_BYTES = 256 * 80 * 2 + 3 * 256 * 272 * 2 + 256 * 256 * 2 + 80 * 256 * 2 + 256 * (48 + 272) * 2 + 16 * 272 * 2
+
+
+def pack_sdf_tc(p: Dict[str, Tensor]) -> Tensor:
+    """uint8 blob [SDF_TC_STREAM_BYTES + 260*4] for nsk_sdf_field_tc_fwd (weight_norm folded)."""
+    W0, W1, W2 = (fold_weight_norm(p, f"glin{l}") for l in range(3))
+    C0, C1, C2 = (fold_weight_norm(p, f"clin{l}") for l in range(3))
+    if tuple(W0.shape) != (256, 71) or tuple(W1.shape) != (256, 256) or tuple(W2.shape) != (257, 256) or tuple(C0.shape) != (256, 295) or tuple(C2.shape) != (3, 256):
+        raise ValueError("pack_sdf_tc: expected the NeuSky SDFAlbedoField shape (71->256->256->257, 295->256->256->3)")
+    dev = W0.device
+    f32 = lambda k: p[k].to(torch.float32).flatten()
+    z = lambda *shape: torch.zeros(shape, dtype=torch.float32, device=dev)
+    b2 = f32("glin2.bias")
+    st = []
+    # G0 / G0': K = [x_hi 3 | PE 36 | feat 32 | bias hi, lo | x_lo 3 | 0 x4] = 80
+    G0 = _with_bias_cols(W0, f32("glin0.bias"), 80)
+    G0[:, 73:76] = W0[:, 0:3]
+    st += _stages(G0, 2, 32, 16)
+    st += _stages(_with_bias_cols(W1, f32("glin1.bias"), 272), 8, 32, 16)          # G1
+    st += _stages(_with_bias_cols(W2[1:], b2[1:], 272), 8, 32, 16)                 # G2 (geo feature rows)
+    st += _stages(W1.t().contiguous(), 8, 32, 0)                                   # B1: B[n=j][k=i] = W1[i][j]
+    B0 = z(80, 256)                                                                # B0: rows [x 3 | PE 36 | 0 | feat 32 | 0 x8]
+    B0[0:39] = W0[:, 0:39].t()
+    B0[40:72] = W0[:, 39:71].t()
+    st += _stages(B0, 4, 64, 0)
+    Ca = z(256, 48)                                                                # C0: IN columns 0..47 (x, PE; feat columns get zeros)
+    Ca[:, 0:39] = C0[:, 0:39]
+    st += _stages(Ca, 1, 32, 16)
+    st += _stages(_with_bias_cols(C0[:, 39:], f32("clin0.bias"), 272), 8, 32, 16)
+    st += _stages(_with_bias_cols(C1, f32("clin1.bias"), 272), 8, 32, 16)          # C1
+    Cc = z(16, 272)                                                                # C2: 3 real rows
+    Cc[0:3] = _with_bias_cols(C2, f32("clin2.bias"), 272)
+    st += _stages(Cc, 1, 272, 0)
+    stream = torch.cat(st).contiguous().view(torch.uint8)
+    assert stream.numel() == SDF_TC_STREAM_BYTES, (stream.numel(), SDF_TC_STREAM_BYTES)
+    vec = z(260)
+    vec[:256] = W2[0]
+    vec[256] = b2[0]
+    return torch.cat([stream, vec.view(torch.uint8)]).contiguous()

@@ -167,7 +167,7 @@ class RayRenderer:
 
     def set_sdf_weights(self, sdf_params: Dict[str, Tensor]) -> None:
         p = {k: v.to(self.device) for k, v in sdf_params.items() if k.startswith(("glin", "clin"))}
-        self.sdf_blob = packing.pack_sdf_simt(p)
+        self.sdf_blob = packing.pack_sdf_tc(p) if self.sdf_impl == "tc" else packing.pack_sdf_simt(p)
         var = sdf_params["deviation_network.variance"]
         self.inv_s = float(torch.exp(10.0 * var.detach().float().cpu()).clip(1e-6, 1e6))   # LearnedVariance.get_variance [SURVEY A.4]
 

@@ -83,6 +83,19 @@ x = ((torch.rand(n, 3, generator=g) * 2 - 1) * 0.6).to(dev)
 ms = timeit(lambda: ops.sdf_field(x, blob, tab, sc, 19), iters=3)
 report("sdf_field_simt (K2, exact fp32 CUDA cores)", "tensor", ms, n * 881664.0, 881664, n, {"note": "fp32 FMA path; fraction is against the dense fp16/bf16 tensor peak"})
 
+blob_tc = packing.pack_sdf_tc({k: v.to(dev) for k, v in p.items()})
+n = 8_000_000
+x = ((torch.rand(n, 3, generator=g) * 2 - 1) * 0.6).to(dev)
+ms = timeit(lambda: ops.sdf_field(x, blob_tc, tab, sc, 19, impl="tc"), iters=3)
+report("sdf_field_tc (K2, tcgen05 fp16xfp16->fp32), random points", "tensor", ms, n * 881664.0, 881664, n)
+R, S = 62_500, 128
+d = torch.nn.functional.normalize(torch.randn(R, 3, generator=g), dim=-1).to(dev)
+t = torch.linspace(0.05, 0.9, S, device=dev)
+xr = (torch.tensor([0.0, -0.3, 0.1], device=dev) + d[:, None, :] * t[None, :, None] * 0.7).reshape(-1, 3).contiguous()
+ms = timeit(lambda: ops.sdf_field(xr, blob_tc, tab, sc, 19, impl="tc"), iters=3)
+report("sdf_field_tc (K2), ray-ordered samples", "tensor", ms, xr.shape[0] * 881664.0, 881664, xr.shape[0])
+del x, xr
+
 # ---- RENI++ decode: 524,544 FLOP per (camera, direction) ------------------------------------------------
 rp = nb_init.init_reni_params(1)
 rblob = packing.pack_reni({k: v.to(dev) for k, v in rp.items()})

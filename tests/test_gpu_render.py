@@ -40,10 +40,10 @@ def scene():
     return dict(log2_T=log2_T, sdf_p=sdf_p, ddf_p=ddf_p, reni_p=reni_p, H=H, W=W, c2w=c2w, dirs=dirs, Z=Z, S=S, ref=ref, o=o, d=d, dn=dn)
 
 
-def _render(dev, sc, impl):
+def _render(dev, sc, impl, sdf_impl="simt"):
     from neusky_b200.render import RayRenderer
 
-    r = RayRenderer(sc["sdf_p"], sc["ddf_p"], sc["reni_p"], device=dev, log2_T=sc["log2_T"], impl=impl)
+    r = RayRenderer(sc["sdf_p"], sc["ddf_p"], sc["reni_p"], device=dev, log2_T=sc["log2_T"], impl=impl, sdf_impl=sdf_impl)
     r.set_directions(sc["dirs"])
     o, d, dn = (t.to(dev) for t in (sc["o"], sc["d"], sc["dn"]))   # the ray bundle is an INPUT of the path (neusky_model.py:425)
     out = r.render(o, d, dn, sc["S"], sc["Z"].to(dev), torch.zeros((), device=dev), want_vis=True)
@@ -86,3 +86,14 @@ def test_render_tensor_core_path_vs_oracle(dev, scene):
     for k in ("accumulation", "depth", "normal", "albedo"):     # these do not go through the fp16 kernel
         err = (out[k] - ref[k]).abs().max() / ref[k].abs().max().clamp_min(1e-6)
         assert float(err) <= 1e-3, (k, float(err))
+
+
+def test_render_all_tensor_core_vs_oracle(dev, scene):
+    """K2 and K4 both on tcgen05 (fp16 operands): the throughput configuration.  Stated tolerances: rgb 1e-2 absolute,
+    accumulation / depth 5e-3 relative, rendered normal 1e-2 absolute."""
+    _, _, _, out = _render(dev, scene, "tc", "tc")
+    ref = scene["ref"]
+    errs = {k: float((out[k] - ref[k]).abs().max()) for k in ("rgb", "accumulation", "depth", "normal", "albedo")}
+    print(errs)
+    assert errs["rgb"] <= 1e-2 and errs["normal"] <= 1e-2 and errs["albedo"] <= 1e-2
+    assert errs["accumulation"] <= 5e-3 and errs["depth"] <= 5e-3 * float(ref["depth"].abs().max())
