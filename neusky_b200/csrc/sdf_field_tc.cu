@@ -403,50 +403,63 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_field_tc_kernel(const Para
     const float TWO_PI = 6.283185307179586f;
     uint32_t ph_empty = 0, ph_b0 = 0;
 
-    // forward features of one sample -> 40 packed words (the IN row)
+    // sin / cos of 2 pi x 2^f with the period removed exactly first (x 2^f is exact in fp32), then the fast SFU path
+    auto pe_sincos = [&](float xd, int f, float& sn, float& cs) {
+      float t = xd * (float)(1 << f);
+      t -= rintf(t);
+      __sincosf(TWO_PI * t, &sn, &cs);
+    };
+    // 4 hash levels per batch: 32 independent 8-byte gathers in flight per thread
+    auto gather4 = [&](const float (&pos)[3], int lev0, float2 (&f)[4][8], float (&o)[4][3]) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float sc = __ldg(P.scalings + lev0 + u);
+        uint32_t idx[8];
+        hash_corners(__fmul_rn(pos[0], sc), __fmul_rn(pos[1], sc), __fmul_rn(pos[2], sc), mask, idx, o[u][0], o[u][1], o[u][2]);
+        const float2* tl = P.table + ((size_t)(lev0 + u) << P.log2_T);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) f[u][c] = __ldg(tl + idx[c]);
+      }
+    };
+
+    // forward features of one sample -> 40 packed words (the IN row):
+    // [x_hi 3 | PE sin 18 | PE cos 18 | feat 32 | 1, 1 | x_lo 3 | 0 x4]
     auto features = [&](int64_t sample, uint32_t (&w)[40]) {
       const int64_t s = min(sample, P.n - 1);
       const float xv[3] = {__ldg(P.x + s * 3), __ldg(P.x + s * 3 + 1), __ldg(P.x + s * 3 + 2)};
       float pos[3], J[9];
       sdf_contract(xv, pos, J);
-      float h[80];
+      float h[40];   // columns 0..39 (x, PE, feat0) assembled as floats, the rest packed on the fly
       float xl[3];
 #pragma unroll
       for (int d = 0; d < 3; ++d) {
         const float hi = __half2float(__float2half_rn(xv[d]));
         h[d] = hi;
         xl[d] = xv[d] - hi;
-        const float a = TWO_PI * xv[d];
 #pragma unroll
-        for (int f = 0; f < 6; ++f) {
-          float sn, cs;
-          sincosf(a * (float)(1 << f), &sn, &cs);
-          h[3 + d * 6 + f] = sn;
-          h[3 + 18 + d * 6 + f] = cs;
+        for (int f = 0; f < 6; ++f) pe_sincos(xv[d], f, h[3 + d * 6 + f], h[3 + 18 + d * 6 + f]);
+      }
+      float carry = 0.f;   // feature waiting for its pair partner (features start at the odd column 39)
+#pragma unroll
+      for (int lev0 = 0; lev0 < SDF_LEVELS; lev0 += 4) {
+        float2 f[4][8];
+        float o[4][3];
+        gather4(pos, lev0, f, o);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float2 r = hash_interp(f[u], o[u][0], o[u][1], o[u][2]);
+          const int lev = lev0 + u;
+          if (lev == 0) h[39] = r.x;
+          else w[19 + lev] = pack_h2(carry, r.x);       // columns 38+2lev, 39+2lev
+          carry = r.y;                                    // column 40+2lev
         }
       }
 #pragma unroll
-      for (int lev = 0; lev < SDF_LEVELS; lev += 2) {
-        float2 f[2][8];
-        float ox[2], oy[2], oz[2];
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const float sc = __ldg(P.scalings + lev + u);
-          uint32_t idx[8];
-          hash_corners(__fmul_rn(pos[0], sc), __fmul_rn(pos[1], sc), __fmul_rn(pos[2], sc), mask, idx, ox[u], oy[u], oz[u]);
-          const float2* tl = P.table + ((size_t)(lev + u) << P.log2_T);
-#pragma unroll
-          for (int c = 0; c < 8; ++c) f[u][c] = __ldg(tl + idx[c]);
-        }
-        const float2 r0 = hash_interp(f[0], ox[0], oy[0], oz[0]);
-        const float2 r1 = hash_interp(f[1], ox[1], oy[1], oz[1]);
-        h[39 + 2 * lev] = r0.x; h[40 + 2 * lev] = r0.y; h[41 + 2 * lev] = r1.x; h[42 + 2 * lev] = r1.y;
-      }
-      h[71] = 1.0f; h[72] = 1.0f;                      // bias hi / lo columns
-      h[73] = xl[0]; h[74] = xl[1]; h[75] = xl[2];     // x low parts (same weights as columns 0..2)
-      h[76] = h[77] = h[78] = h[79] = 0.f;
-#pragma unroll
-      for (int i = 0; i < 40; ++i) w[i] = pack_h2(h[2 * i], h[2 * i + 1]);
+      for (int i = 0; i < 20; ++i) w[i] = pack_h2(h[2 * i], h[2 * i + 1]);
+      w[35] = pack_h2(carry, 1.0f);          // columns 70 (feat 31), 71 (bias hi)
+      w[36] = pack_h2(1.0f, xl[0]);          // columns 72 (bias lo), 73
+      w[37] = pack_h2(xl[1], xl[2]);         // columns 74, 75
+      w[38] = 0u; w[39] = 0u;
     };
     auto write_in = [&](const uint32_t (&w)[40]) {
       uint8_t* d = smem + OFF_IN + row * 16;
@@ -463,8 +476,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_field_tc_kernel(const Para
     }
     for (int64_t tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
       const int64_t next = tile + gridDim.x;
-      if (next < P.n_tiles) features(next * TM + row, w);
-      // ---- gradient of this tile: g0 = d sdf / d(layer-0 input) from TMEM (B0) -------------------------------
+      if (next < P.n_tiles) features(next * TM + row, w);       // overlaps the MMA chain of `tile`
+      // ---- g0 = d sdf / d(layer-0 input) of this tile, straight from TMEM (B0) -----------------------------------
       mbar_wait(bars + 8 * B_B0DONE, ph_b0); ph_b0 ^= 1;
       tc_fence_after();
       const int64_t sample = tile * TM + row;
@@ -477,65 +490,64 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_field_tc_kernel(const Para
 #pragma unroll
         for (int i = 0; i < 5; ++i) tmem_ld8(tmem + TM_ACC_B + lane_off + i * 8, g[i]);
         tmem_ld_wait();
-        const float* gf = reinterpret_cast<const float*>(&g[0][0]);
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
-          float acc = gf[d];
-          const float a = TWO_PI * xv[d];
+          float acc = __uint_as_float(g[0][d]);
 #pragma unroll
           for (int f = 0; f < 6; ++f) {
             float sn, cs;
-            sincosf(a * (float)(1 << f), &sn, &cs);
-            acc += TWO_PI * (float)(1 << f) * (cs * gf[3 + d * 6 + f] - sn * gf[3 + 18 + d * 6 + f]);
+            pe_sincos(xv[d], f, sn, cs);
+            const int cs_i = 3 + d * 6 + f, cc_i = 3 + 18 + d * 6 + f;
+            acc += TWO_PI * (float)(1 << f) * (cs * __uint_as_float(g[cs_i >> 3][cs_i & 7]) - sn * __uint_as_float(g[cc_i >> 3][cc_i & 7]));
           }
           gx[d] = acc;
         }
       }
-      float gfe[32];
-      {
-        uint32_t g[4][8];
+      uint32_t gfe[4][8];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) tmem_ld8(tmem + TM_ACC_B + lane_off + 40 + i * 8, g[i]);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) gfe[i] = __uint_as_float(g[i >> 3][i & 7]);
-      }
+      for (int i = 0; i < 4; ++i) tmem_ld8(tmem + TM_ACC_B + lane_off + 40 + i * 8, gfe[i]);
+      tmem_ld_wait();
       tc_fence_before();
-      mbar_arrive(bars + 8 * B_PGDONE);     // TMEM columns of B0 may be overwritten (C1)
+      mbar_arrive(bars + 8 * B_PGDONE);     // the TMEM columns of B0 may be overwritten (C1)
+      // ---- hand the next tile's inputs over as soon as C0 of this tile has consumed IN ------------------------------
+      if (next < P.n_tiles) {
+        mbar_wait(bars + 8 * B_INEMPTY, ph_empty); ph_empty ^= 1;
+        write_in(w);
+      }
+      // ---- chain rule through the trilinear hash interpolation and the contraction (overlaps the next tile's MMAs) ----
       {
         float pos[3], J[9];
         sdf_contract(xv, pos, J);
         float a0 = 0.f, a1 = 0.f, a2 = 0.f;
 #pragma unroll
-        for (int lev = 0; lev < SDF_LEVELS; ++lev) {
-          const float sc = __ldg(P.scalings + lev);
-          uint32_t idx[8];
-          float ox, oy, oz;
-          hash_corners(__fmul_rn(pos[0], sc), __fmul_rn(pos[1], sc), __fmul_rn(pos[2], sc), mask, idx, ox, oy, oz);
-          const float2* tl = P.table + ((size_t)lev << P.log2_T);
-          float fa[8], fb[8];
+        for (int lev0 = 0; lev0 < SDF_LEVELS; lev0 += 4) {
+          float2 f[4][8];
+          float o[4][3];
+          gather4(pos, lev0, f, o);
 #pragma unroll
-          for (int c = 0; c < 8; ++c) { const float2 v = __ldg(tl + idx[c]); fa[c] = v.x; fb[c] = v.y; }
-          float da[3], db[3];
-          hash_interp_grad(fa, ox, oy, oz, da);
-          hash_interp_grad(fb, ox, oy, oz, db);
-          const float ga = gfe[2 * lev], gb = gfe[2 * lev + 1];
-          a0 += sc * (da[0] * ga + db[0] * gb);
-          a1 += sc * (da[1] * ga + db[1] * gb);
-          a2 += sc * (da[2] * ga + db[2] * gb);
+          for (int u = 0; u < 4; ++u) {
+            const int lev = lev0 + u;
+            const float sc = __ldg(P.scalings + lev);
+            float fa[8], fb[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) { fa[c] = f[u][c].x; fb[c] = f[u][c].y; }
+            float da[3], db[3];
+            hash_interp_grad(fa, o[u][0], o[u][1], o[u][2], da);
+            hash_interp_grad(fb, o[u][0], o[u][1], o[u][2], db);
+            const float ga = __uint_as_float(gfe[(2 * lev) >> 3][(2 * lev) & 7]), gb = __uint_as_float(gfe[(2 * lev + 1) >> 3][(2 * lev + 1) & 7]);
+            a0 += sc * (da[0] * ga + db[0] * gb);
+            a1 += sc * (da[1] * ga + db[1] * gb);
+            a2 += sc * (da[2] * ga + db[2] * gb);
+          }
         }
         gx[0] += J[0] * a0 + J[3] * a1 + J[6] * a2;
         gx[1] += J[1] * a0 + J[4] * a1 + J[7] * a2;
         gx[2] += J[2] * a0 + J[5] * a1 + J[8] * a2;
       }
       if (sample < P.n) { P.grad[sample * 3] = gx[0]; P.grad[sample * 3 + 1] = gx[1]; P.grad[sample * 3 + 2] = gx[2]; }
-      // ---- hand the next tile's inputs over once C0 of this tile has consumed IN --------------------------------
-      if (next < P.n_tiles) {
-        mbar_wait(bars + 8 * B_INEMPTY, ph_empty); ph_empty ^= 1;
-        write_in(w);
-      }
     }
   }
+
 
   __syncwarp();
   tc_fence_before();
