@@ -54,13 +54,15 @@ def _peaks():
     return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "source": "fallback"}
 
 
-def _ncu_traffic():
-    """dram bytes per launch of the K4 kernel from the committed `ncu --set full` summary, if any."""
+def _ncu_traffic(pairs: int):
+    """dram bytes per launch of the K4 kernel from the committed ncu capture (profiles/k4_ncu_summary.json); only
+    reported when the capture was taken at this launch size."""
     path = os.path.join(ROOT, "profiles", "k4_ncu_summary.json")
     if os.path.exists(path):
         try:
             with open(path) as f:
-                return json.load(f).get("dram_bytes_per_launch")
+                d = json.load(f)
+            return d.get("dram_bytes_per_launch") if int(d.get("pairs_per_launch", -1)) == pairs else None
         except Exception:
             return None
     return None
@@ -130,16 +132,10 @@ def _latents():
 
 
 def _equirect_directions(width: int):
-    """EquirectangularSampler(width) directions, z-up (ns_reni illumination_samplers.py:373-432 through nerfstudio's
-    equirectangular ray generation)."""
-    H, W = width // 2, width
-    ys, xs = torch.meshgrid(torch.arange(H, dtype=torch.float32) + 0.5, torch.arange(W, dtype=torch.float32) + 0.5, indexing="ij")
-    u = (xs - float(W // 2)) / float(H)
-    v = -(ys - float(H // 2)) / float(H)
-    theta, phi = -torch.pi * u, torch.pi * (0.5 - v)
-    d_cam = torch.stack([-torch.sin(theta) * torch.sin(phi), torch.cos(phi), -torch.cos(theta) * torch.sin(phi)], -1).reshape(-1, 3)
-    d = d_cam @ torch.tensor([[1.0, 0, 0], [0, 0, 1.0], [0, 1.0, 0]]).T
-    return d / d.norm(dim=-1, keepdim=True)
+    """EquirectangularSampler(width) directions, z-up (ns_reni illumination_samplers.py:373-432)."""
+    from neusky_b200.samplers import EquirectangularSampler
+
+    return EquirectangularSampler(width)().frustums.directions
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
@@ -206,6 +202,67 @@ def _config(args, world):
             "k4_numerics": "fp16 operands, fp32 accumulate (tcgen05 kind::f16), fp32 epilogues"}
 
 
+# ------------------------------------------------------------------------------------------ eval-render arm (configs[2])
+def eval_arm(args):
+    """Full-image eval render of a 1280x720 synthetic camera, S uniform samples per ray, D = 642 icosphere directions
+    (308 through the DDF), ray tiles round-robin over the ranks, per-ray outputs gathered at the end (strong scaling:
+    the image is fixed).  Supplementary line: the driver's headline is the default workload."""
+    rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    import math
+    from neusky_b200 import _lib, init as nb_init, samplers
+    from neusky_b200.render import RayRenderer, pinhole_rays, render_image
+
+    sdf_p = nb_init.init_sdf_params(SEED_W + 2, bias=0.45)
+    sdf_p["deviation_network.variance"] = torch.tensor(0.3)
+    r = RayRenderer(sdf_p, nb_init.init_ddf_params(SEED_W), nb_init.init_reni_params(SEED_W + 1), device=dev)
+    r.set_directions(samplers.IcosahedronSampler(512)().frustums.directions)
+    H, W = args.height, args.width
+    fx = (W / 2) / math.tan(math.radians(30.0))
+    eye = torch.tensor([0.0, -0.9, 0.25]); f = torch.nn.functional.normalize(-eye, dim=0)
+    rt = torch.nn.functional.normalize(torch.linalg.cross(f, torch.tensor([0.0, 0.0, 1.0])), dim=0)
+    c2w = torch.cat([torch.stack([rt, torch.linalg.cross(rt, f), -f], 1), eye[:, None]], 1)
+    o, d, dn = pinhole_rays(H, W, fx, fx, W / 2, H / 2, c2w, dev)
+    Z, sc = (t.to(dev) for t in _latents())
+    Dp = int(r.shader.mask.sum())
+
+    def step():
+        return render_image(r, o, d, dn, args.samples, Z[0], sc[0], tile=args.tile)
+
+    for _ in range(args.warmup):
+        step()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    l0 = _lib.launches
+    ts = []
+    for _ in range(args.steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); out = step(); e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) / 1e3)
+    t = sum(ts)
+    if dist is not None:
+        tt = torch.tensor([t], device=dev, dtype=torch.float64); dist.all_reduce(tt, op=dist.ReduceOp.MAX); t = float(tt.item())
+    if rank == 0:
+        n = H * W
+        acc = out["accumulation"]
+        print(json.dumps({"metric": METRIC, "value": n * args.steps / t, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                          "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f16xf16->f32", "data": "synthetic",
+                          "config": {"workload": f"BASELINE.json configs[2]: full-image eval render {W}x{H}, {args.samples} uniform samples/ray, 642 icosphere directions (D'={Dp}), "
+                                                 f"ray tiles of {args.tile} round-robin over {world} GPU(s), outputs gathered", "parallelism": f"ray tiles x{world}, weights replicated",
+                                     "l2": "inputs (118 M samples/frame) exceed L2", "surface_coverage": float((acc > 0.5).float().mean())},
+                          "gpu_launches": _lib.launches - l0, "pairs_per_frame": n * Dp, "samples_per_frame": n * args.samples}), flush=True)
+    if dist is not None:
+        dist.barrier(); dist.destroy_process_group()
+
+
 # ------------------------------------------------------------------------------------------ GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -215,9 +272,18 @@ def main():
     ap.add_argument("--points", type=int, default=1_000_000)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="shade", choices=["shade", "eval"],
+                    help="shade = BASELINE.json configs[1] (the headline line); eval = configs[2], a supplementary full-image render line")
+    ap.add_argument("--height", type=int, default=720)
+    ap.add_argument("--width", type=int, default=1280)
+    ap.add_argument("--samples", type=int, default=128)
+    ap.add_argument("--tile", type=int, default=16384)
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)
+        return
+    if args.workload == "eval":
+        eval_arm(args)
         return
 
     rank = int(os.environ.get("RANK", "0"))
@@ -310,7 +376,7 @@ def main():
                     "api": "neusky_b200.render.SkyShader.shade_points_host", "steps": e2e_steps},
             "gpu_launches": launches,
             "roofline": {"kernel": "sky_shade_tc_kernel", "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": _ncu_traffic(), "peak_source": f"{peaks['source']} dense bf16/fp16 cuBLAS, sustained ({peaks['tf_burst']:.0f} burst)",
+                         "traffic": _ncu_traffic(pairs), "peak_source": f"{peaks['source']} dense bf16/fp16 cuBLAS, sustained ({peaks['tf_burst']:.0f} burst)",
                          "frac_of_burst": achieved / peaks["tf_burst"], "pairs_per_launch": pairs, "flop_per_pair": FLOP_PER_PAIR,
                          "ms_per_launch": 1e3 * k4_s, "k4_share_of_step": k4_s * args.steps / t_dev if world == 1 else None},
             "clocks": clocks, "wall_s_timed_region": wall,

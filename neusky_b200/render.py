@@ -156,7 +156,7 @@ class RayRenderer:
     one camera (one latent code) per call; outputs use the reference's keys (:881-931)."""
 
     def __init__(self, sdf_params: Dict[str, Tensor], ddf_params: Dict[str, Tensor], reni_params: Dict[str, Tensor], device="cuda",
-                 log2_T: int = 19, num_levels: int = 16, ddf_radius: float = 1.0, impl: str = "tc", sdf_impl: str = "simt"):
+                 log2_T: int = 19, num_levels: int = 16, ddf_radius: float = 1.0, impl: str = "tc", sdf_impl: str = "tc"):
         self.device = torch.device(device)
         self.log2_T = log2_T
         self.sdf_impl = sdf_impl
@@ -200,3 +200,40 @@ class RayRenderer:
         if want_vis:
             out["visibility"] = s["visibility"]
         return out
+
+
+def global_steps_minmax(origins: Tensor, directions: Tensor, S: int) -> Tensor:
+    """[min, max] of the sample mid-points over a whole ray bundle (what nerfstudio's DepthRenderer clips to when the
+    bundle is rendered in one batch), from the first and last bins only -- same arithmetic as uniform_samples, so the
+    values are bit-identical to a full placement.  Lets tiles / ranks clip to an image-global range."""
+    near, far = sphere_collider(origins, directions)
+    bins = torch.linspace(0.0, 1.0, S + 1, dtype=near.dtype)[None].to(near.device)
+    sel = bins[:, [0, 1, S - 1, S]]
+    e = sel * far + (1 - sel) * near
+    return torch.stack([((e[:, 0] + e[:, 1]) / 2).min(), ((e[:, 2] + e[:, 3]) / 2).max()]).contiguous()
+
+
+def render_image(renderer: "RayRenderer", origins: Tensor, directions: Tensor, dnorm: Tensor, S: int, latent: Tensor, scale: Tensor,
+                 tile: int = 16384, keys=("rgb", "albedo", "normal", "depth", "p2p_dist", "accumulation"), group=None, **kw) -> Dict[str, Tensor]:
+    """Eval render of a full camera (BASELINE.json config 3): the H*W rays are cut into tiles of `tile` rays, tile i is
+    rendered by rank i mod world (weights replicated, no data-path collective) and the per-ray outputs are gathered
+    once at the end (neusky_b200/parallel.py).  Single process: a plain loop over tiles.  The reference renders the
+    same image serially in 256-ray chunks on one GPU (neusky/models/neusky_model.py:1413-1437)."""
+    from . import parallel
+
+    n = origins.shape[0]
+    mm = global_steps_minmax(origins, directions, S)
+
+    def fn(idx: Tensor) -> Dict[str, Tensor]:
+        outs = {k: [] for k in keys}
+        for a in range(0, idx.shape[0], tile):
+            sel = idx[a:a + tile]
+            o = renderer.render(origins[sel].contiguous(), directions[sel].contiguous(), dnorm[sel].contiguous(), S, latent, scale, steps_minmax=mm, **kw)
+            for k in keys:
+                outs[k].append(o[k])
+        if not idx.numel():
+            w = {"rgb": 3, "albedo": 3, "normal": 3}
+            return {k: torch.zeros((0, w.get(k, 1)), device=origins.device) for k in keys}
+        return {k: torch.cat(v, 0) for k, v in outs.items()}
+
+    return parallel.render_sharded(fn, n, tile, tuple(keys), device=origins.device, group=group)
