@@ -124,6 +124,14 @@ int nsk_reni_decode_fwd(const float* dirs, int64_t D, const float* latents, cons
 int nsk_lambert_prep(const float* normals, const float* wa, int64_t R, int S, const float* dirs,
                      const uint8_t* ddf_mask, int D, const float* radiance, const int32_t* cam,
                      float unoccluded_vis, float* inv_count, float* rgb_lin, void* stream);
+/* Relighting with cached visibility (fixed geometry, new illumination; the reference's illumination animation
+ * re-renders geometry AND visibility per frame, neusky/models/neusky_model.py:1896-1980): the same Lambertian sum as
+ * nsk_lambert_prep + nsk_sky_shade_* with vis_sel [R,Dp] read from the cache instead of evaluating the DDF.
+ * sel_index [D] int32: position of direction j inside the masked set, or -1 (visibility = unoccluded_vis).
+ * rgb_lin [R,3] is OVERWRITTEN. */
+int nsk_lambert_relight(const float* normals, const float* wa, const float* inv_count, int64_t R, int S,
+                        const float* dirs, const int32_t* sel_index, int D, int Dp, const float* radiance,
+                        const int32_t* cam, const float* vis_sel, float unoccluded_vis, float* rgb_lin, void* stream);
 int nsk_shade_finalize(const float* rgb_lin, const float* bg, const float* acc, int64_t R, int training,
                        float* rgb, void* stream);
 

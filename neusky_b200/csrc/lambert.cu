@@ -40,6 +40,37 @@ lambert_prep_kernel(const float* __restrict__ normals, const float* __restrict__
   if (lane == 0) { rgb_lin[ray * 3] = o0; rgb_lin[ray * 3 + 1] = o1; rgb_lin[ray * 3 + 2] = o2; }
 }
 
+// Relighting pass: the Lambertian sum of lambert_prep + K4 with the per-ray visibility taken from a cache instead of
+// the DDF (fixed geometry, new illumination: neusky/models/neusky_model.py:1896-1980 re-renders everything per frame).
+// one warp per ray; vis_sel [R, Dp] holds the visibility of the directions with ddf_mask == 1, in mask order.
+__global__ void __launch_bounds__(LP_WARPS * 32)
+lambert_relight_kernel(const float* __restrict__ normals, const float* __restrict__ wa, const float* __restrict__ inv_count,
+                       int64_t R, int S, const float* __restrict__ dirs, const int32_t* __restrict__ sel_index, int D, int Dp,
+                       const float* __restrict__ radiance, const int32_t* __restrict__ cam, const float* __restrict__ vis_sel,
+                       float unocc_vis, float* __restrict__ rgb_lin) {
+  const int lane = threadIdx.x & 31;
+  const int64_t ray = (int64_t)blockIdx.x * LP_WARPS + (threadIdx.x >> 5);
+  if (ray >= R) return;
+  const float* rad = radiance + (int64_t)(cam ? cam[ray] : 0) * D * 3;
+  const float* vr = vis_sel + ray * Dp;
+  float o0 = 0.f, o1 = 0.f, o2 = 0.f;
+  for (int j = lane; j < D; j += 32) {
+    const float lx = dirs[j * 3], ly = dirs[j * 3 + 1], lz = dirs[j * 3 + 2];
+    const int sj = sel_index[j];                       // position in the masked set, or -1
+    const float v = sj >= 0 ? vr[sj] : unocc_vis;
+    float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+    for (int s = 0; s < S; ++s) {
+      const int64_t i = ray * S + s;
+      float c = normals[i * 3] * lx + normals[i * 3 + 1] * ly + normals[i * 3 + 2] * lz;
+      c = fminf(fmaxf(c, 0.f), 1.f) * inv_count[i];
+      c0 = fmaf(wa[i * 3], c, c0); c1 = fmaf(wa[i * 3 + 1], c, c1); c2 = fmaf(wa[i * 3 + 2], c, c2);
+    }
+    o0 = fmaf(c0 * v, rad[j * 3], o0); o1 = fmaf(c1 * v, rad[j * 3 + 1], o1); o2 = fmaf(c2 * v, rad[j * 3 + 2], o2);
+  }
+  o0 = warp_sum(o0); o1 = warp_sum(o1); o2 = warp_sum(o2);
+  if (lane == 0) { rgb_lin[ray * 3] = o0; rgb_lin[ray * 3 + 1] = o1; rgb_lin[ray * 3 + 2] = o2; }
+}
+
 __device__ __forceinline__ float srgb(float c) {
   // neusky/utils/utils.py:25-30
   const float v = (c <= 0.0031308f) ? 12.92f * c : 1.055f * powf(fabsf(c), 1.0f / 2.4f) - 0.055f;
@@ -77,4 +108,18 @@ extern "C" int nsk_shade_finalize(const float* rgb_lin, const float* bg, const f
   const int64_t n = R * 3;
   nsk::shade_finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, nsk::as_stream(stream)>>>(rgb_lin, bg, acc, R, rgb);
   return nsk::check_launch("shade_finalize_kernel");
+}
+
+extern "C" int nsk_lambert_relight(const float* normals, const float* wa, const float* inv_count, int64_t R, int S,
+                                   const float* dirs, const int32_t* sel_index, int D, int Dp, const float* radiance,
+                                   const int32_t* cam, const float* vis_sel, float unoccluded_vis, float* rgb_lin,
+                                   void* stream) {
+  if (R == 0) return 0;
+  NSK_REQUIRE(S >= 1 && D >= 1, "nsk_lambert_relight: S and D must be >= 1");
+  NSK_REQUIRE(normals && wa && inv_count && dirs && sel_index && radiance && rgb_lin && (vis_sel || Dp == 0), "nsk_lambert_relight: null pointer");
+  const int64_t blocks = (R + nsk::LP_WARPS - 1) / nsk::LP_WARPS;
+  NSK_REQUIRE(blocks < (1ll << 31), "nsk_lambert_relight: too many rays for one launch");
+  nsk::lambert_relight_kernel<<<(unsigned)blocks, nsk::LP_WARPS * 32, 0, nsk::as_stream(stream)>>>(
+      normals, wa, inv_count, R, S, dirs, sel_index, D, Dp, radiance, cam, vis_sel, unoccluded_vis, rgb_lin);
+  return nsk::check_launch("lambert_relight_kernel");
 }

@@ -192,6 +192,24 @@ def lambert_prep(normals, wa, dirs, ddf_mask, radiance, cam=None, unoccluded_vis
     return inv_count, rgb_lin
 
 
+def lambert_relight(normals, wa, inv_count, dirs, sel_index, radiance, vis_sel, cam=None, unoccluded_vis: float = 1.0) -> Tensor:
+    """Lambertian sum with cached per-ray visibility vis_sel [R,Dp] -> linear rgb [R,3] (config 5: relighting)."""
+    R, S = normals.shape[0], normals.shape[1]
+    D = dirs.shape[0]
+    Dp = vis_sel.shape[1]
+    normals, wa = _chk("normals", normals, shape=(R, S, 3)), _chk("wa", wa, shape=(R, S, 3))
+    inv_count = _chk("inv_count", inv_count, shape=(R, S))
+    dirs = _chk("dirs", dirs, shape=(D, 3))
+    sel_index = _chk("sel_index", sel_index, dtype=torch.int32, shape=(D,))
+    radiance = _chk("radiance", radiance, shape=(None, D, 3))
+    vis_sel = _chk("vis_sel", vis_sel, shape=(R, Dp))
+    if cam is not None:
+        cam = _chk("cam", cam, dtype=torch.int32, shape=(R,))
+    rgb_lin = torch.empty((R, 3), device=normals.device, dtype=torch.float32)
+    _lib.check(_lib.load().nsk_lambert_relight(_ptr(normals), _ptr(wa), _ptr(inv_count), c_int64(R), c_int(S), _ptr(dirs), _ptr(sel_index), c_int(D), c_int(Dp), _ptr(radiance), _ptr(cam), _ptr(vis_sel), c_float(unoccluded_vis), _ptr(rgb_lin), _stream(normals)), "nsk_lambert_relight")
+    return rgb_lin
+
+
 def shade_finalize(rgb_lin, bg, acc, training: bool = False) -> Tensor:
     R = rgb_lin.shape[0]
     rgb_lin, bg = _chk("rgb_lin", rgb_lin, shape=(R, 3)), _chk("bg", bg, shape=(R, 3))

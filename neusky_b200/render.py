@@ -51,6 +51,7 @@ class SkyShader:
         self.mask = m
         self.mask_u8 = m.to(torch.uint8).contiguous()
         self.dirs_sel = self.dirs[m].contiguous()
+        self.sel_index = torch.where(m, torch.cumsum(m.to(torch.int32), 0, dtype=torch.int32) - 1, torch.full_like(m, -1, dtype=torch.int32)).to(torch.int32).contiguous()
 
     def radiance_table(self, latents: Tensor, scale: Optional[Tensor], rotation: Optional[Tensor] = None) -> Tensor:
         return ops.reni_radiance_table(self.dirs, latents, scale, self.reni_blob, rotation)
@@ -78,6 +79,7 @@ class SkyShader:
             full = torch.full((points.shape[0], self.dirs.shape[0]), self.lower_vis, device=self.device)
             full[:, self.mask] = vis
             out["visibility"] = full
+            out["visibility_sel"] = vis
         if ddf is not None:
             out["expected_termination_dist"], out["termination_dist"] = ddf, term
         return out
@@ -177,7 +179,7 @@ class RayRenderer:
     @torch.no_grad()
     def render(self, origins: Tensor, directions: Tensor, dnorm: Tensor, S: int, latent: Tensor, scale: Tensor, rotation: Optional[Tensor] = None,
                threshold: float = 0.1, sigmoid_scale: float = 25.0, cos_anneal_ratio: float = 1.0, want_vis: bool = False,
-               steps_minmax: Optional[Tensor] = None) -> Dict[str, Tensor]:
+               steps_minmax: Optional[Tensor] = None, want_cache: bool = False) -> Dict[str, Tensor]:
         """origins/directions [R,3], dnorm [R,1]; latent [L,3]; scale scalar tensor.  All rays belong to one camera."""
         R = origins.shape[0]
         sh = self.shader
@@ -192,14 +194,32 @@ class RayRenderer:
         radiance = sh.radiance_table(Z, sc, rotation)                                    # [1,D,3]
         bg = ops.reni_radiance_table(directions, Z, sc, sh.reni_blob, rotation)[0]      # per-ray background (neusky_model.py:535-549)
         pts = ops.surface_points(origins, directions, c["p2p_dist"], sh.radius)
-        s = sh.shade(pts, c["normals"], c["wa"], radiance, want_vis=want_vis, threshold=threshold, sigmoid_scale=sigmoid_scale)
+        s = sh.shade(pts, c["normals"], c["wa"], radiance, want_vis=want_vis or want_cache, threshold=threshold, sigmoid_scale=sigmoid_scale)
         rgb = ops.shade_finalize(s["rgb_lin"], bg, c["accumulation"])
         out = {"rgb": rgb, "albedo": c["albedo"], "accumulation": c["accumulation"][:, None], "depth": c["depth"][:, None], "p2p_dist": c["p2p_dist"][:, None],
                "normal": c["normal"], "weights": c["weights"][..., None], "hdr_background_colours": bg, "directions_norm": dnorm,
                "starts": starts, "ends": ends}
         if want_vis:
             out["visibility"] = s["visibility"]
+        if want_cache:
+            # everything a new illumination needs (fixed geometry): per-sample shading inputs, per-ray visibility of the
+            # DDF directions, accumulation.  The geometry-only outputs above stay valid for every latent code.
+            out["relight_cache"] = {"normals": c["normals"], "wa": c["wa"], "inv_count": s["inv_count"], "visibility_sel": s["visibility_sel"],
+                                    "accumulation": c["accumulation"], "directions": directions}
         return out
+
+    @torch.no_grad()
+    def relight(self, cache: Dict[str, Tensor], latent: Tensor, scale: Tensor, rotation: Optional[Tensor] = None) -> Tensor:
+        """sRGB [R,3] of the cached rays under another RENI++ latent code / rotation (BASELINE.json config 5): RENI++ decode
+        of the direction set and of the per-ray background, then one Lambertian pass over the cached visibility --
+        no SDF field, no compositing, no DDF.  Equals render(...)["rgb"] for the same latent."""
+        sh = self.shader
+        Z = latent.reshape(1, -1, 3).to(self.device, torch.float32)
+        sc = scale.reshape(1).to(self.device, torch.float32)
+        radiance = sh.radiance_table(Z, sc, rotation)
+        bg = ops.reni_radiance_table(cache["directions"], Z, sc, sh.reni_blob, rotation)[0]
+        lin = ops.lambert_relight(cache["normals"], cache["wa"], cache["inv_count"], sh.dirs, sh.sel_index, radiance, cache["visibility_sel"], None, sh.lower_vis)
+        return ops.shade_finalize(lin, bg, cache["accumulation"])
 
 
 def global_steps_minmax(origins: Tensor, directions: Tensor, S: int) -> Tensor:

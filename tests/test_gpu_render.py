@@ -114,3 +114,27 @@ def test_render_image_is_tile_invariant(dev, scene):
     ref = scene["ref"]
     assert float((a["rgb"].cpu() - ref["rgb"]).abs().max()) <= 1e-3
     assert float((a["depth"].cpu() - ref["depth"]).abs().max()) <= 1e-3 * float(ref["depth"].abs().max())
+
+
+def test_relight_from_cache_equals_rerender(dev, scene):
+    """BASELINE.json config 5 (relighting sweep, reduced): re-shading cached geometry + visibility under other latent
+    codes and a rotated latent equals a full re-render with that latent."""
+    from neusky_b200.render import RayRenderer
+    from neusky_b200 import ops
+
+    r = RayRenderer(scene["sdf_p"], scene["ddf_p"], scene["reni_p"], device=dev, log2_T=scene["log2_T"])
+    r.set_directions(scene["dirs"])
+    o, d, dn = (t.to(dev) for t in (scene["o"], scene["d"], scene["dn"]))
+    sc = torch.zeros((), device=dev)
+    base = r.render(o, d, dn, scene["S"], scene["Z"].to(dev), sc, want_cache=True)
+    g = torch.Generator().manual_seed(11)
+    ang = 0.7
+    rot = torch.tensor([[float(torch.cos(torch.tensor(ang))), -float(torch.sin(torch.tensor(ang))), 0.0],
+                        [float(torch.sin(torch.tensor(ang))), float(torch.cos(torch.tensor(ang))), 0.0], [0.0, 0.0, 1.0]], device=dev)
+    for k in range(4):
+        Zk = torch.randn(100, 3, generator=g).to(dev)
+        rk = rot if k == 3 else None
+        full = r.render(o, d, dn, scene["S"], Zk, sc, rotation=rk)["rgb"]
+        fast = r.relight(base["relight_cache"], Zk, sc, rotation=rk)
+        assert float((full - fast).abs().max()) <= 2e-5, float((full - fast).abs().max())
+    assert float((base["rgb"] - r.relight(base["relight_cache"], scene["Z"].to(dev), sc)).abs().max()) <= 2e-5
