@@ -165,6 +165,16 @@ int nsk_sky_shade_tc_fwd(const float* points, int64_t R, const float* normals, c
                          const float* scalings, int num_levels, int log2_T, float radius, float threshold,
                          float sigmoid_scale, float* rgb_lin, float* vis_out, float* ddf_out, float* term_out,
                          void* stream);
+/* CTA-pair variant of the tensor-core path (tcgen05.mma.cta_group::2, M = 256 across two SMs of a TPC; each CTA streams
+ * half of every weight stage).  Same arguments and numerics as nsk_sky_shade_tc_fwd; ddf_weights = nsk pack "tc2" blob
+ * (neusky_b200.packing.pack_ddf_tc2). */
+int nsk_sky_shade_tc2_fwd(const float* points, int64_t R, const float* normals, const float* wa,
+                          const float* inv_count, int S, const float* dirs, int Dp, const float* radiance,
+                          const int32_t* cam, const void* ddf_weights, const float* hash_table,
+                          const float* scalings, int num_levels, int log2_T, float radius, float threshold,
+                          float sigmoid_scale, float* rgb_lin, float* vis_out, float* ddf_out, float* term_out,
+                          void* stream);
+int64_t nsk_ddf_tc2_weights_bytes(void);
 int64_t nsk_ddf_simt_weights_floats(void);
 int64_t nsk_ddf_tc_weights_bytes(void);
 

@@ -246,7 +246,10 @@ def sky_shade(points, normals, wa, inv_count, dirs_sel, radiance_sel, ddf_blob, 
     elif impl == "tc":
         blob = _chk("ddf_blob", ddf_blob, dtype=torch.uint8, shape=(lib.nsk_ddf_tc_weights_bytes(),))
         fn, name = lib.nsk_sky_shade_tc_fwd, "nsk_sky_shade_tc_fwd"
+    elif impl == "tc2":
+        blob = _chk("ddf_blob", ddf_blob, dtype=torch.uint8, shape=(lib.nsk_ddf_tc2_weights_bytes(),))
+        fn, name = lib.nsk_sky_shade_tc2_fwd, "nsk_sky_shade_tc2_fwd"
     else:
-        raise ValueError(f"impl must be 'tc' or 'simt', got {impl!r}")
+        raise ValueError(f"impl must be 'tc2', 'tc' or 'simt', got {impl!r}")
     _lib.check(fn(_ptr(points), c_int64(R), _ptr(normals), _ptr(wa), _ptr(inv_count), c_int(S), _ptr(dirs_sel), c_int(Dp), _ptr(radiance_sel), _ptr(cam), _ptr(blob), _ptr(hash_table), _ptr(scalings), c_int(L), c_int(log2_T), c_float(radius), c_float(threshold), c_float(sigmoid_scale), _ptr(rgb_lin), _ptr(vis), _ptr(ddf), _ptr(term), _stream(points)), name)
     return vis, ddf, term

@@ -52,6 +52,50 @@ def pack_reni(p: Dict[str, Tensor], num_layers: int = 6) -> Tensor:
     return torch.cat([x.to(torch.float32).flatten() for x in parts]).contiguous()
 
 
+def pack_ddf_tc2(p: Dict[str, Tensor]) -> Tensor:
+    """uint8 blob for nsk_sky_shade_tc2_fwd (CTA-pair kernel, csrc/sky_shade_tc2.cu): the same operand matrices as
+    pack_ddf_tc, but every [N][K] tile is split by rows between the two CTAs of a pair (rank r streams rows
+    [r N/2, (r+1) N/2) -- for a FiLM chunk that is the freq' rows for rank 0 and the phase' rows for rank 1) and cut
+    into 16 KB stages of twice the K extent.  Layout: [rank-0 stream | rank-1 stream | fp32 tail]."""
+    dev = p["ddf.final_layer.weight"].device
+    f32 = lambda k: p[k].to(torch.float32)
+    Wf, bf, Wp, bp = fold_film(p)
+    ops_ = []   # (matrix [N][K], nfull, kps, ktail) in MMA issue order
+    ops_.append((_with_bias_cols(f32("ddf.mapping_network.network.0.weight"), f32("ddf.mapping_network.network.0.bias"), 48), 0, 64, 48))
+    for i in range(1, DDF_LAYERS):
+        ops_.append((_with_bias_cols(f32(f"ddf.mapping_network.network.{2 * i}.weight"), f32(f"ddf.mapping_network.network.{2 * i}.bias"), 272), 4, 64, 16))
+
+    def fp(l, c):
+        rows = slice(l * DDF_HID + c * 64, l * DDF_HID + c * 64 + 64)
+        return (torch.cat([_with_bias_cols(Wf[rows], bf[rows], 272), _with_bias_cols(Wp[rows], bp[rows], 272)], 0), 2, 128, 16)
+
+    def z(l):
+        W = f32(f"ddf.net.{l}.layer.weight")
+        if l == 0:
+            W0 = torch.zeros((DDF_HID, 16), dtype=torch.float32, device=dev)
+            W0[:, :15] = W
+            return (W0, 0, 64, 16)
+        return (W, 4, 64, 0)
+
+    ops_ += [fp(0, 0), z(0), fp(0, 1)]
+    for l in range(DDF_LAYERS):
+        ops_ += [fp(l, 2), fp(l, 3)]
+        if l + 1 < DDF_LAYERS:
+            ops_ += [fp(l + 1, 0), z(l + 1), fp(l + 1, 1)]
+    streams = []
+    for r in range(2):
+        st = []
+        for W, nfull, kps, ktail in ops_:
+            h = W.shape[0] // 2
+            st += _stages(W[r * h:(r + 1) * h], nfull, kps, ktail)
+        streams.append(torch.cat(st).contiguous().view(torch.uint8))
+    assert streams[0].numel() == TC_STREAM_BYTES // 2 == streams[1].numel(), (streams[0].numel(), TC_STREAM_BYTES)
+    vec = torch.zeros(TC_TAIL_FLOATS, dtype=torch.float32, device=dev)
+    vec[:256] = f32("ddf.final_layer.weight").flatten()
+    vec[256] = f32("ddf.final_layer.bias").flatten()[0]
+    return torch.cat([streams[0], streams[1], vec.view(torch.uint8)]).contiguous()
+
+
 def fold_weight_norm(p: Dict[str, Tensor], name: str) -> Tensor:
     """nn.utils.weight_norm(dim=0) fold W = g * v / ||v||_row (SDFFieldConfig.weight_norm=True [NS-mem A.4];
     neusky/fields/sdf_albedo_field.py:159-160); plain ``.weight`` is accepted too."""

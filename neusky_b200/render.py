@@ -38,7 +38,8 @@ class SkyShader:
     def set_ddf_weights(self, ddf_params: Dict[str, Tensor]) -> None:
         p = {k: v.to(self.device) for k, v in ddf_params.items() if k.startswith("ddf.")}
         self.ddf_blob_simt = packing.pack_ddf_simt(p)
-        self.ddf_blob_tc = packing.pack_ddf_tc(p) if hasattr(packing, "pack_ddf_tc") else None
+        self.ddf_blob_tc = packing.pack_ddf_tc(p)
+        self.ddf_blob_tc2 = packing.pack_ddf_tc2(p)
 
     # -- direction set -------------------------------------------------------------------------
     def set_directions(self, dirs: Tensor) -> None:
@@ -65,7 +66,7 @@ class SkyShader:
         impl = impl or self.impl
         inv_count, rgb_lin = ops.lambert_prep(normals, wa, self.dirs, self.mask_u8, radiance, cam, self.lower_vis)
         rad_sel = radiance[:, self.mask].contiguous()
-        blob = self.ddf_blob_tc if impl == "tc" else self.ddf_blob_simt
+        blob = {"tc": self.ddf_blob_tc, "tc2": self.ddf_blob_tc2, "simt": self.ddf_blob_simt}[impl]
         if self.k4_events is not None:
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             ev[0].record()

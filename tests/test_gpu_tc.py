@@ -32,8 +32,9 @@ def _scene(R, D, S, seed):
     return pts, normals, wa, dirs, radiance
 
 
+@pytest.mark.parametrize("impl", ["tc", "tc2"])
 @pytest.mark.parametrize("R,D,S,gain", [(1, 1, 1, 8.0), (3, 50, 2, 8.0), (64, 162, 1, 8.0), (700, 642, 1, 1.0), (257, 300, 3, 8.0)])
-def test_tc_vs_simt(dev, R, D, S, gain):
+def test_tc_vs_simt(dev, R, D, S, gain, impl):
     from neusky_b200.render import SkyShader
 
     p = nb_init.init_ddf_params(21, final_gain=gain)
@@ -42,7 +43,7 @@ def test_tc_vs_simt(dev, R, D, S, gain):
     sh.set_directions(dirs)
     args = (pts.to(dev), normals.to(dev), wa.to(dev), radiance.to(dev))
     ref = sh.shade(*args, want_vis=True, want_ddf=True, impl="simt")
-    out = sh.shade(*args, want_vis=True, want_ddf=True, impl="tc")
+    out = sh.shade(*args, want_vis=True, want_ddf=True, impl=impl)
     torch.cuda.synchronize()
     assert torch.allclose(out["termination_dist"], ref["termination_dist"], rtol=1e-5, atol=2e-6)
     e_ddf = (out["expected_termination_dist"] - ref["expected_termination_dist"]).abs()
@@ -75,7 +76,8 @@ def test_tc_vs_reference_golden(dev, golden):
     assert float(e_ddf.max()) <= 4e-3
 
 
-def test_tc_multi_tile_persistent_and_no_vis_buffer(dev):
+@pytest.mark.parametrize("impl", ["tc", "tc2"])
+def test_tc_multi_tile_persistent_and_no_vis_buffer(dev, impl):
     """More tiles than SMs (persistent loop, ring phases wrap many times); vis tensor not requested."""
     from neusky_b200.render import SkyShader
 
@@ -86,8 +88,8 @@ def test_tc_multi_tile_persistent_and_no_vis_buffer(dev):
     sh.set_directions(dirs)
     args = (pts.to(dev), normals.to(dev), wa.to(dev), radiance.to(dev))
     ref = sh.shade(*args, impl="simt")
-    out = sh.shade(*args, impl="tc")
-    out2 = sh.shade(*args, impl="tc")
+    out = sh.shade(*args, impl=impl)
+    out2 = sh.shade(*args, impl=impl)
     torch.cuda.synchronize()
     assert "visibility" not in out
     rel = ((out["rgb_lin"] - ref["rgb_lin"]).abs() / ref["rgb_lin"].abs().clamp_min(1e-3)).max()
