@@ -264,7 +264,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) sky_
         const Op op = c_sched.ops[o];
         if (op.wait != NOB) {
           const long long c0 = clock64();
-          mbar_wait_cluster(bars + 8 * op.wait, (phases >> op.wait) & 1u);
+          mbar_wait(bars + 8 * op.wait, (phases >> op.wait) & 1u);
           const long long dt = clock64() - c0;
           t_dep += dt;
           if (o < 6) t_dep_map += dt;
@@ -290,7 +290,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) sky_
             {
               const long long c0 = clock64();
               mbar_wait(bars + 8 * (B_WFULL + wst), wph);                  // my half of the stage
-              mbar_wait_cluster(bars + 8 * (B_PFULL + wst), wph);          // the peer's half
+              mbar_wait(bars + 8 * (B_PFULL + wst), wph);          // the peer's half
               t_w += clock64() - c0;
             }
             tc_fence_after();

@@ -219,12 +219,14 @@ __device__ __forceinline__ void umma_commit2(uint32_t bar) {
                "h"((uint16_t)3)
                : "memory");
 }
-// arrive on the mbarrier at local offset `bar` in CTA `cta` of the cluster (release at cluster scope)
+// arrive on the mbarrier at local offset `bar` in CTA `cta` of the cluster (default semantics, as CUTLASS's
+// ClusterBarrier::arrive(cta_id): explicit .release.cluster / .acquire.cluster qualifiers cost hundreds of cycles per
+// operation on the serial MMA-issue path, measured on B200)
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
   asm volatile(
       "{\n\t.reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar),
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar),
       "r"(cta)
       : "memory");
 }

@@ -135,15 +135,16 @@ static int probe_mma(bool ts, int N, int K) {
 // probe 3: MMA issue throughput on every SM (cycles per 128xNx16 MMA), SS vs TS, with or without
 // concurrent shared-memory traffic from 4 "epilogue" warps.
 // ------------------------------------------------------------------------------------------------
+__device__ int g_commit_every = 0;   // power of two; 0 = a single commit at the end
 template <bool A_IN_TMEM>
 __global__ void __launch_bounds__(256) mma_rate_kernel(int N, int iters, int smem_noise, long long* __restrict__ cycles, float* sink) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t bar;
+  __shared__ uint64_t bar, bar2;
   __shared__ uint32_t tmem_base_s;
   const int t = threadIdx.x, warp = t >> 5;
   // operands: A 128x256, B 256x256 (zeros are fine for timing)
   for (int e = t; e < (128 + 256) * 256 * 2 / 16; e += blockDim.x) reinterpret_cast<uint4*>(smem)[e] = make_uint4(0, 0, 0, 0);
-  if (t == 0) { mbar_init(smem_u32(&bar), 1); fence_barrier_init(); }
+  if (t == 0) { mbar_init(smem_u32(&bar), 1); mbar_init(smem_u32(&bar2), 1); fence_barrier_init(); }
   if (warp == 0) tmem_alloc<512>(smem_u32(&tmem_base_s));
   fence_proxy_async_smem();
   tc_fence_before();
@@ -159,6 +160,7 @@ __global__ void __launch_bounds__(256) mma_rate_kernel(int N, int iters, int sme
       const uint64_t bd = make_smem_desc(sB + (k0 / 8) * N * 16, N * 16, 128);
       if (A_IN_TMEM) umma_ts(tmem, tmem + 256 + k0 / 2, bd, idesc, 1);
       else umma_ss(tmem, make_smem_desc(sA + (k0 / 8) * 128 * 16, 128 * 16, 128), bd, idesc, 1);
+      if (g_commit_every > 0 && ((i + 1) & (g_commit_every - 1)) == 0) umma_commit(smem_u32(&bar2));
     }
     umma_commit(smem_u32(&bar));
     mbar_wait(smem_u32(&bar), 0);
@@ -180,8 +182,9 @@ __global__ void __launch_bounds__(256) mma_rate_kernel(int N, int iters, int sme
   if (warp == 0) tmem_dealloc<512>(tmem);
 }
 
-static void probe_rate(bool ts, int N, int noise) {
+static void probe_rate(bool ts, int N, int noise, int commit_every = 0) {
   const int iters = 4096, grid = 148;
+  CK(cudaMemcpyToSymbol(g_commit_every, &commit_every, sizeof(int)));
   long long* d; float* sink;
   CK(cudaMalloc(&d, grid * sizeof(long long))); CK(cudaMalloc(&sink, 4));
   const size_t smem = (size_t)(128 + 256) * 256 * 2 + 16384 + 1024;
@@ -199,7 +202,7 @@ static void probe_rate(bool ts, int N, int noise) {
   CK(cudaMemcpy(h.data(), d, grid * sizeof(long long), cudaMemcpyDeviceToHost));
   double mean = 0; for (auto v : h) mean += (double)v; mean /= grid;
   const double flops = 2.0 * 128 * N * 16 * (double)iters * grid;
-  printf("probe rate_%s N=%d noise=%d : %.1f cycles/MMA (ideal %d), kernel %.3f ms -> %.0f TFLOP/s\n", ts ? "ts" : "ss", N, noise,
+  printf("probe rate_%s N=%d noise=%d commit_every=%d : %.1f cycles/MMA (ideal %d), kernel %.3f ms -> %.0f TFLOP/s\n", ts ? "ts" : "ss", N, noise, commit_every,
          mean / iters, N / 2, ms, flops / (ms * 1e-3) / 1e12);
 }
 
@@ -311,6 +314,79 @@ static void probe_ldtm() {
          mean / iters, mean / iters);
 }
 
+// ------------------------------------------------------------------------------------------------
+// probe 6: issue rate of tcgen05.mma.cta_group::2 (M = 256 across a CTA pair), A and B from shared memory.
+// commit_every > 0: a multicast tcgen05.commit after every `commit_every` MMAs (the per-stage pattern of the kernel).
+// ------------------------------------------------------------------------------------------------
+// local-only commit of a cta_group::2 MMA group (no multicast): arrives on the mbarrier of the executing CTA only
+__device__ __forceinline__ void umma_commit2_local(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128) mma_rate2_kernel(int N, int iters, int commit_every, int mode, long long* __restrict__ cycles) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar, bar2;
+  __shared__ uint32_t tmem_base_s;
+  const int t = threadIdx.x, warp = t >> 5;
+  const uint32_t rank = cluster_ctarank();
+  for (int e = t; e < (128 + 128) * 256 * 2 / 16; e += blockDim.x) reinterpret_cast<uint4*>(smem)[e] = make_uint4(0, 0, 0, 0);
+  if (t == 0) { mbar_init(smem_u32(&bar), 1); mbar_init(smem_u32(&bar2), 1); fence_barrier_init(); }
+  if (warp == 0) tmem_alloc2<512>(smem_u32(&tmem_base_s));
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  const int Nh = N / 2;
+  const uint32_t sA = smem_u32(smem), sB = smem_u32(smem) + 128 * 256 * 2;
+  uint32_t peer_bar2;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(peer_bar2) : "r"(smem_u32(&bar2)), "r"(1));
+  if (t == 0 && rank == 0) {
+    const uint32_t idesc = make_idesc_f16(256, N);
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+      const int k0 = (i & 15) * 16;
+      umma_ss2(tmem, make_smem_desc(sA + (k0 / 8) * 128 * 16, 128 * 16, 128), make_smem_desc(sB + (k0 / 8) * Nh * 16, Nh * 16, 128), idesc, 1);
+      if (commit_every > 0 && ((i + 1) & (commit_every - 1)) == 0) {
+        if (mode == 0) umma_commit2(smem_u32(&bar2));                 // multicast to both CTAs
+        else if (mode == 1) umma_commit2_local(smem_u32(&bar2));      // leader's barrier only
+        else { umma_commit2_local(smem_u32(&bar2)); umma_commit2_local(peer_bar2); }   // two unicast commits: local + peer address
+      }
+    }
+    umma_commit2(smem_u32(&bar));
+    mbar_wait(smem_u32(&bar), 0);
+    cycles[blockIdx.x >> 1] = clock64() - t0;
+  } else if (t == 0) {
+    mbar_wait(smem_u32(&bar), 0);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 0) tmem_dealloc2<512>(tmem);
+}
+
+static void probe_rate2(int N, int commit_every, int mode) {
+  const int iters = 4096, grid = 148;
+  long long* d;
+  CK(cudaMalloc(&d, grid / 2 * sizeof(long long)));
+  const size_t smem = (size_t)(128 + 128) * 256 * 2 + 1024;
+  CK(cudaFuncSetAttribute(mma_rate2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  for (int rep = 0; rep < 2; ++rep) mma_rate2_kernel<<<grid, 128, smem>>>(N, iters, commit_every, mode, d);
+  CK(cudaDeviceSynchronize());
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaEventRecord(e0);
+  mma_rate2_kernel<<<grid, 128, smem>>>(N, iters, commit_every, mode, d);
+  cudaEventRecord(e1);
+  CK(cudaDeviceSynchronize());
+  float ms; cudaEventElapsedTime(&ms, e0, e1);
+  std::vector<long long> h(grid / 2);
+  CK(cudaMemcpy(h.data(), d, grid / 2 * sizeof(long long), cudaMemcpyDeviceToHost));
+  double mean = 0; for (auto v : h) mean += (double)v; mean /= (grid / 2);
+  const double flops = 2.0 * 256 * N * 16 * (double)iters * (grid / 2);
+  printf("probe rate2 (cta_group::2, M=256) N=%d commit_every=%d mode=%d : %.1f cycles/MMA (ideal %d), kernel %.3f ms -> %.0f TFLOP/s\n", N, commit_every, mode,
+         mean / iters, N / 2, ms, flops / (ms * 1e-3) / 1e12);
+}
+
 int main(int argc, char** argv) {
   const char* what = argc > 1 ? argv[1] : "all";
   int fails = 0;
@@ -318,9 +394,10 @@ int main(int argc, char** argv) {
   printf("device: %s, %d SMs, cc %d.%d, smem/block optin %zu\n", prop.name, prop.multiProcessorCount, prop.major, prop.minor, prop.sharedMemPerBlockOptin);
   if (!strcmp(what, "mma_ss")) { fails += probe_mma(false, atoi(argv[2]), atoi(argv[3])); }
   else if (!strcmp(what, "mma_ts")) { fails += probe_mma(true, atoi(argv[2]), atoi(argv[3])); }
-  else if (!strcmp(what, "rate")) { probe_rate(atoi(argv[2]) != 0, atoi(argv[3]), atoi(argv[4])); }
+  else if (!strcmp(what, "rate")) { probe_rate(atoi(argv[2]) != 0, atoi(argv[3]), atoi(argv[4]), argc > 5 ? atoi(argv[5]) : 0); }
   else if (!strcmp(what, "stream")) { fails += probe_stream(atoi(argv[2]), atoi(argv[3])); }
   else if (!strcmp(what, "ldtm")) { probe_ldtm(); }
+  else if (!strcmp(what, "rate2")) { probe_rate2(atoi(argv[2]), atoi(argv[3]), argc > 4 ? atoi(argv[4]) : 0); }
   else { printf("unknown probe %s\n", what); return 2; }
   return fails ? 1 : 0;
 }
