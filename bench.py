@@ -199,7 +199,7 @@ def _config(args, world):
             "points_per_gpu": args.points, "directions": 2048, "ddf_directions": 1024, "latent_codes": 1,
             "parallelism": f"ray-sharded x{world}, weights replicated, no collective",
             "l2": "256 MiB scratch write between timed steps (L2 flush); the 1.7 MB fp16 weight stream is L2-resident by design",
-            "k4_numerics": "fp16 operands, fp32 accumulate (tcgen05 kind::f16), fp32 epilogues"}
+            "k4_numerics": "fp16 operands, fp32 accumulate (tcgen05.mma.cta_group::2 kind::f16, CTA pairs), fp32 epilogues"}
 
 
 # ------------------------------------------------------------------------------------------ eval-render arm (configs[2])
@@ -375,7 +375,7 @@ def main():
             "e2e": {"value": world * P * e2e_steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": 3 * P * 12, "d2h_bytes_per_step": P * 12,
                     "api": "neusky_b200.render.SkyShader.shade_points_host", "steps": e2e_steps},
             "gpu_launches": launches,
-            "roofline": {"kernel": "sky_shade_tc_kernel", "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+            "roofline": {"kernel": "sky_shade_tc2_kernel", "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          "traffic": _ncu_traffic(pairs), "peak_source": f"{peaks['source']} dense bf16/fp16 cuBLAS, sustained ({peaks['tf_burst']:.0f} burst)",
                          "frac_of_burst": achieved / peaks["tf_burst"], "pairs_per_launch": pairs, "flop_per_pair": FLOP_PER_PAIR,
                          "ms_per_launch": 1e3 * k4_s, "k4_share_of_step": k4_s * args.steps / t_dev if world == 1 else None},

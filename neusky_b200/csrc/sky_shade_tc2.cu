@@ -159,6 +159,8 @@ __constant__ int c_shape_ktail[6] = {48, 16, 16, 16, 0, 0};
 template <int VARIANT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) sky_shade_tc2_kernel(const Params P) {
   // VARIANT bit0: epilogue math stripped (diagnostic), bit1: MMAs not issued (diagnostic)
+  constexpr bool PROF = (VARIANT & 4) != 0;      // per-role cycle accounting (diagnostic instantiation only)
+#define NSK_CLK() (PROF ? clock64() : 0ll)
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bars = sbase + OFF_BAR;
@@ -208,7 +210,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) sky_
       const uint64_t pol = l2_policy_evict_last();
       uint32_t st = 0, ph = 0;
       long long t_wait = 0;
-      const long long t_begin = clock64();
+      const long long t_begin = NSK_CLK();
       for (int64_t tp = tp0; tp < P.n_tp; tp += tp_step) {
         const uint8_t* src = P.blob + (int64_t)rank * STREAM_BYTES_RANK;
 #pragma unroll 1
@@ -219,9 +221,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) sky_
 #pragma unroll 1
           for (int sg = 0; sg < nst; ++sg) {
             const uint32_t bytes = (uint32_t)(N >> 1) * (uint32_t)(sg < nfull ? kps : ktail) * 2u;
-            const long long c0 = clock64();
             mbar_wait(bars + 8 * (B_WEMPTY + st), ph ^ 1);
-            t_wait += clock64() - c0;
             mbar_arrive_expect_tx(bars + 8 * (B_WFULL + st), bytes);
             bulk_g2s_hint(sbase + OFF_RING + st * STAGE_BYTES, src, bytes, bars + 8 * (B_WFULL + st), pol);
             src += bytes;
@@ -229,7 +229,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) sky_
           }
         }
       }
-      if (P.prof) { P.prof[blockIdx.x * 16 + 0] = clock64() - t_begin; P.prof[blockIdx.x * 16 + 1] = t_wait; }
+      if (P.prof) { P.prof[blockIdx.x * 16 + 0] = NSK_CLK() - t_begin; P.prof[blockIdx.x * 16 + 1] = t_wait; }
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -238,7 +238,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) sky_
     // tcgen05.mma / tcgen05.commit instructions.  Descriptors are advanced by adding to their low words.
     uint32_t wst = 0, wph = 0, phases = 0;
     long long t_dep = 0, t_w = 0, t_dep_map = 0;
-    const long long t_begin = clock64();
+    const long long t_begin = NSK_CLK();
     const uint64_t desc_hi = ((uint64_t)1 << 46) | ((uint64_t)(128 >> 4) << 32);   // version 1, SBO = 128 B
     if (!leader) {
       // ---- peer CTA: relay "my half of stage s has landed" to the leader's PFULL barriers -----------------------
@@ -263,11 +263,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) sky_
       for (int o = 0; o < NUM_OPS; ++o) {
         const Op op = c_sched.ops[o];
         if (op.wait != NOB) {
-          const long long c0 = clock64();
+          const long long c0 = NSK_CLK();
           mbar_wait(bars + 8 * op.wait, (phases >> op.wait) & 1u);
-          const long long dt = clock64() - c0;
-          t_dep += dt;
-          if (o < 6) t_dep_map += dt;
+          if (PROF) {
+            const long long dt = NSK_CLK() - c0;
+            t_dep += dt;
+            if (o < 6) t_dep_map += dt;
+          }
           phases ^= 1u << op.wait;
           tc_fence_after();
         }
@@ -288,10 +290,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) sky_
           for (int sg = 0; sg < nst; ++sg) {
             const int nmma = (sg < nfull ? kps : ktail) >> 4;
             {
-              const long long c0 = clock64();
+              const long long c0 = NSK_CLK();
               mbar_wait(bars + 8 * (B_WFULL + wst), wph);                  // my half of the stage
-              mbar_wait(bars + 8 * (B_PFULL + wst), wph);          // the peer's half
-              t_w += clock64() - c0;
+              mbar_wait(bars + 8 * (B_PFULL + wst), wph);                  // the peer's half
+              if (PROF) t_w += NSK_CLK() - c0;
             }
             tc_fence_after();
             if (elect_one()) {
@@ -321,8 +323,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) sky_
       }
     }
     }
-    if (P.prof && lane == 0) {
-      P.prof[blockIdx.x * 16 + 2] = clock64() - t_begin; P.prof[blockIdx.x * 16 + 3] = t_dep; P.prof[blockIdx.x * 16 + 4] = t_w;
+    if (PROF && P.prof && lane == 0) {
+      P.prof[blockIdx.x * 16 + 2] = NSK_CLK() - t_begin; P.prof[blockIdx.x * 16 + 3] = t_dep; P.prof[blockIdx.x * 16 + 4] = t_w;
       P.prof[blockIdx.x * 16 + 5] = t_dep_map;
     }
   } else if (warp >= EPI_WARP0 && warp < PRO_WARP0) {
@@ -333,17 +335,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) sky_
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     uint32_t ph_acca = 0, ph_mapb = 0, ph_fp0 = 0, ph_fp1 = 0;
     long long t_wmap = 0, t_wz = 0, t_wfp = 0, t_tail = 0;
-    const long long t_begin = clock64();
+    const long long t_begin = NSK_CLK();
     int par = 0;
     for (int64_t tp = tp0; tp < P.n_tp; tp += tp_step, par ^= 1) {
       const int64_t tile = tp * 2 + rank;
       // ---- mapping layers: LeakyReLU(acc) -> ACT_M (bias already inside the accumulator) ----
       for (int i = 1; i <= 5; ++i) {
         const bool fromB = (i & 1) == 0;
-        const long long c0 = clock64();
+        const long long c0 = NSK_CLK();
         if (fromB) { mbar_wait(bars + 8 * B_MAPB, ph_mapb); ph_mapb ^= 1; }
         else { mbar_wait(bars + 8 * B_ACCA, ph_acca); ph_acca ^= 1; }
-        t_wmap += clock64() - c0;
+        t_wmap += NSK_CLK() - c0;
         tc_fence_after();
         const uint32_t src = tmem + (fromB ? TM_ACC_B : TM_ACC_A) + lane_off + hsel * 128;
         uint8_t* dst = smem + OFF_ACT_M + (uint32_t)(hsel * 16) * (TM * 16) + row * 16;
@@ -376,14 +378,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) sky_
       // ---- trunk: h = sin(freq' * z + phase') ----
       float fin = 0.f;
       for (int l = 0; l < DDF_LAYERS; ++l) {
-        long long c0 = clock64();
+        long long c0 = NSK_CLK();
         mbar_wait(bars + 8 * B_ACCA, ph_acca); ph_acca ^= 1;   // Z_l
-        t_wz += clock64() - c0;
+        t_wz += NSK_CLK() - c0;
         for (int c = 0; c < 4; ++c) {
-          c0 = clock64();
+          c0 = NSK_CLK();
           if (c & 1) { mbar_wait(bars + 8 * (B_FPFULL + 1), ph_fp1); ph_fp1 ^= 1; }
           else { mbar_wait(bars + 8 * (B_FPFULL + 0), ph_fp0); ph_fp0 ^= 1; }
-          t_wfp += clock64() - c0;
+          t_wfp += NSK_CLK() - c0;
           tc_fence_after();
           const uint32_t fp = tmem + ((c & 1) ? TM_FP1 : TM_FP0) + lane_off + hsel * 32;
           const uint32_t zz = tmem + TM_ACC_A + lane_off + c * 64 + hsel * 32;
@@ -424,7 +426,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) sky_
         }
       }
       // ---- tail: sigmoid, visibility, Lambertian accumulation ----
-      const long long c_tail = clock64();
+      const long long c_tail = NSK_CLK();
       if (hsel == 1) fin_part[row] = fin;
       asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
       if (hsel == 0) {
@@ -463,10 +465,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) sky_
         }
       }
       asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");   // fin_part reusable
-      t_tail += clock64() - c_tail;
+      t_tail += NSK_CLK() - c_tail;
     }
     if (P.prof && e == 0 && lane == 0) {
-      P.prof[blockIdx.x * 16 + 6] = clock64() - t_begin; P.prof[blockIdx.x * 16 + 7] = t_wmap; P.prof[blockIdx.x * 16 + 8] = t_wz;
+      P.prof[blockIdx.x * 16 + 6] = NSK_CLK() - t_begin; P.prof[blockIdx.x * 16 + 7] = t_wmap; P.prof[blockIdx.x * 16 + 8] = t_wz;
       P.prof[blockIdx.x * 16 + 9] = t_wfp; P.prof[blockIdx.x * 16 + 10] = t_tail;
     }
   } else if (warp >= PRO_WARP0) {
@@ -476,7 +478,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) sky_
     uint32_t ph_empty = 0;
     int par = 0;
     long long t_wempty = 0;
-    const long long t_begin = clock64();
+    const long long t_begin = NSK_CLK();
     for (int64_t tp = tp0; tp < P.n_tp; tp += tp_step, par ^= 1) {
       const int64_t tile = tp * 2 + rank;
       const int64_t pr = min(tile * TM + row, P.n_pairs - 1);
@@ -522,9 +524,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) sky_
       mp[19] = mp[20] = mp[21] = mp[22] = mp[23] = 0u;
       // wait until the MMAs of the previous tile have consumed IN_M / IN_H
       {
-        const long long c0 = clock64();
+        const long long c0 = NSK_CLK();
         mbar_wait(bars + 8 * B_INEMPTY, ph_empty ^ 1); ph_empty ^= 1;
-        t_wempty += clock64() - c0;
+        t_wempty += NSK_CLK() - c0;
       }
       {
         uint8_t* dm = smem + OFF_IN_M + row * 16;
@@ -541,7 +543,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) sky_
       fence_proxy_async_smem();
       arrive_leader(bars + 8 * B_INFULL);
     }
-    if (P.prof && row == 0) { P.prof[blockIdx.x * 16 + 11] = clock64() - t_begin; P.prof[blockIdx.x * 16 + 12] = t_wempty; }
+    if (P.prof && row == 0) { P.prof[blockIdx.x * 16 + 11] = NSK_CLK() - t_begin; P.prof[blockIdx.x * 16 + 12] = t_wempty; }
   }
 
   __syncwarp();
@@ -583,6 +585,7 @@ extern "C" int nsk_sky_shade_tc2_fwd(const float* points, int64_t R, const float
     cudaError_t e = cudaGetDevice(&dev);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(sky_shade_tc2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(sky_shade_tc2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
     if (e != cudaSuccess) { num_sms = 0; return nsk::fail("nsk_sky_shade_tc2_fwd: device setup", cudaGetErrorString(e)); }
   }
   Params P;
@@ -599,6 +602,7 @@ extern "C" int nsk_sky_shade_tc2_fwd(const float* points, int64_t R, const float
   P.n_tp = (P.n_tiles + 1) / 2;
   const int64_t clusters = P.n_tp < num_sms / 2 ? P.n_tp : num_sms / 2;
   const int64_t grid = 2 * clusters;
-  sky_shade_tc2_kernel<0><<<(unsigned)grid, NUM_THREADS, SMEM_BYTES, nsk::as_stream(stream)>>>(P);
+  if (P.prof) sky_shade_tc2_kernel<4><<<(unsigned)grid, NUM_THREADS, SMEM_BYTES, nsk::as_stream(stream)>>>(P);
+  else sky_shade_tc2_kernel<0><<<(unsigned)grid, NUM_THREADS, SMEM_BYTES, nsk::as_stream(stream)>>>(P);
   return nsk::check_launch("sky_shade_tc2_kernel");
 }

@@ -181,7 +181,7 @@ class NeuSkyVisibility:
     """The visibility step of NeuSkyFactoModel (neusky/models/neusky_model.py:1624-1778) behind the reference's
     ``compute_visibility`` signature.  ``ddf_params`` = state_dict of the DDF field (DirectionalDistanceField)."""
 
-    def __init__(self, ddf_params: Dict[str, Tensor], device="cuda", ddf_radius: float = 1.0, log2_T: int = 19, impl: str = "tc",
+    def __init__(self, ddf_params: Dict[str, Tensor], device="cuda", ddf_radius: float = 1.0, log2_T: int = 19, impl: str = "tc2",
                  only_upperhemisphere_visibility: bool = True, lower_hemisphere_visibility: float = 1.0):
         self.shader = SkyShader(ddf_params, None, device=device, ddf_radius=ddf_radius, log2_T=log2_T, only_upper_hemisphere=only_upperhemisphere_visibility,
                                 lower_hemisphere_visibility=lower_hemisphere_visibility, impl=impl)

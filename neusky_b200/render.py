@@ -22,7 +22,7 @@ class SkyShader:
 
     def __init__(self, ddf_params: Dict[str, Tensor], reni_params: Optional[Dict[str, Tensor]], device="cuda", ddf_radius: float = 1.0,
                  log2_T: int = 19, num_levels: int = 16, only_upper_hemisphere: bool = True, lower_hemisphere_visibility: float = 1.0,
-                 impl: str = "tc"):
+                 impl: str = "tc2"):
         self.device = torch.device(device)
         self.radius = float(ddf_radius)
         self.log2_T = log2_T
@@ -159,7 +159,7 @@ class RayRenderer:
     one camera (one latent code) per call; outputs use the reference's keys (:881-931)."""
 
     def __init__(self, sdf_params: Dict[str, Tensor], ddf_params: Dict[str, Tensor], reni_params: Dict[str, Tensor], device="cuda",
-                 log2_T: int = 19, num_levels: int = 16, ddf_radius: float = 1.0, impl: str = "tc", sdf_impl: str = "tc"):
+                 log2_T: int = 19, num_levels: int = 16, ddf_radius: float = 1.0, impl: str = "tc2", sdf_impl: str = "tc"):
         self.device = torch.device(device)
         self.log2_T = log2_T
         self.sdf_impl = sdf_impl

@@ -35,7 +35,7 @@ def test_compute_visibility_signature_vs_reference_golden(dev, golden):
     R, S, D = o.shape[0], 3, dirs.shape[0]
     rs = _ray_samples(o[:, None].expand(R, S, 3).contiguous(), d[:, None].expand(R, S, 3).contiguous(), torch.zeros(R, S, 1, device=dev), torch.ones(R, S, 1, device=dev))
     illum = dirs[None].expand(R * S, D, 3)
-    for impl, tol in (("simt", 5e-4), ("tc", 2e-2)):
+    for impl, tol in (("simt", 5e-4), ("tc", 2e-2), ("tc2", 2e-2)):
         m = NeuSkyVisibility(p, device=dev, impl=impl)
         vd = m.compute_visibility(rs, p2p, illum, float(g["threshold"]), float(g["sigmoid_scale"]))
         assert vd["visibility"].shape == (R * S, D, 1)

@@ -78,8 +78,9 @@ def test_render_fp32_path_vs_oracle(dev, scene):
     assert torch.allclose(out["weights"], ref["weights"], rtol=1e-3, atol=1e-5)
 
 
-def test_render_tensor_core_path_vs_oracle(dev, scene):
-    _, _, _, out = _render(dev, scene, "tc")
+@pytest.mark.parametrize("impl", ["tc", "tc2"])
+def test_render_tensor_core_path_vs_oracle(dev, scene, impl):
+    _, _, _, out = _render(dev, scene, impl)
     ref = scene["ref"]
     assert float((out["rgb"] - ref["rgb"]).abs().max()) <= 5e-3
     assert float((out["visibility"] - ref["visibility"]).abs().max()) <= 2e-2
@@ -91,7 +92,7 @@ def test_render_tensor_core_path_vs_oracle(dev, scene):
 def test_render_all_tensor_core_vs_oracle(dev, scene):
     """K2 and K4 both on tcgen05 (fp16 operands): the throughput configuration.  Stated tolerances: rgb 1e-2 absolute,
     accumulation / depth 5e-3 relative, rendered normal 1e-2 absolute."""
-    _, _, _, out = _render(dev, scene, "tc", "tc")
+    _, _, _, out = _render(dev, scene, "tc2", "tc")
     ref = scene["ref"]
     errs = {k: float((out[k] - ref[k]).abs().max()) for k in ("rgb", "accumulation", "depth", "normal", "albedo")}
     print(errs)
