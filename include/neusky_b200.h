@@ -92,6 +92,17 @@ int nsk_neus_composite_fwd(const float* sdf, const float* grad, const float* alb
                            int64_t R, int S, float inv_s, float cos_anneal_ratio, int training,
                            float* weights, float* wa, float* normals, float* acc, float* p2p_raw,
                            float* normal_out, float* albedo_out, float* bg_T, float* steps_minmax, void* stream);
+/* Backward of nsk_neus_composite_fwd (training mode: no output clamps): cotangents of weights [R,S], wa [R,S,3], normals
+ * [R,S,3], acc [R], p2p_raw [R], normal_out [R,3], albedo_out [R,3], bg_T [R] (any may be NULL = zero) ->
+ * d_sdf [R,S], d_grad [R,S,3], d_albedo [R,S,3] (OVERWRITTEN) and d_inv_s [1] (ACCUMULATED INTO; caller zero-fills).
+ * What torch autograd computes through SDFField.get_alpha, get_weights_and_transmittance_from_alphas and the renderers in
+ * the reference (neusky/fields/sdf_albedo_field.py:266, neusky/models/neusky_model.py:565, 591-595, 806-813). */
+int nsk_neus_composite_bwd(const float* sdf, const float* grad, const float* albedo, const float* ray_dirs,
+                           const float* starts, const float* ends, const float* deltas, int64_t R, int S,
+                           float inv_s, float cos_anneal_ratio, const float* g_weights, const float* g_wa,
+                           const float* g_normals, const float* g_acc, const float* g_p2p_raw,
+                           const float* g_normal_out, const float* g_albedo_out, const float* g_bg_T,
+                           float* d_sdf, float* d_grad, float* d_albedo, float* d_inv_s, void* stream);
 int nsk_neus_finalize_depth(const float* p2p_raw, const float* dnorm, const float* steps_minmax, int64_t R,
                             float* p2p, float* depth, void* stream);
 

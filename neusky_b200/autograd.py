@@ -1,0 +1,56 @@
+"""torch.autograd bindings of the C-ABI ops that have hand-written backward kernels (the "torch custom-op layer" of
+north_star for the training path).  Forward and backward both run the CUDA kernels; there is no torch fallback.
+
+  hash_encode(x, table, ...)      d/d table  (nsk_hash_encode_bwd; x is treated as a constant, like tcnn's default)
+  neus_composite(sdf, grad, albedo, inv_s, ...)   d/d sdf, grad, albedo, inv_s  (nsk_neus_composite_bwd)
+"""
+from __future__ import annotations
+
+from typing import Tuple
+
+import torch
+
+from . import ops
+
+Tensor = torch.Tensor
+
+
+class _HashEncode(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x: Tensor, table: Tensor, scalings: Tensor, log2_T: int) -> Tensor:
+        ctx.save_for_backward(x, scalings)
+        ctx.log2_T, ctx.table_shape = log2_T, table.shape
+        return ops.hash_encode(x, table, scalings, log2_T)
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        x, scalings = ctx.saved_tensors
+        return None, ops.hash_encode_bwd(x, scalings, ctx.log2_T, g.contiguous()), None, None
+
+
+def hash_encode(x: Tensor, table: Tensor, scalings: Tensor, log2_T: int) -> Tensor:
+    return _HashEncode.apply(x, table, scalings, log2_T)
+
+
+class _NeusComposite(torch.autograd.Function):
+    OUT = ("weights", "wa", "normals", "accumulation", "p2p_raw", "normal", "albedo", "bg_transmittance")
+
+    @staticmethod
+    def forward(ctx, sdf, grad, albedo, inv_s, ray_dirs, starts, ends, deltas, dnorm, cos_anneal_ratio: float):
+        o = ops.neus_composite(sdf, grad, albedo, ray_dirs, starts, ends, deltas, dnorm, float(inv_s), cos_anneal_ratio, True)
+        ctx.save_for_backward(sdf, grad, albedo, inv_s, ray_dirs, starts, ends, deltas)
+        ctx.rho = cos_anneal_ratio
+        return tuple(o[k] for k in _NeusComposite.OUT)
+
+    @staticmethod
+    def backward(ctx, *gs):
+        sdf, grad, albedo, inv_s, ray_dirs, starts, ends, deltas = ctx.saved_tensors
+        g = {k: (None if v is None else v.contiguous()) for k, v in zip(_NeusComposite.OUT, gs)}
+        d_sdf, d_grad, d_alb, d_inv = ops.neus_composite_bwd(sdf, grad, albedo, ray_dirs, starts, ends, deltas, float(inv_s), ctx.rho, g)
+        return d_sdf.reshape(sdf.shape), d_grad, d_alb, d_inv.reshape(inv_s.shape), None, None, None, None, None, None
+
+
+def neus_composite(sdf, grad, albedo, inv_s: Tensor, ray_dirs, starts, ends, deltas, dnorm, cos_anneal_ratio: float = 1.0) -> Tuple[Tensor, ...]:
+    """Differentiable K3 (training mode).  Returns (weights [R,S], wa [R,S,3], normals [R,S,3], accumulation [R],
+    p2p_raw [R], normal [R,3], albedo [R,3], bg_transmittance [R]); inv_s is a 0-dim / 1-element tensor."""
+    return _NeusComposite.apply(sdf, grad, albedo, inv_s, ray_dirs, starts, ends, deltas, dnorm, cos_anneal_ratio)

@@ -169,3 +169,156 @@ extern "C" int nsk_surface_points(const float* origins, const float* ray_dirs, c
   nsk::surface_points_kernel<<<(unsigned)((R + 255) / 256), 256, 0, nsk::as_stream(stream)>>>(origins, ray_dirs, p2p, R, radius, points);
   return nsk::check_launch("surface_points_kernel");
 }
+
+// =================================================================================================================
+// K3 backward: cotangents of every forward output -> d sdf, d gradient, d albedo (per sample) and d inv_s (scalar).
+// Same algebra that torch autograd derives for SDFField.get_alpha + get_weights_and_transmittance_from_alphas + the
+// renderers; one warp per ray, alpha / transmittance recomputed (nothing but the inputs is saved).
+//   w_s = alpha_s T_s,  T_{s+1} = T_s (1 - alpha_s + 1e-7):
+//   dL/dalpha_s = gw_s T_s - (sum_{k>s} gw_k w_k + g_bgT T_S) / (1 - alpha_s + 1e-7)        (gw = total cotangent of w)
+// =================================================================================================================
+namespace nsk {
+
+constexpr int NCB_MAX_CHUNKS = 32;   // S <= 1024
+
+__global__ void __launch_bounds__(NC_WARPS * 32)
+neus_composite_bwd_kernel(const float* __restrict__ sdf, const float* __restrict__ grad, const float* __restrict__ albedo,
+                          const float* __restrict__ ray_dirs, const float* __restrict__ starts, const float* __restrict__ ends,
+                          const float* __restrict__ deltas, int64_t R, int S, float inv_s, float rho,
+                          const float* __restrict__ g_weights, const float* __restrict__ g_wa, const float* __restrict__ g_normals,
+                          const float* __restrict__ g_acc, const float* __restrict__ g_p2p_raw, const float* __restrict__ g_normal_out,
+                          const float* __restrict__ g_albedo_out, const float* __restrict__ g_bgT,
+                          float* __restrict__ d_sdf, float* __restrict__ d_grad, float* __restrict__ d_albedo, float* __restrict__ d_inv_s) {
+  __shared__ float s_Tin[NC_WARPS][NCB_MAX_CHUNKS];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t warp_global = (int64_t)blockIdx.x * NC_WARPS + wib;
+  const int64_t warps_total = (int64_t)gridDim.x * NC_WARPS;
+  const int nchunks = (S + 31) / 32;
+  float dinv_acc = 0.f;
+
+  for (int64_t r = warp_global; r < R; r += warps_total) {
+    const float dx = ray_dirs[r * 3], dy = ray_dirs[r * 3 + 1], dz = ray_dirs[r * 3 + 2];
+    // alpha of sample i (recomputed); also returns the pieces the chain rule needs
+    auto alpha_of = [&](int64_t i, float& pc, float& nc, float& prv, float& nxt, float& tcos, bool& clipped) {
+      const float sd = sdf[i], dl = deltas[i];
+      tcos = dx * grad[i * 3] + dy * grad[i * 3 + 1] + dz * grad[i * 3 + 2];
+      const float ic = -(fmaxf(-tcos * 0.5f + 0.5f, 0.f) * (1.0f - rho) + fmaxf(-tcos, 0.f) * rho);
+      nxt = sd + ic * dl * 0.5f;
+      prv = sd - ic * dl * 0.5f;
+      pc = sigmoidf_(prv * inv_s);
+      nc = sigmoidf_(nxt * inv_s);
+      const float a = ((pc - nc) + 1e-5f) / (pc + 1e-5f);
+      clipped = !(a >= 0.f && a <= 1.f);
+      return fminf(fmaxf(a, 0.f), 1.f);
+    };
+    // ---- sweep 1: transmittance entering each 32-sample chunk, and the per-ray sums ----------------------------
+    float T_carry = 1.0f, acc = 0.f, dsum = 0.f;
+    for (int c = 0; c < nchunks; ++c) {
+      const int s = c * 32 + lane;
+      const bool ok = s < S;
+      const int64_t i = r * S + (ok ? s : S - 1);
+      float pc, nc, prv, nxt, tc; bool cl;
+      const float alpha = alpha_of(i, pc, nc, prv, nxt, tc, cl);
+      float incl = ok ? (1.0f - alpha + 1e-7f) : 1.0f;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const float up = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl *= up; }
+      float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+      if (lane == 0) excl = 1.0f;
+      if (lane == 0) s_Tin[wib][c] = T_carry;
+      const float w = ok ? alpha * T_carry * excl : 0.f;
+      acc += w;
+      dsum += w * (starts[i] + ends[i]) * 0.5f;
+      T_carry *= __shfl_sync(0xffffffffu, incl, 31);
+    }
+    acc = warp_sum(acc); dsum = warp_sum(dsum);
+    __syncwarp();
+    const float T_end = T_carry;
+    const float gacc = g_acc ? g_acc[r] : 0.f, gp2p = g_p2p_raw ? g_p2p_raw[r] : 0.f, gbg = g_bgT ? g_bgT[r] : 0.f;
+    float gno[3] = {0.f, 0.f, 0.f}, gao[3] = {0.f, 0.f, 0.f};
+    if (g_normal_out) { gno[0] = g_normal_out[r * 3]; gno[1] = g_normal_out[r * 3 + 1]; gno[2] = g_normal_out[r * 3 + 2]; }
+    if (g_albedo_out) { gao[0] = g_albedo_out[r * 3]; gao[1] = g_albedo_out[r * 3 + 1]; gao[2] = g_albedo_out[r * 3 + 2]; }
+    const float den = acc + 1e-10f;
+    // ---- sweep 2: chunks in reverse, suffix sums of gw_k w_k ---------------------------------------------------------
+    float suffix = gbg * T_end;
+    for (int c = nchunks - 1; c >= 0; --c) {
+      const int s = c * 32 + lane;
+      const bool ok = s < S;
+      const int64_t i = r * S + (ok ? s : S - 1);
+      float pc, nc, prv, nxt, tc; bool cl;
+      const float alpha = alpha_of(i, pc, nc, prv, nxt, tc, cl);
+      const float fct = ok ? (1.0f - alpha + 1e-7f) : 1.0f;
+      float incl = fct;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const float up = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl *= up; }
+      float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+      if (lane == 0) excl = 1.0f;
+      const float T = s_Tin[wib][c] * excl;
+      const float w = ok ? alpha * T : 0.f;
+      const float gx = grad[i * 3], gy = grad[i * 3 + 1], gz = grad[i * 3 + 2];
+      const float gn = fmaxf(sqrtf(gx * gx + gy * gy + gz * gz), 1e-12f);
+      const float nx = gx / gn, ny = gy / gn, nz = gz / gn;
+      const float ax = albedo[i * 3], ay = albedo[i * 3 + 1], az = albedo[i * 3 + 2];
+      const float mid = (starts[i] + ends[i]) * 0.5f;
+      float gwa0 = 0.f, gwa1 = 0.f, gwa2 = 0.f;
+      if (g_wa) { gwa0 = g_wa[i * 3]; gwa1 = g_wa[i * 3 + 1]; gwa2 = g_wa[i * 3 + 2]; }
+      // total cotangent of w_s
+      float gw = (g_weights ? g_weights[i] : 0.f) + gacc + gp2p * (mid / den - dsum / (den * den)) + gno[0] * nx + gno[1] * ny + gno[2] * nz +
+                 gao[0] * (ax - 1.0f) + gao[1] * (ay - 1.0f) + gao[2] * (az - 1.0f) + gwa0 * ax + gwa1 * ay + gwa2 * az;
+      if (!ok) gw = 0.f;
+      // suffix over k > s within the chunk (reverse exclusive scan of gw_k w_k) + everything after the chunk
+      const float v = gw * w;
+      float rincl = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const float dn = __shfl_down_sync(0xffffffffu, rincl, o); if (lane + o < 32) rincl += dn; }
+      float rexcl = __shfl_down_sync(0xffffffffu, rincl, 1);
+      if (lane == 31) rexcl = 0.f;
+      const float after = rexcl + suffix;
+      suffix += __shfl_sync(0xffffffffu, rincl, 0);
+      if (ok) {
+        float dalpha = gw * T - after / fct;
+        if (cl) dalpha = 0.f;                                     // clip(0,1) passes no gradient outside the interval
+        const float dpc = dalpha * nc / ((pc + 1e-5f) * (pc + 1e-5f));
+        const float dnc = -dalpha / (pc + 1e-5f);
+        const float dprv = dpc * pc * (1.0f - pc) * inv_s, dnxt = dnc * nc * (1.0f - nc) * inv_s;
+        dinv_acc += dpc * pc * (1.0f - pc) * prv + dnc * nc * (1.0f - nc) * nxt;
+        d_sdf[i] = dprv + dnxt;
+        const float dic = (dnxt - dprv) * deltas[i] * 0.5f;
+        const float dtc = dic * (((-tc * 0.5f + 0.5f) > 0.f ? (1.0f - rho) * 0.5f : 0.f) + ((-tc) > 0.f ? rho : 0.f));
+        // normals_s = g/|g|: cotangent from the rendered normal and from the shading pass
+        float dn0 = w * gno[0], dn1 = w * gno[1], dn2 = w * gno[2];
+        if (g_normals) { dn0 += g_normals[i * 3]; dn1 += g_normals[i * 3 + 1]; dn2 += g_normals[i * 3 + 2]; }
+        const float dot = dn0 * nx + dn1 * ny + dn2 * nz;
+        d_grad[i * 3] = dtc * dx + (dn0 - dot * nx) / gn;
+        d_grad[i * 3 + 1] = dtc * dy + (dn1 - dot * ny) / gn;
+        d_grad[i * 3 + 2] = dtc * dz + (dn2 - dot * nz) / gn;
+        d_albedo[i * 3] = w * (gao[0] + gwa0);
+        d_albedo[i * 3 + 1] = w * (gao[1] + gwa1);
+        d_albedo[i * 3 + 2] = w * (gao[2] + gwa2);
+      }
+    }
+    __syncwarp();
+  }
+  dinv_acc = warp_sum(dinv_acc);
+  if (lane == 0 && dinv_acc != 0.f) atomicAdd(d_inv_s, dinv_acc);
+}
+
+}  // namespace nsk
+
+extern "C" int nsk_neus_composite_bwd(const float* sdf, const float* grad, const float* albedo, const float* ray_dirs,
+                                      const float* starts, const float* ends, const float* deltas, int64_t R, int S,
+                                      float inv_s, float cos_anneal_ratio, const float* g_weights, const float* g_wa,
+                                      const float* g_normals, const float* g_acc, const float* g_p2p_raw,
+                                      const float* g_normal_out, const float* g_albedo_out, const float* g_bg_T,
+                                      float* d_sdf, float* d_grad, float* d_albedo, float* d_inv_s, void* stream) {
+  if (R == 0) return 0;
+  NSK_REQUIRE(S >= 1 && S <= 32 * nsk::NCB_MAX_CHUNKS, "nsk_neus_composite_bwd: S must be in [1, 1024]");
+  NSK_REQUIRE(sdf && grad && albedo && ray_dirs && starts && ends && deltas && d_sdf && d_grad && d_albedo && d_inv_s,
+              "nsk_neus_composite_bwd: null pointer");
+  int64_t blocks = (R + nsk::NC_WARPS - 1) / nsk::NC_WARPS;
+  const int64_t cap = 148 * 8 * 8;
+  if (blocks > cap) blocks = cap;
+  nsk::neus_composite_bwd_kernel<<<(unsigned)blocks, nsk::NC_WARPS * 32, 0, nsk::as_stream(stream)>>>(
+      sdf, grad, albedo, ray_dirs, starts, ends, deltas, R, S, inv_s, cos_anneal_ratio, g_weights, g_wa, g_normals, g_acc,
+      g_p2p_raw, g_normal_out, g_albedo_out, g_bg_T, d_sdf, d_grad, d_albedo, d_inv_s);
+  return nsk::check_launch("neus_composite_bwd_kernel");
+}

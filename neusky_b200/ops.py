@@ -145,6 +145,24 @@ def neus_composite(sdf, grad, albedo, ray_dirs, starts, ends, deltas, dnorm, inv
     return out
 
 
+def neus_composite_bwd(sdf, grad, albedo, ray_dirs, starts, ends, deltas, inv_s: float, cos_anneal_ratio: float, g: Dict[str, Optional[Tensor]]):
+    """Cotangents g[{"weights","wa","normals","accumulation","p2p_raw","normal","albedo","bg_transmittance"}] (missing / None = 0)
+    -> (d_sdf [R,S], d_grad [R,S,3], d_albedo [R,S,3], d_inv_s [1])."""
+    R, S = sdf.shape[0], sdf.shape[1]
+    sdf = _chk("sdf", sdf.reshape(R, S))
+    grad, albedo = _chk("grad", grad, shape=(R, S, 3)), _chk("albedo", albedo, shape=(R, S, 3))
+    ray_dirs = _chk("ray_dirs", ray_dirs, shape=(R, 3))
+    starts, ends, deltas = (_chk(n, t.reshape(R, S)) for n, t in (("starts", starts), ("ends", ends), ("deltas", deltas)))
+    shapes = {"weights": (R, S), "wa": (R, S, 3), "normals": (R, S, 3), "accumulation": (R,), "p2p_raw": (R,), "normal": (R, 3), "albedo": (R, 3), "bg_transmittance": (R,)}
+    gg = {k: (None if g.get(k) is None else _chk("g_" + k, g[k].reshape(shp), shape=shp)) for k, shp in shapes.items()}
+    f = dict(device=sdf.device, dtype=torch.float32)
+    d_sdf, d_grad, d_alb, d_inv = torch.empty((R, S), **f), torch.empty((R, S, 3), **f), torch.empty((R, S, 3), **f), torch.zeros((1,), **f)
+    _lib.check(_lib.load().nsk_neus_composite_bwd(_ptr(sdf), _ptr(grad), _ptr(albedo), _ptr(ray_dirs), _ptr(starts), _ptr(ends), _ptr(deltas), c_int64(R), c_int(S), c_float(inv_s), c_float(cos_anneal_ratio),
+                                                  _ptr(gg["weights"]), _ptr(gg["wa"]), _ptr(gg["normals"]), _ptr(gg["accumulation"]), _ptr(gg["p2p_raw"]), _ptr(gg["normal"]), _ptr(gg["albedo"]), _ptr(gg["bg_transmittance"]),
+                                                  _ptr(d_sdf), _ptr(d_grad), _ptr(d_alb), _ptr(d_inv), _stream(sdf)), "nsk_neus_composite_bwd")
+    return d_sdf, d_grad, d_alb, d_inv
+
+
 def surface_points(origins: Tensor, ray_dirs: Tensor, p2p: Tensor, radius: float) -> Tensor:
     R = origins.shape[0]
     origins, ray_dirs = _chk("origins", origins, shape=(R, 3)), _chk("ray_dirs", ray_dirs, shape=(R, 3))

@@ -1,0 +1,87 @@
+"""Backward kernels vs torch autograd through the CPU oracle (fp64), driven through neusky_b200.autograd."""
+import pytest
+import torch
+
+from neusky_b200 import init as nb_init
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from neusky_b200 import _lib
+
+    _lib.load()
+    return torch.device("cuda:0")
+
+
+def _case(R, S, seed):
+    g = torch.Generator().manual_seed(seed)
+    t = torch.sort(torch.rand(R, S + 1, generator=g) * 2.0 + 0.05, dim=1).values
+    starts, ends = t[:, :-1, None].contiguous(), t[:, 1:, None].contiguous()
+    ray_dirs = torch.nn.functional.normalize(torch.randn(R, 3, generator=g), dim=-1)
+    sdf = (1.0 - (starts + ends) / 2) * 0.3 + 0.02 * torch.randn(R, S, 1, generator=g)
+    grad = -ray_dirs[:, None, :] * (0.7 + 0.6 * torch.rand(R, S, 1, generator=g)) + 0.3 * torch.randn(R, S, 3, generator=g)
+    albedo = torch.rand(R, S, 3, generator=g)
+    dnorm = 1.0 + torch.rand(R, 1, generator=g)
+    return sdf, grad, albedo, ray_dirs, starts, ends, dnorm
+
+
+@pytest.mark.parametrize("R,S,rho", [(3, 5, 1.0), (17, 48, 1.0), (9, 128, 0.3), (4, 200, 1.0)])
+def test_neus_composite_backward_vs_oracle_autograd(dev, R, S, rho):
+    from neusky_b200 import autograd as nba
+    from oracle import neusky_oracle as O
+
+    sdf, grad, albedo, ray_dirs, starts, ends, dnorm = _case(R, S, R * 31 + S)
+    inv_s0 = 12.0
+    g = torch.Generator().manual_seed(5)
+    # random cotangents for every output
+    cot = {"weights": torch.randn(R, S, generator=g), "wa": torch.randn(R, S, 3, generator=g), "normals": torch.randn(R, S, 3, generator=g),
+           "accumulation": torch.randn(R, generator=g), "p2p_raw": torch.randn(R, generator=g), "normal": torch.randn(R, 3, generator=g),
+           "albedo": torch.randn(R, 3, generator=g), "bg_transmittance": torch.randn(R, generator=g)}
+
+    # ---- reference: fp64 autograd through the oracle ----
+    a = [t.double().requires_grad_(True) for t in (sdf, grad, albedo)]
+    inv_ref = torch.tensor(inv_s0, dtype=torch.float64, requires_grad=True)
+    alpha = O.neus_alpha(a[0], a[1], ray_dirs.double()[:, None, :], (ends - starts).double(), inv_ref, rho)
+    w, T = O.weights_from_alphas(alpha)
+    normals = torch.nn.functional.normalize(a[1], dim=-1)
+    steps = ((starts + ends) / 2).double()
+    acc = w.sum(-2)
+    outs = {"weights": w[..., 0], "wa": w * a[2], "normals": normals, "accumulation": acc[:, 0], "p2p_raw": ((w * steps).sum(-2) / (acc + 1e-10))[:, 0],
+            "normal": (w * normals).sum(-2), "albedo": (w * a[2]).sum(-2) + (1.0 - acc), "bg_transmittance": T[:, -1, 0]}
+    loss = sum((outs[k] * cot[k].double()).sum() for k in cot)
+    loss.backward()
+
+    # ---- CUDA ----
+    dv = lambda t: t.to(dev).requires_grad_(True)
+    sd, gr, al = dv(sdf), dv(grad), dv(albedo)
+    inv_t = torch.tensor(inv_s0, device=dev, requires_grad=True)
+    o = nba.neus_composite(sd, gr, al, inv_t, ray_dirs.to(dev), starts.to(dev), ends.to(dev), (ends - starts).to(dev), dnorm.to(dev), rho)
+    names = ("weights", "wa", "normals", "accumulation", "p2p_raw", "normal", "albedo", "bg_transmittance")
+    for k, t in zip(names, o):
+        assert torch.allclose(t.detach().cpu().double(), outs[k].detach().reshape(t.shape), rtol=2e-4, atol=2e-6), k
+    sum((t * cot[k].to(dev).reshape(t.shape)).sum() for k, t in zip(names, o)).backward()
+    for name, got, ref in (("sdf", sd.grad, a[0].grad), ("grad", gr.grad, a[1].grad), ("albedo", al.grad, a[2].grad)):
+        ref = ref.float()
+        scale = ref.abs().max().clamp_min(1e-6)
+        err = (got.cpu().reshape(ref.shape) - ref).abs().max() / scale
+        assert float(err) <= 2e-3, (name, float(err))
+    assert abs(float(inv_t.grad) - float(inv_ref.grad)) <= 2e-3 * max(1.0, abs(float(inv_ref.grad)))
+
+
+def test_hash_encode_autograd_table_gradient(dev):
+    from neusky_b200 import autograd as nba
+    from oracle import neusky_oracle as O
+
+    log2_T, L = 12, 16
+    table = nb_init.init_hash_table(4, L, log2_T)
+    sc = O.hash_scalings(L)
+    x = torch.rand(2000, 3, generator=torch.Generator().manual_seed(2)) * 2 - 1
+    t_ref = table.clone().requires_grad_(True)
+    (O.hash_encode(x, t_ref, sc, log2_T) ** 2).sum().backward()
+    t_gpu = table.to(dev).requires_grad_(True)
+    (nba.hash_encode(x.to(dev), t_gpu, sc.to(dev), log2_T) ** 2).sum().backward()
+    assert torch.allclose(t_gpu.grad.cpu(), t_ref.grad, rtol=1e-4, atol=1e-8)
