@@ -143,6 +143,16 @@ int nsk_lambert_prep(const float* normals, const float* wa, int64_t R, int S, co
 int nsk_lambert_relight(const float* normals, const float* wa, const float* inv_count, int64_t R, int S,
                         const float* dirs, const int32_t* sel_index, int D, int Dp, const float* radiance,
                         const int32_t* cam, const float* vis_sel, float unoccluded_vis, float* rgb_lin, void* stream);
+/* Backward of nsk_lambert_relight for a cotangent g_rgb_lin [R,3]: d_wa [R,S,3], d_normals [R,S,3] (overwritten),
+ * d_vis_sel [R,Dp] (overwritten; NULL = skip), d_radiance [K,D,3] (ACCUMULATED INTO with atomics; NULL = skip).  The
+ * positively-lit count is piecewise constant, as in torch autograd through renderers.py:93-113. */
+int nsk_lambert_relight_bwd(const float* normals, const float* wa, const float* inv_count, int64_t R, int S,
+                            const float* dirs, const int32_t* sel_index, int D, int Dp, const float* radiance,
+                            const int32_t* cam, const float* vis_sel, float unoccluded_vis, const float* g_rgb_lin,
+                            float* d_wa, float* d_normals, float* d_vis_sel, float* d_radiance, void* stream);
+/* Backward of nsk_shade_finalize: d_rgb_lin [R,3], d_bg [R,3], d_acc [R]. */
+int nsk_shade_finalize_bwd(const float* rgb_lin, const float* bg, const float* acc, const float* g_rgb, int64_t R,
+                           float* d_rgb_lin, float* d_bg, float* d_acc, void* stream);
 int nsk_shade_finalize(const float* rgb_lin, const float* bg, const float* acc, int64_t R, int training,
                        float* rgb, void* stream);
 

@@ -3,6 +3,8 @@ north_star for the training path).  Forward and backward both run the CUDA kerne
 
   hash_encode(x, table, ...)      d/d table  (nsk_hash_encode_bwd; x is treated as a constant, like tcnn's default)
   neus_composite(sdf, grad, albedo, inv_s, ...)   d/d sdf, grad, albedo, inv_s  (nsk_neus_composite_bwd)
+  lambert_shade(normals, wa, radiance, vis, ...)   d/d normals, wa, radiance, visibility  (nsk_lambert_relight_bwd)
+  shade_finalize(rgb_lin, bg, acc)                 d/d rgb_lin, bg, acc  (nsk_shade_finalize_bwd)
 """
 from __future__ import annotations
 
@@ -54,3 +56,41 @@ def neus_composite(sdf, grad, albedo, inv_s: Tensor, ray_dirs, starts, ends, del
     """Differentiable K3 (training mode).  Returns (weights [R,S], wa [R,S,3], normals [R,S,3], accumulation [R],
     p2p_raw [R], normal [R,3], albedo [R,3], bg_transmittance [R]); inv_s is a 0-dim / 1-element tensor."""
     return _NeusComposite.apply(sdf, grad, albedo, inv_s, ray_dirs, starts, ends, deltas, dnorm, cos_anneal_ratio)
+
+
+class _LambertShade(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, normals, wa, radiance, vis_sel, inv_count, dirs, sel_index, cam, unocc: float):
+        ctx.save_for_backward(normals, wa, radiance, vis_sel, inv_count, dirs, sel_index, cam if cam is not None else torch.empty(0))
+        ctx.has_cam, ctx.unocc = cam is not None, unocc
+        return ops.lambert_relight(normals, wa, inv_count, dirs, sel_index, radiance, vis_sel, cam, unocc)
+
+    @staticmethod
+    def backward(ctx, g):
+        normals, wa, radiance, vis_sel, inv_count, dirs, sel_index, cam = ctx.saved_tensors
+        cam = cam if ctx.has_cam else None
+        d_wa, d_n, d_vis, d_rad = ops.lambert_relight_bwd(normals, wa, inv_count, dirs, sel_index, radiance, vis_sel, g.contiguous(), cam, ctx.unocc,
+                                                          ctx.needs_input_grad[3], ctx.needs_input_grad[2])
+        return d_n, d_wa, d_rad, d_vis, None, None, None, None, None
+
+
+def lambert_shade(normals, wa, radiance, vis_sel, inv_count, dirs, sel_index, cam=None, unoccluded_vis: float = 1.0) -> Tensor:
+    """Differentiable Lambertian sum with given per-ray visibility: linear rgb [R,3] (renderers.py:93-113)."""
+    return _LambertShade.apply(normals, wa, radiance, vis_sel, inv_count, dirs, sel_index, cam, unoccluded_vis)
+
+
+class _ShadeFinalize(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rgb_lin, bg, acc):
+        ctx.save_for_backward(rgb_lin, bg, acc)
+        return ops.shade_finalize(rgb_lin, bg, acc, training=True)
+
+    @staticmethod
+    def backward(ctx, g):
+        rgb_lin, bg, acc = ctx.saved_tensors
+        d_lin, d_bg, d_acc = ops.shade_finalize_bwd(rgb_lin, bg, acc, g.contiguous())
+        return d_lin, d_bg, d_acc.reshape(acc.shape)
+
+
+def shade_finalize(rgb_lin, bg, acc) -> Tensor:
+    return _ShadeFinalize.apply(rgb_lin, bg, acc)

@@ -71,6 +71,90 @@ lambert_relight_kernel(const float* __restrict__ normals, const float* __restric
   if (lane == 0) { rgb_lin[ray * 3] = o0; rgb_lin[ray * 3 + 1] = o1; rgb_lin[ray * 3 + 2] = o2; }
 }
 
+// Backward of lambert_relight_kernel for a cotangent g [R,3] of rgb_lin:
+//   d wa [R,S,3], d normals [R,S,3] (lanes = samples), d vis_sel [R,Dp], d radiance [K,D,3] (lanes = directions, atomics).
+// The count of positively lit directions is piecewise constant (no gradient), as in torch (renderers.py:101-106).
+__global__ void __launch_bounds__(LP_WARPS * 32)
+lambert_relight_bwd_kernel(const float* __restrict__ normals, const float* __restrict__ wa, const float* __restrict__ inv_count,
+                           int64_t R, int S, const float* __restrict__ dirs, const int32_t* __restrict__ sel_index, int D, int Dp,
+                           const float* __restrict__ radiance, const int32_t* __restrict__ cam, const float* __restrict__ vis_sel,
+                           float unocc_vis, const float* __restrict__ g_rgb, float* __restrict__ d_wa, float* __restrict__ d_normals,
+                           float* __restrict__ d_vis_sel, float* __restrict__ d_radiance) {
+  const int lane = threadIdx.x & 31;
+  const int64_t ray = (int64_t)blockIdx.x * LP_WARPS + (threadIdx.x >> 5);
+  if (ray >= R) return;
+  const int64_t krow = (int64_t)(cam ? cam[ray] : 0) * D * 3;
+  const float* rad = radiance + krow;
+  const float* vr = vis_sel + ray * Dp;
+  const float g0 = g_rgb[ray * 3], g1 = g_rgb[ray * 3 + 1], g2 = g_rgb[ray * 3 + 2];
+  // ---- pass A: lanes over directions -> d vis, d radiance -------------------------------------------------------
+  for (int j = lane; j < D; j += 32) {
+    const float lx = dirs[j * 3], ly = dirs[j * 3 + 1], lz = dirs[j * 3 + 2];
+    const int sj = sel_index[j];
+    const float v = sj >= 0 ? vr[sj] : unocc_vis;
+    float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+    for (int s = 0; s < S; ++s) {
+      const int64_t i = ray * S + s;
+      float c = normals[i * 3] * lx + normals[i * 3 + 1] * ly + normals[i * 3 + 2] * lz;
+      c = fminf(fmaxf(c, 0.f), 1.f) * inv_count[i];
+      c0 = fmaf(wa[i * 3], c, c0); c1 = fmaf(wa[i * 3 + 1], c, c1); c2 = fmaf(wa[i * 3 + 2], c, c2);
+    }
+    if (sj >= 0 && d_vis_sel) d_vis_sel[ray * Dp + sj] = g0 * c0 * rad[j * 3] + g1 * c1 * rad[j * 3 + 1] + g2 * c2 * rad[j * 3 + 2];
+    if (d_radiance) {
+      atomicAdd(d_radiance + krow + j * 3, g0 * c0 * v);
+      atomicAdd(d_radiance + krow + j * 3 + 1, g1 * c1 * v);
+      atomicAdd(d_radiance + krow + j * 3 + 2, g2 * c2 * v);
+    }
+  }
+  // ---- pass B: lanes over samples -> d wa, d normals ------------------------------------------------------------
+  for (int s = lane; s < S; s += 32) {
+    const int64_t i = ray * S + s;
+    const float nx = normals[i * 3], ny = normals[i * 3 + 1], nz = normals[i * 3 + 2];
+    const float w0 = wa[i * 3], w1 = wa[i * 3 + 1], w2 = wa[i * 3 + 2];
+    const float ic = inv_count[i];
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, dn0 = 0.f, dn1 = 0.f, dn2 = 0.f;
+    for (int j = 0; j < D; ++j) {
+      const float lx = dirs[j * 3], ly = dirs[j * 3 + 1], lz = dirs[j * 3 + 2];
+      const int sj = sel_index[j];
+      const float v = (sj >= 0 ? vr[sj] : unocc_vis) * ic;
+      const float craw = nx * lx + ny * ly + nz * lz;
+      const float c = fminf(fmaxf(craw, 0.f), 1.f);
+      const float r0 = rad[j * 3] * g0, r1 = rad[j * 3 + 1] * g1, r2 = rad[j * 3 + 2] * g2;
+      a0 = fmaf(r0, c * v, a0); a1 = fmaf(r1, c * v, a1); a2 = fmaf(r2, c * v, a2);
+      if (craw >= 0.f && craw <= 1.f) {                     // clamp passes the gradient inside [0,1]
+        const float k = (w0 * r0 + w1 * r1 + w2 * r2) * v;
+        dn0 = fmaf(k, lx, dn0); dn1 = fmaf(k, ly, dn1); dn2 = fmaf(k, lz, dn2);
+      }
+    }
+    d_wa[i * 3] = a0; d_wa[i * 3 + 1] = a1; d_wa[i * 3 + 2] = a2;
+    d_normals[i * 3] = dn0; d_normals[i * 3 + 1] = dn1; d_normals[i * 3 + 2] = dn2;
+  }
+}
+
+// d rgb_lin, d bg, d acc of rgb = srgb(rgb_lin + bg (1 - acc)) (training: linear_to_sRGB clamps to [0,1], no gradient outside)
+__global__ void shade_finalize_bwd_kernel(const float* __restrict__ rgb_lin, const float* __restrict__ bg, const float* __restrict__ acc,
+                                          const float* __restrict__ g_rgb, int64_t R, float* __restrict__ d_lin, float* __restrict__ d_bg,
+                                          float* __restrict__ d_acc) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  float dacc = 0.f;
+  const float t = 1.0f - acc[r];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float x = rgb_lin[r * 3 + c] + bg[r * 3 + c] * t;
+    float d;
+    if (x <= 0.0031308f) d = 12.92f;
+    else d = 1.055f / 2.4f * powf(fabsf(x), 1.0f / 2.4f - 1.0f);
+    const float y = (x <= 0.0031308f) ? 12.92f * x : 1.055f * powf(fabsf(x), 1.0f / 2.4f) - 0.055f;
+    if (!(y >= 0.f && y <= 1.f)) d = 0.f;
+    const float gx = g_rgb[r * 3 + c] * d;
+    d_lin[r * 3 + c] = gx;
+    d_bg[r * 3 + c] = gx * t;
+    dacc -= gx * bg[r * 3 + c];
+  }
+  d_acc[r] = dacc;
+}
+
 __device__ __forceinline__ float srgb(float c) {
   // neusky/utils/utils.py:25-30
   const float v = (c <= 0.0031308f) ? 12.92f * c : 1.055f * powf(fabsf(c), 1.0f / 2.4f) - 0.055f;
@@ -122,4 +206,28 @@ extern "C" int nsk_lambert_relight(const float* normals, const float* wa, const 
   nsk::lambert_relight_kernel<<<(unsigned)blocks, nsk::LP_WARPS * 32, 0, nsk::as_stream(stream)>>>(
       normals, wa, inv_count, R, S, dirs, sel_index, D, Dp, radiance, cam, vis_sel, unoccluded_vis, rgb_lin);
   return nsk::check_launch("lambert_relight_kernel");
+}
+
+extern "C" int nsk_lambert_relight_bwd(const float* normals, const float* wa, const float* inv_count, int64_t R, int S,
+                                       const float* dirs, const int32_t* sel_index, int D, int Dp, const float* radiance,
+                                       const int32_t* cam, const float* vis_sel, float unoccluded_vis, const float* g_rgb_lin,
+                                       float* d_wa, float* d_normals, float* d_vis_sel, float* d_radiance, void* stream) {
+  if (R == 0) return 0;
+  NSK_REQUIRE(S >= 1 && D >= 1, "nsk_lambert_relight_bwd: S and D must be >= 1");
+  NSK_REQUIRE(normals && wa && inv_count && dirs && sel_index && radiance && g_rgb_lin && d_wa && d_normals && (vis_sel || Dp == 0),
+              "nsk_lambert_relight_bwd: null pointer");
+  const int64_t blocks = (R + nsk::LP_WARPS - 1) / nsk::LP_WARPS;
+  NSK_REQUIRE(blocks < (1ll << 31), "nsk_lambert_relight_bwd: too many rays for one launch");
+  nsk::lambert_relight_bwd_kernel<<<(unsigned)blocks, nsk::LP_WARPS * 32, 0, nsk::as_stream(stream)>>>(
+      normals, wa, inv_count, R, S, dirs, sel_index, D, Dp, radiance, cam, vis_sel, unoccluded_vis, g_rgb_lin, d_wa, d_normals,
+      d_vis_sel, d_radiance);
+  return nsk::check_launch("lambert_relight_bwd_kernel");
+}
+
+extern "C" int nsk_shade_finalize_bwd(const float* rgb_lin, const float* bg, const float* acc, const float* g_rgb, int64_t R,
+                                      float* d_rgb_lin, float* d_bg, float* d_acc, void* stream) {
+  if (R == 0) return 0;
+  NSK_REQUIRE(rgb_lin && bg && acc && g_rgb && d_rgb_lin && d_bg && d_acc, "nsk_shade_finalize_bwd: null pointer");
+  nsk::shade_finalize_bwd_kernel<<<(unsigned)((R + 255) / 256), 256, 0, nsk::as_stream(stream)>>>(rgb_lin, bg, acc, g_rgb, R, d_rgb_lin, d_bg, d_acc);
+  return nsk::check_launch("shade_finalize_bwd_kernel");
 }

@@ -228,6 +228,38 @@ def lambert_relight(normals, wa, inv_count, dirs, sel_index, radiance, vis_sel, 
     return rgb_lin
 
 
+def lambert_relight_bwd(normals, wa, inv_count, dirs, sel_index, radiance, vis_sel, g_rgb_lin, cam=None, unoccluded_vis: float = 1.0, want_vis: bool = True, want_radiance: bool = True):
+    """-> (d_wa [R,S,3], d_normals [R,S,3], d_vis_sel [R,Dp] | None, d_radiance [K,D,3] | None)."""
+    R, S = normals.shape[0], normals.shape[1]
+    D, Dp = dirs.shape[0], vis_sel.shape[1]
+    normals, wa = _chk("normals", normals, shape=(R, S, 3)), _chk("wa", wa, shape=(R, S, 3))
+    inv_count = _chk("inv_count", inv_count, shape=(R, S))
+    dirs = _chk("dirs", dirs, shape=(D, 3))
+    sel_index = _chk("sel_index", sel_index, dtype=torch.int32, shape=(D,))
+    radiance = _chk("radiance", radiance, shape=(None, D, 3))
+    vis_sel = _chk("vis_sel", vis_sel, shape=(R, Dp))
+    g = _chk("g_rgb_lin", g_rgb_lin, shape=(R, 3))
+    if cam is not None:
+        cam = _chk("cam", cam, dtype=torch.int32, shape=(R,))
+    f = dict(device=normals.device, dtype=torch.float32)
+    d_wa, d_n = torch.empty((R, S, 3), **f), torch.empty((R, S, 3), **f)
+    d_vis = torch.empty((R, Dp), **f) if want_vis else None
+    d_rad = torch.zeros(tuple(radiance.shape), **f) if want_radiance else None
+    _lib.check(_lib.load().nsk_lambert_relight_bwd(_ptr(normals), _ptr(wa), _ptr(inv_count), c_int64(R), c_int(S), _ptr(dirs), _ptr(sel_index), c_int(D), c_int(Dp), _ptr(radiance), _ptr(cam), _ptr(vis_sel),
+                                                   c_float(unoccluded_vis), _ptr(g), _ptr(d_wa), _ptr(d_n), _ptr(d_vis), _ptr(d_rad), _stream(normals)), "nsk_lambert_relight_bwd")
+    return d_wa, d_n, d_vis, d_rad
+
+
+def shade_finalize_bwd(rgb_lin, bg, acc, g_rgb):
+    R = rgb_lin.shape[0]
+    rgb_lin, bg, g_rgb = _chk("rgb_lin", rgb_lin, shape=(R, 3)), _chk("bg", bg, shape=(R, 3)), _chk("g_rgb", g_rgb, shape=(R, 3))
+    acc = _chk("acc", acc.reshape(R))
+    f = dict(device=rgb_lin.device, dtype=torch.float32)
+    d_lin, d_bg, d_acc = torch.empty((R, 3), **f), torch.empty((R, 3), **f), torch.empty((R,), **f)
+    _lib.check(_lib.load().nsk_shade_finalize_bwd(_ptr(rgb_lin), _ptr(bg), _ptr(acc), _ptr(g_rgb), c_int64(R), _ptr(d_lin), _ptr(d_bg), _ptr(d_acc), _stream(rgb_lin)), "nsk_shade_finalize_bwd")
+    return d_lin, d_bg, d_acc
+
+
 def shade_finalize(rgb_lin, bg, acc, training: bool = False) -> Tensor:
     R = rgb_lin.shape[0]
     rgb_lin, bg = _chk("rgb_lin", rgb_lin, shape=(R, 3)), _chk("bg", bg, shape=(R, 3))

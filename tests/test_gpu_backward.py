@@ -85,3 +85,47 @@ def test_hash_encode_autograd_table_gradient(dev):
     t_gpu = table.to(dev).requires_grad_(True)
     (nba.hash_encode(x.to(dev), t_gpu, sc.to(dev), log2_T) ** 2).sum().backward()
     assert torch.allclose(t_gpu.grad.cpu(), t_ref.grad, rtol=1e-4, atol=1e-8)
+
+
+def test_lambert_shade_and_finalize_backward_vs_oracle_autograd(dev):
+    from neusky_b200 import autograd as nba, ops
+    from oracle import neusky_oracle as O
+
+    R, S, D, K = 13, 6, 70, 3
+    g = torch.Generator().manual_seed(8)
+    normals = torch.nn.functional.normalize(torch.randn(R, S, 3, generator=g), dim=-1)
+    wa = torch.rand(R, S, 3, generator=g) / S
+    dirs = torch.nn.functional.normalize(torch.randn(D, 3, generator=g), dim=-1)
+    rad = torch.exp(0.5 * torch.randn(K, D, 3, generator=g))
+    mask = dirs[:, 2] > 0
+    Dp = int(mask.sum())
+    vis_sel = torch.rand(R, Dp, generator=g)
+    cam = torch.randint(0, K, (R,), generator=g)
+    bg = torch.rand(R, 3, generator=g)
+    acc = torch.rand(R, generator=g)
+    cot = torch.randn(R, 3, generator=g)
+
+    # reference: fp64 autograd through the oracle's renderer pieces
+    n64, w64, r64, v64, b64, a64 = (t.double().requires_grad_(True) for t in (normals, wa, rad, vis_sel, bg, acc))
+    vis_full = torch.ones(R, D, dtype=torch.float64)
+    vis_full = vis_full.index_put((torch.arange(R)[:, None], torch.nonzero(mask)[:, 0][None, :].expand(R, Dp)), v64)
+    lin = torch.zeros(R, 3, dtype=torch.float64)
+    for s in range(S):
+        lin = lin + w64[:, s] * O.lambertian_radiance(torch.ones(R, 3, dtype=torch.float64), n64[:, s], dirs.double(), r64[cam], vis_full)
+    rgb_ref = O.linear_to_srgb(lin + b64 * (1.0 - a64[:, None]))
+    (rgb_ref * cot.double()).sum().backward()
+
+    dv = lambda t: t.to(dev).requires_grad_(True)
+    n, w, r, v, b, a = dv(normals), dv(wa), dv(rad), dv(vis_sel), dv(bg), dv(acc)
+    dirs_d = dirs.to(dev)
+    m = mask.to(dev)
+    sel_index = torch.where(m, torch.cumsum(m.to(torch.int32), 0, dtype=torch.int32) - 1, torch.full_like(m, -1, dtype=torch.int32)).to(torch.int32)
+    inv_count, _ = ops.lambert_prep(n.detach(), w.detach(), dirs_d, m.to(torch.uint8), r.detach(), cam.to(dev, torch.int32), 1.0)
+    lin_g = nba.lambert_shade(n, w, r, v, inv_count, dirs_d, sel_index, cam.to(dev, torch.int32))
+    rgb = nba.shade_finalize(lin_g, b, a)
+    assert torch.allclose(rgb.detach().cpu().double(), rgb_ref.detach(), rtol=1e-4, atol=1e-5)
+    (rgb * cot.to(dev)).sum().backward()
+    for name, got, ref in (("normals", n.grad, n64.grad), ("wa", w.grad, w64.grad), ("radiance", r.grad, r64.grad), ("vis", v.grad, v64.grad), ("bg", b.grad, b64.grad), ("acc", a.grad, a64.grad)):
+        ref = ref.float()
+        err = (got.cpu() - ref).abs().max() / ref.abs().max().clamp_min(1e-6)
+        assert float(err) <= 2e-3, (name, float(err))
