@@ -47,6 +47,17 @@ int nsk_hash_encode_fwd(const float* x, int64_t n, const float* table, const flo
 int nsk_hash_encode_bwd(const float* x, int64_t n, const float* scalings, int num_levels, int log2_T,
                         const float* grad_out, float* grad_table, void* stream);
 
+/* d L / d x through the trilinear interpolation (what autograd returns for the encode's input): grad_x [n,3] =
+ * sum_l scale_l * sum_ch grad_out[.,l,ch] * d feat / d offset.  The reference gets its normals this way
+ * (torch.autograd.grad(sdf, x, create_graph=True), neusky/fields/sdf_albedo_field.py:235-238).
+ * nsk_hash_encode_grad_x_bwd is ITS backward for a cotangent cot_x [n,3] (double backward of the encode, needed because the
+ * normals feed the losses): d_grad_out [n,2L] (overwritten; NULL = skip) and d_table [L*T,2] (ACCUMULATED INTO; NULL = skip). */
+int nsk_hash_encode_grad_x(const float* x, int64_t n, const float* table, const float* scalings, int num_levels,
+                           int log2_T, const float* grad_out, float* grad_x, void* stream);
+int nsk_hash_encode_grad_x_bwd(const float* x, int64_t n, const float* table, const float* scalings, int num_levels,
+                               int log2_T, const float* grad_out, const float* cot_x, float* d_grad_out, float* d_table,
+                               void* stream);
+
 /* Integer part only, for bit-exact index parity tests: idx [n,L,8] int64 (including the l*T level
  * offset, corner order of SURVEY A.3), offsets [n,L,3]. */
 int nsk_hash_indices(const float* x, int64_t n, const float* scalings, int num_levels, int log2_T,

@@ -1,7 +1,7 @@
 """torch.autograd bindings of the C-ABI ops that have hand-written backward kernels (the "torch custom-op layer" of
 north_star for the training path).  Forward and backward both run the CUDA kernels; there is no torch fallback.
 
-  hash_encode(x, table, ...)      d/d table  (nsk_hash_encode_bwd; x is treated as a constant, like tcnn's default)
+  hash_encode(x, table, ...)      d/d table, d/d x and the double backward d(d/d x)/d table  (nsk_hash_encode_bwd, _grad_x, _grad_x_bwd)
   neus_composite(sdf, grad, albedo, inv_s, ...)   d/d sdf, grad, albedo, inv_s  (nsk_neus_composite_bwd)
   lambert_shade(normals, wa, radiance, vis, ...)   d/d normals, wa, radiance, visibility  (nsk_lambert_relight_bwd)
   shade_finalize(rgb_lin, bg, acc)                 d/d rgb_lin, bg, acc  (nsk_shade_finalize_bwd)
@@ -17,20 +17,46 @@ from . import ops
 Tensor = torch.Tensor
 
 
+class _HashEncodeBwd(torch.autograd.Function):
+    """The backward of the encode as a differentiable op: (x, table, g) -> (d x [n,3], d table [L*T,2]).  Its own backward
+    is what makes `torch.autograd.grad(sdf, x, create_graph=True)` (the reference's normals, sdf_albedo_field.py:235-238)
+    trainable: the normals depend on the table through the trilinear slopes."""
+
+    @staticmethod
+    def forward(ctx, x, table, g, scalings, log2_T: int):
+        ctx.save_for_backward(x, table, g, scalings)
+        ctx.log2_T = log2_T
+        g = g.contiguous()
+        return ops.hash_encode_grad_x(x, table, scalings, log2_T, g), ops.hash_encode_bwd(x, scalings, log2_T, g)
+
+    @staticmethod
+    def backward(ctx, c_gx, c_gtable):
+        x, table, g, scalings = ctx.saved_tensors
+        d_g = d_table = None
+        if c_gx is not None:
+            d_g, d_table = ops.hash_encode_grad_x_bwd(x, table, scalings, ctx.log2_T, g, c_gx.contiguous(), ctx.needs_input_grad[2], ctx.needs_input_grad[1])
+        if c_gtable is not None and ctx.needs_input_grad[2]:
+            extra = ops.hash_encode(x, c_gtable.contiguous(), scalings, ctx.log2_T)       # d g of the table scatter = encode with that "table"
+            d_g = extra.reshape(g.shape) if d_g is None else d_g.reshape(g.shape) + extra.reshape(g.shape)
+        return None, d_table, (None if d_g is None else d_g.reshape(g.shape)), None, None
+
+
 class _HashEncode(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x: Tensor, table: Tensor, scalings: Tensor, log2_T: int) -> Tensor:
-        ctx.save_for_backward(x, scalings)
-        ctx.log2_T, ctx.table_shape = log2_T, table.shape
+        ctx.save_for_backward(x, table, scalings)
+        ctx.log2_T = log2_T
         return ops.hash_encode(x, table, scalings, log2_T)
 
     @staticmethod
     def backward(ctx, g: Tensor):
-        x, scalings = ctx.saved_tensors
-        return None, ops.hash_encode_bwd(x, scalings, ctx.log2_T, g.contiguous()), None, None
+        x, table, scalings = ctx.saved_tensors
+        gx, gtable = _HashEncodeBwd.apply(x, table, g, scalings, ctx.log2_T)
+        return (gx if ctx.needs_input_grad[0] else None), (gtable if ctx.needs_input_grad[1] else None), None, None
 
 
 def hash_encode(x: Tensor, table: Tensor, scalings: Tensor, log2_T: int) -> Tensor:
+    """Twice-differentiable hash-grid encode: d/d table and d/d x, and the derivative of d/d x wrt the table."""
     return _HashEncode.apply(x, table, scalings, log2_T)
 
 

@@ -101,7 +101,103 @@ __global__ void hash_indices_kernel(const float* __restrict__ x, int64_t n, cons
   off_out[i * 3 + 0] = ox; off_out[i * 3 + 1] = oy; off_out[i * 3 + 2] = oz;
 }
 
+// ---- first derivative wrt the position and its own backward (double backward of the encode) ---------------------
+// coefficient of corner value f[c] in d interp / d o_axis (corner order of hash_corners)
+__device__ __forceinline__ void interp_grad_coefs(float ox, float oy, float oz, float cf[3][8]) {
+  const float px[2] = {ox, 1.f - ox}, py[2] = {oy, 1.f - oy}, pz[2] = {oz, 1.f - oz};
+  const int ux[8] = {0, 0, 1, 1, 0, 0, 1, 1}, uy[8] = {0, 1, 1, 0, 0, 1, 1, 0}, uz[8] = {0, 0, 0, 0, 1, 1, 1, 1};
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const float sx = ux[c] ? -1.f : 1.f, sy = uy[c] ? -1.f : 1.f, sz = uz[c] ? -1.f : 1.f;   // d w / d o: +1 for the "ceil" side
+    cf[0][c] = sx * py[uy[c]] * pz[uz[c]];
+    cf[1][c] = px[ux[c]] * sy * pz[uz[c]];
+    cf[2][c] = px[ux[c]] * py[uy[c]] * sz;
+  }
+}
+
+// gx[p] = sum_l s_l * sum_ch g[p,l,ch] * d feat[p,l,ch] / d (s_l x)      (what autograd returns for d L / d x)
+__global__ void __launch_bounds__(256)
+hash_encode_grad_x_kernel(const float* __restrict__ x, int64_t n, const float2* __restrict__ table, const float* __restrict__ scalings,
+                          int L, int log2_T, const float* __restrict__ g, float* __restrict__ gx) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const uint32_t mask = (1u << log2_T) - 1u;
+  const float px = x[p * 3], py = x[p * 3 + 1], pz = x[p * 3 + 2];
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+  for (int lev = 0; lev < L; ++lev) {
+    const float s = scalings[lev];
+    uint32_t idx[8];
+    float ox, oy, oz;
+    hash_corners(__fmul_rn(px, s), __fmul_rn(py, s), __fmul_rn(pz, s), mask, idx, ox, oy, oz);
+    float cf[3][8];
+    interp_grad_coefs(ox, oy, oz, cf);
+    const float2* tl = table + ((size_t)lev << log2_T);
+    const float ga = g[p * 2 * L + 2 * lev], gb = g[p * 2 * L + 2 * lev + 1];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const float2 v = __ldg(tl + idx[c]);
+      const float t = s * (v.x * ga + v.y * gb);
+      a0 = fmaf(cf[0][c], t, a0); a1 = fmaf(cf[1][c], t, a1); a2 = fmaf(cf[2][c], t, a2);
+    }
+  }
+  gx[p * 3] = a0; gx[p * 3 + 1] = a1; gx[p * 3 + 2] = a2;
+}
+
+// backward of the above for a cotangent cx [n,3] of gx:
+//   d g[p,l,ch]        = s_l * sum_axis cx_axis * d feat[p,l,ch] / d o_axis           (a JVP of the encode along cx)
+//   d table[idx_c][ch] += s_l * g[p,l,ch] * sum_axis cx_axis * coef[axis][c]
+__global__ void __launch_bounds__(256)
+hash_encode_grad_x_bwd_kernel(const float* __restrict__ x, int64_t n, const float2* __restrict__ table, const float* __restrict__ scalings,
+                              int L, int log2_T, const float* __restrict__ g, const float* __restrict__ cx, float* __restrict__ d_g,
+                              float* __restrict__ d_table) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lev = blockIdx.y;
+  if (p >= n) return;
+  const uint32_t mask = (1u << log2_T) - 1u;
+  const float s = scalings[lev];
+  uint32_t idx[8];
+  float ox, oy, oz;
+  hash_corners(__fmul_rn(x[p * 3], s), __fmul_rn(x[p * 3 + 1], s), __fmul_rn(x[p * 3 + 2], s), mask, idx, ox, oy, oz);
+  float cf[3][8];
+  interp_grad_coefs(ox, oy, oz, cf);
+  const float c0 = cx[p * 3], c1 = cx[p * 3 + 1], c2 = cx[p * 3 + 2];
+  const float ga = g[p * 2 * L + 2 * lev], gb = g[p * 2 * L + 2 * lev + 1];
+  const float2* tl = table + ((size_t)lev << log2_T);
+  float2* dtl = reinterpret_cast<float2*>(d_table) + ((size_t)lev << log2_T);
+  float ja = 0.f, jb = 0.f;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const float k = s * (c0 * cf[0][c] + c1 * cf[1][c] + c2 * cf[2][c]);
+    const float2 v = __ldg(tl + idx[c]);
+    ja = fmaf(k, v.x, ja); jb = fmaf(k, v.y, jb);
+    if (d_table) atomicAdd(dtl + idx[c], make_float2(k * ga, k * gb));
+  }
+  if (d_g) { d_g[p * 2 * L + 2 * lev] = ja; d_g[p * 2 * L + 2 * lev + 1] = jb; }
+}
+
 }  // namespace nsk
+
+extern "C" int nsk_hash_encode_grad_x(const float* x, int64_t n, const float* table, const float* scalings, int num_levels,
+                                      int log2_T, const float* grad_out, float* grad_x, void* stream) {
+  NSK_REQUIRE(num_levels >= 1 && num_levels <= nsk::HE_MAX_LEVELS, "nsk_hash_encode_grad_x: num_levels out of range");
+  if (n == 0) return 0;
+  NSK_REQUIRE(x && table && scalings && grad_out && grad_x, "nsk_hash_encode_grad_x: null pointer");
+  nsk::hash_encode_grad_x_kernel<<<(unsigned)((n + 255) / 256), 256, 0, nsk::as_stream(stream)>>>(
+      x, n, reinterpret_cast<const float2*>(table), scalings, num_levels, log2_T, grad_out, grad_x);
+  return nsk::check_launch("hash_encode_grad_x_kernel");
+}
+
+extern "C" int nsk_hash_encode_grad_x_bwd(const float* x, int64_t n, const float* table, const float* scalings, int num_levels,
+                                          int log2_T, const float* grad_out, const float* cot_x, float* d_grad_out,
+                                          float* d_table, void* stream) {
+  NSK_REQUIRE(num_levels >= 1 && num_levels <= nsk::HE_MAX_LEVELS, "nsk_hash_encode_grad_x_bwd: num_levels out of range");
+  if (n == 0) return 0;
+  NSK_REQUIRE(x && table && scalings && grad_out && cot_x && (d_grad_out || d_table), "nsk_hash_encode_grad_x_bwd: null pointer");
+  dim3 grid((unsigned)((n + 255) / 256), num_levels);
+  nsk::hash_encode_grad_x_bwd_kernel<<<grid, 256, 0, nsk::as_stream(stream)>>>(x, n, reinterpret_cast<const float2*>(table), scalings,
+                                                                              num_levels, log2_T, grad_out, cot_x, d_grad_out, d_table);
+  return nsk::check_launch("hash_encode_grad_x_bwd_kernel");
+}
 
 extern "C" int nsk_hash_encode_fwd(const float* x, int64_t n, const float* table, const float* scalings,
                                    int num_levels, int log2_T, float* out, void* stream) {

@@ -64,6 +64,31 @@ def hash_encode_bwd(x: Tensor, scalings: Tensor, log2_T: int, grad_out: Tensor, 
     return grad_table
 
 
+def hash_encode_grad_x(x: Tensor, table: Tensor, scalings: Tensor, log2_T: int, grad_out: Tensor) -> Tensor:
+    """d L / d x [n,3] of the encode for a cotangent grad_out [n,2L]."""
+    x2 = _chk("x", x.reshape(-1, 3), shape=(None, 3))
+    L = scalings.numel()
+    table = _chk("table", table, shape=(L << log2_T, 2))
+    g = _chk("grad_out", grad_out.reshape(-1, 2 * L), shape=(x2.shape[0], 2 * L))
+    gx = torch.empty((x2.shape[0], 3), device=x.device, dtype=torch.float32)
+    _lib.check(_lib.load().nsk_hash_encode_grad_x(_ptr(x2), c_int64(x2.shape[0]), _ptr(table), _ptr(_chk("scalings", scalings)), c_int(L), c_int(log2_T), _ptr(g), _ptr(gx), _stream(x)), "nsk_hash_encode_grad_x")
+    return gx.reshape(x.shape)
+
+
+def hash_encode_grad_x_bwd(x: Tensor, table: Tensor, scalings: Tensor, log2_T: int, grad_out: Tensor, cot_x: Tensor, want_g: bool = True, want_table: bool = True):
+    """Backward of hash_encode_grad_x: (d_grad_out [n,2L] | None, d_table [L*T,2] | None)."""
+    x2 = _chk("x", x.reshape(-1, 3), shape=(None, 3))
+    n, L = x2.shape[0], scalings.numel()
+    table = _chk("table", table, shape=(L << log2_T, 2))
+    g = _chk("grad_out", grad_out.reshape(-1, 2 * L), shape=(n, 2 * L))
+    c = _chk("cot_x", cot_x.reshape(-1, 3), shape=(n, 3))
+    d_g = torch.empty((n, 2 * L), device=x.device, dtype=torch.float32) if want_g else None
+    d_t = torch.zeros((L << log2_T, 2), device=x.device, dtype=torch.float32) if want_table else None
+    if want_g or want_table:
+        _lib.check(_lib.load().nsk_hash_encode_grad_x_bwd(_ptr(x2), c_int64(n), _ptr(table), _ptr(_chk("scalings", scalings)), c_int(L), c_int(log2_T), _ptr(g), _ptr(c), _ptr(d_g), _ptr(d_t), _stream(x)), "nsk_hash_encode_grad_x_bwd")
+    return d_g, d_t
+
+
 def hash_indices(x: Tensor, scalings: Tensor, log2_T: int) -> Tuple[Tensor, Tensor]:
     x2 = _chk("x", x.reshape(-1, 3), shape=(None, 3))
     L = scalings.numel()

@@ -129,3 +129,33 @@ def test_lambert_shade_and_finalize_backward_vs_oracle_autograd(dev):
         ref = ref.float()
         err = (got.cpu() - ref).abs().max() / ref.abs().max().clamp_min(1e-6)
         assert float(err) <= 2e-3, (name, float(err))
+
+
+def test_hash_encode_double_backward_normals_path(dev):
+    """The reference's normals: n = d sdf / d x by autograd with create_graph, and a loss on n back-propagated into the
+    hash table (sdf_albedo_field.py:235-238 + the eikonal loss).  Here sdf = sum(W . feat) with a fixed random W."""
+    from neusky_b200 import autograd as nba
+    from oracle import neusky_oracle as O
+
+    log2_T, L = 10, 16
+    table = nb_init.init_hash_table(6, L, log2_T) * 300.0
+    sc = O.hash_scalings(L)
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(1500, 3, generator=g) * 1.6 - 0.8
+    W = torch.randn(2 * L, generator=g)
+    cot = torch.randn(1500, 3, generator=g)
+
+    def run(enc, xx, tt, Wd, cotd):
+        xx = xx.clone().requires_grad_(True)
+        sdf = (enc(xx, tt) * Wd).sum(-1)
+        (n,) = torch.autograd.grad(sdf.sum(), xx, create_graph=True)
+        loss = (n * cotd).sum() + 0.1 * (sdf ** 2).sum()
+        loss.backward()
+        return n.detach(), tt.grad
+
+    t_ref = table.double().requires_grad_(True)
+    n_ref, gt_ref = run(lambda a, b: O.hash_encode(a, b, sc, log2_T), x.double(), t_ref, W.double(), cot.double())
+    t_gpu = table.to(dev).requires_grad_(True)
+    n_gpu, gt_gpu = run(lambda a, b: nba.hash_encode(a, b, sc.to(dev), log2_T), x.to(dev), t_gpu, W.to(dev), cot.to(dev))
+    assert float((n_gpu.cpu() - n_ref.float()).abs().max() / n_ref.abs().max()) <= 1e-4
+    assert float((gt_gpu.cpu() - gt_ref.float()).abs().max() / gt_ref.abs().max()) <= 1e-3
