@@ -215,6 +215,55 @@ int64_t nsk_ddf_tc_weights_bytes(void);
 int nsk_surface_points(const float* origins, const float* ray_dirs, const float* p2p, int64_t R, float radius,
                        float* points, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Training step (BASELINE config 4): the layer contractions and the pointwise stages of the reference's
+ * autograd graph, forward and backward.  The reference runs these as torch.nn.Linear / cuBLAS calls recorded
+ * by autograd (film_siren.py:45-156 for the DDF, sdf_albedo_field.py:185-269 + nerfstudio SDFField for the
+ * SDF/colour MLP); here every contraction is one tcgen05 tf32 launch with fp32 operands read straight from HBM
+ * and the pointwise stage fused into its epilogue where it is a function of the output element only.
+ *
+ * nsk_gemm_tf32_nt:  C[M,N] = dact'(aux) * act(A[M,K] . B[N,K]^T + bias[N])  (+ C when accumulate)
+ *     A, B row-major with leading dimensions lda, ldb (multiples of 4, 16-byte aligned bases), K a multiple of 8
+ *     (pad with zero columns).  act: 0 none, 1 relu, 2 leaky-relu(0.2), 3 softplus(beta=100), 4 sigmoid.
+ *     dact != 0 multiplies by the derivative of that activation expressed through its forward OUTPUT aux[M, ldaux]
+ *     (the backward "dZ = dA * act'(z)" step fused into dA = dZ_next . W).
+ * nsk_gemm_tf32_tn:  C[P,Q] += sum_m A[m,P]^T B[m,Q]   (weight gradients; the m range is split across CTAs and
+ *     reduced with red.global.add, so C must hold zeros or a running sum).
+ * split: 1 = one tf32 pass (10-bit mantissa operands, fp32 accumulate); 3 = 3xTF32 (hi/lo operand split, three MMAs
+ *     per step), fp32-accurate -- the mode the parity tests pin against the fp32 oracle.
+ * ------------------------------------------------------------------------------------------- */
+int nsk_gemm_tf32_nt(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int64_t M, int N, int K,
+                     const float* bias, int act, const float* aux, int ldaux, int dact, int accumulate, int split,
+                     void* stream);
+int nsk_gemm_tf32_tn(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int64_t M, int P, int Q,
+                     int split, void* stream);
+
+/* DDF visibility network, training path.  Row i = r * D + j of every [N, .] tensor is the pair (surface point r,
+ * light direction j), N = R * D (neusky_model.py:1685-1690).
+ * nsk_ddf_pairs_fwd: points [R,3], dirs [D,3] (unit, already masked to the upper hemisphere) ->
+ *     cond [N,40] = (q, hash(q), 0-pad)   q = sphere exit point (neusky_model.py:1693-1695; directional_distance_field.py:267-268)
+ *     xin  [N,16] = (d_local, PE2(d_local), 0-pad) for d = -l in the local frame of q (ddf_model.py:158-200; :270-271)
+ *     q    [N,3], term_dist [N] = |q - p| (neusky_model.py:1697-1699)
+ * nsk_film_sin_fwd / _bwd: a = sin((15 f + 30) z + phase) with f, phase = columns [layer*256, +256) of the two halves of the
+ *     mapping output film [N, ldf] (film_siren.py:66-67, 74-81, 140); bwd writes d z [N,256] and the two column blocks of d film.
+ * nsk_ddf_head_fwd: that = 2 r sigmoid(a5 . w + b) (directional_distance_field.py:297-299), vis = 1 - sigmoid(scale *
+ *     (min(term_dist, 2r) - that - threshold)) (neusky_model.py:1724-1740); threshold is a device scalar (learnable).
+ * nsk_ddf_head_bwd: cotangents d_vis [N] (NULL = 0) and d_that_extra [N] (NULL = 0; the sdf_at_termination branch) ->
+ *     d a5 [N,256] (overwritten), d w [256], d b [1], d threshold [1] (NULL = skip) accumulated.
+ * nsk_colsum: out[c] += sum_r X[r, c]  (bias gradients). */
+int nsk_ddf_pairs_fwd(const float* points, int64_t R, const float* dirs, int D, const float* table, const float* scalings,
+                      int num_levels, int log2_T, float radius, float* cond, float* xin, float* q, float* term_dist,
+                      void* stream);
+int nsk_film_sin_fwd(const float* z, const float* film, int ldf, int layer, int64_t N, float* a, void* stream);
+int nsk_film_sin_bwd(const float* da, const float* z, const float* film, int ldf, int layer, int64_t N, float* dz,
+                     float* dfilm, void* stream);
+int nsk_ddf_head_fwd(const float* a5, const float* w_final, const float* b_final, const float* term_dist, int64_t N,
+                     float radius, const float* threshold, float sigmoid_scale, float* that, float* vis, void* stream);
+int nsk_ddf_head_bwd(const float* a5, const float* w_final, const float* that, const float* term_dist, const float* d_vis,
+                     const float* d_that_extra, int64_t N, float radius, const float* threshold, float sigmoid_scale,
+                     float* da5, float* d_w_final, float* d_b_final, float* d_threshold, void* stream);
+int nsk_colsum(const float* X, int ld, int64_t M, int ncols, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,424 @@
+// Training-path dense contractions on the 5th-gen tensor cores: tcgen05.mma.kind::tf32 with fp32 operands read
+// straight from HBM (no fp16 copies of activations or gradients), fp32 accumulators in TMEM.
+//
+//   nsk_gemm_tf32_nt : C[M,N]  = act(A[M,K] . B[N,K]^T + bias[N]) (+ C)      forward layers and dX = dY . W
+//   nsk_gemm_tf32_tn : C[P,Q] += sum_m A[m,P]^T . B[m,Q]                      dW = dY^T . X, split over m across CTAs
+//
+// These are the layer contractions of the reference's torch autograd graph for the SDF/colour MLP
+// (neusky/fields/sdf_albedo_field.py:185-269) and the FiLM-SIREN DDF (ns_reni/reni/field_components/film_siren.py:45-156)
+// in the training step; the fused forward-only kernels (sdf_field_tc.cu, sky_shade_tc2.cu) stay the eval path.
+//
+// One persistent CTA per SM, 416 threads, warp-specialised:
+//   warps 0-7   operand staging: ld.global (coalesced, full sectors) -> registers -> st.shared in the no-swizzle K-major
+//               core-matrix layout [K/4][rows][4 x tf32] (the TN variant transposes in registers, so both variants feed the
+//               same descriptors); `split=3` stores a hi (top 19 bits) and a lo (remainder) plane for the 3xTF32 scheme
+//               (A_hi.B_hi + A_lo.B_hi + A_hi.B_lo), whose result is fp32-accurate and is what the parity tests pin.
+//   warp 12     one lane issues tcgen05.mma (M=128, N<=256, K=8 per instruction) into a double-buffered TMEM accumulator
+//   warps 8-11  epilogue: tcgen05.ld, bias + activation, st.global (NT) / red.global.add (TN)
+// Stage ring: 4 x 48 KB (2 x 96 KB with split=3), mbarrier full/empty; accumulator ring: 2 x 256 TMEM columns.
+#include <algorithm>
+
+#include "nsk_common.cuh"
+#include "tc_util.cuh"
+
+namespace nsk {
+namespace gemm {
+using namespace nsk::tc;
+
+constexpr int TM = 128;
+constexpr int BN = 256;
+constexpr int KC = 32;
+constexpr int PROD_WARPS = 8;
+constexpr int EPI_WARP0 = 8;
+constexpr int MMA_WARP = 12;
+constexpr int THREADS = 13 * 32;
+constexpr uint32_t A_BYTES = TM * KC * 4;
+constexpr uint32_t B_BYTES = BN * KC * 4;
+constexpr uint32_t A_LBO = TM * 16, B_LBO = BN * 16;
+
+struct Params {
+  const float* A;
+  const float* B;
+  float* C;
+  const float* bias;
+  int64_t M;        // NT: rows of A and C.  TN: reduction length (rows of A and B)
+  int N;            // NT: columns of C (rows of B).  TN: P = columns of A = rows of C
+  int K;            // NT: reduction length.  TN: Q = columns of B = columns of C
+  int lda, ldb, ldc;
+  const float* aux; // NT only: forward OUTPUT of the activation whose derivative multiplies the result (dact != 0)
+  int ldaux;
+  int act;          // NT only: 0 none, 1 relu, 2 leaky relu 0.2, 3 softplus beta=100 (torch threshold 20), 4 sigmoid
+  int dact;         // NT only: result *= act'(.) expressed through the activation's output aux[row, col] (same codes)
+  int accumulate;   // NT only: C += result
+  int n_btiles;     // tiles along the B-operand rows
+  int n_atiles;     // TN only: tiles along P
+  int64_t rows_per_split;  // TN only
+  int64_t n_items;
+};
+
+struct Item {
+  int64_t a0;   // first A-operand row (NT: row of A; TN: column of A)
+  int b0;       // first B-operand row (NT: row of B; TN: column of B)
+  int bn;       // MMA N: valid B-operand rows rounded up to 16
+  int64_t r0, r1;  // reduction range
+};
+
+template <bool TN>
+__device__ __forceinline__ Item get_item(const Params& p, int64_t w) {
+  Item it;
+  if (!TN) {
+    const int64_t mt = w / p.n_btiles;
+    const int nt = (int)(w % p.n_btiles);
+    it.a0 = mt * TM;
+    it.b0 = nt * BN;
+    it.bn = (min(BN, p.N - it.b0) + 15) & ~15;
+    it.r0 = 0;
+    it.r1 = p.K;
+  } else {
+    const int per = p.n_atiles * p.n_btiles;
+    const int64_t split = w / per;
+    const int rem = (int)(w % per);
+    it.a0 = (int64_t)(rem / p.n_btiles) * TM;
+    it.b0 = (rem % p.n_btiles) * BN;
+    it.bn = (min(BN, p.K - it.b0) + 15) & ~15;
+    it.r0 = split * p.rows_per_split;
+    it.r1 = min(p.M, it.r0 + p.rows_per_split);
+  }
+  return it;
+}
+
+// fp32 accumulate, tf32 A and B, both K-major
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
+
+template <int SPLIT>
+__device__ __forceinline__ void put(uint8_t* hi_plane, uint32_t off, float4 v) {
+  if (SPLIT == 1) {
+    *reinterpret_cast<float4*>(hi_plane + off) = v;
+  } else {
+    const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+    *reinterpret_cast<float4*>(hi_plane + off) = h;
+    *reinterpret_cast<float4*>(hi_plane + (A_BYTES + B_BYTES) + off) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+  }
+}
+
+__device__ __forceinline__ float act_apply(float v, int act) {
+  if (act == 1) return fmaxf(v, 0.0f);
+  if (act == 2) return v > 0.0f ? v : 0.2f * v;
+  if (act == 3) return (v * 100.0f > 20.0f) ? v : log1pf(expf(v * 100.0f)) * 0.01f;
+  if (act == 4) return 1.0f / (1.0f + expf(-v));
+  return v;
+}
+// derivative of activation `dact` written in terms of its output a
+__device__ __forceinline__ float dact_from_output(float a, int dact) {
+  if (dact == 1) return a > 0.0f ? 1.0f : 0.0f;
+  if (dact == 2) return a > 0.0f ? 1.0f : 0.2f;
+  if (dact == 3) return 1.0f - expf(-100.0f * a);   // softplus_100: sigmoid(100 z) = 1 - exp(-100 a)
+  if (dact == 4) return a * (1.0f - a);
+  return 1.0f;
+}
+
+template <int SPLIT, bool TN>
+__global__ void __launch_bounds__(THREADS, 1) gemm_tf32_kernel(const Params p) {
+  constexpr int ST = (SPLIT == 3) ? 2 : 4;
+  constexpr uint32_t STAGE = (A_BYTES + B_BYTES) * (SPLIT == 3 ? 2 : 1);
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* const bars_p = reinterpret_cast<uint64_t*>(smem + ST * STAGE);
+  const uint32_t bars = smem_u32(bars_p);
+  const uint32_t FULL = bars, EMPTY = bars + 8 * ST, ACCF = bars + 16 * ST, ACCE = bars + 16 * ST + 16;
+  uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(bars_p + 2 * ST + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < ST; ++s) {
+      mbar_init(FULL + 8 * s, PROD_WARPS * 32);
+      mbar_init(EMPTY + 8 * s, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(ACCF + 8 * b, 1);
+      mbar_init(ACCE + 8 * b, 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == MMA_WARP) tmem_alloc<512>(smem_u32(tmem_slot));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp < PROD_WARPS) {
+    // ------------------------------------------------------------------ operand staging
+    uint32_t stage = 0, phase = 0;
+    const int r8 = lane & 7, kq_lo = lane >> 3;
+    for (int64_t w = blockIdx.x; w < p.n_items; w += gridDim.x) {
+      const Item it = get_item<TN>(p, w);
+      for (int64_t r = it.r0; r < it.r1; r += KC) {
+        mbar_wait(EMPTY + 8 * stage, phase ^ 1);
+        uint8_t* const sa = smem + stage * STAGE;
+        uint8_t* const sb = sa + A_BYTES;
+        float4 va[4], vb[8];
+        if (!TN) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int wi = warp + 8 * j, row = (wi >> 1) * 8 + r8, kq = (wi & 1) * 4 + kq_lo;
+            const int64_t grow = it.a0 + row, k = r + kq * 4;
+            va[j] = (grow < p.M && k < it.r1) ? ldg4(p.A + grow * p.lda + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int wi = warp + 8 * j, row = (wi >> 1) * 8 + r8, kq = (wi & 1) * 4 + kq_lo;
+            const int64_t k = r + kq * 4;
+            const int n = it.b0 + row;
+            vb[j] = (row < it.bn && n < p.N && k < it.r1) ? ldg4(p.B + (int64_t)n * p.ldb + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int wi = warp + 8 * j, row = (wi >> 1) * 8 + r8, kq = (wi & 1) * 4 + kq_lo;
+            put<SPLIT>(sa, (uint32_t)(kq * A_LBO + row * 16), va[j]);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int wi = warp + 8 * j, row = (wi >> 1) * 8 + r8, kq = (wi & 1) * 4 + kq_lo;
+            put<SPLIT>(sb, (uint32_t)(kq * B_LBO + row * 16), vb[j]);
+          }
+        } else {
+          // element (operand row n, k = m): X[(r + k) * ld + col0 + n]; 4 consecutive m per thread -> one 16-byte store
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int wi = warp + 8 * j, n = (wi & 3) * 32 + lane, mq = wi >> 2;
+            const int64_t col = it.a0 + n, m = r + mq * 4;
+            const bool cv = col < p.N;
+            const float* src = p.A + m * p.lda + col;
+            va[j].x = (cv && m + 0 < it.r1) ? __ldg(src) : 0.f;
+            va[j].y = (cv && m + 1 < it.r1) ? __ldg(src + p.lda) : 0.f;
+            va[j].z = (cv && m + 2 < it.r1) ? __ldg(src + 2 * (int64_t)p.lda) : 0.f;
+            va[j].w = (cv && m + 3 < it.r1) ? __ldg(src + 3 * (int64_t)p.lda) : 0.f;
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int wi = warp + 8 * j, n = (wi & 7) * 32 + lane, mq = wi >> 3;
+            const int64_t m = r + mq * 4;
+            const int col = it.b0 + n;
+            const bool cv = n < it.bn && col < p.K;
+            const float* src = p.B + m * p.ldb + col;
+            vb[j].x = (cv && m + 0 < it.r1) ? __ldg(src) : 0.f;
+            vb[j].y = (cv && m + 1 < it.r1) ? __ldg(src + p.ldb) : 0.f;
+            vb[j].z = (cv && m + 2 < it.r1) ? __ldg(src + 2 * (int64_t)p.ldb) : 0.f;
+            vb[j].w = (cv && m + 3 < it.r1) ? __ldg(src + 3 * (int64_t)p.ldb) : 0.f;
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int wi = warp + 8 * j, n = (wi & 3) * 32 + lane, mq = wi >> 2;
+            put<SPLIT>(sa, (uint32_t)(mq * A_LBO + n * 16), va[j]);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int wi = warp + 8 * j, n = (wi & 7) * 32 + lane, mq = wi >> 3;
+            put<SPLIT>(sb, (uint32_t)(mq * B_LBO + n * 16), vb[j]);
+          }
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(FULL + 8 * stage);
+        if (++stage == ST) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == MMA_WARP) {
+    // ------------------------------------------------------------------ MMA issue (one lane)
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, iter = 0;
+      for (int64_t w = blockIdx.x; w < p.n_items; w += gridDim.x, ++iter) {
+        const Item it = get_item<TN>(p, w);
+        const uint32_t buf = iter & 1;
+        mbar_wait(ACCE + 8 * buf, ((iter >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d = tmem + buf * BN;
+        const uint32_t idesc = make_idesc_tf32(TM, it.bn);
+        uint32_t acc = 0;
+        if (it.r0 >= it.r1) {
+          // empty reduction range (TN tail split): nothing to add; still hand the buffer over (epilogue skips it)
+        }
+        for (int64_t r = it.r0; r < it.r1; r += KC) {
+          mbar_wait(FULL + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * STAGE), sb = sa + A_BYTES;
+          const int ksteps = (int)min((int64_t)(KC / 8), (it.r1 - r + 7) / 8);
+          for (int j = 0; j < ksteps; ++j) {
+            const uint64_t ah = make_smem_desc(sa + j * 2 * A_LBO, A_LBO, 128), bh = make_smem_desc(sb + j * 2 * B_LBO, B_LBO, 128);
+            if (SPLIT == 3) {
+              const uint32_t lo = A_BYTES + B_BYTES;
+              const uint64_t al = make_smem_desc(sa + lo + j * 2 * A_LBO, A_LBO, 128), bl = make_smem_desc(sb + lo + j * 2 * B_LBO, B_LBO, 128);
+              umma_tf32(d, al, bh, idesc, acc);
+              umma_tf32(d, ah, bl, idesc, 1);
+              umma_tf32(d, ah, bh, idesc, 1);
+            } else {
+              umma_tf32(d, ah, bh, idesc, acc);
+            }
+            acc = 1;
+          }
+          umma_commit(EMPTY + 8 * stage);
+          if (++stage == ST) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(ACCF + 8 * buf);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ epilogue
+    const int q = warp - EPI_WARP0;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    uint32_t iter = 0;
+    const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+    for (int64_t w = blockIdx.x; w < p.n_items; w += gridDim.x, ++iter) {
+      const Item it = get_item<TN>(p, w);
+      const uint32_t buf = iter & 1;
+      mbar_wait(ACCF + 8 * buf, (iter >> 1) & 1);
+      tc_fence_after();
+      const int64_t row = it.a0 + q * 32 + lane;
+      const bool row_ok = TN ? (row < p.N) : (row < p.M);
+      const int ncols = TN ? p.K : p.N;
+      const bool has_data = it.r0 < it.r1;
+      for (int c0 = 0; c0 < it.bn; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem + lane_off + buf * BN + c0, v);
+        tmem_ld_wait();
+        if (!row_ok || !has_data) continue;
+        float* crow = p.C + row * p.ldc + it.b0 + c0;
+        if (TN) {
+#pragma unroll
+          for (int c = 0; c < 32; ++c)
+            if (it.b0 + c0 + c < ncols) atomicAdd(crow + c, __uint_as_float(v[c]));
+        } else {
+          float f[32];
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            float x = __uint_as_float(v[c]);
+            const int n = it.b0 + c0 + c;
+            if (p.bias != nullptr && n < ncols) x += __ldg(p.bias + n);
+            x = act_apply(x, p.act);
+            if (p.dact != 0 && n < ncols) x *= dact_from_output(p.aux[row * p.ldaux + n], p.dact);
+            f[c] = x;
+          }
+          if (vec_ok && it.b0 + c0 + 32 <= ncols) {
+#pragma unroll
+            for (int c = 0; c < 32; c += 4) {
+              float4 o = make_float4(f[c], f[c + 1], f[c + 2], f[c + 3]);
+              if (p.accumulate) {
+                const float4 old = *reinterpret_cast<const float4*>(crow + c);
+                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+              }
+              *reinterpret_cast<float4*>(crow + c) = o;
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < 32; ++c)
+              if (it.b0 + c0 + c < ncols) crow[c] = p.accumulate ? crow[c] + f[c] : f[c];
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(ACCE + 8 * buf);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem);
+  }
+}
+
+template <int SPLIT>
+constexpr size_t smem_bytes() {
+  return (size_t)((SPLIT == 3) ? 2 : 4) * (A_BYTES + B_BYTES) * (SPLIT == 3 ? 2 : 1) + 256;
+}
+
+static int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int SPLIT, bool TN>
+static int launch(const Params& p, cudaStream_t st) {
+  auto kern = gemm_tf32_kernel<SPLIT, TN>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<SPLIT>());
+    if (e != cudaSuccess) return fail("gemm_tf32: cudaFuncSetAttribute", cudaGetErrorString(e));
+    configured = true;
+  }
+  const int grid = (int)std::min<int64_t>(p.n_items, sm_count());
+  kern<<<grid, THREADS, smem_bytes<SPLIT>(), st>>>(p);
+  return check_launch("gemm_tf32_kernel");
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace gemm
+}  // namespace nsk
+
+extern "C" int nsk_gemm_tf32_nt(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int64_t M, int N, int K,
+                                const float* bias, int act, const float* aux, int ldaux, int dact, int accumulate, int split,
+                                void* stream) {
+  using namespace nsk::gemm;
+  NSK_REQUIRE(A && B && C, "nsk_gemm_tf32_nt: null pointer");
+  NSK_REQUIRE(M >= 0 && N > 0 && K > 0, "nsk_gemm_tf32_nt: bad sizes");
+  NSK_REQUIRE((K & 7) == 0, "nsk_gemm_tf32_nt: K must be a multiple of 8 (pad with zeros)");
+  NSK_REQUIRE((lda & 3) == 0 && (ldb & 3) == 0 && lda >= K && ldb >= K && ldc >= N, "nsk_gemm_tf32_nt: leading dimensions");
+  NSK_REQUIRE(aligned16(A) && aligned16(B), "nsk_gemm_tf32_nt: A and B must be 16-byte aligned");
+  NSK_REQUIRE(act >= 0 && act <= 4 && dact >= 0 && dact <= 4, "nsk_gemm_tf32_nt: act / dact");
+  NSK_REQUIRE(dact == 0 || (aux != nullptr && ldaux >= N), "nsk_gemm_tf32_nt: dact needs aux [M, ldaux >= N]");
+  NSK_REQUIRE(split == 1 || split == 3, "nsk_gemm_tf32_nt: split must be 1 (tf32) or 3 (3xtf32)");
+  if (M == 0) return 0;
+  Params p{};
+  p.A = A; p.B = B; p.C = C; p.bias = bias;
+  p.M = M; p.N = N; p.K = K; p.lda = lda; p.ldb = ldb; p.ldc = ldc;
+  p.act = act; p.accumulate = accumulate;
+  p.aux = aux; p.ldaux = ldaux; p.dact = dact;
+  p.n_btiles = (N + BN - 1) / BN;
+  p.n_atiles = 0;
+  p.rows_per_split = 0;
+  p.n_items = ((M + TM - 1) / TM) * p.n_btiles;
+  return split == 3 ? launch<3, false>(p, nsk::as_stream(stream)) : launch<1, false>(p, nsk::as_stream(stream));
+}
+
+extern "C" int nsk_gemm_tf32_tn(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int64_t M, int P, int Q,
+                                int split, void* stream) {
+  using namespace nsk::gemm;
+  NSK_REQUIRE(A && B && C, "nsk_gemm_tf32_tn: null pointer");
+  NSK_REQUIRE(M >= 0 && P > 0 && Q > 0, "nsk_gemm_tf32_tn: bad sizes");
+  NSK_REQUIRE(lda >= P && ldb >= Q && ldc >= Q, "nsk_gemm_tf32_tn: leading dimensions");
+  NSK_REQUIRE(split == 1 || split == 3, "nsk_gemm_tf32_tn: split must be 1 (tf32) or 3 (3xtf32)");
+  if (M == 0) return 0;
+  Params p{};
+  p.A = A; p.B = B; p.C = C; p.bias = nullptr;
+  p.M = M; p.N = P; p.K = Q; p.lda = lda; p.ldb = ldb; p.ldc = ldc;
+  p.act = 0; p.accumulate = 1;
+  p.n_atiles = (P + TM - 1) / TM;
+  p.n_btiles = (Q + BN - 1) / BN;
+  const int per = p.n_atiles * p.n_btiles;
+  const int want = std::max(1, sm_count() / per);
+  int64_t rows = (M + want - 1) / want;
+  rows = std::max<int64_t>(rows, 512);
+  rows = (rows + KC - 1) / KC * KC;
+  p.rows_per_split = rows;
+  p.n_items = ((M + rows - 1) / rows) * per;
+  return split == 3 ? launch<3, true>(p, nsk::as_stream(stream)) : launch<1, true>(p, nsk::as_stream(stream));
+}

@@ -1,0 +1,276 @@
+// Training-path companions of the tf32 layer contractions (gemm_tf32.cu): everything between two GEMMs of the DDF
+// visibility network in the training step, forward and backward.  Row r of every [N, .] tensor is one
+// (surface point, light direction) pair, N = R * D' (neusky/models/neusky_model.py:1685-1690).
+//
+//   nsk_ddf_pairs_fwd   pair geometry: sphere exit q (neusky_model.py:1693-1695), local-frame direction and its NeRF
+//                       encoding (neusky/models/ddf_model.py:158-200, directional_distance_field.py:270-271), hash-grid
+//                       conditioning (directional_distance_field.py:267-268), clamped ground-truth distance (:1724-1727)
+//   nsk_film_sin_fwd    FiLM layer activation sin((15 f + 30) z + phase) (film_siren.py:74-81, 140)
+//   nsk_film_sin_bwd    its backward: d z, and d f / d phase written into the [N, 2560] mapping-output gradient
+//   nsk_ddf_head_fwd    final 256 -> 1 layer, sigmoid * 2r (directional_distance_field.py:297-299), visibility sigmoid
+//                       (neusky_model.py:1730-1740)
+//   nsk_ddf_head_bwd    backward of the head: d a5, d w_final, d b_final, d threshold
+//   nsk_colsum          bias gradients: out[c] += sum_r X[r, c]
+// All fp32, memory-bound elementwise / row-reduction kernels; one pass over their operands each.
+#include "nsk_common.cuh"
+
+namespace nsk {
+namespace train {
+
+constexpr int COND_LD = 40;   // 3 + 32 padded to a multiple of 8 (tf32 MMA K step)
+constexpr int XIN_LD = 16;    // 15 padded
+
+__global__ void __launch_bounds__(128)
+ddf_pairs_fwd_kernel(const float* __restrict__ points, int64_t R, const float* __restrict__ dirs, int D,
+                     const float2* __restrict__ table, const float* __restrict__ scalings, int L, int log2_T, float radius,
+                     float* __restrict__ cond, float* __restrict__ xin, float* __restrict__ qout, float* __restrict__ gt) {
+  const int64_t N = R * D;
+  const uint32_t mask = (1u << log2_T) - 1u;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / D;
+    const int j = (int)(i - r * D);
+    const float p[3] = {points[r * 3], points[r * 3 + 1], points[r * 3 + 2]};
+    const float l[3] = {dirs[j * 3], dirs[j * 3 + 1], dirs[j * 3 + 2]};
+    float q[3], t;
+    sphere_exit(p, l, radius, q, t);
+    // termination_dist / dist_to_ray_origins: |q - p| (neusky_model.py:1697-1699, 1724)
+    const float dx = q[0] - p[0], dy = q[1] - p[1], dz = q[2] - p[2];
+    const float dist = sqrtf(dx * dx + dy * dy + dz * dz);
+    gt[i] = dist;
+    qout[i * 3] = q[0]; qout[i * 3 + 1] = q[1]; qout[i * 3 + 2] = q[2];
+    const float dneg[3] = {-l[0], -l[1], -l[2]};
+    float dl[3], feat[15];
+    ddf_local_dir(q, dneg, dl);
+    ddf_dir_features(dl, feat);
+    float* xr = xin + i * XIN_LD;
+#pragma unroll
+    for (int c = 0; c < 15; ++c) xr[c] = feat[c];
+    xr[15] = 0.f;
+    float* cr = cond + i * COND_LD;
+    cr[0] = q[0]; cr[1] = q[1]; cr[2] = q[2];
+    for (int lev = 0; lev < L; ++lev) {
+      const float s = scalings[lev];
+      uint32_t idx[8];
+      float ox, oy, oz;
+      hash_corners(__fmul_rn(q[0], s), __fmul_rn(q[1], s), __fmul_rn(q[2], s), mask, idx, ox, oy, oz);
+      const float2* tl = table + ((size_t)lev << log2_T);
+      float2 f[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) f[c] = __ldg(tl + idx[c]);
+      const float2 v = hash_interp(f, ox, oy, oz);
+      cr[3 + 2 * lev] = v.x;
+      cr[4 + 2 * lev] = v.y;
+    }
+    for (int c = 3 + 2 * L; c < COND_LD; ++c) cr[c] = 0.f;
+  }
+}
+
+// a = sin((15 F[:, l*H + c] + 30) * z + F[:, half + l*H + c]);  H = 256, F row stride ldf, half = ldf / 2
+__global__ void __launch_bounds__(256)
+film_sin_fwd_kernel(const float* __restrict__ z, const float* __restrict__ F, int ldf, int layer, int64_t N, float* __restrict__ a) {
+  const int64_t total = N * 64;  // float4 granules of a [N,256] tensor
+  const int half = ldf >> 1;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i >> 6;
+    const int c = (int)(i & 63) * 4;
+    const float4 zz = *reinterpret_cast<const float4*>(z + r * 256 + c);
+    const float4 fr = *reinterpret_cast<const float4*>(F + r * ldf + layer * 256 + c);
+    const float4 ph = *reinterpret_cast<const float4*>(F + r * ldf + half + layer * 256 + c);
+    float4 o;
+    o.x = sinf(fmaf(fmaf(15.f, fr.x, 30.f), zz.x, ph.x));
+    o.y = sinf(fmaf(fmaf(15.f, fr.y, 30.f), zz.y, ph.y));
+    o.z = sinf(fmaf(fmaf(15.f, fr.z, 30.f), zz.z, ph.z));
+    o.w = sinf(fmaf(fmaf(15.f, fr.w, 30.f), zz.w, ph.w));
+    *reinterpret_cast<float4*>(a + r * 256 + c) = o;
+  }
+}
+
+// du = da * cos(u); dz = du * freq; dF[:, l*H + c] = 15 * du * z; dF[:, half + l*H + c] = du
+__global__ void __launch_bounds__(256)
+film_sin_bwd_kernel(const float* __restrict__ da, const float* __restrict__ z, const float* __restrict__ F, int ldf, int layer,
+                    int64_t N, float* __restrict__ dz, float* __restrict__ dF) {
+  const int64_t total = N * 64;
+  const int half = ldf >> 1;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i >> 6;
+    const int c = (int)(i & 63) * 4;
+    const float4 g = *reinterpret_cast<const float4*>(da + r * 256 + c);
+    const float4 zz = *reinterpret_cast<const float4*>(z + r * 256 + c);
+    const float4 fr = *reinterpret_cast<const float4*>(F + r * ldf + layer * 256 + c);
+    const float4 ph = *reinterpret_cast<const float4*>(F + r * ldf + half + layer * 256 + c);
+    float4 odz, odf, odp;
+#define NSK_FILM_BWD(k)                                          \
+  {                                                              \
+    const float fq = fmaf(15.f, fr.k, 30.f);                     \
+    const float du = g.k * cosf(fmaf(fq, zz.k, ph.k));           \
+    odz.k = du * fq;                                             \
+    odf.k = 15.f * du * zz.k;                                    \
+    odp.k = du;                                                  \
+  }
+    NSK_FILM_BWD(x) NSK_FILM_BWD(y) NSK_FILM_BWD(z) NSK_FILM_BWD(w)
+#undef NSK_FILM_BWD
+    *reinterpret_cast<float4*>(dz + r * 256 + c) = odz;
+    *reinterpret_cast<float4*>(dF + r * ldf + layer * 256 + c) = odf;
+    *reinterpret_cast<float4*>(dF + r * ldf + half + layer * 256 + c) = odp;
+  }
+}
+
+// one warp per pair: o = a5 . w + b; that = 2 r sigmoid(o); vis = 1 - sigmoid(scale * (min(gt, 2r) - that - thr))
+__global__ void __launch_bounds__(256)
+ddf_head_fwd_kernel(const float* __restrict__ a5, const float* __restrict__ wf, const float* __restrict__ bf,
+                    const float* __restrict__ gt, int64_t N, float radius, const float* __restrict__ thr_p, float scale,
+                    float* __restrict__ that, float* __restrict__ vis) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const float4 w0 = *reinterpret_cast<const float4*>(wf + lane * 8), w1 = *reinterpret_cast<const float4*>(wf + lane * 8 + 4);
+  const float b = bf[0], thr = thr_p[0];
+  for (int64_t r = warp; r < N; r += nwarps) {
+    const float4 x0 = *reinterpret_cast<const float4*>(a5 + r * 256 + lane * 8), x1 = *reinterpret_cast<const float4*>(a5 + r * 256 + lane * 8 + 4);
+    float s = x0.x * w0.x + x0.y * w0.y + x0.z * w0.z + x0.w * w0.w + x1.x * w1.x + x1.y * w1.y + x1.z * w1.z + x1.w * w1.w;
+    s = warp_sum(s);
+    if (lane == 0) {
+      const float t = 2.0f * radius * sigmoidf_(s + b);
+      that[r] = t;
+      vis[r] = visibility_from_ddf(t, gt[r], radius, thr, scale);
+    }
+  }
+}
+
+// d that = d vis * scale * occ (1 - occ) + d that_extra;  d o = d that * 2r * sig (1 - sig), sig = that / 2r
+// d a5 = d o * w;  d w += sum d o * a5;  d b += sum d o;  d thr += sum d vis * scale * occ (1 - occ)
+__global__ void __launch_bounds__(256)
+ddf_head_bwd_kernel(const float* __restrict__ a5, const float* __restrict__ wf, const float* __restrict__ that,
+                    const float* __restrict__ gt, const float* __restrict__ d_vis, const float* __restrict__ d_that_extra,
+                    int64_t N, float radius, const float* __restrict__ thr_p, float scale, float* __restrict__ da5,
+                    float* __restrict__ d_wf, float* __restrict__ d_bf, float* __restrict__ d_thr) {
+  __shared__ float s_dw[8][256];
+  __shared__ float s_db[8], s_dt[8];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const float4 w0 = *reinterpret_cast<const float4*>(wf + lane * 8), w1 = *reinterpret_cast<const float4*>(wf + lane * 8 + 4);
+  const float thr = thr_p[0];
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float acc_b = 0.f, acc_t = 0.f;
+  for (int64_t r = warp; r < N; r += nwarps) {
+    const float t = that[r];
+    const float g = fminf(gt[r], 2.0f * radius);
+    const float occ = sigmoidf_(scale * ((g - t) - thr));
+    const float dv = d_vis ? d_vis[r] : 0.f;
+    const float k = dv * scale * occ * (1.0f - occ);
+    float dt = k + (d_that_extra ? d_that_extra[r] : 0.f);
+    const float sg = t / (2.0f * radius);
+    const float d_o = dt * 2.0f * radius * sg * (1.0f - sg);
+    const float4 x0 = *reinterpret_cast<const float4*>(a5 + r * 256 + lane * 8), x1 = *reinterpret_cast<const float4*>(a5 + r * 256 + lane * 8 + 4);
+    *reinterpret_cast<float4*>(da5 + r * 256 + lane * 8) = make_float4(d_o * w0.x, d_o * w0.y, d_o * w0.z, d_o * w0.w);
+    *reinterpret_cast<float4*>(da5 + r * 256 + lane * 8 + 4) = make_float4(d_o * w1.x, d_o * w1.y, d_o * w1.z, d_o * w1.w);
+    acc[0] = fmaf(d_o, x0.x, acc[0]); acc[1] = fmaf(d_o, x0.y, acc[1]); acc[2] = fmaf(d_o, x0.z, acc[2]); acc[3] = fmaf(d_o, x0.w, acc[3]);
+    acc[4] = fmaf(d_o, x1.x, acc[4]); acc[5] = fmaf(d_o, x1.y, acc[5]); acc[6] = fmaf(d_o, x1.z, acc[6]); acc[7] = fmaf(d_o, x1.w, acc[7]);
+    acc_b += d_o;
+    acc_t += k;
+  }
+#pragma unroll
+  for (int c = 0; c < 8; ++c) s_dw[wib][lane * 8 + c] = acc[c];
+  if (lane == 0) { s_db[wib] = acc_b; s_dt[wib] = acc_t; }
+  __syncthreads();
+  {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += s_dw[w][threadIdx.x];
+    atomicAdd(d_wf + threadIdx.x, s);
+  }
+  if (threadIdx.x == 0) {
+    float sb = 0.f, stt = 0.f;
+    for (int w = 0; w < 8; ++w) { sb += s_db[w]; stt += s_dt[w]; }
+    atomicAdd(d_bf, sb);
+    if (d_thr) atomicAdd(d_thr, stt);
+  }
+}
+
+// out[c] += sum_r X[r, c] ; block = 256 threads owning 256 consecutive columns of a row slab
+__global__ void __launch_bounds__(256)
+colsum_kernel(const float* __restrict__ X, int ld, int64_t M, int ncols, int64_t rows_per_block, float* __restrict__ out) {
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
+  if (c >= ncols) return;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int64_t r = r0;
+  for (; r + 3 < r1; r += 4) {
+    s0 += X[r * ld + c];
+    s1 += X[(r + 1) * ld + c];
+    s2 += X[(r + 2) * ld + c];
+    s3 += X[(r + 3) * ld + c];
+  }
+  for (; r < r1; ++r) s0 += X[r * ld + c];
+  atomicAdd(out + c, (s0 + s1) + (s2 + s3));
+}
+
+static int grid_for(int64_t work_items, int block, int max_blocks = 148 * 8) {
+  const int64_t b = (work_items + block - 1) / block;
+  return (int)std::max<int64_t>(1, std::min<int64_t>(b, max_blocks));
+}
+
+}  // namespace train
+}  // namespace nsk
+
+using namespace nsk;
+using namespace nsk::train;
+
+extern "C" int nsk_ddf_pairs_fwd(const float* points, int64_t R, const float* dirs, int D, const float* table,
+                                 const float* scalings, int num_levels, int log2_T, float radius, float* cond, float* xin,
+                                 float* q, float* gt, void* stream) {
+  NSK_REQUIRE(points && dirs && table && scalings && cond && xin && q && gt, "nsk_ddf_pairs_fwd: null pointer");
+  NSK_REQUIRE(num_levels == 16 && log2_T > 0 && log2_T < 31, "nsk_ddf_pairs_fwd: hash grid shape");
+  if (R * D == 0) return 0;
+  ddf_pairs_fwd_kernel<<<grid_for(R * D, 128, 148 * 16), 128, 0, as_stream(stream)>>>(
+      points, R, dirs, D, reinterpret_cast<const float2*>(table), scalings, num_levels, log2_T, radius, cond, xin, q, gt);
+  return check_launch("ddf_pairs_fwd_kernel");
+}
+
+extern "C" int nsk_film_sin_fwd(const float* z, const float* film, int ldf, int layer, int64_t N, float* a, void* stream) {
+  NSK_REQUIRE(z && film && a, "nsk_film_sin_fwd: null pointer");
+  NSK_REQUIRE((ldf & 7) == 0 && layer >= 0 && (layer + 1) * 256 <= ldf / 2, "nsk_film_sin_fwd: layer / ldf");
+  if (N == 0) return 0;
+  film_sin_fwd_kernel<<<grid_for(N * 64, 256), 256, 0, as_stream(stream)>>>(z, film, ldf, layer, N, a);
+  return check_launch("film_sin_fwd_kernel");
+}
+
+extern "C" int nsk_film_sin_bwd(const float* da, const float* z, const float* film, int ldf, int layer, int64_t N, float* dz,
+                                float* dfilm, void* stream) {
+  NSK_REQUIRE(da && z && film && dz && dfilm, "nsk_film_sin_bwd: null pointer");
+  NSK_REQUIRE((ldf & 7) == 0 && layer >= 0 && (layer + 1) * 256 <= ldf / 2, "nsk_film_sin_bwd: layer / ldf");
+  if (N == 0) return 0;
+  film_sin_bwd_kernel<<<grid_for(N * 64, 256), 256, 0, as_stream(stream)>>>(da, z, film, ldf, layer, N, dz, dfilm);
+  return check_launch("film_sin_bwd_kernel");
+}
+
+extern "C" int nsk_ddf_head_fwd(const float* a5, const float* w_final, const float* b_final, const float* gt, int64_t N,
+                                float radius, const float* threshold, float sigmoid_scale, float* that, float* vis,
+                                void* stream) {
+  NSK_REQUIRE(a5 && w_final && b_final && gt && threshold && that && vis, "nsk_ddf_head_fwd: null pointer");
+  if (N == 0) return 0;
+  ddf_head_fwd_kernel<<<grid_for(N * 32, 256), 256, 0, as_stream(stream)>>>(a5, w_final, b_final, gt, N, radius, threshold,
+                                                                         sigmoid_scale, that, vis);
+  return check_launch("ddf_head_fwd_kernel");
+}
+
+extern "C" int nsk_ddf_head_bwd(const float* a5, const float* w_final, const float* that, const float* gt, const float* d_vis,
+                                const float* d_that_extra, int64_t N, float radius, const float* threshold,
+                                float sigmoid_scale, float* da5, float* d_w_final, float* d_b_final, float* d_threshold,
+                                void* stream) {
+  NSK_REQUIRE(a5 && w_final && that && gt && threshold && da5 && d_w_final && d_b_final, "nsk_ddf_head_bwd: null pointer");
+  if (N == 0) return 0;
+  ddf_head_bwd_kernel<<<grid_for(N * 32, 256, 148 * 4), 256, 0, as_stream(stream)>>>(
+      a5, w_final, that, gt, d_vis, d_that_extra, N, radius, threshold, sigmoid_scale, da5, d_w_final, d_b_final, d_threshold);
+  return check_launch("ddf_head_bwd_kernel");
+}
+
+extern "C" int nsk_colsum(const float* X, int ld, int64_t M, int ncols, float* out, void* stream) {
+  NSK_REQUIRE(X && out && ld >= ncols && ncols > 0, "nsk_colsum: arguments");
+  if (M == 0) return 0;
+  const int cb = (ncols + 255) / 256;
+  int64_t rb = std::max<int64_t>(1, std::min<int64_t>((M + 255) / 256, (148 * 8) / cb));
+  const int64_t rows_per_block = (M + rb - 1) / rb;
+  rb = (M + rows_per_block - 1) / rows_per_block;
+  colsum_kernel<<<dim3(cb, (unsigned)rb), 256, 0, as_stream(stream)>>>(X, ld, M, ncols, rows_per_block, out);
+  return check_launch("colsum_kernel");
+}

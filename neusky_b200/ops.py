@@ -328,3 +328,127 @@ def sky_shade(points, normals, wa, inv_count, dirs_sel, radiance_sel, ddf_blob, 
         raise ValueError(f"impl must be 'tc2', 'tc' or 'simt', got {impl!r}")
     _lib.check(fn(_ptr(points), c_int64(R), _ptr(normals), _ptr(wa), _ptr(inv_count), c_int(S), _ptr(dirs_sel), c_int(Dp), _ptr(radiance_sel), _ptr(cam), _ptr(blob), _ptr(hash_table), _ptr(scalings), c_int(L), c_int(log2_T), c_float(radius), c_float(threshold), c_float(sigmoid_scale), _ptr(rgb_lin), _ptr(vis), _ptr(ddf), _ptr(term), _stream(points)), name)
     return vis, ddf, term
+
+
+# ------------------------------------------------------------------------------------------- training path
+ACT = {"none": 0, "relu": 1, "leaky": 2, "softplus100": 3, "sigmoid": 4}
+
+
+def _mat(name: str, t: Tensor, rows: Optional[int] = None, cols: Optional[int] = None) -> Tuple[Tensor, int]:
+    """A row-major 2-D CUDA fp32 view with unit column stride (row stride = leading dimension); slices of wider
+    buffers are passed without a copy."""
+    if not isinstance(t, torch.Tensor) or t.dim() != 2:
+        raise ValueError(f"{name}: expected a 2-D tensor")
+    if not t.is_cuda or t.dtype != torch.float32:
+        raise ValueError(f"{name}: expected a CUDA fp32 tensor (neusky_b200 has no CPU path), got {t.device} {t.dtype}")
+    if t.shape[1] > 1 and t.stride(1) != 1:
+        raise ValueError(f"{name}: columns must be contiguous (stride {t.stride()})")
+    if (rows is not None and t.shape[0] != rows) or (cols is not None and t.shape[1] != cols):
+        raise ValueError(f"{name}: expected shape ({rows}, {cols}), got {tuple(t.shape)}")
+    ld = t.stride(0) if t.shape[0] > 1 else max(t.shape[1], t.stride(0))
+    return t, int(ld)
+
+
+def gemm_nt(A: Tensor, B: Tensor, bias: Optional[Tensor] = None, act: str = "none", out: Optional[Tensor] = None, aux: Optional[Tensor] = None,
+            dact: str = "none", accumulate: bool = False, split: int = 1) -> Tensor:
+    """out[M,N] = dact'(aux) * act(A[M,K] @ B[N,K]^T + bias) (+ out).  tcgen05 kind::tf32; split=3 is the fp32-accurate 3xTF32 mode."""
+    A, lda = _mat("A", A)
+    B, ldb = _mat("B", B, cols=A.shape[1])
+    M, K = A.shape
+    N = B.shape[0]
+    if out is None:
+        if accumulate:
+            raise ValueError("gemm_nt: accumulate needs `out`")
+        out = torch.empty((M, N), device=A.device, dtype=torch.float32)
+    out, ldc = _mat("out", out, rows=M, cols=N)
+    if bias is not None:
+        bias = _chk("bias", bias, shape=(N,))
+    auxp, ldaux = None, 0
+    if dact != "none":
+        auxp, ldaux = _mat("aux", aux, rows=M, cols=N)
+    _lib.check(_lib.load().nsk_gemm_tf32_nt(_ptr(A), c_int(lda), _ptr(B), c_int(ldb), _ptr(out), c_int(ldc), c_int64(M), c_int(N), c_int(K), _ptr(bias), c_int(ACT[act]),
+                                            _ptr(auxp), c_int(ldaux), c_int(ACT[dact]), c_int(int(accumulate)), c_int(split), _stream(A)), "nsk_gemm_tf32_nt")
+    return out
+
+
+def gemm_tn(A: Tensor, B: Tensor, out: Tensor, split: int = 1) -> Tensor:
+    """out[P,Q] += A[M,P]^T @ B[M,Q]  (weight gradient; `out` holds zeros or a running sum)."""
+    A, lda = _mat("A", A)
+    B, ldb = _mat("B", B, rows=A.shape[0])
+    out, ldc = _mat("out", out, rows=A.shape[1], cols=B.shape[1])
+    _lib.check(_lib.load().nsk_gemm_tf32_tn(_ptr(A), c_int(lda), _ptr(B), c_int(ldb), _ptr(out), c_int(ldc), c_int64(A.shape[0]), c_int(A.shape[1]), c_int(B.shape[1]),
+                                            c_int(split), _stream(A)), "nsk_gemm_tf32_tn")
+    return out
+
+
+def colsum(X: Tensor, out: Tensor) -> Tensor:
+    """out[c] += sum_r X[r, c]."""
+    X, ld = _mat("X", X)
+    out = _chk("out", out, shape=(X.shape[1],))
+    _lib.check(_lib.load().nsk_colsum(_ptr(X), c_int(ld), c_int64(X.shape[0]), c_int(X.shape[1]), _ptr(out), _stream(X)), "nsk_colsum")
+    return out
+
+
+def ddf_pairs(points: Tensor, dirs_sel: Tensor, hash_table: Tensor, scalings: Tensor, log2_T: int, radius: float):
+    """(points [R,3], dirs [D',3]) -> cond [N,40], xin [N,16], q [N,3], term_dist [N] with N = R*D' (pair i = r*D' + j)."""
+    R, D = points.shape[0], dirs_sel.shape[0]
+    points, dirs_sel = _chk("points", points, shape=(R, 3)), _chk("dirs_sel", dirs_sel, shape=(D, 3))
+    L = scalings.numel()
+    hash_table, scalings = _chk("hash_table", hash_table, shape=(L << log2_T, 2)), _chk("scalings", scalings)
+    N, dev = R * D, points.device
+    cond = torch.empty((N, 40), device=dev, dtype=torch.float32)
+    xin = torch.empty((N, 16), device=dev, dtype=torch.float32)
+    q = torch.empty((N, 3), device=dev, dtype=torch.float32)
+    term = torch.empty((N,), device=dev, dtype=torch.float32)
+    _lib.check(_lib.load().nsk_ddf_pairs_fwd(_ptr(points), c_int64(R), _ptr(dirs_sel), c_int(D), _ptr(hash_table), _ptr(scalings), c_int(L), c_int(log2_T), c_float(radius),
+                                             _ptr(cond), _ptr(xin), _ptr(q), _ptr(term), _stream(points)), "nsk_ddf_pairs_fwd")
+    return cond, xin, q, term
+
+
+def film_sin(z: Tensor, film: Tensor, layer: int) -> Tensor:
+    N = z.shape[0]
+    z, film = _chk("z", z, shape=(N, 256)), _chk("film", film, shape=(N, None))
+    a = torch.empty_like(z)
+    _lib.check(_lib.load().nsk_film_sin_fwd(_ptr(z), _ptr(film), c_int(film.shape[1]), c_int(layer), c_int64(N), _ptr(a), _stream(z)), "nsk_film_sin_fwd")
+    return a
+
+
+def film_sin_bwd(da: Tensor, z: Tensor, film: Tensor, layer: int, dfilm: Tensor) -> Tensor:
+    """Returns d z [N,256]; writes the layer's frequency / phase column blocks of ``dfilm`` [N, ldf]."""
+    N = z.shape[0]
+    da, z, film = _chk("da", da, shape=(N, 256)), _chk("z", z, shape=(N, 256)), _chk("film", film, shape=(N, None))
+    if not (dfilm.is_cuda and dfilm.dtype == torch.float32 and dfilm.is_contiguous() and dfilm.shape == film.shape):
+        raise ValueError("dfilm: expected a contiguous CUDA fp32 tensor shaped like film")
+    dz = torch.empty_like(z)
+    _lib.check(_lib.load().nsk_film_sin_bwd(_ptr(da), _ptr(z), _ptr(film), c_int(film.shape[1]), c_int(layer), c_int64(N), _ptr(dz), _ptr(dfilm), _stream(z)), "nsk_film_sin_bwd")
+    return dz
+
+
+def ddf_head(a5: Tensor, w_final: Tensor, b_final: Tensor, term_dist: Tensor, radius: float, threshold: Tensor, sigmoid_scale: float):
+    """-> (that [N] expected termination distance, vis [N])."""
+    N = a5.shape[0]
+    a5, w_final, b_final = _chk("a5", a5, shape=(N, 256)), _chk("w_final", w_final.reshape(-1), shape=(256,)), _chk("b_final", b_final.reshape(-1), shape=(1,))
+    term_dist, threshold = _chk("term_dist", term_dist, shape=(N,)), _chk("threshold", threshold.reshape(-1), shape=(1,))
+    that, vis = torch.empty_like(term_dist), torch.empty_like(term_dist)
+    _lib.check(_lib.load().nsk_ddf_head_fwd(_ptr(a5), _ptr(w_final), _ptr(b_final), _ptr(term_dist), c_int64(N), c_float(radius), _ptr(threshold), c_float(sigmoid_scale),
+                                            _ptr(that), _ptr(vis), _stream(a5)), "nsk_ddf_head_fwd")
+    return that, vis
+
+
+def ddf_head_bwd(a5: Tensor, w_final: Tensor, that: Tensor, term_dist: Tensor, d_vis: Optional[Tensor], d_that_extra: Optional[Tensor], radius: float, threshold: Tensor,
+                 sigmoid_scale: float, d_w_final: Tensor, d_b_final: Tensor, d_threshold: Optional[Tensor]) -> Tensor:
+    """-> d a5 [N,256]; accumulates d w_final [256], d b_final [1], d threshold [1]."""
+    N = a5.shape[0]
+    a5, w_final = _chk("a5", a5, shape=(N, 256)), _chk("w_final", w_final.reshape(-1), shape=(256,))
+    that, term_dist, threshold = _chk("that", that, shape=(N,)), _chk("term_dist", term_dist, shape=(N,)), _chk("threshold", threshold.reshape(-1), shape=(1,))
+    if d_vis is not None:
+        d_vis = _chk("d_vis", d_vis.reshape(-1), shape=(N,))
+    if d_that_extra is not None:
+        d_that_extra = _chk("d_that_extra", d_that_extra.reshape(-1), shape=(N,))
+    for nm, t, n in (("d_w_final", d_w_final, 256), ("d_b_final", d_b_final, 1)) + ((("d_threshold", d_threshold, 1),) if d_threshold is not None else ()):
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.numel() == n):
+            raise ValueError(f"{nm}: expected a contiguous CUDA fp32 accumulator with {n} elements")
+    da5 = torch.empty_like(a5)
+    _lib.check(_lib.load().nsk_ddf_head_bwd(_ptr(a5), _ptr(w_final), _ptr(that), _ptr(term_dist), _ptr(d_vis), _ptr(d_that_extra), c_int64(N), c_float(radius), _ptr(threshold),
+                                            c_float(sigmoid_scale), _ptr(da5), _ptr(d_w_final), _ptr(d_b_final), _ptr(d_threshold), _stream(a5)), "nsk_ddf_head_bwd")
+    return da5

@@ -1,0 +1,183 @@
+"""Training-path ops (csrc/gemm_tf32.cu, csrc/train_ops.cu, neusky_b200/train.py) vs the CPU oracle.
+
+Tolerances.  split=3 (3xTF32) is the fp32-accurate mode: contractions must match an fp64 matmul to 2e-6 of the
+operand-norm product and network gradients must match fp64 autograd through the oracle to 2e-3 relative.  split=1 (one
+tf32 pass, 10-bit mantissa operands) is the throughput mode: 2e-3 on contractions, 5e-2 relative (norm-wise) on gradients.
+"""
+import pytest
+import torch
+
+from neusky_b200 import init as nb_init
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from neusky_b200 import _lib
+
+    _lib.load()
+    return torch.device("cuda:0")
+
+
+def _rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+ACT_REF = {
+    "none": lambda v: v,
+    "relu": torch.relu,
+    "leaky": lambda v: torch.nn.functional.leaky_relu(v, 0.2),
+    "softplus100": lambda v: torch.nn.functional.softplus(v, beta=100),
+    "sigmoid": torch.sigmoid,
+}
+DACT_REF = {
+    "relu": lambda a: (a > 0).double(),
+    "leaky": lambda a: torch.where(a > 0, 1.0, 0.2).double(),
+    "softplus100": lambda a: 1.0 - torch.exp(-100.0 * a),
+    "sigmoid": lambda a: a * (1 - a),
+}
+
+
+@pytest.mark.parametrize("split", [3, 1])
+@pytest.mark.parametrize(
+    "M,N,K,act,bias",
+    [
+        (1000, 256, 256, "none", False),
+        (128, 256, 32, "none", False),
+        (333, 2560, 256, "none", True),
+        (129, 40, 256, "leaky", True),
+        (777, 256, 40, "softplus100", True),
+        (500, 3, 256, "sigmoid", True),
+        (4099, 256, 72, "relu", True),
+        (260, 296, 296, "none", False),
+        (1, 32, 2560, "none", False),
+    ],
+)
+def test_gemm_nt(dev, split, M, N, K, act, bias):
+    from neusky_b200 import ops
+
+    g = torch.Generator().manual_seed(M * 7 + N * 3 + K)
+    A = torch.randn(M, K, generator=g) * 0.5
+    B = torch.randn(N, K, generator=g) * 0.2
+    b = torch.randn(N, generator=g) * 0.1 if bias else None
+    ref = A.double() @ B.double().T + (b.double() if bias else 0.0)
+    ref = ACT_REF[act](ref)
+    out = ops.gemm_nt(A.to(dev), B.to(dev), bias=None if b is None else b.to(dev), act=act, split=split)
+    scale = float((A.double().norm(dim=1)[:, None] * B.double().norm(dim=1)[None, :]).mean())
+    err = float((out.double().cpu() - ref).abs().max())
+    tol = (2e-6 if split == 3 else 2e-3) * scale if act in ("none", "relu", "leaky") else (1e-5 if split == 3 else 3e-3)
+    assert err <= tol, f"gemm_nt M={M} N={N} K={K} act={act} split={split}: max err {err:.3e} > {tol:.3e}"
+
+
+@pytest.mark.parametrize("dact", ["leaky", "softplus100", "relu", "sigmoid"])
+def test_gemm_nt_dact_accumulate_strided(dev, dact):
+    from neusky_b200 import ops
+
+    g = torch.Generator().manual_seed(11)
+    M, N, K = 517, 256, 256
+    wide = torch.randn(M, K + 40, generator=g).to(dev)      # A is a column slice of a wider buffer (lda = K + 40)
+    A = wide[:, 8:8 + K]
+    B = (torch.randn(N, K, generator=g) * 0.1).to(dev)
+    aux = torch.rand(M, N, generator=g) * (0.05 if dact == "softplus100" else 1.0) - (0.0 if dact in ("softplus100", "sigmoid") else 0.5)
+    aux = aux.to(dev)
+    C0 = torch.randn(M, N, generator=g).to(dev)
+    out = ops.gemm_nt(A, B, out=C0.clone(), aux=aux, dact=dact, accumulate=True, split=3)
+    ref = C0.double().cpu() + (A.double().cpu() @ B.double().cpu().T) * DACT_REF[dact](aux.double().cpu())
+    assert float((out.double().cpu() - ref).abs().max()) <= 2e-5
+
+
+@pytest.mark.parametrize("split", [3, 1])
+@pytest.mark.parametrize("M,P,Q", [(5000, 256, 256), (333, 2560, 256), (1000, 256, 72), (2049, 256, 296), (700, 3, 256), (31, 256, 16), (40000, 256, 40)])
+def test_gemm_tn(dev, split, M, P, Q):
+    from neusky_b200 import ops
+
+    g = torch.Generator().manual_seed(M + P + Q)
+    A = torch.randn(M, P, generator=g) * 0.3
+    B = torch.randn(M, Q, generator=g) * 0.3
+    C0 = torch.randn(P, Q, generator=g)
+    out = ops.gemm_tn(A.to(dev), B.to(dev), C0.to(dev).clone(), split=split)
+    ref = C0.double() + A.double().T @ B.double()
+    scale = float((A.double().norm(dim=0)[:, None] * B.double().norm(dim=0)[None, :]).mean())
+    err = float((out.double().cpu() - ref).abs().max())
+    tol = (3e-6 if split == 3 else 2e-3) * scale + 1e-5
+    assert err <= tol, f"gemm_tn M={M} P={P} Q={Q} split={split}: max err {err:.3e} > {tol:.3e}"
+
+
+def test_colsum_and_film_sin(dev):
+    from neusky_b200 import ops
+
+    g = torch.Generator().manual_seed(3)
+    X = torch.randn(3001, 300, generator=g)
+    out = ops.colsum(X.to(dev)[:, 4:260], torch.ones(256, device=dev))
+    assert float((out.cpu().double() - (1.0 + X[:, 4:260].double().sum(0))).abs().max()) <= 2e-3
+    N = 777
+    z = torch.randn(N, 256, generator=g) * 0.3
+    film = torch.randn(N, 2560, generator=g) * 0.5
+    for l in (0, 3, 4):
+        a = ops.film_sin(z.to(dev), film.to(dev), l)
+        zd, fd = z.double().requires_grad_(True), film.double().requires_grad_(True)
+        ref = torch.sin((fd[:, l * 256:(l + 1) * 256] * 15 + 30) * zd + fd[:, 1280 + l * 256:1280 + (l + 1) * 256])
+        assert float((a.cpu().double() - ref.detach()).abs().max()) <= 2e-5
+        cot = torch.randn(N, 256, generator=g)
+        ref.backward(cot.double())
+        dfilm = torch.zeros(N, 2560, device=dev)
+        dz = ops.film_sin_bwd(cot.to(dev), z.to(dev), film.to(dev), l, dfilm)
+        assert _rel(dz, zd.grad) <= 1e-4
+        assert _rel(dfilm, fd.grad) <= 1e-4
+
+
+def _ddf_case(R, Dn, seed, log2_T=14):
+    from oracle import neusky_oracle as O
+
+    p = nb_init.init_ddf_params(seed, final_gain=8.0, log2_T=log2_T, table_scale=0.1)
+    g = torch.Generator().manual_seed(seed + 1)
+    pts = torch.nn.functional.normalize(torch.randn(R, 3, generator=g), dim=-1) * torch.rand(R, 1, generator=g) ** (1 / 3) * 0.9
+    dirs = O.icosphere_directions(Dn)
+    dirs = dirs[dirs[:, 2] > 0].contiguous()
+    return p, pts, dirs
+
+
+@pytest.mark.parametrize("split,tol_fwd,tol_grad", [(3, 2e-4, 2e-3), (1, 2e-2, 8e-2)])
+def test_ddf_visibility_forward_backward_vs_oracle_autograd(dev, split, tol_fwd, tol_grad):
+    """vis / expected termination distance and the gradients of every DDF parameter, the hash table and the threshold
+    against fp64 autograd through oracle.compute_visibility (neusky_model.py:1685-1740 + ddf_model.py + film_siren.py)."""
+    from neusky_b200 import train as T
+    from oracle import neusky_oracle as O
+
+    log2_T = 14
+    R = 37
+    p, pts, dirs = _ddf_case(R, 100, 5, log2_T)
+    Dp = dirs.shape[0]
+    thr0, scale = 0.35, 25.0
+    g = torch.Generator().manual_seed(99)
+    cot_vis = torch.randn(R, Dp, generator=g)
+    cot_that = torch.randn(R * Dp, generator=g) * 0.3
+
+    # ---- oracle, fp64 autograd ----
+    pd = {k: v.double().requires_grad_(True) for k, v in p.items()}
+    thr_ref = torch.tensor(thr0, dtype=torch.float64, requires_grad=True)
+    o = O.compute_visibility(pts.double(), dirs.double(), pd, O.hash_scalings().double(), log2_T, 1.0, thr_ref, scale, only_upper=True)
+    loss = (o["visibility"] * cot_vis.double()).sum() + (o["expected_termination_dist"] * cot_that.double()).sum()
+    loss.backward()
+
+    # ---- CUDA ----
+    cfg = T.DDFConfig(scalings=O.hash_scalings().to(dev), log2_T=log2_T, radius=1.0, sigmoid_scale=scale, split=split)
+    pc = {k: v.to(dev).requires_grad_(True) for k, v in p.items()}
+    thr = torch.tensor(thr0, device=dev, requires_grad=True)
+    vis, that, q, term = T.ddf_visibility(cfg, pts.to(dev), dirs.to(dev), thr, pc["position_encoding.hash_table"], pc["ddf.final_layer.weight"], pc["ddf.final_layer.bias"],
+                                          T.ddf_param_list(pc))
+    assert float((term.cpu().double() - o["termination_dist"].detach()).abs().max()) <= 1e-5
+    assert float((that.cpu().double() - o["expected_termination_dist"].detach()).abs().max()) <= tol_fwd
+    assert float((vis.cpu().double() - o["visibility"].detach()).abs().max()) <= tol_fwd * 25
+    ((vis * cot_vis.to(dev)).sum() + (that * cot_that.to(dev)).sum()).backward()
+    assert abs(float(thr.grad) - float(thr_ref.grad)) <= tol_grad * abs(float(thr_ref.grad)) + 1e-6
+    worst = {}
+    for k in p:
+        assert pc[k].grad is not None, k
+        worst[k] = _rel(pc[k].grad, pd[k].grad)
+    bad = {k: v for k, v in worst.items() if not v <= tol_grad}
+    assert not bad, f"split={split}: gradient mismatch {bad} (all: {worst})"
