@@ -264,6 +264,29 @@ int nsk_ddf_head_bwd(const float* a5, const float* w_final, const float* that, c
                      float* da5, float* d_w_final, float* d_b_final, float* d_threshold, void* stream);
 int nsk_colsum(const float* X, int ld, int64_t M, int ncols, float* out, void* stream);
 
+/* SDF / albedo field, training path (sdf_albedo_field.py:211-269; nerfstudio SDFField.forward_geonetwork).
+ * nsk_sdf_inputs_fwd: x [n,3] -> H0 [n,72] = (x | PE6(x) | hash((contract_inf(x)+2)/4) | 0) (the geo-network input in the
+ *     reference's concatenation order), tail [n, ld_tail] columns [0,40) = (x | PE6(x) | 0) (colour-network input tail; NULL =
+ *     skip), pos [n,3] (hash-grid position) and J [n,9] = d pos / d x.
+ * nsk_sdf_grad_assemble: input stage of the reverse pass that replaces torch.autograd.grad(sdf, x) (sdf_albedo_field.py:235-238):
+ *     grad_x [n,3] = G[:,0:3] + PE6'(x)^T G[:,3:39] + J^T gpos, with G [n,72] = d . / d H0 and gpos [n,3] = nsk_hash_encode_grad_x
+ *     of G[:,39:71].  nsk_sdf_grad_assemble_bwd is its transpose for a cotangent c [n,3] (the normals' double backward): writes
+ *     columns [0,39) and 71 of dG [n,72] and cpos [n,3] = J c; the hash columns come from nsk_hash_encode_grad_x_bwd.
+ * nsk_ew256: pointwise family over [n,256] tensors with s' / s'' of softplus(beta=100) taken from the activation OUTPUT:
+ *     0: out = w[col] s'(a)   1: out = a s'(b)   2: out = a s'(b) + c d s''(b)   3: out = a s'(b) + c w[col] s''(b)
+ *     4: out = a + s[row] w[col]      (NULL a / c drop that term).
+ * nsk_rowdot256: out[r] = X[r,:256] . w + b[0] (the sdf head, exact fp32).  nsk_colsum_w: out[c] += sum_r v[r] X[r,c]. */
+int nsk_sdf_inputs_fwd(const float* x, int64_t n, const float* table, const float* scalings, int num_levels, int log2_T,
+                       float* H0, float* tail, int ld_tail, float* pos, float* J, void* stream);
+int nsk_sdf_grad_assemble(const float* x, const float* G, const float* gpos, const float* J, int64_t n, float* grad,
+                          void* stream);
+int nsk_sdf_grad_assemble_bwd(const float* x, const float* c, const float* J, int64_t n, float* dG, float* cpos,
+                              void* stream);
+int nsk_ew256(int op, int64_t n, const float* a, const float* b, const float* c, const float* d, const float* w,
+              const float* s, float* out, void* stream);
+int nsk_rowdot256(const float* X, const float* w, const float* b, int64_t n, float* out, void* stream);
+int nsk_colsum_w(const float* X, int ld, const float* v, int64_t M, int ncols, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

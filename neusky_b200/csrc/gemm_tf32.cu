@@ -35,6 +35,8 @@ constexpr int THREADS = 13 * 32;
 constexpr uint32_t A_BYTES = TM * KC * 4;
 constexpr uint32_t B_BYTES = BN * KC * 4;
 constexpr uint32_t A_LBO = TM * 16, B_LBO = BN * 16;
+constexpr int EPI_LD = 36;                                  // floats per staged row (32 + 4: conflict-free 16-byte accesses)
+constexpr uint32_t EPI_BYTES = 4 * 32 * EPI_LD * 4;         // 4 epilogue warps x 32 rows
 
 struct Params {
   const float* A;
@@ -125,7 +127,7 @@ __device__ __forceinline__ float act_apply(float v, int act) {
 __device__ __forceinline__ float dact_from_output(float a, int dact) {
   if (dact == 1) return a > 0.0f ? 1.0f : 0.0f;
   if (dact == 2) return a > 0.0f ? 1.0f : 0.2f;
-  if (dact == 3) return 1.0f - expf(-100.0f * a);   // softplus_100: sigmoid(100 z) = 1 - exp(-100 a)
+  if (dact == 3) return -expm1f(-100.0f * a);        // softplus_100: sigmoid(100 z) = 1 - exp(-100 a)
   if (dact == 4) return a * (1.0f - a);
   return 1.0f;
 }
@@ -276,55 +278,87 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32_kernel(const Params p) {
     __syncwarp();
   } else {
     // ------------------------------------------------------------------ epilogue
+    // tcgen05.ld gives thread = row, 32 consecutive columns.  NT: transpose each 32x32 chunk through shared memory so that
+    // one st.global.v4 of the warp covers 4 rows x 128 contiguous bytes (and the bias / aux / accumulate reads are coalesced
+    // the same way).  TN: red.global.add straight from the registers (once per split, not per row tile).
     const int q = warp - EPI_WARP0;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    float* const stg = reinterpret_cast<float*>(smem + ST * STAGE + 256) + q * (32 * EPI_LD);
     uint32_t iter = 0;
-    const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+    const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
+                        (p.dact == 0 || (((p.ldaux & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.aux) & 15) == 0)));
+    const int sub = lane >> 3, c4 = (lane & 7) * 4;   // phase 2: 8 lanes per row, 4 rows per instruction
     for (int64_t w = blockIdx.x; w < p.n_items; w += gridDim.x, ++iter) {
       const Item it = get_item<TN>(p, w);
       const uint32_t buf = iter & 1;
       mbar_wait(ACCF + 8 * buf, (iter >> 1) & 1);
       tc_fence_after();
-      const int64_t row = it.a0 + q * 32 + lane;
-      const bool row_ok = TN ? (row < p.N) : (row < p.M);
       const int ncols = TN ? p.K : p.N;
       const bool has_data = it.r0 < it.r1;
-      for (int c0 = 0; c0 < it.bn; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem + lane_off + buf * BN + c0, v);
-        tmem_ld_wait();
-        if (!row_ok || !has_data) continue;
-        float* crow = p.C + row * p.ldc + it.b0 + c0;
-        if (TN) {
+      if (TN) {
+        const int64_t row = it.a0 + q * 32 + lane;
+        const bool row_ok = row < p.N;
+        for (int c0 = 0; c0 < it.bn; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(tmem + lane_off + buf * BN + c0, v);
+          tmem_ld_wait();
+          if (!row_ok || !has_data) continue;
+          float* crow = p.C + row * p.ldc + it.b0 + c0;
 #pragma unroll
           for (int c = 0; c < 32; ++c)
             if (it.b0 + c0 + c < ncols) atomicAdd(crow + c, __uint_as_float(v[c]));
-        } else {
-          float f[32];
+        }
+      } else {
+        const int64_t row0 = it.a0 + q * 32;
+        for (int c0 = 0; c0 < it.bn; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(tmem + lane_off + buf * BN + c0, v);
+          tmem_ld_wait();
 #pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            float x = __uint_as_float(v[c]);
-            const int n = it.b0 + c0 + c;
-            if (p.bias != nullptr && n < ncols) x += __ldg(p.bias + n);
-            x = act_apply(x, p.act);
-            if (p.dact != 0 && n < ncols) x *= dact_from_output(p.aux[row * p.ldaux + n], p.dact);
-            f[c] = x;
+          for (int c = 0; c < 32; c += 4)
+            *reinterpret_cast<float4*>(stg + lane * EPI_LD + c) =
+                make_float4(__uint_as_float(v[c]), __uint_as_float(v[c + 1]), __uint_as_float(v[c + 2]), __uint_as_float(v[c + 3]));
+          __syncwarp();
+          const int n0 = it.b0 + c0 + c4;
+          float bia[4] = {0.f, 0.f, 0.f, 0.f};
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (n0 + e < ncols) bia[e] = __ldg(p.bias + n0 + e);
           }
-          if (vec_ok && it.b0 + c0 + 32 <= ncols) {
 #pragma unroll
-            for (int c = 0; c < 32; c += 4) {
-              float4 o = make_float4(f[c], f[c + 1], f[c + 2], f[c + 3]);
-              if (p.accumulate) {
-                const float4 old = *reinterpret_cast<const float4*>(crow + c);
-                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+          for (int rr = 0; rr < 32; rr += 4) {
+            const int rl = rr + sub;
+            const int64_t row = row0 + rl;
+            const float4 t = *reinterpret_cast<const float4*>(stg + rl * EPI_LD + c4);
+            if (row >= p.M || n0 >= ncols) continue;
+            float f[4] = {t.x + bia[0], t.y + bia[1], t.z + bia[2], t.w + bia[3]};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) f[e] = act_apply(f[e], p.act);
+            float* cp = p.C + row * p.ldc + n0;
+            if (vec_ok && n0 + 4 <= ncols) {
+              if (p.dact != 0) {
+                const float4 a = *reinterpret_cast<const float4*>(p.aux + row * p.ldaux + n0);
+                f[0] *= dact_from_output(a.x, p.dact); f[1] *= dact_from_output(a.y, p.dact);
+                f[2] *= dact_from_output(a.z, p.dact); f[3] *= dact_from_output(a.w, p.dact);
               }
-              *reinterpret_cast<float4*>(crow + c) = o;
-            }
-          } else {
+              if (p.accumulate) {
+                const float4 old = *reinterpret_cast<const float4*>(cp);
+                f[0] += old.x; f[1] += old.y; f[2] += old.z; f[3] += old.w;
+              }
+              *reinterpret_cast<float4*>(cp) = make_float4(f[0], f[1], f[2], f[3]);
+            } else {
 #pragma unroll
-            for (int c = 0; c < 32; ++c)
-              if (it.b0 + c0 + c < ncols) crow[c] = p.accumulate ? crow[c] + f[c] : f[c];
+              for (int e = 0; e < 4; ++e) {
+                if (n0 + e < ncols) {
+                  float x = f[e];
+                  if (p.dact != 0) x *= dact_from_output(p.aux[row * p.ldaux + n0 + e], p.dact);
+                  cp[e] = p.accumulate ? cp[e] + x : x;
+                }
+              }
+            }
           }
+          __syncwarp();
         }
       }
       tc_fence_before();
@@ -341,7 +375,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32_kernel(const Params p) {
 
 template <int SPLIT>
 constexpr size_t smem_bytes() {
-  return (size_t)((SPLIT == 3) ? 2 : 4) * (A_BYTES + B_BYTES) * (SPLIT == 3 ? 2 : 1) + 256;
+  return (size_t)((SPLIT == 3) ? 2 : 4) * (A_BYTES + B_BYTES) * (SPLIT == 3 ? 2 : 1) + 256 + EPI_BYTES;
 }
 
 static int sm_count() {

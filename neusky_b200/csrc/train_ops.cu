@@ -12,7 +12,10 @@
 //   nsk_ddf_head_bwd    backward of the head: d a5, d w_final, d b_final, d threshold
 //   nsk_colsum          bias gradients: out[c] += sum_r X[r, c]
 // All fp32, memory-bound elementwise / row-reduction kernels; one pass over their operands each.
+#include <algorithm>
+
 #include "nsk_common.cuh"
+#include "sdf_common.cuh"
 
 namespace nsk {
 namespace train {
@@ -273,4 +276,259 @@ extern "C" int nsk_colsum(const float* X, int ld, int64_t M, int ncols, float* o
   rb = (M + rows_per_block - 1) / rows_per_block;
   colsum_kernel<<<dim3(cb, (unsigned)rb), 256, 0, as_stream(stream)>>>(X, ld, M, ncols, rows_per_block, out);
   return check_launch("colsum_kernel");
+}
+
+// =====================================================================================================================
+// SDF / albedo field, training path (neusky/fields/sdf_albedo_field.py:211-269 + nerfstudio SDFField.forward_geonetwork):
+// the stages between the tf32 contractions, including the pieces of the normals' double backward.
+// =====================================================================================================================
+
+namespace nsk {
+namespace train {
+
+constexpr int H0_LD = 72;     // [x 3 | PE6 36 | hash 32 | pad 1]   (reference concatenation order, sdf_albedo_field.py / SDFField)
+constexpr float TWO_PI_F = 6.283185307179586f;
+
+// PE6(x): index d*6+k -> sin(2 pi 2^k x_d), 18 + d*6+k -> sin(2 pi 2^k x_d + pi/2)   [nerfstudio NeRFEncoding, SURVEY A.2]
+__device__ __forceinline__ void pe6(const float x[3], float* out /*36*/) {
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const float s = TWO_PI_F * x[d];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const float a = s * (float)(1 << k);
+      out[d * 6 + k] = sinf(a);
+      out[18 + d * 6 + k] = sinf(a + 1.5707963267948966f);
+    }
+  }
+}
+
+// x [n,3] -> H0 [n,72] (x, PE, hash(pos), 0), tail [n, ld_tail] columns [0,39) = (x, PE) and column 39 = 0 (colour-net input
+// tail; NULL = skip), pos [n,3] = (contract_inf(x) + 2) / 4, J [n,9] = d pos / d x
+__global__ void __launch_bounds__(128)
+sdf_inputs_fwd_kernel(const float* __restrict__ x, int64_t n, const float2* __restrict__ table, const float* __restrict__ scalings,
+                      int L, int log2_T, float* __restrict__ H0, float* __restrict__ tail, int ld_tail, float* __restrict__ pos_out,
+                      float* __restrict__ J_out) {
+  const uint32_t mask = (1u << log2_T) - 1u;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float xv[3] = {x[i * 3], x[i * 3 + 1], x[i * 3 + 2]};
+    float pos[3], J[9], enc[36];
+    sdf_contract(xv, pos, J);
+    pe6(xv, enc);
+    float* h = H0 + i * H0_LD;
+    h[0] = xv[0]; h[1] = xv[1]; h[2] = xv[2];
+#pragma unroll
+    for (int c = 0; c < 36; ++c) h[3 + c] = enc[c];
+    if (tail != nullptr) {
+      float* t = tail + i * ld_tail;
+      t[0] = xv[0]; t[1] = xv[1]; t[2] = xv[2];
+#pragma unroll
+      for (int c = 0; c < 36; ++c) t[3 + c] = enc[c];
+      t[39] = 0.f;
+    }
+    for (int lev = 0; lev < L; ++lev) {
+      const float s = scalings[lev];
+      uint32_t idx[8];
+      float ox, oy, oz;
+      hash_corners(__fmul_rn(pos[0], s), __fmul_rn(pos[1], s), __fmul_rn(pos[2], s), mask, idx, ox, oy, oz);
+      const float2* tl = table + ((size_t)lev << log2_T);
+      float2 f[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) f[c] = __ldg(tl + idx[c]);
+      const float2 v = hash_interp(f, ox, oy, oz);
+      h[39 + 2 * lev] = v.x;
+      h[40 + 2 * lev] = v.y;
+    }
+    h[71] = 0.f;
+    pos_out[i * 3] = pos[0]; pos_out[i * 3 + 1] = pos[1]; pos_out[i * 3 + 2] = pos[2];
+#pragma unroll
+    for (int c = 0; c < 9; ++c) J_out[i * 9 + c] = J[c];
+  }
+}
+
+// grad_x = G[:, 0:3] + PE'(x)^T G[:, 3:39] + J^T gpos      (the input stage of the reverse pass; G = d . / d H0)
+__global__ void __launch_bounds__(128)
+sdf_grad_assemble_kernel(const float* __restrict__ x, const float* __restrict__ G, const float* __restrict__ gpos,
+                         const float* __restrict__ J, int64_t n, float* __restrict__ grad) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float* g = G + i * H0_LD;
+    float out[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const float s = TWO_PI_F * x[i * 3 + d];
+      float acc = g[d];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        const float f = (float)(1 << k), a = s * f;
+        // d sin(a)/dx = 2 pi f cos(a);  d sin(a + pi/2)/dx = 2 pi f cos(a + pi/2)
+        acc += TWO_PI_F * f * (g[3 + d * 6 + k] * cosf(a) + g[3 + 18 + d * 6 + k] * cosf(a + 1.5707963267948966f));
+      }
+      out[d] = acc;
+    }
+    const float* Jr = J + i * 9;
+    const float gp[3] = {gpos[i * 3], gpos[i * 3 + 1], gpos[i * 3 + 2]};
+#pragma unroll
+    for (int d = 0; d < 3; ++d) grad[i * 3 + d] = out[d] + Jr[0 * 3 + d] * gp[0] + Jr[1 * 3 + d] * gp[1] + Jr[2 * 3 + d] * gp[2];
+  }
+}
+
+// transpose of the above for a cotangent c [n,3] on grad_x: dG[:, 0:3] = c, dG[:, 3:39] = PE'(x) c, dG[:, 71] = 0, cpos = J c
+// (columns 39..70 of dG, the hash part, are filled from nsk_hash_encode_grad_x_bwd by the host)
+__global__ void __launch_bounds__(128)
+sdf_grad_assemble_bwd_kernel(const float* __restrict__ x, const float* __restrict__ c, const float* __restrict__ J, int64_t n,
+                             float* __restrict__ dG, float* __restrict__ cpos) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float* g = dG + i * H0_LD;
+    const float cv[3] = {c[i * 3], c[i * 3 + 1], c[i * 3 + 2]};
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const float s = TWO_PI_F * x[i * 3 + d];
+      g[d] = cv[d];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        const float f = (float)(1 << k), a = s * f;
+        g[3 + d * 6 + k] = TWO_PI_F * f * cosf(a) * cv[d];
+        g[3 + 18 + d * 6 + k] = TWO_PI_F * f * cosf(a + 1.5707963267948966f) * cv[d];
+      }
+    }
+    g[71] = 0.f;
+    const float* Jr = J + i * 9;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) cpos[i * 3 + r] = Jr[r * 3 + 0] * cv[0] + Jr[r * 3 + 1] * cv[1] + Jr[r * 3 + 2] * cv[2];
+  }
+}
+
+// softplus_100 derivatives through the OUTPUT a: s' = sigmoid(100 z) = 1 - exp(-100 a), s'' = 100 s' (1 - s')
+__device__ __forceinline__ float sp_d1(float a) { return -expm1f(-100.0f * a); }
+__device__ __forceinline__ float sp_d2(float a) { const float s = sp_d1(a); return 100.0f * s * (1.0f - s); }
+
+// pointwise family over [n,256] fp32 tensors (a, b, c, d, out contiguous), w [256] column vector, s [n] row vector
+//   0  out = w[col] * sp'(a)                          G2 of the reverse pass
+//   1  out = a * sp'(b)
+//   2  out = a * sp'(b) + c * d * sp''(b)             (c == NULL: second term dropped; a == NULL: first term dropped)
+//   3  out = a * sp'(b) + c * w[col] * sp''(b)        (same NULL rules)
+//   4  out = a + s[row] * w[col]                      (a == NULL: outer product only)
+__global__ void __launch_bounds__(256)
+ew256_kernel(int op, int64_t n, const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c,
+             const float* __restrict__ d, const float* __restrict__ w, const float* __restrict__ s, float* __restrict__ out) {
+  const int64_t total = n * 64;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i >> 6;
+    const int col = (int)(i & 63) * 4;
+    const int64_t o = r * 256 + col;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 va = a ? *reinterpret_cast<const float4*>(a + o) : z4;
+    const float4 vb = b ? *reinterpret_cast<const float4*>(b + o) : z4;
+    const float4 vc = c ? *reinterpret_cast<const float4*>(c + o) : z4;
+    const float4 vd = d ? *reinterpret_cast<const float4*>(d + o) : z4;
+    const float4 vw = w ? *reinterpret_cast<const float4*>(w + col) : z4;
+    const float sr = s ? s[r] : 0.f;
+    float4 res;
+#define NSK_EW(k)                                                                  \
+  {                                                                                \
+    float v;                                                                       \
+    if (op == 0) v = vw.k * sp_d1(va.k);                                           \
+    else if (op == 1) v = va.k * sp_d1(vb.k);                                      \
+    else if (op == 2) v = va.k * sp_d1(vb.k) + (c ? vc.k * vd.k * sp_d2(vb.k) : 0.f); \
+    else if (op == 3) v = va.k * sp_d1(vb.k) + (c ? vc.k * vw.k * sp_d2(vb.k) : 0.f); \
+    else v = va.k + sr * vw.k;                                                     \
+    res.k = v;                                                                     \
+  }
+    NSK_EW(x) NSK_EW(y) NSK_EW(z) NSK_EW(w)
+#undef NSK_EW
+    *reinterpret_cast<float4*>(out + o) = res;
+  }
+}
+
+// out[r] = X[r, :256] . w + b   (exact fp32; the sdf head)
+__global__ void __launch_bounds__(256)
+rowdot256_kernel(const float* __restrict__ X, const float* __restrict__ w, const float* __restrict__ b, int64_t n, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const float4 w0 = *reinterpret_cast<const float4*>(w + lane * 8), w1 = *reinterpret_cast<const float4*>(w + lane * 8 + 4);
+  const float bias = b ? b[0] : 0.f;
+  for (int64_t r = warp; r < n; r += nwarps) {
+    const float4 x0 = *reinterpret_cast<const float4*>(X + r * 256 + lane * 8), x1 = *reinterpret_cast<const float4*>(X + r * 256 + lane * 8 + 4);
+    float s = x0.x * w0.x + x0.y * w0.y + x0.z * w0.z + x0.w * w0.w + x1.x * w1.x + x1.y * w1.y + x1.z * w1.z + x1.w * w1.w;
+    s = warp_sum(s);
+    if (lane == 0) out[r] = s + bias;
+  }
+}
+
+// out[c] += sum_r v[r] * X[r, c]
+__global__ void __launch_bounds__(256)
+colsum_w_kernel(const float* __restrict__ X, int ld, const float* __restrict__ v, int64_t M, int ncols, int64_t rows_per_block,
+                float* __restrict__ out) {
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
+  if (c >= ncols) return;
+  float s0 = 0.f, s1 = 0.f;
+  int64_t r = r0;
+  for (; r + 1 < r1; r += 2) {
+    s0 = fmaf(v[r], X[r * ld + c], s0);
+    s1 = fmaf(v[r + 1], X[(r + 1) * ld + c], s1);
+  }
+  if (r < r1) s0 = fmaf(v[r], X[r * ld + c], s0);
+  atomicAdd(out + c, s0 + s1);
+}
+
+}  // namespace train
+}  // namespace nsk
+
+extern "C" int nsk_sdf_inputs_fwd(const float* x, int64_t n, const float* table, const float* scalings, int num_levels,
+                                  int log2_T, float* H0, float* tail, int ld_tail, float* pos, float* J, void* stream) {
+  NSK_REQUIRE(x && table && scalings && H0 && pos && J, "nsk_sdf_inputs_fwd: null pointer");
+  NSK_REQUIRE(num_levels == 16 && log2_T > 0 && log2_T < 31, "nsk_sdf_inputs_fwd: hash grid shape");
+  NSK_REQUIRE(tail == nullptr || ld_tail >= 40, "nsk_sdf_inputs_fwd: ld_tail");
+  if (n == 0) return 0;
+  sdf_inputs_fwd_kernel<<<grid_for(n, 128, 148 * 16), 128, 0, as_stream(stream)>>>(x, n, reinterpret_cast<const float2*>(table), scalings,
+                                                                                 num_levels, log2_T, H0, tail, ld_tail, pos, J);
+  return check_launch("sdf_inputs_fwd_kernel");
+}
+
+extern "C" int nsk_sdf_grad_assemble(const float* x, const float* G, const float* gpos, const float* J, int64_t n, float* grad,
+                                     void* stream) {
+  NSK_REQUIRE(x && G && gpos && J && grad, "nsk_sdf_grad_assemble: null pointer");
+  if (n == 0) return 0;
+  sdf_grad_assemble_kernel<<<grid_for(n, 128, 148 * 16), 128, 0, as_stream(stream)>>>(x, G, gpos, J, n, grad);
+  return check_launch("sdf_grad_assemble_kernel");
+}
+
+extern "C" int nsk_sdf_grad_assemble_bwd(const float* x, const float* c, const float* J, int64_t n, float* dG, float* cpos,
+                                         void* stream) {
+  NSK_REQUIRE(x && c && J && dG && cpos, "nsk_sdf_grad_assemble_bwd: null pointer");
+  if (n == 0) return 0;
+  sdf_grad_assemble_bwd_kernel<<<grid_for(n, 128, 148 * 16), 128, 0, as_stream(stream)>>>(x, c, J, n, dG, cpos);
+  return check_launch("sdf_grad_assemble_bwd_kernel");
+}
+
+extern "C" int nsk_ew256(int op, int64_t n, const float* a, const float* b, const float* c, const float* d, const float* w,
+                         const float* s, float* out, void* stream) {
+  NSK_REQUIRE(op >= 0 && op <= 4 && out, "nsk_ew256: op / out");
+  NSK_REQUIRE(op != 0 || (a && w), "nsk_ew256 op 0 needs a, w");
+  NSK_REQUIRE(op != 1 || (a && b), "nsk_ew256 op 1 needs a, b");
+  NSK_REQUIRE(op != 2 || (b && (!c || d)), "nsk_ew256 op 2 needs b (and d with c)");
+  NSK_REQUIRE(op != 3 || (b && (!c || w)), "nsk_ew256 op 3 needs b (and w with c)");
+  NSK_REQUIRE(op != 4 || (w && s), "nsk_ew256 op 4 needs w, s");
+  if (n == 0) return 0;
+  ew256_kernel<<<grid_for(n * 64, 256), 256, 0, as_stream(stream)>>>(op, n, a, b, c, d, w, s, out);
+  return check_launch("ew256_kernel");
+}
+
+extern "C" int nsk_rowdot256(const float* X, const float* w, const float* b, int64_t n, float* out, void* stream) {
+  NSK_REQUIRE(X && w && out, "nsk_rowdot256: null pointer");
+  if (n == 0) return 0;
+  rowdot256_kernel<<<grid_for(n * 32, 256), 256, 0, as_stream(stream)>>>(X, w, b, n, out);
+  return check_launch("rowdot256_kernel");
+}
+
+extern "C" int nsk_colsum_w(const float* X, int ld, const float* v, int64_t M, int ncols, float* out, void* stream) {
+  NSK_REQUIRE(X && v && out && ld >= ncols && ncols > 0, "nsk_colsum_w: arguments");
+  if (M == 0) return 0;
+  const int cb = (ncols + 255) / 256;
+  int64_t rb = std::max<int64_t>(1, std::min<int64_t>((M + 255) / 256, (148 * 8) / cb));
+  const int64_t rows_per_block = (M + rb - 1) / rb;
+  rb = (M + rows_per_block - 1) / rows_per_block;
+  colsum_w_kernel<<<dim3(cb, (unsigned)rb), 256, 0, as_stream(stream)>>>(X, ld, v, M, ncols, rows_per_block, out);
+  return check_launch("colsum_w_kernel");
 }

@@ -452,3 +452,75 @@ def ddf_head_bwd(a5: Tensor, w_final: Tensor, that: Tensor, term_dist: Tensor, d
     _lib.check(_lib.load().nsk_ddf_head_bwd(_ptr(a5), _ptr(w_final), _ptr(that), _ptr(term_dist), _ptr(d_vis), _ptr(d_that_extra), c_int64(N), c_float(radius), _ptr(threshold),
                                             c_float(sigmoid_scale), _ptr(da5), _ptr(d_w_final), _ptr(d_b_final), _ptr(d_threshold), _stream(a5)), "nsk_ddf_head_bwd")
     return da5
+
+
+def colsum_w(X: Tensor, v: Tensor, out: Tensor) -> Tensor:
+    """out[c] += sum_r v[r] X[r, c]."""
+    X, ld = _mat("X", X)
+    v = _chk("v", v.reshape(-1), shape=(X.shape[0],))
+    out = _chk("out", out, shape=(X.shape[1],))
+    _lib.check(_lib.load().nsk_colsum_w(_ptr(X), c_int(ld), _ptr(v), c_int64(X.shape[0]), c_int(X.shape[1]), _ptr(out), _stream(X)), "nsk_colsum_w")
+    return out
+
+
+def sdf_inputs(x: Tensor, hash_table: Tensor, scalings: Tensor, log2_T: int, tail: Optional[Tensor] = None):
+    """x [n,3] -> (H0 [n,72], pos [n,3], J [n,9]); also fills tail[:, 0:40] (a column slice of the colour-net input) if given."""
+    n = x.shape[0]
+    x = _chk("x", x, shape=(n, 3))
+    L = scalings.numel()
+    hash_table, scalings = _chk("hash_table", hash_table, shape=(L << log2_T, 2)), _chk("scalings", scalings)
+    dev = x.device
+    H0 = torch.empty((n, 72), device=dev, dtype=torch.float32)
+    pos = torch.empty((n, 3), device=dev, dtype=torch.float32)
+    J = torch.empty((n, 9), device=dev, dtype=torch.float32)
+    ld_tail = 0
+    if tail is not None:
+        tail, ld_tail = _mat("tail", tail, rows=n, cols=40)
+    _lib.check(_lib.load().nsk_sdf_inputs_fwd(_ptr(x), c_int64(n), _ptr(hash_table), _ptr(scalings), c_int(L), c_int(log2_T), _ptr(H0), _ptr(tail), c_int(ld_tail),
+                                              _ptr(pos), _ptr(J), _stream(x)), "nsk_sdf_inputs_fwd")
+    return H0, pos, J
+
+
+def sdf_grad_assemble(x: Tensor, G: Tensor, gpos: Tensor, J: Tensor) -> Tensor:
+    n = x.shape[0]
+    x, G, gpos, J = _chk("x", x, shape=(n, 3)), _chk("G", G, shape=(n, 72)), _chk("gpos", gpos, shape=(n, 3)), _chk("J", J, shape=(n, 9))
+    grad = torch.empty((n, 3), device=x.device, dtype=torch.float32)
+    _lib.check(_lib.load().nsk_sdf_grad_assemble(_ptr(x), _ptr(G), _ptr(gpos), _ptr(J), c_int64(n), _ptr(grad), _stream(x)), "nsk_sdf_grad_assemble")
+    return grad
+
+
+def sdf_grad_assemble_bwd(x: Tensor, c: Tensor, J: Tensor):
+    """-> (dG [n,72] with the hash columns 39..70 left for the caller, cpos [n,3])."""
+    n = x.shape[0]
+    x, c, J = _chk("x", x, shape=(n, 3)), _chk("c", c, shape=(n, 3)), _chk("J", J, shape=(n, 9))
+    dG = torch.empty((n, 72), device=x.device, dtype=torch.float32)
+    cpos = torch.empty((n, 3), device=x.device, dtype=torch.float32)
+    _lib.check(_lib.load().nsk_sdf_grad_assemble_bwd(_ptr(x), _ptr(c), _ptr(J), c_int64(n), _ptr(dG), _ptr(cpos), _stream(x)), "nsk_sdf_grad_assemble_bwd")
+    return dG, cpos
+
+
+EW = {"sp_chain": 0, "mul_dsp": 1, "sp_bwd2": 2, "sp_bwd2_w": 3, "outer_add": 4}
+
+
+def ew256(op: str, n: int, a=None, b=None, c=None, d=None, w=None, s=None) -> Tensor:
+    """Pointwise family over [n,256] tensors (see include/neusky_b200.h, nsk_ew256)."""
+    ref = next(t for t in (a, b, c, d) if t is not None) if any(t is not None for t in (a, b, c, d)) else w
+    chk = lambda nm, t: None if t is None else _chk(nm, t, shape=(n, 256))
+    a, b, c, d = chk("a", a), chk("b", b), chk("c", c), chk("d", d)
+    if w is not None:
+        w = _chk("w", w.reshape(-1), shape=(256,))
+    if s is not None:
+        s = _chk("s", s.reshape(-1), shape=(n,))
+    out = torch.empty((n, 256), device=ref.device, dtype=torch.float32)
+    _lib.check(_lib.load().nsk_ew256(c_int(EW[op]), c_int64(n), _ptr(a), _ptr(b), _ptr(c), _ptr(d), _ptr(w), _ptr(s), _ptr(out), _stream(out)), "nsk_ew256")
+    return out
+
+
+def rowdot256(X: Tensor, w: Tensor, b: Optional[Tensor] = None) -> Tensor:
+    n = X.shape[0]
+    X, w = _chk("X", X, shape=(n, 256)), _chk("w", w.reshape(-1), shape=(256,))
+    if b is not None:
+        b = _chk("b", b.reshape(-1), shape=(1,))
+    out = torch.empty((n,), device=X.device, dtype=torch.float32)
+    _lib.check(_lib.load().nsk_rowdot256(_ptr(X), _ptr(w), _ptr(b), c_int64(n), _ptr(out), _stream(X)), "nsk_rowdot256")
+    return out

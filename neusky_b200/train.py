@@ -154,3 +154,159 @@ def ddf_visibility(cfg: DDFConfig, points: Tensor, dirs_sel: Tensor, threshold: 
     sphere points q [R*D',3], termination_dist [R*D']).  Differentiable w.r.t. threshold, the hash table, the final layer and
     every mapping / trunk weight (`mlp` in `ddf_param_list` order)."""
     return _DDFVisibility.apply(cfg, points, dirs_sel, threshold, table, w_final, b_final, *mlp)
+
+
+# =====================================================================================================================
+# SDF / albedo field (neusky/fields/sdf_albedo_field.py:211-269; nerfstudio SDFField.forward_geonetwork, SURVEY A.4)
+# =====================================================================================================================
+@dataclass(frozen=True)
+class SDFConfig:
+    scalings: Tensor
+    log2_T: int = 19
+    split_geo: int = 3       # the sdf feeds the NeuS logistic CDF scaled by inv_s: keep the geometry network fp32-accurate
+    split_colour: int = 1
+
+
+def sdf_param_list(p: Dict[str, Tensor]) -> List[Tensor]:
+    """weight_norm-folded weights in the positional order `sdf_field` takes: glin0..2 (W, b), clin0..2 (W, b).  The fold
+    W = g v / |v| (nn.utils.weight_norm, dim=0) is done here with torch ops so autograd carries the gradient back to
+    weight_g / weight_v; it touches 6 small matrices per step."""
+    out: List[Tensor] = []
+    for name in ("glin0", "glin1", "glin2", "clin0", "clin1", "clin2"):
+        if name + ".weight" in p:
+            W = p[name + ".weight"]
+        else:
+            v, g = p[name + ".weight_v"], p[name + ".weight_g"]
+            W = v * (g / v.norm(dim=1, keepdim=True))
+        out += [W, p[name + ".bias"]]
+    return out
+
+
+class _SDFField(torch.autograd.Function):
+    """sdf [n], grad_x sdf [n,3] (analytic reverse pass instead of torch.autograd.grad, sdf_albedo_field.py:235-238) and
+    albedo [n,3]; backward for cotangents on all three, including the double backward through the reverse pass that the
+    eikonal loss and the rendered normals need (the reference gets it from create_graph=True)."""
+
+    @staticmethod
+    def forward(ctx, cfg: SDFConfig, want_normals: bool, want_albedo: bool, x: Tensor, table: Tensor, W0, b0, W1, b1, W2, b2, C0, c0, C1, c1, C2, c2):
+        sg, sc = cfg.split_geo, cfg.split_colour
+        n, dev = x.shape[0], x.device
+        x = x.contiguous()
+        Hc = torch.empty((n, 296), device=dev, dtype=torch.float32) if want_albedo else None
+        H0, pos, J = ops.sdf_inputs(x, table, cfg.scalings, cfg.log2_T, tail=None if Hc is None else Hc[:, 256:296])
+        W0p = _pad_cols(W0)                                        # [256, 72]
+        A1 = ops.gemm_nt(H0, W0p, bias=b0, act="softplus100", split=sg)
+        A2 = ops.gemm_nt(A1, W1.contiguous(), bias=b1, act="softplus100", split=sg)
+        w2s = W2[0].contiguous()
+        sdf = ops.rowdot256(A2, w2s, b2[0:1])
+        empty = x.new_zeros(0)
+        Ca1 = Ca2 = alb = C0p = empty
+        if want_albedo:
+            ops.gemm_nt(A2, W2[1:].contiguous(), bias=b2[1:].contiguous(), out=Hc[:, :256], split=sg)
+            # colour-net input reordered to (geo | x | PE | 0) so the geometry feature lands 16-byte aligned; C0's columns follow
+            C0p = torch.cat([C0[:, 39:295], C0[:, :39], C0.new_zeros((C0.shape[0], 1))], dim=1).contiguous()
+            Ca1 = ops.gemm_nt(Hc, C0p, bias=c0, act="relu", split=sc)
+            Ca2 = ops.gemm_nt(Ca1, C1.contiguous(), bias=c1, act="relu", split=sc)
+            alb = ops.gemm_nt(Ca2, C2.contiguous(), bias=c2, act="sigmoid", split=sc)
+        G2 = P1 = D1 = G0 = grad = empty
+        if want_normals:
+            G2 = ops.ew256("sp_chain", n, a=A2, w=w2s)
+            P1 = ops.gemm_nt(G2, W1.t().contiguous(), split=sg)
+            D1 = ops.ew256("mul_dsp", n, a=P1, b=A1)
+            G0 = ops.gemm_nt(D1, W0p.t().contiguous(), split=sg)    # [n, 72] = d sdf / d H0
+            gpos = ops.hash_encode_grad_x(pos, table, cfg.scalings, cfg.log2_T, G0[:, 39:71].contiguous())
+            grad = ops.sdf_grad_assemble(x, G0, gpos, J)
+        ctx.cfg, ctx.want = cfg, (want_normals, want_albedo)
+        ctx.save_for_backward(x, table, pos, J, H0, A1, A2, W0p, W1, W2, C0p, C1, C2, Hc if Hc is not None else empty, Ca1, Ca2, alb, G2, P1, D1, G0)
+        return sdf, grad, alb
+
+    @staticmethod
+    def backward(ctx, g_sdf, g_grad, g_alb):
+        cfg: SDFConfig = ctx.cfg
+        sg, sc = cfg.split_geo, cfg.split_colour
+        want_normals, want_albedo = ctx.want
+        x, table, pos, J, H0, A1, A2, W0p, W1, W2, C0p, C1, C2, Hc, Ca1, Ca2, alb, G2, P1, D1, G0 = ctx.saved_tensors
+        n, dev = x.shape[0], x.device
+        zeros = lambda *s: torch.zeros(s, device=dev, dtype=torch.float32)
+        w2s = W2[0].contiguous()
+        need_table = ctx.needs_input_grad[4]
+        d_table = zeros(*table.shape) if need_table else None
+        dW0p, dW1, dW2 = zeros(*W0p.shape), zeros(*W1.shape), zeros(*W2.shape)
+        db0, db1, db2 = zeros(256), zeros(256), zeros(W2.shape[0])
+        dC0 = dc0 = dC1 = dc1 = dC2 = dc2 = None
+
+        # ---- colour network -> d geo feature -> d A2
+        dA2 = None
+        if want_albedo and g_alb is not None:
+            dz3 = zeros(n, 8)
+            dz3[:, :3] = g_alb * alb * (1.0 - alb)                                   # sigmoid'
+            dC2 = ops.gemm_tn(dz3[:, :3], Ca2, zeros(3, 256), split=sc)
+            dc2 = ops.colsum(dz3[:, :3], zeros(3))
+            C2t = zeros(256, 8)
+            C2t[:, :3] = C2.t()
+            dz2 = ops.gemm_nt(dz3, C2t, aux=Ca2, dact="relu", split=sc)              # [n,256]
+            dC1 = ops.gemm_tn(dz2, Ca1, zeros(256, 256), split=sc)
+            dc1 = ops.colsum(dz2, zeros(256))
+            dz1 = ops.gemm_nt(dz2, C1.t().contiguous(), aux=Ca1, dact="relu", split=sc)
+            dC0p = ops.gemm_tn(dz1, Hc, zeros(256, 296), split=sc)
+            dc0 = ops.colsum(dz1, zeros(256))
+            dC0 = torch.cat([dC0p[:, 256:295], dC0p[:, :256]], dim=1)                # back to the reference's (x | PE | geo) order
+            dgeo = ops.gemm_nt(dz1, C0p[:, :256].t().contiguous(), split=sc)         # d Hc[:, :256]
+            ops.gemm_tn(dgeo, A2, dW2[1:], split=sg)
+            ops.colsum(dgeo, db2[1:])
+            dA2 = ops.gemm_nt(dgeo, W2[1:].t().contiguous(), split=sg)
+        # ---- sdf head
+        if g_sdf is not None:
+            gs = g_sdf.contiguous()
+            dA2 = ops.ew256("outer_add", n, a=dA2, w=w2s, s=gs)
+            ops.colsum_w(A2, gs, dW2[0])
+            db2[0:1] += gs.sum().reshape(1)
+        # ---- double backward through the reverse pass (cotangent on grad_x sdf)
+        dD1 = dG2 = None
+        if want_normals and g_grad is not None:
+            dG0, cpos = ops.sdf_grad_assemble_bwd(x, g_grad.contiguous(), J)
+            d_g, d_t2 = ops.hash_encode_grad_x_bwd(pos, table, cfg.scalings, cfg.log2_T, G0[:, 39:71].contiguous(), cpos, True, need_table)
+            dG0[:, 39:71] = d_g
+            if need_table:
+                d_table = d_t2                                                        # freshly zero-filled by the op: reuse as the accumulator
+            dD1 = ops.gemm_nt(dG0, W0p, split=sg)                                     # [n,256] = dG0 . W0p^T
+            ops.gemm_tn(D1, dG0, dW0p, split=sg)
+            dP1 = ops.ew256("mul_dsp", n, a=dD1, b=A1)
+            dG2 = ops.gemm_nt(dP1, W1.contiguous(), split=sg)                         # dG2[i] = sum_j dP1[j] W1[i,j]
+            ops.gemm_tn(G2, dP1, dW1, split=sg)
+            ops.colsum(ops.ew256("mul_dsp", n, a=dG2, b=A2), dW2[0])                  # G2 = w2s * s'(A2)
+        # ---- geometry network
+        if dA2 is None and dG2 is None:
+            dZ2 = None
+        else:
+            dZ2 = ops.ew256("sp_bwd2_w", n, a=dA2, b=A2, c=dG2, w=w2s)
+        d_x = None
+        if dZ2 is not None:
+            ops.gemm_tn(dZ2, A1, dW1, split=sg)
+            ops.colsum(dZ2, db1)
+            dA1 = ops.gemm_nt(dZ2, W1.t().contiguous(), split=sg)
+            dZ1 = ops.ew256("sp_bwd2", n, a=dA1, b=A1, c=dD1, d=P1 if dD1 is not None else None)
+        elif dD1 is not None:
+            dZ1 = ops.ew256("sp_bwd2", n, a=None, b=A1, c=dD1, d=P1)
+        else:
+            dZ1 = None
+        if dZ1 is not None:
+            ops.gemm_tn(dZ1, H0, dW0p, split=sg)
+            ops.colsum(dZ1, db0)
+            if need_table or ctx.needs_input_grad[3]:
+                dH0 = ops.gemm_nt(dZ1, W0p.t().contiguous(), split=sg)                # [n,72]
+                dH0h = dH0[:, 39:71].contiguous()
+                if need_table:
+                    ops.hash_encode_bwd(pos, cfg.scalings, cfg.log2_T, dH0h, d_table)
+                if ctx.needs_input_grad[3]:
+                    # first-order input gradient (positions that depend on other networks, e.g. sdf_at_termination); the
+                    # second-order d(grad_x)/dx term is not propagated (the reference's sample positions are detached)
+                    d_x = ops.sdf_grad_assemble(x, dH0, ops.hash_encode_grad_x(pos, table, cfg.scalings, cfg.log2_T, dH0h), J)
+        dW0 = dW0p[:, :71]
+        return (None, None, None, d_x, d_table, dW0, db0, dW1, db1, dW2, db2, dC0, dc0, dC1, dc1, dC2, dc2)
+
+
+def sdf_field(cfg: SDFConfig, x: Tensor, table: Tensor, weights: Sequence[Tensor], want_normals: bool = True, want_albedo: bool = True) -> Tuple[Tensor, Tensor, Tensor]:
+    """x [n,3] -> (sdf [n], gradient [n,3], albedo [n,3]); `weights` in `sdf_param_list` order.  Differentiable w.r.t. the
+    hash table and all weights (twice through the gradient output), and to first order w.r.t. x."""
+    return _SDFField.apply(cfg, want_normals, want_albedo, x, table, *weights)
