@@ -102,6 +102,18 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint
       : "memory");
 }
 
+// LDGSTS with zero fill (src-size 0) for out-of-range elements; completion is observed through cp_async_arrive
+__device__ __forceinline__ void cp_async16(uint32_t dst, const float* src, bool valid) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(valid ? 16u : 0u) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const float* src, bool valid) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(valid ? 4u : 0u) : "memory");
+}
+// the mbarrier receives one arrival from this thread once all its prior cp.async have landed (.noinc: the arrival is part
+// of the barrier's expected count)
+__device__ __forceinline__ void cp_async_arrive(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
 
@@ -170,6 +182,49 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32_kernel(const Params p) {
         mbar_wait(EMPTY + 8 * stage, phase ^ 1);
         uint8_t* const sa = smem + stage * STAGE;
         uint8_t* const sb = sa + A_BYTES;
+        if (SPLIT == 1) {
+          // asynchronous path: LDGSTS straight into the operand layout, completion counted on the stage's mbarrier, so
+          // every stage of the ring is in flight at once (the register path below has one chunk in flight per thread)
+          const uint32_t sa32 = smem_u32(sa), sb32 = sa32 + A_BYTES;
+          if (!TN) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int wi = warp + 8 * j, row = (wi >> 1) * 8 + r8, kq = (wi & 1) * 4 + kq_lo;
+              const int64_t grow = it.a0 + row, k = r + kq * 4;
+              const bool ok = grow < p.M && k < it.r1;
+              cp_async16(sa32 + kq * A_LBO + row * 16, ok ? p.A + grow * p.lda + k : p.A, ok);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int wi = warp + 8 * j, row = (wi >> 1) * 8 + r8, kq = (wi & 1) * 4 + kq_lo;
+              const int64_t k = r + kq * 4;
+              const int n = it.b0 + row;
+              const bool ok = row < it.bn && n < p.N && k < it.r1;
+              cp_async16(sb32 + kq * B_LBO + row * 16, ok ? p.B + (int64_t)n * p.ldb + k : p.B, ok);
+            }
+          } else {
+            // lane = (m & 3) + 4 * (n & 7): a warp instruction reads 4 rows x one 32-byte sector and writes 128 contiguous bytes
+            const int ml = lane & 3, nl = lane >> 2;
+#pragma unroll 4
+            for (int j = 0; j < 16; ++j) {           // A operand: 128 n x 32 m = 16 n-groups x 8 m-quads = 128 warp items
+              const int wi = warp + 8 * j, n = (wi & 15) * 8 + nl, mq = wi >> 4;
+              const int64_t col = it.a0 + n, m = r + mq * 4 + ml;
+              const bool ok = col < p.N && m < it.r1;
+              cp_async4(sa32 + mq * A_LBO + n * 16 + ml * 4, ok ? p.A + m * p.lda + col : p.A, ok);
+            }
+#pragma unroll 4
+            for (int j = 0; j < 32; ++j) {           // B operand: 256 n x 32 m = 32 n-groups x 8 m-quads = 256 warp items
+              const int wi = warp + 8 * j, n = (wi & 31) * 8 + nl, mq = wi >> 5;
+              const int64_t m = r + mq * 4 + ml;
+              const int col = it.b0 + n;
+              const bool ok = n < it.bn && col < p.K && m < it.r1;
+              cp_async4(sb32 + mq * B_LBO + n * 16 + ml * 4, ok ? p.B + m * p.ldb + col : p.B, ok);
+            }
+          }
+          cp_async_arrive(FULL + 8 * stage);
+          if (++stage == ST) { stage = 0; phase ^= 1; }
+          continue;
+        }
         float4 va[4], vb[8];
         if (!TN) {
 #pragma unroll

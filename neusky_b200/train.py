@@ -310,3 +310,155 @@ def sdf_field(cfg: SDFConfig, x: Tensor, table: Tensor, weights: Sequence[Tensor
     """x [n,3] -> (sdf [n], gradient [n,3], albedo [n,3]); `weights` in `sdf_param_list` order.  Differentiable w.r.t. the
     hash table and all weights (twice through the gradient output), and to first order w.r.t. x."""
     return _SDFField.apply(cfg, want_normals, want_albedo, x, table, *weights)
+
+
+# =====================================================================================================================
+# One training iteration: NeuSkyFactoModel.get_outputs (training) + get_loss_dict   (neusky_model.py:553-1068)
+# =====================================================================================================================
+LOSS_COEFFICIENTS = {  # neusky/configs/neusky_config.py:132-146
+    "rgb_l1_loss": 1.0, "eikonal_loss": 0.1, "fg_mask_loss": 1.0, "sdf_level_set_visibility_loss": 1.0, "sky_pixel_loss": 1.0,
+    "hashgrid_density_loss": 1e-4, "ground_plane_loss": 0.1, "visibility_sigmoid_loss": 0.01,
+}
+
+
+def _monosdf_normal_loss(normal_pred: Tensor, normal_gt: Tensor) -> Tensor:
+    normal_gt = torch.nn.functional.normalize(normal_gt, p=2, dim=-1)
+    normal_pred = torch.nn.functional.normalize(normal_pred, p=2, dim=-1)
+    return torch.abs(normal_pred - normal_gt).sum(dim=-1).mean() + (1.0 - torch.sum(normal_pred * normal_gt, dim=-1)).mean()
+
+
+def _linear_to_srgb(c: Tensor) -> Tensor:
+    c = torch.where(c <= 0.0031308, 12.92 * c, 1.055 * torch.pow(torch.abs(c), 1 / 2.4) - 0.055)
+    return torch.clamp(c, 0.0, 1.0)
+
+
+def _neus_alpha(sdf, grad, ray_dirs, deltas, inv_s, rho: float):
+    """SDFField.get_alpha on a handful of grid samples (hashgrid_density_loss, neusky_model.py:675-734): torch glue."""
+    true_cos = (ray_dirs * grad).sum(-1, keepdim=True)
+    iter_cos = -(torch.relu(-true_cos * 0.5 + 0.5) * (1.0 - rho) + torch.relu(-true_cos) * rho)
+    nxt, prv = sdf + iter_cos * deltas * 0.5, sdf - iter_cos * deltas * 0.5
+    p, q = torch.sigmoid(prv * inv_s), torch.sigmoid(nxt * inv_s)
+    return ((p - q + 1e-5) / (p + 1e-5)).clip(0.0, 1.0)
+
+
+class NeuSkyTrainStep(torch.nn.Module):
+    """Host mirror of one `ns-train neusky` iteration for a ray batch: the reference's NeuSkyFactoModel.forward in training
+    mode plus get_loss_dict, with every heavy stage on the CUDA ops of this package.  Parameters carry the reference's
+    state-dict names (dots replaced by '__' for nn.Module registration) and its optimizer groups
+    (neusky_model.py:379-398): fields, ddf_field, illumination latents, visibility_sigmoid.
+
+    Not differentiated here: the RENI++ decoder (fixed_decoder=True in the reference, neusky_config.py:94) -- and, in this
+    round, the per-image latent codes feeding it (forward only through csrc/reni_decode.cu)."""
+
+    def __init__(self, sdf_params: Dict[str, Tensor], ddf_params: Dict[str, Tensor], reni_params: Dict[str, Tensor], num_cameras: int, device="cuda",
+                 log2_T: int = 19, num_levels: int = 16, num_samples: int = 48, ddf_radius: float = 1.0, sigmoid_scale: float = 25.0,
+                 split_geo: int = 3, split: int = 1, threshold_init: Optional[float] = None, only_upper_hemisphere: bool = True,
+                 lower_hemisphere_visibility: float = 1.0):
+        super().__init__()
+        from . import packing
+        from .init import hash_scalings
+
+        self.dev = torch.device(device)
+        self.S, self.radius, self.log2_T = num_samples, float(ddf_radius), log2_T
+        self.only_upper, self.lower_vis = only_upper_hemisphere, float(lower_hemisphere_visibility)
+        self.scalings = hash_scalings(num_levels).to(self.dev)
+        self._names: Dict[str, Dict[str, str]] = {"sdf": {}, "ddf": {}}
+        for grp, params in (("sdf", sdf_params), ("ddf", ddf_params)):
+            for k, v in params.items():
+                reg = f"{grp}__{k.replace('.', '__')}"
+                self.register_parameter(reg, torch.nn.Parameter(v.detach().to(self.dev, torch.float32).clone().contiguous()))
+                self._names[grp][k] = reg
+        self.latents = torch.nn.Parameter(torch.zeros(num_cameras, 100, 3, device=self.dev))      # neusky_model.py:261-269 (zero init)
+        self.scale = torch.nn.Parameter(torch.zeros(num_cameras, device=self.dev))
+        thr0 = 2.0 * self.radius if threshold_init is None else threshold_init                    # :234
+        self.visibility_threshold = torch.nn.Parameter(torch.tensor(float(thr0), device=self.dev))
+        self.reni_blob = packing.pack_reni({k: v.to(self.dev) for k, v in reni_params.items()})
+        self.sdf_cfg = SDFConfig(scalings=self.scalings, log2_T=log2_T, split_geo=split_geo, split_colour=split)
+        self.ddf_cfg = DDFConfig(scalings=self.scalings, log2_T=log2_T, radius=self.radius, sigmoid_scale=sigmoid_scale, split=split)
+        self.cos_anneal_ratio = 1.0
+        self.grid_resolution = 10                                                                  # neusky_config.py:127
+
+    # -- parameter access under the reference's names -------------------------------------------------------
+    def group(self, grp: str) -> Dict[str, Tensor]:
+        return {k: getattr(self, reg) for k, reg in self._names[grp].items()}
+
+    def get_param_groups(self) -> Dict[str, List[torch.nn.Parameter]]:
+        return {"fields": list(self.group("sdf").values()), "ddf_field": list(self.group("ddf").values()),
+                "illumination_field": [self.latents, self.scale], "visibility_sigmoid": [self.visibility_threshold]}
+
+    def set_directions(self, dirs: Tensor) -> None:
+        """Illumination directions of this iteration [D,3] (IcosahedronSampler with its random rotation, neusky_model.py:452-456)."""
+        self.dirs = dirs.to(self.dev, torch.float32).contiguous()
+        m = (self.dirs[:, 2] > 0) if self.only_upper else torch.ones(self.dirs.shape[0], dtype=torch.bool, device=self.dev)
+        self.mask_u8 = m.to(torch.uint8).contiguous()
+        self.dirs_sel = self.dirs[m].contiguous()
+        self.sel_index = torch.where(m, torch.cumsum(m.to(torch.int32), 0, dtype=torch.int32) - 1, torch.full_like(m, -1, dtype=torch.int32)).to(torch.int32).contiguous()
+
+    # -- forward ---------------------------------------------------------------------------------------------
+    def forward(self, batch: Dict[str, Tensor], grid_positions: Optional[Tensor] = None, grid_dirs: Optional[Tensor] = None) -> Tuple[Tensor, Dict[str, Tensor], Dict[str, Tensor]]:
+        from . import autograd as nba
+        from .render import sphere_collider, uniform_samples
+
+        o, d, dn = batch["origins"], batch["directions"], batch["dnorm"]
+        cam = batch["cam"].to(torch.int32).contiguous()
+        R, S = o.shape[0], self.S
+        sdf_p, ddf_p = self.group("sdf"), self.group("ddf")
+        sdf_w = sdf_param_list(sdf_p)
+        table = sdf_p["encoding.hash_table"]
+
+        near, far = sphere_collider(o, d, radius=1.0, training=True)
+        starts, ends = uniform_samples(near, far, S)                                   # [R,S,1]
+        x = (o[:, None, :] + d[:, None, :] * starts).reshape(-1, 3)
+        sdf, grad, alb = sdf_field(self.sdf_cfg, x, table, sdf_w)
+        inv_s = torch.exp(sdf_p["deviation_network.variance"] * 10.0).clip(1e-6, 1e6)
+        starts2, ends2 = starts.reshape(R, S), ends.reshape(R, S)
+        weights, wa, normals, acc, p2p_raw, normal, _albedo, _bgT = nba.neus_composite(
+            sdf.reshape(R, S), grad.reshape(R, S, 3), alb.reshape(R, S, 3), inv_s, d, starts2, ends2, ends2 - starts2, dn.reshape(R), self.cos_anneal_ratio)
+        steps = (starts2 + ends2) * 0.5
+        p2p = torch.clip(p2p_raw.detach(), steps.min(), steps.max())                   # DepthRenderer clip; detached (stop-gradients "depth")
+        pts = ops.surface_points(o, d, p2p, self.radius)
+
+        with torch.no_grad():
+            radiance = ops.reni_radiance_table(self.dirs, self.latents, self.scale, self.reni_blob)      # [K,D,3]
+            bg_all = ops.reni_radiance_table(d, self.latents, self.scale, self.reni_blob)                # [K,R,3]
+            bg = bg_all[cam.long(), torch.arange(R, device=self.dev)].contiguous()
+
+        vis, that, q, _term = ddf_visibility(self.ddf_cfg, pts, self.dirs_sel, self.visibility_threshold, ddf_p["position_encoding.hash_table"],
+                                             ddf_p["ddf.final_layer.weight"], ddf_p["ddf.final_layer.bias"], ddf_param_list(ddf_p))
+        Dp = self.dirs_sel.shape[0]
+        term_pts = q + (-self.dirs_sel)[None].expand(R, Dp, 3).reshape(-1, 3) * that[:, None]          # ddf_model.py:243
+        sdf_term, _, _ = sdf_field(self.sdf_cfg, term_pts, table, sdf_w, want_normals=False, want_albedo=False)
+
+        inv_count, _ = ops.lambert_prep(normals.detach(), wa.detach(), self.dirs, self.mask_u8, radiance, cam, self.lower_vis)
+        rgb_lin = nba.lambert_shade(normals, wa, radiance, vis, inv_count, self.dirs, self.sel_index, cam, self.lower_vis)
+        rgb = nba.shade_finalize(rgb_lin, bg, acc)
+        out = {"rgb": rgb, "eik_grad": grad.reshape(R, S, 3), "weights": weights, "normal": normal, "accumulation": acc, "hdr_background_colours": bg,
+               "p2p_dist": p2p, "sdf_at_termination": sdf_term, "visibility_sel": vis, "expected_termination_dist": that}
+        if grid_positions is not None:
+            gs, gg, _ = sdf_field(self.sdf_cfg, grid_positions, table, sdf_w, want_normals=True, want_albedo=False)
+            gap = 2.0 / self.grid_resolution
+            out["grid_density"] = _neus_alpha(gs[:, None], gg, grid_dirs, torch.full_like(gs[:, None], gap), inv_s, self.cos_anneal_ratio)
+        losses = self.get_loss_dict(out, batch)
+        return sum(losses.values()), losses, out
+
+    def get_loss_dict(self, out: Dict[str, Tensor], batch: Dict[str, Tensor]) -> Dict[str, Tensor]:
+        """neusky_model.py:935-1031, training branch; per-ray reductions on [R, .] tensors (torch)."""
+        image, fg, ground, sky = batch["image"], batch["fg"], batch["ground"], batch["sky"]
+        keep = (1.0 - sky.to(image.dtype))[:, None]
+        L: Dict[str, Tensor] = {}
+        L["rgb_l1_loss"] = torch.nn.functional.l1_loss(image * keep, out["rgb"] * keep)
+        L["eikonal_loss"] = ((out["eik_grad"].norm(2, dim=-1) - 1) ** 2).mean()
+        ws = out["accumulation"].clip(1e-3, 1.0 - 1e-3)
+        L["fg_mask_loss"] = torch.nn.functional.binary_cross_entropy(ws, fg.to(ws.dtype))
+        gm = ground.to(image.dtype)[:, None]
+        up = torch.tensor([0.0, 0.0, 1.0], device=image.device).expand_as(out["normal"])
+        L["ground_plane_loss"] = _monosdf_normal_loss(out["normal"] * gm, up * gm)
+        srgb_bg = _linear_to_srgb(out["hdr_background_colours"])
+        m = sky.to(image.dtype)[:, None].expand_as(srgb_bg)
+        a, b = srgb_bg * m, image * m
+        L["sky_pixel_loss"] = torch.nn.functional.mse_loss(a, b) + 0.1 * (1 - torch.nn.functional.cosine_similarity(a, b, dim=1, eps=1e-20).mean())
+        L["visibility_sigmoid_loss"] = (self.visibility_threshold - 0.1) ** 2
+        L["sdf_level_set_visibility_loss"] = (out["sdf_at_termination"] ** 2).mean()
+        if "grid_density" in out:
+            L["hashgrid_density_loss"] = out["grid_density"].abs().mean()
+        return {k: v * LOSS_COEFFICIENTS[k] for k, v in L.items()}

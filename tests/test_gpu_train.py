@@ -141,7 +141,7 @@ def _ddf_case(R, Dn, seed, log2_T=14):
     return p, pts, dirs
 
 
-@pytest.mark.parametrize("split,tol_fwd,tol_grad", [(3, 2e-4, 2e-3), (1, 2e-2, 8e-2)])
+@pytest.mark.parametrize("split,tol_fwd,tol_grad", [(3, 2e-4, 5e-3), (1, 2e-2, 8e-2)])
 def test_ddf_visibility_forward_backward_vs_oracle_autograd(dev, split, tol_fwd, tol_grad):
     """vis / expected termination distance and the gradients of every DDF parameter, the hash table and the threshold
     against fp64 autograd through oracle.compute_visibility (neusky_model.py:1685-1740 + ddf_model.py + film_siren.py)."""
@@ -258,3 +258,70 @@ def test_sdf_field_geo_only_input_gradient(dev):
     assert float((sdf.detach().cpu().double() - sdf_r.detach()).abs().max()) <= 1e-4
     assert _rel(xc.grad, xr.grad) <= 2e-3
     assert _rel(grad.detach() * torch.sign(sdf.detach())[:, None], xr.grad) <= 2e-3
+
+
+def _train_case(R, K, seed):
+    g = torch.Generator().manual_seed(seed)
+    o = torch.nn.functional.normalize(torch.randn(R, 3, generator=g), dim=-1) * (0.5 + 0.3 * torch.rand(R, 1, generator=g))
+    d = torch.nn.functional.normalize(-o + 0.12 * torch.randn(R, 3, generator=g), dim=-1)     # towards the geometric-init sphere (radius ~0.1)
+    batch = {"origins": o, "directions": d, "dnorm": 1.0 + 0.2 * torch.rand(R, 1, generator=g), "cam": torch.randint(0, K, (R,), generator=g),
+             "image": torch.rand(R, 3, generator=g), "fg": (torch.rand(R, generator=g) > 0.3).float(), "ground": (torch.rand(R, generator=g) > 0.7).float(),
+             "sky": (torch.rand(R, generator=g) > 0.8).float()}
+    return batch
+
+
+@pytest.mark.parametrize("split,tol_loss,tol_grad", [(3, 2e-4, 1e-2), (1, 2e-2, 2.5e-1)])
+def test_train_step_losses_and_gradients_vs_oracle_autograd(dev, split, tol_loss, tol_grad):
+    """One training iteration (forward + every loss of neusky_model.py:935-1031 that the path carries + backward into the SDF
+    field, its hash table, the DDF, its hash table, the variance and the visibility threshold) against fp64 autograd through
+    oracle/train_oracle.py.  split=1 (single-pass tf32) is a sanity bound: the comparison is dominated by tf32 rounding."""
+    from neusky_b200 import train as T
+    from oracle import neusky_oracle as O
+    from oracle import train_oracle as TO
+
+    log2_T, R, S, K = 14, 16, 12, 3
+    g = torch.Generator().manual_seed(41)
+    sdf_p = nb_init.init_sdf_params(3, log2_T=log2_T)
+    sdf_p["encoding.hash_table"] = (torch.rand(sdf_p["encoding.hash_table"].shape, generator=g) * 2 - 1) * 0.05
+    for l in range(3):
+        sdf_p[f"glin{l}.weight_v"] = sdf_p[f"glin{l}.weight_v"] + 0.02 * torch.randn(sdf_p[f"glin{l}.weight_v"].shape, generator=g)
+    sdf_p["deviation_network.variance"] = torch.tensor(0.25)
+    ddf_p = nb_init.init_ddf_params(5, final_gain=8.0, log2_T=log2_T, table_scale=0.1)
+    reni_p = nb_init.init_reni_params(8)
+    latents, scales = torch.randn(K, 100, 3, generator=g), 0.1 * torch.randn(K, generator=g)
+    dirs = O.icosphere_directions(100)
+    batch = _train_case(R, K, 43)
+    gp = (torch.rand(27, 3, generator=g) * 2 - 1) * 0.9
+    gd = torch.nn.functional.normalize(torch.randn(27, 3, generator=g), dim=-1)
+    thr0 = 0.4
+
+    # ---- oracle, fp64 autograd
+    dbl = lambda p: {k: v.double().requires_grad_(True) for k, v in p.items()}
+    sp, dp = dbl(sdf_p), dbl(ddf_p)
+    rp = {k: v.double() for k, v in reni_p.items()}
+    thr_ref = torch.tensor(thr0, dtype=torch.float64, requires_grad=True)
+    b64 = {k: (v.double() if v.is_floating_point() else v) for k, v in batch.items()}
+    out_r = TO.training_forward(b64, sp, dp, rp, latents.double(), scales.double(), thr_ref, dirs.double(), S, log2_T, grid_positions=gp.double(), grid_dirs=gd.double(), grid_gap=0.2)
+    L_r = TO.training_losses(out_r, b64, thr_ref)
+    sum(L_r.values()).backward()
+
+    # ---- CUDA
+    step = T.NeuSkyTrainStep(sdf_p, ddf_p, reni_p, num_cameras=K, device=dev, log2_T=log2_T, num_samples=S, split_geo=split, split=split, threshold_init=thr0)
+    with torch.no_grad():
+        step.latents.copy_(latents.to(dev))
+        step.scale.copy_(scales.to(dev))
+    step.set_directions(dirs)
+    bc = {k: v.to(dev) for k, v in batch.items()}
+    loss, L, out = step(bc, grid_positions=gp.to(dev), grid_dirs=gd.to(dev))
+    loss.backward()
+    for k in L_r:
+        assert abs(float(L[k]) - float(L_r[k])) <= tol_loss * max(1.0, abs(float(L_r[k]))), f"{k}: {float(L[k])} vs {float(L_r[k])}"
+    assert float((out["rgb"].detach().cpu().double() - out_r["rgb"].detach()).abs().max()) <= tol_loss * 50
+    worst = {}
+    for grp, ref in (("sdf", sp), ("ddf", dp)):
+        for k, v in step.group(grp).items():
+            assert v.grad is not None, k
+            worst[f"{grp}.{k}"] = _rel(v.grad, ref[k].grad)
+    worst["threshold"] = abs(float(step.visibility_threshold.grad) - float(thr_ref.grad)) / (abs(float(thr_ref.grad)) + 1e-12)
+    bad = {k: v for k, v in worst.items() if not v <= tol_grad}
+    assert not bad, f"split={split}: gradient mismatch {bad} (all: {worst})"
