@@ -263,6 +263,129 @@ def eval_arm(args):
         dist.barrier(); dist.destroy_process_group()
 
 
+
+# ------------------------------------------------------------------------------------------ training-step arm (configs[3])
+def _train_batch(R: int, K: int, seed: int):
+    """R rays sampled from K synthetic cameras on a ring of radius 0.9 around the origin (z-up,
+    height 0.25), each looking at a random point of the ball |x| < 0.5; random target colours and masks."""
+    g = torch.Generator().manual_seed(seed)
+    cam = torch.randint(0, K, (R,), generator=g)
+    ang = cam.to(torch.float32) * (2 * 3.141592653589793 / K)
+    o = torch.stack([0.9 * torch.cos(ang), 0.9 * torch.sin(ang), torch.full((R,), 0.25)], 1)
+    tgt = torch.nn.functional.normalize(torch.randn(R, 3, generator=g), dim=-1) * torch.rand(R, 1, generator=g) ** (1 / 3) * 0.5
+    d = torch.nn.functional.normalize(tgt - o, dim=-1)
+    return {"origins": o.contiguous(), "directions": d.contiguous(), "dnorm": torch.ones(R, 1), "cam": cam.to(torch.int32),
+            "image": torch.rand(R, 3, generator=g), "fg": (torch.rand(R, generator=g) > 0.3).float(), "ground": (torch.rand(R, generator=g) > 0.7).float(),
+            "sky": (torch.rand(R, generator=g) > 0.8).float()}
+
+
+def train_arm(args):
+    """One `ns-train neusky` iteration per step at R = 1024 rays per GPU (README default): forward (uniform S = 48 samples,
+    SDF/albedo field with analytic normals, NeuS compositing, RENI++ radiance, DDF visibility on the R x D' pairs of a randomly
+    rotated 642-direction icosphere, sdf_at_termination, Lambertian shading), the reference's losses, backward into every
+    parameter group, bucketed gradient all-reduce (NCCL) and a fused Adam step.  Weak scaling: every rank has its own R rays."""
+    rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    import numpy as np
+    from scipy.spatial.transform import Rotation
+    from neusky_b200 import _lib, init as nb_init, samplers
+    from neusky_b200.parallel import GradBucketReducer
+    from neusky_b200.train import NeuSkyTrainStep
+
+    _lib.load()
+    R, K, S = args.rays, 32, args.train_samples
+    sdf_p = nb_init.init_sdf_params(SEED_W + 2, bias=0.45)
+    sdf_p["deviation_network.variance"] = torch.tensor(0.3)
+    step_mod = NeuSkyTrainStep(sdf_p, nb_init.init_ddf_params(SEED_W), nb_init.init_reni_params(SEED_W + 1), num_cameras=K, device=dev,
+                               num_samples=S, split_geo=3, split=args.split, threshold_init=0.4)
+    with torch.no_grad():
+        step_mod.latents.copy_(torch.randn(K, 100, 3, generator=torch.Generator().manual_seed(3)).to(dev))
+    params = [p for p in step_mod.parameters() if p.requires_grad]
+    red = GradBucketReducer(params)
+    opt = torch.optim.Adam(params, lr=1e-4, fused=True)
+    base_dirs = samplers.IcosahedronSampler(512)().frustums.directions.to(torch.float64).numpy()
+    rots = Rotation.random(args.steps + args.warmup + 8, random_state=np.random.RandomState(11 + rank)).as_matrix()
+    batch_h = {k: v.pin_memory() for k, v in _train_batch(R, K, 100 + rank).items()}
+    gres = 10
+    lin = torch.linspace(-1.0, 1.0, gres)
+    gpos0 = torch.stack(torch.meshgrid(lin, lin, lin, indexing="ij"), -1).reshape(-1, 3)
+    gg = torch.Generator().manual_seed(200 + rank)
+    it = {"i": 0}
+    loss_h = torch.zeros(1).pin_memory()
+    Dp_seen = []
+
+    def one_step():
+        i = it["i"]; it["i"] += 1
+        dirs = torch.from_numpy((base_dirs @ rots[i % len(rots)]).astype(np.float32))          # IcosahedronSampler random rotation (host, :339-341)
+        step_mod.set_directions(dirs)
+        Dp_seen.append(int(step_mod.dirs_sel.shape[0]))
+        gp = (gpos0 + (torch.rand(gpos0.shape, generator=gg) - 0.5) * (2.0 / gres)).to(dev, non_blocking=True)
+        gd = torch.nn.functional.normalize(torch.randn(gpos0.shape, generator=gg), dim=-1).to(dev, non_blocking=True)
+        b = {k: v.to(dev, non_blocking=True) for k, v in batch_h.items()}                       # h2d of the ray batch inside the step
+        red.zero_grad()
+        loss, _, _ = step_mod(b, grid_positions=gp, grid_dirs=gd)
+        loss.backward()
+        red.finish()
+        opt.step()
+        loss_h.copy_(loss.detach().reshape(1), non_blocking=True)                               # d2h of the step's result
+
+    for _ in range(args.warmup):
+        one_step()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    Dp_seen.clear()
+    l0 = _lib.launches
+    wall0 = time.perf_counter()
+    evs = []
+    for _ in range(args.steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); one_step(); e1.record()
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    t = sum(a.elapsed_time(b) for a, b in evs) / 1e3
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop() if sampler else None
+    launches = _lib.launches - l0
+    if dist is not None:
+        tt = torch.tensor([t, wall], device=dev, dtype=torch.float64); dist.all_reduce(tt, op=dist.ReduceOp.MAX); t, wall = (float(x) for x in tt)
+    if rank == 0:
+        peaks = _peaks()
+        Dp = sum(Dp_seen) / max(1, len(Dp_seen))
+        # algorithmic FLOP of one iteration, forward figures of SURVEY 8(d) x 3 (forward + two backward contractions):
+        flop = 3.0 * (R * Dp * (FLOP_PER_PAIR + 2 * 149_504) + R * S * 881_664 + gres**3 * 2 * 2 * 149_504)
+        h2d = sum(v.numel() * v.element_size() for v in batch_h.values()) + 2 * gpos0.numel() * 4 + 642 * 3 * 4
+        line = {"metric": "training rays/s (forward + losses + backward + gradient all-reduce + Adam)", "value": world * R * args.steps / t, "unit": UNIT,
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "wall_ms_per_step": 1e3 * wall / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": f"tf32 operands (3xTF32 on the SDF geometry network, split={args.split} elsewhere), fp32 accumulate / activations / gradients", "data": "synthetic",
+                "config": {"workload": f"BASELINE.json configs[3]: training step, {R} rays/GPU from {K} cameras, S={S} uniform samples/ray, 642-direction icosphere with a random "
+                                       f"rotation per step (mean D'={Dp:.0f} through the DDF), sdf_at_termination branch, hashgrid density loss on {gres**3} grid points, "
+                                       f"hash tables 2 x 2^19 x 16 x 2 fp32", "rays_per_gpu": R, "samples_per_ray": S,
+                           "parallelism": f"data-parallel x{world}, bucketed gradient all-reduce ({red.bytes_per_step / 2**20:.0f} MiB/step, {len(red.buckets)} buckets)"
+                                          + (" over NCCL" if world > 1 else " (single rank: no collective)"),
+                           "l2": "per-step activations (~15 GB) exceed L2"},
+                "e2e": {"value": world * R * args.steps / wall, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                        "api": "neusky_b200.train.NeuSkyTrainStep + parallel.GradBucketReducer; e2e value is wall-clock over the timed steps (host work, h2d of the ray batch and d2h of the loss included); `value` is CUDA-event time of the same steps"},
+                "gpu_launches": launches, "algorithmic_tflops": flop * args.steps / t / 1e12, "tf32_peak_tflops_sustained": peaks["tf_sustained"] / 2,
+                "clocks": clocks, "loss": float(loss_h.item())}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier(); dist.destroy_process_group()
+
+
 # ------------------------------------------------------------------------------------------ GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -272,18 +395,24 @@ def main():
     ap.add_argument("--points", type=int, default=1_000_000)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="shade", choices=["shade", "eval"],
-                    help="shade = BASELINE.json configs[1] (the headline line); eval = configs[2], a supplementary full-image render line")
+    ap.add_argument("--workload", default="shade", choices=["shade", "eval", "train"],
+                    help="shade = BASELINE.json configs[1] (the headline line); eval = configs[2] full-image render, train = configs[3] training step (supplementary lines)")
     ap.add_argument("--height", type=int, default=720)
     ap.add_argument("--width", type=int, default=1280)
     ap.add_argument("--samples", type=int, default=128)
     ap.add_argument("--tile", type=int, default=16384)
+    ap.add_argument("--rays", type=int, default=1024, help="train: rays per GPU")
+    ap.add_argument("--train-samples", type=int, default=48)
+    ap.add_argument("--split", type=int, default=3, choices=[1, 3], help="train: 1 = tf32 GEMMs, 3 = 3xTF32 (fp32-accurate)")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)
         return
     if args.workload == "eval":
         eval_arm(args)
+        return
+    if args.workload == "train":
+        train_arm(args)
         return
 
     rank = int(os.environ.get("RANK", "0"))

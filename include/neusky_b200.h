@@ -131,6 +131,23 @@ int64_t nsk_reni_weights_floats(int latent_dim, int hidden, int num_layers);
 int nsk_reni_decode_fwd(const float* dirs, int64_t D, const float* latents, const float* scale, int64_t K,
                         const float* rotation, const float* weights, int latent_dim, int hidden, int num_layers,
                         int log_domain, float* workspace, float* out, void* stream);
+/* Per-row variant: direction n is decoded with latent code row_cam[n] (int32) -> out [N,3]; the background radiance along
+ * each camera ray of a mixed-camera batch (neusky/models/neusky_model.py:535-549).  Same workspace as above. */
+int nsk_reni_decode_rows_fwd(const float* dirs, const int* row_cam, int64_t N, const float* latents, const float* scale, int64_t K,
+                             const float* rotation, const float* weights, int latent_dim, int hidden, int num_layers,
+                             int log_domain, float* workspace, float* out, void* stream);
+/* Backward of both variants w.r.t. the latent codes and scales, decoder frozen: what torch autograd computes for the
+ * per-image `illumination_latents` / `scale` parameters (neusky_model.py:261-269, 488-504) under
+ * RENIField.hold_decoder_fixed (reni_illumination_field.py:157-196).  row_cam NULL = table mode (out, g_out [K,D,3]), else
+ * per-row mode (out, g_out [D,3]).  out = the forward result; weights_bwd = the [out][in] copy of the linear weights
+ * (nsk_reni_bwd_weights_floats / neusky_b200.packing.pack_reni_bwd); workspace nsk_reni_bwd_workspace_floats floats;
+ * d_latents [K,Ld,3] and d_scale [K] are ACCUMULATED into (d_scale NULL iff scale NULL). */
+int64_t nsk_reni_bwd_weights_floats(int latent_dim, int hidden, int num_layers);
+int64_t nsk_reni_bwd_workspace_floats(int64_t K, int latent_dim, int hidden, int num_layers);
+int nsk_reni_decode_bwd(const float* dirs, const int* row_cam, int64_t D, const float* latents, const float* scale, int64_t K,
+                        const float* rotation, const float* weights, const float* weights_bwd, int latent_dim, int hidden,
+                        int num_layers, int log_domain, const float* out, const float* g_out, float* workspace,
+                        float* d_latents, float* d_scale, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Lambertian pre-pass and finalisation.

@@ -5,6 +5,7 @@ north_star for the training path).  Forward and backward both run the CUDA kerne
   neus_composite(sdf, grad, albedo, inv_s, ...)   d/d sdf, grad, albedo, inv_s  (nsk_neus_composite_bwd)
   lambert_shade(normals, wa, radiance, vis, ...)   d/d normals, wa, radiance, visibility  (nsk_lambert_relight_bwd)
   shade_finalize(rgb_lin, bg, acc)                 d/d rgb_lin, bg, acc  (nsk_shade_finalize_bwd)
+  reni_radiance(dirs, latents, scale, ...)         d/d latents, scale with the decoder frozen  (nsk_reni_decode_bwd)
 """
 from __future__ import annotations
 
@@ -120,3 +121,33 @@ class _ShadeFinalize(torch.autograd.Function):
 
 def shade_finalize(rgb_lin, bg, acc) -> Tensor:
     return _ShadeFinalize.apply(rgb_lin, bg, acc)
+
+
+class _ReniRadiance(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, dirs, row_cam, latents, scale, packed, packed_bwd, rotation, log_domain: bool):
+        if row_cam is None:
+            out = ops.reni_radiance_table(dirs, latents, scale, packed, rotation=rotation, log_domain=log_domain)
+        else:
+            out = ops.reni_radiance_rows(dirs, row_cam, latents, scale, packed, rotation=rotation, log_domain=log_domain)
+        e = torch.empty(0)
+        ctx.save_for_backward(dirs, row_cam if row_cam is not None else e, latents, scale if scale is not None else e, packed, packed_bwd,
+                              rotation if rotation is not None else e, out)
+        ctx.flags = (row_cam is not None, scale is not None, rotation is not None, log_domain)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        dirs, row_cam, latents, scale, packed, packed_bwd, rotation, out = ctx.saved_tensors
+        has_cam, has_scale, has_rot, log_domain = ctx.flags
+        d_lat = torch.zeros_like(latents)
+        d_scale = torch.zeros_like(scale) if has_scale else None
+        ops.reni_decode_bwd(dirs, row_cam if has_cam else None, latents, scale if has_scale else None, packed, packed_bwd, out, g.contiguous(), d_lat, d_scale,
+                            rotation=rotation if has_rot else None, log_domain=log_domain)
+        return None, None, d_lat, d_scale, None, None, None, None
+
+
+def reni_radiance(dirs: Tensor, latents: Tensor, scale, packed: Tensor, packed_bwd: Tensor, row_cam=None, rotation=None, log_domain: bool = True) -> Tensor:
+    """RENI++ HDR radiance, differentiable w.r.t. the latent codes and scales (decoder frozen, as under the reference's
+    hold_decoder_fixed): [K,D,3] for every (code, direction) pair, or [N,3] with one code per direction when row_cam [N] is given."""
+    return _ReniRadiance.apply(dirs, row_cam, latents, scale, packed, packed_bwd, rotation, log_domain)

@@ -9,50 +9,9 @@
 // computes those 6 x [H] vectors once per latent code; kernel 2 runs the per-(code, direction)
 // residual MLP.  The reference instead expands the latent to [K*D,100,3] and recomputes the
 // per-code part for every row.  fp32 throughout (the table is K*D*0.5 MFLOP: negligible work).
-#include "nsk_common.cuh"
+#include "reni_common.cuh"
 
 namespace nsk {
-
-struct ReniLayout {
-  int L, H, NL, d_in, c_in;
-  int64_t vn, res_wt, res_b, layer0, layer_stride, fc_w, fc_b, total;
-  // per-layer offsets relative to layer start
-  int64_t o_val_wt, o_val_b, o_out_wt, o_out_b, o_n1w, o_n1b, o_f0_wt, o_f0_b, o_f2_wt, o_f2_b, o_n2w, o_n2b;
-};
-
-__host__ __device__ inline ReniLayout reni_layout(int L, int H, int NL) {
-  ReniLayout y;
-  y.L = L; y.H = H; y.NL = NL;
-  y.d_in = (L + 2) * 5;
-  y.c_in = L * 3;
-  int64_t o = 0;
-  y.vn = o; o += 16;  // [proj(1), lin(2), W(4), U(4), pad]
-  y.res_wt = o; o += (int64_t)y.d_in * H;
-  y.res_b = o; o += H;
-  y.layer0 = o;
-  int64_t q = 0;
-  y.o_val_wt = q; q += (int64_t)y.c_in * H;
-  y.o_val_b = q; q += H;
-  y.o_out_wt = q; q += (int64_t)H * H;
-  y.o_out_b = q; q += H;
-  y.o_n1w = q; q += H;
-  y.o_n1b = q; q += H;
-  y.o_f0_wt = q; q += (int64_t)H * H;
-  y.o_f0_b = q; q += H;
-  y.o_f2_wt = q; q += (int64_t)H * H;
-  y.o_f2_b = q; q += H;
-  y.o_n2w = q; q += H;
-  y.o_n2b = q; q += H;
-  y.layer_stride = q;
-  o += q * NL;
-  y.fc_w = o; o += 3 * (int64_t)H;
-  y.fc_b = o; o += 4;
-  y.total = o;
-  return y;
-}
-
-constexpr int RENI_H = 128;
-constexpr int RENI_MAX_L = 128;
 
 // ---- kernel 1: per latent code ----------------------------------------------------------------
 __global__ void __launch_bounds__(RENI_H)
@@ -73,28 +32,10 @@ reni_prep_kernel(const float* __restrict__ latents, const float* __restrict__ ro
     }
     zxy_out[((int64_t)k * y.L + l) * 2] = z0;
     zxy_out[((int64_t)k * y.L + l) * 2 + 1] = z1;
-    // vn_proj_in: VNLinear(1,1): x[c] = w * z[c]           (vn_layers.py:191-216)
-    const float x0 = vn[0] * z0, x1 = vn[0] * z1;
-    // VNInvariant.mlp[0]: VNLinear(1,2): yv[o][c] = w0[o] * x[c]
-    float yv[2][2] = {{vn[1] * x0, vn[1] * x1}, {vn[2] * x0, vn[2] * x1}};
-    // VNReLU(2): q = W y, kk = U y (over the feature index), per coordinate c   (vn_layers.py:218-246)
-    float q[2][2], kk[2][2];
-    for (int o = 0; o < 2; ++o)
-      for (int c = 0; c < 2; ++c) {
-        q[o][c] = vn[3 + o * 2 + 0] * yv[0][c] + vn[3 + o * 2 + 1] * yv[1][c];
-        kk[o][c] = vn[7 + o * 2 + 0] * yv[0][c] + vn[7 + o * 2 + 1] * yv[1][c];
-      }
-    float outv[2][2];
-    for (int o = 0; o < 2; ++o) {
-      const float qk = q[o][0] * kk[o][0] + q[o][1] * kk[o][1];
-      const float kn = sqrtf(fmaxf(kk[o][0] * kk[o][0] + kk[o][1] * kk[o][1], 1e-6f));
-      const float proj = q[o][0] * (kk[o][0] / kn) + q[o][1] * (kk[o][1] / kn);
-      for (int c = 0; c < 2; ++c) outv[o][c] = (qk >= 0.f) ? q[o][c] : (q[o][c] - proj * kk[o][c]);
-    }
-    // rearrange '... d e -> ... e d' then einsum('b n d i, b n i o -> b n o') with d == 1:
-    // inv[o] = sum_i x[i] * outv[o][i]                                  (vn_layers.py:404-419)
-    cond[l * 3 + 0] = x0 * outv[0][0] + x1 * outv[0][1];
-    cond[l * 3 + 1] = x0 * outv[1][0] + x1 * outv[1][1];
+    float c0, c1;
+    vn_invariant_xy<float>(z0, z1, vn, c0, c1);
+    cond[l * 3 + 0] = c0;
+    cond[l * 3 + 1] = c1;
     cond[l * 3 + 2] = z2;  // invariant z component (reni_illumination_field.py:228,244)
   }
   __syncthreads();
@@ -112,8 +53,6 @@ reni_prep_kernel(const float* __restrict__ latents, const float* __restrict__ ro
 }
 
 // ---- kernel 2: per (latent code, direction) row ---------------------------------------------
-constexpr int RENI_ROWS = 8;
-
 __device__ __forceinline__ void block_layernorm(float (&x)[RENI_ROWS], const float* gw, const float* gb, int t,
                                                 float (*red)[RENI_H / 32][2]) {
   // LayerNorm over the H = 128 threads of the block, for RENI_ROWS rows at once (eps 1e-5, biased var)
@@ -144,21 +83,27 @@ __device__ __forceinline__ void block_layernorm(float (&x)[RENI_ROWS], const flo
 }
 
 __global__ void __launch_bounds__(RENI_H)
-reni_rows_kernel(const float* __restrict__ dirs, int64_t D, const float* __restrict__ zxy, const float* __restrict__ scale,
-                 const float* __restrict__ attn, const float* __restrict__ W, ReniLayout y, int log_domain,
-                 float* __restrict__ out) {
+reni_rows_kernel(const float* __restrict__ dirs, int64_t D, const int* __restrict__ row_cam, const float* __restrict__ zxy,
+                 const float* __restrict__ scale, const float* __restrict__ attn, const float* __restrict__ W, ReniLayout y,
+                 int log_domain, float* __restrict__ out) {
   extern __shared__ float sm[];
   float* pe = sm;                                  // [d_in][RENI_ROWS]
   float* act = sm + (size_t)y.d_in * RENI_ROWS;    // [H][RENI_ROWS]
   __shared__ float red[RENI_ROWS][RENI_H / 32][2];
-  const int k = blockIdx.y, t = threadIdx.x;
+  const int t = threadIdx.x;
   const int64_t row0 = (int64_t)blockIdx.x * RENI_ROWS;
   const int Lp2 = y.L + 2;
   const float TWO_PI = 6.283185307179586f, HALF_PI = 1.5707963267948966f;
+  // latent code of each row: the table mode (row_cam == NULL) decodes code blockIdx.y in every direction; the per-row mode
+  // decodes direction d with code row_cam[d] (background radiance along camera rays, neusky_model.py:535-549)
+  int kr[RENI_ROWS];
+#pragma unroll
+  for (int r = 0; r < RENI_ROWS; ++r) kr[r] = row_cam ? row_cam[min(row0 + r, D - 1)] : (int)blockIdx.y;
   // directional input + NeRF PE (2 freqs {1,4}, include_input appended) [NS-mem A.2]
   for (int e = t; e < Lp2 * RENI_ROWS; e += blockDim.x) {
     const int j = e / RENI_ROWS, r = e % RENI_ROWS;
     const int64_t d = min(row0 + r, D - 1);
+    const int k = row_cam ? row_cam[d] : (int)blockIdx.y;
     const float dx = dirs[d * 3], dy = dirs[d * 3 + 1], dz = dirs[d * 3 + 2];
     float xin;
     if (j < y.L) xin = zxy[((int64_t)k * y.L + j) * 2] * dx + zxy[((int64_t)k * y.L + j) * 2 + 1] * dy;
@@ -188,9 +133,8 @@ reni_rows_kernel(const float* __restrict__ dirs, int64_t D, const float* __restr
   }
   for (int i = 0; i < y.NL; ++i) {
     const float* Wl = W + y.layer0 + (int64_t)i * y.layer_stride;
-    const float a = attn[((int64_t)k * y.NL + i) * y.H + t];
 #pragma unroll
-    for (int r = 0; r < RENI_ROWS; ++r) x[r] += a;
+    for (int r = 0; r < RENI_ROWS; ++r) x[r] += attn[((int64_t)kr[r] * y.NL + i) * y.H + t];
     block_layernorm(x, Wl + y.o_n1w, Wl + y.o_n1b, t, red);   // out1 = LN(attn + x)
 #pragma unroll
     for (int r = 0; r < RENI_ROWS; ++r) act[t * RENI_ROWS + r] = x[r];
@@ -237,11 +181,12 @@ reni_rows_kernel(const float* __restrict__ dirs, int64_t D, const float* __restr
     if (row0 + r < D) {
       float o = W[y.fc_b + c];
       for (int j = 0; j < y.H; ++j) o += act[j * RENI_ROWS + r] * W[y.fc_w + (int64_t)c * y.H + j];
+      const int k = row_cam ? row_cam[row0 + r] : (int)blockIdx.y;
       if (scale) {
         const float s = expf(scale[k]);
         o = log_domain ? (o + logf(s)) : (o * s);
       }
-      out[((int64_t)k * D + row0 + r) * 3 + c] = log_domain ? expf(o) : o;
+      out[((row_cam ? 0 : (int64_t)k * D) + row0 + r) * 3 + c] = log_domain ? expf(o) : o;
     }
   }
 }
@@ -252,22 +197,41 @@ extern "C" int64_t nsk_reni_weights_floats(int latent_dim, int hidden, int num_l
   return nsk::reni_layout(latent_dim, hidden, num_layers).total;
 }
 
-extern "C" int nsk_reni_decode_fwd(const float* dirs, int64_t D, const float* latents, const float* scale, int64_t K,
-                                   const float* rotation, const float* weights, int latent_dim, int hidden, int num_layers,
-                                   int log_domain, float* workspace, float* out, void* stream) {
-  NSK_REQUIRE(hidden == nsk::RENI_H, "nsk_reni_decode_fwd: hidden_features must be 128");
-  NSK_REQUIRE(latent_dim >= 1 && latent_dim <= nsk::RENI_MAX_L, "nsk_reni_decode_fwd: latent_dim out of range");
+int nsk::reni_launch_prep(const float* latents, const float* rotation, const float* W, ReniLayout y, int64_t K, float* zxy, float* attn, cudaStream_t st) {
+  nsk::reni_prep_kernel<<<(unsigned)K, nsk::RENI_H, 0, st>>>(latents, rotation, W, y, zxy, attn);
+  return nsk::check_launch("reni_prep_kernel");
+}
+
+static int reni_decode_launch(const char* what, const float* dirs, int64_t D, const int* row_cam, const float* latents, const float* scale,
+                              int64_t K, const float* rotation, const float* weights, int latent_dim, int hidden, int num_layers,
+                              int log_domain, float* workspace, float* out, void* stream) {
+  NSK_REQUIRE(hidden == nsk::RENI_H, "nsk_reni_decode: hidden_features must be 128");
+  NSK_REQUIRE(latent_dim >= 1 && latent_dim <= nsk::RENI_MAX_L, "nsk_reni_decode: latent_dim out of range");
   if (K == 0 || D == 0) return 0;
-  NSK_REQUIRE(dirs && latents && weights && workspace && out, "nsk_reni_decode_fwd: null pointer");
-  NSK_REQUIRE(K <= 65535, "nsk_reni_decode_fwd: too many latent codes for one launch");
+  NSK_REQUIRE(dirs && latents && weights && workspace && out, "nsk_reni_decode: null pointer");
+  NSK_REQUIRE(K <= 65535, "nsk_reni_decode: too many latent codes for one launch");
   const nsk::ReniLayout y = nsk::reni_layout(latent_dim, hidden, num_layers);
   float* attn = workspace;                                  // [K, NL, H]
   float* zxy = workspace + K * num_layers * (int64_t)hidden;  // [K, L, 2]
   cudaStream_t st = nsk::as_stream(stream);
-  nsk::reni_prep_kernel<<<(unsigned)K, nsk::RENI_H, 0, st>>>(latents, rotation, weights, y, zxy, attn);
-  if (int e = nsk::check_launch("reni_prep_kernel")) return e;
+  if (int e = nsk::reni_launch_prep(latents, rotation, weights, y, K, zxy, attn, st)) return e;
   const size_t smem = ((size_t)y.d_in + hidden) * nsk::RENI_ROWS * sizeof(float);
-  dim3 grid((unsigned)((D + nsk::RENI_ROWS - 1) / nsk::RENI_ROWS), (unsigned)K);
-  nsk::reni_rows_kernel<<<grid, nsk::RENI_H, smem, st>>>(dirs, D, zxy, scale, attn, weights, y, log_domain, out);
-  return nsk::check_launch("reni_rows_kernel");
+  dim3 grid((unsigned)((D + nsk::RENI_ROWS - 1) / nsk::RENI_ROWS), row_cam ? 1u : (unsigned)K);
+  nsk::reni_rows_kernel<<<grid, nsk::RENI_H, smem, st>>>(dirs, D, row_cam, zxy, scale, attn, weights, y, log_domain, out);
+  return nsk::check_launch(what);
+}
+
+extern "C" int nsk_reni_decode_fwd(const float* dirs, int64_t D, const float* latents, const float* scale, int64_t K,
+                                   const float* rotation, const float* weights, int latent_dim, int hidden, int num_layers,
+                                   int log_domain, float* workspace, float* out, void* stream) {
+  return reni_decode_launch("nsk_reni_decode_fwd", dirs, D, nullptr, latents, scale, K, rotation, weights, latent_dim, hidden, num_layers,
+                            log_domain, workspace, out, stream);
+}
+
+extern "C" int nsk_reni_decode_rows_fwd(const float* dirs, const int* row_cam, int64_t N, const float* latents, const float* scale, int64_t K,
+                                        const float* rotation, const float* weights, int latent_dim, int hidden, int num_layers,
+                                        int log_domain, float* workspace, float* out, void* stream) {
+  NSK_REQUIRE(row_cam != nullptr || N == 0, "nsk_reni_decode_rows_fwd: null row_cam");
+  return reni_decode_launch("nsk_reni_decode_rows_fwd", dirs, N, row_cam, latents, scale, K, rotation, weights, latent_dim, hidden, num_layers,
+                            log_domain, workspace, out, stream);
 }

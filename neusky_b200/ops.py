@@ -219,6 +219,54 @@ def reni_radiance_table(dirs: Tensor, latents: Tensor, scale: Optional[Tensor], 
     return out
 
 
+def reni_radiance_rows(dirs: Tensor, row_cam: Tensor, latents: Tensor, scale: Optional[Tensor], packed: Tensor, rotation: Optional[Tensor] = None, hidden: int = 128, num_layers: int = 6, log_domain: bool = True) -> Tensor:
+    """dirs [N,3], row_cam [N] int32 (latent code of each row), latents [K,L,3], scale [K] -> HDR radiance [N,3]
+    (the per-ray background colours of a mixed-camera batch, neusky_model.py:535-549)."""
+    N = dirs.shape[0]
+    K, L = latents.shape[0], latents.shape[1]
+    dirs = _chk("dirs", dirs, shape=(N, 3))
+    row_cam = _chk("row_cam", row_cam, dtype=torch.int32, shape=(N,))
+    latents = _chk("latents", latents, shape=(K, L, 3))
+    if scale is not None:
+        scale = _chk("scale", scale, shape=(K,))
+    if rotation is not None:
+        rotation = _chk("rotation", rotation, shape=(3, 3))
+    lib = _lib.load()
+    packed = _chk("packed", packed, shape=(lib.nsk_reni_weights_floats(c_int(L), c_int(hidden), c_int(num_layers)),))
+    ws = torch.empty((K * num_layers * hidden + K * L * 2,), device=dirs.device, dtype=torch.float32)
+    out = torch.empty((N, 3), device=dirs.device, dtype=torch.float32)
+    _lib.check(lib.nsk_reni_decode_rows_fwd(_ptr(dirs), _ptr(row_cam), c_int64(N), _ptr(latents), _ptr(scale), c_int64(K), _ptr(rotation), _ptr(packed), c_int(L), c_int(hidden), c_int(num_layers), c_int(int(log_domain)), _ptr(ws), _ptr(out), _stream(dirs)), "nsk_reni_decode_rows_fwd")
+    return out
+
+
+def reni_decode_bwd(dirs: Tensor, row_cam: Optional[Tensor], latents: Tensor, scale: Optional[Tensor], packed: Tensor, packed_bwd: Tensor, out: Tensor, g_out: Tensor,
+                    d_latents: Tensor, d_scale: Optional[Tensor], rotation: Optional[Tensor] = None, hidden: int = 128, num_layers: int = 6, log_domain: bool = True) -> None:
+    """Accumulates d loss / d latents [K,L,3] and d loss / d scale [K] of reni_radiance_table (row_cam None; out, g_out [K,D,3])
+    or reni_radiance_rows (out, g_out [N,3]); the decoder weights are frozen (RENIField.hold_decoder_fixed)."""
+    D = dirs.shape[0]
+    K, L = latents.shape[0], latents.shape[1]
+    dirs = _chk("dirs", dirs, shape=(D, 3))
+    latents = _chk("latents", latents, shape=(K, L, 3))
+    oshape = (D, 3) if row_cam is not None else (K, D, 3)
+    out, g_out = _chk("out", out, shape=oshape), _chk("g_out", g_out, shape=oshape)
+    d_latents = _chk("d_latents", d_latents, shape=(K, L, 3))
+    if row_cam is not None:
+        row_cam = _chk("row_cam", row_cam, dtype=torch.int32, shape=(D,))
+    if (scale is None) != (d_scale is None):
+        raise ValueError("reni_decode_bwd: scale and d_scale must be given together")
+    if scale is not None:
+        scale, d_scale = _chk("scale", scale, shape=(K,)), _chk("d_scale", d_scale, shape=(K,))
+    if rotation is not None:
+        rotation = _chk("rotation", rotation, shape=(3, 3))
+    lib = _lib.load()
+    packed = _chk("packed", packed, shape=(lib.nsk_reni_weights_floats(c_int(L), c_int(hidden), c_int(num_layers)),))
+    packed_bwd = _chk("packed_bwd", packed_bwd, shape=(lib.nsk_reni_bwd_weights_floats(c_int(L), c_int(hidden), c_int(num_layers)),))
+    ws = torch.empty((lib.nsk_reni_bwd_workspace_floats(c_int64(K), c_int(L), c_int(hidden), c_int(num_layers)),), device=dirs.device, dtype=torch.float32)
+    _lib.check(lib.nsk_reni_decode_bwd(_ptr(dirs), _ptr(row_cam), c_int64(D), _ptr(latents), _ptr(scale), c_int64(K), _ptr(rotation), _ptr(packed), _ptr(packed_bwd),
+                                       c_int(L), c_int(hidden), c_int(num_layers), c_int(int(log_domain)), _ptr(out), _ptr(g_out), _ptr(ws), _ptr(d_latents), _ptr(d_scale),
+                                       _stream(dirs)), "nsk_reni_decode_bwd")
+
+
 # ------------------------------------------------------------------------------------------- Lambert / K4
 def lambert_prep(normals, wa, dirs, ddf_mask, radiance, cam=None, unoccluded_vis: float = 1.0):
     R, S = normals.shape[0], normals.shape[1]

@@ -52,6 +52,16 @@ def pack_reni(p: Dict[str, Tensor], num_layers: int = 6) -> Tensor:
     return torch.cat([x.to(torch.float32).flatten() for x in parts]).contiguous()
 
 
+def pack_reni_bwd(p: Dict[str, Tensor], num_layers: int = 6) -> Tensor:
+    """fp32 blob for nsk_reni_decode_bwd (see reni_bwd_layout()): the decoder's linear weights in torch's own [out][in]
+    layout, which is the coalesced one for the transposed products of the backward pass."""
+    parts = [p["network.residual_projection.weight"]]
+    for i in range(num_layers):
+        pre = f"network.layers.{i}."
+        parts += [p[pre + "mha.value.weight"], p[pre + "mha.fc_out.weight"], p[pre + "fc.0.weight"], p[pre + "fc.2.weight"]]
+    return torch.cat([x.to(torch.float32).contiguous().flatten() for x in parts]).contiguous()
+
+
 def pack_ddf_tc2(p: Dict[str, Tensor]) -> Tensor:
     """uint8 blob for nsk_sky_shade_tc2_fwd (CTA-pair kernel, csrc/sky_shade_tc2.cu): the same operand matrices as
     pack_ddf_tc, but every [N][K] tile is split by rows between the two CTAs of a pair (rank r streams rows

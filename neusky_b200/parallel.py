@@ -73,3 +73,103 @@ def render_sharded(render_fn: Callable[[Tensor], Dict[str, Tensor]], n_rays: int
         res[k] = full[:, o : o + w]
         o += w
     return res
+
+
+# =====================================================================================================================
+# Training: data-parallel gradient all-reduce (the reference wraps the model in torch DDP,
+# neusky/pipelines/neusky_pipeline.py:198-200)
+# =====================================================================================================================
+class GradBucketReducer:
+    """Bucketed gradient all-reduce (sum -> mean) for identical model replicas, one process per GPU.
+
+    Every parameter's .grad is a view into one of a few flat fp32 buckets, so backward kernels accumulate straight into
+    communication buffers and nothing is packed or unpacked.  The two hash tables (64 MiB each at T = 2^19) get a bucket
+    of their own; the ~5 MB of MLP weights, latents and scalars share one.  A bucket's all-reduce is issued from a
+    post-accumulate-grad hook as soon as its last gradient has landed, on the process group's own stream (NCCL over
+    NVLink / NVSwitch on GPUs, gloo on CPU), so the DDF buckets are reduced while the SDF backward is still running.
+    `finish()` waits for the outstanding work and applies the 1/world factor.
+
+        red = GradBucketReducer(params)           # once
+        red.zero_grad(); loss.backward(); red.finish()          # per step: grads are now the mean over ranks
+    """
+
+    def __init__(self, params, big_bytes: int = 8 << 20, group=None):
+        import torch.distributed as dist
+
+        self.group = group
+        self.on = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        self.world = dist.get_world_size(group) if self.on else 1
+        self.params = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("GradBucketReducer: no trainable parameters")
+        dev = self.params[0].device
+        small, assign = [], []
+        for p in self.params:
+            if p.dtype != torch.float32 or p.device != dev:
+                raise ValueError("GradBucketReducer: parameters must be fp32 on one device")
+            if p.numel() * 4 >= big_bytes:
+                assign.append([p])
+            else:
+                small.append(p)
+        if small:
+            assign.append(small)
+        self.buckets: List[Tensor] = []
+        self._pending: List[int] = []
+        self._bucket_of: Dict[int, int] = {}
+        self._sizes: List[int] = []
+        for bi, ps in enumerate(assign):
+            n = sum((p.numel() + 3) // 4 * 4 for p in ps)                      # 16-byte aligned views
+            flat = torch.zeros(n, dtype=torch.float32, device=dev)
+            o = 0
+            for p in ps:
+                p.grad = flat[o : o + p.numel()].view_as(p)
+                self._bucket_of[id(p)] = bi
+                o += (p.numel() + 3) // 4 * 4
+            self.buckets.append(flat)
+            self._sizes.append(len(ps))
+        self._left = list(self._sizes)
+        self._work: List = []
+        self.launched_order: List[int] = []
+        for p in self.params:
+            p.register_post_accumulate_grad_hook(self._hook)
+
+    @property
+    def bytes_per_step(self) -> int:
+        return sum(b.numel() * 4 for b in self.buckets)
+
+    def zero_grad(self) -> None:
+        """Zero the buckets in place (the .grad views stay attached) and re-arm the ready counters."""
+        for b in self.buckets:
+            b.zero_()
+        self._left = list(self._sizes)
+        self._work = []
+        self.launched_order = []
+
+    def _launch(self, bi: int) -> None:
+        import torch.distributed as dist
+
+        self.launched_order.append(bi)
+        if self.on:
+            self._work.append(dist.all_reduce(self.buckets[bi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def _hook(self, p) -> None:
+        bi = self._bucket_of[id(p)]
+        if p.grad is None or p.grad.untyped_storage().data_ptr() != self.buckets[bi].untyped_storage().data_ptr():
+            raise RuntimeError("GradBucketReducer: a parameter's .grad was replaced; use reducer.zero_grad(), not optimizer.zero_grad(set_to_none=True)")
+        self._left[bi] -= 1
+        if self._left[bi] == 0:
+            self._launch(bi)
+
+    def finish(self) -> None:
+        """Reduce buckets whose hooks never completed (parameters unused this step keep zero gradients, as DDP's
+        find_unused_parameters would), wait, and turn sums into means."""
+        for bi, left in enumerate(self._left):
+            if left > 0:
+                self._left[bi] = 0
+                self._launch(bi)
+        for w in self._work:
+            w.wait()
+        self._work = []
+        if self.world > 1:
+            for b in self.buckets:
+                b.mul_(1.0 / self.world)

@@ -347,12 +347,12 @@ class NeuSkyTrainStep(torch.nn.Module):
     state-dict names (dots replaced by '__' for nn.Module registration) and its optimizer groups
     (neusky_model.py:379-398): fields, ddf_field, illumination latents, visibility_sigmoid.
 
-    Not differentiated here: the RENI++ decoder (fixed_decoder=True in the reference, neusky_config.py:94) -- and, in this
-    round, the per-image latent codes feeding it (forward only through csrc/reni_decode.cu)."""
+    The RENI++ decoder is frozen (fixed_decoder=True in the reference, neusky_config.py:94); the per-image latent codes and
+    scales feeding it are trained through csrc/reni_decode_bwd.cu."""
 
     def __init__(self, sdf_params: Dict[str, Tensor], ddf_params: Dict[str, Tensor], reni_params: Dict[str, Tensor], num_cameras: int, device="cuda",
                  log2_T: int = 19, num_levels: int = 16, num_samples: int = 48, ddf_radius: float = 1.0, sigmoid_scale: float = 25.0,
-                 split_geo: int = 3, split: int = 1, threshold_init: Optional[float] = None, only_upper_hemisphere: bool = True,
+                 split_geo: int = 3, split: int = 3, threshold_init: Optional[float] = None, only_upper_hemisphere: bool = True,
                  lower_hemisphere_visibility: float = 1.0):
         super().__init__()
         from . import packing
@@ -373,6 +373,7 @@ class NeuSkyTrainStep(torch.nn.Module):
         thr0 = 2.0 * self.radius if threshold_init is None else threshold_init                    # :234
         self.visibility_threshold = torch.nn.Parameter(torch.tensor(float(thr0), device=self.dev))
         self.reni_blob = packing.pack_reni({k: v.to(self.dev) for k, v in reni_params.items()})
+        self.reni_blob_bwd = packing.pack_reni_bwd({k: v.to(self.dev) for k, v in reni_params.items()})
         self.sdf_cfg = SDFConfig(scalings=self.scalings, log2_T=log2_T, split_geo=split_geo, split_colour=split)
         self.ddf_cfg = DDFConfig(scalings=self.scalings, log2_T=log2_T, radius=self.radius, sigmoid_scale=sigmoid_scale, split=split)
         self.cos_anneal_ratio = 1.0
@@ -388,11 +389,14 @@ class NeuSkyTrainStep(torch.nn.Module):
 
     def set_directions(self, dirs: Tensor) -> None:
         """Illumination directions of this iteration [D,3] (IcosahedronSampler with its random rotation, neusky_model.py:452-456)."""
-        self.dirs = dirs.to(self.dev, torch.float32).contiguous()
-        m = (self.dirs[:, 2] > 0) if self.only_upper else torch.ones(self.dirs.shape[0], dtype=torch.bool, device=self.dev)
-        self.mask_u8 = m.to(torch.uint8).contiguous()
-        self.dirs_sel = self.dirs[m].contiguous()
-        self.sel_index = torch.where(m, torch.cumsum(m.to(torch.int32), 0, dtype=torch.int32) - 1, torch.full_like(m, -1, dtype=torch.int32)).to(torch.int32).contiguous()
+        d0 = dirs.to(torch.float32).contiguous()          # mask / compaction on the device the sampler produced them on (host: no sync)
+        m = (d0[:, 2] > 0) if self.only_upper else torch.ones(d0.shape[0], dtype=torch.bool, device=d0.device)
+        sel = torch.where(m, torch.cumsum(m.to(torch.int32), 0, dtype=torch.int32) - 1, torch.full_like(m, -1, dtype=torch.int32)).to(torch.int32)
+        nb = d0.device.type == "cpu"
+        self.dirs = d0.to(self.dev, non_blocking=nb)
+        self.mask_u8 = m.to(torch.uint8).contiguous().to(self.dev, non_blocking=nb)
+        self.dirs_sel = d0[m].contiguous().to(self.dev, non_blocking=nb)
+        self.sel_index = sel.contiguous().to(self.dev, non_blocking=nb)
 
     # -- forward ---------------------------------------------------------------------------------------------
     def forward(self, batch: Dict[str, Tensor], grid_positions: Optional[Tensor] = None, grid_dirs: Optional[Tensor] = None) -> Tuple[Tensor, Dict[str, Tensor], Dict[str, Tensor]]:
@@ -407,8 +411,8 @@ class NeuSkyTrainStep(torch.nn.Module):
         table = sdf_p["encoding.hash_table"]
 
         near, far = sphere_collider(o, d, radius=1.0, training=True)
-        starts, ends = uniform_samples(near, far, S)                                   # [R,S,1]
-        x = (o[:, None, :] + d[:, None, :] * starts).reshape(-1, 3)
+        starts, ends = uniform_samples(near, far, S)                                   # [R,S]
+        x = (o[:, None, :] + d[:, None, :] * starts[:, :, None]).reshape(-1, 3)
         sdf, grad, alb = sdf_field(self.sdf_cfg, x, table, sdf_w)
         inv_s = torch.exp(sdf_p["deviation_network.variance"] * 10.0).clip(1e-6, 1e6)
         starts2, ends2 = starts.reshape(R, S), ends.reshape(R, S)
@@ -418,10 +422,10 @@ class NeuSkyTrainStep(torch.nn.Module):
         p2p = torch.clip(p2p_raw.detach(), steps.min(), steps.max())                   # DepthRenderer clip; detached (stop-gradients "depth")
         pts = ops.surface_points(o, d, p2p, self.radius)
 
-        with torch.no_grad():
-            radiance = ops.reni_radiance_table(self.dirs, self.latents, self.scale, self.reni_blob)      # [K,D,3]
-            bg_all = ops.reni_radiance_table(d, self.latents, self.scale, self.reni_blob)                # [K,R,3]
-            bg = bg_all[cam.long(), torch.arange(R, device=self.dev)].contiguous()
+        # RENI++ radiance of every (camera, light direction) pair and along each camera ray; differentiable w.r.t. the per-image
+        # latent codes and scales, decoder frozen (neusky_model.py:261-269, 488-504, 535-549; neusky_config.py:94)
+        radiance = nba.reni_radiance(self.dirs, self.latents, self.scale, self.reni_blob, self.reni_blob_bwd)                 # [K,D,3]
+        bg = nba.reni_radiance(d.contiguous(), self.latents, self.scale, self.reni_blob, self.reni_blob_bwd, row_cam=cam)     # [R,3]
 
         vis, that, q, _term = ddf_visibility(self.ddf_cfg, pts, self.dirs_sel, self.visibility_threshold, ddf_p["position_encoding.hash_table"],
                                              ddf_p["ddf.final_layer.weight"], ddf_p["ddf.final_layer.bias"], ddf_param_list(ddf_p))
@@ -429,7 +433,7 @@ class NeuSkyTrainStep(torch.nn.Module):
         term_pts = q + (-self.dirs_sel)[None].expand(R, Dp, 3).reshape(-1, 3) * that[:, None]          # ddf_model.py:243
         sdf_term, _, _ = sdf_field(self.sdf_cfg, term_pts, table, sdf_w, want_normals=False, want_albedo=False)
 
-        inv_count, _ = ops.lambert_prep(normals.detach(), wa.detach(), self.dirs, self.mask_u8, radiance, cam, self.lower_vis)
+        inv_count, _ = ops.lambert_prep(normals.detach(), wa.detach(), self.dirs, self.mask_u8, radiance.detach(), cam, self.lower_vis)
         rgb_lin = nba.lambert_shade(normals, wa, radiance, vis, inv_count, self.dirs, self.sel_index, cam, self.lower_vis)
         rgb = nba.shade_finalize(rgb_lin, bg, acc)
         out = {"rgb": rgb, "eik_grad": grad.reshape(R, S, 3), "weights": weights, "normal": normal, "accumulation": acc, "hdr_background_colours": bg,

@@ -159,3 +159,51 @@ def test_hash_encode_double_backward_normals_path(dev):
     n_gpu, gt_gpu = run(lambda a, b: nba.hash_encode(a, b, sc.to(dev), log2_T), x.to(dev), t_gpu, W.to(dev), cot.to(dev))
     assert float((n_gpu.cpu() - n_ref.float()).abs().max() / n_ref.abs().max()) <= 1e-4
     assert float((gt_gpu.cpu() - gt_ref.float()).abs().max() / gt_ref.abs().max()) <= 1e-3
+
+
+@pytest.mark.parametrize("mode,rot,log_domain,with_scale", [("table", False, True, True), ("table", True, True, True), ("rows", False, True, True),
+                                                           ("rows", True, False, True), ("table", False, True, False)])
+def test_reni_radiance_backward_vs_oracle_autograd(dev, mode, rot, log_domain, with_scale):
+    """d/d latent codes and d/d scale of the RENI++ radiance (decoder frozen) against fp64 torch autograd through the oracle's
+    restatement of RENIField.get_outputs + unnormalise (reni_illumination_field.py:493-573, base_spherical_field.py:143-154);
+    table mode = every (code, direction) pair (neusky_model.py:488-504), rows mode = one code per camera ray (:535-549)."""
+    from neusky_b200 import autograd as nba, packing
+    from oracle import neusky_oracle as O
+
+    K, D = 3, 37            # D not a multiple of the 8-row block
+    p = nb_init.init_reni_params(8)
+    g = torch.Generator().manual_seed(17)
+    Z = torch.randn(K, 100, 3, generator=g)
+    sc = 0.2 * torch.randn(K, generator=g)
+    dirs = torch.nn.functional.normalize(torch.randn(D, 3, generator=g), dim=-1)
+    R = None
+    if rot:
+        q, _ = torch.linalg.qr(torch.randn(3, 3, generator=g))
+        R = q.contiguous()
+    cam = torch.randint(0, K, (D,), generator=g)
+    cot = torch.randn((K, D, 3) if mode == "table" else (D, 3), generator=g)
+
+    # ---- oracle, fp64 autograd
+    Zr, scr = Z.double().requires_grad_(True), sc.double().requires_grad_(True)
+    pd = {k: v.double() for k, v in p.items()}
+    Rd = None if R is None else R.double()
+    if mode == "table":
+        ref = torch.stack([O.reni_unnormalise(O.reni_field(dirs.double(), Zr[k : k + 1].expand(D, -1, -1), scr[k : k + 1].expand(D) if with_scale else None, pd, Rd, log_domain), log_domain)
+                           for k in range(K)], 0)
+    else:
+        ref = O.reni_unnormalise(O.reni_field(dirs.double(), Zr[cam], scr[cam] if with_scale else None, pd, Rd, log_domain), log_domain)
+    (ref * cot.double()).sum().backward()
+
+    # ---- CUDA
+    pc = {k: v.to(dev) for k, v in p.items()}
+    blob, blob_b = packing.pack_reni(pc), packing.pack_reni_bwd(pc)
+    Zc = Z.to(dev).requires_grad_(True)
+    scc = sc.to(dev).requires_grad_(True) if with_scale else None
+    out = nba.reni_radiance(dirs.to(dev), Zc, scc, blob, blob_b, row_cam=cam.to(dev, torch.int32) if mode == "rows" else None,
+                            rotation=None if R is None else R.to(dev), log_domain=log_domain)
+    assert float((out.detach().cpu().double() - ref.detach()).abs().max() / ref.detach().abs().max()) <= 1e-3
+    (out * cot.to(dev)).sum().backward()
+    rel = lambda a, b: float((a.double().cpu() - b).norm() / (b.norm() + 1e-30))
+    assert rel(Zc.grad, Zr.grad) <= 2e-3, rel(Zc.grad, Zr.grad)
+    if with_scale:
+        assert rel(scc.grad, scr.grad) <= 2e-3, rel(scc.grad, scr.grad)
