@@ -163,6 +163,12 @@ def test_ddf_visibility_forward_backward_vs_oracle_autograd(dev, split, tol_fwd,
     o = O.compute_visibility(pts.double(), dirs.double(), pd, O.hash_scalings().double(), log2_T, 1.0, thr_ref, scale, only_upper=True)
     loss = (o["visibility"] * cot_vis.double()).sum() + (o["expected_termination_dist"] * cot_that.double()).sum()
     loss.backward()
+    # conditioning: how far a plain fp32 autograd pass through the same oracle lands from fp64, per parameter
+    p32 = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    thr32 = torch.tensor(thr0, requires_grad=True)
+    o32 = O.compute_visibility(pts, dirs, p32, O.hash_scalings(), log2_T, 1.0, thr32, scale, only_upper=True)
+    ((o32["visibility"] * cot_vis).sum() + (o32["expected_termination_dist"] * cot_that).sum()).backward()
+    cond = {k: _rel(p32[k].grad, pd[k].grad) for k in p if p32[k].grad is not None}
 
     # ---- CUDA ----
     cfg = T.DDFConfig(scalings=O.hash_scalings().to(dev), log2_T=log2_T, radius=1.0, sigmoid_scale=scale, split=split)
@@ -215,6 +221,11 @@ def test_sdf_field_forward_double_backward_vs_oracle_autograd(dev, split, tol_fw
     pd = {k: v.double().requires_grad_(True) for k, v in p.items()}
     xr, sdf_r, grad_r, alb_r = _sdf_oracle_outputs(x.double(), pd, O.hash_scalings().double(), log2_T)
     ((sdf_r * cot_s.double()).sum() + (grad_r * cot_g.double()).sum() + (alb_r * cot_a.double()).sum()).backward()
+    # conditioning: fp32 autograd through the same oracle vs fp64, per parameter
+    p32 = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    _, sdf_32, grad_32, alb_32 = _sdf_oracle_outputs(x, p32, O.hash_scalings(), log2_T)
+    ((sdf_32 * cot_s).sum() + (grad_32 * cot_g).sum() + (alb_32 * cot_a).sum()).backward()
+    cond = {k: _rel(p32[k].grad, pd[k].grad) for k in p if p32[k].grad is not None}
 
     cfg = T.SDFConfig(scalings=O.hash_scalings().to(dev), log2_T=log2_T, split_geo=split, split_colour=split)
     pc = {k: v.to(dev).requires_grad_(True) for k, v in p.items()}
