@@ -304,6 +304,42 @@ int nsk_ew256(int op, int64_t n, const float* a, const float* b, const float* c,
 int nsk_rowdot256(const float* X, const float* w, const float* b, int64_t n, float* out, void* stream);
 int nsk_colsum_w(const float* X, int ld, const float* v, int64_t M, int ncols, float* out, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Proposal-network sampler: the sample placement in front of the path.
+ * replaces nerfstudio ProposalNetworkSampler.generate_ray_samples as called at neusky/models/neusky_model.py:561
+ * (UniformSampler -> HashMLPDensityField.density_fn -> RaySamples.get_weights -> PDFSampler, NeuSFactoModelConfig defaults,
+ * SURVEY A.6) and the interlevel loss that trains the proposal networks (neusky_model.py:575-576, 987-988).
+ *
+ * Sample placement lives in the SPACING domain: bins [R,S+1] in [0,1]; the euclidean edge is bin*far + (1-bin)*near.
+ *   nsk_uniform_bins      base [S+1] = linspace(0,1,S+1) (host), jitter [R] in [0,1) or NULL (eval) -> bins [R,S+1]
+ *   nsk_proposal_density_fwd   HashMLPDensityField: density [R,S] at the bin mid-points of rays (origins, dirs [R,3], near, far
+ *       [R]); dirs == NULL: positions mode, `origins` is [R*S,3] world positions (density_fn(positions)).
+ *       table [L*T,2], scalings [L]; mlp = packed blob W0 [2L][16] (input-major) | b0 [16] | W1 [16] | b1 (nsk_proposal_mlp_floats).
+ *   nsk_proposal_density_bwd   g_density [R,S] -> d_table [L*T,2], d_mlp (both ACCUMULATED INTO).
+ *   nsk_pdf_resample      density [R,S] (get_weights is fused) OR weights_in [R,S]  -> weights^anneal + histogram_padding -> pdf ->
+ *       cdf -> N+1 new bin edges at u = u_base[j] + (jitter ? jitter[r]/(N+1) : u_half); u_base [N+1] =
+ *       linspace(0, 1-1/(N+1), N+1) (host).  Writes weights_out [R,S] (NULL = skip), new_bins [R,N+1], new_euclid [R,N+1] (NULL =
+ *       skip).  Bit-exact vs the oracle given the weights (fp64 scans, see proposal_sampler.cu).
+ *   nsk_density_weights_bwd    g_weights [R,S] -> g_density [R,S] through RaySamples.get_weights.
+ *   nsk_interlevel_loss   c [R,Sf+1], w [R,Sf] (fine histogram, detached), cp [R,Sp+1], wp [R,Sp] (proposal) -> loss_ray [R] =
+ *       sum_i relu(w_i - outer_i)^2 / (w_i + eps), g_wp [R,Sp] = d loss_ray / d wp (NULL = skip).
+ * ------------------------------------------------------------------------------------------- */
+int64_t nsk_proposal_mlp_floats(int num_levels, int hidden);
+int nsk_uniform_bins(const float* base, const float* jitter, int64_t R, int S, float* bins, void* stream);
+int nsk_proposal_density_fwd(const float* origins, const float* dirs, const float* near, const float* far, const float* bins,
+                             int64_t R, int S, const float* table, const float* scalings, int num_levels, int log2_T,
+                             const float* mlp, int hidden, float* density, void* stream);
+int nsk_proposal_density_bwd(const float* origins, const float* dirs, const float* near, const float* far, const float* bins,
+                             int64_t R, int S, const float* table, const float* scalings, int num_levels, int log2_T,
+                             const float* mlp, int hidden, const float* g_density, float* d_table, float* d_mlp, void* stream);
+int nsk_pdf_resample(const float* bins, const float* density, const float* weights_in, const float* near, const float* far,
+                     int64_t R, int S, int N, float anneal, float histogram_padding, float eps, const float* u_base,
+                     float u_half, const float* jitter, float* weights_out, float* new_bins, float* new_euclid, void* stream);
+int nsk_density_weights_bwd(const float* bins, const float* density, const float* near, const float* far, int64_t R, int S,
+                            const float* g_weights, float* g_density, void* stream);
+int nsk_interlevel_loss(const float* c, const float* w, int Sf, const float* cp, const float* wp, int Sp, int64_t R,
+                        float* loss_ray, float* g_wp, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -177,3 +177,67 @@ def init_proposal_net(seed: int, num_levels: int = 5, log2_T: int = 17, hidden: 
         p[f"mlp.{i}.bias"] = (torch.rand(fout, generator=g) * 2 - 1) * b
     p["mlp.1.bias"] = p["mlp.1.bias"] + density_bias
     return p
+
+
+# --------------------------------------------------------------------------------------
+# Interlevel (proposal) loss [NS-mem]: nerfstudio/model_components/losses.py interlevel_loss / lossfun_outer / outer,
+# called at neusky/models/neusky_model.py:987-988 with the NeuS weights and samples appended (:575-576).  torch ops, so that
+# fp64 autograd gives the reference gradient for the proposal weights.
+# --------------------------------------------------------------------------------------
+
+def outer(t0_starts: Tensor, t0_ends: Tensor, t1_starts: Tensor, t1_ends: Tensor, y1: Tensor) -> Tensor:
+    cy1 = torch.cat([torch.zeros_like(y1[..., :1]), torch.cumsum(y1, dim=-1)], dim=-1)
+    idx_lo = torch.searchsorted(t1_starts.contiguous(), t0_starts.contiguous(), side="right") - 1
+    idx_lo = torch.clamp(idx_lo, min=0, max=y1.shape[-1] - 1)
+    idx_hi = torch.searchsorted(t1_ends.contiguous(), t0_ends.contiguous(), side="right")
+    idx_hi = torch.clamp(idx_hi, min=0, max=y1.shape[-1] - 1)
+    cy1_lo = torch.take_along_dim(cy1[..., :-1], idx_lo, dim=-1)
+    cy1_hi = torch.take_along_dim(cy1[..., 1:], idx_hi, dim=-1)
+    return cy1_hi - cy1_lo
+
+
+def lossfun_outer(t: Tensor, w: Tensor, t_env: Tensor, w_env: Tensor) -> Tensor:
+    eps = 1.1920928955078125e-07
+    w_outer = outer(t[..., :-1], t[..., 1:], t_env[..., :-1], t_env[..., 1:], w_env)
+    return torch.clip(w - w_outer, min=0) ** 2 / (w + eps)
+
+
+def interlevel_loss(weights_list: List[Tensor], sdist_list: List[Tensor]) -> Tensor:
+    """weights_list[i] [R,S_i], sdist_list[i] [R,S_i+1] (spacing bins); the last entry is the fine (NeuS) level, detached."""
+    c, w = sdist_list[-1].detach(), weights_list[-1].detach()
+    loss = 0.0
+    for cp, wp in zip(sdist_list[:-1], weights_list[:-1]):
+        loss = loss + torch.mean(lossfun_outer(c, w, cp, wp))
+    return loss
+
+
+def density_weights_torch(density: Tensor, deltas: Tensor) -> Tensor:
+    """RaySamples.get_weights in torch ops (differentiable twin of density_weights)."""
+    dd = deltas * density
+    alphas = 1 - torch.exp(-dd)
+    T = torch.cumsum(dd[..., :-1], dim=-1)
+    T = torch.exp(-torch.cat([torch.zeros_like(dd[..., :1]), T], dim=-1))
+    return torch.nan_to_num(alphas * T)
+
+
+def pdf_resample_torch(spacing_bins: Tensor, weights: Tensor, N: int, histogram_padding: float = 0.01, eps: float = 1e-5) -> Tensor:
+    """PDFSampler eval placement written with the torch calls nerfstudio makes (torch.sum / cumsum / searchsorted): the
+    cross-check that the explicit-order numpy statement above restates the same algorithm (agreement to a few ulp)."""
+    nb = N + 1
+    w = weights + histogram_padding
+    ws = torch.sum(w, dim=-1, keepdim=True)
+    padding = torch.relu(eps - ws)
+    w = w + padding / w.shape[-1]
+    ws = ws + padding
+    pdf = w / ws
+    cdf = torch.min(torch.ones_like(pdf), torch.cumsum(pdf, dim=-1))
+    cdf = torch.cat([torch.zeros_like(cdf[..., :1]), cdf], dim=-1)
+    u = torch.linspace(0.0, 1.0 - (1.0 / nb), steps=nb) + 1.0 / (2 * nb)
+    u = u.expand(*cdf.shape[:-1], nb).contiguous()
+    inds = torch.searchsorted(cdf, u, side="right")
+    below = torch.clamp(inds - 1, 0, spacing_bins.shape[-1] - 1)
+    above = torch.clamp(inds, 0, spacing_bins.shape[-1] - 1)
+    c0, c1 = torch.gather(cdf, -1, below), torch.gather(cdf, -1, above)
+    b0, b1 = torch.gather(spacing_bins, -1, below), torch.gather(spacing_bins, -1, above)
+    t = torch.clip(torch.nan_to_num((u - c0) / (c1 - c0), 0), 0, 1)
+    return b0 + t * (b1 - b0)
