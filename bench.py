@@ -221,7 +221,10 @@ def eval_arm(args):
 
     sdf_p = nb_init.init_sdf_params(SEED_W + 2, bias=0.45)
     sdf_p["deviation_network.variance"] = torch.tensor(0.3)
-    r = RayRenderer(sdf_p, nb_init.init_ddf_params(SEED_W), nb_init.init_reni_params(SEED_W + 1), device=dev)
+    prop = None
+    if args.sampler == "proposal":      # the shipped NeuS-facto placement: 256 -> 96 -> S samples through two HashMLPDensityFields
+        prop = [nb_init.init_proposal_params(SEED_W + 3, table_scale=1.0, density_bias=1.0), nb_init.init_proposal_params(SEED_W + 4, table_scale=1.0, density_bias=2.0)]
+    r = RayRenderer(sdf_p, nb_init.init_ddf_params(SEED_W), nb_init.init_reni_params(SEED_W + 1), device=dev, proposal_params=prop)
     r.set_directions(samplers.IcosahedronSampler(512)().frustums.directions)
     H, W = args.height, args.width
     fx = (W / 2) / math.tan(math.radians(30.0))
@@ -255,7 +258,7 @@ def eval_arm(args):
         acc = out["accumulation"]
         print(json.dumps({"metric": METRIC, "value": n * args.steps / t, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                           "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f16xf16->f32", "data": "synthetic",
-                          "config": {"workload": f"BASELINE.json configs[2]: full-image eval render {W}x{H}, {args.samples} uniform samples/ray, 642 icosphere directions (D'={Dp}), "
+                          "config": {"workload": f"BASELINE.json configs[2]: full-image eval render {W}x{H}, {args.samples} {'proposal-network (256->96->' + str(args.samples) + ')' if args.sampler == 'proposal' else 'uniform'} samples/ray, 642 icosphere directions (D'={Dp}), "
                                                  f"ray tiles of {args.tile} round-robin over {world} GPU(s), outputs gathered", "parallelism": f"ray tiles x{world}, weights replicated",
                                      "l2": "inputs (118 M samples/frame) exceed L2", "surface_coverage": float((acc > 0.5).float().mean())},
                           "gpu_launches": _lib.launches - l0, "pairs_per_frame": n * Dp, "samples_per_frame": n * args.samples}), flush=True)
@@ -401,6 +404,7 @@ def main():
     ap.add_argument("--width", type=int, default=1280)
     ap.add_argument("--samples", type=int, default=128)
     ap.add_argument("--tile", type=int, default=16384)
+    ap.add_argument("--sampler", default="uniform", choices=["uniform", "proposal"], help="eval: sample placement (proposal = shipped NeuS-facto default, use --samples 48)")
     ap.add_argument("--rays", type=int, default=1024, help="train: rays per GPU")
     ap.add_argument("--train-samples", type=int, default=48)
     ap.add_argument("--split", type=int, default=3, choices=[1, 3], help="train: 1 = tf32 GEMMs, 3 = 3xTF32 (fp32-accurate)")

@@ -163,3 +163,15 @@ def init_sdf_params(
     p["encoding.hash_table"] = _uniform(g, ((1 << log2_T) * num_levels, features), 1e-3)
     p["deviation_network.variance"] = torch.tensor(beta_init)
     return p
+
+
+def init_proposal_params(seed: int, num_levels: int = 5, log2_T: int = 17, hidden: int = 16, table_scale: float = 1e-3, density_bias: float = 0.0) -> Dict[str, Tensor]:
+    """Random-init state of one nerfstudio HashMLPDensityField (proposal network): hash table U(-1,1)*table_scale
+    (nerfstudio: 1e-3), torch Linear default init for Linear(2L,16) and Linear(16,1).  A larger ``table_scale`` / ``density_bias``
+    gives a non-trivial density (benchmarks and tests use that so the resampled placement is not uniform)."""
+    g = _gen(seed)
+    p = {"encoding.hash_table": _uniform(g, ((1 << log2_T) * num_levels, 2), table_scale)}
+    for i, (fin, fout) in enumerate(((2 * num_levels, hidden), (hidden, 1))):
+        p[f"mlp.{i}.weight"], p[f"mlp.{i}.bias"] = _linear_default(g, fout, fin)
+    p["mlp.1.bias"] = p["mlp.1.bias"] + density_bias
+    return p

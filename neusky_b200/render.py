@@ -7,7 +7,7 @@ between them (neusky/models/neusky_model.py:445-551, 1624-1778, 797-805) without
 """
 from __future__ import annotations
 
-from typing import Dict, Optional
+from typing import Dict, Optional, Sequence
 
 import torch
 
@@ -159,8 +159,19 @@ class RayRenderer:
     one camera (one latent code) per call; outputs use the reference's keys (:881-931)."""
 
     def __init__(self, sdf_params: Dict[str, Tensor], ddf_params: Dict[str, Tensor], reni_params: Dict[str, Tensor], device="cuda",
-                 log2_T: int = 19, num_levels: int = 16, ddf_radius: float = 1.0, impl: str = "tc2", sdf_impl: str = "tc"):
+                 log2_T: int = 19, num_levels: int = 16, ddf_radius: float = 1.0, impl: str = "tc2", sdf_impl: str = "tc",
+                 proposal_params: Optional[Sequence[Dict[str, Tensor]]] = None, proposal_max_res: Sequence[int] = (64, 256),
+                 num_proposal_samples_per_ray: Sequence[int] = (256, 96), proposal_log2_T: int = 17):
+        """``proposal_params``: state of the two HashMLPDensityFields -> sample placement by the proposal-network sampler
+        (the shipped NeuS-facto configuration, neusky_model.py:561); None -> uniform placement."""
         self.device = torch.device(device)
+        self.proposal_fields = None
+        if proposal_params is not None:
+            from . import proposal as _proposal
+
+            self.proposal_fields = [_proposal.HashMLPDensityField(p, mr, log2_hashmap_size=proposal_log2_T, device=device) for p, mr in zip(proposal_params, proposal_max_res)]
+            self._proposal_counts = tuple(num_proposal_samples_per_ray)
+            self._proposal_samplers = {}
         self.log2_T = log2_T
         self.sdf_impl = sdf_impl
         self.shader = SkyShader(ddf_params, reni_params, device=device, ddf_radius=ddf_radius, log2_T=log2_T, num_levels=num_levels, impl=impl)
@@ -185,7 +196,17 @@ class RayRenderer:
         R = origins.shape[0]
         sh = self.shader
         near, far = sphere_collider(origins, directions)
-        starts, ends = uniform_samples(near, far, S)
+        if self.proposal_fields is not None:
+            from . import proposal as _proposal
+
+            smp = self._proposal_samplers.get(S)
+            if smp is None:
+                smp = self._proposal_samplers[S] = _proposal.ProposalNetworkSampler(S, self._proposal_counts, len(self.proposal_fields))
+            rs, _, _ = smp.generate_ray_samples(origins, directions, near, far, self.proposal_fields)
+            e = rs.euclidean_bins
+            starts, ends = e[:, :-1].contiguous(), e[:, 1:].contiguous()
+        else:
+            starts, ends = uniform_samples(near, far, S)
         x = origins[:, None, :] + directions[:, None, :] * starts[..., None]          # get_start_positions
         f = ops.sdf_field(x, self.sdf_blob, self.sdf_table, self.scalings, self.log2_T, impl=self.sdf_impl)
         c = ops.neus_composite(f["sdf"], f["gradient"], f["albedo"], directions, starts, ends, ends - starts, dnorm, self.inv_s, cos_anneal_ratio, False,
@@ -243,7 +264,9 @@ def render_image(renderer: "RayRenderer", origins: Tensor, directions: Tensor, d
     from . import parallel
 
     n = origins.shape[0]
-    mm = global_steps_minmax(origins, directions, S)
+    # uniform placement: clip depth to the image-global range (known in closed form); proposal placement is data dependent, so each
+    # tile clips to its own range -- as the reference does per 256-ray chunk (neusky_model.py:1413-1437)
+    mm = global_steps_minmax(origins, directions, S) if renderer.proposal_fields is None else None
 
     def fn(idx: Tensor) -> Dict[str, Tensor]:
         outs = {k: [] for k in keys}

@@ -586,15 +586,23 @@ def uniform_samples(near: Tensor, far: Tensor, S: int) -> Tuple[Tensor, Tensor]:
 
 
 def render_rays(origins, directions, dnorm, S, sdf_p, ddf_p, reni_p, latent, scale, dirs, inv_s, log2_T=19,
-                ddf_radius=1.0, threshold=0.1, sigmoid_scale=25.0, rotation=None, chunk=256):
-    """Eval render of R rays of ONE camera with uniform sample placement.  Returns the outputs dict of
-    neusky_model.py:881-931 (rgb, albedo, accumulation, depth, p2p_dist, normal) plus visibility [R,D]."""
+                ddf_radius=1.0, threshold=0.1, sigmoid_scale=25.0, rotation=None, chunk=256, proposal_nets=None, proposal_log2_T=17):
+    """Eval render of R rays of ONE camera.  Sample placement: uniform, or -- with ``proposal_nets`` = the state of the two
+    HashMLPDensityFields -- the proposal-network sampler (neusky_model.py:561; oracle/sampler_oracle.py).  Returns the outputs
+    dict of neusky_model.py:881-931 (rgb, albedo, accumulation, depth, p2p_dist, normal) plus visibility [R,D]."""
     sca = hash_scalings()
     radiance = reni_radiance_table(dirs, latent[None], scale.reshape(1), reni_p, rotation)[0]  # [D,3] (:488-518)
     out = {k: [] for k in ("rgb", "albedo", "accumulation", "depth", "p2p_dist", "normal", "visibility", "weights")}
     R = origins.shape[0]
     near, far = sphere_collider(origins, directions)
-    starts_all, ends_all = uniform_samples(near, far, S)
+    if proposal_nets is not None:
+        from . import sampler_oracle as SO
+
+        e, _, _, _ = SO.proposal_sample(origins, directions, near, far, proposal_nets, num_final=S, log2_T=proposal_log2_T)
+        e = torch.from_numpy(e)
+        starts_all, ends_all = e[:, :-1, None], e[:, 1:, None]
+    else:
+        starts_all, ends_all = uniform_samples(near, far, S)
     mids = (starts_all + ends_all) / 2
     smin, smax = mids.min(), mids.max()
     for s in range(0, R, chunk):

@@ -106,3 +106,24 @@ for K in (1, 64):
     s0 = torch.zeros(K, device=dev)
     ms = timeit(lambda: ops.reni_radiance_table(dirs, Z, s0, rblob))
     report(f"reni_decode K={K} D=2048", "tensor", ms, K * 2048 * 524544.0 + K * 657408.0, 524544, K * 2048)
+
+# ---- proposal-network sampler (8f row f1): density field 372 B/sample algorithmic (12 + 5*8*8 gather + 40 features);
+# ---- PDF resampling: reads bins (S+1)*4 + density S*4, writes weights S*4 + new bins/euclid 2*(N+1)*4 per ray --------------------
+from neusky_b200 import proposal as P
+R = 921_600 // 4
+c2 = torch.nn.functional.normalize(torch.randn(R, 3, generator=g), dim=-1)
+o = (torch.tensor([0.0, -0.9, 0.25]) + torch.zeros(R, 3)).to(dev).contiguous()
+d = torch.nn.functional.normalize(-o.cpu() + 0.4 * c2, dim=-1).to(dev).contiguous()
+from neusky_b200.render import sphere_collider
+near, far = (t.reshape(-1).contiguous() for t in sphere_collider(o, d))
+for S, N, mr in ((256, 96, 64), (96, 48, 256)):
+    f = P.HashMLPDensityField(nb_init.init_proposal_params(mr, table_scale=1.0, density_bias=1.0), mr, device=dev)
+    bins = P.uniform_bins(R, S, dev, torch.rand(R, device=dev))
+    ms = timeit(lambda: f.density_on_rays(o, d, near, far, bins))
+    report(f"proposal_density_fwd (P1) S={S} max_res={mr}", "hbm", ms, R * S * 372.0, 372, R * S,
+           {"note": "table 5 MB: gathers are L2/L1 hits; actual HBM traffic is ~8 B/sample", "achieved_actual_GBps": R * S * 8.0 / (ms * 1e-3) / 1e9,
+            "Gsamples_per_s": R * S / (ms * 1e-3) / 1e9})
+    dens = f.density_on_rays(o, d, near, far, bins)
+    ms = timeit(lambda: P.pdf_resample(bins, near, far, N, density=dens))
+    byt = (S + 1) * 4 + S * 4 + S * 4 + 2 * (N + 1) * 4 + 8
+    report(f"pdf_resample (P2) S={S} -> N={N}", "hbm", ms, R * float(byt), byt, R, {"Mrays_per_s": R / (ms * 1e-3) / 1e6})

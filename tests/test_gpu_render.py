@@ -139,3 +139,29 @@ def test_relight_from_cache_equals_rerender(dev, scene):
         fast = r.relight(base["relight_cache"], Zk, sc, rotation=rk)
         assert float((full - fast).abs().max()) <= 2e-5, float((full - fast).abs().max())
     assert float((base["rgb"] - r.relight(base["relight_cache"], scene["Z"].to(dev), sc)).abs().max()) <= 2e-5
+
+
+def test_render_with_proposal_sampler_vs_oracle(dev, scene):
+    """The shipped sample placement (proposal-network sampler 256 -> 96 -> S, neusky_model.py:561) in front of the same path:
+    fp32 kernels vs the oracle's render_rays with the oracle's sampler.  Placement within 5e-5 absolute (bit-exact given equal
+    weights, see tests/test_gpu_sampler.py); rendered outputs within 2e-3 relative (the placement perturbation propagates through
+    the NeuS alpha at inv_s = e^3)."""
+    from oracle import neusky_oracle as O, sampler_oracle as SO
+    from neusky_b200.render import RayRenderer
+
+    nets = [SO.init_proposal_net(21, table_scale=1.0, density_bias=1.0), SO.init_proposal_net(22, table_scale=1.0, density_bias=2.0)]
+    S = 24
+    with torch.no_grad():
+        ref = O.render_rays(scene["o"], scene["d"], scene["dn"], S, scene["sdf_p"], scene["ddf_p"], scene["reni_p"], scene["Z"], torch.zeros(()), scene["dirs"],
+                            float(torch.exp(torch.tensor(3.0))), log2_T=scene["log2_T"], proposal_nets=nets)
+    r = RayRenderer(scene["sdf_p"], scene["ddf_p"], scene["reni_p"], device=dev, log2_T=scene["log2_T"], impl="simt", sdf_impl="simt", proposal_params=nets)
+    r.set_directions(scene["dirs"])
+    o, d, dn = (t.to(dev) for t in (scene["o"], scene["d"], scene["dn"]))
+    out = {k: v.cpu() for k, v in r.render(o, d, dn, S, scene["Z"].to(dev), torch.zeros((), device=dev), want_vis=True).items()}
+    near, far = O.sphere_collider(scene["o"], scene["d"])
+    e_ref, *_ = SO.proposal_sample(scene["o"], scene["d"], near, far, nets, num_final=S)
+    assert float((out["starts"] - torch.from_numpy(e_ref[:, :-1])).abs().max()) <= 5e-5
+    assert not torch.allclose(out["starts"], O.uniform_samples(near, far, S)[0][..., 0], atol=1e-3)      # placement is really non-uniform
+    for k, tol in (("accumulation", 2e-3), ("p2p_dist", 2e-3), ("depth", 2e-3), ("normal", 2e-3), ("albedo", 2e-3), ("rgb", 2e-3)):
+        err = (out[k] - ref[k]).abs().max() / ref[k].abs().max().clamp_min(1e-6)
+        assert float(err) <= tol, (k, float(err))
