@@ -261,6 +261,9 @@ int nsk_gemm_tf32_tn(const float* A, int lda, const float* B, int ldb, float* C,
  *     cond [N,40] = (q, hash(q), 0-pad)   q = sphere exit point (neusky_model.py:1693-1695; directional_distance_field.py:267-268)
  *     xin  [N,16] = (d_local, PE2(d_local), 0-pad) for d = -l in the local frame of q (ddf_model.py:158-200; :270-271)
  *     q    [N,3], term_dist [N] = |q - p| (neusky_model.py:1697-1699)
+ * nsk_ddf_rows_fwd: the same cond / xin for rows that carry their own sphere point and world direction, origins [N,3],
+ *     directions [N,3] -- DDFModel.get_outputs on a sampled ray bundle and its multi-view / sky-ray batches (the DDF fitting
+ *     pass, ddf_model.py:193-217, 279-363).
  * nsk_film_sin_fwd / _bwd: a = sin((15 f + 30) z + phase) with f, phase = columns [layer*256, +256) of the two halves of the
  *     mapping output film [N, ldf] (film_siren.py:66-67, 74-81, 140); bwd writes d z [N,256] and the two column blocks of d film.
  * nsk_ddf_head_fwd: that = 2 r sigmoid(a5 . w + b) (directional_distance_field.py:297-299), vis = 1 - sigmoid(scale *
@@ -271,6 +274,8 @@ int nsk_gemm_tf32_tn(const float* A, int lda, const float* B, int ldb, float* C,
 int nsk_ddf_pairs_fwd(const float* points, int64_t R, const float* dirs, int D, const float* table, const float* scalings,
                       int num_levels, int log2_T, float radius, float* cond, float* xin, float* q, float* term_dist,
                       void* stream);
+int nsk_ddf_rows_fwd(const float* origins, const float* directions, int64_t N, const float* table, const float* scalings,
+                     int num_levels, int log2_T, float* cond, float* xin, void* stream);
 int nsk_film_sin_fwd(const float* z, const float* film, int ldf, int layer, int64_t N, float* a, void* stream);
 int nsk_film_sin_bwd(const float* da, const float* z, const float* film, int ldf, int layer, int64_t N, float* dz,
                      float* dfilm, void* stream);

@@ -23,12 +23,39 @@ namespace train {
 constexpr int COND_LD = 40;   // 3 + 32 padded to a multiple of 8 (tf32 MMA K step)
 constexpr int XIN_LD = 16;    // 15 padded
 
+// cond = q | hash(q) (directional_distance_field.py:267-268), xin = d_local | PE2(d_local) (:270-271) for one row
+__device__ __forceinline__ void ddf_row_inputs(const float q[3], const float d[3], const float2* __restrict__ table,
+                                               const float* __restrict__ scalings, int L, int log2_T,
+                                               float* __restrict__ cr, float* __restrict__ xr) {
+  const uint32_t mask = (1u << log2_T) - 1u;
+  float dl[3], feat[15];
+  ddf_local_dir(q, d, dl);
+  ddf_dir_features(dl, feat);
+#pragma unroll
+  for (int c = 0; c < 15; ++c) xr[c] = feat[c];
+  xr[15] = 0.f;
+  cr[0] = q[0]; cr[1] = q[1]; cr[2] = q[2];
+  for (int lev = 0; lev < L; ++lev) {
+    const float s = scalings[lev];
+    uint32_t idx[8];
+    float ox, oy, oz;
+    hash_corners(__fmul_rn(q[0], s), __fmul_rn(q[1], s), __fmul_rn(q[2], s), mask, idx, ox, oy, oz);
+    const float2* tl = table + ((size_t)lev << log2_T);
+    float2 f[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) f[c] = __ldg(tl + idx[c]);
+    const float2 v = hash_interp(f, ox, oy, oz);
+    cr[3 + 2 * lev] = v.x;
+    cr[4 + 2 * lev] = v.y;
+  }
+  for (int c = 3 + 2 * L; c < COND_LD; ++c) cr[c] = 0.f;
+}
+
 __global__ void __launch_bounds__(128)
 ddf_pairs_fwd_kernel(const float* __restrict__ points, int64_t R, const float* __restrict__ dirs, int D,
                      const float2* __restrict__ table, const float* __restrict__ scalings, int L, int log2_T, float radius,
                      float* __restrict__ cond, float* __restrict__ xin, float* __restrict__ qout, float* __restrict__ gt) {
   const int64_t N = R * D;
-  const uint32_t mask = (1u << log2_T) - 1u;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / D;
     const int j = (int)(i - r * D);
@@ -42,29 +69,21 @@ ddf_pairs_fwd_kernel(const float* __restrict__ points, int64_t R, const float* _
     gt[i] = dist;
     qout[i * 3] = q[0]; qout[i * 3 + 1] = q[1]; qout[i * 3 + 2] = q[2];
     const float dneg[3] = {-l[0], -l[1], -l[2]};
-    float dl[3], feat[15];
-    ddf_local_dir(q, dneg, dl);
-    ddf_dir_features(dl, feat);
-    float* xr = xin + i * XIN_LD;
-#pragma unroll
-    for (int c = 0; c < 15; ++c) xr[c] = feat[c];
-    xr[15] = 0.f;
-    float* cr = cond + i * COND_LD;
-    cr[0] = q[0]; cr[1] = q[1]; cr[2] = q[2];
-    for (int lev = 0; lev < L; ++lev) {
-      const float s = scalings[lev];
-      uint32_t idx[8];
-      float ox, oy, oz;
-      hash_corners(__fmul_rn(q[0], s), __fmul_rn(q[1], s), __fmul_rn(q[2], s), mask, idx, ox, oy, oz);
-      const float2* tl = table + ((size_t)lev << log2_T);
-      float2 f[8];
-#pragma unroll
-      for (int c = 0; c < 8; ++c) f[c] = __ldg(tl + idx[c]);
-      const float2 v = hash_interp(f, ox, oy, oz);
-      cr[3 + 2 * lev] = v.x;
-      cr[4 + 2 * lev] = v.y;
-    }
-    for (int c = 3 + 2 * L; c < COND_LD; ++c) cr[c] = 0.f;
+    ddf_row_inputs(q, dneg, table, scalings, L, log2_T, cond + i * COND_LD, xin + i * XIN_LD);
+  }
+}
+
+// Same network inputs for rows that already carry their own sphere point and world direction: the DDF fitting pass
+// (neusky/models/ddf_model.py:193-217 -- DDFModel.get_outputs on a sampled ray bundle, the multi-view and the sky-ray
+// batches :279-363).
+__global__ void __launch_bounds__(128)
+ddf_rows_fwd_kernel(const float* __restrict__ origins, const float* __restrict__ directions, int64_t N,
+                    const float2* __restrict__ table, const float* __restrict__ scalings, int L, int log2_T,
+                    float* __restrict__ cond, float* __restrict__ xin) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+    const float q[3] = {origins[i * 3], origins[i * 3 + 1], origins[i * 3 + 2]};
+    const float d[3] = {directions[i * 3], directions[i * 3 + 1], directions[i * 3 + 2]};
+    ddf_row_inputs(q, d, table, scalings, L, log2_T, cond + i * COND_LD, xin + i * XIN_LD);
   }
 }
 
@@ -227,6 +246,16 @@ extern "C" int nsk_ddf_pairs_fwd(const float* points, int64_t R, const float* di
   ddf_pairs_fwd_kernel<<<grid_for(R * D, 128, 148 * 16), 128, 0, as_stream(stream)>>>(
       points, R, dirs, D, reinterpret_cast<const float2*>(table), scalings, num_levels, log2_T, radius, cond, xin, q, gt);
   return check_launch("ddf_pairs_fwd_kernel");
+}
+
+extern "C" int nsk_ddf_rows_fwd(const float* origins, const float* directions, int64_t N, const float* table,
+                                const float* scalings, int num_levels, int log2_T, float* cond, float* xin, void* stream) {
+  NSK_REQUIRE(origins && directions && table && scalings && cond && xin, "nsk_ddf_rows_fwd: null pointer");
+  NSK_REQUIRE(num_levels == 16 && log2_T > 0 && log2_T < 31, "nsk_ddf_rows_fwd: hash grid shape");
+  if (N == 0) return 0;
+  ddf_rows_fwd_kernel<<<grid_for(N, 128, 148 * 16), 128, 0, as_stream(stream)>>>(
+      origins, directions, N, reinterpret_cast<const float2*>(table), scalings, num_levels, log2_T, cond, xin);
+  return check_launch("ddf_rows_fwd_kernel");
 }
 
 extern "C" int nsk_film_sin_fwd(const float* z, const float* film, int ldf, int layer, int64_t N, float* a, void* stream) {

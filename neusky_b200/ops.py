@@ -453,6 +453,19 @@ def ddf_pairs(points: Tensor, dirs_sel: Tensor, hash_table: Tensor, scalings: Te
     return cond, xin, q, term
 
 
+def ddf_rows(origins: Tensor, directions: Tensor, hash_table: Tensor, scalings: Tensor, log2_T: int):
+    """(origins [N,3] on the DDF sphere, world directions [N,3]) -> cond [N,40], xin [N,16] (row-wise DDF inputs)."""
+    N = origins.shape[0]
+    origins, directions = _chk("origins", origins, shape=(N, 3)), _chk("directions", directions, shape=(N, 3))
+    L = scalings.numel()
+    hash_table, scalings = _chk("hash_table", hash_table, shape=(L << log2_T, 2)), _chk("scalings", scalings)
+    cond = torch.empty((N, 40), device=origins.device, dtype=torch.float32)
+    xin = torch.empty((N, 16), device=origins.device, dtype=torch.float32)
+    _lib.check(_lib.load().nsk_ddf_rows_fwd(_ptr(origins), _ptr(directions), c_int64(N), _ptr(hash_table), _ptr(scalings), c_int(L), c_int(log2_T),
+                                            _ptr(cond), _ptr(xin), _stream(origins)), "nsk_ddf_rows_fwd")
+    return cond, xin
+
+
 def film_sin(z: Tensor, film: Tensor, layer: int) -> Tensor:
     N = z.shape[0]
     z, film = _chk("z", z, shape=(N, 256)), _chk("film", film, shape=(N, None))

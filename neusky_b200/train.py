@@ -60,28 +60,90 @@ def ddf_param_list(p: Dict[str, Tensor], prefix: str = "ddf.") -> List[Tensor]:
     return out
 
 
+def _ddf_forward_core(cfg: DDFConfig, cond: Tensor, xin: Tensor, term: Tensor, threshold: Tensor, w_final: Tensor, b_final: Tensor, mlp: Sequence[Tensor]):
+    """Mapping network + FiLM-SIREN trunk + head on prepared rows (film_siren.py:45-156, directional_distance_field.py:261-306).
+    Returns (that, vis, tensors the backward needs)."""
+    if len(mlp) != 2 * (DDF_MAP_LAYERS + DDF_TRUNK_LAYERS):
+        raise ValueError(f"DDF network: expected {2 * (DDF_MAP_LAYERS + DDF_TRUNK_LAYERS)} MLP tensors, got {len(mlp)}")
+    sp = cfg.split
+    Wm, bm = mlp[0:2 * DDF_MAP_LAYERS:2], mlp[1:2 * DDF_MAP_LAYERS:2]
+    Wt, bt = mlp[2 * DDF_MAP_LAYERS::2], mlp[2 * DDF_MAP_LAYERS + 1::2]
+    h, hs = cond, []
+    for i in range(DDF_MAP_LAYERS - 1):
+        h = ops.gemm_nt(h, _pad_cols(Wm[i]), bias=bm[i], act="leaky", split=sp)
+        hs.append(h)
+    film = ops.gemm_nt(h, Wm[-1].contiguous(), bias=bm[-1], split=sp)          # [N, 2560]
+    a, zs, acts = xin, [], []
+    for l in range(DDF_TRUNK_LAYERS):
+        z = ops.gemm_nt(a, _pad_cols(Wt[l]), bias=bt[l], split=sp)
+        a = ops.film_sin(z, film, l)
+        zs.append(z)
+        acts.append(a)
+    that, vis = ops.ddf_head(a, w_final, b_final, term, cfg.radius, threshold, cfg.sigmoid_scale)
+    return that, vis, (film, Wm, Wt, hs, zs, acts)
+
+
+def _ddf_backward_core(cfg: DDFConfig, cond, xin, q, term, film, that, threshold, w_final, Wm, Wt, hs, zs, acts, d_vis, d_that,
+                       need_table: bool, need_xin: bool, b_shape):
+    """Backward of `_ddf_forward_core`: gradients for threshold, hash table, final layer, every mapping / trunk weight and
+    (optionally) the trunk input rows xin."""
+    sp = cfg.split
+    dev = cond.device
+    zeros = lambda *s: torch.zeros(s, device=dev, dtype=torch.float32)
+
+    d_wf, d_bf, d_thr = zeros(256), zeros(1), zeros(1)
+    da = ops.ddf_head_bwd(acts[-1], w_final, that, term, None if d_vis is None else d_vis.contiguous(), None if d_that is None else d_that.contiguous(),
+                          cfg.radius, threshold, cfg.sigmoid_scale, d_wf, d_bf, d_thr)
+    dfilm = torch.empty_like(film)
+    dWt: List[Optional[Tensor]] = [None] * DDF_TRUNK_LAYERS
+    dbt: List[Optional[Tensor]] = [None] * DDF_TRUNK_LAYERS
+    d_xin = None
+    for l in reversed(range(DDF_TRUNK_LAYERS)):
+        dz = ops.film_sin_bwd(da, zs[l], film, l, dfilm)
+        a_prev = acts[l - 1] if l > 0 else xin
+        g = zeros(256, a_prev.shape[1])
+        ops.gemm_tn(dz, a_prev, g, split=sp)
+        dWt[l] = g[:, :Wt[l].shape[1]]
+        dbt[l] = ops.colsum(dz, zeros(256))
+        if l > 0:
+            da = ops.gemm_nt(dz, Wt[l].t().contiguous(), split=sp)
+        elif need_xin:
+            d_xin = ops.gemm_nt(dz, _pad_cols(Wt[0]).t().contiguous(), split=sp)          # [N,16]
+    dWm: List[Optional[Tensor]] = [None] * DDF_MAP_LAYERS
+    dbm: List[Optional[Tensor]] = [None] * DDF_MAP_LAYERS
+    g = zeros(*Wm[-1].shape)
+    ops.gemm_tn(dfilm, hs[-1], g, split=sp)
+    dWm[-1] = g
+    dbm[-1] = ops.colsum(dfilm, zeros(film.shape[1]))
+    dz = ops.gemm_nt(dfilm, Wm[-1].t().contiguous(), aux=hs[-1], dact="leaky", split=sp)
+    del dfilm
+    d_table = None
+    for i in reversed(range(DDF_MAP_LAYERS - 1)):
+        h_prev = hs[i - 1] if i > 0 else cond
+        g = zeros(256, h_prev.shape[1])
+        ops.gemm_tn(dz, h_prev, g, split=sp)
+        dWm[i] = g[:, :Wm[i].shape[1]]
+        dbm[i] = ops.colsum(dz, zeros(256))
+        if i > 0:
+            dz = ops.gemm_nt(dz, Wm[i].t().contiguous(), aux=hs[i - 1], dact="leaky", split=sp)
+        elif need_table:
+            L2 = 2 * cfg.scalings.numel()
+            dhash = ops.gemm_nt(dz, Wm[0][:, 3:3 + L2].t().contiguous(), split=sp)     # [N, 32]: d cond[:, 3:35]
+            d_table = ops.hash_encode_bwd(q, cfg.scalings, cfg.log2_T, dhash)
+    grads_mlp: List[Optional[Tensor]] = []
+    for i in range(DDF_MAP_LAYERS):
+        grads_mlp += [dWm[i], dbm[i]]
+    for l in range(DDF_TRUNK_LAYERS):
+        grads_mlp += [dWt[l], dbt[l]]
+    return d_thr.reshape(threshold.shape), d_table, d_wf.reshape(w_final.shape), d_bf.reshape(b_shape), grads_mlp, d_xin
+
+
 class _DDFVisibility(torch.autograd.Function):
     @staticmethod
     def forward(ctx, cfg: DDFConfig, points: Tensor, dirs_sel: Tensor, threshold: Tensor, table: Tensor, w_final: Tensor, b_final: Tensor, *mlp: Tensor):
-        if len(mlp) != 2 * (DDF_MAP_LAYERS + DDF_TRUNK_LAYERS):
-            raise ValueError(f"ddf_visibility: expected {2 * (DDF_MAP_LAYERS + DDF_TRUNK_LAYERS)} MLP tensors, got {len(mlp)}")
-        sp = cfg.split
-        Wm, bm = mlp[0:2 * DDF_MAP_LAYERS:2], mlp[1:2 * DDF_MAP_LAYERS:2]
-        Wt, bt = mlp[2 * DDF_MAP_LAYERS::2], mlp[2 * DDF_MAP_LAYERS + 1::2]
         R, D = points.shape[0], dirs_sel.shape[0]
         cond, xin, q, term = ops.ddf_pairs(points, dirs_sel, table, cfg.scalings, cfg.log2_T, cfg.radius)
-        h, hs = cond, []
-        for i in range(DDF_MAP_LAYERS - 1):
-            h = ops.gemm_nt(h, _pad_cols(Wm[i]), bias=bm[i], act="leaky", split=sp)
-            hs.append(h)
-        film = ops.gemm_nt(h, Wm[-1].contiguous(), bias=bm[-1], split=sp)          # [N, 2560]
-        a, zs, acts = xin, [], []
-        for l in range(DDF_TRUNK_LAYERS):
-            z = ops.gemm_nt(a, _pad_cols(Wt[l]), bias=bt[l], split=sp)
-            a = ops.film_sin(z, film, l)
-            zs.append(z)
-            acts.append(a)
-        that, vis = ops.ddf_head(a, w_final, b_final, term, cfg.radius, threshold, cfg.sigmoid_scale)
+        that, vis, (film, Wm, Wt, hs, zs, acts) = _ddf_forward_core(cfg, cond, xin, term, threshold, w_final, b_final, mlp)
         ctx.cfg = cfg
         ctx.b_shape = b_final.shape
         ctx.n_act = (len(hs), len(zs))
@@ -91,8 +153,6 @@ class _DDFVisibility(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, d_vis, d_that, _dq, _dterm):
-        cfg: DDFConfig = ctx.cfg
-        sp = cfg.split
         sv = ctx.saved_tensors
         cond, xin, q, term, film, that, threshold, w_final = sv[:8]
         o = 8
@@ -101,51 +161,9 @@ class _DDFVisibility(torch.autograd.Function):
         hs = sv[o:o + ctx.n_act[0]]; o += ctx.n_act[0]
         zs = sv[o:o + ctx.n_act[1]]; o += ctx.n_act[1]
         acts = sv[o:o + ctx.n_act[1]]
-        dev = cond.device
-        zeros = lambda *s: torch.zeros(s, device=dev, dtype=torch.float32)
-
-        d_wf, d_bf, d_thr = zeros(256), zeros(1), zeros(1)
-        da = ops.ddf_head_bwd(acts[-1], w_final, that, term, None if d_vis is None else d_vis.contiguous(), None if d_that is None else d_that.contiguous(),
-                              cfg.radius, threshold, cfg.sigmoid_scale, d_wf, d_bf, d_thr)
-        dfilm = torch.empty_like(film)
-        dWt: List[Optional[Tensor]] = [None] * DDF_TRUNK_LAYERS
-        dbt: List[Optional[Tensor]] = [None] * DDF_TRUNK_LAYERS
-        for l in reversed(range(DDF_TRUNK_LAYERS)):
-            dz = ops.film_sin_bwd(da, zs[l], film, l, dfilm)
-            a_prev = acts[l - 1] if l > 0 else xin
-            g = zeros(256, a_prev.shape[1])
-            ops.gemm_tn(dz, a_prev, g, split=sp)
-            dWt[l] = g[:, :Wt[l].shape[1]]
-            dbt[l] = ops.colsum(dz, zeros(256))
-            if l > 0:
-                da = ops.gemm_nt(dz, Wt[l].t().contiguous(), split=sp)
-        dWm: List[Optional[Tensor]] = [None] * DDF_MAP_LAYERS
-        dbm: List[Optional[Tensor]] = [None] * DDF_MAP_LAYERS
-        g = zeros(*Wm[-1].shape)
-        ops.gemm_tn(dfilm, hs[-1], g, split=sp)
-        dWm[-1] = g
-        dbm[-1] = ops.colsum(dfilm, zeros(film.shape[1]))
-        dz = ops.gemm_nt(dfilm, Wm[-1].t().contiguous(), aux=hs[-1], dact="leaky", split=sp)
-        del dfilm
-        d_table = None
-        for i in reversed(range(DDF_MAP_LAYERS - 1)):
-            h_prev = hs[i - 1] if i > 0 else cond
-            g = zeros(256, h_prev.shape[1])
-            ops.gemm_tn(dz, h_prev, g, split=sp)
-            dWm[i] = g[:, :Wm[i].shape[1]]
-            dbm[i] = ops.colsum(dz, zeros(256))
-            if i > 0:
-                dz = ops.gemm_nt(dz, Wm[i].t().contiguous(), aux=hs[i - 1], dact="leaky", split=sp)
-            elif ctx.needs_input_grad[4]:
-                L2 = 2 * cfg.scalings.numel()
-                dhash = ops.gemm_nt(dz, Wm[0][:, 3:3 + L2].t().contiguous(), split=sp)     # [N, 32]: d cond[:, 3:35]
-                d_table = ops.hash_encode_bwd(q, cfg.scalings, cfg.log2_T, dhash)
-        grads_mlp: List[Optional[Tensor]] = []
-        for i in range(DDF_MAP_LAYERS):
-            grads_mlp += [dWm[i], dbm[i]]
-        for l in range(DDF_TRUNK_LAYERS):
-            grads_mlp += [dWt[l], dbt[l]]
-        return (None, None, None, d_thr.reshape(threshold.shape), d_table, d_wf.reshape(w_final.shape), d_bf.reshape(ctx.b_shape), *grads_mlp)
+        d_thr, d_table, d_wf, d_bf, grads_mlp, _ = _ddf_backward_core(ctx.cfg, cond, xin, q, term, film, that, threshold, w_final, Wm, Wt, hs, zs, acts,
+                                                                      d_vis, d_that, ctx.needs_input_grad[4], False, ctx.b_shape)
+        return (None, None, None, d_thr, d_table, d_wf, d_bf, *grads_mlp)
 
 
 def ddf_visibility(cfg: DDFConfig, points: Tensor, dirs_sel: Tensor, threshold: Tensor, table: Tensor, w_final: Tensor, b_final: Tensor,
@@ -154,6 +172,66 @@ def ddf_visibility(cfg: DDFConfig, points: Tensor, dirs_sel: Tensor, threshold: 
     sphere points q [R*D',3], termination_dist [R*D']).  Differentiable w.r.t. threshold, the hash table, the final layer and
     every mapping / trunk weight (`mlp` in `ddf_param_list` order)."""
     return _DDFVisibility.apply(cfg, points, dirs_sel, threshold, table, w_final, b_final, *mlp)
+
+
+def ddf_row_features_torch(origins: Tensor, directions: Tensor) -> Tensor:
+    """Local-frame direction and its NeRF encoding for DDF rows in torch ops ([N,15]): only used to carry the cotangent of
+    the trunk input back to `directions` when those depend on another network (multi-view batch with
+    stop_sdf_gradients=False, ddf_model.py:286-307).  ddf_model.py:158-200, directional_distance_field.py:270-271."""
+    y = -origins
+    x = torch.stack([-y[:, 1], y[:, 0], torch.zeros_like(y[:, 0])], dim=-1)
+    x = x / x.norm(dim=-1, keepdim=True)
+    z = torch.linalg.cross(y, x)
+    z = z / z.norm(dim=-1, keepdim=True)
+    dl = torch.stack([(x * directions).sum(-1), (y * directions).sum(-1), (z * directions).sum(-1)], dim=-1)
+    ang = (2.0 * torch.pi * dl)[:, :, None] * dl.new_tensor([1.0, 4.0])                      # [N,3,2]
+    ang = ang.reshape(-1, 6)
+    return torch.cat([dl, torch.sin(ang), torch.sin(ang + torch.pi / 2.0)], dim=-1)
+
+
+class _DDFRows(torch.autograd.Function):
+    """DDFModel.get_outputs -> DirectionalDistanceField.forward on rows (origin on the sphere, world direction):
+    expected termination distance [N] (ddf_model.py:193-219)."""
+
+    @staticmethod
+    def forward(ctx, cfg: DDFConfig, origins: Tensor, directions: Tensor, table: Tensor, w_final: Tensor, b_final: Tensor, *mlp: Tensor):
+        origins, directions = origins.contiguous(), directions.contiguous()
+        cond, xin = ops.ddf_rows(origins, directions, table, cfg.scalings, cfg.log2_T)
+        term = torch.zeros(origins.shape[0], device=origins.device, dtype=torch.float32)        # visibility head unused here
+        thr = torch.zeros((), device=origins.device, dtype=torch.float32)
+        that, _vis, (film, Wm, Wt, hs, zs, acts) = _ddf_forward_core(cfg, cond, xin, term, thr, w_final, b_final, mlp)
+        ctx.cfg = cfg
+        ctx.b_shape = b_final.shape
+        ctx.n_act = (len(hs), len(zs))
+        ctx.save_for_backward(cond, xin, origins, directions, term, film, that, thr, w_final, *Wm, *Wt, *hs, *zs, *acts)
+        return that
+
+    @staticmethod
+    def backward(ctx, d_that):
+        sv = ctx.saved_tensors
+        cond, xin, origins, directions, term, film, that, thr, w_final = sv[:9]
+        o = 9
+        Wm = sv[o:o + DDF_MAP_LAYERS]; o += DDF_MAP_LAYERS
+        Wt = sv[o:o + DDF_TRUNK_LAYERS]; o += DDF_TRUNK_LAYERS
+        hs = sv[o:o + ctx.n_act[0]]; o += ctx.n_act[0]
+        zs = sv[o:o + ctx.n_act[1]]; o += ctx.n_act[1]
+        acts = sv[o:o + ctx.n_act[1]]
+        need_dir = ctx.needs_input_grad[2]
+        _, d_table, d_wf, d_bf, grads_mlp, d_xin = _ddf_backward_core(ctx.cfg, cond, xin, origins, term, film, that, thr, w_final, Wm, Wt, hs, zs, acts,
+                                                                      None, d_that, ctx.needs_input_grad[3], need_dir, ctx.b_shape)
+        d_dir = None
+        if need_dir:
+            with torch.enable_grad():
+                dd = directions.detach().requires_grad_(True)
+                feat = ddf_row_features_torch(origins.detach(), dd)
+                (d_dir,) = torch.autograd.grad(feat, dd, d_xin[:, :15])
+        return (None, None, d_dir, d_table, d_wf, d_bf, *grads_mlp)
+
+
+def ddf_termination(cfg: DDFConfig, origins: Tensor, directions: Tensor, table: Tensor, w_final: Tensor, b_final: Tensor, mlp: Sequence[Tensor]) -> Tensor:
+    """Row-wise DDF: origins [N,3] on the sphere, world directions [N,3] -> expected termination distance [N].
+    Differentiable w.r.t. the DDF hash table, final layer, every mapping / trunk weight, and `directions`."""
+    return _DDFRows.apply(cfg, origins, directions, table, w_final, b_final, *mlp)
 
 
 # =====================================================================================================================

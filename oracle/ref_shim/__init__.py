@@ -245,8 +245,18 @@ class Field(nn.Module):
         return self.get_outputs(ray_samples)
 
 
+def _scale_dict(dictionary, coefficients):
+    """nerfstudio.utils.misc.scale_dict [NS-mem]: multiply the entries that have a coefficient, in place."""
+    for key in dictionary:
+        if key in coefficients:
+            dictionary[key] *= coefficients[key]
+    return dictionary
+
+
 def _populate(module: types.ModuleType) -> None:
     real = {
+        "nerfstudio.utils.misc": dict(scale_dict=_scale_dict),
+        "nerfstudio.utils": dict(misc=types.SimpleNamespace(scale_dict=_scale_dict)),   # `from nerfstudio.utils import misc`
         "nerfstudio.cameras.rays": dict(Frustums=Frustums, RaySamples=RaySamples, RayBundle=RayBundle),
         "nerfstudio.field_components.encodings": dict(NeRFEncoding=NeRFEncoding),
         "nerfstudio.field_components.field_heads": dict(FieldHeadNames=FieldHeadNames),

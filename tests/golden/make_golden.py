@@ -206,9 +206,66 @@ def golden_lambert():
     save("lambert", albedo=albedo, normals=normals, dirs=dirs, light=light, visibility=vis, bg=bg, weights=w, rgb=rgb)
 
 
+# ------------------------------------------------------------------------------ DDF fitting pass (samplers, DDFModel training outputs + losses)
+DDF_FIT_SDF_SEED = 3
+DDF_FIT_LOG2_T_SDF = 14
+
+
+def golden_ddf_fit():
+    from neusky.model_components.ddf_sampler import UniformDDFSampler, UniformDDFSamplerConfig, VMFDDFSampler, VMFDDFSamplerConfig
+    from neusky.models.ddf_model import DDFModel
+    from nerfstudio.cameras.rays import RayBundle
+    from oracle import neusky_oracle as O
+
+    # --- samplers under a fixed torch CPU seed (ddf_sampler.py:119-286; NeuSky config neusky_config.py:207-212)
+    vmf = VMFDDFSampler(VMFDDFSamplerConfig(num_samples_on_sphere=8, num_rays_per_sample=128, only_sample_upper_hemisphere=True, concentration=20.0))
+    torch.manual_seed(2024)
+    rb_v = vmf()
+    uni = UniformDDFSampler(UniformDDFSamplerConfig(num_samples_on_sphere=4, num_rays_per_sample=16, only_sample_upper_hemisphere=True))
+    torch.manual_seed(2025)
+    rb_u = uni()
+
+    # --- DDFModel.get_outputs (training) + get_loss_dict with the NeuSky loss configuration (neusky_config.py:178-205)
+    field, params = build_reference_ddf()
+    inclusions = {"depth_l1_loss": True, "depth_l2_loss": False, "sdf_l1_loss": False, "sdf_l2_loss": True, "prob_hit_loss": False,
+                  "normal_loss": False, "multi_view_loss": True, "sky_ray_loss": True}
+    coefficients = {"depth_l1_loss": 1.0, "depth_l2_loss": 0.0, "sdf_l1_loss": 1.0, "sdf_l2_loss": 0.01, "prob_hit_loss": 0.01,
+                    "normal_loss": 1.0, "multi_view_loss": 0.01, "sky_ray_loss": 1.0}
+    ddf_self = types.SimpleNamespace(
+        field=field, training=True, ddf_radius=1.0,
+        config=types.SimpleNamespace(compute_normals=False, include_depth_loss_scene_center_weight=True, scene_center_weight_exp=3.0,
+                                     scene_center_weight_include_z=False, mask_to_circumference=False, inverse_depth_weight=False,
+                                     loss_inclusions=inclusions, loss_coefficients=coefficients),
+        depth_l1_loss=torch.nn.L1Loss(reduction="none"), sdf_l2_loss=torch.nn.MSELoss(), sky_ray_loss=torch.nn.L1Loss(),
+    )
+    ddf_self.get_localised_transforms = lambda pos: DDFModel.get_localised_transforms(ddf_self, pos)
+    sdf_p = nb_init.init_sdf_params(DDF_FIT_SDF_SEED, log2_T=DDF_FIT_LOG2_T_SDF)
+    sca = O.hash_scalings()
+    neusky = types.SimpleNamespace(field=types.SimpleNamespace(
+        get_sdf_at_pos=lambda x: O.sdf_geo_network(x, sdf_p, sca, DDF_FIT_LOG2_T_SDF)[:, :1]))   # nerfstudio SDFField: restated, unpinned
+    g = torch.Generator().manual_seed(31)
+    N = 256
+    origins, directions = rb_v.origins[:N].clone(), rb_v.directions[:N].clone()
+    term = 0.3 + 1.5 * torch.rand(N, 1, generator=g)
+    mask = (torch.rand(N, 1, generator=g) > 0.25).float()
+    n_sky = 48
+    sky_o = torch.tensor([0.0, -0.6, 0.1]).expand(n_sky, 3) + 0.1 * torch.randn(n_sky, 3, generator=g)
+    sky_d = torch.nn.functional.normalize(torch.randn(n_sky, 3, generator=g) + torch.tensor([0.0, 0.0, 1.0]), dim=-1)
+    batch = {"termination_dist": term, "mask": mask, "sky_ray_bundle": RayBundle(origins=sky_o, directions=sky_d, pixel_area=torch.ones(n_sky, 1))}
+    MV_SEED = 77
+    torch.manual_seed(MV_SEED)          # the multi-view points are the first draw inside get_outputs (ddf_model.py:289)
+    with torch.no_grad():
+        out = DDFModel.get_outputs(ddf_self, RayBundle(origins=origins, directions=directions, pixel_area=torch.ones(N, 1)), batch, neusky, False)
+        losses = DDFModel.get_loss_dict(ddf_self, out, batch)
+    save("ddf_fit", seed=DDF_SEED, final_gain=DDF_FINAL_GAIN, weights_sha256=checksum(params), sdf_seed=DDF_FIT_SDF_SEED, sdf_log2_T=DDF_FIT_LOG2_T_SDF,
+         vmf_seed=2024, vmf_origins=rb_v.origins, vmf_directions=rb_v.directions, uniform_seed=2025, uniform_origins=rb_u.origins, uniform_directions=rb_u.directions,
+         origins=origins, directions=directions, termination_dist=term, mask=mask, sky_origins=sky_o, sky_directions=sky_d, multi_view_seed=MV_SEED,
+         **{"out_" + k: v for k, v in out.items()}, **{"loss_" + k: v for k, v in losses.items()})
+
+
 if __name__ == "__main__":
+    only = sys.argv[1:]
     torch.manual_seed(0)
-    golden_icosphere()
-    golden_lambert()
-    golden_reni()
-    golden_ddf_and_visibility()
+    for fn in (golden_icosphere, golden_lambert, golden_reni, golden_ddf_and_visibility, golden_ddf_fit):
+        if not only or fn.__name__ in only:
+            fn()
