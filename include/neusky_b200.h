@@ -345,6 +345,32 @@ int nsk_density_weights_bwd(const float* bins, const float* density, const float
 int nsk_interlevel_loss(const float* c, const float* w, int Sf, const float* cp, const float* wp, int Sp, int64_t R,
                         float* loss_ray, float* g_wp, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Light-sum shaders (csrc/shaders.cu): ns_reni's inverse-rendering shaders and NeuSky's Blinn-Phong renderer branch.
+ * Replaces  reni.model_components.shaders.LambertianShader.forward   (ns_reni/reni/model_components/shaders.py:25-70)   mode 0
+ *           reni.model_components.shaders.BlinnPhongShader.forward   (ns_reni/reni/model_components/shaders.py:73-161)  mode 1
+ *           RGBBlinnPhongRendererWithVisibility.render_and_combine_rgb light sum (neusky/model_components/renderers.py:199-241) mode 2
+ * Rows i < N are pixels (modes 0, 1) or ray samples (mode 2).  albedo, normals, specular, view_dirs [N,3]; shininess [N];
+ * dirs [M,3] shared by all rows (dirs_per_row = 0) or [N,M,3]; radiance [K,M,3] with cam [N] -> K (NULL = row 0 for all);
+ * vis [ceil(N / rows_per_vis), M] (NULL = 1; mode 2).
+ *   mode 0: out_a = sum_j max(n.l_j, 0) L_j              out_b = albedo * out_a
+ *   mode 1: out_a = max(albedo * sum_j max(n.l_j,0) L_j + specular * (s+2)/(4(2-exp(-s/2))) * sum_j max(n.h_j,0)^s L_j, 1e-3),
+ *           h_j = (l_j + v) / (|l_j + v| + 1e-8)
+ *   mode 2: out_a = sum_j L_j vis_j (albedo * clamp01(n.l_j) + clamp01(n.h_j)^s),  h_j = (l_j + v) / |l_j + v|;
+ *           with weights [N] and rgb_lin [N/S,3] (zero-filled): rgb_lin[i / S] += weights[i] * out_a[i]  (renderers.py:247).
+ * nsk_shade_lights_bwd: cotangents g_a (on out_a), g_b (on out_b, mode 0; either may be NULL) -> d_albedo, d_normals, d_specular
+ *   [N,3], d_shininess [N] (overwritten; NULL = skip) and d_radiance [K,M,3], d_vis (ACCUMULATED INTO; NULL = skip).
+ * ------------------------------------------------------------------------------------------- */
+int nsk_shade_lights_fwd(int mode, const float* albedo, const float* normals, const float* specular, const float* shininess,
+                         const float* view_dirs, const float* dirs, int dirs_per_row, int normalize_dirs, const float* radiance,
+                         const int* cam, const float* vis, int rows_per_vis, int64_t N, int M, float* out_a, float* out_b,
+                         const float* weights, float* rgb_lin, int S, void* stream);
+int nsk_shade_lights_bwd(int mode, const float* albedo, const float* normals, const float* specular, const float* shininess,
+                         const float* view_dirs, const float* dirs, int dirs_per_row, int normalize_dirs, const float* radiance,
+                         const int* cam, const float* vis, int rows_per_vis, int64_t N, int M, const float* g_a, const float* g_b,
+                         float* d_albedo, float* d_normals, float* d_specular, float* d_shininess, float* d_radiance,
+                         float* d_vis, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -585,3 +585,69 @@ def rowdot256(X: Tensor, w: Tensor, b: Optional[Tensor] = None) -> Tensor:
     out = torch.empty((n,), device=X.device, dtype=torch.float32)
     _lib.check(_lib.load().nsk_rowdot256(_ptr(X), _ptr(w), _ptr(b), c_int64(n), _ptr(out), _stream(X)), "nsk_rowdot256")
     return out
+
+
+# ------------------------------------------------------------------------------------------- light-sum shaders (csrc/shaders.cu)
+def _shade_args(mode: int, albedo, normals, specular, shininess, view_dirs, dirs, radiance, cam, vis):
+    N = albedo.shape[0]
+    albedo, normals = _chk("albedo", albedo, shape=(N, 3)), _chk("normals", normals, shape=(N, 3))
+    per_row = dirs.dim() == 3
+    M = dirs.shape[-2]
+    dirs = _chk("light_directions", dirs, shape=(N, M, 3) if per_row else (M, 3))
+    radiance = _chk("radiance", radiance, shape=(None, M, 3))
+    if cam is not None:
+        cam = _chk("cam", cam, dtype=torch.int32, shape=(N,))
+    elif radiance.shape[0] != 1:
+        raise ValueError("radiance has several light tables but no row -> table index (cam) was given")
+    if mode >= 1:
+        shininess, view_dirs = _chk("shininess", shininess, shape=(N,)), _chk("view_directions", view_dirs, shape=(N, 3))
+    if mode == 1:
+        specular = _chk("specular", specular, shape=(N, 3))
+    rows_per_vis = 1
+    if vis is not None:
+        if vis.dim() != 2 or vis.shape[1] != M or vis.shape[0] == 0 or N % vis.shape[0] != 0:
+            raise ValueError(f"visibility: expected [N / S, {M}] with N = {N} a multiple of its rows, got {tuple(vis.shape)}")
+        vis = _chk("visibility", vis)
+        rows_per_vis = N // vis.shape[0]
+    return N, M, per_row, albedo, normals, specular, shininess, view_dirs, dirs, radiance, cam, vis, rows_per_vis
+
+
+def shade_lights(mode: int, albedo: Tensor, normals: Tensor, dirs: Tensor, radiance: Tensor, cam: Optional[Tensor] = None, specular: Optional[Tensor] = None,
+                 shininess: Optional[Tensor] = None, view_dirs: Optional[Tensor] = None, vis: Optional[Tensor] = None, normalize_dirs: bool = False,
+                 weights: Optional[Tensor] = None, rgb_lin: Optional[Tensor] = None):
+    """Per-row light sums (see include/neusky_b200.h, nsk_shade_lights_fwd).  Returns (out_a, out_b | None)."""
+    N, M, per_row, albedo, normals, specular, shininess, view_dirs, dirs, radiance, cam, vis, rpv = _shade_args(
+        mode, albedo, normals, specular, shininess, view_dirs, dirs, radiance, cam, vis)
+    out_a = torch.empty((N, 3), device=albedo.device, dtype=torch.float32)
+    out_b = torch.empty((N, 3), device=albedo.device, dtype=torch.float32) if mode == 0 else None
+    S = 0
+    if weights is not None and rgb_lin is not None:
+        weights = _chk("weights", weights.reshape(-1), shape=(N,))
+        rgb_lin = _chk("rgb_lin", rgb_lin, shape=(None, 3))
+        if rgb_lin.shape[0] == 0 or N % rgb_lin.shape[0] != 0:
+            raise ValueError("rgb_lin rows must divide the number of samples")
+        S = N // rgb_lin.shape[0]
+    _lib.check(_lib.load().nsk_shade_lights_fwd(c_int(mode), _ptr(albedo), _ptr(normals), _ptr(specular), _ptr(shininess), _ptr(view_dirs), _ptr(dirs), c_int(int(per_row)),
+                                                c_int(int(normalize_dirs)), _ptr(radiance), _ptr(cam), _ptr(vis), c_int(rpv), c_int64(N), c_int(M), _ptr(out_a), _ptr(out_b),
+                                                _ptr(weights if S else None), _ptr(rgb_lin if S else None), c_int(S), _stream(albedo)), "nsk_shade_lights_fwd")
+    return out_a, out_b
+
+
+def shade_lights_bwd(mode: int, albedo: Tensor, normals: Tensor, dirs: Tensor, radiance: Tensor, g_a: Optional[Tensor], g_b: Optional[Tensor] = None,
+                     cam: Optional[Tensor] = None, specular: Optional[Tensor] = None, shininess: Optional[Tensor] = None, view_dirs: Optional[Tensor] = None,
+                     vis: Optional[Tensor] = None, normalize_dirs: bool = False, want_radiance: bool = True, want_vis: bool = True):
+    """Backward of shade_lights: (d_albedo, d_normals, d_specular | None, d_shininess | None, d_radiance | None, d_vis | None)."""
+    N, M, per_row, albedo, normals, specular, shininess, view_dirs, dirs, radiance, cam, vis, rpv = _shade_args(
+        mode, albedo, normals, specular, shininess, view_dirs, dirs, radiance, cam, vis)
+    dev = albedo.device
+    g_a = None if g_a is None else _chk("g_a", g_a, shape=(N, 3))
+    g_b = None if g_b is None else _chk("g_b", g_b, shape=(N, 3))
+    d_alb, d_nrm = torch.empty((N, 3), device=dev), torch.empty((N, 3), device=dev)
+    d_spec = torch.empty((N, 3), device=dev) if mode == 1 else None
+    d_shin = torch.empty((N,), device=dev) if mode >= 1 else None
+    d_rad = torch.zeros_like(radiance) if want_radiance else None
+    d_vis = torch.zeros_like(vis) if (want_vis and vis is not None and mode == 2) else None
+    _lib.check(_lib.load().nsk_shade_lights_bwd(c_int(mode), _ptr(albedo), _ptr(normals), _ptr(specular), _ptr(shininess), _ptr(view_dirs), _ptr(dirs), c_int(int(per_row)),
+                                                c_int(int(normalize_dirs)), _ptr(radiance), _ptr(cam), _ptr(vis), c_int(rpv), c_int64(N), c_int(M), _ptr(g_a), _ptr(g_b),
+                                                _ptr(d_alb), _ptr(d_nrm), _ptr(d_spec), _ptr(d_shin), _ptr(d_rad), _ptr(d_vis), _stream(albedo)), "nsk_shade_lights_bwd")
+    return d_alb, d_nrm, d_spec, d_shin, d_rad, d_vis

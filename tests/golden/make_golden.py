@@ -263,9 +263,65 @@ def golden_ddf_fit():
          **{"out_" + k: v for k, v in out.items()}, **{"loss_" + k: v for k, v in losses.items()})
 
 
+# ------------------------------------------------------------------------------ light-sum shaders (values + autograd gradients)
+def golden_shaders():
+    from reni.model_components.shaders import BlinnPhongShader, LambertianShader
+    from neusky.model_components.renderers import RGBBlinnPhongRendererWithVisibility
+
+    g = torch.Generator().manual_seed(61)
+    N, M, K = 70, 37, 3
+    leaf = lambda t: t.clone().requires_grad_(True)
+    albedo = leaf(torch.rand(N, 3, generator=g))
+    normals = leaf(torch.nn.functional.normalize(torch.randn(N, 3, generator=g), dim=-1))
+    dirs = torch.nn.functional.normalize(torch.randn(M, 3, generator=g), dim=-1)
+    table = leaf(torch.exp(0.5 * torch.randn(K, M, 3, generator=g)))
+    cam = torch.randint(0, K, (N,), generator=g)
+    specular = leaf(torch.rand(N, 3, generator=g))
+    shininess = leaf(1.5 + 30.0 * torch.rand(N, generator=g))
+    view = torch.nn.functional.normalize(torch.randn(N, 3, generator=g), dim=-1)
+    cot = torch.randn(N, 3, generator=g)
+    cot2 = torch.randn(N, 3, generator=g)
+    out = dict(albedo=albedo, normals=normals, dirs=dirs, table=table, cam=cam, specular=specular, shininess=shininess, view=view, cot=cot, cot2=cot2)
+    leaves = dict(albedo=albedo, normals=normals, table=table, specular=specular, shininess=shininess)
+
+    def grads(prefix, loss, names):
+        gs = torch.autograd.grad(loss, [leaves[n] for n in names], allow_unused=True, retain_graph=True)
+        for n, gr in zip(names, gs):
+            out[f"{prefix}_d_{n}"] = torch.zeros_like(leaves[n]) if gr is None else gr
+
+    ld, lc = dirs[None].expand(N, M, 3), table[cam]
+    s0, rgb0 = LambertianShader.forward(albedo, normals, ld, lc, detach_normals=False)
+    out["lambert_sum"], out["lambert_rgb"] = s0, rgb0
+    grads("lambert", (s0 * cot).sum() + (rgb0 * cot2).sum(), ["albedo", "normals", "table"])
+
+    bp = BlinnPhongShader.forward(albedo, normals, ld, lc, specular, shininess, view, detach_normals=False, normalize_directions=False)
+    out["blinn_phong"] = bp
+    grads("blinn_phong", (bp * cot).sum(), ["albedo", "normals", "table", "specular", "shininess"])
+    bp_n = BlinnPhongShader.forward(albedo, normals, 1.7 * dirs[None], table[:1], specular, shininess, view, normalize_directions=True)
+    out["blinn_phong_normalized_broadcast"] = bp_n
+
+    # --- NeuSky's renderer: R rays x S samples, visibility per ray repeated over the samples (neusky_model.py:1755-1759)
+    R, S = 10, 7
+    assert R * S == N
+    vis_ray = leaf(torch.rand(R, M, generator=g))
+    weights = leaf(torch.rand(R, S, 1, generator=g) / S)
+    bg = torch.rand(R, 3, generator=g)
+    c2w = torch.randn(R, 3, 4, generator=g)
+    c2w_s = c2w[:, None].expand(R, S, 3, 4).contiguous()
+    leaves.update(vis_ray=vis_ray, weights=weights)
+    ren = RGBBlinnPhongRendererWithVisibility()
+    ren.train()
+    rgb = ren(albedos=albedo.view(R, S, 3), normals=normals.view(R, S, 3), light_directions=ld, light_colors=lc,
+              visibility=vis_ray[:, None].expand(R, S, M).reshape(N, M, 1), background_illumination=bg, weights=weights,
+              shininess=shininess.view(R, S, 1), c2w_matrices=c2w_s)
+    out.update(ren_vis=vis_ray, ren_weights=weights, ren_bg=bg, ren_c2w=c2w, ren_rgb=rgb, ren_cot=cot[:R])
+    grads("ren", (rgb * cot[:R]).sum(), ["albedo", "normals", "table", "shininess", "vis_ray", "weights"])
+    save("shaders", **out)
+
+
 if __name__ == "__main__":
     only = sys.argv[1:]
     torch.manual_seed(0)
-    for fn in (golden_icosphere, golden_lambert, golden_reni, golden_ddf_and_visibility, golden_ddf_fit):
+    for fn in (golden_icosphere, golden_lambert, golden_reni, golden_ddf_and_visibility, golden_ddf_fit, golden_shaders):
         if not only or fn.__name__ in only:
             fn()
