@@ -17,8 +17,21 @@ Tensor = torch.Tensor
 c_void_p, c_int, c_int64, c_float = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float
 
 
+_EMPTY_SENTINEL: Dict[torch.device, Tensor] = {}
+
+
 def _ptr(t: Optional[Tensor]):
-    return c_void_p(0 if t is None else t.data_ptr())
+    """Device address of `t` (NULL for None).  An EMPTY tensor has no storage (data_ptr() == 0), which the C ABI would take
+    for a missing argument; it gets the address of a 16-byte sentinel instead -- never dereferenced, the ops return before
+    launching when a count is zero."""
+    if t is None:
+        return c_void_p(0)
+    if t.numel() == 0 and t.is_cuda:
+        s = _EMPTY_SENTINEL.get(t.device)
+        if s is None:
+            s = _EMPTY_SENTINEL[t.device] = torch.zeros(4, device=t.device, dtype=torch.float32)
+        return c_void_p(s.data_ptr())
+    return c_void_p(t.data_ptr())
 
 
 def _stream(t: Tensor):

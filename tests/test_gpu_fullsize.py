@@ -1,0 +1,133 @@
+"""BASELINE.json configs[1] at its FULL size (1,000,000 surface points x 2048 equirect directions, D' = 1024 through the DDF)
+checked through size-independent properties, plus the empty / ragged edge cases of the C-ABI ops.
+
+The CPU oracle needs ~6 ms per point at this direction count, so at full size it checks a random 192-point sample; the rest of
+the million points is covered by properties that hold for the reference's arithmetic whatever the size:
+  * tile / order invariance: a point's colour does not depend on which other points are in the batch or where it sits in it;
+  * linearity in the light: shading under radiance L1 + L2 equals the sum of the two shadings (same visibility), and
+    scaling the albedo scales the linear colour (renderers.py:93-113 is bilinear in albedo and light colours);
+  * zero light -> zero colour; visibility bounds [0, 1].
+Tolerances: the tensor-core path computes the DDF in fp16 x fp16 -> fp32, identical in both runs of a pair, so the pairwise
+properties hold to fp32 summation-order noise (2e-5 relative); the oracle sample uses the stated K4 tolerance (5e-3 sRGB).
+"""
+import pytest
+import torch
+
+from neusky_b200 import init as nb_init
+
+pytestmark = pytest.mark.gpu
+
+N_FULL = 1_000_000
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from neusky_b200 import _lib
+
+    _lib.load()
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def full(dev):
+    from neusky_b200.render import SkyShader
+    from oracle import neusky_oracle as O
+
+    ddf = nb_init.init_ddf_params(7, final_gain=8.0)
+    reni = nb_init.init_reni_params(8)
+    dirs = O.equirect_directions(64)                     # 32 x 64 = 2048 directions, 1024 with z > 0
+    g = torch.Generator().manual_seed(1)
+    pts = torch.nn.functional.normalize(torch.randn(N_FULL, 3, generator=g), dim=-1) * torch.rand(N_FULL, 1, generator=g) ** (1 / 3) * 0.95
+    nrm = torch.nn.functional.normalize(torch.randn(N_FULL, 3, generator=g), dim=-1)
+    alb = torch.rand(N_FULL, 3, generator=g)
+    Z = torch.randn(1, 100, 3, generator=g)
+    sh = SkyShader(ddf, reni, device=dev)
+    sh.set_directions(dirs)
+    rad = sh.radiance_table(Z.to(dev), torch.zeros(1, device=dev))
+    return dict(sh=sh, ddf=ddf, reni=reni, dirs=dirs, pts=pts.to(dev), nrm=nrm.to(dev), alb=alb.to(dev), Z=Z, rad=rad, O=O)
+
+
+def _lin(f, rad, idx=None, alb_scale=1.0):
+    pts, nrm, alb = f["pts"], f["nrm"], f["alb"]
+    if idx is not None:
+        pts, nrm, alb = pts[idx].contiguous(), nrm[idx].contiguous(), alb[idx].contiguous()
+    n = pts.shape[0]
+    return f["sh"].shade(pts, nrm.reshape(n, 1, 3), (alb * alb_scale).reshape(n, 1, 3), rad)["rgb_lin"]
+
+
+def test_full_size_matches_oracle_on_a_sample(full, dev):
+    from neusky_b200 import ops
+
+    O = full["O"]
+    lin = _lin(full, full["rad"])
+    assert lin.shape == (N_FULL, 3) and bool(torch.isfinite(lin).all())
+    rgb = ops.shade_finalize(lin, torch.zeros(N_FULL, 3, device=dev), torch.ones(N_FULL, device=dev))
+    g = torch.Generator().manual_seed(5)
+    idx = torch.randint(0, N_FULL, (192,), generator=g)
+    with torch.no_grad():
+        rad_cpu = O.reni_radiance_table(full["dirs"], full["Z"], torch.zeros(1), full["reni"])[0]
+        ref_lin, _ = O.shade_points(full["pts"][idx.to(dev)].cpu(), full["nrm"][idx.to(dev)].cpu(), full["alb"][idx.to(dev)].cpu(), full["dirs"], rad_cpu,
+                                    full["ddf"], O.hash_scalings(), 19, 1.0, 0.1, 25.0)
+        ref = O.linear_to_srgb(ref_lin)
+    assert float((rgb[idx.to(dev)].cpu() - ref).abs().max()) <= 5e-3
+    full["lin_full"] = lin
+
+
+def test_full_size_order_and_batch_invariance(full, dev):
+    lin = full.get("lin_full")
+    if lin is None:
+        lin = _lin(full, full["rad"])
+    g = torch.Generator().manual_seed(6)
+    idx = torch.randperm(N_FULL, generator=g)[:300_001].to(dev)          # ragged: not a multiple of the 128-pair tile
+    sub = _lin(full, full["rad"], idx)
+    ref = lin[idx]
+    assert float((sub - ref).abs().max()) <= 2e-5 * float(ref.abs().max())
+
+
+def test_full_size_linearity_in_light_and_albedo(full, dev):
+    lin = full.get("lin_full")
+    if lin is None:
+        lin = _lin(full, full["rad"])
+    g = torch.Generator(device="cpu").manual_seed(7)
+    split = torch.rand(full["rad"].shape, generator=g).to(dev)
+    l1, l2 = full["rad"] * split, full["rad"] * (1.0 - split)
+    a, b = _lin(full, l1.contiguous()), _lin(full, l2.contiguous())
+    scale = float(lin.abs().max())
+    assert float((a + b - lin).abs().max()) <= 3e-5 * scale
+    half = _lin(full, full["rad"], alb_scale=0.5)
+    assert float((2.0 * half - lin).abs().max()) <= 3e-5 * scale
+    zero = _lin(full, torch.zeros_like(full["rad"]))
+    assert float(zero.abs().max()) == 0.0
+
+
+def test_visibility_bounds_and_lower_hemisphere(full, dev):
+    sh = full["sh"]
+    n = 4099                                                             # ragged
+    out = sh.shade(full["pts"][:n].contiguous(), full["nrm"][:n].reshape(n, 1, 3).contiguous(), full["alb"][:n].reshape(n, 1, 3).contiguous(), full["rad"], want_vis=True)
+    vis = out["visibility"]
+    assert vis.shape == (n, 2048) and float(vis.min()) >= 0.0 and float(vis.max()) <= 1.0
+    assert bool((vis[:, ~sh.mask] == 1.0).all())                         # lower hemisphere forced visible (neusky_model.py:1745-1753)
+
+
+def test_empty_inputs(dev):
+    """R = 0 / N = 0: every op returns empty outputs of the right shape without launching."""
+    from neusky_b200 import ops
+    from neusky_b200 import train as T
+    from oracle import neusky_oracle as O
+
+    sca = O.hash_scalings().to(dev)
+    table = torch.zeros(16 << 12, 2, device=dev)
+    e3 = torch.zeros(0, 3, device=dev)
+    assert ops.hash_encode(e3, table, sca, 12).shape == (0, 32)
+    assert ops.surface_points(e3, e3, torch.zeros(0, device=dev), 1.0).shape == (0, 3)
+    assert ops.gemm_nt(torch.zeros(0, 16, device=dev), torch.zeros(8, 16, device=dev)).shape == (0, 8)
+    cond, xin = ops.ddf_rows(e3, e3, table, sca, 12)
+    assert cond.shape == (0, 40) and xin.shape == (0, 16)
+    a, b = ops.shade_lights(0, e3, e3, torch.rand(5, 3, device=dev), torch.rand(1, 5, 3, device=dev))
+    assert a.shape == (0, 3) and b.shape == (0, 3)
+    ddf_p = {k: v.to(dev) for k, v in nb_init.init_ddf_params(5, log2_T=12).items()}
+    cfg = T.DDFConfig(scalings=sca, log2_T=12, split=3)
+    that = T.ddf_termination(cfg, e3, e3, ddf_p["position_encoding.hash_table"], ddf_p["ddf.final_layer.weight"], ddf_p["ddf.final_layer.bias"], T.ddf_param_list(ddf_p))
+    assert that.shape == (0,)
