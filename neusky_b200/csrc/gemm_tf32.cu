@@ -8,14 +8,16 @@
 // (neusky/fields/sdf_albedo_field.py:185-269) and the FiLM-SIREN DDF (ns_reni/reni/field_components/film_siren.py:45-156)
 // in the training step; the fused forward-only kernels (sdf_field_tc.cu, sky_shade_tc2.cu) stay the eval path.
 //
-// One persistent CTA per SM, 416 threads, warp-specialised:
+// One persistent CTA per SM, 544 threads, warp-specialised:
 //   warps 0-7   operand staging: ld.global (coalesced, full sectors) -> registers -> st.shared in the no-swizzle K-major
 //               core-matrix layout [K/4][rows][4 x tf32] (the TN variant transposes in registers, so both variants feed the
 //               same descriptors); `split=3` stores a hi (top 19 bits) and a lo (remainder) plane for the 3xTF32 scheme
 //               (A_hi.B_hi + A_lo.B_hi + A_hi.B_lo), whose result is fp32-accurate and is what the parity tests pin.
-//   warp 12     one lane issues tcgen05.mma (M=128, N<=256, K=8 per instruction) into a double-buffered TMEM accumulator
-//   warps 8-11  epilogue: tcgen05.ld, bias + activation, st.global (NT) / red.global.add (TN)
-// Stage ring: 4 x 48 KB (2 x 96 KB with split=3), mbarrier full/empty; accumulator ring: 2 x 256 TMEM columns.
+//   warp 16     one lane issues tcgen05.mma (M=128, N<=256, K=8 per instruction) into a double-buffered TMEM accumulator
+//   warps 8-15  epilogue (two per TMEM lane quadrant, alternating 32-column chunks): tcgen05.ld, bias + activation,
+//               st.global (NT) / red.global.add (TN).  The epilogue, not the tensor pipe or HBM, was what bounded the first
+//               version (4 warps, ~3300 cycles per 32x32 chunk: profiles/r01_gemm_tf32_ncu_before.txt).
+// Stage ring: NT 3 x 48 KB, TN 4 x 48 KB (2 x 96 KB with split=3), mbarrier full/empty; accumulator ring: 2 x 256 TMEM columns.
 #include <algorithm>
 
 #include "nsk_common.cuh"
@@ -27,16 +29,32 @@ using namespace nsk::tc;
 
 constexpr int TM = 128;
 constexpr int BN = 256;
-constexpr int KC = 32;
 constexpr int PROD_WARPS = 8;
 constexpr int EPI_WARP0 = 8;
-constexpr int MMA_WARP = 12;
-constexpr int THREADS = 13 * 32;
-constexpr uint32_t A_BYTES = TM * KC * 4;
-constexpr uint32_t B_BYTES = BN * KC * 4;
+constexpr int EPI_WARPS = 8;                                // two per TMEM lane quadrant, interleaved 32-column chunks
+constexpr int MMA_WARP = 16;
+constexpr int THREADS = 17 * 32;
 constexpr uint32_t A_LBO = TM * 16, B_LBO = BN * 16;
+// Pipeline shape per variant.  The 3xTF32 NT variant (every forward layer and every dX of the training step) is the "pair"
+// shape: a work item is TWO 128-row tiles of A against one <=256-row tile of B, so every B chunk fetched from L2 feeds twice
+// the MMA work (B is 2/3 of the load traffic with single tiles), chunks are 8 wide (one k-step) in a 5-deep ring so that
+// ~3.5 chunks of loads are in flight per SM -- with hi + lo planes a stage costs twice its global bytes in shared memory, and
+// the first version (2 x 96 KB) never had more than one chunk in flight.  The two tiles use both TMEM accumulators, so the
+// epilogue of an item does not overlap the next item's MMAs; it is short since it runs on 8 warps.
+template <int SPLIT, bool TN> struct Cfg {
+  static constexpr bool PAIR = (SPLIT == 3 && !TN);
+  static constexpr int KC = PAIR ? 8 : 32;
+  static constexpr int ST = PAIR ? 5 : (TN ? (SPLIT == 3 ? 2 : 4) : 3);       // NT keeps 36 KB for the epilogue staging
+  static constexpr int TMI = PAIR ? 2 * TM : TM;                              // rows of the A operand per work item
+  static constexpr uint32_t A_HALF = TM * KC * 4;
+  static constexpr uint32_t A_BYTES = TMI * KC * 4;
+  static constexpr uint32_t B_BYTES = BN * KC * 4;
+  static constexpr uint32_t LO_OFF = A_BYTES + B_BYTES;                       // split 3: lo planes follow the hi planes
+  static constexpr uint32_t STAGE = (A_BYTES + B_BYTES) * (SPLIT == 3 ? 2 : 1);
+};
+constexpr int KC_TN = 32;   // host-side rounding of the TN row split
 constexpr int EPI_LD = 36;                                  // floats per staged row (32 + 4: conflict-free 16-byte accesses)
-constexpr uint32_t EPI_BYTES = 4 * 32 * EPI_LD * 4;         // 4 epilogue warps x 32 rows
+constexpr uint32_t EPI_BYTES = EPI_WARPS * 32 * EPI_LD * 4; // one 32 x 32 transposition tile per epilogue warp (NT only)
 
 struct Params {
   const float* A;
@@ -65,13 +83,13 @@ struct Item {
   int64_t r0, r1;  // reduction range
 };
 
-template <bool TN>
+template <bool TN, int TMI = TM>
 __device__ __forceinline__ Item get_item(const Params& p, int64_t w) {
   Item it;
   if (!TN) {
     const int64_t mt = w / p.n_btiles;
     const int nt = (int)(w % p.n_btiles);
-    it.a0 = mt * TM;
+    it.a0 = mt * TMI;
     it.b0 = nt * BN;
     it.bn = (min(BN, p.N - it.b0) + 15) & ~15;
     it.r0 = 0;
@@ -87,6 +105,16 @@ __device__ __forceinline__ Item get_item(const Params& p, int64_t w) {
     it.r1 = min(p.M, it.r0 + p.rows_per_split);
   }
   return it;
+}
+
+// Start of the c-th reduction chunk of a work item.  NT: every CTA walks the same [N,K] weight matrix, and CTAs launched
+// together stay in lockstep, so with a common order all 148 SMs ask the same few L2 slices for the same 16-32 KB chunk at
+// the same moment (~1 us per chunk whatever N or the split mode, measured).  Rotating the chunk order by the CTA index
+// spreads the concurrent requests over the whole matrix.  Producer and MMA issuer must use the same order (the k tail).
+template <bool TN>
+__device__ __forceinline__ int64_t chunk_start(const Item& it, int c, int nch, int kc) {
+  if (TN) return it.r0 + (int64_t)c * kc;
+  return it.r0 + (int64_t)((c + (int)(blockIdx.x % (unsigned)nch)) % nch) * kc;
 }
 
 // fp32 accumulate, tf32 A and B, both K-major
@@ -117,16 +145,27 @@ __device__ __forceinline__ void cp_async_arrive(uint32_t bar) {
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
 
-template <int SPLIT>
+template <int SPLIT, uint32_t LO_OFF>
 __device__ __forceinline__ void put(uint8_t* hi_plane, uint32_t off, float4 v) {
   if (SPLIT == 1) {
     *reinterpret_cast<float4*>(hi_plane + off) = v;
   } else {
     const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
     *reinterpret_cast<float4*>(hi_plane + off) = h;
-    *reinterpret_cast<float4*>(hi_plane + (A_BYTES + B_BYTES) + off) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+    *reinterpret_cast<float4*>(hi_plane + LO_OFF + off) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
   }
 }
+// lo plane from a raw fp32 piece already sitting in the hi plane: tcgen05.mma.kind::tf32 truncates its operands to the top 19
+// bits (profiles/r01_tf32_truncation_probe.log), so the raw tile IS the hi operand and only v - trunc(v) has to be written
+template <uint32_t LO_OFF>
+__device__ __forceinline__ void fix_lo(uint8_t* hi_plane, uint32_t off) {
+  const float4 v = *reinterpret_cast<const float4*>(hi_plane + off);
+  *reinterpret_cast<float4*>(hi_plane + LO_OFF + off) =
+      make_float4(v.x - tf32_hi(v.x), v.y - tf32_hi(v.y), v.z - tf32_hi(v.z), v.w - tf32_hi(v.w));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 __device__ __forceinline__ float act_apply(float v, int act) {
   if (act == 1) return fmaxf(v, 0.0f);
@@ -134,6 +173,10 @@ __device__ __forceinline__ float act_apply(float v, int act) {
   if (act == 3) return (v * 100.0f > 20.0f) ? v : log1pf(expf(v * 100.0f)) * 0.01f;
   if (act == 4) return 1.0f / (1.0f + expf(-v));
   return v;
+}
+template <int ACT>
+__device__ __forceinline__ float4 bias_act4(float4 t, float4 b) {
+  return make_float4(act_apply(t.x + b.x, ACT), act_apply(t.y + b.y, ACT), act_apply(t.z + b.z, ACT), act_apply(t.w + b.w, ACT));
 }
 // derivative of activation `dact` written in terms of its output a
 __device__ __forceinline__ float dact_from_output(float a, int dact) {
@@ -146,23 +189,29 @@ __device__ __forceinline__ float dact_from_output(float a, int dact) {
 
 template <int SPLIT, bool TN>
 __global__ void __launch_bounds__(THREADS, 1) gemm_tf32_kernel(const Params p) {
-  constexpr int ST = (SPLIT == 3) ? 2 : 4;
-  constexpr uint32_t STAGE = (A_BYTES + B_BYTES) * (SPLIT == 3 ? 2 : 1);
+  using C = Cfg<SPLIT, TN>;
+  constexpr int ST = C::ST, KC = C::KC, TMI = C::TMI;
+  constexpr bool PAIR = C::PAIR;
+  constexpr uint32_t STAGE = C::STAGE, A_BYTES = C::A_BYTES, B_BYTES = C::B_BYTES, LO_OFF = C::LO_OFF, A_HALF = C::A_HALF;
+  (void)A_HALF;
+  (void)B_BYTES;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* const bars_p = reinterpret_cast<uint64_t*>(smem + ST * STAGE);
   const uint32_t bars = smem_u32(bars_p);
-  const uint32_t FULL = bars, EMPTY = bars + 8 * ST, ACCF = bars + 16 * ST, ACCE = bars + 16 * ST + 16;
-  uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(bars_p + 2 * ST + 4);
+  const uint32_t FULL = bars, EMPTY = bars + 8 * ST, ACCF = bars + 16 * ST, ACCE = bars + 16 * ST + 16, RAW = bars + 16 * ST + 32;
+  (void)RAW;
+  uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(smem + ST * STAGE + 248);   // barriers: (3 ST + 4) x 8 B <= 152 B
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < ST; ++s) {
-      mbar_init(FULL + 8 * s, PROD_WARPS * 32);
+      mbar_init(FULL + 8 * s, PAIR ? 128 : PROD_WARPS * 32);
       mbar_init(EMPTY + 8 * s, 1);
+      if (PAIR) mbar_init(RAW + 8 * s, 128);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(ACCF + 8 * b, 1);
-      mbar_init(ACCE + 8 * b, 128);
+      mbar_init(ACCE + 8 * b, EPI_WARPS * 32);
     }
     fence_barrier_init();
   }
@@ -176,9 +225,76 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32_kernel(const Params p) {
     // ------------------------------------------------------------------ operand staging
     uint32_t stage = 0, phase = 0;
     const int r8 = lane & 7, kq_lo = lane >> 3;
+    if constexpr (PAIR) {
+      // Warps 0-3 LOAD: raw fp32 chunks go global -> shared with LDGSTS (they are the hi planes as they are: the MMA
+      // truncates); completion is counted on the stage's RAW mbarrier, so the whole ring is in flight.  Warps 4-7 SPLIT: wait
+      // RAW, derive the lo planes, publish FULL.  Two roles because fence.proxy.async -- needed before the MMA may read the lo
+      // planes -- also waits for the issuing thread's outstanding LDGSTS: with one role doing both, every chunk paid a full
+      // global-load latency (~1 us per chunk whatever the ring depth, measured).
+      const int spi = (p.K + KC - 1) / KC;                                        // chunks per work item
+      const int rot = (int)(blockIdx.x % spi);                                    // see chunk_start()
+      const int r16 = lane & 15, kq = lane >> 4;                                  // warp item = 16 rows x 2 k-quads (32 B per row)
+      const int w4 = warp & 3;
+      int rowv[4];
+      uint32_t offA[4], offB[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        rowv[j] = (w4 + 4 * j) * 16 + r16;                                        // 0..255
+        offA[j] = (uint32_t)((rowv[j] >> 7) * A_HALF + kq * A_LBO + (rowv[j] & 127) * 16);
+        offB[j] = (uint32_t)(kq * B_LBO + rowv[j] * 16);
+      }
+      if (warp < 4) {
+        for (int64_t w = blockIdx.x; w < p.n_items; w += gridDim.x) {
+          const Item it = get_item<TN, TMI>(p, w);
+          const float* ap[4];
+          const float* bp[4];
+          bool aok[4], bok[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int64_t grow = it.a0 + rowv[j];
+            const int n = it.b0 + rowv[j];
+            aok[j] = grow < p.M;
+            bok[j] = rowv[j] < it.bn && n < p.N;
+            ap[j] = aok[j] ? p.A + grow * p.lda + kq * 4 : p.A;
+            bp[j] = bok[j] ? p.B + (int64_t)n * p.ldb + kq * 4 : p.B;
+          }
+          for (int c = 0; c < spi; ++c) {
+            int cc = c + rot;
+            if (cc >= spi) cc -= spi;
+            const int k0 = cc * KC;
+            const bool kok = k0 + kq * 4 < it.r1;
+            mbar_wait(EMPTY + 8 * stage, phase ^ 1);
+            const uint32_t sa32 = smem_u32(smem + stage * STAGE), sb32 = sa32 + A_BYTES;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) cp_async16(sa32 + offA[j], (aok[j] && kok) ? ap[j] + k0 : p.A, aok[j] && kok);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) cp_async16(sb32 + offB[j], (bok[j] && kok) ? bp[j] + k0 : p.B, bok[j] && kok);
+            cp_async_arrive(RAW + 8 * stage);
+            if (++stage == ST) { stage = 0; phase ^= 1; }
+          }
+        }
+      } else {
+        for (int64_t w = blockIdx.x; w < p.n_items; w += gridDim.x) {
+          for (int c = 0; c < spi; ++c) {
+            mbar_wait(RAW + 8 * stage, phase);
+            uint8_t* const sa = smem + stage * STAGE;
+            uint8_t* const sb = sa + A_BYTES;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) fix_lo<LO_OFF>(sa, offA[j]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) fix_lo<LO_OFF>(sb, offB[j]);
+            fence_proxy_async_smem();
+            mbar_arrive(FULL + 8 * stage);
+            if (++stage == ST) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    } else
     for (int64_t w = blockIdx.x; w < p.n_items; w += gridDim.x) {
-      const Item it = get_item<TN>(p, w);
-      for (int64_t r = it.r0; r < it.r1; r += KC) {
+      const Item it = get_item<TN, TMI>(p, w);
+      const int nch = (int)((it.r1 - it.r0 + KC - 1) / KC);
+      for (int c = 0; c < nch; ++c) {
+        const int64_t r = chunk_start<TN>(it, c, nch, KC);
         mbar_wait(EMPTY + 8 * stage, phase ^ 1);
         uint8_t* const sa = smem + stage * STAGE;
         uint8_t* const sb = sa + A_BYTES;
@@ -243,12 +359,12 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32_kernel(const Params p) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int wi = warp + 8 * j, row = (wi >> 1) * 8 + r8, kq = (wi & 1) * 4 + kq_lo;
-            put<SPLIT>(sa, (uint32_t)(kq * A_LBO + row * 16), va[j]);
+            put<SPLIT, LO_OFF>(sa, (uint32_t)(kq * A_LBO + row * 16), va[j]);
           }
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const int wi = warp + 8 * j, row = (wi >> 1) * 8 + r8, kq = (wi & 1) * 4 + kq_lo;
-            put<SPLIT>(sb, (uint32_t)(kq * B_LBO + row * 16), vb[j]);
+            put<SPLIT, LO_OFF>(sb, (uint32_t)(kq * B_LBO + row * 16), vb[j]);
           }
         } else {
           // element (operand row n, k = m): X[(r + k) * ld + col0 + n]; 4 consecutive m per thread -> one 16-byte store
@@ -278,12 +394,12 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32_kernel(const Params p) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int wi = warp + 8 * j, n = (wi & 3) * 32 + lane, mq = wi >> 2;
-            put<SPLIT>(sa, (uint32_t)(mq * A_LBO + n * 16), va[j]);
+            put<SPLIT, LO_OFF>(sa, (uint32_t)(mq * A_LBO + n * 16), va[j]);
           }
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const int wi = warp + 8 * j, n = (wi & 7) * 32 + lane, mq = wi >> 3;
-            put<SPLIT>(sb, (uint32_t)(mq * B_LBO + n * 16), vb[j]);
+            put<SPLIT, LO_OFF>(sb, (uint32_t)(mq * B_LBO + n * 16), vb[j]);
           }
         }
         fence_proxy_async_smem();
@@ -296,7 +412,34 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32_kernel(const Params p) {
     if (lane == 0) {
       uint32_t stage = 0, phase = 0, iter = 0;
       for (int64_t w = blockIdx.x; w < p.n_items; w += gridDim.x, ++iter) {
-        const Item it = get_item<TN>(p, w);
+        const Item it = get_item<TN, TMI>(p, w);
+        if constexpr (PAIR) {
+          // both accumulators belong to this item (tile halves 0 / 1); each barrier completes once per item
+          mbar_wait(ACCE, (iter & 1) ^ 1);
+          mbar_wait(ACCE + 8, (iter & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t idesc = make_idesc_tf32(TM, it.bn);
+          const int halves = (it.a0 + TM < p.M) ? 2 : 1;
+          const int nch = (int)((it.r1 - it.r0 + KC - 1) / KC);
+          for (int c = 0; c < nch; ++c) {
+            mbar_wait(FULL + 8 * stage, phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + stage * STAGE), sb = sa + A_BYTES;
+            const uint64_t bh = make_smem_desc(sb, B_LBO, 128), bl = make_smem_desc(sb + LO_OFF, B_LBO, 128);
+            for (int hf = 0; hf < halves; ++hf) {
+              const uint32_t d = tmem + hf * BN;
+              const uint64_t ah = make_smem_desc(sa + hf * A_HALF, A_LBO, 128), al = make_smem_desc(sa + LO_OFF + hf * A_HALF, A_LBO, 128);
+              umma_tf32(d, al, bh, idesc, c > 0);
+              umma_tf32(d, ah, bl, idesc, 1);
+              umma_tf32(d, ah, bh, idesc, 1);
+            }
+            umma_commit(EMPTY + 8 * stage);
+            if (++stage == ST) { stage = 0; phase ^= 1; }
+          }
+          umma_commit(ACCF);
+          umma_commit(ACCF + 8);
+          continue;
+        }
         const uint32_t buf = iter & 1;
         mbar_wait(ACCE + 8 * buf, ((iter >> 1) & 1) ^ 1);
         tc_fence_after();
@@ -306,7 +449,9 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32_kernel(const Params p) {
         if (it.r0 >= it.r1) {
           // empty reduction range (TN tail split): nothing to add; still hand the buffer over (epilogue skips it)
         }
-        for (int64_t r = it.r0; r < it.r1; r += KC) {
+        const int nch = it.r0 < it.r1 ? (int)((it.r1 - it.r0 + KC - 1) / KC) : 0;
+        for (int c = 0; c < nch; ++c) {
+          const int64_t r = chunk_start<TN>(it, c, nch, KC);
           mbar_wait(FULL + 8 * stage, phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * STAGE), sb = sa + A_BYTES;
@@ -314,7 +459,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32_kernel(const Params p) {
           for (int j = 0; j < ksteps; ++j) {
             const uint64_t ah = make_smem_desc(sa + j * 2 * A_LBO, A_LBO, 128), bh = make_smem_desc(sb + j * 2 * B_LBO, B_LBO, 128);
             if (SPLIT == 3) {
-              const uint32_t lo = A_BYTES + B_BYTES;
+              const uint32_t lo = LO_OFF;
               const uint64_t al = make_smem_desc(sa + lo + j * 2 * A_LBO, A_LBO, 128), bl = make_smem_desc(sb + lo + j * 2 * B_LBO, B_LBO, 128);
               umma_tf32(d, al, bh, idesc, acc);
               umma_tf32(d, ah, bl, idesc, 1);
@@ -336,24 +481,26 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32_kernel(const Params p) {
     // tcgen05.ld gives thread = row, 32 consecutive columns.  NT: transpose each 32x32 chunk through shared memory so that
     // one st.global.v4 of the warp covers 4 rows x 128 contiguous bytes (and the bias / aux / accumulate reads are coalesced
     // the same way).  TN: red.global.add straight from the registers (once per split, not per row tile).
-    const int q = warp - EPI_WARP0;
+    const int e = warp - EPI_WARP0, q = e & 3, half = e >> 2;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-    float* const stg = reinterpret_cast<float*>(smem + ST * STAGE + 256) + q * (32 * EPI_LD);
+    float* const stg = reinterpret_cast<float*>(smem + ST * STAGE + 256) + e * (32 * EPI_LD);
     uint32_t iter = 0;
     const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
-                        (p.dact == 0 || (((p.ldaux & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.aux) & 15) == 0)));
+                        (p.dact == 0 || (((p.ldaux & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.aux) & 15) == 0))) &&
+                        (p.bias == nullptr || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
     const int sub = lane >> 3, c4 = (lane & 7) * 4;   // phase 2: 8 lanes per row, 4 rows per instruction
     for (int64_t w = blockIdx.x; w < p.n_items; w += gridDim.x, ++iter) {
-      const Item it = get_item<TN>(p, w);
-      const uint32_t buf = iter & 1;
-      mbar_wait(ACCF + 8 * buf, (iter >> 1) & 1);
+      const Item it = get_item<TN, TMI>(p, w);
+     for (int hf = 0; hf < (PAIR ? 2 : 1); ++hf) {
+      const uint32_t buf = PAIR ? (uint32_t)hf : (iter & 1);
+      mbar_wait(ACCF + 8 * buf, PAIR ? (iter & 1) : ((iter >> 1) & 1));
       tc_fence_after();
       const int ncols = TN ? p.K : p.N;
       const bool has_data = it.r0 < it.r1;
       if (TN) {
         const int64_t row = it.a0 + q * 32 + lane;
         const bool row_ok = row < p.N;
-        for (int c0 = 0; c0 < it.bn; c0 += 32) {
+        for (int c0 = half * 32; c0 < it.bn; c0 += 64) {
           uint32_t v[32];
           tmem_ld32(tmem + lane_off + buf * BN + c0, v);
           tmem_ld_wait();
@@ -364,8 +511,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32_kernel(const Params p) {
             if (it.b0 + c0 + c < ncols) atomicAdd(crow + c, __uint_as_float(v[c]));
         }
       } else {
-        const int64_t row0 = it.a0 + q * 32;
-        for (int c0 = 0; c0 < it.bn; c0 += 32) {
+        const int64_t row0 = it.a0 + hf * TM + q * 32;
+        for (int c0 = half * 32; (PAIR ? row0 - q * 32 < p.M : true) && c0 < it.bn; c0 += 64) {
           uint32_t v[32];
           tmem_ld32(tmem + lane_off + buf * BN + c0, v);
           tmem_ld_wait();
@@ -375,40 +522,78 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32_kernel(const Params p) {
                 make_float4(__uint_as_float(v[c]), __uint_as_float(v[c + 1]), __uint_as_float(v[c + 2]), __uint_as_float(v[c + 3]));
           __syncwarp();
           const int n0 = it.b0 + c0 + c4;
-          float bia[4] = {0.f, 0.f, 0.f, 0.f};
-          if (p.bias != nullptr) {
+          if (vec_ok && n0 + 4 <= ncols) {
+            // fast path: 8 independent 16-byte rows per lane; every load of a phase is issued before its first use
+            float4 t[8];
 #pragma unroll
-            for (int e = 0; e < 4; ++e)
-              if (n0 + e < ncols) bia[e] = __ldg(p.bias + n0 + e);
-          }
+            for (int i = 0; i < 8; ++i) t[i] = *reinterpret_cast<const float4*>(stg + (i * 4 + sub) * EPI_LD + c4);
+            const float4 b = p.bias != nullptr ? ldg4(p.bias + n0) : make_float4(0.f, 0.f, 0.f, 0.f);
+            switch (p.act) {
+              case 1:
 #pragma unroll
-          for (int rr = 0; rr < 32; rr += 4) {
-            const int rl = rr + sub;
-            const int64_t row = row0 + rl;
-            const float4 t = *reinterpret_cast<const float4*>(stg + rl * EPI_LD + c4);
-            if (row >= p.M || n0 >= ncols) continue;
-            float f[4] = {t.x + bia[0], t.y + bia[1], t.z + bia[2], t.w + bia[3]};
+                for (int i = 0; i < 8; ++i) t[i] = bias_act4<1>(t[i], b);
+                break;
+              case 2:
 #pragma unroll
-            for (int e = 0; e < 4; ++e) f[e] = act_apply(f[e], p.act);
-            float* cp = p.C + row * p.ldc + n0;
-            if (vec_ok && n0 + 4 <= ncols) {
-              if (p.dact != 0) {
-                const float4 a = *reinterpret_cast<const float4*>(p.aux + row * p.ldaux + n0);
-                f[0] *= dact_from_output(a.x, p.dact); f[1] *= dact_from_output(a.y, p.dact);
-                f[2] *= dact_from_output(a.z, p.dact); f[3] *= dact_from_output(a.w, p.dact);
+                for (int i = 0; i < 8; ++i) t[i] = bias_act4<2>(t[i], b);
+                break;
+              case 3:
+#pragma unroll
+                for (int i = 0; i < 8; ++i) t[i] = bias_act4<3>(t[i], b);
+                break;
+              case 4:
+#pragma unroll
+                for (int i = 0; i < 8; ++i) t[i] = bias_act4<4>(t[i], b);
+                break;
+              default:
+#pragma unroll
+                for (int i = 0; i < 8; ++i) t[i] = bias_act4<0>(t[i], b);
+            }
+            const int64_t rowl = row0 + sub;
+            if (p.dact != 0) {
+              float4 a[8];
+              const float* ap = p.aux + rowl * p.ldaux + n0;
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                a[i] = (rowl + i * 4 < p.M) ? *reinterpret_cast<const float4*>(ap + (int64_t)i * 4 * p.ldaux) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                t[i].x *= dact_from_output(a[i].x, p.dact); t[i].y *= dact_from_output(a[i].y, p.dact);
+                t[i].z *= dact_from_output(a[i].z, p.dact); t[i].w *= dact_from_output(a[i].w, p.dact);
               }
-              if (p.accumulate) {
-                const float4 old = *reinterpret_cast<const float4*>(cp);
-                f[0] += old.x; f[1] += old.y; f[2] += old.z; f[3] += old.w;
-              }
-              *reinterpret_cast<float4*>(cp) = make_float4(f[0], f[1], f[2], f[3]);
-            } else {
+            }
+            float* cp = p.C + rowl * p.ldc + n0;
+            if (p.accumulate) {
+              float4 o[8];
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                if (n0 + e < ncols) {
-                  float x = f[e];
-                  if (p.dact != 0) x *= dact_from_output(p.aux[row * p.ldaux + n0 + e], p.dact);
-                  cp[e] = p.accumulate ? cp[e] + x : x;
+              for (int i = 0; i < 8; ++i)
+                o[i] = (rowl + i * 4 < p.M) ? *reinterpret_cast<const float4*>(cp + (int64_t)i * 4 * p.ldc) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) { t[i].x += o[i].x; t[i].y += o[i].y; t[i].z += o[i].z; t[i].w += o[i].w; }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              if (rowl + i * 4 < p.M) *reinterpret_cast<float4*>(cp + (int64_t)i * 4 * p.ldc) = t[i];
+          } else if (n0 < ncols) {
+            float bia[4] = {0.f, 0.f, 0.f, 0.f};
+            if (p.bias != nullptr) {
+#pragma unroll
+              for (int el = 0; el < 4; ++el)
+                if (n0 + el < ncols) bia[el] = __ldg(p.bias + n0 + el);
+            }
+            for (int rr = 0; rr < 32; rr += 4) {
+              const int rl = rr + sub;
+              const int64_t row = row0 + rl;
+              if (row >= p.M) continue;
+              const float4 t = *reinterpret_cast<const float4*>(stg + rl * EPI_LD + c4);
+              const float f[4] = {t.x + bia[0], t.y + bia[1], t.z + bia[2], t.w + bia[3]};
+              float* cp = p.C + row * p.ldc + n0;
+#pragma unroll
+              for (int el = 0; el < 4; ++el) {
+                if (n0 + el < ncols) {
+                  float x = act_apply(f[el], p.act);
+                  if (p.dact != 0) x *= dact_from_output(p.aux[row * p.ldaux + n0 + el], p.dact);
+                  cp[el] = p.accumulate ? cp[el] + x : x;
                 }
               }
             }
@@ -418,6 +603,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32_kernel(const Params p) {
       }
       tc_fence_before();
       mbar_arrive(ACCE + 8 * buf);
+     }
     }
   }
   tc_fence_before();
@@ -428,9 +614,9 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32_kernel(const Params p) {
   }
 }
 
-template <int SPLIT>
+template <int SPLIT, bool TN>
 constexpr size_t smem_bytes() {
-  return (size_t)((SPLIT == 3) ? 2 : 4) * (A_BYTES + B_BYTES) * (SPLIT == 3 ? 2 : 1) + 256 + EPI_BYTES;
+  return (size_t)Cfg<SPLIT, TN>::ST * Cfg<SPLIT, TN>::STAGE + 256 + (TN ? 0 : EPI_BYTES);
 }
 
 static int sm_count() {
@@ -449,12 +635,12 @@ static int launch(const Params& p, cudaStream_t st) {
   auto kern = gemm_tf32_kernel<SPLIT, TN>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<SPLIT>());
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<SPLIT, TN>());
     if (e != cudaSuccess) return fail("gemm_tf32: cudaFuncSetAttribute", cudaGetErrorString(e));
     configured = true;
   }
   const int grid = (int)std::min<int64_t>(p.n_items, sm_count());
-  kern<<<grid, THREADS, smem_bytes<SPLIT>(), st>>>(p);
+  kern<<<grid, THREADS, smem_bytes<SPLIT, TN>(), st>>>(p);
   return check_launch("gemm_tf32_kernel");
 }
 
@@ -484,7 +670,8 @@ extern "C" int nsk_gemm_tf32_nt(const float* A, int lda, const float* B, int ldb
   p.n_btiles = (N + BN - 1) / BN;
   p.n_atiles = 0;
   p.rows_per_split = 0;
-  p.n_items = ((M + TM - 1) / TM) * p.n_btiles;
+  const int tmi = split == 3 ? Cfg<3, false>::TMI : Cfg<1, false>::TMI;
+  p.n_items = ((M + tmi - 1) / tmi) * p.n_btiles;
   return split == 3 ? launch<3, false>(p, nsk::as_stream(stream)) : launch<1, false>(p, nsk::as_stream(stream));
 }
 
@@ -506,7 +693,7 @@ extern "C" int nsk_gemm_tf32_tn(const float* A, int lda, const float* B, int ldb
   const int want = std::max(1, sm_count() / per);
   int64_t rows = (M + want - 1) / want;
   rows = std::max<int64_t>(rows, 512);
-  rows = (rows + KC - 1) / KC * KC;
+  rows = (rows + KC_TN - 1) / KC_TN * KC_TN;
   p.rows_per_split = rows;
   p.n_items = ((M + rows - 1) / rows) * per;
   return split == 3 ? launch<3, true>(p, nsk::as_stream(stream)) : launch<1, true>(p, nsk::as_stream(stream));
