@@ -37,14 +37,15 @@ constexpr int THREADS = 17 * 32;
 constexpr uint32_t A_LBO = TM * 16, B_LBO = BN * 16;
 // Pipeline shape per variant.  The 3xTF32 NT variant (every forward layer and every dX of the training step) is the "pair"
 // shape: a work item is TWO 128-row tiles of A against one <=256-row tile of B, so every B chunk fetched from L2 feeds twice
-// the MMA work (B is 2/3 of the load traffic with single tiles), chunks are 8 wide (one k-step) in a 5-deep ring so that
-// ~3.5 chunks of loads are in flight per SM -- with hi + lo planes a stage costs twice its global bytes in shared memory, and
-// the first version (2 x 96 KB) never had more than one chunk in flight.  The two tiles use both TMEM accumulators, so the
-// epilogue of an item does not overlap the next item's MMAs; it is short since it runs on 8 warps.
+// the MMA work (B is 2/3 of the load traffic with single tiles); chunks are 16 wide in a 3-deep LDGSTS ring (with hi + lo
+// planes a stage costs twice its global bytes in shared memory).  The two tiles use both TMEM accumulators, so the epilogue
+// of an item does not overlap the next item's MMAs; it is short since it runs on 8 warps.  What bounds this variant now is
+// the LDGSTS issue rate of the 4 loader warps (ncu: loaders stalled issuing, epilogue warps 2/3 idle); the next step is a
+// tensor-map TMA load (SWIZZLE_64B boxes), which takes the L1tex pipe out of the operand path.
 template <int SPLIT, bool TN> struct Cfg {
   static constexpr bool PAIR = (SPLIT == 3 && !TN);
-  static constexpr int KC = PAIR ? 8 : 32;
-  static constexpr int ST = PAIR ? 5 : (TN ? (SPLIT == 3 ? 2 : 4) : 3);       // NT keeps 36 KB for the epilogue staging
+  static constexpr int KC = PAIR ? 16 : 32;
+  static constexpr int ST = PAIR ? 3 : (TN ? (SPLIT == 3 ? 2 : 4) : 3);       // NT keeps 18 KB for the epilogue staging
   static constexpr int TMI = PAIR ? 2 * TM : TM;                              // rows of the A operand per work item
   static constexpr uint32_t A_HALF = TM * KC * 4;
   static constexpr uint32_t A_BYTES = TMI * KC * 4;
@@ -54,7 +55,8 @@ template <int SPLIT, bool TN> struct Cfg {
 };
 constexpr int KC_TN = 32;   // host-side rounding of the TN row split
 constexpr int EPI_LD = 36;                                  // floats per staged row (32 + 4: conflict-free 16-byte accesses)
-constexpr uint32_t EPI_BYTES = EPI_WARPS * 32 * EPI_LD * 4; // one 32 x 32 transposition tile per epilogue warp (NT only)
+constexpr int EPI_ROWS = 16;                                // rows transposed per pass (two passes per 32 x 32 chunk)
+constexpr uint32_t EPI_BYTES = EPI_WARPS * EPI_ROWS * EPI_LD * 4;   // one 16 x 32 transposition tile per epilogue warp (NT only)
 
 struct Params {
   const float* A;
@@ -233,24 +235,28 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32_kernel(const Params p) {
       // global-load latency (~1 us per chunk whatever the ring depth, measured).
       const int spi = (p.K + KC - 1) / KC;                                        // chunks per work item
       const int rot = (int)(blockIdx.x % spi);                                    // see chunk_start()
-      const int r16 = lane & 15, kq = lane >> 4;                                  // warp item = 16 rows x 2 k-quads (32 B per row)
+      // warp item = 8 rows x 4 k-quads (64 B per row): 8 distinct 128-byte lines per LDGSTS instruction (the L1tex pipe spends
+      // ~2 cycles per line touched, which is what bounded the 8-wide chunk variant: 16 lines per instruction) and 8 distinct
+      // 16-byte bank groups per quarter warp on the shared-memory side
+      constexpr int NP = 8;                                                        // pieces of A (and of B) per thread per chunk
+      const int kq = lane >> 3;
       const int w4 = warp & 3;
-      int rowv[4];
-      uint32_t offA[4], offB[4];
+      int rowv[NP];
+      uint32_t offA[NP], offB[NP];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        rowv[j] = (w4 + 4 * j) * 16 + r16;                                        // 0..255
+      for (int j = 0; j < NP; ++j) {
+        rowv[j] = (w4 + 4 * j) * 8 + r8;                                          // 0..255
         offA[j] = (uint32_t)((rowv[j] >> 7) * A_HALF + kq * A_LBO + (rowv[j] & 127) * 16);
         offB[j] = (uint32_t)(kq * B_LBO + rowv[j] * 16);
       }
       if (warp < 4) {
         for (int64_t w = blockIdx.x; w < p.n_items; w += gridDim.x) {
           const Item it = get_item<TN, TMI>(p, w);
-          const float* ap[4];
-          const float* bp[4];
-          bool aok[4], bok[4];
+          const float* ap[NP];
+          const float* bp[NP];
+          bool aok[NP], bok[NP];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          for (int j = 0; j < NP; ++j) {
             const int64_t grow = it.a0 + rowv[j];
             const int n = it.b0 + rowv[j];
             aok[j] = grow < p.M;
@@ -266,9 +272,9 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32_kernel(const Params p) {
             mbar_wait(EMPTY + 8 * stage, phase ^ 1);
             const uint32_t sa32 = smem_u32(smem + stage * STAGE), sb32 = sa32 + A_BYTES;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) cp_async16(sa32 + offA[j], (aok[j] && kok) ? ap[j] + k0 : p.A, aok[j] && kok);
+            for (int j = 0; j < NP; ++j) cp_async16(sa32 + offA[j], (aok[j] && kok) ? ap[j] + k0 : p.A, aok[j] && kok);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) cp_async16(sb32 + offB[j], (bok[j] && kok) ? bp[j] + k0 : p.B, bok[j] && kok);
+            for (int j = 0; j < NP; ++j) cp_async16(sb32 + offB[j], (bok[j] && kok) ? bp[j] + k0 : p.B, bok[j] && kok);
             cp_async_arrive(RAW + 8 * stage);
             if (++stage == ST) { stage = 0; phase ^= 1; }
           }
@@ -280,9 +286,9 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32_kernel(const Params p) {
             uint8_t* const sa = smem + stage * STAGE;
             uint8_t* const sb = sa + A_BYTES;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) fix_lo<LO_OFF>(sa, offA[j]);
+            for (int j = 0; j < NP; ++j) fix_lo<LO_OFF>(sa, offA[j]);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) fix_lo<LO_OFF>(sb, offB[j]);
+            for (int j = 0; j < NP; ++j) fix_lo<LO_OFF>(sb, offB[j]);
             fence_proxy_async_smem();
             mbar_arrive(FULL + 8 * stage);
             if (++stage == ST) { stage = 0; phase ^= 1; }
@@ -422,16 +428,21 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32_kernel(const Params p) {
           const int halves = (it.a0 + TM < p.M) ? 2 : 1;
           const int nch = (int)((it.r1 - it.r0 + KC - 1) / KC);
           for (int c = 0; c < nch; ++c) {
+            const int64_t r = chunk_start<TN>(it, c, nch, KC);                  // same rotated order as the loader
+            const int ksteps = (int)min((int64_t)(KC / 8), (it.r1 - r + 7) / 8);
             mbar_wait(FULL + 8 * stage, phase);
             tc_fence_after();
             const uint32_t sa = smem_u32(smem + stage * STAGE), sb = sa + A_BYTES;
-            const uint64_t bh = make_smem_desc(sb, B_LBO, 128), bl = make_smem_desc(sb + LO_OFF, B_LBO, 128);
-            for (int hf = 0; hf < halves; ++hf) {
-              const uint32_t d = tmem + hf * BN;
-              const uint64_t ah = make_smem_desc(sa + hf * A_HALF, A_LBO, 128), al = make_smem_desc(sa + LO_OFF + hf * A_HALF, A_LBO, 128);
-              umma_tf32(d, al, bh, idesc, c > 0);
-              umma_tf32(d, ah, bl, idesc, 1);
-              umma_tf32(d, ah, bh, idesc, 1);
+            for (int j = 0; j < ksteps; ++j) {
+              const uint64_t bh = make_smem_desc(sb + j * 2 * B_LBO, B_LBO, 128), bl = make_smem_desc(sb + LO_OFF + j * 2 * B_LBO, B_LBO, 128);
+              for (int hf = 0; hf < halves; ++hf) {
+                const uint32_t d = tmem + hf * BN;
+                const uint64_t ah = make_smem_desc(sa + hf * A_HALF + j * 2 * A_LBO, A_LBO, 128);
+                const uint64_t al = make_smem_desc(sa + LO_OFF + hf * A_HALF + j * 2 * A_LBO, A_LBO, 128);
+                umma_tf32(d, al, bh, idesc, (c > 0 || j > 0) ? 1u : 0u);
+                umma_tf32(d, ah, bl, idesc, 1);
+                umma_tf32(d, ah, bh, idesc, 1);
+              }
             }
             umma_commit(EMPTY + 8 * stage);
             if (++stage == ST) { stage = 0; phase ^= 1; }
@@ -483,7 +494,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32_kernel(const Params p) {
     // the same way).  TN: red.global.add straight from the registers (once per split, not per row tile).
     const int e = warp - EPI_WARP0, q = e & 3, half = e >> 2;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-    float* const stg = reinterpret_cast<float*>(smem + ST * STAGE + 256) + e * (32 * EPI_LD);
+    float* const stg = reinterpret_cast<float*>(smem + ST * STAGE + 256) + e * (EPI_ROWS * EPI_LD);
     uint32_t iter = 0;
     const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
                         (p.dact == 0 || (((p.ldaux & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.aux) & 15) == 0))) &&
@@ -516,63 +527,66 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32_kernel(const Params p) {
           uint32_t v[32];
           tmem_ld32(tmem + lane_off + buf * BN + c0, v);
           tmem_ld_wait();
-#pragma unroll
-          for (int c = 0; c < 32; c += 4)
-            *reinterpret_cast<float4*>(stg + lane * EPI_LD + c) =
-                make_float4(__uint_as_float(v[c]), __uint_as_float(v[c + 1]), __uint_as_float(v[c + 2]), __uint_as_float(v[c + 3]));
-          __syncwarp();
           const int n0 = it.b0 + c0 + c4;
-          if (vec_ok && n0 + 4 <= ncols) {
-            // fast path: 8 independent 16-byte rows per lane; every load of a phase is issued before its first use
-            float4 t[8];
+         for (int rh = 0; rh < 32 / EPI_ROWS; ++rh) {          // 16 rows of the chunk per transposition pass
+          if ((lane >> 4) == rh) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) t[i] = *reinterpret_cast<const float4*>(stg + (i * 4 + sub) * EPI_LD + c4);
+            for (int c = 0; c < 32; c += 4)
+              *reinterpret_cast<float4*>(stg + (lane & 15) * EPI_LD + c) =
+                  make_float4(__uint_as_float(v[c]), __uint_as_float(v[c + 1]), __uint_as_float(v[c + 2]), __uint_as_float(v[c + 3]));
+          }
+          __syncwarp();
+          if (vec_ok && n0 + 4 <= ncols) {
+            // fast path: 4 independent 16-byte rows per lane; every load of a phase is issued before its first use
+            float4 t[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) t[i] = *reinterpret_cast<const float4*>(stg + (i * 4 + sub) * EPI_LD + c4);
             const float4 b = p.bias != nullptr ? ldg4(p.bias + n0) : make_float4(0.f, 0.f, 0.f, 0.f);
             switch (p.act) {
               case 1:
 #pragma unroll
-                for (int i = 0; i < 8; ++i) t[i] = bias_act4<1>(t[i], b);
+                for (int i = 0; i < 4; ++i) t[i] = bias_act4<1>(t[i], b);
                 break;
               case 2:
 #pragma unroll
-                for (int i = 0; i < 8; ++i) t[i] = bias_act4<2>(t[i], b);
+                for (int i = 0; i < 4; ++i) t[i] = bias_act4<2>(t[i], b);
                 break;
               case 3:
 #pragma unroll
-                for (int i = 0; i < 8; ++i) t[i] = bias_act4<3>(t[i], b);
+                for (int i = 0; i < 4; ++i) t[i] = bias_act4<3>(t[i], b);
                 break;
               case 4:
 #pragma unroll
-                for (int i = 0; i < 8; ++i) t[i] = bias_act4<4>(t[i], b);
+                for (int i = 0; i < 4; ++i) t[i] = bias_act4<4>(t[i], b);
                 break;
               default:
 #pragma unroll
-                for (int i = 0; i < 8; ++i) t[i] = bias_act4<0>(t[i], b);
+                for (int i = 0; i < 4; ++i) t[i] = bias_act4<0>(t[i], b);
             }
-            const int64_t rowl = row0 + sub;
+            const int64_t rowl = row0 + rh * EPI_ROWS + sub;
             if (p.dact != 0) {
-              float4 a[8];
+              float4 a[4];
               const float* ap = p.aux + rowl * p.ldaux + n0;
 #pragma unroll
-              for (int i = 0; i < 8; ++i)
+              for (int i = 0; i < 4; ++i)
                 a[i] = (rowl + i * 4 < p.M) ? *reinterpret_cast<const float4*>(ap + (int64_t)i * 4 * p.ldaux) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
+              for (int i = 0; i < 4; ++i) {
                 t[i].x *= dact_from_output(a[i].x, p.dact); t[i].y *= dact_from_output(a[i].y, p.dact);
                 t[i].z *= dact_from_output(a[i].z, p.dact); t[i].w *= dact_from_output(a[i].w, p.dact);
               }
             }
             float* cp = p.C + rowl * p.ldc + n0;
             if (p.accumulate) {
-              float4 o[8];
+              float4 o[4];
 #pragma unroll
-              for (int i = 0; i < 8; ++i)
+              for (int i = 0; i < 4; ++i)
                 o[i] = (rowl + i * 4 < p.M) ? *reinterpret_cast<const float4*>(cp + (int64_t)i * 4 * p.ldc) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-              for (int i = 0; i < 8; ++i) { t[i].x += o[i].x; t[i].y += o[i].y; t[i].z += o[i].z; t[i].w += o[i].w; }
+              for (int i = 0; i < 4; ++i) { t[i].x += o[i].x; t[i].y += o[i].y; t[i].z += o[i].z; t[i].w += o[i].w; }
             }
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+            for (int i = 0; i < 4; ++i)
               if (rowl + i * 4 < p.M) *reinterpret_cast<float4*>(cp + (int64_t)i * 4 * p.ldc) = t[i];
           } else if (n0 < ncols) {
             float bia[4] = {0.f, 0.f, 0.f, 0.f};
@@ -581,9 +595,9 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32_kernel(const Params p) {
               for (int el = 0; el < 4; ++el)
                 if (n0 + el < ncols) bia[el] = __ldg(p.bias + n0 + el);
             }
-            for (int rr = 0; rr < 32; rr += 4) {
+            for (int rr = 0; rr < EPI_ROWS; rr += 4) {
               const int rl = rr + sub;
-              const int64_t row = row0 + rl;
+              const int64_t row = row0 + rh * EPI_ROWS + rl;
               if (row >= p.M) continue;
               const float4 t = *reinterpret_cast<const float4*>(stg + rl * EPI_LD + c4);
               const float f[4] = {t.x + bia[0], t.y + bia[1], t.z + bia[2], t.w + bia[3]};
@@ -599,6 +613,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32_kernel(const Params p) {
             }
           }
           __syncwarp();
+         }
         }
       }
       tc_fence_before();
