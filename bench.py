@@ -322,6 +322,15 @@ def train_arm(args):
     it = {"i": 0}
     loss_h = torch.zeros(1).pin_memory()
     Dp_seen = []
+    fit = None
+    if not args.no_ddf_fit:
+        # the reference's iteration also fits the DDF to the scene (fit_visibility_field=True, neusky_pipeline.py:272-289): 8 x 128 vMF
+        # rays rendered through the SDF field + DDF on those rays, on the multi-view rows and on 256 sky rays, stop_sdf_gradients=False
+        from neusky_b200.ddf_fit import DDFFit
+        fit = DDFFit(step_mod)
+        gs = torch.Generator().manual_seed(300 + rank)
+        sky_o = (torch.tensor([0.0, -0.6, 0.1]).expand(256, 3) + 0.1 * torch.randn(256, 3, generator=gs)).to(dev)
+        sky_d = torch.nn.functional.normalize(torch.randn(256, 3, generator=gs) + torch.tensor([0.0, 0.0, 1.0]), dim=-1).to(dev)
 
     def one_step():
         i = it["i"]; it["i"] += 1
@@ -333,6 +342,8 @@ def train_arm(args):
         b = {k: v.to(dev, non_blocking=True) for k, v in batch_h.items()}                       # h2d of the ray batch inside the step
         red.zero_grad()
         loss, _, _ = step_mod(b, grid_positions=gp, grid_dirs=gd)
+        if fit is not None:
+            loss = loss + fit(sky_o, sky_d)[0]
         loss.backward()
         red.finish()
         opt.step()
@@ -369,6 +380,8 @@ def train_arm(args):
         Dp = sum(Dp_seen) / max(1, len(Dp_seen))
         # algorithmic FLOP of one iteration, forward figures of SURVEY 8(d) x 3 (forward + two backward contractions):
         flop = 3.0 * (R * Dp * (FLOP_PER_PAIR + 2 * 149_504) + R * S * 881_664 + gres**3 * 2 * 2 * 149_504)
+        if fit is not None:      # fitting pass: 1024 rays x S samples through the geometry network with normals, 2304 DDF rows, 1024 sdf_at_termination rows
+            flop += 3.0 * (1024 * S * 4 * 149_504 + 2304 * FLOP_PER_PAIR + 1024 * 2 * 149_504)
         h2d = sum(v.numel() * v.element_size() for v in batch_h.values()) + 2 * gpos0.numel() * 4 + 642 * 3 * 4
         line = {"metric": "training rays/s (forward + losses + backward + gradient all-reduce + Adam)", "value": world * R * args.steps / t, "unit": UNIT,
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "wall_ms_per_step": 1e3 * wall / args.steps,
@@ -376,6 +389,8 @@ def train_arm(args):
                 "dtype": f"tf32 operands (3xTF32 on the SDF geometry network, split={args.split} elsewhere), fp32 accumulate / activations / gradients", "data": "synthetic",
                 "config": {"workload": f"BASELINE.json configs[3]: training step, {R} rays/GPU from {K} cameras, S={S} uniform samples/ray, 642-direction icosphere with a random "
                                        f"rotation per step (mean D'={Dp:.0f} through the DDF), sdf_at_termination branch, hashgrid density loss on {gres**3} grid points, "
+                                       + ("DDF fitting pass (8 x 128 vMF rays rendered through the SDF field, DDF on 1024 + 1024 multi-view + 256 sky rows, gradients into both fields), " if fit is not None else "no DDF fitting pass, ")
+                                       + 
                                        f"hash tables 2 x 2^19 x 16 x 2 fp32", "rays_per_gpu": R, "samples_per_ray": S,
                            "parallelism": f"data-parallel x{world}, bucketed gradient all-reduce ({red.bytes_per_step / 2**20:.0f} MiB/step, {len(red.buckets)} buckets)"
                                           + (" over NCCL" if world > 1 else " (single rank: no collective)"),
@@ -408,6 +423,7 @@ def main():
     ap.add_argument("--rays", type=int, default=1024, help="train: rays per GPU")
     ap.add_argument("--train-samples", type=int, default=48)
     ap.add_argument("--split", type=int, default=3, choices=[1, 3], help="train: 1 = tf32 GEMMs, 3 = 3xTF32 (fp32-accurate)")
+    ap.add_argument("--no-ddf-fit", action="store_true", help="train: leave the DDF fitting pass (fit_visibility_field=True in the reference) out of the step")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)
