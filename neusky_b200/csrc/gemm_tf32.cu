@@ -20,6 +20,8 @@
 // Stage ring: NT 3 x 48 KB, TN 4 x 48 KB (2 x 96 KB with split=3), mbarrier full/empty; accumulator ring: 2 x 256 TMEM columns.
 #include <algorithm>
 
+#include <cuda.h>   // CUtensorMap (types only; the encoder is fetched with cudaGetDriverEntryPoint, no libcuda link)
+
 #include "nsk_common.cuh"
 #include "tc_util.cuh"
 
@@ -109,6 +111,24 @@ __device__ __forceinline__ Item get_item(const Params& p, int64_t w) {
   return it;
 }
 
+// Shared-memory descriptor for a K-major operand written by TMA with CU_TENSOR_MAP_SWIZZLE_64B: rows of 64 B (16 tf32), 8-row
+// atoms of 512 B (SBO), 16-byte chunks XOR-swizzled by address bits [7,9); layout type 4 = SWIZZLE_64B; LBO unused (one k-step
+// of 8 tf32 = 32 B stays inside the swizzle span).  k-steps advance the start address by 32 B.
+__device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((512u >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;
+  return d;
+}
+// 2-D tiled TMA load global -> shared, completion (bytes) on an mbarrier.  c0 = innermost coordinate (k), c1 = row.
+__device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst_smem),
+               "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar)
+               : "memory");
+}
+
 // Start of the c-th reduction chunk of a work item.  NT: every CTA walks the same [N,K] weight matrix, and CTAs launched
 // together stay in lockstep, so with a common order all 148 SMs ask the same few L2 slices for the same 16-32 KB chunk at
 // the same moment (~1 us per chunk whatever N or the split mode, measured).  Rotating the chunk order by the CTA index
@@ -189,8 +209,9 @@ __device__ __forceinline__ float dact_from_output(float a, int dact) {
   return 1.0f;
 }
 
-template <int SPLIT, bool TN>
-__global__ void __launch_bounds__(THREADS, 1) gemm_tf32_kernel(const Params p) {
+template <int SPLIT, bool TN, bool TMA>
+__global__ void __launch_bounds__(THREADS, 1) gemm_tf32_kernel(const Params p, const __grid_constant__ CUtensorMap tmA,
+                                                               const __grid_constant__ CUtensorMap tmB) {
   using C = Cfg<SPLIT, TN>;
   constexpr int ST = C::ST, KC = C::KC, TMI = C::TMI;
   constexpr bool PAIR = C::PAIR;
@@ -209,7 +230,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32_kernel(const Params p) {
     for (int s = 0; s < ST; ++s) {
       mbar_init(FULL + 8 * s, PAIR ? 128 : PROD_WARPS * 32);
       mbar_init(EMPTY + 8 * s, 1);
-      if (PAIR) mbar_init(RAW + 8 * s, 128);
+      if (PAIR) mbar_init(RAW + 8 * s, TMA ? 1 : 128);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(ACCF + 8 * b, 1);
@@ -249,7 +270,25 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32_kernel(const Params p) {
         offA[j] = (uint32_t)((rowv[j] >> 7) * A_HALF + kq * A_LBO + (rowv[j] & 127) * 16);
         offB[j] = (uint32_t)(kq * B_LBO + rowv[j] * 16);
       }
-      if (warp < 4) {
+      if (TMA && warp < 4) {
+        // one thread feeds the ring with two tensor-map boxes per chunk (A: 256 rows x 64 B, B: 256 rows x 64 B, SWIZZLE_64B,
+        // out-of-range rows / columns zero-filled by the TMA unit): no L1tex wavefronts, no per-thread address math
+        if (warp == 0 && lane == 0) {
+          for (int64_t w = blockIdx.x; w < p.n_items; w += gridDim.x) {
+            const Item it = get_item<TN, TMI>(p, w);
+            for (int c = 0; c < spi; ++c) {
+              int cc = c + rot;
+              if (cc >= spi) cc -= spi;
+              mbar_wait(EMPTY + 8 * stage, phase ^ 1);
+              const uint32_t sa32 = smem_u32(smem + stage * STAGE);
+              mbar_arrive_expect_tx(RAW + 8 * stage, A_BYTES + B_BYTES);
+              tma_load_2d(sa32, &tmA, cc * KC, (int)it.a0, RAW + 8 * stage);
+              tma_load_2d(sa32 + A_BYTES, &tmB, cc * KC, it.b0, RAW + 8 * stage);
+              if (++stage == ST) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      } else if (warp < 4) {
         for (int64_t w = blockIdx.x; w < p.n_items; w += gridDim.x) {
           const Item it = get_item<TN, TMI>(p, w);
           const float* ap[NP];
@@ -285,10 +324,16 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32_kernel(const Params p) {
             mbar_wait(RAW + 8 * stage, phase);
             uint8_t* const sa = smem + stage * STAGE;
             uint8_t* const sb = sa + A_BYTES;
+            if (TMA) {                                       // layout-agnostic: hi and lo planes share the (swizzled) layout
+              const uint32_t t128 = (uint32_t)(threadIdx.x & 127) * 16;
 #pragma unroll
-            for (int j = 0; j < NP; ++j) fix_lo<LO_OFF>(sa, offA[j]);
+              for (int j = 0; j < 2 * NP; ++j) fix_lo<LO_OFF>(sa, t128 + (uint32_t)j * 2048);
+            } else {
 #pragma unroll
-            for (int j = 0; j < NP; ++j) fix_lo<LO_OFF>(sb, offB[j]);
+              for (int j = 0; j < NP; ++j) fix_lo<LO_OFF>(sa, offA[j]);
+#pragma unroll
+              for (int j = 0; j < NP; ++j) fix_lo<LO_OFF>(sb, offB[j]);
+            }
             fence_proxy_async_smem();
             mbar_arrive(FULL + 8 * stage);
             if (++stage == ST) { stage = 0; phase ^= 1; }
@@ -434,11 +479,13 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32_kernel(const Params p) {
             tc_fence_after();
             const uint32_t sa = smem_u32(smem + stage * STAGE), sb = sa + A_BYTES;
             for (int j = 0; j < ksteps; ++j) {
-              const uint64_t bh = make_smem_desc(sb + j * 2 * B_LBO, B_LBO, 128), bl = make_smem_desc(sb + LO_OFF + j * 2 * B_LBO, B_LBO, 128);
+              const uint64_t bh = TMA ? make_smem_desc_sw64(sb + j * 32) : make_smem_desc(sb + j * 2 * B_LBO, B_LBO, 128);
+              const uint64_t bl = TMA ? make_smem_desc_sw64(sb + LO_OFF + j * 32) : make_smem_desc(sb + LO_OFF + j * 2 * B_LBO, B_LBO, 128);
               for (int hf = 0; hf < halves; ++hf) {
                 const uint32_t d = tmem + hf * BN;
-                const uint64_t ah = make_smem_desc(sa + hf * A_HALF + j * 2 * A_LBO, A_LBO, 128);
-                const uint64_t al = make_smem_desc(sa + LO_OFF + hf * A_HALF + j * 2 * A_LBO, A_LBO, 128);
+                const uint64_t ah = TMA ? make_smem_desc_sw64(sa + hf * A_HALF + j * 32) : make_smem_desc(sa + hf * A_HALF + j * 2 * A_LBO, A_LBO, 128);
+                const uint64_t al = TMA ? make_smem_desc_sw64(sa + LO_OFF + hf * A_HALF + j * 32)
+                                        : make_smem_desc(sa + LO_OFF + hf * A_HALF + j * 2 * A_LBO, A_LBO, 128);
                 umma_tf32(d, al, bh, idesc, (c > 0 || j > 0) ? 1u : 0u);
                 umma_tf32(d, ah, bl, idesc, 1);
                 umma_tf32(d, ah, bh, idesc, 1);
@@ -645,9 +692,36 @@ static int sm_count() {
   return n;
 }
 
-template <int SPLIT, bool TN>
-static int launch(const Params& p, cudaStream_t st) {
-  auto kern = gemm_tf32_kernel<SPLIT, TN>;
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no libcuda link dependency)
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                      const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TensorMapEncodeFn tensor_map_encoder() {
+  static TensorMapEncodeFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<TensorMapEncodeFn>(ptr);
+  }
+  return fn;
+}
+// fp32 [rows, cols] matrix with row stride ld (elements): boxes of box_rows x 16 columns (64 B), SWIZZLE_64B, zero fill out of range
+static bool make_tensor_map(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  TensorMapEncodeFn fn = tensor_map_encoder();
+  if (fn == nullptr || (reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld & 3) != 0) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  const cuuint32_t box[2] = {16u, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1u, 1u};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int SPLIT, bool TN, bool TMA>
+static int launch_variant(const Params& p, const CUtensorMap& ma, const CUtensorMap& mb, cudaStream_t st) {
+  auto kern = gemm_tf32_kernel<SPLIT, TN, TMA>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<SPLIT, TN>());
@@ -655,8 +729,19 @@ static int launch(const Params& p, cudaStream_t st) {
     configured = true;
   }
   const int grid = (int)std::min<int64_t>(p.n_items, sm_count());
-  kern<<<grid, THREADS, smem_bytes<SPLIT, TN>(), st>>>(p);
+  kern<<<grid, THREADS, smem_bytes<SPLIT, TN>(), st>>>(p, ma, mb);
   return check_launch("gemm_tf32_kernel");
+}
+
+template <int SPLIT, bool TN>
+static int launch(const Params& p, cudaStream_t st) {
+  CUtensorMap ma, mb;
+  memset(&ma, 0, sizeof(ma));
+  memset(&mb, 0, sizeof(mb));
+  if (Cfg<SPLIT, TN>::PAIR && getenv("NSK_GEMM_NO_TMA") == nullptr &&
+      make_tensor_map(&ma, p.A, p.M, p.K, p.lda, Cfg<SPLIT, TN>::TMI) && make_tensor_map(&mb, p.B, p.N, p.K, p.ldb, BN))
+    return launch_variant<SPLIT, TN, Cfg<SPLIT, TN>::PAIR>(p, ma, mb, st);
+  return launch_variant<SPLIT, TN, false>(p, ma, mb, st);
 }
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
