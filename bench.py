@@ -365,6 +365,7 @@ def train_arm(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); one_step(); e1.record()
         evs.append((e0, e1))
+    host_launch = time.perf_counter() - wall0        # the loop never synchronises: time until the last launch of the last step was queued
     torch.cuda.synchronize()
     t = sum(a.elapsed_time(b) for a, b in evs) / 1e3
     if dist is not None:
@@ -385,6 +386,7 @@ def train_arm(args):
         h2d = sum(v.numel() * v.element_size() for v in batch_h.values()) + 2 * gpos0.numel() * 4 + 642 * 3 * 4
         line = {"metric": "training rays/s (forward + losses + backward + gradient all-reduce + Adam)", "value": world * R * args.steps / t, "unit": UNIT,
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "wall_ms_per_step": 1e3 * wall / args.steps,
+                "host_launch_ms_per_step": 1e3 * host_launch / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": f"tf32 operands (3xTF32 on the SDF geometry network, split={args.split} elsewhere), fp32 accumulate / activations / gradients", "data": "synthetic",
                 "config": {"workload": f"BASELINE.json configs[3]: training step, {R} rays/GPU from {K} cameras, S={S} uniform samples/ray, 642-direction icosphere with a random "
