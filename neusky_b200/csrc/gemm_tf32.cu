@@ -9,10 +9,11 @@
 // in the training step; the fused forward-only kernels (sdf_field_tc.cu, sky_shade_tc2.cu) stay the eval path.
 //
 // One persistent CTA per SM, 544 threads, warp-specialised:
-//   warps 0-7   operand staging: ld.global (coalesced, full sectors) -> registers -> st.shared in the no-swizzle K-major
-//               core-matrix layout [K/4][rows][4 x tf32] (the TN variant transposes in registers, so both variants feed the
-//               same descriptors); `split=3` stores a hi (top 19 bits) and a lo (remainder) plane for the 3xTF32 scheme
-//               (A_hi.B_hi + A_lo.B_hi + A_hi.B_lo), whose result is fp32-accurate and is what the parity tests pin.
+//   warps 0-7   operand staging.  3xTF32 NT (the training step's forward layers and dX): one thread issues tensor-map TMA boxes
+//               (raw fp32 = the hi plane, the MMA truncates to 19 bits), warps 4-7 derive the lo plane (v - trunc(v)) for the
+//               3xTF32 scheme (A_hi.B_hi + A_lo.B_hi + A_hi.B_lo), whose result is fp32-accurate and is what the parity tests
+//               pin.  Other variants: LDGSTS / ld.global -> registers -> st.shared in the no-swizzle K-major core-matrix layout
+//               [K/4][rows][4 x tf32] (the TN variant transposes in registers, so both feed the same descriptors).
 //   warp 16     one lane issues tcgen05.mma (M=128, N<=256, K=8 per instruction) into a double-buffered TMEM accumulator
 //   warps 8-15  epilogue (two per TMEM lane quadrant, alternating 32-column chunks): tcgen05.ld, bias + activation,
 //               st.global (NT) / red.global.add (TN).  The epilogue, not the tensor pipe or HBM, was what bounded the first
@@ -41,9 +42,9 @@ constexpr uint32_t A_LBO = TM * 16, B_LBO = BN * 16;
 // shape: a work item is TWO 128-row tiles of A against one <=256-row tile of B, so every B chunk fetched from L2 feeds twice
 // the MMA work (B is 2/3 of the load traffic with single tiles); chunks are 16 wide in a 3-deep LDGSTS ring (with hi + lo
 // planes a stage costs twice its global bytes in shared memory).  The two tiles use both TMEM accumulators, so the epilogue
-// of an item does not overlap the next item's MMAs; it is short since it runs on 8 warps.  What bounds this variant now is
-// the LDGSTS issue rate of the 4 loader warps (ncu: loaders stalled issuing, epilogue warps 2/3 idle); the next step is a
-// tensor-map TMA load (SWIZZLE_64B boxes), which takes the L1tex pipe out of the operand path.
+// of an item does not overlap the next item's MMAs; it is short since it runs on 8 warps.  With LDGSTS the variant was bound
+// by the issue rate of the 4 loader warps (ncu: loaders stalled issuing, epilogue warps 2/3 idle); the operands therefore
+// arrive as tensor-map TMA boxes (TMA = true: SWIZZLE_64B, one issuing thread), the LDGSTS loader stays as the fallback.
 template <int SPLIT, bool TN> struct Cfg {
   static constexpr bool PAIR = (SPLIT == 3 && !TN);
   static constexpr int KC = PAIR ? 16 : 32;
