@@ -267,6 +267,103 @@ def eval_arm(args):
 
 
 
+# ------------------------------------------------------------------------------------------ relighting sweep (configs[4])
+def relight_arm(args):
+    """BASELINE.json configs[4]: fixed geometry, 64 RENI++ latent codes re-shaded per view.  The frame is rendered once with
+    `want_cache=True` (per-sample shading inputs + per-ray visibility of the D' DDF directions, kept in HBM), then every
+    latent code is one RENI++ decode + one Lambertian pass over the cache per tile -- no SDF field, no compositing, no DDF.
+    The timed region is the 64-code sweep; the cache build is reported separately.  Ray tiles are partitioned over the ranks
+    (strong scaling), each rank relights its own tiles; no collective in the timed region."""
+    rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    import math
+    from neusky_b200 import _lib, init as nb_init, samplers
+    from neusky_b200.render import RayRenderer, global_steps_minmax, pinhole_rays
+
+    sdf_p = nb_init.init_sdf_params(SEED_W + 2, bias=0.45)
+    sdf_p["deviation_network.variance"] = torch.tensor(0.3)
+    r = RayRenderer(sdf_p, nb_init.init_ddf_params(SEED_W), nb_init.init_reni_params(SEED_W + 1), device=dev)
+    r.set_directions(samplers.IcosahedronSampler(512)().frustums.directions)
+    H, W, S, NL = args.height, args.width, args.samples, args.latents
+    fx = (W / 2) / math.tan(math.radians(30.0))
+    eye = torch.tensor([0.0, -0.9, 0.25]); f = torch.nn.functional.normalize(-eye, dim=0)
+    rt = torch.nn.functional.normalize(torch.linalg.cross(f, torch.tensor([0.0, 0.0, 1.0])), dim=0)
+    c2w = torch.cat([torch.stack([rt, torch.linalg.cross(rt, f), -f], 1), eye[:, None]], 1)
+    o, d, dn = pinhole_rays(H, W, fx, fx, W / 2, H / 2, c2w, dev)
+    Z0, sc = (t.to(dev) for t in _latents())
+    codes = torch.randn(NL, 100, 3, generator=torch.Generator().manual_seed(3)).to(dev)     # SURVEY 8d: 64 latent codes N(0,1), seed 3
+    n = H * W
+    tiles = [(a, min(n, a + args.tile)) for a in range(0, n, args.tile)][rank::world]
+    my_dirs = torch.cat([d[a:b] for a, b in tiles]).contiguous() if tiles else d[:0]
+    offs = [0]
+    for a, b in tiles:
+        offs.append(offs[-1] + (b - a))
+    mm = global_steps_minmax(o, d, S)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    caches = []
+    for a, b in tiles:
+        out = r.render(o[a:b].contiguous(), d[a:b].contiguous(), dn[a:b].contiguous(), S, Z0[0], sc[0], steps_minmax=mm, want_cache=True,
+                       collapse_cache=not args.per_sample_cache)
+        c = out["relight_cache"]
+        # keep what a new illumination needs; collapse nothing (parity with a full re-render is tested in tests/test_gpu_render.py)
+        caches.append(c)
+    e1.record()
+    torch.cuda.synchronize()
+    build_s = e0.elapsed_time(e1) / 1e3
+    cache_bytes = sum(sum(v.numel() * v.element_size() for v in c.values()) for c in caches)
+
+    def sweep():
+        last = None
+        for k in range(NL):
+            rad, bg = r.illumination_for(codes[k], sc[0], my_dirs)          # two RENI++ decodes per latent, not per tile
+            for i, c in enumerate(caches):
+                last = r.relight(c, codes[k], sc[0], radiance=rad, background=bg[offs[i]:offs[i + 1]])
+        return last
+
+    for _ in range(max(1, args.warmup // 3)):
+        sweep()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    l0 = _lib.launches
+    ts = []
+    for _ in range(args.steps):
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record(); sweep(); s1.record()
+        torch.cuda.synchronize()
+        ts.append(s0.elapsed_time(s1) / 1e3)
+    t = sum(ts)
+    if dist is not None:
+        tt = torch.tensor([t, build_s], device=dev, dtype=torch.float64); dist.all_reduce(tt, op=dist.ReduceOp.MAX); t, build_s = (float(x) for x in tt)
+    if rank == 0:
+        peaks = _peaks()
+        # bytes one relight pass must read per ray: the collapsed coefficients D x 3 x 4 (or, per-sample cache: normals 12 + wa 12 +
+        # inv_count 4 per sample and D' x 4 visibilities) + accumulation + direction; writes 12
+        Dp = int(r.shader.mask.sum())
+        per_ray = (S * 28 + Dp * 4) if args.per_sample_cache else 642 * 12
+        algo = n * (per_ray + 16 + 12) * NL * args.steps
+        print(json.dumps({"metric": "relit rays/s (fixed geometry, new RENI++ latent code per pass)", "value": n * NL * args.steps / t, "unit": UNIT, "n_gpus": world,
+                          "steps": args.steps, "warmup": max(1, args.warmup // 3), "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "strong",
+                          "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": f"BASELINE.json configs[4]: relighting sweep, {W}x{H} frame, {S} samples/ray, {NL} latent codes per step, "
+                                                 f"642 icosphere directions (D'={Dp} cached visibilities per ray), tiles of {args.tile} rays over {world} GPU(s)",
+                                     "parallelism": f"ray tiles x{world}, weights replicated, no collective", "l2": f"relight cache {cache_bytes / 2**30:.2f} GiB per rank exceeds L2",
+                                     "cache_build_s": build_s, "ms_per_latent_frame": 1e3 * t / args.steps / NL},
+                          "roofline": {"kernel": "lambert_relight_kernel" if args.per_sample_cache else "relight_collapsed_kernel", "bound": "hbm", "achieved": algo / t / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                       "frac": algo / t / 1e9 / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
+                                       "note": "whole-sweep rate over the cache bytes: includes the RENI++ decodes of the direction set and of the per-ray background"},
+                          "gpu_launches": _lib.launches - l0}), flush=True)
+    if dist is not None:
+        dist.barrier(); dist.destroy_process_group()
+
+
 # ------------------------------------------------------------------------------------------ training-step arm (configs[3])
 def _train_batch(R: int, K: int, seed: int):
     """R rays sampled from K synthetic cameras on a ring of radius 0.9 around the origin (z-up,
@@ -415,13 +512,15 @@ def main():
     ap.add_argument("--points", type=int, default=1_000_000)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="shade", choices=["shade", "eval", "train"],
+    ap.add_argument("--workload", default="shade", choices=["shade", "eval", "train", "relight"],
                     help="shade = BASELINE.json configs[1] (the headline line); eval = configs[2] full-image render, train = configs[3] training step (supplementary lines)")
     ap.add_argument("--height", type=int, default=720)
     ap.add_argument("--width", type=int, default=1280)
     ap.add_argument("--samples", type=int, default=128)
     ap.add_argument("--tile", type=int, default=16384)
     ap.add_argument("--sampler", default="uniform", choices=["uniform", "proposal"], help="eval: sample placement (proposal = shipped NeuS-facto default, use --samples 48)")
+    ap.add_argument("--latents", type=int, default=64, help="relight: latent codes per sweep")
+    ap.add_argument("--per-sample-cache", action="store_true", help="relight: keep the per-sample cache instead of the collapsed [R,D,3] coefficients")
     ap.add_argument("--rays", type=int, default=1024, help="train: rays per GPU")
     ap.add_argument("--train-samples", type=int, default=48)
     ap.add_argument("--split", type=int, default=3, choices=[1, 3], help="train: 1 = tf32 GEMMs, 3 = 3xTF32 (fp32-accurate)")
@@ -432,6 +531,9 @@ def main():
         return
     if args.workload == "eval":
         eval_arm(args)
+        return
+    if args.workload == "relight":
+        relight_arm(args)
         return
     if args.workload == "train":
         train_arm(args)

@@ -171,6 +171,15 @@ int nsk_lambert_prep(const float* normals, const float* wa, int64_t R, int S, co
 int nsk_lambert_relight(const float* normals, const float* wa, const float* inv_count, int64_t R, int S,
                         const float* dirs, const int32_t* sel_index, int D, int Dp, const float* radiance,
                         const int32_t* cam, const float* vis_sel, float unoccluded_vis, float* rgb_lin, void* stream);
+/* Collapsed relighting cache (config 5; replaces the per-frame re-render of the reference's illumination animation,
+ * neusky/models/neusky_model.py:1896-1980, publication/render_animation.py:188-221):
+ * nsk_lambert_collapse: H [R,D,3] = vis * sum_s wa * clamp01(n.l_j) * inv_count   (everything but the light colours; OVERWRITTEN)
+ * nsk_relight_collapsed: rgb_lin [R,3] = sum_j H[r,j,:] * radiance[cam(r)][j,:]   (one streaming pass per new illumination) */
+int nsk_lambert_collapse(const float* normals, const float* wa, const float* inv_count, int64_t R, int S, const float* dirs,
+                         const int32_t* sel_index, int D, int Dp, const float* vis_sel, float unoccluded_vis, float* H,
+                         void* stream);
+int nsk_relight_collapsed(const float* H, int64_t R, int D, const float* radiance, const int32_t* cam, float* rgb_lin,
+                          void* stream);
 /* Backward of nsk_lambert_relight for a cotangent g_rgb_lin [R,3]: d_wa [R,S,3], d_normals [R,S,3] (overwritten),
  * d_vis_sel [R,Dp] (overwritten; NULL = skip), d_radiance [K,D,3] (ACCUMULATED INTO with atomics; NULL = skip).  The
  * positively-lit count is piecewise constant, as in torch autograd through renderers.py:93-113. */

@@ -71,6 +71,58 @@ lambert_relight_kernel(const float* __restrict__ normals, const float* __restric
   if (lane == 0) { rgb_lin[ray * 3] = o0; rgb_lin[ray * 3 + 1] = o1; rgb_lin[ray * 3 + 2] = o2; }
 }
 
+// Collapsed relighting cache.  Everything in the Lambertian sum except the light colours is fixed once the
+// geometry is: H[r, j, c] = vis[r, j] * sum_s wa[r, s, c] * clamp01(n[r, s] . l_j) * inv_count[r, s], so a new illumination costs
+// one pass over H: rgb_lin[r, c] = sum_j H[r, j, c] * L[j, c] -- D x 3 floats streamed per ray, no per-sample data, no DDF.
+// one warp per ray, lanes over directions (same arithmetic order as lambert_relight_kernel up to the final product)
+__global__ void __launch_bounds__(LP_WARPS * 32)
+lambert_collapse_kernel(const float* __restrict__ normals, const float* __restrict__ wa, const float* __restrict__ inv_count,
+                        int64_t R, int S, const float* __restrict__ dirs, const int32_t* __restrict__ sel_index, int D, int Dp,
+                        const float* __restrict__ vis_sel, float unocc_vis, float* __restrict__ H) {
+  const int lane = threadIdx.x & 31;
+  const int64_t ray = (int64_t)blockIdx.x * LP_WARPS + (threadIdx.x >> 5);
+  if (ray >= R) return;
+  const float* vr = vis_sel + ray * Dp;
+  float* hr = H + ray * D * 3;
+  for (int j = lane; j < D; j += 32) {
+    const float lx = dirs[j * 3], ly = dirs[j * 3 + 1], lz = dirs[j * 3 + 2];
+    const int sj = sel_index[j];
+    const float v = sj >= 0 ? vr[sj] : unocc_vis;
+    float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+    for (int s = 0; s < S; ++s) {
+      const int64_t i = ray * S + s;
+      float c = normals[i * 3] * lx + normals[i * 3 + 1] * ly + normals[i * 3 + 2] * lz;
+      c = fminf(fmaxf(c, 0.f), 1.f) * inv_count[i];
+      c0 = fmaf(wa[i * 3], c, c0); c1 = fmaf(wa[i * 3 + 1], c, c1); c2 = fmaf(wa[i * 3 + 2], c, c2);
+    }
+    hr[j * 3] = c0 * v; hr[j * 3 + 1] = c1 * v; hr[j * 3 + 2] = c2 * v;
+  }
+}
+
+// rgb_lin[r, c] = sum_j H[r, j, c] * L[cam(r)][j, c]: one warp per ray streaming its D*3 floats (HBM-bound: 12 D bytes per ray)
+__global__ void __launch_bounds__(LP_WARPS * 32)
+relight_collapsed_kernel(const float* __restrict__ H, int64_t R, int D, const float* __restrict__ radiance,
+                         const int32_t* __restrict__ cam, float* __restrict__ rgb_lin) {
+  const int lane = threadIdx.x & 31;
+  const int64_t ray = (int64_t)blockIdx.x * LP_WARPS + (threadIdx.x >> 5);
+  if (ray >= R) return;
+  const float* hr = H + ray * D * 3;
+  const float* rad = radiance + (int64_t)(cam ? cam[ray] : 0) * D * 3;
+  // lane l owns flat elements l, l + 96, l + 192, ... of the three interleaved phases: element e = 3 j + c has channel e % 3;
+  // with a stride of 96 = 32 * 3 the channel of a lane's elements never changes within a phase
+  float acc[3] = {0.f, 0.f, 0.f};
+  const int n = D * 3;
+#pragma unroll
+  for (int ph = 0; ph < 3; ++ph) {
+    float a = 0.f;
+    for (int e = ph * 32 + lane; e < n; e += 96) a = fmaf(__ldcs(hr + e), __ldg(rad + e), a);
+    const int ch = (ph * 32 + lane) % 3;
+    acc[0] += ch == 0 ? a : 0.f; acc[1] += ch == 1 ? a : 0.f; acc[2] += ch == 2 ? a : 0.f;
+  }
+  const float o0 = warp_sum(acc[0]), o1 = warp_sum(acc[1]), o2 = warp_sum(acc[2]);
+  if (lane == 0) { rgb_lin[ray * 3] = o0; rgb_lin[ray * 3 + 1] = o1; rgb_lin[ray * 3 + 2] = o2; }
+}
+
 // Backward of lambert_relight_kernel for a cotangent g [R,3] of rgb_lin:
 //   d wa [R,S,3], d normals [R,S,3] (lanes = samples), d vis_sel [R,Dp], d radiance [K,D,3] (lanes = directions, atomics).
 // The count of positively lit directions is piecewise constant (no gradient), as in torch (renderers.py:101-106).
@@ -206,6 +258,29 @@ extern "C" int nsk_lambert_relight(const float* normals, const float* wa, const 
   nsk::lambert_relight_kernel<<<(unsigned)blocks, nsk::LP_WARPS * 32, 0, nsk::as_stream(stream)>>>(
       normals, wa, inv_count, R, S, dirs, sel_index, D, Dp, radiance, cam, vis_sel, unoccluded_vis, rgb_lin);
   return nsk::check_launch("lambert_relight_kernel");
+}
+
+extern "C" int nsk_lambert_collapse(const float* normals, const float* wa, const float* inv_count, int64_t R, int S,
+                                    const float* dirs, const int32_t* sel_index, int D, int Dp, const float* vis_sel,
+                                    float unoccluded_vis, float* H, void* stream) {
+  if (R == 0) return 0;
+  NSK_REQUIRE(S >= 1 && D >= 1, "nsk_lambert_collapse: S and D must be >= 1");
+  NSK_REQUIRE(normals && wa && inv_count && dirs && sel_index && H && (vis_sel || Dp == 0), "nsk_lambert_collapse: null pointer");
+  const int64_t blocks = (R + nsk::LP_WARPS - 1) / nsk::LP_WARPS;
+  NSK_REQUIRE(blocks < (1ll << 31), "nsk_lambert_collapse: too many rays for one launch");
+  nsk::lambert_collapse_kernel<<<(unsigned)blocks, nsk::LP_WARPS * 32, 0, nsk::as_stream(stream)>>>(
+      normals, wa, inv_count, R, S, dirs, sel_index, D, Dp, vis_sel, unoccluded_vis, H);
+  return nsk::check_launch("lambert_collapse_kernel");
+}
+
+extern "C" int nsk_relight_collapsed(const float* H, int64_t R, int D, const float* radiance, const int32_t* cam, float* rgb_lin,
+                                     void* stream) {
+  if (R == 0) return 0;
+  NSK_REQUIRE(D >= 1 && H && radiance && rgb_lin, "nsk_relight_collapsed: null pointer / D");
+  const int64_t blocks = (R + nsk::LP_WARPS - 1) / nsk::LP_WARPS;
+  NSK_REQUIRE(blocks < (1ll << 31), "nsk_relight_collapsed: too many rays for one launch");
+  nsk::relight_collapsed_kernel<<<(unsigned)blocks, nsk::LP_WARPS * 32, 0, nsk::as_stream(stream)>>>(H, R, D, radiance, cam, rgb_lin);
+  return nsk::check_launch("relight_collapsed_kernel");
 }
 
 extern "C" int nsk_lambert_relight_bwd(const float* normals, const float* wa, const float* inv_count, int64_t R, int S,

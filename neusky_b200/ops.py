@@ -326,6 +326,35 @@ def lambert_relight(normals, wa, inv_count, dirs, sel_index, radiance, vis_sel, 
     return rgb_lin
 
 
+def lambert_collapse(normals, wa, inv_count, dirs, sel_index, vis_sel, unoccluded_vis: float = 1.0) -> Tensor:
+    """Per-(ray, direction) shading coefficients H [R,D,3] with visibility folded in: the relighting cache (config 5)."""
+    R, S = normals.shape[0], normals.shape[1]
+    D, Dp = dirs.shape[0], vis_sel.shape[1]
+    normals, wa = _chk("normals", normals, shape=(R, S, 3)), _chk("wa", wa, shape=(R, S, 3))
+    inv_count = _chk("inv_count", inv_count, shape=(R, S))
+    dirs = _chk("dirs", dirs, shape=(D, 3))
+    sel_index = _chk("sel_index", sel_index, dtype=torch.int32, shape=(D,))
+    vis_sel = _chk("vis_sel", vis_sel, shape=(R, Dp))
+    H = torch.empty((R, D, 3), device=normals.device, dtype=torch.float32)
+    _lib.check(_lib.load().nsk_lambert_collapse(_ptr(normals), _ptr(wa), _ptr(inv_count), c_int64(R), c_int(S), _ptr(dirs), _ptr(sel_index), c_int(D), c_int(Dp),
+                                                _ptr(vis_sel), c_float(unoccluded_vis), _ptr(H), _stream(normals)), "nsk_lambert_collapse")
+    return H
+
+
+def relight_collapsed(H: Tensor, radiance: Tensor, cam: Optional[Tensor] = None) -> Tensor:
+    """H [R,D,3], radiance [K,D,3] -> linear rgb [R,3]: one streaming pass per new illumination."""
+    R, D = H.shape[0], H.shape[1]
+    H = _chk("H", H, shape=(R, D, 3))
+    radiance = _chk("radiance", radiance, shape=(None, D, 3))
+    if cam is not None:
+        cam = _chk("cam", cam, dtype=torch.int32, shape=(R,))
+    elif radiance.shape[0] != 1:
+        raise ValueError("radiance has several tables but no per-ray camera index was given")
+    rgb_lin = torch.empty((R, 3), device=H.device, dtype=torch.float32)
+    _lib.check(_lib.load().nsk_relight_collapsed(_ptr(H), c_int64(R), c_int(D), _ptr(radiance), _ptr(cam), _ptr(rgb_lin), _stream(H)), "nsk_relight_collapsed")
+    return rgb_lin
+
+
 def lambert_relight_bwd(normals, wa, inv_count, dirs, sel_index, radiance, vis_sel, g_rgb_lin, cam=None, unoccluded_vis: float = 1.0, want_vis: bool = True, want_radiance: bool = True):
     """-> (d_wa [R,S,3], d_normals [R,S,3], d_vis_sel [R,Dp] | None, d_radiance [K,D,3] | None)."""
     R, S = normals.shape[0], normals.shape[1]

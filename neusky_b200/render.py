@@ -191,7 +191,7 @@ class RayRenderer:
     @torch.no_grad()
     def render(self, origins: Tensor, directions: Tensor, dnorm: Tensor, S: int, latent: Tensor, scale: Tensor, rotation: Optional[Tensor] = None,
                threshold: float = 0.1, sigmoid_scale: float = 25.0, cos_anneal_ratio: float = 1.0, want_vis: bool = False,
-               steps_minmax: Optional[Tensor] = None, want_cache: bool = False) -> Dict[str, Tensor]:
+               steps_minmax: Optional[Tensor] = None, want_cache: bool = False, collapse_cache: bool = False) -> Dict[str, Tensor]:
         """origins/directions [R,3], dnorm [R,1]; latent [L,3]; scale scalar tensor.  All rays belong to one camera."""
         R = origins.shape[0]
         sh = self.shader
@@ -226,22 +226,46 @@ class RayRenderer:
         if want_cache:
             # everything a new illumination needs (fixed geometry): per-sample shading inputs, per-ray visibility of the
             # DDF directions, accumulation.  The geometry-only outputs above stay valid for every latent code.
-            out["relight_cache"] = {"normals": c["normals"], "wa": c["wa"], "inv_count": s["inv_count"], "visibility_sel": s["visibility_sel"],
-                                    "accumulation": c["accumulation"], "directions": directions}
+            if collapse_cache:
+                # collapsed form: per (ray, direction) coefficients with the visibility folded in -- D x 3 floats
+                # per ray, independent of S; a new illumination is one streaming pass over it
+                H = ops.lambert_collapse(c["normals"], c["wa"], s["inv_count"], sh.dirs, sh.sel_index, s["visibility_sel"], sh.lower_vis)
+                out["relight_cache"] = {"H": H, "accumulation": c["accumulation"], "directions": directions}
+            else:
+                out["relight_cache"] = {"normals": c["normals"], "wa": c["wa"], "inv_count": s["inv_count"], "visibility_sel": s["visibility_sel"],
+                                        "accumulation": c["accumulation"], "directions": directions}
         return out
 
     @torch.no_grad()
-    def relight(self, cache: Dict[str, Tensor], latent: Tensor, scale: Tensor, rotation: Optional[Tensor] = None) -> Tensor:
+    def relight(self, cache: Dict[str, Tensor], latent: Tensor, scale: Tensor, rotation: Optional[Tensor] = None,
+                radiance: Optional[Tensor] = None, background: Optional[Tensor] = None) -> Tensor:
         """sRGB [R,3] of the cached rays under another RENI++ latent code / rotation (BASELINE.json config 5): RENI++ decode
         of the direction set and of the per-ray background, then one Lambertian pass over the cached visibility --
-        no SDF field, no compositing, no DDF.  Equals render(...)["rgb"] for the same latent."""
+        no SDF field, no compositing, no DDF.  Equals render(...)["rgb"] for the same latent.
+        `radiance` [1,D,3] / `background` [R,3]: already decoded for this latent (a frame cut into tiles decodes the direction
+        table and the background of all its rays once per latent instead of once per tile: `illumination_for`)."""
         sh = self.shader
+        if radiance is None or background is None:
+            Z = latent.reshape(1, -1, 3).to(self.device, torch.float32)
+            sc = scale.reshape(1).to(self.device, torch.float32)
+            if radiance is None:
+                radiance = sh.radiance_table(Z, sc, rotation)
+            if background is None:
+                background = ops.reni_radiance_table(cache["directions"], Z, sc, sh.reni_blob, rotation)[0]
+        bg = background
+        if "H" in cache:
+            lin = ops.relight_collapsed(cache["H"], radiance)
+        else:
+            lin = ops.lambert_relight(cache["normals"], cache["wa"], cache["inv_count"], sh.dirs, sh.sel_index, radiance, cache["visibility_sel"], None, sh.lower_vis)
+        return ops.shade_finalize(lin, bg, cache["accumulation"])
+
+    @torch.no_grad()
+    def illumination_for(self, latent: Tensor, scale: Tensor, ray_directions: Tensor, rotation: Optional[Tensor] = None):
+        """(radiance table [1,D,3], per-ray background [R,3]) of one latent code for a whole ray bundle: the two RENI++ decodes
+        of `relight`, done once per latent."""
         Z = latent.reshape(1, -1, 3).to(self.device, torch.float32)
         sc = scale.reshape(1).to(self.device, torch.float32)
-        radiance = sh.radiance_table(Z, sc, rotation)
-        bg = ops.reni_radiance_table(cache["directions"], Z, sc, sh.reni_blob, rotation)[0]
-        lin = ops.lambert_relight(cache["normals"], cache["wa"], cache["inv_count"], sh.dirs, sh.sel_index, radiance, cache["visibility_sel"], None, sh.lower_vis)
-        return ops.shade_finalize(lin, bg, cache["accumulation"])
+        return self.shader.radiance_table(Z, sc, rotation), ops.reni_radiance_table(ray_directions, Z, sc, self.shader.reni_blob, rotation)[0]
 
 
 def global_steps_minmax(origins: Tensor, directions: Tensor, S: int) -> Tensor:

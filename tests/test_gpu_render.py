@@ -128,6 +128,8 @@ def test_relight_from_cache_equals_rerender(dev, scene):
     o, d, dn = (t.to(dev) for t in (scene["o"], scene["d"], scene["dn"]))
     sc = torch.zeros((), device=dev)
     base = r.render(o, d, dn, scene["S"], scene["Z"].to(dev), sc, want_cache=True)
+    coll = r.render(o, d, dn, scene["S"], scene["Z"].to(dev), sc, want_cache=True, collapse_cache=True)["relight_cache"]
+    assert set(coll) == {"H", "accumulation", "directions"} and coll["H"].shape == (o.shape[0], scene["dirs"].shape[0], 3)
     g = torch.Generator().manual_seed(11)
     ang = 0.7
     rot = torch.tensor([[float(torch.cos(torch.tensor(ang))), -float(torch.sin(torch.tensor(ang))), 0.0],
@@ -138,6 +140,13 @@ def test_relight_from_cache_equals_rerender(dev, scene):
         full = r.render(o, d, dn, scene["S"], Zk, sc, rotation=rk)["rgb"]
         fast = r.relight(base["relight_cache"], Zk, sc, rotation=rk)
         assert float((full - fast).abs().max()) <= 2e-5, float((full - fast).abs().max())
+        fast2 = r.relight(coll, Zk, sc, rotation=rk)                  # collapsed [R, D, 3] cache: one streaming pass per latent
+        assert float((full - fast2).abs().max()) <= 2e-5, float((full - fast2).abs().max())
+        rad, bg = r.illumination_for(Zk, sc, d, rotation=rk)          # decodes hoisted out of the per-tile call
+        half = o.shape[0] // 2
+        c0 = {k2: (v[:half] if k2 != "directions" else v[:half]) for k2, v in coll.items()}
+        fast3 = r.relight(c0, Zk, sc, rotation=rk, radiance=rad, background=bg[:half])
+        assert torch.equal(fast3, fast2[:half])
     assert float((base["rgb"] - r.relight(base["relight_cache"], scene["Z"].to(dev), sc)).abs().max()) <= 2e-5
 
 
