@@ -171,6 +171,18 @@ int nsk_lambert_prep(const float* normals, const float* wa, int64_t R, int S, co
 int nsk_lambert_relight(const float* normals, const float* wa, const float* inv_count, int64_t R, int S,
                         const float* dirs, const int32_t* sel_index, int D, int Dp, const float* radiance,
                         const int32_t* cam, const float* vis_sel, float unoccluded_vis, float* rgb_lin, void* stream);
+/* RENI++ decode of many rows on the tensor cores (csrc/reni_rows_tc.cu): the same arithmetic as nsk_reni_decode_rows_fwd
+ * (RENIField.get_outputs, ns_reni/reni/illumination_fields/reni_illumination_field.py:493-573; Decoder, transformer_decoder.py:21-155)
+ * with the 13 dense layers on nsk_gemm_tf32_nt (3xTF32).  These entry points are the pieces between the contractions:
+ * nsk_reni_prep: workspace [K*NL*H + K*L*2] <- attention vectors [K,NL,H] then rotated latent xy [K,L,2] (per latent code).
+ * nsk_reni_pe_rows: pe [N,512] <- decoder input rows (510 features, zero padded); row_cam [N] int32 = code of each row (NULL = 0);
+ *     zxy = workspace + K*NL*H.
+ * nsk_reni_ln_rows: x [N,128] <- LayerNorm(x + add[code(row) * add_stride : +128]) * ln_weight + ln_bias, in place (add NULL = 0). */
+int nsk_reni_prep(const float* latents, const float* rotation, int64_t K, const float* weights, int latent_dim, int hidden,
+                  int num_layers, float* workspace, void* stream);
+int nsk_reni_pe_rows(const float* dirs, const int* row_cam, int64_t N, const float* zxy, int latent_dim, float* pe, void* stream);
+int nsk_reni_ln_rows(float* x, int64_t N, const float* add, int add_stride, const int* row_cam, const float* ln_weight,
+                     const float* ln_bias, void* stream);
 /* Collapsed relighting cache (config 5; replaces the per-frame re-render of the reference's illumination animation,
  * neusky/models/neusky_model.py:1896-1980, publication/render_animation.py:188-221):
  * nsk_lambert_collapse: H [R,D,3] = vis * sum_s wa * clamp01(n.l_j) * inv_count   (everything but the light colours; OVERWRITTEN)

@@ -244,6 +244,59 @@ def reni_radiance_table(dirs: Tensor, latents: Tensor, scale: Optional[Tensor], 
     return out
 
 
+def reni_rows_tc(dirs: Tensor, latents: Tensor, scale: Optional[Tensor], packed: Tensor, gemm_w: Dict[str, Tensor], rotation: Optional[Tensor] = None,
+                 row_cam: Optional[Tensor] = None, hidden: int = 128, num_layers: int = 6, log_domain: bool = True, chunk: int = 1 << 20) -> Tensor:
+    """dirs [N,3] (+ row_cam [N] int32 when K > 1), latents [K,L,3], scale [K] -> HDR radiance [N,3]: the decoder's 13 dense layers on
+    the 3xTF32 tensor-core GEMM (fp32-accurate), prep / input rows / LayerNorm on the kernels of csrc/reni_rows_tc.cu.  Same
+    result as reni_radiance_rows up to fp32 summation order; meant for large N (a frame's background rays).  `packed` =
+    packing.pack_reni(...), `gemm_w` = packing.pack_reni_gemm(...).  Rows are processed in chunks to bound the [N,512] input buffer."""
+    N = dirs.shape[0]
+    K, L = latents.shape[0], latents.shape[1]
+    dirs = _chk("dirs", dirs, shape=(N, 3))
+    latents = _chk("latents", latents, shape=(K, L, 3))
+    if row_cam is not None:
+        row_cam = _chk("row_cam", row_cam, dtype=torch.int32, shape=(N,))
+    elif K != 1:
+        raise ValueError("reni_rows_tc: several latent codes need row_cam")
+    if scale is not None:
+        scale = _chk("scale", scale, shape=(K,))
+    if rotation is not None:
+        if rotation.dim() == 3:
+            raise NotImplementedError("Batched rotation not implemented yet")  # reni_illumination_field.py:520-521
+        rotation = _chk("rotation", rotation, shape=(3, 3))
+    lib = _lib.load()
+    need = lib.nsk_reni_weights_floats(c_int(L), c_int(hidden), c_int(num_layers))
+    packed = _chk("packed", packed, shape=(need,))
+    dev = dirs.device
+    ws = torch.empty((K * num_layers * hidden + K * L * 2,), device=dev, dtype=torch.float32)
+    _lib.check(lib.nsk_reni_prep(_ptr(latents), _ptr(rotation), c_int64(K), _ptr(packed), c_int(L), c_int(hidden), c_int(num_layers), _ptr(ws), _stream(dirs)), "nsk_reni_prep")
+    attn = ws[:K * num_layers * hidden].view(K, num_layers, hidden)
+    zxy = ws[K * num_layers * hidden:]
+    out = torch.empty((N, 3), device=dev, dtype=torch.float32)
+    st = _stream(dirs)
+    for a in range(0, N, chunk):
+        b = min(N, a + chunk)
+        n = b - a
+        d_c = dirs[a:b]
+        rc = None if row_cam is None else row_cam[a:b]
+        pe = torch.empty((n, 512), device=dev, dtype=torch.float32)
+        _lib.check(lib.nsk_reni_pe_rows(_ptr(d_c), _ptr(rc), c_int64(n), _ptr(zxy), c_int(L), _ptr(pe), st), "nsk_reni_pe_rows")
+        x = gemm_nt(pe, gemm_w["res_w"], bias=gemm_w["res_b"], split=3)                       # [n,128]
+        del pe
+        for i in range(num_layers):
+            _lib.check(lib.nsk_reni_ln_rows(_ptr(x), c_int64(n), _ptr(attn[:, i]), c_int(num_layers * hidden), _ptr(rc), _ptr(gemm_w[f"n1w{i}"]), _ptr(gemm_w[f"n1b{i}"]), st),
+                       "nsk_reni_ln_rows")                                                     # x = LN(attn_i + x)
+            h = gemm_nt(x, gemm_w[f"f0w{i}"], bias=gemm_w[f"f0b{i}"], act="relu", split=3)
+            gemm_nt(h, gemm_w[f"f2w{i}"], bias=gemm_w[f"f2b{i}"], out=x, accumulate=True, split=3)   # x += fc2(relu(fc1 x))
+            _lib.check(lib.nsk_reni_ln_rows(_ptr(x), c_int64(n), _ptr(None), c_int(0), _ptr(None), _ptr(gemm_w[f"n2w{i}"]), _ptr(gemm_w[f"n2b{i}"]), st), "nsk_reni_ln_rows")
+        o = gemm_nt(x, gemm_w["fc_w"], bias=gemm_w["fc_b"], split=3)                            # [n,3]
+        if scale is not None:
+            sc = scale if rc is None else scale[rc.long()][:, None]
+            o = (o + sc) if log_domain else (o * torch.exp(sc))                                 # + log(exp(scale)) in the log domain (:561-565)
+        out[a:b] = torch.exp(o) if log_domain else o
+    return out
+
+
 def reni_radiance_rows(dirs: Tensor, row_cam: Tensor, latents: Tensor, scale: Optional[Tensor], packed: Tensor, rotation: Optional[Tensor] = None, hidden: int = 128, num_layers: int = 6, log_domain: bool = True) -> Tensor:
     """dirs [N,3], row_cam [N] int32 (latent code of each row), latents [K,L,3], scale [K] -> HDR radiance [N,3]
     (the per-ray background colours of a mixed-camera batch, neusky_model.py:535-549)."""

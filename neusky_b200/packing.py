@@ -52,6 +52,21 @@ def pack_reni(p: Dict[str, Tensor], num_layers: int = 6) -> Tensor:
     return torch.cat([x.to(torch.float32).flatten() for x in parts]).contiguous()
 
 
+def pack_reni_gemm(p: Dict[str, Tensor], num_layers: int = 6) -> Dict[str, Tensor]:
+    """Decoder weights in the [out, in] layout nsk_gemm_tf32_nt takes (torch's own), for ops.reni_rows_tc: the residual
+    projection zero-padded from 510 to 512 input columns, per layer norm1 / fc.0 / fc.2 / norm2, and the 128 -> 3 head."""
+    f = lambda k: p[k].to(torch.float32).contiguous()
+    Wr = f("network.residual_projection.weight")
+    Wp = Wr.new_zeros((Wr.shape[0], 512))
+    Wp[:, :Wr.shape[1]] = Wr
+    out = {"res_w": Wp.contiguous(), "res_b": f("network.residual_projection.bias"), "fc_w": f("network.fc.weight"), "fc_b": f("network.fc.bias")}
+    for i in range(num_layers):
+        pre = f"network.layers.{i}."
+        out.update({f"n1w{i}": f(pre + "norm1.weight"), f"n1b{i}": f(pre + "norm1.bias"), f"f0w{i}": f(pre + "fc.0.weight"), f"f0b{i}": f(pre + "fc.0.bias"),
+                    f"f2w{i}": f(pre + "fc.2.weight"), f"f2b{i}": f(pre + "fc.2.bias"), f"n2w{i}": f(pre + "norm2.weight"), f"n2b{i}": f(pre + "norm2.bias")})
+    return out
+
+
 def pack_reni_bwd(p: Dict[str, Tensor], num_layers: int = 6) -> Tensor:
     """fp32 blob for nsk_reni_decode_bwd (see reni_bwd_layout()): the decoder's linear weights in torch's own [out][in]
     layout, which is the coalesced one for the transposed products of the backward pass."""

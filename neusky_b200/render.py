@@ -33,6 +33,8 @@ class SkyShader:
         self.hash_table = ddf_params["position_encoding.hash_table"].to(self.device, torch.float32).contiguous()
         self.set_ddf_weights(ddf_params)
         self.reni_blob = packing.pack_reni({k: v.to(self.device) for k, v in reni_params.items()}) if reni_params is not None else None
+        self.reni_gemm = packing.pack_reni_gemm({k: v.to(self.device) for k, v in reni_params.items()}) if reni_params is not None else None
+        self.reni_tc_min_rows = 8192    # below this the fp32 SIMT decode wins (one launch instead of ~30)
         self.k4_events = None   # bench hook: when a list, (start, end) CUDA events are recorded around every K4 launch
 
     def set_ddf_weights(self, ddf_params: Dict[str, Tensor]) -> None:
@@ -56,6 +58,13 @@ class SkyShader:
 
     def radiance_table(self, latents: Tensor, scale: Optional[Tensor], rotation: Optional[Tensor] = None) -> Tensor:
         return ops.reni_radiance_table(self.dirs, latents, scale, self.reni_blob, rotation)
+
+    def radiance_rows(self, ray_directions: Tensor, latents: Tensor, scale: Optional[Tensor], rotation: Optional[Tensor] = None) -> Tensor:
+        """HDR radiance [N,3] along N directions for ONE latent code [1,L,3] (per-ray background, neusky_model.py:535-549): the
+        tensor-core GEMM chain for frame-sized batches, the fp32 SIMT decode for small ones."""
+        if ray_directions.shape[0] >= self.reni_tc_min_rows:
+            return ops.reni_rows_tc(ray_directions, latents, scale, self.reni_blob, self.reni_gemm, rotation)
+        return ops.reni_radiance_table(ray_directions, latents, scale, self.reni_blob, rotation)[0]
 
     # -- shading ---------------------------------------------------------------------------------
     def shade(self, points: Tensor, normals: Tensor, wa: Tensor, radiance: Tensor, cam: Optional[Tensor] = None,
@@ -191,8 +200,11 @@ class RayRenderer:
     @torch.no_grad()
     def render(self, origins: Tensor, directions: Tensor, dnorm: Tensor, S: int, latent: Tensor, scale: Tensor, rotation: Optional[Tensor] = None,
                threshold: float = 0.1, sigmoid_scale: float = 25.0, cos_anneal_ratio: float = 1.0, want_vis: bool = False,
-               steps_minmax: Optional[Tensor] = None, want_cache: bool = False, collapse_cache: bool = False) -> Dict[str, Tensor]:
-        """origins/directions [R,3], dnorm [R,1]; latent [L,3]; scale scalar tensor.  All rays belong to one camera."""
+               steps_minmax: Optional[Tensor] = None, want_cache: bool = False, collapse_cache: bool = False,
+               radiance: Optional[Tensor] = None, background: Optional[Tensor] = None) -> Dict[str, Tensor]:
+        """origins/directions [R,3], dnorm [R,1]; latent [L,3]; scale scalar tensor.  All rays belong to one camera.
+        `radiance` [1,D,3] / `background` [R,3]: this latent's RENI++ decodes when the caller already has them (a tiled frame
+        decodes once per frame, `illumination_for`, instead of once per tile)."""
         R = origins.shape[0]
         sh = self.shader
         near, far = sphere_collider(origins, directions)
@@ -211,10 +223,14 @@ class RayRenderer:
         f = ops.sdf_field(x, self.sdf_blob, self.sdf_table, self.scalings, self.log2_T, impl=self.sdf_impl)
         c = ops.neus_composite(f["sdf"], f["gradient"], f["albedo"], directions, starts, ends, ends - starts, dnorm, self.inv_s, cos_anneal_ratio, False,
                                steps_minmax=steps_minmax)
-        Z = latent.reshape(1, -1, 3).to(self.device, torch.float32)
-        sc = scale.reshape(1).to(self.device, torch.float32)
-        radiance = sh.radiance_table(Z, sc, rotation)                                    # [1,D,3]
-        bg = ops.reni_radiance_table(directions, Z, sc, sh.reni_blob, rotation)[0]      # per-ray background (neusky_model.py:535-549)
+        if radiance is None or background is None:
+            Z = latent.reshape(1, -1, 3).to(self.device, torch.float32)
+            sc = scale.reshape(1).to(self.device, torch.float32)
+            if radiance is None:
+                radiance = sh.radiance_table(Z, sc, rotation)                            # [1,D,3]
+            if background is None:
+                background = sh.radiance_rows(directions, Z, sc, rotation)               # per-ray background (neusky_model.py:535-549)
+        bg = background
         pts = ops.surface_points(origins, directions, c["p2p_dist"], sh.radius)
         s = sh.shade(pts, c["normals"], c["wa"], radiance, want_vis=want_vis or want_cache, threshold=threshold, sigmoid_scale=sigmoid_scale)
         rgb = ops.shade_finalize(s["rgb_lin"], bg, c["accumulation"])
@@ -251,7 +267,7 @@ class RayRenderer:
             if radiance is None:
                 radiance = sh.radiance_table(Z, sc, rotation)
             if background is None:
-                background = ops.reni_radiance_table(cache["directions"], Z, sc, sh.reni_blob, rotation)[0]
+                background = sh.radiance_rows(cache["directions"], Z, sc, rotation)
         bg = background
         if "H" in cache:
             lin = ops.relight_collapsed(cache["H"], radiance)
@@ -265,7 +281,7 @@ class RayRenderer:
         of `relight`, done once per latent."""
         Z = latent.reshape(1, -1, 3).to(self.device, torch.float32)
         sc = scale.reshape(1).to(self.device, torch.float32)
-        return self.shader.radiance_table(Z, sc, rotation), ops.reni_radiance_table(ray_directions, Z, sc, self.shader.reni_blob, rotation)[0]
+        return self.shader.radiance_table(Z, sc, rotation), self.shader.radiance_rows(ray_directions, Z, sc, rotation)
 
 
 def global_steps_minmax(origins: Tensor, directions: Tensor, S: int) -> Tensor:
@@ -294,9 +310,13 @@ def render_image(renderer: "RayRenderer", origins: Tensor, directions: Tensor, d
 
     def fn(idx: Tensor) -> Dict[str, Tensor]:
         outs = {k: [] for k in keys}
+        rad = bg_all = None
+        if idx.numel():          # the frame has one latent code: decode its direction table and the background of this rank's rays once
+            rad, bg_all = renderer.illumination_for(latent, scale, directions[idx].contiguous(), kw.get("rotation"))
         for a in range(0, idx.shape[0], tile):
             sel = idx[a:a + tile]
-            o = renderer.render(origins[sel].contiguous(), directions[sel].contiguous(), dnorm[sel].contiguous(), S, latent, scale, steps_minmax=mm, **kw)
+            o = renderer.render(origins[sel].contiguous(), directions[sel].contiguous(), dnorm[sel].contiguous(), S, latent, scale, steps_minmax=mm,
+                                radiance=rad, background=bg_all[a:a + tile], **kw)
             for k in keys:
                 outs[k].append(o[k])
         if not idx.numel():

@@ -211,3 +211,29 @@ def test_shade_points_simt_vs_oracle(dev, O, R, D):
     out = sh.shade(pts.to(dev), normals[:, None].to(dev), albedo[:, None].to(dev), radiance[None].to(dev), want_vis=True)
     assert torch.allclose(out["visibility"].cpu(), ref_v["visibility"], rtol=0, atol=5e-4)
     assert torch.allclose(out["rgb_lin"].cpu(), ref_rad, rtol=1e-3, atol=1e-5), (out["rgb_lin"].cpu() - ref_rad).abs().max()
+
+
+def test_reni_rows_tensor_core_chain_vs_reference_golden_and_simt(dev, O, golden):
+    """RENI++ decode of many rows on the 3xTF32 GEMM chain (csrc/reni_rows_tc.cu + gemm_tf32.cu): against the reference's own
+    RENIField outputs (tests/golden/reni.npz, per-row latent codes, with and without the latent rotation) and against the fp32
+    SIMT decode on a frame-sized batch.  fp32-accurate: 1e-4 relative on HDR radiance."""
+    from neusky_b200 import ops, packing
+
+    g = golden("reni")
+    p = {k: v.to(dev) for k, v in nb_init.init_reni_params(int(g["seed"])).items()}
+    blob, gw = packing.pack_reni(p), packing.pack_reni_gemm(p)
+    dirs, Z, scale, rot = (torch.from_numpy(g[k]).to(dev) for k in ("dirs", "latents", "scale", "rotation"))
+    K, D = Z.shape[0], dirs.shape[0]
+    rows = dirs[None].expand(K, D, 3).reshape(-1, 3).contiguous()
+    cam = torch.arange(K, device=dev, dtype=torch.int32)[:, None].expand(K, D).reshape(-1).contiguous()
+    for tag, R in (("radiance", None), ("radiance_rot", rot)):
+        out = ops.reni_rows_tc(rows, Z, scale, blob, gw, rotation=R, row_cam=cam).reshape(K, D, 3)
+        ref = torch.from_numpy(g[tag]).to(dev)
+        assert float(((out - ref).abs() / (ref.abs() + 1e-3)).max()) <= 2e-4, tag
+    # frame-sized single-code batch (ragged: not a multiple of any tile), chunked
+    gen = torch.Generator().manual_seed(5)
+    big = torch.nn.functional.normalize(torch.randn(70001, 3, generator=gen), dim=-1).to(dev)
+    a = ops.reni_rows_tc(big, Z[:1], scale[:1], blob, gw, chunk=32768)
+    b = ops.reni_radiance_table(big, Z[:1], scale[:1], blob)[0]
+    assert float(((a - b).abs() / (b.abs() + 1e-3)).max()) <= 2e-4
+    assert ops.reni_rows_tc(big[:0], Z[:1], scale[:1], blob, gw).shape == (0, 3)
