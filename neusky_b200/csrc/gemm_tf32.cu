@@ -12,8 +12,9 @@
 //   warps 0-7   operand staging.  3xTF32 NT (the training step's forward layers and dX): one thread issues tensor-map TMA boxes
 //               (raw fp32 = the hi plane, the MMA truncates to 19 bits), warps 4-7 derive the lo plane (v - trunc(v)) for the
 //               3xTF32 scheme (A_hi.B_hi + A_lo.B_hi + A_hi.B_lo), whose result is fp32-accurate and is what the parity tests
-//               pin.  Other variants: LDGSTS / ld.global -> registers -> st.shared in the no-swizzle K-major core-matrix layout
-//               [K/4][rows][4 x tf32] (the TN variant transposes in registers, so both feed the same descriptors).
+//               pin.  3xTF32 TN (dW): the same roles with MN-major tensor-map boxes (both operands are read as they lie in HBM,
+//               rows = reduction index).  Other variants / fallbacks: LDGSTS / ld.global -> registers -> st.shared in the
+//               no-swizzle K-major core-matrix layout [K/4][rows][4 x tf32] (TN transposes in registers).
 //   warp 16     one lane issues tcgen05.mma (M=128, N<=256, K=8 per instruction) into a double-buffered TMEM accumulator
 //   warps 8-15  epilogue (two per TMEM lane quadrant, alternating 32-column chunks): tcgen05.ld, bias + activation,
 //               st.global (NT) / red.global.add (TN).  The epilogue, not the tensor pipe or HBM, was what bounded the first
@@ -45,10 +46,12 @@ constexpr uint32_t A_LBO = TM * 16, B_LBO = BN * 16;
 // of an item does not overlap the next item's MMAs; it is short since it runs on 8 warps.  With LDGSTS the variant was bound
 // by the issue rate of the 4 loader warps (ncu: loaders stalled issuing, epilogue warps 2/3 idle); the operands therefore
 // arrive as tensor-map TMA boxes (TMA = true: SWIZZLE_64B, one issuing thread), the LDGSTS loader stays as the fallback.
-template <int SPLIT, bool TN> struct Cfg {
+template <int SPLIT, bool TN, bool TMA = false> struct Cfg {
   static constexpr bool PAIR = (SPLIT == 3 && !TN);
-  static constexpr int KC = PAIR ? 16 : 32;
-  static constexpr int ST = PAIR ? 3 : (TN ? (SPLIT == 3 ? 2 : 4) : 3);       // NT keeps 18 KB for the epilogue staging
+  static constexpr bool TNT = (SPLIT == 3 && TN && TMA);                       // 3xTF32 TN fed by MN-major tensor-map boxes
+  static constexpr bool ROLES = PAIR || TNT;                                   // loader + hi/lo splitter warps
+  static constexpr int KC = (PAIR || TNT) ? 16 : 32;
+  static constexpr int ST = PAIR ? 3 : (TNT ? 4 : (TN ? (SPLIT == 3 ? 2 : 4) : 3));   // NT keeps 18 KB for the epilogue staging
   static constexpr int TMI = PAIR ? 2 * TM : TM;                              // rows of the A operand per work item
   static constexpr uint32_t A_HALF = TM * KC * 4;
   static constexpr uint32_t A_BYTES = TMI * KC * 4;
@@ -123,6 +126,27 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t smem_addr) {
   d |= (uint64_t)4 << 61;
   return d;
 }
+// MN-major fp32/tf32 operand written by TMA with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B as [MN block of 32][k rows][128 B]: 32 tf32
+// of the MN dimension are contiguous (128 B), consecutive k rows are 128 B apart, 32-byte chunks are XOR-swizzled over 4 rows
+// (Swizzle<2,5,2>: the atom is 32 MN x 4 K).  UMMA layout type 1 = SWIZZLE_128B_BASE32B, which is the mode 32-bit MN-major
+// operands need (with the plain 128B/16B-atom mode the MMA returns zeros; bring-up notes: scripts/tn_debug.py).
+// LBO = byte stride between 32-wide MN blocks, SBO = stride between the two 4-row k atoms of one K=8 instruction (512 B);
+// k-steps advance the start address by 8 rows = 1024 B.
+__device__ __forceinline__ uint64_t make_smem_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((512u >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;
+  return d;
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst_smem, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst_smem),
+               "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+               : "memory");
+}
+
 // 2-D tiled TMA load global -> shared, completion (bytes) on an mbarrier.  c0 = innermost coordinate (k), c1 = row.
 __device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst_smem),
@@ -141,8 +165,8 @@ __device__ __forceinline__ int64_t chunk_start(const Item& it, int c, int nch, i
 }
 
 // fp32 accumulate, tf32 A and B, both K-major
-__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, bool mn_major = false) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (mn_major ? (3u << 15) : 0u) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -213,9 +237,9 @@ __device__ __forceinline__ float dact_from_output(float a, int dact) {
 template <int SPLIT, bool TN, bool TMA>
 __global__ void __launch_bounds__(THREADS, 1) gemm_tf32_kernel(const Params p, const __grid_constant__ CUtensorMap tmA,
                                                                const __grid_constant__ CUtensorMap tmB) {
-  using C = Cfg<SPLIT, TN>;
+  using C = Cfg<SPLIT, TN, TMA>;
   constexpr int ST = C::ST, KC = C::KC, TMI = C::TMI;
-  constexpr bool PAIR = C::PAIR;
+  constexpr bool PAIR = C::PAIR, TNT = C::TNT, ROLES = C::ROLES;
   constexpr uint32_t STAGE = C::STAGE, A_BYTES = C::A_BYTES, B_BYTES = C::B_BYTES, LO_OFF = C::LO_OFF, A_HALF = C::A_HALF;
   (void)A_HALF;
   (void)B_BYTES;
@@ -229,9 +253,9 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32_kernel(const Params p, c
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < ST; ++s) {
-      mbar_init(FULL + 8 * s, PAIR ? 128 : PROD_WARPS * 32);
+      mbar_init(FULL + 8 * s, ROLES ? 128 : PROD_WARPS * 32);
       mbar_init(EMPTY + 8 * s, 1);
-      if (PAIR) mbar_init(RAW + 8 * s, TMA ? 1 : 128);
+      if (ROLES) mbar_init(RAW + 8 * s, TMA ? 1 : 128);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(ACCF + 8 * b, 1);
@@ -249,7 +273,37 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32_kernel(const Params p, c
     // ------------------------------------------------------------------ operand staging
     uint32_t stage = 0, phase = 0;
     const int r8 = lane & 7, kq_lo = lane >> 3;
-    if constexpr (PAIR) {
+    if constexpr (TNT) {
+      // dW = dY^T X with both operands read as they lie in HBM (rows = reduction index m): MN-major tensor-map boxes
+      // [32 columns x KC rows x 4 | 8 column blocks], SWIZZLE_128B_ATOM_32B; no register transposition, no L1tex traffic.
+      if (warp == 0 && lane == 0) {
+        for (int64_t w = blockIdx.x; w < p.n_items; w += gridDim.x) {
+          const Item it = get_item<TN, TMI>(p, w);
+          for (int64_t r = it.r0; r < it.r1; r += KC) {
+            mbar_wait(EMPTY + 8 * stage, phase ^ 1);
+            const uint32_t sa32 = smem_u32(smem + stage * STAGE);
+            mbar_arrive_expect_tx(RAW + 8 * stage, A_BYTES + B_BYTES);
+            tma_load_3d(sa32, &tmA, 0, (int)r, (int)(it.a0 >> 5), RAW + 8 * stage);
+            tma_load_3d(sa32 + A_BYTES, &tmB, 0, (int)r, it.b0 >> 5, RAW + 8 * stage);
+            if (++stage == ST) { stage = 0; phase ^= 1; }
+          }
+        }
+      } else if (warp >= 4) {
+        const uint32_t t128 = (uint32_t)(threadIdx.x & 127) * 16;
+        for (int64_t w = blockIdx.x; w < p.n_items; w += gridDim.x) {
+          const Item it = get_item<TN, TMI>(p, w);
+          for (int64_t r = it.r0; r < it.r1; r += KC) {
+            mbar_wait(RAW + 8 * stage, phase);
+            uint8_t* const sa = smem + stage * STAGE;
+#pragma unroll
+            for (int j = 0; j < (int)((A_BYTES + B_BYTES) / 2048); ++j) fix_lo<LO_OFF>(sa, t128 + (uint32_t)j * 2048);
+            fence_proxy_async_smem();
+            mbar_arrive(FULL + 8 * stage);
+            if (++stage == ST) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    } else if constexpr (PAIR) {
       // Warps 0-3 LOAD: raw fp32 chunks go global -> shared with LDGSTS (they are the hi planes as they are: the MMA
       // truncates); completion is counted on the stage's RAW mbarrier, so the whole ring is in flight.  Warps 4-7 SPLIT: wait
       // RAW, derive the lo planes, publish FULL.  Two roles because fence.proxy.async -- needed before the MMA may read the lo
@@ -503,7 +557,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32_kernel(const Params p, c
         mbar_wait(ACCE + 8 * buf, ((iter >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d = tmem + buf * BN;
-        const uint32_t idesc = make_idesc_tf32(TM, it.bn);
+        const uint32_t idesc = make_idesc_tf32(TM, it.bn, TNT);
         uint32_t acc = 0;
         if (it.r0 >= it.r1) {
           // empty reduction range (TN tail split): nothing to add; still hand the buffer over (epilogue skips it)
@@ -516,10 +570,13 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32_kernel(const Params p, c
           const uint32_t sa = smem_u32(smem + stage * STAGE), sb = sa + A_BYTES;
           const int ksteps = (int)min((int64_t)(KC / 8), (it.r1 - r + 7) / 8);
           for (int j = 0; j < ksteps; ++j) {
-            const uint64_t ah = make_smem_desc(sa + j * 2 * A_LBO, A_LBO, 128), bh = make_smem_desc(sb + j * 2 * B_LBO, B_LBO, 128);
+            constexpr uint32_t MN_LBO = KC * 128;            // TNT: one 32-column block = KC rows x 128 B
+            const uint64_t ah = TNT ? make_smem_desc_mn_sw128(sa + j * 1024, MN_LBO) : make_smem_desc(sa + j * 2 * A_LBO, A_LBO, 128);
+            const uint64_t bh = TNT ? make_smem_desc_mn_sw128(sb + j * 1024, MN_LBO) : make_smem_desc(sb + j * 2 * B_LBO, B_LBO, 128);
             if (SPLIT == 3) {
               const uint32_t lo = LO_OFF;
-              const uint64_t al = make_smem_desc(sa + lo + j * 2 * A_LBO, A_LBO, 128), bl = make_smem_desc(sb + lo + j * 2 * B_LBO, B_LBO, 128);
+              const uint64_t al = TNT ? make_smem_desc_mn_sw128(sa + lo + j * 1024, MN_LBO) : make_smem_desc(sa + lo + j * 2 * A_LBO, A_LBO, 128);
+              const uint64_t bl = TNT ? make_smem_desc_mn_sw128(sb + lo + j * 1024, MN_LBO) : make_smem_desc(sb + lo + j * 2 * B_LBO, B_LBO, 128);
               umma_tf32(d, al, bh, idesc, acc);
               umma_tf32(d, ah, bl, idesc, 1);
               umma_tf32(d, ah, bh, idesc, 1);
@@ -677,9 +734,9 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32_kernel(const Params p, c
   }
 }
 
-template <int SPLIT, bool TN>
+template <int SPLIT, bool TN, bool TMA>
 constexpr size_t smem_bytes() {
-  return (size_t)Cfg<SPLIT, TN>::ST * Cfg<SPLIT, TN>::STAGE + 256 + (TN ? 0 : EPI_BYTES);
+  return (size_t)Cfg<SPLIT, TN, TMA>::ST * Cfg<SPLIT, TN, TMA>::STAGE + 256 + (TN ? 0 : EPI_BYTES);
 }
 
 static int sm_count() {
@@ -725,13 +782,26 @@ static int launch_variant(const Params& p, const CUtensorMap& ma, const CUtensor
   auto kern = gemm_tf32_kernel<SPLIT, TN, TMA>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<SPLIT, TN>());
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<SPLIT, TN, TMA>());
     if (e != cudaSuccess) return fail("gemm_tf32: cudaFuncSetAttribute", cudaGetErrorString(e));
     configured = true;
   }
   const int grid = (int)std::min<int64_t>(p.n_items, sm_count());
-  kern<<<grid, THREADS, smem_bytes<SPLIT, TN>(), st>>>(p, ma, mb);
+  kern<<<grid, THREADS, smem_bytes<SPLIT, TN, TMA>(), st>>>(p, ma, mb);
   return check_launch("gemm_tf32_kernel");
+}
+
+// fp32 [rows, cols] matrix read MN-major: 3-D view (32 columns, rows, cols / 32) -> boxes of 32 x KC rows x `blocks` column blocks,
+// SWIZZLE_128B_ATOM_32B, landing as [block][row][128 B].  cols must be a multiple of 32 (a partial block would read past the row end).
+static bool make_tensor_map_mn(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, int blocks) {
+  TensorMapEncodeFn fn = tensor_map_encoder();
+  if (fn == nullptr || (reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld & 3) != 0 || (cols & 31) != 0) return false;
+  const cuuint64_t dims[3] = {32u, (cuuint64_t)rows, (cuuint64_t)(cols / 32)};
+  const cuuint64_t strides[2] = {(cuuint64_t)ld * 4, 128u};
+  const cuuint32_t box[3] = {32u, (cuuint32_t)box_rows, (cuuint32_t)blocks};
+  const cuuint32_t estr[3] = {1u, 1u, 1u};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 template <int SPLIT, bool TN>
@@ -739,9 +809,17 @@ static int launch(const Params& p, cudaStream_t st) {
   CUtensorMap ma, mb;
   memset(&ma, 0, sizeof(ma));
   memset(&mb, 0, sizeof(mb));
-  if (Cfg<SPLIT, TN>::PAIR && getenv("NSK_GEMM_NO_TMA") == nullptr &&
-      make_tensor_map(&ma, p.A, p.M, p.K, p.lda, Cfg<SPLIT, TN>::TMI) && make_tensor_map(&mb, p.B, p.N, p.K, p.ldb, BN))
-    return launch_variant<SPLIT, TN, Cfg<SPLIT, TN>::PAIR>(p, ma, mb, st);
+  if (getenv("NSK_GEMM_NO_TMA") == nullptr) {
+    if constexpr (Cfg<SPLIT, TN>::PAIR) {
+      if (make_tensor_map(&ma, p.A, p.M, p.K, p.lda, Cfg<SPLIT, TN>::TMI) && make_tensor_map(&mb, p.B, p.N, p.K, p.ldb, BN))
+        return launch_variant<SPLIT, TN, true>(p, ma, mb, st);
+    } else if constexpr (SPLIT == 3 && TN) {
+      // TN: A [M, P = p.N] and B [M, Q = p.K]; the reduction index (rows) must fit the int32 TMA coordinate
+      if (p.M < (1ll << 31) && make_tensor_map_mn(&ma, p.A, p.M, p.N, p.lda, Cfg<3, true, true>::KC, TM / 32) &&
+          make_tensor_map_mn(&mb, p.B, p.M, p.K, p.ldb, Cfg<3, true, true>::KC, BN / 32))
+        return launch_variant<SPLIT, TN, true>(p, ma, mb, st);
+    }
+  }
   return launch_variant<SPLIT, TN, false>(p, ma, mb, st);
 }
 
