@@ -237,3 +237,27 @@ def test_reni_rows_tensor_core_chain_vs_reference_golden_and_simt(dev, O, golden
     b = ops.reni_radiance_table(big, Z[:1], scale[:1], blob)[0]
     assert float(((a - b).abs() / (b.abs() + 1e-3)).max()) <= 2e-4
     assert ops.reni_rows_tc(big[:0], Z[:1], scale[:1], blob, gw).shape == (0, 3)
+
+
+@pytest.mark.parametrize("R,S,D", [(37, 48, 162), (5, 128, 642), (64, 33, 642)])
+def test_lambert_prep_thread_per_sample_matches_warp_per_ray(dev, R, S, D):
+    """Full renders (S >= 32, one camera) take the thread-per-sample kernel; a per-ray camera index (all zero) forces the
+    warp-per-ray kernel on the same data.  inv_count is an exact count (bit-equal); the colour sums differ by summation order."""
+    from neusky_b200 import ops
+
+    g = torch.Generator().manual_seed(R * 1000 + S)
+    nrm = torch.nn.functional.normalize(torch.randn(R, S, 3, generator=g), dim=-1).to(dev)
+    wa = torch.rand(R, S, 3, generator=g).to(dev) / S
+    dirs = torch.nn.functional.normalize(torch.randn(D, 3, generator=g), dim=-1).to(dev)
+    mask = (dirs[:, 2] > 0).to(torch.uint8)
+    rad = torch.exp(torch.randn(1, D, 3, generator=g)).to(dev)
+    ic_a, lin_a = ops.lambert_prep(nrm, wa, dirs, mask, rad, None, 0.75)
+    ic_b, lin_b = ops.lambert_prep(nrm, wa, dirs, mask, rad, torch.zeros(R, dtype=torch.int32, device=dev), 0.75)
+    assert torch.equal(ic_a, ic_b)
+    assert torch.allclose(lin_a, lin_b, rtol=2e-5, atol=1e-6), float((lin_a - lin_b).abs().max())
+    # reference arithmetic (renderers.py:93-113 restricted to the un-masked directions)
+    c = torch.einsum("rsk,dk->rsd", nrm.double(), dirs.double()).clamp(0, 1)
+    cnt = (c > 0).sum(-1).clamp(min=1)
+    unm = (mask == 0).double()
+    ref = (wa.double() * (torch.einsum("rsd,dc->rsc", c * unm, rad[0].double()) / cnt[..., None]) * 0.75).sum(1)
+    assert torch.allclose(lin_a.double(), ref, rtol=1e-4, atol=1e-6)
