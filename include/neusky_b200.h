@@ -192,6 +192,11 @@ int nsk_lambert_collapse(const float* normals, const float* wa, const float* inv
                          void* stream);
 int nsk_relight_collapsed(const float* H, int64_t R, int D, const float* radiance, const int32_t* cam, float* rgb_lin,
                           void* stream);
+/* nsk_lambert_collapse_sel: G [R,Dp,3] = sum_s wa * clamp01(n.l_j) * inv_count over the Dp directions that go through the DDF
+ * (dirs_sel [Dp,3]).  nsk_sky_shade_tc2_fwd called with S = 0 takes this table in its `wa` argument (normals / inv_count may be
+ * NULL) and skips the per-pair loop over the ray's samples -- the form full renders (S = 48..128) use. */
+int nsk_lambert_collapse_sel(const float* normals, const float* wa, const float* inv_count, int64_t R, int S, const float* dirs_sel,
+                             int Dp, float* G, void* stream);
 /* Backward of nsk_lambert_relight for a cotangent g_rgb_lin [R,3]: d_wa [R,S,3], d_normals [R,S,3] (overwritten),
  * d_vis_sel [R,Dp] (overwritten; NULL = skip), d_radiance [K,D,3] (ACCUMULATED INTO with atomics; NULL = skip).  The
  * positively-lit count is piecewise constant, as in torch autograd through renderers.py:93-113. */

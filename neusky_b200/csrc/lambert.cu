@@ -152,6 +152,55 @@ lambert_collapse_kernel(const float* __restrict__ normals, const float* __restri
   }
 }
 
+// G[r, j, c] = sum_s wa[r, s, c] * clamp01(n[r, s] . l_j) * inv_count[r, s] for the Dp directions that go through the DDF: the
+// per-pair Lambert coefficient K4 otherwise recomputes from the S samples in its tail (nsk_sky_shade_tc2_fwd with S = 0 reads
+// this table instead).  One block per ray: the ray's samples are staged in shared memory as {n, .} and {wa * inv_count, .},
+// each thread owns up to 3 directions in registers and walks the samples with broadcast loads.
+constexpr int LCS_THREADS = 128;
+constexpr int LCS_DPT = 3;
+__global__ void __launch_bounds__(LCS_THREADS)
+lambert_collapse_sel_kernel(const float* __restrict__ normals, const float* __restrict__ wa, const float* __restrict__ inv_count,
+                            int64_t R, int S, const float* __restrict__ dirs_sel, int Dp, float* __restrict__ G) {
+  extern __shared__ float4 s_lc[];
+  float4* sn = s_lc;          // [S] {nx, ny, nz, 0}
+  float4* sw = s_lc + S;      // [S] {w0, w1, w2, 0} * inv_count
+  const int64_t ray = blockIdx.x;
+  for (int s = threadIdx.x; s < S; s += blockDim.x) {
+    const int64_t i = ray * S + s;
+    const float ic = inv_count[i];
+    sn[s] = make_float4(normals[i * 3], normals[i * 3 + 1], normals[i * 3 + 2], 0.f);
+    sw[s] = make_float4(wa[i * 3] * ic, wa[i * 3 + 1] * ic, wa[i * 3 + 2] * ic, 0.f);
+  }
+  __syncthreads();
+  for (int j0 = threadIdx.x; j0 < Dp; j0 += LCS_THREADS * LCS_DPT) {
+    float lx[LCS_DPT], ly[LCS_DPT], lz[LCS_DPT], a[LCS_DPT][3];
+#pragma unroll
+    for (int d = 0; d < LCS_DPT; ++d) {
+      const int j = min(j0 + d * LCS_THREADS, Dp - 1);
+      lx[d] = dirs_sel[j * 3]; ly[d] = dirs_sel[j * 3 + 1]; lz[d] = dirs_sel[j * 3 + 2];
+      a[d][0] = a[d][1] = a[d][2] = 0.f;
+    }
+#pragma unroll 2
+    for (int s = 0; s < S; ++s) {
+      const float4 n = sn[s], w = sw[s];
+#pragma unroll
+      for (int d = 0; d < LCS_DPT; ++d) {
+        float c = n.x * lx[d] + n.y * ly[d] + n.z * lz[d];
+        c = fminf(fmaxf(c, 0.f), 1.f);
+        a[d][0] = fmaf(w.x, c, a[d][0]); a[d][1] = fmaf(w.y, c, a[d][1]); a[d][2] = fmaf(w.z, c, a[d][2]);
+      }
+    }
+#pragma unroll
+    for (int d = 0; d < LCS_DPT; ++d) {
+      const int j = j0 + d * LCS_THREADS;
+      if (j < Dp) {
+        float* g = G + (ray * Dp + j) * 3;
+        g[0] = a[d][0]; g[1] = a[d][1]; g[2] = a[d][2];
+      }
+    }
+  }
+}
+
 // rgb_lin[r, c] = sum_j H[r, j, c] * L[cam(r)][j, c]: one warp per ray streaming its D*3 floats (HBM-bound: 12 D bytes per ray)
 __global__ void __launch_bounds__(LP_WARPS * 32)
 relight_collapsed_kernel(const float* __restrict__ H, int64_t R, int D, const float* __restrict__ radiance,
@@ -343,6 +392,25 @@ extern "C" int nsk_lambert_collapse(const float* normals, const float* wa, const
   nsk::lambert_collapse_kernel<<<(unsigned)blocks, nsk::LP_WARPS * 32, 0, nsk::as_stream(stream)>>>(
       normals, wa, inv_count, R, S, dirs, sel_index, D, Dp, vis_sel, unoccluded_vis, H);
   return nsk::check_launch("lambert_collapse_kernel");
+}
+
+extern "C" int nsk_lambert_collapse_sel(const float* normals, const float* wa, const float* inv_count, int64_t R, int S,
+                                        const float* dirs_sel, int Dp, float* G, void* stream) {
+  if (R == 0 || Dp == 0) return 0;
+  NSK_REQUIRE(S >= 1 && S <= 2048, "nsk_lambert_collapse_sel: S out of range");
+  NSK_REQUIRE(normals && wa && inv_count && dirs_sel && G, "nsk_lambert_collapse_sel: null pointer");
+  NSK_REQUIRE(R < (1ll << 31), "nsk_lambert_collapse_sel: too many rays for one launch");
+  const size_t smem = (size_t)S * 2 * sizeof(float4);
+  if (smem > 48 * 1024) {
+    static bool configured = false;
+    if (!configured) {
+      if (cudaFuncSetAttribute(nsk::lambert_collapse_sel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024) != cudaSuccess)
+        return nsk::fail("nsk_lambert_collapse_sel", "shared memory opt-in");
+      configured = true;
+    }
+  }
+  nsk::lambert_collapse_sel_kernel<<<(unsigned)R, nsk::LCS_THREADS, smem, nsk::as_stream(stream)>>>(normals, wa, inv_count, R, S, dirs_sel, Dp, G);
+  return nsk::check_launch("lambert_collapse_sel_kernel");
 }
 
 extern "C" int nsk_relight_collapsed(const float* H, int64_t R, int D, const float* radiance, const int32_t* cam, float* rgb_lin,

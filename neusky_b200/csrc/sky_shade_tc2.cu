@@ -446,6 +446,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) sky_
         }
         const float lx = __ldg(P.dirs + j * 3), ly = __ldg(P.dirs + j * 3 + 1), lz = __ldg(P.dirs + j * 3 + 2);
         float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+        if (P.S == 0) {
+          // pre-collapsed shading coefficients G [R, Dp, 3] = sum_s wa * clamp01(n.l_j) * inv_count (nsk_lambert_collapse_sel):
+          // full renders have 48..128 samples per ray, and running that sum here costs the tile ~20 % (it is per pair, on 4 warps)
+          const float* gp = P.wa + prc * 3;
+          c0 = __ldg(gp); c1 = __ldg(gp + 1); c2 = __ldg(gp + 2);
+        }
         for (int s = 0; s < P.S; ++s) {
           const int64_t i = ray * P.S + s;
           float c = __ldg(P.normals + i * 3) * lx + __ldg(P.normals + i * 3 + 1) * ly + __ldg(P.normals + i * 3 + 2) * lz;
@@ -575,8 +581,8 @@ extern "C" int nsk_sky_shade_tc2_fwd(const float* points, int64_t R, const float
   using namespace nsk::tcs2;
   NSK_REQUIRE(num_levels == nsk::DDF_LEVELS, "nsk_sky_shade_tc2_fwd: the DDF position encoding has 16 levels");
   if (R == 0 || Dp == 0) return 0;
-  NSK_REQUIRE(S >= 1, "nsk_sky_shade_tc2_fwd: S must be >= 1");
-  NSK_REQUIRE(points && normals && wa && inv_count && dirs && radiance && ddf_weights && hash_table && scalings && rgb_lin,
+  NSK_REQUIRE(S >= 0, "nsk_sky_shade_tc2_fwd: S must be >= 0");
+  NSK_REQUIRE(points && wa && dirs && radiance && ddf_weights && hash_table && scalings && rgb_lin && (S == 0 || (normals && inv_count)),
               "nsk_sky_shade_tc2_fwd: null pointer");
   NSK_REQUIRE((reinterpret_cast<uintptr_t>(ddf_weights) & 15) == 0, "nsk_sky_shade_tc2_fwd: weight blob must be 16-byte aligned");
   static thread_local int num_sms = 0;

@@ -394,6 +394,19 @@ def lambert_collapse(normals, wa, inv_count, dirs, sel_index, vis_sel, unocclude
     return H
 
 
+def lambert_collapse_sel(normals, wa, inv_count, dirs_sel) -> Tensor:
+    """G [R,Dp,3]: per (ray, DDF direction) Lambert coefficients summed over the ray's samples (K4 with S = 0 reads them)."""
+    R, S = normals.shape[0], normals.shape[1]
+    Dp = dirs_sel.shape[0]
+    normals, wa = _chk("normals", normals, shape=(R, S, 3)), _chk("wa", wa, shape=(R, S, 3))
+    inv_count = _chk("inv_count", inv_count, shape=(R, S))
+    dirs_sel = _chk("dirs_sel", dirs_sel, shape=(Dp, 3))
+    G = torch.empty((R, Dp, 3), device=normals.device, dtype=torch.float32)
+    _lib.check(_lib.load().nsk_lambert_collapse_sel(_ptr(normals), _ptr(wa), _ptr(inv_count), c_int64(R), c_int(S), _ptr(dirs_sel), c_int(Dp), _ptr(G), _stream(normals)),
+               "nsk_lambert_collapse_sel")
+    return G
+
+
 def relight_collapsed(H: Tensor, radiance: Tensor, cam: Optional[Tensor] = None) -> Tensor:
     """H [R,D,3], radiance [K,D,3] -> linear rgb [R,3]: one streaming pass per new illumination."""
     R, D = H.shape[0], H.shape[1]
@@ -449,6 +462,9 @@ def shade_finalize(rgb_lin, bg, acc, training: bool = False) -> Tensor:
     return out
 
 
+COLLAPSE_MIN_SAMPLES = 8     # K4 (tc2): from this many samples per ray on, pre-collapse the Lambert coefficients
+
+
 def sky_shade(points, normals, wa, inv_count, dirs_sel, radiance_sel, ddf_blob, hash_table, scalings, log2_T: int, radius: float, threshold: float, sigmoid_scale: float, rgb_lin: Tensor, cam=None, want_vis: bool = False, want_ddf: bool = False, impl: str = "tc"):
     """K4.  Accumulates into ``rgb_lin`` [R,3]; returns (vis [R,Dp] | None, ddf [R*Dp] | None, term | None)."""
     R, S = normals.shape[0], normals.shape[1]
@@ -470,6 +486,11 @@ def sky_shade(points, normals, wa, inv_count, dirs_sel, radiance_sel, ddf_blob, 
     ddf = torch.empty((R * Dp,), device=dev, dtype=torch.float32) if want_ddf else None
     term = torch.empty((R * Dp,), device=dev, dtype=torch.float32) if want_ddf else None
     lib = _lib.load()
+    if impl == "tc2" and S >= COLLAPSE_MIN_SAMPLES:
+        # full renders: sum the ray's samples once per (ray, direction) up front instead of per pair inside K4's tail
+        wa = lambert_collapse_sel(normals, wa, inv_count, dirs_sel)
+        normals = inv_count = None
+        S = 0
     if impl == "simt":
         blob = _chk("ddf_blob", ddf_blob, shape=(lib.nsk_ddf_simt_weights_floats(),))
         fn, name = lib.nsk_sky_shade_simt_fwd, "nsk_sky_shade_simt_fwd"
