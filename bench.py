@@ -305,6 +305,11 @@ def relight_arm(args):
     for a, b in tiles:
         offs.append(offs[-1] + (b - a))
     mm = global_steps_minmax(o, d, S)
+    if tiles:      # untimed warm-up of the render path (allocator, lazy kernel attributes) so that cache_build_s is a steady-state figure
+        a, b = tiles[0]
+        r.render(o[a:b].contiguous(), d[a:b].contiguous(), dn[a:b].contiguous(), S, Z0[0], sc[0], steps_minmax=mm, want_cache=True,
+                 collapse_cache=not args.per_sample_cache)
+        torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     caches = []

@@ -245,7 +245,8 @@ class RayRenderer:
             if collapse_cache:
                 # collapsed form: per (ray, direction) coefficients with the visibility folded in -- D x 3 floats
                 # per ray, independent of S; a new illumination is one streaming pass over it
-                H = ops.lambert_collapse(c["normals"], c["wa"], s["inv_count"], sh.dirs, sh.sel_index, s["visibility_sel"], sh.lower_vis)
+                # G over ALL directions (block-per-ray kernel), then fold the per-ray visibility in (lower hemisphere = lower_vis)
+                H = ops.lambert_collapse_sel(c["normals"], c["wa"], s["inv_count"], sh.dirs) * s["visibility"][:, :, None]
                 out["relight_cache"] = {"H": H, "accumulation": c["accumulation"], "directions": directions}
             else:
                 out["relight_cache"] = {"normals": c["normals"], "wa": c["wa"], "inv_count": s["inv_count"], "visibility_sel": s["visibility_sel"],
