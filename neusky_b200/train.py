@@ -405,6 +405,13 @@ def _monosdf_normal_loss(normal_pred: Tensor, normal_gt: Tensor) -> Tensor:
     return torch.abs(normal_pred - normal_gt).sum(dim=-1).mean() + (1.0 - torch.sum(normal_pred * normal_gt, dim=-1)).mean()
 
 
+def sky_pixel_loss(inputs: Tensor, targets: Tensor, mask: Tensor, alpha: float = 0.1) -> Tensor:
+    """RENISkyPixelLoss (neusky/model_components/losses.py:44-58): MSE + alpha * (1 - mean cosine similarity) on masked pixels;
+    alpha = cosine_weight of neusky_config.py (0.1)."""
+    a, b = inputs * mask, targets * mask
+    return torch.nn.functional.mse_loss(a, b) + alpha * (1 - torch.nn.functional.cosine_similarity(a, b, dim=1, eps=1e-20).mean())
+
+
 def _linear_to_srgb(c: Tensor) -> Tensor:
     c = torch.where(c <= 0.0031308, 12.92 * c, 1.055 * torch.pow(torch.abs(c), 1 / 2.4) - 0.055)
     return torch.clamp(c, 0.0, 1.0)
@@ -536,9 +543,7 @@ class NeuSkyTrainStep(torch.nn.Module):
         up = torch.tensor([0.0, 0.0, 1.0], device=image.device).expand_as(out["normal"])
         L["ground_plane_loss"] = _monosdf_normal_loss(out["normal"] * gm, up * gm)
         srgb_bg = _linear_to_srgb(out["hdr_background_colours"])
-        m = sky.to(image.dtype)[:, None].expand_as(srgb_bg)
-        a, b = srgb_bg * m, image * m
-        L["sky_pixel_loss"] = torch.nn.functional.mse_loss(a, b) + 0.1 * (1 - torch.nn.functional.cosine_similarity(a, b, dim=1, eps=1e-20).mean())
+        L["sky_pixel_loss"] = sky_pixel_loss(srgb_bg, image, sky.to(image.dtype)[:, None].expand_as(srgb_bg))
         L["visibility_sigmoid_loss"] = (self.visibility_threshold - 0.1) ** 2
         L["sdf_level_set_visibility_loss"] = (out["sdf_at_termination"] ** 2).mean()
         if "grid_density" in out:

@@ -319,9 +319,24 @@ def golden_shaders():
     save("shaders", **out)
 
 
+# ------------------------------------------------------------------------------ NeuSky-specific training losses
+def golden_losses():
+    from neusky.model_components.losses import RENISkyPixelLoss
+    from neusky.utils.utils import linear_to_sRGB
+
+    g = torch.Generator().manual_seed(71)
+    R = 97
+    hdr = torch.exp(torch.randn(R, 3, generator=g)).requires_grad_(True)           # hdr_background_colours
+    image = torch.rand(R, 3, generator=g)
+    sky = (torch.rand(R, generator=g) > 0.6).float()
+    loss = RENISkyPixelLoss(alpha=0.1)(linear_to_sRGB(hdr), image, sky[:, None].expand(R, 3))    # neusky_model.py:1005-1012
+    (grad,) = torch.autograd.grad(loss, hdr)
+    save("losses", hdr=hdr, image=image, sky=sky, sky_pixel_loss=loss, sky_pixel_loss_d_hdr=grad)
+
+
 if __name__ == "__main__":
     only = sys.argv[1:]
     torch.manual_seed(0)
-    for fn in (golden_icosphere, golden_lambert, golden_reni, golden_ddf_and_visibility, golden_ddf_fit, golden_shaders):
+    for fn in (golden_icosphere, golden_lambert, golden_reni, golden_ddf_and_visibility, golden_ddf_fit, golden_shaders, golden_losses):
         if not only or fn.__name__ in only:
             fn()

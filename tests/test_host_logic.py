@@ -42,3 +42,22 @@ def test_ops_reject_cpu_tensors():
         ops.lambert_collapse_sel(torch.zeros(2, 4, 3), torch.zeros(2, 4, 3), torch.zeros(2, 4), torch.zeros(5, 3))
     with pytest.raises(ValueError):
         ops.relight_collapsed(torch.zeros(2, 5, 3), torch.zeros(1, 5, 3))
+
+
+def test_sky_pixel_loss_vs_reference_golden(golden):
+    """RENISkyPixelLoss(alpha=0.1) on sRGB(hdr background) vs the image under the sky mask: value and gradient from the
+    reference's own class (tests/golden/make_golden.py::golden_losses); product formula and oracle restatement."""
+    from neusky_b200 import train as T
+    from oracle import train_oracle as TO
+    from oracle import neusky_oracle as O
+
+    g = golden("losses")
+    hdr = torch.from_numpy(g["hdr"]).requires_grad_(True)
+    image, sky = torch.from_numpy(g["image"]), torch.from_numpy(g["sky"])
+    m = sky[:, None].expand_as(image)
+    ours = T.sky_pixel_loss(T._linear_to_srgb(hdr), image, m)
+    (grad,) = torch.autograd.grad(ours, hdr)
+    assert abs(float(ours) - float(g["sky_pixel_loss"])) <= 1e-6
+    assert torch.allclose(grad, torch.from_numpy(g["sky_pixel_loss_d_hdr"]), rtol=1e-5, atol=1e-8)
+    ref2 = TO.sky_pixel_loss(O.linear_to_srgb(hdr.detach()), image, m)
+    assert abs(float(ref2) - float(g["sky_pixel_loss"])) <= 1e-6
