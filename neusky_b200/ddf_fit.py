@@ -198,7 +198,7 @@ class DDFFit:
         near, far = sphere_collider(origins, directions, radius=1.0, training=True)
         starts, ends = uniform_samples(near, far, S)
         x = (origins[:, None, :] + directions[:, None, :] * starts[:, :, None]).reshape(-1, 3)
-        sdf, grad, _ = sdf_field(st.sdf_cfg, x, sdf_p["encoding.hash_table"], sdf_param_list(sdf_p), want_normals=True, want_albedo=False)
+        sdf, grad, _ = sdf_field(st.sdf_cfg, x, sdf_p["encoding.hash_table"], st.sdf_weights(), want_normals=True, want_albedo=False)
         inv_s = torch.exp(sdf_p["deviation_network.variance"] * 10.0).clip(1e-6, 1e6)
         dn = torch.ones(R, device=origins.device)
         alb0 = torch.zeros(R, S, 3, device=origins.device)
@@ -279,10 +279,10 @@ class DDFFit:
             if stop_gradients:                                                           # :244-248
                 with torch.no_grad():
                     term_pts = positions + directions * expected.unsqueeze(-1)
-                    s, _, _ = sdf_field(st.sdf_cfg, term_pts, sdf_p["encoding.hash_table"], sdf_param_list(sdf_p), want_normals=False, want_albedo=False)
+                    s, _, _ = sdf_field(st.sdf_cfg, term_pts, sdf_p["encoding.hash_table"], st.sdf_weights(), want_normals=False, want_albedo=False)
             else:
                 term_pts = positions + directions * expected.unsqueeze(-1)
-                s, _, _ = sdf_field(st.sdf_cfg, term_pts, sdf_p["encoding.hash_table"], sdf_param_list(sdf_p), want_normals=False, want_albedo=False)
+                s, _, _ = sdf_field(st.sdf_cfg, term_pts, sdf_p["encoding.hash_table"], st.sdf_weights(), want_normals=False, want_albedo=False)
             out["sdf_at_termination"] = s.reshape(-1, 1)
         return out
 

@@ -468,6 +468,25 @@ class NeuSkyTrainStep(torch.nn.Module):
     def group(self, grp: str) -> Dict[str, Tensor]:
         return {k: getattr(self, reg) for k, reg in self._names[grp].items()}
 
+    def sdf_weights(self) -> List[Tensor]:
+        """`sdf_param_list` of the current SDF parameters (weight-norm fold), computed once per optimizer state: the main pass,
+        the sdf_at_termination branch, the density probe and the DDF fitting pass all evaluate the same field in one iteration,
+        and every fold is ~25 small torch ops forward plus their backward.  Keyed on the parameters' version counters, so an
+        optimizer step (in-place update) invalidates it."""
+        sdf_p = self.group("sdf")
+        key = tuple(v._version for v in sdf_p.values()) + (torch.is_grad_enabled(),)
+        if getattr(self, "_sdf_w_key", None) != key:
+            self._sdf_w_key, self._sdf_w = key, sdf_param_list(sdf_p)
+            for w in self._sdf_w:
+                if w.requires_grad and not w.is_leaf:      # the fold's graph is freed by the first backward through it: drop the cache then
+                    w.register_hook(self._drop_sdf_weights)
+                    break
+        return self._sdf_w
+
+    def _drop_sdf_weights(self, grad):
+        self._sdf_w_key = None
+        return None
+
     def get_param_groups(self) -> Dict[str, List[torch.nn.Parameter]]:
         return {"fields": list(self.group("sdf").values()), "ddf_field": list(self.group("ddf").values()),
                 "illumination_field": [self.latents, self.scale], "visibility_sigmoid": [self.visibility_threshold]}
@@ -492,7 +511,7 @@ class NeuSkyTrainStep(torch.nn.Module):
         cam = batch["cam"].to(torch.int32).contiguous()
         R, S = o.shape[0], self.S
         sdf_p, ddf_p = self.group("sdf"), self.group("ddf")
-        sdf_w = sdf_param_list(sdf_p)
+        sdf_w = self.sdf_weights()
         table = sdf_p["encoding.hash_table"]
 
         near, far = sphere_collider(o, d, radius=1.0, training=True)
