@@ -407,8 +407,11 @@ def train_arm(args):
     R, K, S = args.rays, 32, args.train_samples
     sdf_p = nb_init.init_sdf_params(SEED_W + 2, bias=0.45)
     sdf_p["deviation_network.variance"] = torch.tensor(0.3)
+    prop = None
+    if args.train_sampler == "proposal":   # the shipped NeuS-facto placement: 256 -> 96 -> S samples through two HashMLPDensityFields + interlevel loss
+        prop = [nb_init.init_proposal_params(SEED_W + 3, table_scale=1.0, density_bias=1.0), nb_init.init_proposal_params(SEED_W + 4, table_scale=1.0, density_bias=2.0)]
     step_mod = NeuSkyTrainStep(sdf_p, nb_init.init_ddf_params(SEED_W), nb_init.init_reni_params(SEED_W + 1), num_cameras=K, device=dev,
-                               num_samples=S, split_geo=3, split=args.split, threshold_init=0.4)
+                               num_samples=S, split_geo=3, split=args.split, threshold_init=0.4, proposal_params=prop)
     with torch.no_grad():
         step_mod.latents.copy_(torch.randn(K, 100, 3, generator=torch.Generator().manual_seed(3)).to(dev))
     params = [p for p in step_mod.parameters() if p.requires_grad]
@@ -491,7 +494,7 @@ def train_arm(args):
                 "host_launch_ms_per_step": 1e3 * host_launch / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": f"tf32 operands (3xTF32 on the SDF geometry network, split={args.split} elsewhere), fp32 accumulate / activations / gradients", "data": "synthetic",
-                "config": {"workload": f"BASELINE.json configs[3]: training step, {R} rays/GPU from {K} cameras, S={S} uniform samples/ray, 642-direction icosphere with a random "
+                "config": {"workload": f"BASELINE.json configs[3]: training step, {R} rays/GPU from {K} cameras, S={S} {'proposal-network (256->96->' + str(S) + ', interlevel loss)' if prop is not None else 'uniform'} samples/ray, 642-direction icosphere with a random "
                                        f"rotation per step (mean D'={Dp:.0f} through the DDF), sdf_at_termination branch, hashgrid density loss on {gres**3} grid points, "
                                        + ("DDF fitting pass (8 x 128 vMF rays rendered through the SDF field, DDF on 1024 + 1024 multi-view + 256 sky rows, gradients into both fields), " if fit is not None else "no DDF fitting pass, ")
                                        + 
@@ -529,6 +532,7 @@ def main():
     ap.add_argument("--rays", type=int, default=1024, help="train: rays per GPU")
     ap.add_argument("--train-samples", type=int, default=48)
     ap.add_argument("--split", type=int, default=3, choices=[1, 3], help="train: 1 = tf32 GEMMs, 3 = 3xTF32 (fp32-accurate)")
+    ap.add_argument("--train-sampler", default="proposal", choices=["proposal", "uniform"], help="train: sample placement (proposal = shipped NeuS-facto default)")
     ap.add_argument("--no-ddf-fit", action="store_true", help="train: leave the DDF fitting pass (fit_visibility_field=True in the reference) out of the step")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -185,7 +185,10 @@ class HashMLPDensityField:
         grads["encoding.hash_table"] = d_table
         for k, g in grads.items():
             p = self.params[k]
-            p.grad = g if p.grad is None else p.grad + g
+            if p.grad is None:
+                p.grad = g
+            else:
+                p.grad.add_(g)          # in place: .grad may be a view into a GradBucketReducer communication bucket
 
 
 def _ray_samples(origins, dirs, euclid, spacing, near, far):

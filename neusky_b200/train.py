@@ -395,7 +395,7 @@ def sdf_field(cfg: SDFConfig, x: Tensor, table: Tensor, weights: Sequence[Tensor
 # =====================================================================================================================
 LOSS_COEFFICIENTS = {  # neusky/configs/neusky_config.py:132-146
     "rgb_l1_loss": 1.0, "eikonal_loss": 0.1, "fg_mask_loss": 1.0, "sdf_level_set_visibility_loss": 1.0, "sky_pixel_loss": 1.0,
-    "hashgrid_density_loss": 1e-4, "ground_plane_loss": 0.1, "visibility_sigmoid_loss": 0.01,
+    "hashgrid_density_loss": 1e-4, "ground_plane_loss": 0.1, "visibility_sigmoid_loss": 0.01, "interlevel_loss": 1.0,
 }
 
 
@@ -438,7 +438,10 @@ class NeuSkyTrainStep(torch.nn.Module):
     def __init__(self, sdf_params: Dict[str, Tensor], ddf_params: Dict[str, Tensor], reni_params: Dict[str, Tensor], num_cameras: int, device="cuda",
                  log2_T: int = 19, num_levels: int = 16, num_samples: int = 48, ddf_radius: float = 1.0, sigmoid_scale: float = 25.0,
                  split_geo: int = 3, split: int = 3, threshold_init: Optional[float] = None, only_upper_hemisphere: bool = True,
-                 lower_hemisphere_visibility: float = 1.0):
+                 lower_hemisphere_visibility: float = 1.0, proposal_params: Optional[Sequence[Dict[str, Tensor]]] = None,
+                 proposal_max_res: Sequence[int] = (64, 256), num_proposal_samples_per_ray: Sequence[int] = (256, 96), proposal_log2_T: int = 17):
+        """``proposal_params``: state of the two HashMLPDensityFields -> the shipped NeuS-facto sample placement (proposal-network
+        sampler, neusky_model.py:561) and its interlevel loss (:987-988, coefficient 1.0); None -> uniform placement."""
         super().__init__()
         from . import packing
         from .init import hash_scalings
@@ -463,6 +466,16 @@ class NeuSkyTrainStep(torch.nn.Module):
         self.ddf_cfg = DDFConfig(scalings=self.scalings, log2_T=log2_T, radius=self.radius, sigmoid_scale=sigmoid_scale, split=split)
         self.cos_anneal_ratio = 1.0
         self.grid_resolution = 10                                                                  # neusky_config.py:127
+        self.proposal_fields, self.proposal_sampler, self.proposal_anneal = None, None, 1.0
+        if proposal_params is not None:
+            from . import proposal as _proposal
+            self.proposal_fields = [_proposal.HashMLPDensityField(pp, max_res=mr, log2_hashmap_size=proposal_log2_T, device=self.dev)
+                                    for pp, mr in zip(proposal_params, proposal_max_res)]
+            for i, f in enumerate(self.proposal_fields):          # the fields' own Parameter objects, registered here for optimizers / reducers
+                for k, v in f.params.items():
+                    self.register_parameter(f"prop{i}__{k.replace('.', '__')}", v)
+            self.proposal_sampler = _proposal.ProposalNetworkSampler(num_samples, num_proposal_samples_per_ray, len(self.proposal_fields))
+            self.proposal_sampler.training = True
 
     # -- parameter access under the reference's names -------------------------------------------------------
     def group(self, grp: str) -> Dict[str, Tensor]:
@@ -488,8 +501,11 @@ class NeuSkyTrainStep(torch.nn.Module):
         return None
 
     def get_param_groups(self) -> Dict[str, List[torch.nn.Parameter]]:
-        return {"fields": list(self.group("sdf").values()), "ddf_field": list(self.group("ddf").values()),
-                "illumination_field": [self.latents, self.scale], "visibility_sigmoid": [self.visibility_threshold]}
+        g = {"fields": list(self.group("sdf").values()), "ddf_field": list(self.group("ddf").values()),
+             "illumination_field": [self.latents, self.scale], "visibility_sigmoid": [self.visibility_threshold]}
+        if self.proposal_fields is not None:
+            g["proposal_networks"] = [p for f in self.proposal_fields for p in f.parameters()]
+        return g
 
     def set_directions(self, dirs: Tensor) -> None:
         """Illumination directions of this iteration [D,3] (IcosahedronSampler with its random rotation, neusky_model.py:452-456)."""
@@ -515,7 +531,19 @@ class NeuSkyTrainStep(torch.nn.Module):
         table = sdf_p["encoding.hash_table"]
 
         near, far = sphere_collider(o, d, radius=1.0, training=True)
-        starts, ends = uniform_samples(near, far, S)                                   # [R,S]
+        rs = None
+        if self.proposal_fields is not None:
+            # proposal-network sampler (training mode: one jitter per ray and level); placement carries no gradient, the proposal
+            # networks learn from the interlevel loss below
+            for f in self.proposal_fields:
+                f.refresh()
+            self.proposal_sampler.set_anneal(self.proposal_anneal)
+            with torch.no_grad():
+                rs, _wl, _sl = self.proposal_sampler.generate_ray_samples(o, d, near, far, self.proposal_fields, jitters=batch.get("jitters"))
+            e = rs.euclidean_bins
+            starts, ends = e[:, :-1].contiguous(), e[:, 1:].contiguous()
+        else:
+            starts, ends = uniform_samples(near, far, S)                               # [R,S]
         x = (o[:, None, :] + d[:, None, :] * starts[:, :, None]).reshape(-1, 3)
         sdf, grad, alb = sdf_field(self.sdf_cfg, x, table, sdf_w)
         inv_s = torch.exp(sdf_p["deviation_network.variance"] * 10.0).clip(1e-6, 1e6)
@@ -542,6 +570,12 @@ class NeuSkyTrainStep(torch.nn.Module):
         rgb = nba.shade_finalize(rgb_lin, bg, acc)
         out = {"rgb": rgb, "eik_grad": grad.reshape(R, S, 3), "weights": weights, "normal": normal, "accumulation": acc, "hdr_background_colours": bg,
                "p2p_dist": p2p, "sdf_at_termination": sdf_term, "visibility_sel": vis, "expected_termination_dist": that}
+        if rs is not None:
+            # nerfstudio interlevel_loss with the fine NeuS weights appended (neusky_model.py:575-576, 987-988): value here, gradients
+            # straight into the proposal networks' .grad (weights -> density -> MLP + hash table; the fine histogram is detached)
+            out["interlevel_loss"] = self.proposal_sampler.interlevel_loss_backward(weights.detach(), rs, o, d, near, far,
+                                                                                    loss_mult=LOSS_COEFFICIENTS["interlevel_loss"])
+            out["starts"], out["ends"] = starts, ends
         if grid_positions is not None:
             gs, gg, _ = sdf_field(self.sdf_cfg, grid_positions, table, sdf_w, want_normals=True, want_albedo=False)
             gap = 2.0 / self.grid_resolution
@@ -567,4 +601,6 @@ class NeuSkyTrainStep(torch.nn.Module):
         L["sdf_level_set_visibility_loss"] = (out["sdf_at_termination"] ** 2).mean()
         if "grid_density" in out:
             L["hashgrid_density_loss"] = out["grid_density"].abs().mean()
+        if "interlevel_loss" in out:
+            L["interlevel_loss"] = out["interlevel_loss"].detach()       # its gradient has already been accumulated (see forward)
         return {k: v * LOSS_COEFFICIENTS[k] for k, v in L.items()}

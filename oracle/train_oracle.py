@@ -52,8 +52,11 @@ def sky_pixel_loss(inputs: Tensor, targets: Tensor, mask: Tensor, alpha: float =
 
 def training_forward(batch: Dict[str, Tensor], sdf_p, ddf_p, reni_p, latents: Tensor, scales: Tensor, threshold: Tensor, dirs: Tensor, S: int,
                      log2_T: int, ddf_radius: float = 1.0, sigmoid_scale: float = 25.0, cos_anneal_ratio: float = 1.0,
-                     grid_positions: Optional[Tensor] = None, grid_dirs: Optional[Tensor] = None, grid_gap: float = 0.2) -> Dict[str, Tensor]:
+                     grid_positions: Optional[Tensor] = None, grid_dirs: Optional[Tensor] = None, grid_gap: float = 0.2,
+                     sample_edges: Optional[Tensor] = None) -> Dict[str, Tensor]:
     """batch: origins, directions [R,3], dnorm [R,1], cam [R] int64, image [R,3], fg/ground/sky masks [R].
+    sample_edges [R,S+1]: euclidean bin edges from the proposal-network sampler (neusky_model.py:561; placement is detached
+    there too) instead of the uniform placement; the sampler itself is covered by oracle/sampler_oracle.py.
     Returns the outputs dict (rgb, eik_grad, weights, normal, accumulation, hdr_background_colours, sdf_at_termination,
     visibility, expected_termination_dist, grid_density) of neusky_model.py:881-931 in training mode."""
     o, d, dn, cam = batch["origins"], batch["directions"], batch["dnorm"], batch["cam"]
@@ -61,7 +64,10 @@ def training_forward(batch: Dict[str, Tensor], sdf_p, ddf_p, reni_p, latents: Te
     dt = o.dtype
     sca = O.hash_scalings().to(dt)
     near, far = O.sphere_collider(o, d, radius=1.0, training=True)
-    starts, ends = O.uniform_samples(near, far, S)
+    if sample_edges is not None:
+        starts, ends = sample_edges[:, :-1, None].to(dt), sample_edges[:, 1:, None].to(dt)
+    else:
+        starts, ends = O.uniform_samples(near, far, S)
     x = (o[:, None, :] + d[:, None, :] * starts).reshape(-1, 3).detach().requires_grad_(True)
     h = O.sdf_geo_network(x, sdf_p, sca, log2_T)                                         # sdf_albedo_field.py:233
     sdf, geo = h[:, :1], h[:, 1:]

@@ -356,3 +356,70 @@ def test_train_step_losses_and_gradients_vs_oracle_autograd(dev, split, tol_loss
     bad = {k: (v, worst32.get(k), cond.get(k)) for k, v in worst.items()
            if not (v <= tol_of(k) or worst32.get(k, 1e9) <= tol_of(k) or v <= 2.0 * net_cond.get(k.split(".")[0], 0.0))}
     assert not bad, f"split={split}: gradient mismatch {{name: (ours vs fp64, ours vs fp32 oracle, fp32 oracle vs fp64)}} = {bad}"
+
+
+def test_train_step_with_proposal_sampler_and_interlevel_loss(dev):
+    """The shipped sample placement in the training step: proposal-network sampler (256 -> 96 -> S, one jitter per ray and level),
+    NeuS losses on those samples against the oracle evaluated on the SAME bin edges, interlevel loss against the sampler oracle's
+    restatement, and gradients reaching both proposal networks (hash table + MLP) outside autograd."""
+    import numpy as np
+
+    from neusky_b200 import proposal as P
+    from neusky_b200 import train as T
+    from oracle import neusky_oracle as O
+    from oracle import sampler_oracle as SO
+    from oracle import train_oracle as TO
+
+    log2_T, R, S, K = 14, 16, 12, 3
+    g = torch.Generator().manual_seed(41)
+    sdf_p = nb_init.init_sdf_params(3, log2_T=log2_T)
+    sdf_p["encoding.hash_table"] = (torch.rand(sdf_p["encoding.hash_table"].shape, generator=g) * 2 - 1) * 0.05
+    sdf_p["deviation_network.variance"] = torch.tensor(0.25)
+    ddf_p = nb_init.init_ddf_params(5, final_gain=8.0, log2_T=log2_T, table_scale=0.1)
+    reni_p = nb_init.init_reni_params(8)
+    nets = [SO.init_proposal_net(1, table_scale=1.0, density_bias=1.0), SO.init_proposal_net(2, table_scale=1.0, density_bias=2.0)]
+    latents, scales = torch.randn(K, 100, 3, generator=g), 0.1 * torch.randn(K, generator=g)
+    dirs = O.icosphere_directions(100)
+    batch = _train_case(R, K, 43)
+    jit = [torch.rand(R, generator=g) for _ in range(3)]
+    thr0 = 0.4
+
+    step = T.NeuSkyTrainStep(sdf_p, ddf_p, reni_p, num_cameras=K, device=dev, log2_T=log2_T, num_samples=S, split_geo=3, split=3, threshold_init=thr0,
+                             proposal_params=nets, num_proposal_samples_per_ray=(32, 20))
+    assert set(step.get_param_groups()) == {"fields", "ddf_field", "illumination_field", "visibility_sigmoid", "proposal_networks"}
+    with torch.no_grad():
+        step.latents.copy_(latents.to(dev))
+        step.scale.copy_(scales.to(dev))
+    step.set_directions(dirs)
+    bc = {k: v.to(dev) for k, v in batch.items()}
+    bc["jitters"] = [j.to(dev) for j in jit]
+    loss, L, out = step(bc)
+    loss.backward()
+
+    # placement: what the sampler itself returns for these jitters (bit-identical: same kernels, same inputs)
+    smp = P.ProposalNetworkSampler(S, (32, 20), 2)
+    smp.training = True
+    near, far = (t.to(dev) for t in O.sphere_collider(batch["origins"], batch["directions"], radius=1.0, training=True))
+    rs, wl, sl = smp.generate_ray_samples(bc["origins"], bc["directions"], near, far, step.proposal_fields, jitters=bc["jitters"])
+    assert torch.equal(rs.euclidean_bins[:, :-1], out["starts"]) and torch.equal(rs.euclidean_bins[:, 1:], out["ends"])
+    edges = rs.euclidean_bins.cpu()
+    assert bool((edges[:, 1:] >= edges[:, :-1]).all()) and edges.shape == (R, S + 1)
+
+    # NeuS losses on those samples vs the fp64 oracle on the same edges
+    c64 = lambda p: {k: v.double() for k, v in p.items()}
+    b64 = {k: (v.double() if v.is_floating_point() else v) for k, v in batch.items()}
+    out_r = TO.training_forward(b64, c64(sdf_p), c64(ddf_p), c64(reni_p), latents.double(), scales.double(), torch.tensor(thr0, dtype=torch.float64), dirs.double(), S,
+                                log2_T, sample_edges=edges.double())
+    L_r = TO.training_losses(out_r, b64, torch.tensor(thr0, dtype=torch.float64))
+    for k in L_r:
+        assert abs(float(L[k]) - float(L_r[k])) <= 5e-4 * max(1.0, abs(float(L_r[k]))), f"{k}: {float(L[k])} vs {float(L_r[k])}"
+
+    # interlevel loss: sampler oracle on the GPU's own histograms (proposal weights + fine NeuS weights)
+    w_list = [w[..., 0].cpu().double() for w in wl] + [out["weights"].detach().cpu().double()]
+    s_list = [s_.spacing_bins.cpu().double() for s_ in sl] + [rs.spacing_bins.cpu().double()]
+    il_ref = SO.interlevel_loss(w_list, s_list)
+    assert abs(float(L["interlevel_loss"]) - float(il_ref)) <= 1e-4 * max(1.0, abs(float(il_ref))), (float(L["interlevel_loss"]), float(il_ref))
+    for f in step.proposal_fields:
+        for k, v in f.params.items():
+            assert v.grad is not None and bool(torch.isfinite(v.grad).all()), k
+        assert float(f.params["encoding.hash_table"].grad.abs().sum()) > 0.0
