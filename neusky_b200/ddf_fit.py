@@ -187,7 +187,8 @@ class DDFFit:
     # -- neusky_model.py:1337-1367 ---------------------------------------------------------------------------------
     def generate_ddf_ground_truth(self, origins: Tensor, directions: Tensor, mask_threshold: float = 0.5) -> Dict[str, Tensor]:
         """Render accumulation, expected depth (clamped to the sphere diameter) and normals of the rays through the SDF field:
-        collider -> sample placement -> SDFAlbedoField(return_alphas) -> weights -> renderers.  Differentiable w.r.t. the SDF
+        collider -> sample placement (the step's proposal sampler when it has one, else uniform) -> SDFAlbedoField(return_alphas) ->
+        weights -> renderers.  Differentiable w.r.t. the SDF
         field (the reference only cuts this graph when stop_sdf_gradients is set, neusky_pipeline.py:505-513)."""
         from . import autograd as nba
         from .render import sphere_collider, uniform_samples
@@ -196,7 +197,14 @@ class DDFFit:
         R, S = origins.shape[0], st.S
         sdf_p = st.group("sdf")
         near, far = sphere_collider(origins, directions, radius=1.0, training=True)
-        starts, ends = uniform_samples(near, far, S)
+        if st.proposal_fields is not None:
+            # the model's own sampler, as in the reference (:1343); its state for the interlevel loss was consumed in the main pass
+            with torch.no_grad():
+                rs, _, _ = st.proposal_sampler.generate_ray_samples(origins, directions, near, far, st.proposal_fields)
+            e = rs.euclidean_bins
+            starts, ends = e[:, :-1].contiguous(), e[:, 1:].contiguous()
+        else:
+            starts, ends = uniform_samples(near, far, S)
         x = (origins[:, None, :] + directions[:, None, :] * starts[:, :, None]).reshape(-1, 3)
         sdf, grad, _ = sdf_field(st.sdf_cfg, x, sdf_p["encoding.hash_table"], st.sdf_weights(), want_normals=True, want_albedo=False)
         inv_s = torch.exp(sdf_p["deviation_network.variance"] * 10.0).clip(1e-6, 1e6)

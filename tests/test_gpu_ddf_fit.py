@@ -184,3 +184,37 @@ def test_fit_pass_end_to_end_default_config(dev):
     assert all(torch.isfinite(v) for v in L.values()) and set(L) == {"depth_l1_loss", "sdf_l2_loss", "multi_view_loss", "sky_ray_loss"}
     for k, v in step.group("ddf").items():
         assert v.grad is not None and bool(torch.isfinite(v.grad).all()), k
+
+
+def test_fit_pass_uses_the_steps_proposal_sampler(dev):
+    """With proposal networks on the training step, the ground-truth render of the fitting pass places its samples with the
+    model's own sampler (neusky_model.py:1343) and the whole iteration (main pass + fitting pass) still backpropagates."""
+    from neusky_b200 import ddf_fit as F
+    from neusky_b200 import train as T
+    from oracle import neusky_oracle as O
+
+    log2_T, S = 14, 16
+    g = torch.Generator().manual_seed(5)
+    sdf_p = nb_init.init_sdf_params(3, log2_T=log2_T)
+    sdf_p["glin2.bias"] = sdf_p["glin2.bias"].clone()
+    sdf_p["glin2.bias"][0] -= 0.35
+    ddf_p = nb_init.init_ddf_params(5, final_gain=8.0, log2_T=log2_T, table_scale=0.1)
+    prop = [nb_init.init_proposal_params(1, table_scale=1.0, density_bias=1.0), nb_init.init_proposal_params(2, table_scale=1.0, density_bias=2.0)]
+    step = T.NeuSkyTrainStep(sdf_p, ddf_p, nb_init.init_reni_params(8), num_cameras=2, device=dev, log2_T=log2_T, num_samples=S, split_geo=1, split=1,
+                             threshold_init=0.4, proposal_params=prop, num_proposal_samples_per_ray=(32, 24))
+    step.set_directions(O.icosphere_directions(100))
+    R = 32
+    o = torch.nn.functional.normalize(torch.randn(R, 3, generator=g), dim=-1) * 0.7
+    d = torch.nn.functional.normalize(-o + 0.1 * torch.randn(R, 3, generator=g), dim=-1)
+    batch = {"origins": o, "directions": d, "dnorm": torch.ones(R, 1), "cam": torch.randint(0, 2, (R,), generator=g), "image": torch.rand(R, 3, generator=g),
+             "fg": torch.ones(R), "ground": torch.zeros(R), "sky": torch.zeros(R)}
+    loss, L, _ = step({k: v.to(dev) for k, v in batch.items()})
+    fit = F.DDFFit(step, sampler=F.VMFDDFSampler(F.DDFSamplerConfig(num_samples_on_sphere=2, num_rays_per_sample=16), device=dev))
+    sky_o = (torch.tensor([0.0, -0.6, 0.1]).expand(8, 3) + 0.05 * torch.randn(8, 3, generator=g)).to(dev)
+    sky_d = torch.nn.functional.normalize(torch.randn(8, 3, generator=g) + torch.tensor([0.0, 0.0, 1.0]), dim=-1).to(dev)
+    lfit, Lf, _, data = fit(sky_o, sky_d)
+    (loss + lfit).backward()
+    assert "interlevel_loss" in L and all(bool(torch.isfinite(v)) for v in {**L, **Lf}.values())
+    assert data["termination_dist"].shape == (32, 1)
+    for grp in ("sdf", "ddf"):
+        assert all(v.grad is not None and bool(torch.isfinite(v.grad).all()) for k, v in step.group(grp).items() if k != "embedding_appearance.embedding.weight")
