@@ -105,7 +105,18 @@ for K in (1, 64):
     Z = torch.randn(K, 100, 3, generator=g).to(dev)
     s0 = torch.zeros(K, device=dev)
     ms = timeit(lambda: ops.reni_radiance_table(dirs, Z, s0, rblob))
-    report(f"reni_decode K={K} D=2048", "tensor", ms, K * 2048 * 524544.0 + K * 657408.0, 524544, K * 2048)
+    report(f"reni_decode K={K} D=2048", "tensor", ms, K * 2048 * 524544.0 + K * 657408.0, 524544, K * 2048, {"note": "fp32 SIMT (direction tables, training)"})
+# frame-sized row batch (the per-ray background of a 1280x720 render): 13 dense layers on the 3xTF32 tcgen05 GEMM chain; the
+# fraction is against the dense fp16/bf16 peak although every contraction runs three tf32 passes (1/6 of that peak at best)
+rgw = packing.pack_reni_gemm({k: v.to(dev) for k, v in rp.items()})
+Nf = 1280 * 720
+rows = torch.nn.functional.normalize(torch.randn(Nf, 3, generator=g), dim=-1).to(dev)
+Z1, s1 = torch.randn(1, 100, 3, generator=g).to(dev), torch.zeros(1, device=dev)
+ms = timeit(lambda: ops.reni_rows_tc(rows, Z1, s1, rblob, rgw), iters=3)
+report("reni_rows_tc N=921600 (3xTF32 GEMM chain)", "tensor", ms, Nf * 524544.0, 524544, Nf, {"note": "algorithmic FLOP; 3xTF32 issues 3 tf32 MMAs per product"})
+ms = timeit(lambda: ops.reni_radiance_table(rows, Z1, s1, rblob), iters=3)
+report("reni_decode rows N=921600 (fp32 SIMT, same work)", "tensor", ms, Nf * 524544.0, 524544, Nf)
+del rows
 
 # ---- proposal-network sampler (8f row f1): density field 372 B/sample algorithmic (12 + 5*8*8 gather + 40 features);
 # ---- PDF resampling: reads bins (S+1)*4 + density S*4, writes weights S*4 + new bins/euclid 2*(N+1)*4 per ray --------------------
