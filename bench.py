@@ -326,10 +326,18 @@ def relight_arm(args):
 
     def sweep():
         last = None
-        for k in range(NL):
-            rad, bg = r.illumination_for(codes[k], sc[0], my_dirs)          # two RENI++ decodes per latent, not per tile
+        if args.per_sample_cache:
+            for k in range(NL):
+                rad, bg = r.illumination_for(codes[k], sc[0], my_dirs)          # two RENI++ decodes per latent, not per tile
+                for i, c in enumerate(caches):
+                    last = r.relight(c, codes[k], sc[0], radiance=rad, background=bg[offs[i]:offs[i + 1]])
+            return last
+        for k0 in range(0, NL, 4):                                              # four latent codes per pass over the collapsed cache
+            ill = [r.illumination_for(codes[k], sc[0], my_dirs) for k in range(k0, min(NL, k0 + 4))]
+            rad = torch.cat([a for a, _ in ill], 0)
+            bg = torch.stack([b for _, b in ill], 0)
             for i, c in enumerate(caches):
-                last = r.relight(c, codes[k], sc[0], radiance=rad, background=bg[offs[i]:offs[i + 1]])
+                last = r.relight_many(c, rad, bg[:, offs[i]:offs[i + 1]])
         return last
 
     for _ in range(max(1, args.warmup // 3)):

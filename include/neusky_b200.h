@@ -192,6 +192,9 @@ int nsk_lambert_collapse(const float* normals, const float* wa, const float* inv
                          void* stream);
 int nsk_relight_collapsed(const float* H, int64_t R, int D, const float* radiance, const int32_t* cam, float* rgb_lin,
                           void* stream);
+/* nsk_relight_collapsed_multi: NL illuminations per pass over H: radiance [NL,D,3] -> rgb_lin [NL,R,3] (an illumination sweep is bound
+ * by streaming H; NL = 4 reads it once for four latent codes). */
+int nsk_relight_collapsed_multi(const float* H, int64_t R, int D, const float* radiance, int NL, float* rgb_lin, void* stream);
 /* nsk_lambert_collapse_sel: G [R,Dp,3] = sum_s wa * clamp01(n.l_j) * inv_count over the Dp directions that go through the DDF
  * (dirs_sel [Dp,3]).  nsk_sky_shade_tc2_fwd called with S = 0 takes this table in its `wa` argument (normals / inv_count may be
  * NULL) and skips the per-pair loop over the ray's samples -- the form full renders (S = 48..128) use. */

@@ -225,6 +225,43 @@ relight_collapsed_kernel(const float* __restrict__ H, int64_t R, int D, const fl
   if (lane == 0) { rgb_lin[ray * 3] = o0; rgb_lin[ray * 3 + 1] = o1; rgb_lin[ray * 3 + 2] = o2; }
 }
 
+// Several illuminations per pass over the collapsed cache: H is read once for NL radiance tables (an illumination sweep is bound by
+// streaming H, 12 D bytes per ray and pass).  radiance [NL, D, 3], rgb_lin [NL, R, 3].
+template <int NL>
+__global__ void __launch_bounds__(LP_WARPS * 32)
+relight_collapsed_multi_kernel(const float* __restrict__ H, int64_t R, int D, const float* __restrict__ radiance, float* __restrict__ rgb_lin) {
+  const int lane = threadIdx.x & 31;
+  const int64_t ray = (int64_t)blockIdx.x * LP_WARPS + (threadIdx.x >> 5);
+  if (ray >= R) return;
+  const float* hr = H + ray * D * 3;
+  const int n = D * 3;
+  float acc[NL][3];
+#pragma unroll
+  for (int l = 0; l < NL; ++l) acc[l][0] = acc[l][1] = acc[l][2] = 0.f;
+#pragma unroll
+  for (int ph = 0; ph < 3; ++ph) {
+    float a[NL];
+#pragma unroll
+    for (int l = 0; l < NL; ++l) a[l] = 0.f;
+    for (int e = ph * 32 + lane; e < n; e += 96) {
+      const float h = __ldcs(hr + e);
+#pragma unroll
+      for (int l = 0; l < NL; ++l) a[l] = fmaf(h, __ldg(radiance + (size_t)l * n + e), a[l]);
+    }
+    const int ch = (ph * 32 + lane) % 3;
+#pragma unroll
+    for (int l = 0; l < NL; ++l) { acc[l][0] += ch == 0 ? a[l] : 0.f; acc[l][1] += ch == 1 ? a[l] : 0.f; acc[l][2] += ch == 2 ? a[l] : 0.f; }
+  }
+#pragma unroll
+  for (int l = 0; l < NL; ++l) {
+    const float o0 = warp_sum(acc[l][0]), o1 = warp_sum(acc[l][1]), o2 = warp_sum(acc[l][2]);
+    if (lane == 0) {
+      float* o = rgb_lin + ((size_t)l * R + ray) * 3;
+      o[0] = o0; o[1] = o1; o[2] = o2;
+    }
+  }
+}
+
 // Backward of lambert_relight_kernel for a cotangent g [R,3] of rgb_lin:
 //   d wa [R,S,3], d normals [R,S,3] (lanes = samples), d vis_sel [R,Dp], d radiance [K,D,3] (lanes = directions, atomics).
 // The count of positively lit directions is piecewise constant (no gradient), as in torch (renderers.py:101-106).
@@ -421,6 +458,24 @@ extern "C" int nsk_relight_collapsed(const float* H, int64_t R, int D, const flo
   NSK_REQUIRE(blocks < (1ll << 31), "nsk_relight_collapsed: too many rays for one launch");
   nsk::relight_collapsed_kernel<<<(unsigned)blocks, nsk::LP_WARPS * 32, 0, nsk::as_stream(stream)>>>(H, R, D, radiance, cam, rgb_lin);
   return nsk::check_launch("relight_collapsed_kernel");
+}
+
+extern "C" int nsk_relight_collapsed_multi(const float* H, int64_t R, int D, const float* radiance, int NL, float* rgb_lin, void* stream) {
+  if (R == 0 || NL == 0) return 0;
+  NSK_REQUIRE(D >= 1 && NL >= 1 && H && radiance && rgb_lin, "nsk_relight_collapsed_multi: null pointer / sizes");
+  const int64_t blocks = (R + nsk::LP_WARPS - 1) / nsk::LP_WARPS;
+  NSK_REQUIRE(blocks < (1ll << 31), "nsk_relight_collapsed_multi: too many rays for one launch");
+  cudaStream_t st = nsk::as_stream(stream);
+  const size_t n = (size_t)D * 3;
+  int l = 0;
+  while (l < NL) {                       // groups of 4, then 2, then 1 illuminations per pass over H
+    const float* rad = radiance + (size_t)l * n;
+    float* out = rgb_lin + (size_t)l * R * 3;
+    if (NL - l >= 4) { nsk::relight_collapsed_multi_kernel<4><<<(unsigned)blocks, nsk::LP_WARPS * 32, 0, st>>>(H, R, D, rad, out); l += 4; }
+    else if (NL - l >= 2) { nsk::relight_collapsed_multi_kernel<2><<<(unsigned)blocks, nsk::LP_WARPS * 32, 0, st>>>(H, R, D, rad, out); l += 2; }
+    else { nsk::relight_collapsed_multi_kernel<1><<<(unsigned)blocks, nsk::LP_WARPS * 32, 0, st>>>(H, R, D, rad, out); l += 1; }
+  }
+  return nsk::check_launch("relight_collapsed_multi_kernel");
 }
 
 extern "C" int nsk_lambert_relight_bwd(const float* normals, const float* wa, const float* inv_count, int64_t R, int S,

@@ -421,6 +421,17 @@ def relight_collapsed(H: Tensor, radiance: Tensor, cam: Optional[Tensor] = None)
     return rgb_lin
 
 
+def relight_collapsed_multi(H: Tensor, radiance: Tensor) -> Tensor:
+    """H [R,D,3], radiance [NL,D,3] (one table per illumination) -> linear rgb [NL,R,3], reading H once per 4 illuminations."""
+    R, D = H.shape[0], H.shape[1]
+    H = _chk("H", H, shape=(R, D, 3))
+    radiance = _chk("radiance", radiance, shape=(None, D, 3))
+    NL = radiance.shape[0]
+    out = torch.empty((NL, R, 3), device=H.device, dtype=torch.float32)
+    _lib.check(_lib.load().nsk_relight_collapsed_multi(_ptr(H), c_int64(R), c_int(D), _ptr(radiance), c_int(NL), _ptr(out), _stream(H)), "nsk_relight_collapsed_multi")
+    return out
+
+
 def lambert_relight_bwd(normals, wa, inv_count, dirs, sel_index, radiance, vis_sel, g_rgb_lin, cam=None, unoccluded_vis: float = 1.0, want_vis: bool = True, want_radiance: bool = True):
     """-> (d_wa [R,S,3], d_normals [R,S,3], d_vis_sel [R,Dp] | None, d_radiance [K,D,3] | None)."""
     R, S = normals.shape[0], normals.shape[1]

@@ -277,6 +277,17 @@ class RayRenderer:
         return ops.shade_finalize(lin, bg, cache["accumulation"])
 
     @torch.no_grad()
+    def relight_many(self, cache: Dict[str, Tensor], radiance: Tensor, background: Tensor) -> Tensor:
+        """sRGB [NL,R,3] of the cached rays (collapsed cache) under NL illuminations at once: radiance [NL,D,3] and background [NL,R,3]
+        from `illumination_for`, one pass over the cache per four illuminations."""
+        if "H" not in cache:
+            raise ValueError("relight_many needs the collapsed cache (render(..., want_cache=True, collapse_cache=True))")
+        NL, R = radiance.shape[0], cache["H"].shape[0]
+        lin = ops.relight_collapsed_multi(cache["H"], radiance)
+        rgb = ops.shade_finalize(lin.reshape(NL * R, 3), background.reshape(NL * R, 3).contiguous(), cache["accumulation"].repeat(NL))
+        return rgb.reshape(NL, R, 3)
+
+    @torch.no_grad()
     def illumination_for(self, latent: Tensor, scale: Tensor, ray_directions: Tensor, rotation: Optional[Tensor] = None):
         """(radiance table [1,D,3], per-ray background [R,3]) of one latent code for a whole ray bundle: the two RENI++ decodes
         of `relight`, done once per latent."""

@@ -148,6 +148,13 @@ def test_relight_from_cache_equals_rerender(dev, scene):
         fast3 = r.relight(c0, Zk, sc, rotation=rk, radiance=rad, background=bg[:half])
         assert torch.equal(fast3, fast2[:half])
     assert float((base["rgb"] - r.relight(base["relight_cache"], scene["Z"].to(dev), sc)).abs().max()) <= 2e-5
+    # several illuminations per pass over the collapsed cache (7 = one group of 4, one of 2, one single)
+    Zs = torch.randn(7, 100, 3, generator=g).to(dev)
+    ill = [r.illumination_for(Zs[i], sc, d) for i in range(7)]
+    many = r.relight_many(coll, torch.cat([a for a, _ in ill], 0), torch.stack([b for _, b in ill], 0))
+    for i in range(7):
+        single = r.relight(coll, Zs[i], sc)
+        assert float((many[i] - single).abs().max()) <= 1e-6, i
 
 
 def test_render_with_proposal_sampler_vs_oracle(dev, scene):
