@@ -177,12 +177,14 @@ int nsk_lambert_relight(const float* normals, const float* wa, const float* inv_
  * nsk_reni_prep: workspace [K*NL*H + K*L*2] <- attention vectors [K,NL,H] then rotated latent xy [K,L,2] (per latent code).
  * nsk_reni_pe_rows: pe [N,512] <- decoder input rows (510 features, zero padded); row_cam [N] int32 = code of each row (NULL = 0);
  *     zxy = workspace + K*NL*H.
- * nsk_reni_ln_rows: x [N,128] <- LayerNorm(x + add[code(row) * add_stride : +128]) * ln_weight + ln_bias, in place (add NULL = 0). */
+ * nsk_reni_ln_rows: x [N,128] <- LayerNorm(x + add[code(row) * add_stride : +128]) * ln_weight + ln_bias, in place (add NULL = 0); when
+ *     ln_weight2 is given, followed in the same pass by x <- LayerNorm(x + add2[...]) * ln_weight2 + ln_bias2 (norm2 of one layer and
+ *     norm1 of the next). */
 int nsk_reni_prep(const float* latents, const float* rotation, int64_t K, const float* weights, int latent_dim, int hidden,
                   int num_layers, float* workspace, void* stream);
 int nsk_reni_pe_rows(const float* dirs, const int* row_cam, int64_t N, const float* zxy, int latent_dim, float* pe, void* stream);
 int nsk_reni_ln_rows(float* x, int64_t N, const float* add, int add_stride, const int* row_cam, const float* ln_weight,
-                     const float* ln_bias, void* stream);
+                     const float* ln_bias, const float* add2, const float* ln_weight2, const float* ln_bias2, void* stream);
 /* Collapsed relighting cache (config 5; replaces the per-frame re-render of the reference's illumination animation,
  * neusky/models/neusky_model.py:1896-1980, publication/render_animation.py:188-221):
  * nsk_lambert_collapse: H [R,D,3] = vis * sum_s wa * clamp01(n.l_j) * inv_count   (everything but the light colours; OVERWRITTEN)

@@ -7,7 +7,8 @@
 //                       table path: the single-token attention is a per-code constant)
 //   nsk_reni_pe_rows    decoder input rows [N,512]: VN-invariant inner products, d_z, |d_xy| with their NeRF encoding
 //                       (reni_illumination_field.py:219-246, 345-348), zero-padded from 510 to the MMA K step
-//   nsk_reni_ln_rows    x <- LayerNorm(x + add[code(row)]) * w + b in place, one warp per row (eps 1e-5, biased variance)
+//   nsk_reni_ln_rows    x <- LayerNorm(x + add[code(row)]) * w + b in place, one warp per row (eps 1e-5, biased variance), optionally
+//                       followed by a second (add, LayerNorm) in the same pass
 // All fp32; the elementwise kernels are one pass over their operand (HBM-bound).
 #include "reni_common.cuh"
 
@@ -43,17 +44,7 @@ reni_pe_rows_kernel(const float* __restrict__ dirs, const int* __restrict__ row_
   for (int c = 5 * Lp2 + lane; c < RENI_PE_LD; c += 32) pr[c] = 0.f;
 }
 
-__global__ void __launch_bounds__(256)
-reni_ln_rows_kernel(float* __restrict__ x, int64_t N, const float* __restrict__ add, int add_stride, const int* __restrict__ row_cam,
-                    const float* __restrict__ gw, const float* __restrict__ gb) {
-  const int lane = threadIdx.x & 31;
-  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (row >= N) return;
-  float4 v = *reinterpret_cast<const float4*>(x + row * RENI_H + lane * 4);
-  if (add) {
-    const float4 a = *reinterpret_cast<const float4*>(add + (int64_t)(row_cam ? row_cam[row] : 0) * add_stride + lane * 4);
-    v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
-  }
+__device__ __forceinline__ float4 warp_layernorm4(float4 v, const float* __restrict__ gw, const float* __restrict__ gb, int lane) {
   float s = v.x + v.y + v.z + v.w;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -64,7 +55,33 @@ reni_ln_rows_kernel(float* __restrict__ x, int64_t N, const float* __restrict__ 
   for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
   const float rstd = rsqrtf(q * (1.0f / RENI_H) + 1e-5f);
   const float4 w = *reinterpret_cast<const float4*>(gw + lane * 4), b = *reinterpret_cast<const float4*>(gb + lane * 4);
-  *reinterpret_cast<float4*>(x + row * RENI_H + lane * 4) = make_float4(d0 * rstd * w.x + b.x, d1 * rstd * w.y + b.y, d2 * rstd * w.z + b.z, d3 * rstd * w.w + b.w);
+  return make_float4(d0 * rstd * w.x + b.x, d1 * rstd * w.y + b.y, d2 * rstd * w.z + b.z, d3 * rstd * w.w + b.w);
+}
+
+// x <- LN(x + add) * w + b, optionally followed in registers by x <- LN(x + add2) * w2 + b2 (norm2 of one decoder layer and norm1
+// of the next are back to back: one pass over the activations instead of two)
+__global__ void __launch_bounds__(256)
+reni_ln_rows_kernel(float* __restrict__ x, int64_t N, const float* __restrict__ add, int add_stride, const int* __restrict__ row_cam,
+                    const float* __restrict__ gw, const float* __restrict__ gb, const float* __restrict__ add2,
+                    const float* __restrict__ gw2, const float* __restrict__ gb2) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= N) return;
+  const int64_t code = row_cam ? row_cam[row] : 0;
+  float4 v = *reinterpret_cast<const float4*>(x + row * RENI_H + lane * 4);
+  if (add) {
+    const float4 a = *reinterpret_cast<const float4*>(add + code * add_stride + lane * 4);
+    v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+  }
+  v = warp_layernorm4(v, gw, gb, lane);
+  if (gw2) {
+    if (add2) {
+      const float4 a = *reinterpret_cast<const float4*>(add2 + code * add_stride + lane * 4);
+      v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+    }
+    v = warp_layernorm4(v, gw2, gb2, lane);
+  }
+  *reinterpret_cast<float4*>(x + row * RENI_H + lane * 4) = v;
 }
 
 }  // namespace nsk
@@ -92,12 +109,12 @@ extern "C" int nsk_reni_pe_rows(const float* dirs, const int* row_cam, int64_t N
 }
 
 extern "C" int nsk_reni_ln_rows(float* x, int64_t N, const float* add, int add_stride, const int* row_cam, const float* ln_weight,
-                                const float* ln_bias, void* stream) {
+                                const float* ln_bias, const float* add2, const float* ln_weight2, const float* ln_bias2, void* stream) {
   if (N == 0) return 0;
-  NSK_REQUIRE(x && ln_weight && ln_bias, "nsk_reni_ln_rows: null pointer");
-  NSK_REQUIRE(add == nullptr || (add_stride & 3) == 0, "nsk_reni_ln_rows: add_stride must be a multiple of 4");
+  NSK_REQUIRE(x && ln_weight && ln_bias && ((ln_weight2 == nullptr) == (ln_bias2 == nullptr)), "nsk_reni_ln_rows: null pointer");
+  NSK_REQUIRE((add == nullptr && add2 == nullptr) || (add_stride & 3) == 0, "nsk_reni_ln_rows: add_stride must be a multiple of 4");
   const int64_t blocks = (N + 7) / 8;
   NSK_REQUIRE(blocks < (1ll << 31), "nsk_reni_ln_rows: too many rows for one launch");
-  nsk::reni_ln_rows_kernel<<<(unsigned)blocks, 256, 0, nsk::as_stream(stream)>>>(x, N, add, add_stride, row_cam, ln_weight, ln_bias);
+  nsk::reni_ln_rows_kernel<<<(unsigned)blocks, 256, 0, nsk::as_stream(stream)>>>(x, N, add, add_stride, row_cam, ln_weight, ln_bias, add2, ln_weight2, ln_bias2);
   return nsk::check_launch("reni_ln_rows_kernel");
 }

@@ -283,12 +283,18 @@ def reni_rows_tc(dirs: Tensor, latents: Tensor, scale: Optional[Tensor], packed:
         _lib.check(lib.nsk_reni_pe_rows(_ptr(d_c), _ptr(rc), c_int64(n), _ptr(zxy), c_int(L), _ptr(pe), st), "nsk_reni_pe_rows")
         x = gemm_nt(pe, gemm_w["res_w"], bias=gemm_w["res_b"], split=3)                       # [n,128]
         del pe
+        stride = c_int(num_layers * hidden)
+        _lib.check(lib.nsk_reni_ln_rows(_ptr(x), c_int64(n), _ptr(attn[:, 0]), stride, _ptr(rc), _ptr(gemm_w["n1w0"]), _ptr(gemm_w["n1b0"]), _ptr(None), _ptr(None), _ptr(None), st),
+                   "nsk_reni_ln_rows")                                                         # x = LN1_0(attn_0 + x)
         for i in range(num_layers):
-            _lib.check(lib.nsk_reni_ln_rows(_ptr(x), c_int64(n), _ptr(attn[:, i]), c_int(num_layers * hidden), _ptr(rc), _ptr(gemm_w[f"n1w{i}"]), _ptr(gemm_w[f"n1b{i}"]), st),
-                       "nsk_reni_ln_rows")                                                     # x = LN(attn_i + x)
             h = gemm_nt(x, gemm_w[f"f0w{i}"], bias=gemm_w[f"f0b{i}"], act="relu", split=3)
             gemm_nt(h, gemm_w[f"f2w{i}"], bias=gemm_w[f"f2b{i}"], out=x, accumulate=True, split=3)   # x += fc2(relu(fc1 x))
-            _lib.check(lib.nsk_reni_ln_rows(_ptr(x), c_int64(n), _ptr(None), c_int(0), _ptr(None), _ptr(gemm_w[f"n2w{i}"]), _ptr(gemm_w[f"n2b{i}"]), st), "nsk_reni_ln_rows")
+            if i + 1 < num_layers:    # x = LN1_{i+1}(attn_{i+1} + LN2_i(x)) in one pass
+                _lib.check(lib.nsk_reni_ln_rows(_ptr(x), c_int64(n), _ptr(None), stride, _ptr(rc), _ptr(gemm_w[f"n2w{i}"]), _ptr(gemm_w[f"n2b{i}"]), _ptr(attn[:, i + 1]),
+                                                _ptr(gemm_w[f"n1w{i + 1}"]), _ptr(gemm_w[f"n1b{i + 1}"]), st), "nsk_reni_ln_rows")
+            else:
+                _lib.check(lib.nsk_reni_ln_rows(_ptr(x), c_int64(n), _ptr(None), stride, _ptr(rc), _ptr(gemm_w[f"n2w{i}"]), _ptr(gemm_w[f"n2b{i}"]), _ptr(None), _ptr(None), _ptr(None), st),
+                           "nsk_reni_ln_rows")
         o = gemm_nt(x, gemm_w["fc_w"], bias=gemm_w["fc_b"], split=3)                            # [n,3]
         if scale is not None:
             sc = scale if rc is None else scale[rc.long()][:, None]
