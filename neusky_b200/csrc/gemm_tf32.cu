@@ -739,14 +739,11 @@ constexpr size_t smem_bytes() {
   return (size_t)Cfg<SPLIT, TN, TMA>::ST * Cfg<SPLIT, TN, TMA>::STAGE + 256 + (TN ? 0 : EPI_BYTES);
 }
 
+
+// SM count of the CURRENT device (work-split heuristics only; looked up per call -- an attribute query, no sync)
 static int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
   return n;
 }
 
@@ -780,13 +777,13 @@ static bool make_tensor_map(CUtensorMap* m, const float* base, int64_t rows, int
 template <int SPLIT, bool TN, bool TMA>
 static int launch_variant(const Params& p, const CUtensorMap& ma, const CUtensorMap& mb, cudaStream_t st) {
   auto kern = gemm_tf32_kernel<SPLIT, TN, TMA>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<SPLIT, TN, TMA>());
-    if (e != cudaSuccess) return fail("gemm_tf32: cudaFuncSetAttribute", cudaGetErrorString(e));
-    configured = true;
-  }
-  const int grid = (int)std::min<int64_t>(p.n_items, sm_count());
+  static DeviceOnce once;      // one table per template instantiation
+  int num_sms = 0;
+  if (int err = device_once(once, "gemm_tf32: device setup", &num_sms, [&] {
+        return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<SPLIT, TN, TMA>());
+      }))
+    return err;
+  const int grid = (int)std::min<int64_t>(p.n_items, num_sms);
   kern<<<grid, THREADS, smem_bytes<SPLIT, TN, TMA>(), st>>>(p, ma, mb);
   return check_launch("gemm_tf32_kernel");
 }

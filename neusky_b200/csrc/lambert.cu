@@ -375,12 +375,11 @@ extern "C" int nsk_lambert_prep(const float* normals, const float* wa, int64_t R
     NSK_REQUIRE(nb < (1ll << 31), "nsk_lambert_prep: too many samples for one launch");
     const size_t smem = (size_t)D * 2 * sizeof(float4);
     if (smem > 48 * 1024) {
-      static bool configured = false;
-      if (!configured) {
-        if (cudaFuncSetAttribute(nsk::lambert_prep_samples_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024) != cudaSuccess)
-          return nsk::fail("nsk_lambert_prep", "shared memory opt-in");
-        configured = true;
-      }
+      static nsk::DeviceOnce once;
+      if (int err = nsk::device_once(once, "nsk_lambert_prep: shared memory opt-in", nullptr, [] {
+            return cudaFuncSetAttribute(nsk::lambert_prep_samples_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+          }))
+        return err;
     }
     if (cudaMemsetAsync(rgb_lin, 0, (size_t)R * 3 * sizeof(float), nsk::as_stream(stream)) != cudaSuccess) return nsk::fail("nsk_lambert_prep", "memset");
     nsk::lambert_prep_samples_kernel<<<(unsigned)nb, nsk::LPS_THREADS, smem, nsk::as_stream(stream)>>>(
@@ -439,12 +438,11 @@ extern "C" int nsk_lambert_collapse_sel(const float* normals, const float* wa, c
   NSK_REQUIRE(R < (1ll << 31), "nsk_lambert_collapse_sel: too many rays for one launch");
   const size_t smem = (size_t)S * 2 * sizeof(float4);
   if (smem > 48 * 1024) {
-    static bool configured = false;
-    if (!configured) {
-      if (cudaFuncSetAttribute(nsk::lambert_collapse_sel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024) != cudaSuccess)
-        return nsk::fail("nsk_lambert_collapse_sel", "shared memory opt-in");
-      configured = true;
-    }
+    static nsk::DeviceOnce once;
+    if (int err = nsk::device_once(once, "nsk_lambert_collapse_sel: shared memory opt-in", nullptr, [] {
+          return cudaFuncSetAttribute(nsk::lambert_collapse_sel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        }))
+      return err;
   }
   nsk::lambert_collapse_sel_kernel<<<(unsigned)R, nsk::LCS_THREADS, smem, nsk::as_stream(stream)>>>(normals, wa, inv_count, R, S, dirs_sel, Dp, G);
   return nsk::check_launch("lambert_collapse_sel_kernel");

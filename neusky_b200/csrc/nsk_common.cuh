@@ -6,6 +6,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <math.h>
+#include <atomic>
 
 #include "../../include/neusky_b200.h"
 
@@ -146,5 +147,33 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// ---- per-device one-time setup ----------------------------------------------------------------
+// cudaFuncSetAttribute (dynamic shared-memory opt-in) and the SM count are properties of ONE device; a process may
+// drive several devices and several host threads (training thread + viewer thread on another GPU).  Each launch site
+// owns one `static DeviceOnce` table, indexed by the CURRENT device; the first call on every device runs `setup`.
+// Racing threads may both run `setup` (idempotent); nothing here is a per-process "configured" flag.
+constexpr int MAX_DEVICES = 64;
+struct DeviceOnce {
+  std::atomic<int> ready[MAX_DEVICES];
+  int num_sms[MAX_DEVICES];
+};
+template <typename F>
+inline int device_once(DeviceOnce& st, const char* what, int* num_sms, F&& setup) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return fail(what, cudaGetErrorString(e));
+  if (dev < 0 || dev >= MAX_DEVICES) return fail(what, "device index out of range");
+  if (!st.ready[dev].load(std::memory_order_acquire)) {
+    int n = 0;
+    e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (e == cudaSuccess) e = setup();
+    if (e != cudaSuccess) return fail(what, cudaGetErrorString(e));
+    st.num_sms[dev] = n > 0 ? n : 148;
+    st.ready[dev].store(1, std::memory_order_release);
+  }
+  if (num_sms) *num_sms = st.num_sms[dev];
+  return 0;
+}
 
 }  // namespace nsk

@@ -366,12 +366,11 @@ extern "C" int nsk_reni_decode_bwd(const float* dirs, const int* row_cam, int64_
   if (cudaMemsetAsync(d_attn, 0, (size_t)(n_attn + n_zxy) * sizeof(float), st) != cudaSuccess) return nsk::fail("nsk_reni_decode_bwd", "memset failed");
   if (int e = nsk::reni_launch_prep(latents, rotation, weights, y, K, zxy, attn, st)) return e;
   const size_t smem = nsk::reni_bwd_smem_floats(y.d_in, num_layers) * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(nsk::reni_rows_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)) != cudaSuccess)
-      return nsk::fail("nsk_reni_decode_bwd", "cannot raise the dynamic shared memory limit");
-    attr_set = true;
-  }
+  static nsk::DeviceOnce once;
+  if (int err = nsk::device_once(once, "nsk_reni_decode_bwd: cannot raise the dynamic shared memory limit", nullptr, [] {
+        return cudaFuncSetAttribute(nsk::reni_rows_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024));
+      }))
+    return err;
   NSK_REQUIRE(smem <= 200 * 1024, "nsk_reni_decode_bwd: too many layers for the shared-memory plan");
   dim3 grid((unsigned)((D + nsk::RENI_ROWS - 1) / nsk::RENI_ROWS), row_cam ? 1u : (unsigned)K);
   nsk::reni_rows_bwd_kernel<<<grid, nsk::RENI_H, smem, st>>>(dirs, D, row_cam, zxy, attn, weights, y, weights_bwd, yb, log_domain, scale != nullptr,

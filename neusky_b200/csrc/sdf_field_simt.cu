@@ -289,14 +289,14 @@ extern "C" int nsk_sdf_field_simt_fwd(const float* x, int64_t n, const float* sd
   if (n == 0) return 0;
   NSK_REQUIRE(x && sdf_weights && hash_table && scalings && sdf, "nsk_sdf_field_simt_fwd: null pointer");
   const size_t smem = (size_t)(72 + 4 * nsk::SDF_HID + 72 + 18) * nsk::FR * sizeof(float);
-  static thread_local bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(nsk::sdf_field_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return nsk::fail("cudaFuncSetAttribute(sdf_field_simt_kernel)", cudaGetErrorString(e));
-    attr_set = true;
-  }
+  static nsk::DeviceOnce once;
+  int num_sms = 0;
+  if (int err = nsk::device_once(once, "cudaFuncSetAttribute(sdf_field_simt_kernel)", &num_sms, [&] {
+        return cudaFuncSetAttribute(nsk::sdf_field_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      }))
+    return err;
   const int64_t n_tiles = (n + nsk::FR - 1) / nsk::FR;
-  const int64_t grid = n_tiles < 148 ? n_tiles : 148;
+  const int64_t grid = n_tiles < num_sms ? n_tiles : num_sms;
   const int flags = (grad ? 1 : 0) | (albedo ? 2 : 0);
   nsk::sdf_field_simt_kernel<<<(unsigned)grid, nsk::FT, smem, nsk::as_stream(stream)>>>(
       x, n, sdf_weights, nsk::sdf_layout(), reinterpret_cast<const float2*>(hash_table), scalings, log2_T, flags, sdf, grad,

@@ -568,14 +568,12 @@ extern "C" int nsk_sdf_field_tc_fwd(const float* x, int64_t n, const void* sdf_w
   if (n == 0) return 0;
   NSK_REQUIRE(x && sdf_weights && hash_table && scalings && sdf && grad && albedo, "nsk_sdf_field_tc_fwd: null pointer");
   NSK_REQUIRE((reinterpret_cast<uintptr_t>(sdf_weights) & 15) == 0, "nsk_sdf_field_tc_fwd: weight blob must be 16-byte aligned");
-  static thread_local int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(sdf_field_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
-    if (e != cudaSuccess) { num_sms = 0; return nsk::fail("nsk_sdf_field_tc_fwd: device setup", cudaGetErrorString(e)); }
-  }
+  static nsk::DeviceOnce once;
+  int num_sms = 0;
+  if (int err = nsk::device_once(once, "nsk_sdf_field_tc_fwd: device setup", &num_sms, [] {
+        return cudaFuncSetAttribute(sdf_field_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+      }))
+    return err;
   Params P;
   P.x = x; P.n = n; P.blob = reinterpret_cast<const uint8_t*>(sdf_weights);
   P.table = reinterpret_cast<const float2*>(hash_table); P.scalings = scalings; P.log2_T = log2_T;

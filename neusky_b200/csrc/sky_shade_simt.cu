@@ -219,14 +219,14 @@ extern "C" int nsk_sky_shade_simt_fwd(const float* points, int64_t R, const floa
   NSK_REQUIRE(points && normals && wa && inv_count && dirs && radiance && ddf_weights && hash_table && scalings && rgb_lin,
               "nsk_sky_shade_simt_fwd: null pointer");
   const size_t smem = (size_t)(3 * nsk::DDF_HID + 36 + 16 + 4) * nsk::SR * sizeof(float);
-  static thread_local bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(nsk::sky_shade_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return nsk::fail("cudaFuncSetAttribute(sky_shade_simt_kernel)", cudaGetErrorString(e));
-    attr_set = true;
-  }
+  static nsk::DeviceOnce once;
+  int num_sms = 0;
+  if (int err = nsk::device_once(once, "cudaFuncSetAttribute(sky_shade_simt_kernel)", &num_sms, [&] {
+        return cudaFuncSetAttribute(nsk::sky_shade_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      }))
+    return err;
   const int64_t n_tiles = (R * (int64_t)Dp + nsk::SR - 1) / nsk::SR;
-  const int64_t grid = n_tiles < 148 * 2 ? n_tiles : 148 * 2;
+  const int64_t grid = n_tiles < num_sms * 2 ? n_tiles : num_sms * 2;
   nsk::sky_shade_simt_kernel<<<(unsigned)grid, nsk::ST, smem, nsk::as_stream(stream)>>>(
       points, R, normals, wa, inv_count, S, dirs, Dp, radiance, cam, ddf_weights, nsk::simt_layout(),
       reinterpret_cast<const float2*>(hash_table), scalings, num_levels, log2_T, radius, threshold, sigmoid_scale, rgb_lin,

@@ -534,16 +534,15 @@ extern "C" int nsk_sky_shade_tc_fwd(const float* points, int64_t R, const float*
   NSK_REQUIRE(points && normals && wa && inv_count && dirs && radiance && ddf_weights && hash_table && scalings && rgb_lin,
               "nsk_sky_shade_tc_fwd: null pointer");
   NSK_REQUIRE((reinterpret_cast<uintptr_t>(ddf_weights) & 15) == 0, "nsk_sky_shade_tc_fwd: weight blob must be 16-byte aligned");
-  static thread_local int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(sky_shade_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(sky_shade_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(sky_shade_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
-    if (e != cudaSuccess) { num_sms = 0; return nsk::fail("nsk_sky_shade_tc_fwd: device setup", cudaGetErrorString(e)); }
-  }
+  static nsk::DeviceOnce once;
+  int num_sms = 0;
+  if (int err = nsk::device_once(once, "nsk_sky_shade_tc_fwd: device setup", &num_sms, [] {
+        cudaError_t e = cudaFuncSetAttribute(sky_shade_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(sky_shade_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(sky_shade_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+        return e;
+      }))
+    return err;
   Params P;
   P.points = points; P.R = R; P.normals = normals; P.wa = wa; P.inv_count = inv_count; P.S = S;
   P.dirs = dirs; P.Dp = Dp; P.radiance = radiance; P.cam = cam;

@@ -7,6 +7,8 @@ misuse -- there is no CPU path and no silent fallback (north_star).
 from __future__ import annotations
 
 import ctypes
+import functools
+import types
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -63,6 +65,37 @@ def _chk(name: str, t: Tensor, dtype=torch.float32, shape: Optional[Tuple] = Non
     return t if t.is_contiguous() else t.contiguous()
 
 
+def _chk_out(name: str, t: Tensor, dtype=torch.float32, shape: Optional[Tuple] = None) -> Tensor:
+    """Validation for OUTPUT / accumulator arguments: like `_chk`, but a non-contiguous tensor is an error -- `_chk` would hand the
+    kernel a contiguous temporary and the caller's buffer would silently never be written."""
+    if isinstance(t, torch.Tensor) and t.is_cuda and not t.is_contiguous():
+        raise ValueError(f"{name}: output / accumulator tensors must be contiguous (got strides {t.stride()})")
+    return _chk(name, t, dtype, shape)
+
+
+def _device_guard(fn):
+    """Run an op with the CUDA device of its tensor arguments current.  The kernels, the SM-count / shared-memory opt-in caches
+    (csrc/nsk_common.cuh: device_once) and the stream lookup all act on the process's CURRENT device; a module built with
+    device='cuda:1' while device 0 is current would otherwise launch on GPU 0 against GPU 1 memory.  Mixed-device tensor
+    arguments are an error."""
+
+    @functools.wraps(fn)
+    def wrapped(*args, **kw):
+        dev = None
+        for a in args + tuple(kw.values()):
+            if isinstance(a, torch.Tensor) and a.is_cuda:
+                if dev is None:
+                    dev = a.device
+                elif a.device != dev:
+                    raise ValueError(f"{fn.__name__}: tensor arguments live on different devices ({dev} and {a.device})")
+        if dev is None or dev.index is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kw)
+        with torch.cuda.device(dev):
+            return fn(*args, **kw)
+
+    return wrapped
+
+
 # ------------------------------------------------------------------------------------------- K1
 def hash_encode(x: Tensor, table: Tensor, scalings: Tensor, log2_T: int) -> Tensor:
     """x [...,3] -> [..., 2L]; nerfstudio torch hash-grid semantics."""
@@ -83,7 +116,7 @@ def hash_encode_bwd(x: Tensor, scalings: Tensor, log2_T: int, grad_out: Tensor, 
     g = _chk("grad_out", grad_out.reshape(-1, 2 * L), shape=(x2.shape[0], 2 * L))
     if grad_table is None:
         grad_table = torch.zeros((L << log2_T, 2), device=x.device, dtype=torch.float32)
-    grad_table = _chk("grad_table", grad_table, shape=(L << log2_T, 2))
+    grad_table = _chk_out("grad_table", grad_table, shape=(L << log2_T, 2))
     lib = _lib.load()
     _lib.check(lib.nsk_hash_encode_bwd(_ptr(x2), c_int64(x2.shape[0]), _ptr(_chk("scalings", scalings)), c_int(L), c_int(log2_T), _ptr(g), _ptr(grad_table), _stream(x)), "nsk_hash_encode_bwd")
     return grad_table
@@ -577,7 +610,7 @@ def gemm_tn(A: Tensor, B: Tensor, out: Tensor, split: int = 1) -> Tensor:
 def colsum(X: Tensor, out: Tensor) -> Tensor:
     """out[c] += sum_r X[r, c]."""
     X, ld = _mat("X", X)
-    out = _chk("out", out, shape=(X.shape[1],))
+    out = _chk_out("out", out, shape=(X.shape[1],))
     _lib.check(_lib.load().nsk_colsum(_ptr(X), c_int(ld), c_int64(X.shape[0]), c_int(X.shape[1]), _ptr(out), _stream(X)), "nsk_colsum")
     return out
 
@@ -664,7 +697,7 @@ def colsum_w(X: Tensor, v: Tensor, out: Tensor) -> Tensor:
     """out[c] += sum_r v[r] X[r, c]."""
     X, ld = _mat("X", X)
     v = _chk("v", v.reshape(-1), shape=(X.shape[0],))
-    out = _chk("out", out, shape=(X.shape[1],))
+    out = _chk_out("out", out, shape=(X.shape[1],))
     _lib.check(_lib.load().nsk_colsum_w(_ptr(X), c_int(ld), _ptr(v), c_int64(X.shape[0]), c_int(X.shape[1]), _ptr(out), _stream(X)), "nsk_colsum_w")
     return out
 
@@ -796,3 +829,10 @@ def shade_lights_bwd(mode: int, albedo: Tensor, normals: Tensor, dirs: Tensor, r
                                                 c_int(int(normalize_dirs)), _ptr(radiance), _ptr(cam), _ptr(vis), c_int(rpv), c_int64(N), c_int(M), _ptr(g_a), _ptr(g_b),
                                                 _ptr(d_alb), _ptr(d_nrm), _ptr(d_spec), _ptr(d_shin), _ptr(d_rad), _ptr(d_vis), _stream(albedo)), "nsk_shade_lights_bwd")
     return d_alb, d_nrm, d_spec, d_shin, d_rad, d_vis
+
+
+# every public op runs with the device of its tensor arguments current (see _device_guard)
+for _name, _fn in list(globals().items()):
+    if isinstance(_fn, types.FunctionType) and _fn.__module__ == __name__ and not _name.startswith("_"):
+        globals()[_name] = _device_guard(_fn)
+del _name, _fn

@@ -33,27 +33,45 @@ def max_local_rays(n_rays: int, tile: int, world: int) -> int:
     return max(sum(b - a for a, b in tiles_of_rank(n_rays, tile, r, world)) for r in range(world))
 
 
+_GATHER_MAP: Dict[tuple, Tensor] = {}
+
+
+def _gather_map(n_rays: int, tile: int, world: int, device) -> Tensor:
+    """src [n_rays]: row of the padded all-gather buffer ([world * cap, C]) that holds ray i.  Built once per (image, tile,
+    world, device): tile t sits on rank t mod world at local tile slot t div world."""
+    key = (n_rays, tile, world, str(device))
+    m = _GATHER_MAP.get(key)
+    if m is None:
+        cap = max_local_rays(n_rays, tile, world)
+        i = torch.arange(n_rays, device=device)
+        t = i // tile
+        m = _GATHER_MAP[key] = ((t % world) * cap + (t // world) * tile + (i - t * tile)).contiguous()
+        if len(_GATHER_MAP) > 64:
+            _GATHER_MAP.pop(next(iter(_GATHER_MAP)))
+    return m
+
+
 def gather_rays(local: Tensor, n_rays: int, tile: int, group=None) -> Tensor:
     """local [n_local, C] (rows in the order of local_ray_indices) -> [n_rays, C] on every rank.
-    One all_gather of equally padded buffers (NCCL over NVLink on GPUs, gloo on CPU); world_size 1 is a no-op."""
+    One all_gather of equally padded buffers (NCCL over NVLink on GPUs, gloo on CPU) and ONE indexed copy that puts the
+    rows back into image order; world_size 1 is a no-op."""
     import torch.distributed as dist
 
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         if local.shape[0] != n_rays:
             raise ValueError("gather_rays: single process must hold every ray")
         return local
-    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    world = dist.get_world_size(group)
     C = local.shape[1]
     cap = max_local_rays(n_rays, tile, world)
-    buf = torch.zeros((cap, C), dtype=local.dtype, device=local.device)
-    buf[: local.shape[0]] = local
+    if local.shape[0] == cap:
+        buf = local.contiguous()
+    else:
+        buf = torch.zeros((cap, C), dtype=local.dtype, device=local.device)
+        buf[: local.shape[0]] = local
     out = torch.empty((world * cap, C), dtype=local.dtype, device=local.device)
     dist.all_gather_into_tensor(out, buf, group=group)
-    full = torch.empty((n_rays, C), dtype=local.dtype, device=local.device)
-    for r in range(world):
-        idx = local_ray_indices(n_rays, tile, r, world, device=local.device)
-        full[idx] = out[r * cap : r * cap + idx.shape[0]]
-    return full
+    return out.index_select(0, _gather_map(n_rays, tile, world, local.device))
 
 
 def render_sharded(render_fn: Callable[[Tensor], Dict[str, Tensor]], n_rays: int, tile: int, keys: Tuple[str, ...], device=None, group=None) -> Dict[str, Tensor]:
@@ -87,7 +105,10 @@ class GradBucketReducer:
     of their own; the ~5 MB of MLP weights, latents and scalars share one.  A bucket's all-reduce is issued from a
     post-accumulate-grad hook as soon as its last gradient has landed, on the process group's own stream (NCCL over
     NVLink / NVSwitch on GPUs, gloo on CPU), so the DDF buckets are reduced while the SDF backward is still running.
-    `finish()` waits for the outstanding work and applies the 1/world factor.
+    Buckets are launched in a FIXED order on every rank (bucket i only after buckets 0..i-1, as torch DDP does): a parameter
+    that is unused on one rank only must not reorder that rank's collectives.  One `backward()` per `zero_grad()`: a second
+    backward into already-launched buckets raises instead of silently dropping its gradients.
+    `finish()` launches what is left in order, waits for the outstanding work and applies the 1/world factor.
 
         red = GradBucketReducer(params)           # once
         red.zero_grad(); loss.backward(); red.finish()          # per step: grads are now the mean over ranks
@@ -104,13 +125,16 @@ class GradBucketReducer:
             raise ValueError("GradBucketReducer: no trainable parameters")
         dev = self.params[0].device
         small, assign = [], []
-        for p in self.params:
+        # big parameters in REVERSE registration order (like DDP: gradients of the modules used last in forward arrive first in
+        # backward -- here the DDF hash table, whose 64 MiB all-reduce then overlaps the SDF backward), the small ones last
+        for p in reversed(self.params):
             if p.dtype != torch.float32 or p.device != dev:
                 raise ValueError("GradBucketReducer: parameters must be fp32 on one device")
             if p.numel() * 4 >= big_bytes:
                 assign.append([p])
             else:
                 small.append(p)
+        small.reverse()
         if small:
             assign.append(small)
         self.buckets: List[Tensor] = []
@@ -130,6 +154,8 @@ class GradBucketReducer:
         self._left = list(self._sizes)
         self._work: List = []
         self.launched_order: List[int] = []
+        self._next = 0                      # first bucket not launched yet
+        self._finished = False
         for p in self.params:
             p.register_post_accumulate_grad_hook(self._hook)
 
@@ -144,6 +170,8 @@ class GradBucketReducer:
         self._left = list(self._sizes)
         self._work = []
         self.launched_order = []
+        self._next = 0
+        self._finished = False
 
     def _launch(self, bi: int) -> None:
         import torch.distributed as dist
@@ -156,17 +184,23 @@ class GradBucketReducer:
         bi = self._bucket_of[id(p)]
         if p.grad is None or p.grad.untyped_storage().data_ptr() != self.buckets[bi].untyped_storage().data_ptr():
             raise RuntimeError("GradBucketReducer: a parameter's .grad was replaced; use reducer.zero_grad(), not optimizer.zero_grad(set_to_none=True)")
+        if self._left[bi] <= 0 or self._finished:
+            raise RuntimeError("GradBucketReducer: a gradient arrived for a bucket that is already being reduced -- call reducer.zero_grad() "
+                               "before every backward() (one backward per step; accumulate micro-batches into the loss instead)")
         self._left[bi] -= 1
-        if self._left[bi] == 0:
-            self._launch(bi)
+        # in-order launch: bucket i goes out only when buckets 0..i-1 are out, so every rank issues the same collective sequence
+        while self._next < len(self.buckets) and self._left[self._next] == 0:
+            self._launch(self._next)
+            self._next += 1
 
     def finish(self) -> None:
         """Reduce buckets whose hooks never completed (parameters unused this step keep zero gradients, as DDP's
         find_unused_parameters would), wait, and turn sums into means."""
-        for bi, left in enumerate(self._left):
-            if left > 0:
-                self._left[bi] = 0
-                self._launch(bi)
+        while self._next < len(self.buckets):
+            self._left[self._next] = 0
+            self._launch(self._next)
+            self._next += 1
+        self._finished = True
         for w in self._work:
             w.wait()
         self._work = []

@@ -17,7 +17,7 @@ import torch
 
 from . import _lib
 from .init import hash_scalings
-from .ops import _chk, _ptr, _stream
+from .ops import _chk, _chk_out, _ptr, _stream
 
 Tensor = torch.Tensor
 c_int, c_int64, c_float = ctypes.c_int, ctypes.c_int64, ctypes.c_float
@@ -88,10 +88,8 @@ def proposal_density_bwd(origins: Tensor, dirs: Tensor, near: Tensor, far: Tenso
                          mlp: Tensor, g_density: Tensor, d_table: Optional[Tensor] = None, d_mlp: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
     L = scalings.numel()
     R, S = g_density.shape
-    if d_table is None:
-        d_table = torch.zeros_like(table)
-    if d_mlp is None:
-        d_mlp = torch.zeros_like(mlp)
+    d_table = torch.zeros_like(table) if d_table is None else _chk_out("d_table", d_table, shape=(L << log2_T, 2))
+    d_mlp = torch.zeros_like(mlp) if d_mlp is None else _chk_out("d_mlp", d_mlp, shape=(2 * L * HIDDEN + 2 * HIDDEN + 1,))
     _lib.check(_lib.load().nsk_proposal_density_bwd(_ptr(_chk("origins", origins, shape=(R, 3))), _ptr(_chk("dirs", dirs, shape=(R, 3))), _ptr(_chk("near", near.reshape(-1), shape=(R,))),
                                                     _ptr(_chk("far", far.reshape(-1), shape=(R,))), _ptr(_chk("bins", bins, shape=(R, S + 1))), c_int64(R), c_int(S),
                                                     _ptr(_chk("table", table, shape=(L << log2_T, 2))), _ptr(_chk("scalings", scalings)), c_int(L), c_int(log2_T), _ptr(_chk("mlp", mlp)),
@@ -178,18 +176,6 @@ class HashMLPDensityField:
     def density_on_rays(self, origins: Tensor, dirs: Tensor, near: Tensor, far: Tensor, bins: Tensor) -> Tensor:
         return proposal_density(origins, dirs, near, far, bins, self.table, self.scalings, self.log2_T, self.mlp)
 
-    def backward_on_rays(self, origins, dirs, near, far, bins, g_density: Tensor) -> None:
-        """Accumulate d loss / d params into ``.grad`` of the field's parameters."""
-        d_table, d_mlp = proposal_density_bwd(origins, dirs, near, far, bins, self.table, self.scalings, self.log2_T, self.mlp, g_density)
-        grads = unpack_proposal_mlp_grad(d_mlp, self.num_levels)
-        grads["encoding.hash_table"] = d_table
-        for k, g in grads.items():
-            p = self.params[k]
-            if p.grad is None:
-                p.grad = g
-            else:
-                p.grad.add_(g)          # in place: .grad may be a view into a GradBucketReducer communication bucket
-
 
 def _ray_samples(origins, dirs, euclid, spacing, near, far):
     """Duck-typed nerfstudio RaySamples [SURVEY A.1] over [R,S+1] edges (views, no copies)."""
@@ -251,18 +237,42 @@ class ProposalNetworkSampler:
 
     __call__ = generate_ray_samples
 
-    def interlevel_loss_backward(self, fine_weights: Tensor, fine_samples, origins, directions, nears, fars, loss_mult: float = 1.0) -> Tensor:
+    def interlevel_loss(self, fine_weights: Tensor, fine_samples, origins, directions, nears, fars) -> Tensor:
         """nerfstudio ``interlevel_loss(weights_list, ray_samples_list)`` (neusky_model.py:987-988) with the fine NeuS weights appended as
-        the reference does (:575-576), and its backward into the proposal networks' ``.grad`` (weights -> density -> MLP + hash table).
-        Returns the (unscaled) loss."""
+        the reference does (:575-576).  The (unscaled) loss is returned through autograd: its backward runs weights -> density ->
+        MLP + hash table (nsk_density_weights_bwd, nsk_proposal_density_bwd) scaled by the incoming cotangent, so loss scaling,
+        gradient accumulation and ``torch.no_grad()`` behave as for any torch loss; the fine histogram is detached like the reference's."""
         near, far = nears.reshape(-1).contiguous(), fars.reshape(-1).contiguous()
         c = fine_samples.spacing_bins
         w = fine_weights.reshape(c.shape[0], -1).detach()
+        params = [p for st in self._state for p in st["field"].params.values()]
+        return _InterlevelLoss.apply(self._state, c, w, origins, directions, near, far, *params)
+
+
+class _InterlevelLoss(torch.autograd.Function):
+    """Sum over proposal levels of lossfun_outer(fine, proposal); inputs of the graph = the proposal fields' parameters."""
+
+    @staticmethod
+    def forward(ctx, state, c, w, origins, directions, near, far, *params):
         total = torch.zeros((), device=c.device)
-        for st in self._state:
-            bins, dens, field, wp = st["bins"], st["density"], st["field"], st["weights"]       # weights_list holds the un-annealed weights
-            loss, g_wp = interlevel_loss_level(c, w, bins, wp, want_grad=True)
+        need = any(ctx.needs_input_grad[7:])
+        g_list = []
+        for st in state:
+            loss, g_wp = interlevel_loss_level(c, w, st["bins"], st["weights"], want_grad=need)       # weights_list holds the un-annealed weights
             total = total + loss
-            g_d = density_weights_bwd(bins, dens, near, far, g_wp * loss_mult)
-            field.backward_on_rays(origins, directions, near, far, bins, g_d)
+            g_list.append(g_wp)
+        ctx.levels = [(st["bins"], st["density"], st["field"], g) for st, g in zip(state, g_list)]
+        ctx.rays = (origins, directions, near, far)
         return total
+
+    @staticmethod
+    def backward(ctx, g):
+        origins, directions, near, far = ctx.rays
+        grads = []
+        for bins, dens, field, g_wp in ctx.levels:
+            g_d = density_weights_bwd(bins, dens, near, far, (g_wp * g).contiguous())
+            d_table, d_mlp = proposal_density_bwd(origins, directions, near, far, bins, field.table, field.scalings, field.log2_T, field.mlp, g_d)
+            gm = unpack_proposal_mlp_grad(d_mlp, field.num_levels)
+            gm["encoding.hash_table"] = d_table
+            grads += [gm[k].reshape(p.shape) for k, p in field.params.items()]
+        return (None,) * 7 + tuple(grads)

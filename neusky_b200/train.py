@@ -571,10 +571,9 @@ class NeuSkyTrainStep(torch.nn.Module):
         out = {"rgb": rgb, "eik_grad": grad.reshape(R, S, 3), "weights": weights, "normal": normal, "accumulation": acc, "hdr_background_colours": bg,
                "p2p_dist": p2p, "sdf_at_termination": sdf_term, "visibility_sel": vis, "expected_termination_dist": that}
         if rs is not None:
-            # nerfstudio interlevel_loss with the fine NeuS weights appended (neusky_model.py:575-576, 987-988): value here, gradients
-            # straight into the proposal networks' .grad (weights -> density -> MLP + hash table; the fine histogram is detached)
-            out["interlevel_loss"] = self.proposal_sampler.interlevel_loss_backward(weights.detach(), rs, o, d, near, far,
-                                                                                    loss_mult=LOSS_COEFFICIENTS["interlevel_loss"])
+            # nerfstudio interlevel_loss with the fine NeuS weights appended (neusky_model.py:575-576, 987-988), through autograd into the
+            # proposal networks (weights -> density -> MLP + hash table; the fine histogram is detached)
+            out["interlevel_loss"] = self.proposal_sampler.interlevel_loss(weights.detach(), rs, o, d, near, far)
             out["starts"], out["ends"] = starts, ends
         if grid_positions is not None:
             gs, gg, _ = sdf_field(self.sdf_cfg, grid_positions, table, sdf_w, want_normals=True, want_albedo=False)
@@ -602,5 +601,5 @@ class NeuSkyTrainStep(torch.nn.Module):
         if "grid_density" in out:
             L["hashgrid_density_loss"] = out["grid_density"].abs().mean()
         if "interlevel_loss" in out:
-            L["interlevel_loss"] = out["interlevel_loss"].detach()       # its gradient has already been accumulated (see forward)
+            L["interlevel_loss"] = out["interlevel_loss"]
         return {k: v * LOSS_COEFFICIENTS[k] for k, v in L.items()}
