@@ -58,6 +58,12 @@ int nsk_hash_encode_grad_x_bwd(const float* x, int64_t n, const float* table, co
                                int log2_T, const float* grad_out, const float* cot_x, float* d_grad_out, float* d_table,
                                void* stream);
 
+/* tcnn ("tiny-cuda-nn") grid semantics for imported reference checkpoints: the reference's encodings are tcnn.Encoding modules
+ * (neusky/fields/sdf_albedo_field.py:117-130, neusky/fields/directional_distance_field.py:139-156).  x [n,3] in [0,1];
+ * table = fp32 [L*T,2] filled by neusky_b200.tcnn_import.tcnn_params_to_table; level_meta int32 [L,4] = (float bits of the
+ * level scale, resolution, entries in the level, dense flag), 16-byte aligned; smoothstep 0/1 -> out [n, 2L]. */
+int nsk_hash_encode_tcnn_fwd(const float* x, int64_t n, const float* table, const int32_t* level_meta, int num_levels, int log2_T,
+                             int smoothstep, float* out, void* stream);
 /* Integer part only, for bit-exact index parity tests: idx [n,L,8] int64 (including the l*T level
  * offset, corner order of SURVEY A.3), offsets [n,L,3]. */
 int nsk_hash_indices(const float* x, int64_t n, const float* scalings, int num_levels, int log2_T,
@@ -125,7 +131,8 @@ int nsk_neus_finalize_depth(const float* p2p_raw, const float* dnorm, const floa
  *  neusky/models/neusky_model.py:445-551).
  *   dirs [D,3], latents [K,Ld,3], scale [K] (NULL = no scale), rotation [3,3] (NULL = none; applied
  *   to the latent, Z@R), weights = packed fp32 blob (layout: nsk_reni_weights_floats / python
- *   neusky_b200.packing.pack_reni), workspace [K*6*H] floats, out [K,D,3] = exp(log-HDR) when log_domain.
+ *   neusky_b200.packing.pack_reni), workspace [K*6*H] floats, out [K,D,3] = exp(log-HDR) when log_domain == 1;
+ *   log_domain == 2: log-domain model, out = the raw log-HDR value (what RENIField.forward returns before unnormalise()).
  * ------------------------------------------------------------------------------------------- */
 int64_t nsk_reni_weights_floats(int latent_dim, int hidden, int num_layers);
 int nsk_reni_decode_fwd(const float* dirs, int64_t D, const float* latents, const float* scale, int64_t K,

@@ -175,6 +175,47 @@ hash_encode_grad_x_bwd_kernel(const float* __restrict__ x, int64_t n, const floa
   if (d_g) { d_g[p * 2 * L + 2 * lev] = ja; d_g[p * 2 * L + 2 * lev + 1] = jb; }
 }
 
+// ---- tcnn ("tiny-cuda-nn") grid semantics ---------------------------------------------------------------------------
+// The reference's own encodings are tcnn.Encoding modules (sdf_albedo_field.py:117-130, directional_distance_field.py:139-156);
+// a trained checkpoint therefore needs tcnn's indexing to be read back (SURVEY A.3 "tcnn differences", restated from memory of
+// tiny-cuda-nn grid.h -- unpinned against tcnn itself, pinned by self-consistency tests).  Per level: pos = x * scale + 0.5,
+// corners floor / floor + 1, dense index x + y res + z res^2 when res^3 fits the level, else the prime hash, both modulo the
+// level's size; linear or smoothstep weights.  meta [L][4] int32 = (float bits of scale, resolution, size, dense);
+// the table is our fp32 [L * T, 2] layout filled by tcnn_import.tcnn_params_to_table.
+__global__ void __launch_bounds__(256)
+hash_encode_tcnn_fwd_kernel(const float* __restrict__ x, int64_t n, const float2* __restrict__ table, const int4* __restrict__ meta,
+                            int L, int log2_T, int smoothstep, float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;     // one thread per (point, level): level-major gathers per warp
+  const int lev = blockIdx.y;
+  if (i >= n) return;
+  const int4 m = meta[lev];
+  const float scale = __int_as_float(m.x);
+  const uint32_t res = (uint32_t)m.y, size = (uint32_t)m.z;
+  const bool dense = m.w != 0;
+  float w[3];
+  uint32_t g[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const float pos = fmaf(x[i * 3 + d], scale, 0.5f);
+    const float fl = floorf(pos);
+    g[d] = (uint32_t)(int)fl;
+    const float t = pos - fl;
+    w[d] = smoothstep ? t * t * (3.0f - 2.0f * t) : t;
+  }
+  const float2* tl = table + ((size_t)lev << log2_T);
+  float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const uint32_t gx = g[0] + (c & 1), gy = g[1] + ((c >> 1) & 1), gz = g[2] + ((c >> 2) & 1);
+    const float wc = ((c & 1) ? w[0] : 1.f - w[0]) * (((c >> 1) & 1) ? w[1] : 1.f - w[1]) * (((c >> 2) & 1) ? w[2] : 1.f - w[2]);
+    const uint32_t idx = (dense ? gx + gy * res + gz * res * res : (gx ^ (gy * 2654435761u) ^ (gz * 805459861u))) % size;
+    const float2 f = __ldg(tl + idx);
+    acc.x = fmaf(wc, f.x, acc.x);
+    acc.y = fmaf(wc, f.y, acc.y);
+  }
+  reinterpret_cast<float2*>(out)[i * L + lev] = acc;
+}
+
 }  // namespace nsk
 
 extern "C" int nsk_hash_encode_grad_x(const float* x, int64_t n, const float* table, const float* scalings, int num_levels,
@@ -230,4 +271,17 @@ extern "C" int nsk_hash_indices(const float* x, int64_t n, const float* scalings
   const int64_t total = n * num_levels;
   nsk::hash_indices_kernel<<<(unsigned)((total + 255) / 256), 256, 0, nsk::as_stream(stream)>>>(x, n, scalings, num_levels, log2_T, idx, offsets);
   return nsk::check_launch("hash_indices_kernel");
+}
+
+extern "C" int nsk_hash_encode_tcnn_fwd(const float* x, int64_t n, const float* table, const int32_t* level_meta, int num_levels, int log2_T,
+                                        int smoothstep, float* out, void* stream) {
+  NSK_REQUIRE(num_levels >= 1 && num_levels <= nsk::HE_MAX_LEVELS, "nsk_hash_encode_tcnn_fwd: num_levels out of range");
+  NSK_REQUIRE(log2_T >= 1 && log2_T <= 28, "nsk_hash_encode_tcnn_fwd: log2_T out of range");
+  if (n == 0) return 0;
+  NSK_REQUIRE(x && table && level_meta && out, "nsk_hash_encode_tcnn_fwd: null pointer");
+  NSK_REQUIRE((reinterpret_cast<uintptr_t>(level_meta) & 15) == 0, "nsk_hash_encode_tcnn_fwd: level_meta must be 16-byte aligned");
+  dim3 grid((unsigned)((n + 255) / 256), num_levels);
+  nsk::hash_encode_tcnn_fwd_kernel<<<grid, 256, 0, nsk::as_stream(stream)>>>(x, n, reinterpret_cast<const float2*>(table),
+                                                                            reinterpret_cast<const int4*>(level_meta), num_levels, log2_T, smoothstep, out);
+  return nsk::check_launch("hash_encode_tcnn_fwd_kernel");
 }

@@ -186,7 +186,9 @@ reni_rows_kernel(const float* __restrict__ dirs, int64_t D, const int* __restric
         const float s = expf(scale[k]);
         o = log_domain ? (o + logf(s)) : (o * s);
       }
-      out[((row_cam ? 0 : (int64_t)k * D) + row0 + r) * 3 + c] = log_domain ? expf(o) : o;
+      // log_domain: 0 = linear model; 1 = log-domain model, unnormalised radiance exp(o) (BaseRENIField.unnormalise folded in);
+      // 2 = log-domain model, the raw log value as RENIField.forward returns it (no exp -> log round trip, which underflows to -inf)
+      out[((row_cam ? 0 : (int64_t)k * D) + row0 + r) * 3 + c] = log_domain == 1 ? expf(o) : o;
     }
   }
 }

@@ -65,9 +65,11 @@ constexpr int EPI_THREADS = 256, PRO_THREADS = 128;
 //   M1: [256][32] [256][16]        (K = 35 features + bias hi/lo columns, padded to 48)
 //   M2..M5: 8 x [256][32] + [256][16] (the 16-wide tail carries the bias hi/lo columns)
 //   FP(l,c): 4 x [128][64] + [128][16]   rows 0..63 freq', rows 64..127 phase' of columns c*64..c*64+63
-//   Z_0: [256][16] ; Z_1..Z_4: 8 x [256][32]  (trunk biases are folded into phase')
-constexpr int STAGES_PER_TILE = 2 + 4 * 9 + 20 * 5 + 1 + 4 * 8;  // 171
-constexpr int64_t STREAM_BYTES = (16384 + 8192) + 4ll * (8 * 16384 + 8192) + 20ll * (4 * 16384 + 4096) + 8192 + 4ll * 8 * 16384;
+//   Z_0: [256][48] = [W_hi | W_hi | W_lo] against the input tile [x_hi | x_lo | x_hi] (fp16 hi/lo split of BOTH operands of the
+//        first trunk layer: its pre-activation is multiplied by freq' ~ 30..45, and the fp16 rounding of the 15 direction features
+//        and of W_0 was ~85 % of this path's visibility error; the split costs two extra K = 16 MMAs per tile)
+//   Z_1..Z_4: 8 x [256][32]  (trunk biases are folded into phase')
+constexpr int64_t STREAM_BYTES = (16384 + 8192) + 4ll * (8 * 16384 + 8192) + 20ll * (4 * 16384 + 4096) + 24576 + 4ll * 8 * 16384;
 constexpr int TAIL_FLOATS = 256 /*w_final*/ + 4 /*b_final*/;
 constexpr int64_t STREAM_BYTES_RANK = STREAM_BYTES / 2;        // each CTA of the pair streams its N/2 rows of every operand tile
 constexpr int64_t BLOB_BYTES = STREAM_BYTES + (int64_t)TAIL_FLOATS * 4;   // [rank-0 half | rank-1 half | tail]
@@ -77,11 +79,12 @@ constexpr int KM = 272;                            // ACT_M K extent (256 + ones
 constexpr uint32_t OFF_ACT_M = 0;                  // [128][272] fp16
 constexpr uint32_t OFF_ACT_H = TM * KM * 2;        // [128][256] fp16
 constexpr uint32_t OFF_IN_M = OFF_ACT_H + 65536;   // [128][48] fp16
-constexpr uint32_t OFF_IN_H = OFF_IN_M + 12288;    // [128][16] fp16
-constexpr uint32_t OFF_RING = OFF_IN_H + 4096;
+constexpr uint32_t OFF_IN_H = OFF_IN_M + 12288;    // [128][48] fp16: x_hi | x_lo | x_hi
+constexpr uint32_t OFF_RING = OFF_IN_H + 12288;
 constexpr uint32_t OFF_GEO = OFF_RING + NSTAGE * STAGE_BYTES;   // [2][128] x {term, pad} + fin[128]
 constexpr uint32_t OFF_BAR = OFF_GEO + 2 * 128 * 4 + 128 * 4;
 constexpr uint32_t SMEM_BYTES = OFF_BAR + 32 * 8 + 16;
+static_assert(SMEM_BYTES <= 227 * 1024, "shared-memory plan exceeds the 227 KB per-CTA limit");
 
 // barrier indices
 enum { B_WFULL = 0, B_WEMPTY = 4, B_INFULL = 8, B_INEMPTY = 9, B_ACCA = 10, B_MAPB = 11, B_FPFULL = 12, B_MACT = 14, B_FPFREE = 15, B_PFULL = 17, B_COUNT = 21 };
@@ -154,7 +157,7 @@ __constant__ Schedule c_sched = Schedule();
 __constant__ int c_shape_N[6] = {256, 256, 128, 256, 256, 0};
 __constant__ int c_shape_nfull[6] = {0, 4, 2, 0, 4, 0};
 __constant__ int c_shape_kps[6] = {64, 64, 128, 64, 64, 0};
-__constant__ int c_shape_ktail[6] = {48, 16, 16, 16, 0, 0};
+__constant__ int c_shape_ktail[6] = {48, 16, 16, 48, 0, 0};
 
 template <int VARIANT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) sky_shade_tc2_kernel(const Params P) {
@@ -539,11 +542,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) sky_
 #pragma unroll
         for (int kc = 0; kc < 6; ++kc)
           *reinterpret_cast<uint4*>(dm + kc * (TM * 16)) = make_uint4(mp[kc * 4], mp[kc * 4 + 1], mp[kc * 4 + 2], mp[kc * 4 + 3]);
+        // trunk input [x_hi (16) | x_lo (16) | x_hi (16)]: x = hi + lo exactly to ~2^-22, both halves fp16
         uint8_t* dh = smem + OFF_IN_H + row * 16;
 #pragma unroll
-        for (int kc = 0; kc < 2; ++kc)
-          *reinterpret_cast<uint4*>(dh + kc * (TM * 16)) = make_uint4(pack_h2(feat[kc * 8], feat[kc * 8 + 1]), pack_h2(feat[kc * 8 + 2], feat[kc * 8 + 3]),
-                                                                       pack_h2(feat[kc * 8 + 4], feat[kc * 8 + 5]), pack_h2(feat[kc * 8 + 6], feat[kc * 8 + 7]));
+        for (int kc = 0; kc < 2; ++kc) {
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float a = feat[kc * 8 + 2 * j], b = feat[kc * 8 + 2 * j + 1];
+            const __half2 h = __floats2half2_rn(a, b);
+            const float2 hf = __half22float2(h);
+            hi[j] = *reinterpret_cast<const uint32_t*>(&h);
+            lo[j] = pack_h2(a - hf.x, b - hf.y);
+          }
+          const uint4 vh = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(dh + kc * (TM * 16)) = vh;
+          *reinterpret_cast<uint4*>(dh + (2 + kc) * (TM * 16)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          *reinterpret_cast<uint4*>(dh + (4 + kc) * (TM * 16)) = vh;
+        }
       }
       geo_term[par * 128 + row] = term;
       fence_proxy_async_smem();

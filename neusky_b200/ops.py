@@ -147,6 +147,19 @@ def hash_encode_grad_x_bwd(x: Tensor, table: Tensor, scalings: Tensor, log2_T: i
     return d_g, d_t
 
 
+def hash_encode_tcnn(x: Tensor, table: Tensor, level_meta: Tensor, log2_T: int, smoothstep: bool = True) -> Tensor:
+    """x [...,3] in [0,1] -> [..., 2L] with tiny-cuda-nn's grid semantics (imported reference checkpoints, tcnn_import.py)."""
+    lead = x.shape[:-1]
+    x2 = _chk("x", x.reshape(-1, 3), shape=(None, 3))
+    L = level_meta.shape[0]
+    table = _chk("table", table, shape=(L << log2_T, 2))
+    level_meta = _chk("level_meta", level_meta, dtype=torch.int32, shape=(L, 4))
+    out = torch.empty((x2.shape[0], 2 * L), device=x.device, dtype=torch.float32)
+    _lib.check(_lib.load().nsk_hash_encode_tcnn_fwd(_ptr(x2), c_int64(x2.shape[0]), _ptr(table), _ptr(level_meta), c_int(L), c_int(log2_T), c_int(int(smoothstep)),
+                                                    _ptr(out), _stream(x)), "nsk_hash_encode_tcnn_fwd")
+    return out.reshape(*lead, 2 * L)
+
+
 def hash_indices(x: Tensor, scalings: Tensor, log2_T: int) -> Tuple[Tensor, Tensor]:
     x2 = _chk("x", x.reshape(-1, 3), shape=(None, 3))
     L = scalings.numel()

@@ -6,6 +6,7 @@ update on the host/GPU with torch ops; the kernels never see nn.Parameters direc
 """
 from __future__ import annotations
 
+import functools
 from typing import Dict
 
 import torch
@@ -14,6 +15,27 @@ Tensor = torch.Tensor
 DDF_HID, DDF_LAYERS = 256, 5
 
 
+def _host_packed(fn):
+    """Run a packer on the HOST and upload the finished blob once.  The packers are a few hundred tiny slicing / cast / concat
+    steps (171 operand stages for the DDF stream alone); as device ops that is ~1000 torch kernel launches per weight set, which
+    buried the product's own kernels in every launch trace.  On the host they cost a few milliseconds and the device sees one
+    memcpy.  `device`: where the blob should live (default: the device of the parameters passed in).  Hash tables are not
+    touched by any packer and stay where they are."""
+
+    @functools.wraps(fn)
+    def wrapped(p: Dict[str, Tensor], *args, device=None, **kw):
+        tensors = [v for v in p.values() if isinstance(v, Tensor)]
+        dev = torch.device(device) if device is not None else (tensors[0].device if tensors else torch.device("cpu"))
+        ph = {k: (v.detach().to("cpu") if isinstance(v, Tensor) and "hash_table" not in k else v) for k, v in p.items()}
+        out = fn(ph, *args, **kw)
+        if isinstance(out, dict):
+            return {k: v.to(dev) for k, v in out.items()}
+        return out.to(dev)
+
+    return wrapped
+
+
+@_host_packed
 def pack_ddf_simt(p: Dict[str, Tensor]) -> Tensor:
     """fp32, weights transposed to [K][N]: mapping 0..5, trunk 0..4, final (see simt_layout())."""
     parts = []
@@ -27,6 +49,7 @@ def pack_ddf_simt(p: Dict[str, Tensor]) -> Tensor:
     return torch.cat([x.to(torch.float32) for x in parts]).contiguous()
 
 
+@_host_packed
 def pack_reni(p: Dict[str, Tensor], num_layers: int = 6) -> Tensor:
     """fp32 blob for nsk_reni_decode_fwd (see reni_layout()); linear weights transposed to [in][out]."""
     dev = p["network.fc.weight"].device
@@ -52,6 +75,7 @@ def pack_reni(p: Dict[str, Tensor], num_layers: int = 6) -> Tensor:
     return torch.cat([x.to(torch.float32).flatten() for x in parts]).contiguous()
 
 
+@_host_packed
 def pack_reni_gemm(p: Dict[str, Tensor], num_layers: int = 6) -> Dict[str, Tensor]:
     """Decoder weights in the [out, in] layout nsk_gemm_tf32_nt takes (torch's own), for ops.reni_rows_tc: the residual
     projection zero-padded from 510 to 512 input columns, per layer norm1 / fc.0 / fc.2 / norm2, and the 128 -> 3 head."""
@@ -67,6 +91,7 @@ def pack_reni_gemm(p: Dict[str, Tensor], num_layers: int = 6) -> Dict[str, Tenso
     return out
 
 
+@_host_packed
 def pack_reni_bwd(p: Dict[str, Tensor], num_layers: int = 6) -> Tensor:
     """fp32 blob for nsk_reni_decode_bwd (see reni_bwd_layout()): the decoder's linear weights in torch's own [out][in]
     layout, which is the coalesced one for the transposed products of the backward pass."""
@@ -77,6 +102,7 @@ def pack_reni_bwd(p: Dict[str, Tensor], num_layers: int = 6) -> Tensor:
     return torch.cat([x.to(torch.float32).contiguous().flatten() for x in parts]).contiguous()
 
 
+@_host_packed
 def pack_ddf_tc2(p: Dict[str, Tensor]) -> Tensor:
     """uint8 blob for nsk_sky_shade_tc2_fwd (CTA-pair kernel, csrc/sky_shade_tc2.cu): the same operand matrices as
     pack_ddf_tc, but every [N][K] tile is split by rows between the two CTAs of a pair (rank r streams rows
@@ -97,9 +123,11 @@ def pack_ddf_tc2(p: Dict[str, Tensor]) -> Tensor:
     def z(l):
         W = f32(f"ddf.net.{l}.layer.weight")
         if l == 0:
+            # [W_hi | W_hi | W_lo] against the kernel's input tile [x_hi | x_lo | x_hi]: x W^T = x_hi W_hi + x_lo W_hi + x_hi W_lo (+ 2^-22)
             W0 = torch.zeros((DDF_HID, 16), dtype=torch.float32, device=dev)
             W0[:, :15] = W
-            return (W0, 0, 64, 16)
+            hi = W0.to(torch.float16).to(torch.float32)
+            return (torch.cat([hi, hi, W0 - hi], 1), 0, 64, 48)
         return (W, 4, 64, 0)
 
     ops_ += [fp(0, 0), z(0), fp(0, 1)]
@@ -114,7 +142,7 @@ def pack_ddf_tc2(p: Dict[str, Tensor]) -> Tensor:
             h = W.shape[0] // 2
             st += _stages(W[r * h:(r + 1) * h], nfull, kps, ktail)
         streams.append(torch.cat(st).contiguous().view(torch.uint8))
-    assert streams[0].numel() == TC_STREAM_BYTES // 2 == streams[1].numel(), (streams[0].numel(), TC_STREAM_BYTES)
+    assert streams[0].numel() == TC2_STREAM_BYTES // 2 == streams[1].numel(), (streams[0].numel(), TC2_STREAM_BYTES)
     vec = torch.zeros(TC_TAIL_FLOATS, dtype=torch.float32, device=dev)
     vec[:256] = f32("ddf.final_layer.weight").flatten()
     vec[256] = f32("ddf.final_layer.bias").flatten()[0]
@@ -130,6 +158,7 @@ def fold_weight_norm(p: Dict[str, Tensor], name: str) -> Tensor:
     return v * (g / v.norm(dim=1, keepdim=True))
 
 
+@_host_packed
 def pack_sdf_simt(p: Dict[str, Tensor]) -> Tensor:
     """fp32 blob for nsk_sdf_field_simt_fwd (see sdf_layout() in csrc/sdf_field_simt.cu): forward weights
     transposed to [K][N], reverse-pass weights in torch's [out][in] layout.  NeuSky shape only
@@ -160,6 +189,7 @@ def pack_sdf_simt(p: Dict[str, Tensor]) -> Tensor:
 # ------------------------------------------------------------------------------------------------
 TC_STREAM_BYTES = (16384 + 8192) + 4 * (8 * 16384 + 8192) + 20 * (4 * 16384 + 4096) + 8192 + 4 * 8 * 16384
 TC_TAIL_FLOATS = 256 + 4
+TC2_STREAM_BYTES = TC_STREAM_BYTES + 16384      # CTA-pair kernel: the first trunk layer carries an fp16 hi/lo split of both operands (K = 48)
 
 
 def _image(W: Tensor) -> Tensor:
@@ -202,6 +232,7 @@ def fold_film(p: Dict[str, Tensor]):
     return Wf, bf, Wp, bp
 
 
+@_host_packed
 def pack_ddf_tc(p: Dict[str, Tensor]) -> Tensor:
     """uint8 blob [TC_STREAM_BYTES + 260*4] for nsk_sky_shade_tc_fwd."""
     dev = p["ddf.final_layer.weight"].device
@@ -245,6 +276,7 @@ def pack_ddf_tc(p: Dict[str, Tensor]) -> Tensor:
 SDF_TC_STREAM_BYTES = 256 * 80 * 2 + 3 * 256 * 272 * 2 + 256 * 256 * 2 + 80 * 256 * 2 + 256 * (48 + 272) * 2 + 16 * 272 * 2
 
 
+@_host_packed
 def pack_sdf_tc(p: Dict[str, Tensor]) -> Tensor:
     """uint8 blob [SDF_TC_STREAM_BYTES + 260*4] for nsk_sdf_field_tc_fwd (weight_norm folded)."""
     W0, W1, W2 = (fold_weight_norm(p, f"glin{l}") for l in range(3))

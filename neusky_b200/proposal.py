@@ -147,34 +147,65 @@ def interlevel_loss_level(c: Tensor, w: Tensor, cp: Tensor, wp: Tensor, want_gra
 
 
 # ------------------------------------------------------------------------------------------------ reference-named surface
-class HashMLPDensityField:
+class _Table(torch.nn.Module):
+    def __init__(self, table: Tensor):
+        super().__init__()
+        self.hash_table = torch.nn.Parameter(table)
+
+
+class HashMLPDensityField(torch.nn.Module):
     """nerfstudio ``HashMLPDensityField`` as NeuSFactoModel builds its proposal networks [SURVEY A.6]: hash grid (5 levels, T = 2^17,
     base_res 16, max_res 64 / 256) + Linear(10,16) + ReLU + Linear(16,1) + trunc_exp, on the L-inf-contracted position mapped to
-    [0,1]^3, density zeroed outside (0,1)^3.  ``params`` uses the reference state_dict layout of the field's ``mlp_base``
-    split into ``encoding.hash_table`` / ``mlp.{0,1}.{weight,bias}``."""
+    [0,1]^3, density zeroed outside (0,1)^3.  ``params``: ``encoding.hash_table`` / ``mlp.{0,1}.{weight,bias}`` (the field's
+    ``mlp_base`` split into its two halves); they are registered under exactly those names (``state_dict`` round-trips)."""
 
     def __init__(self, params: Dict[str, Tensor], max_res: int, num_levels: int = 5, base_res: int = 16, log2_hashmap_size: int = 17, device="cuda"):
+        super().__init__()
         self.device = torch.device(device)
         self.num_levels, self.log2_T, self.max_res = num_levels, log2_hashmap_size, max_res
-        self.scalings = hash_scalings(num_levels, base_res, max_res).to(self.device)
-        self.params = {k: torch.nn.Parameter(v.detach().to(self.device, torch.float32).contiguous()) for k, v in params.items()}
+        self.register_buffer("scalings", hash_scalings(num_levels, base_res, max_res).to(self.device), persistent=False)
+        f = lambda k: params[k].detach().to(self.device, torch.float32).contiguous()
+        self.encoding = _Table(f("encoding.hash_table"))
+        lins = []
+        for i in range(2):
+            W, b = f(f"mlp.{i}.weight"), f(f"mlp.{i}.bias")
+            lin = torch.nn.Linear(W.shape[1], W.shape[0], device=self.device)
+            with torch.no_grad():
+                lin.weight.copy_(W)
+                lin.bias.copy_(b)
+            lins.append(lin)
+        self.mlp = torch.nn.ModuleList(lins)
+        self._mlp_key = None
         self.refresh()
 
-    def refresh(self) -> None:
-        """Re-pack the MLP blob after an optimizer step."""
-        self.mlp = pack_proposal_mlp({k: v.detach() for k, v in self.params.items()})
-        self.table = self.params["encoding.hash_table"].detach()
+    @property
+    def params(self) -> Dict[str, torch.nn.Parameter]:
+        return dict(self.named_parameters())
 
-    def parameters(self) -> List[torch.nn.Parameter]:
-        return list(self.params.values())
+    def _apply(self, fn, *args, **kwargs):
+        """Module.to / .cuda: the packed blob and the cached device follow the parameters."""
+        r = super()._apply(fn, *args, **kwargs)
+        self.device = self.encoding.hash_table.device
+        self._mlp_key = None
+        self.refresh()
+        return r
+
+    def refresh(self) -> None:
+        """Re-pack the MLP blob when a parameter changed (optimizer step, load_state_dict)."""
+        ps = self.params
+        key = tuple((v.data_ptr(), v._version) for v in ps.values())
+        if key != self._mlp_key:
+            self.mlp_blob = pack_proposal_mlp({k: v.detach() for k, v in ps.items()})
+            self._mlp_key = key
+        self.table = ps["encoding.hash_table"].detach()
 
     def density_fn(self, positions: Tensor) -> Tensor:
         """positions [...,3] -> density [...,1] (what the reference passes as ``density_fns[i]``)."""
         lead = positions.shape[:-1]
-        return proposal_density(positions.reshape(-1, 3).contiguous(), None, None, None, None, self.table, self.scalings, self.log2_T, self.mlp).reshape(*lead, 1)
+        return proposal_density(positions.reshape(-1, 3).contiguous(), None, None, None, None, self.table, self.scalings, self.log2_T, self.mlp_blob).reshape(*lead, 1)
 
     def density_on_rays(self, origins: Tensor, dirs: Tensor, near: Tensor, far: Tensor, bins: Tensor) -> Tensor:
-        return proposal_density(origins, dirs, near, far, bins, self.table, self.scalings, self.log2_T, self.mlp)
+        return proposal_density(origins, dirs, near, far, bins, self.table, self.scalings, self.log2_T, self.mlp_blob)
 
 
 def _ray_samples(origins, dirs, euclid, spacing, near, far):
@@ -271,7 +302,7 @@ class _InterlevelLoss(torch.autograd.Function):
         grads = []
         for bins, dens, field, g_wp in ctx.levels:
             g_d = density_weights_bwd(bins, dens, near, far, (g_wp * g).contiguous())
-            d_table, d_mlp = proposal_density_bwd(origins, directions, near, far, bins, field.table, field.scalings, field.log2_T, field.mlp, g_d)
+            d_table, d_mlp = proposal_density_bwd(origins, directions, near, far, bins, field.table, field.scalings, field.log2_T, field.mlp_blob, g_d)
             gm = unpack_proposal_mlp_grad(d_mlp, field.num_levels)
             gm["encoding.hash_table"] = d_table
             grads += [gm[k].reshape(p.shape) for k, p in field.params.items()]

@@ -32,16 +32,34 @@ class SkyShader:
         self.scalings = hash_scalings(num_levels).to(self.device)
         self.hash_table = ddf_params["position_encoding.hash_table"].to(self.device, torch.float32).contiguous()
         self.set_ddf_weights(ddf_params)
-        self.reni_blob = packing.pack_reni({k: v.to(self.device) for k, v in reni_params.items()}) if reni_params is not None else None
-        self.reni_gemm = packing.pack_reni_gemm({k: v.to(self.device) for k, v in reni_params.items()}) if reni_params is not None else None
+        self.reni_blob = packing.pack_reni(reni_params, device=self.device) if reni_params is not None else None
+        self.reni_gemm = packing.pack_reni_gemm(reni_params, device=self.device) if reni_params is not None else None
         self.reni_tc_min_rows = 8192    # below this the fp32 SIMT decode wins (one launch instead of ~30)
+        # visibility sigmoid: bias and scale.  Defaults = the values the method config trains towards / fixes (target_min_bias 0.1,
+        # target_max_scale 25: neusky_config.py:122-123); a model passes its learnable `visibility_threshold` (initialised to
+        # 2 * ddf_radius, neusky_model.py:234) explicitly or sets these attributes from the checkpoint
+        self.threshold = 0.1
+        self.sigmoid_scale = 25.0
         self.k4_events = None   # bench hook: when a list, (start, end) CUDA events are recorded around every K4 launch
 
     def set_ddf_weights(self, ddf_params: Dict[str, Tensor]) -> None:
-        p = {k: v.to(self.device) for k, v in ddf_params.items() if k.startswith("ddf.")}
-        self.ddf_blob_simt = packing.pack_ddf_simt(p)
-        self.ddf_blob_tc = packing.pack_ddf_tc(p)
-        self.ddf_blob_tc2 = packing.pack_ddf_tc2(p)
+        """Packed on the host, one upload per kernel variant, lazily: only the blob of the variant that is actually launched exists."""
+        self._ddf_p = {k: v.detach() for k, v in ddf_params.items() if k.startswith("ddf.")}
+        self._ddf_blobs: Dict[str, Tensor] = {}
+
+    _DDF_PACKERS = {"simt": "pack_ddf_simt", "tc": "pack_ddf_tc", "tc2": "pack_ddf_tc2"}
+
+    def ddf_blob(self, impl: str) -> Tensor:
+        b = self._ddf_blobs.get(impl)
+        if b is None:
+            if impl not in self._DDF_PACKERS:
+                raise ValueError(f"impl must be one of {sorted(self._DDF_PACKERS)}, got {impl!r}")
+            b = self._ddf_blobs[impl] = getattr(packing, self._DDF_PACKERS[impl])(self._ddf_p, device=self.device)
+        return b
+
+    ddf_blob_simt = property(lambda self: self.ddf_blob("simt"))
+    ddf_blob_tc = property(lambda self: self.ddf_blob("tc"))
+    ddf_blob_tc2 = property(lambda self: self.ddf_blob("tc2"))
 
     # -- direction set -------------------------------------------------------------------------
     def set_directions(self, dirs: Tensor) -> None:
@@ -68,14 +86,16 @@ class SkyShader:
 
     # -- shading ---------------------------------------------------------------------------------
     def shade(self, points: Tensor, normals: Tensor, wa: Tensor, radiance: Tensor, cam: Optional[Tensor] = None,
-              want_vis: bool = False, want_ddf: bool = False, threshold: float = 0.1, sigmoid_scale: float = 25.0,
+              want_vis: bool = False, want_ddf: bool = False, threshold: Optional[float] = None, sigmoid_scale: Optional[float] = None,
               impl: Optional[str] = None) -> Dict[str, Tensor]:
         """points [R,3]; normals, wa [R,S,3]; radiance [K,D,3] -> linear radiance sum [R,3]
         (sum_s w_s * albedo_s * sum_j c_sj vis_rj L_j) and, on request, the per-pair tensors."""
         impl = impl or self.impl
+        threshold = self.threshold if threshold is None else float(threshold)
+        sigmoid_scale = self.sigmoid_scale if sigmoid_scale is None else float(sigmoid_scale)
         inv_count, rgb_lin = ops.lambert_prep(normals, wa, self.dirs, self.mask_u8, radiance, cam, self.lower_vis)
         rad_sel = radiance[:, self.mask].contiguous()
-        blob = {"tc": self.ddf_blob_tc, "tc2": self.ddf_blob_tc2, "simt": self.ddf_blob_simt}[impl]
+        blob = self.ddf_blob(impl)
         if self.k4_events is not None:
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             ev[0].record()
@@ -96,7 +116,7 @@ class SkyShader:
 
     # -- config-2 entry points (BASELINE.json: surface points x RENI++ directions) ------------------
     def shade_points(self, points: Tensor, normals: Tensor, albedo: Tensor, latents: Tensor, scale: Optional[Tensor] = None,
-                     rotation: Optional[Tensor] = None, threshold: float = 0.1, sigmoid_scale: float = 25.0) -> Tensor:
+                     rotation: Optional[Tensor] = None, threshold: Optional[float] = None, sigmoid_scale: Optional[float] = None) -> Tensor:
         """Device-resident inputs: points/normals/albedo [N,3] (one sample per point, weight 1), latents [1,L,3]
         -> sRGB [N,3].  RENI++ decode -> Lambert pre-pass -> fused DDF visibility + cosine sum -> sRGB."""
         N = points.shape[0]
@@ -189,32 +209,43 @@ class RayRenderer:
         self.set_sdf_weights(sdf_params)
 
     def set_sdf_weights(self, sdf_params: Dict[str, Tensor]) -> None:
-        p = {k: v.to(self.device) for k, v in sdf_params.items() if k.startswith(("glin", "clin"))}
-        self.sdf_blob = packing.pack_sdf_tc(p) if self.sdf_impl == "tc" else packing.pack_sdf_simt(p)
+        p = {k: v for k, v in sdf_params.items() if k.startswith(("glin", "clin"))}
+        self.sdf_blob = packing.pack_sdf_tc(p, device=self.device) if self.sdf_impl == "tc" else packing.pack_sdf_simt(p, device=self.device)
         var = sdf_params["deviation_network.variance"]
         self.inv_s = float(torch.exp(10.0 * var.detach().float().cpu()).clip(1e-6, 1e6))   # LearnedVariance.get_variance [SURVEY A.4]
 
     def set_directions(self, dirs: Tensor) -> None:
         self.shader.set_directions(dirs)
 
+    def radiance_rows_cam(self, ray_directions: Tensor, cam: Tensor, latents: Tensor, scale: Optional[Tensor], rotation: Optional[Tensor] = None) -> Tensor:
+        """Per-ray background radiance of a MIXED-camera batch: ray n is decoded with latent code cam[n] (neusky_model.py:535-549)."""
+        sh = self.shader
+        if ray_directions.shape[0] >= sh.reni_tc_min_rows:
+            return ops.reni_rows_tc(ray_directions, latents, scale, sh.reni_blob, sh.reni_gemm, rotation, row_cam=cam)
+        return ops.reni_radiance_rows(ray_directions, cam, latents, scale, sh.reni_blob, rotation)
+
     @torch.no_grad()
     def render(self, origins: Tensor, directions: Tensor, dnorm: Tensor, S: int, latent: Tensor, scale: Tensor, rotation: Optional[Tensor] = None,
-               threshold: float = 0.1, sigmoid_scale: float = 25.0, cos_anneal_ratio: float = 1.0, want_vis: bool = False,
+               threshold: Optional[float] = None, sigmoid_scale: Optional[float] = None, cos_anneal_ratio: float = 1.0, want_vis: bool = False,
                steps_minmax: Optional[Tensor] = None, want_cache: bool = False, collapse_cache: bool = False,
-               radiance: Optional[Tensor] = None, background: Optional[Tensor] = None) -> Dict[str, Tensor]:
-        """origins/directions [R,3], dnorm [R,1]; latent [L,3]; scale scalar tensor.  All rays belong to one camera.
-        `radiance` [1,D,3] / `background` [R,3]: this latent's RENI++ decodes when the caller already has them (a tiled frame
-        decodes once per frame, `illumination_for`, instead of once per tile)."""
+               radiance: Optional[Tensor] = None, background: Optional[Tensor] = None, cam: Optional[Tensor] = None,
+               want_visibility_batch: bool = False, want_prop_depth: bool = False) -> Dict[str, Tensor]:
+        """origins/directions [R,3], dnorm [R,1].  One camera: latent [L,3], scale scalar tensor.  Mixed-camera batch (what
+        torch.unique(camera_indices) handles in the reference, neusky_model.py:461): latent [K,L,3], scale [K] and `cam` [R]
+        int32 = the latent row of every ray.
+        `radiance` [K,D,3] / `background` [R,3]: RENI++ decodes the caller already has (a tiled frame decodes once per frame,
+        `illumination_for`, instead of once per tile).  Returns the reference's output keys (neusky_model.py:881-931)."""
         R = origins.shape[0]
         sh = self.shader
         near, far = sphere_collider(origins, directions)
+        rs = weights_list = samples_list = None
         if self.proposal_fields is not None:
             from . import proposal as _proposal
 
             smp = self._proposal_samplers.get(S)
             if smp is None:
                 smp = self._proposal_samplers[S] = _proposal.ProposalNetworkSampler(S, self._proposal_counts, len(self.proposal_fields))
-            rs, _, _ = smp.generate_ray_samples(origins, directions, near, far, self.proposal_fields)
+            rs, weights_list, samples_list = smp.generate_ray_samples(origins, directions, near, far, self.proposal_fields)
             e = rs.euclidean_bins
             starts, ends = e[:, :-1].contiguous(), e[:, 1:].contiguous()
         else:
@@ -223,22 +254,42 @@ class RayRenderer:
         f = ops.sdf_field(x, self.sdf_blob, self.sdf_table, self.scalings, self.log2_T, impl=self.sdf_impl)
         c = ops.neus_composite(f["sdf"], f["gradient"], f["albedo"], directions, starts, ends, ends - starts, dnorm, self.inv_s, cos_anneal_ratio, False,
                                steps_minmax=steps_minmax)
+        if cam is not None:
+            cam = cam.reshape(-1).to(torch.int32).contiguous()
         if radiance is None or background is None:
-            Z = latent.reshape(1, -1, 3).to(self.device, torch.float32)
-            sc = scale.reshape(1).to(self.device, torch.float32)
+            Z = latent.reshape(-1, latent.shape[-2], 3).to(self.device, torch.float32)
+            sc = scale.reshape(-1).to(self.device, torch.float32)
+            if Z.shape[0] != 1 and cam is None:
+                raise ValueError("render: several latent codes need `cam` (the latent row of every ray)")
             if radiance is None:
-                radiance = sh.radiance_table(Z, sc, rotation)                            # [1,D,3]
-            if background is None:
-                background = sh.radiance_rows(directions, Z, sc, rotation)               # per-ray background (neusky_model.py:535-549)
+                radiance = sh.radiance_table(Z, sc, rotation)                            # [K,D,3]
+            if background is None:                                                       # per-ray background (neusky_model.py:535-549)
+                background = sh.radiance_rows(directions, Z, sc, rotation) if cam is None else self.radiance_rows_cam(directions, cam, Z, sc, rotation)
         bg = background
         pts = ops.surface_points(origins, directions, c["p2p_dist"], sh.radius)
-        s = sh.shade(pts, c["normals"], c["wa"], radiance, want_vis=want_vis or want_cache, threshold=threshold, sigmoid_scale=sigmoid_scale)
+        s = sh.shade(pts, c["normals"], c["wa"], radiance, cam=cam, want_vis=want_vis or want_cache, want_ddf=want_visibility_batch,
+                     threshold=threshold, sigmoid_scale=sigmoid_scale)
         rgb = ops.shade_finalize(s["rgb_lin"], bg, c["accumulation"])
         out = {"rgb": rgb, "albedo": c["albedo"], "accumulation": c["accumulation"][:, None], "depth": c["depth"][:, None], "p2p_dist": c["p2p_dist"][:, None],
                "normal": c["normal"], "weights": c["weights"][..., None], "hdr_background_colours": bg, "directions_norm": dnorm,
+               "sdf_at_termination": None,                                              # training-only branch (ddf_model.py:241-251)
+               "normal_vis": (c["normal"] + 1.0) / 2.0,                                 # viewer output (neusky_model.py:919)
                "starts": starts, "ends": ends}
         if want_vis:
             out["visibility"] = s["visibility"]
+        if want_visibility_batch:
+            # neusky_model.py:1766-1776: the DDF loss batch of this render (mask = ones, no sdf_at_termination outside training)
+            out["expected_termination_dist"] = s["expected_termination_dist"]
+            out["visibility_batch"] = {"termination_dist": s["termination_dist"], "mask": torch.ones_like(s["termination_dist"]), "sdf_at_termination": None}
+        if want_prop_depth and samples_list is not None:
+            # neusky_model.py:910-917: expected depth of every proposal level (DepthRenderer "expected" on that level's own weights / bins)
+            nf, ff = near.reshape(-1, 1), far.reshape(-1, 1)
+            for i, (w, smp_i) in enumerate(zip(weights_list, samples_list)):
+                e = smp_i.spacing_bins * ff + (1.0 - smp_i.spacing_bins) * nf
+                steps = (e[:, :-1] + e[:, 1:]) * 0.5
+                w2 = w.reshape(R, -1)
+                d_i = (w2 * steps).sum(-1) / (w2.sum(-1) + 1e-10)
+                out[f"prop_depth_{i}"] = torch.clip(d_i, steps.min(), steps.max())[:, None]
         if want_cache:
             # everything a new illumination needs (fixed geometry): per-sample shading inputs, per-ray visibility of the
             # DDF directions, accumulation.  The geometry-only outputs above stay valid for every latent code.
@@ -252,6 +303,36 @@ class RayRenderer:
                 out["relight_cache"] = {"normals": c["normals"], "wa": c["wa"], "inv_count": s["inv_count"], "visibility_sel": s["visibility_sel"],
                                         "accumulation": c["accumulation"], "directions": directions}
         return out
+
+    @torch.no_grad()
+    def shadow_map(self, origins: Tensor, directions: Tensor, p2p_dist: Tensor, accumulation: Tensor, azimuth_deg: float, elevation_deg: float,
+                   threshold: float, sigmoid_scale: float, accumulation_mask_threshold: float = 0.0) -> Dict[str, Tensor]:
+        """Viewer shadow map (neusky_model.py:632-672): visibility of ONE light direction (azimuth / elevation, z up) from the
+        rendered surface points, and the raw `difference` = min(|p - q|, 2r) - DDF (:1724-1727, returned when
+        compute_shadow_map=True, :1764-1765); both masked by accumulation > threshold."""
+        import math
+
+        az, el = math.radians(azimuth_deg), math.radians(elevation_deg)
+        d = torch.tensor([[math.cos(az) * math.cos(el), math.sin(az) * math.cos(el), math.sin(el)]], device=self.device, dtype=torch.float32)
+        sh = self.shader
+        saved = (sh.dirs, sh.mask, sh.mask_u8, sh.dirs_sel, sh.sel_index) if hasattr(sh, "dirs") else None
+        try:
+            sh.set_directions(d)
+            R = origins.shape[0]
+            pts = ops.surface_points(origins, directions, p2p_dist.reshape(R), sh.radius)
+            zero = torch.zeros((R, 1, 3), device=self.device)
+            o = sh.shade(pts, zero, zero, torch.zeros((1, 1, 3), device=self.device), want_vis=True, want_ddf=True, threshold=threshold, sigmoid_scale=sigmoid_scale)
+        finally:
+            if saved is not None:
+                sh.dirs, sh.mask, sh.mask_u8, sh.dirs_sel, sh.sel_index = saved
+        m = (accumulation.reshape(R, 1) > accumulation_mask_threshold).to(torch.float32)
+        vis = o["visibility"].reshape(R, 1, 1) * m[:, :, None]
+        if "expected_termination_dist" in o:
+            diff = torch.clamp(o["termination_dist"], max=2.0 * sh.radius) - o["expected_termination_dist"]
+            diff = diff.reshape(R, -1) * m
+        else:                                   # the direction points into the lower hemisphere: no DDF query, fully lit (:1742-1753)
+            diff = torch.zeros((R, 0), device=self.device)
+        return {"visibility": vis, "difference": diff}
 
     @torch.no_grad()
     def relight(self, cache: Dict[str, Tensor], latent: Tensor, scale: Tensor, rotation: Optional[Tensor] = None,

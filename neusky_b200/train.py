@@ -439,9 +439,14 @@ class NeuSkyTrainStep(torch.nn.Module):
                  log2_T: int = 19, num_levels: int = 16, num_samples: int = 48, ddf_radius: float = 1.0, sigmoid_scale: float = 25.0,
                  split_geo: int = 3, split: int = 3, threshold_init: Optional[float] = None, only_upper_hemisphere: bool = True,
                  lower_hemisphere_visibility: float = 1.0, proposal_params: Optional[Sequence[Dict[str, Tensor]]] = None,
-                 proposal_max_res: Sequence[int] = (64, 256), num_proposal_samples_per_ray: Sequence[int] = (256, 96), proposal_log2_T: int = 17):
+                 proposal_max_res: Sequence[int] = (64, 256), num_proposal_samples_per_ray: Sequence[int] = (256, 96), proposal_log2_T: int = 17,
+                 share_params: bool = False, latents: Optional[torch.nn.Parameter] = None, scale: Optional[torch.nn.Parameter] = None,
+                 visibility_threshold: Optional[torch.nn.Parameter] = None, proposal_fields: Optional[Sequence] = None):
         """``proposal_params``: state of the two HashMLPDensityFields -> the shipped NeuS-facto sample placement (proposal-network
-        sampler, neusky_model.py:561) and its interlevel loss (:987-988, coefficient 1.0); None -> uniform placement."""
+        sampler, neusky_model.py:561) and its interlevel loss (:987-988, coefficient 1.0); None -> uniform placement.
+        ``share_params``: register the ``nn.Parameter`` objects passed in ``sdf_params`` / ``ddf_params`` themselves instead of
+        copies (the drop-in model, neusky_b200/models.py, owns the parameters under the reference's module names and runs its
+        training forward through this class); ``latents`` / ``scale`` / ``visibility_threshold`` / ``proposal_fields`` likewise."""
         super().__init__()
         from . import packing
         from .init import hash_scalings
@@ -454,23 +459,28 @@ class NeuSkyTrainStep(torch.nn.Module):
         for grp, params in (("sdf", sdf_params), ("ddf", ddf_params)):
             for k, v in params.items():
                 reg = f"{grp}__{k.replace('.', '__')}"
-                self.register_parameter(reg, torch.nn.Parameter(v.detach().to(self.dev, torch.float32).clone().contiguous()))
+                if share_params:
+                    if not isinstance(v, torch.nn.Parameter) or v.device != self.dev or v.dtype != torch.float32:
+                        raise ValueError(f"share_params: {grp}.{k} must be an fp32 nn.Parameter on {self.dev}")
+                    self.register_parameter(reg, v)
+                else:
+                    self.register_parameter(reg, torch.nn.Parameter(v.detach().to(self.dev, torch.float32).clone().contiguous()))
                 self._names[grp][k] = reg
-        self.latents = torch.nn.Parameter(torch.zeros(num_cameras, 100, 3, device=self.dev))      # neusky_model.py:261-269 (zero init)
-        self.scale = torch.nn.Parameter(torch.zeros(num_cameras, device=self.dev))
+        self.latents = latents if latents is not None else torch.nn.Parameter(torch.zeros(num_cameras, 100, 3, device=self.dev))      # neusky_model.py:261-269 (zero init)
+        self.scale = scale if scale is not None else torch.nn.Parameter(torch.zeros(num_cameras, device=self.dev))
         thr0 = 2.0 * self.radius if threshold_init is None else threshold_init                    # :234
-        self.visibility_threshold = torch.nn.Parameter(torch.tensor(float(thr0), device=self.dev))
-        self.reni_blob = packing.pack_reni({k: v.to(self.dev) for k, v in reni_params.items()})
-        self.reni_blob_bwd = packing.pack_reni_bwd({k: v.to(self.dev) for k, v in reni_params.items()})
+        self.visibility_threshold = visibility_threshold if visibility_threshold is not None else torch.nn.Parameter(torch.tensor(float(thr0), device=self.dev))
+        self.reni_blob = packing.pack_reni(reni_params, device=self.dev)
+        self.reni_blob_bwd = packing.pack_reni_bwd(reni_params, device=self.dev)
         self.sdf_cfg = SDFConfig(scalings=self.scalings, log2_T=log2_T, split_geo=split_geo, split_colour=split)
         self.ddf_cfg = DDFConfig(scalings=self.scalings, log2_T=log2_T, radius=self.radius, sigmoid_scale=sigmoid_scale, split=split)
         self.cos_anneal_ratio = 1.0
         self.grid_resolution = 10                                                                  # neusky_config.py:127
         self.proposal_fields, self.proposal_sampler, self.proposal_anneal = None, None, 1.0
-        if proposal_params is not None:
+        if proposal_params is not None or proposal_fields is not None:
             from . import proposal as _proposal
-            self.proposal_fields = [_proposal.HashMLPDensityField(pp, max_res=mr, log2_hashmap_size=proposal_log2_T, device=self.dev)
-                                    for pp, mr in zip(proposal_params, proposal_max_res)]
+            self.proposal_fields = list(proposal_fields) if proposal_fields is not None else [
+                _proposal.HashMLPDensityField(pp, max_res=mr, log2_hashmap_size=proposal_log2_T, device=self.dev) for pp, mr in zip(proposal_params, proposal_max_res)]
             for i, f in enumerate(self.proposal_fields):          # the fields' own Parameter objects, registered here for optimizers / reducers
                 for k, v in f.params.items():
                     self.register_parameter(f"prop{i}__{k.replace('.', '__')}", v)

@@ -586,10 +586,12 @@ def uniform_samples(near: Tensor, far: Tensor, S: int) -> Tuple[Tensor, Tensor]:
 
 
 def render_rays(origins, directions, dnorm, S, sdf_p, ddf_p, reni_p, latent, scale, dirs, inv_s, log2_T=19,
-                ddf_radius=1.0, threshold=0.1, sigmoid_scale=25.0, rotation=None, chunk=256, proposal_nets=None, proposal_log2_T=17):
+                ddf_radius=1.0, threshold=0.1, sigmoid_scale=25.0, rotation=None, chunk=256, proposal_nets=None, proposal_log2_T=17,
+                clip_per_chunk=False):
     """Eval render of R rays of ONE camera.  Sample placement: uniform, or -- with ``proposal_nets`` = the state of the two
     HashMLPDensityFields -- the proposal-network sampler (neusky_model.py:561; oracle/sampler_oracle.py).  Returns the outputs
-    dict of neusky_model.py:881-931 (rgb, albedo, accumulation, depth, p2p_dist, normal) plus visibility [R,D]."""
+    dict of neusky_model.py:881-931 (rgb, albedo, accumulation, depth, p2p_dist, normal) plus visibility [R,D].
+    ``clip_per_chunk``: clip the expected depth to each chunk's own sample range, as the reference's chunked eval loop does."""
     sca = hash_scalings()
     radiance = reni_radiance_table(dirs, latent[None], scale.reshape(1), reni_p, rotation)[0]  # [D,3] (:488-518)
     out = {k: [] for k in ("rgb", "albedo", "accumulation", "depth", "p2p_dist", "normal", "visibility", "weights")}
@@ -614,7 +616,12 @@ def render_rays(origins, directions, dnorm, S, sdf_p, ddf_p, reni_p, latent, sca
         sdf, grad, alb = f["sdf"].reshape(r, S, 1), f["gradient"].reshape(r, S, 3), f["albedo"].reshape(r, S, 3)
         bg = reni_radiance_table(d, latent[None], scale.reshape(1), reni_p, rotation)[0]  # :535-549
         c = neus_composite(sdf, grad, alb, torch.zeros(r, S, 3), d, starts, ends, ends - starts, bg, dn, inv_s, 1.0, False)
-        p2p = torch.clip(c["p2p_raw"], smin, smax)   # DepthRenderer clips to the batch-global range [A.7]; here: the whole bundle
+        if clip_per_chunk:
+            # the reference's eval loop calls forward() once per `chunk` rays (neusky_model.py:1413-1437, eval_num_rays_per_chunk = 256), so its
+            # DepthRenderer clips to the sample range of THAT chunk; the default here (and a one-pass render of the bundle) clips to the bundle's
+            cm = (starts + ends) / 2
+            smin, smax = cm.min(), cm.max()
+        p2p = torch.clip(c["p2p_raw"], smin, smax)   # DepthRenderer clips to the batch-global range [A.7]
         pts = surface_points(o, d, p2p, ddf_radius)
         v = compute_visibility(pts, dirs, ddf_p, sca, log2_T, ddf_radius, threshold, sigmoid_scale)
         normals = torch.nn.functional.normalize(grad, dim=-1)

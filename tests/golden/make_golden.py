@@ -334,9 +334,40 @@ def golden_losses():
     save("losses", hdr=hdr, image=image, sky=sky, sky_pixel_loss=loss, sky_pixel_loss_d_hdr=grad)
 
 
+# ------------------------------------------------------------------------------ state_dict layout of the reference's modules (drop-in boundary)
+def golden_state_dicts():
+    """Names, shapes and requires_grad flags of the reference's own modules (the drop-in modules of neusky_b200/fields.py must
+    register exactly these; tests/test_dropin_state_dict.py).  The hash encodings are tcnn.Encoding in the reference (key
+    `params`); under the shim they are the torch hash grid (key `hash_table`) -- recorded as the shim builds them.
+    SDFAlbedoField cannot be built here (its parent class nerfstudio.fields.sdf_field.SDFField is absent)."""
+    import json
+    from reni.illumination_fields.reni_illumination_field import RENIField, RENIFieldConfig
+
+    def layout(m):
+        req = {n: bool(p.requires_grad) for n, p in m.named_parameters()}
+        return {k: {"shape": list(v.shape), "requires_grad": req.get(k)} for k, v in m.state_dict().items()}
+
+    field, _ = build_reference_ddf()
+    cfg = RENIFieldConfig(
+        conditioning="Attention", invariant_function="VN", equivariance="SO2", axis_of_invariance="z",
+        positional_encoding="NeRF", encoded_input="Directions", latent_dim=100, hidden_features=128, hidden_layers=9,
+        mapping_layers=5, mapping_features=128, num_attention_heads=8, num_attention_layers=6,
+        output_activation="None", last_layer_linear=True, fixed_decoder=True, trainable_scale=True,
+    )
+    out = {
+        "DirectionalDistanceField": layout(field),
+        "RENIField": layout(RENIField(cfg, num_train_data=None, num_eval_data=None)),
+        "RENIField_7_3": layout(RENIField(cfg, num_train_data=7, num_eval_data=3, normalisations={"min_max": None, "log_domain": True})),
+    }
+    path = os.path.join(HERE, "state_dict_keys.json")
+    with open(path, "w") as f:
+        json.dump(out, f, indent=1, sort_keys=True)
+    print(f"wrote {path}: " + ", ".join(f"{k} ({len(v)} entries)" for k, v in out.items()))
+
+
 if __name__ == "__main__":
     only = sys.argv[1:]
     torch.manual_seed(0)
-    for fn in (golden_icosphere, golden_lambert, golden_reni, golden_ddf_and_visibility, golden_ddf_fit, golden_shaders, golden_losses):
+    for fn in (golden_icosphere, golden_lambert, golden_reni, golden_ddf_and_visibility, golden_ddf_fit, golden_shaders, golden_losses, golden_state_dicts):
         if not only or fn.__name__ in only:
             fn()

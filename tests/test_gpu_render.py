@@ -48,7 +48,7 @@ def _render(dev, sc, impl, sdf_impl="simt"):
     o, d, dn = (t.to(dev) for t in (sc["o"], sc["d"], sc["dn"]))   # the ray bundle is an INPUT of the path (neusky_model.py:425)
     out = r.render(o, d, dn, sc["S"], sc["Z"].to(dev), torch.zeros((), device=dev), want_vis=True)
     torch.cuda.synchronize()
-    return o, d, dn, {k: v.cpu() for k, v in out.items()}
+    return o, d, dn, {k: v.cpu() for k, v in out.items() if torch.is_tensor(v)}
 
 
 def test_sample_placement_bit_exact(dev, scene):
@@ -173,7 +173,7 @@ def test_render_with_proposal_sampler_vs_oracle(dev, scene):
     r = RayRenderer(scene["sdf_p"], scene["ddf_p"], scene["reni_p"], device=dev, log2_T=scene["log2_T"], impl="simt", sdf_impl="simt", proposal_params=nets)
     r.set_directions(scene["dirs"])
     o, d, dn = (t.to(dev) for t in (scene["o"], scene["d"], scene["dn"]))
-    out = {k: v.cpu() for k, v in r.render(o, d, dn, S, scene["Z"].to(dev), torch.zeros((), device=dev), want_vis=True).items()}
+    out = {k: v.cpu() for k, v in r.render(o, d, dn, S, scene["Z"].to(dev), torch.zeros((), device=dev), want_vis=True).items() if torch.is_tensor(v)}
     near, far = O.sphere_collider(scene["o"], scene["d"])
     e_ref, *_ = SO.proposal_sample(scene["o"], scene["d"], near, far, nets, num_final=S)
     assert float((out["starts"] - torch.from_numpy(e_ref[:, :-1])).abs().max()) <= 5e-5
@@ -207,7 +207,7 @@ def test_baseline_config1_full_size_vs_oracle(dev):
     for impl, sdf_impl in (("simt", "simt"), ("tc2", "tc")):
         r = RayRenderer(sdf_p, ddf_p, reni_p, device=dev, log2_T=log2_T, impl=impl, sdf_impl=sdf_impl)
         r.set_directions(dirs)
-        out = {k: v.cpu() for k, v in r.render(od, dd, dnd, S, Z.to(dev), torch.zeros((), device=dev), want_vis=True).items()}
+        out = {k: v.cpu() for k, v in r.render(od, dd, dnd, S, Z.to(dev), torch.zeros((), device=dev), want_vis=True).items() if torch.is_tensor(v)}
         if impl == "simt":
             rel = {k: float((out[k] - ref[k]).abs().max() / ref[k].abs().max().clamp_min(1e-6)) for k in ("accumulation", "p2p_dist", "depth", "normal", "albedo", "visibility", "rgb")}
             print("config 1, fp32 path, max relative errors:", rel)
