@@ -332,7 +332,7 @@ class NeuSkyFactoModel(nn.Module):
                             ddf_radius=self.visibility_field.ddf_radius, impl=c.k4_impl, sdf_impl=c.sdf_field.impl,
                             proposal_params=[{n: p.detach() for n, p in net.named_parameters()} for net in self.proposal_networks],
                             proposal_max_res=[net.max_res for net in self.proposal_networks], num_proposal_samples_per_ray=c.num_proposal_samples_per_ray,
-                            proposal_log2_T=self.proposal_networks[0].log2_T)
+                            proposal_log2_T=self.proposal_networks[0].log2_T, ddf_log2_T=self.visibility_field.field.position_encoding.log2_T)
             r.shader.only_upper = c.only_upperhemisphere_visibility
             r.shader.lower_vis = 1.0 if c.lower_hermisphere_visibility else 0.0
             self._renderer, self._renderer_key = r, key
@@ -396,7 +396,7 @@ class NeuSkyFactoModel(nn.Module):
                 sigmoid_scale=float(self.sigmoid_scale), only_upper_hemisphere=c.only_upperhemisphere_visibility,
                 lower_hemisphere_visibility=1.0 if c.lower_hermisphere_visibility else 0.0, num_proposal_samples_per_ray=c.num_proposal_samples_per_ray,
                 share_params=True, latents=self.train_illumination_latents, scale=self.train_scale, visibility_threshold=self.visibility_threshold,
-                proposal_fields=list(self.proposal_networks))
+                proposal_fields=list(self.proposal_networks), ddf_log2_T=self.visibility_field.field.position_encoding.log2_T)
             object.__setattr__(self, "_train_step", ts)      # NOT a registered sub-module: its parameters are ours already (state_dict stays the reference's)
         ts = self._train_step
         ts.cos_anneal_ratio = self._cos_anneal_ratio

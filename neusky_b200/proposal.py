@@ -199,6 +199,12 @@ class HashMLPDensityField(torch.nn.Module):
             self._mlp_key = key
         self.table = ps["encoding.hash_table"].detach()
 
+    def backward_on_rays(self, origins, dirs, near, far, bins, g_density: Tensor) -> None:
+        """Manual backward of ``density_on_rays``: accumulate d loss / d params into ``.grad`` (stand-alone use; the training step goes
+        through autograd, ``ProposalNetworkSampler.interlevel_loss``)."""
+        self.refresh()
+        _accumulate_field_grads(self, origins, dirs, near, far, bins, g_density)
+
     def density_fn(self, positions: Tensor) -> Tensor:
         """positions [...,3] -> density [...,1] (what the reference passes as ``density_fns[i]``)."""
         lead = positions.shape[:-1]
@@ -206,6 +212,18 @@ class HashMLPDensityField(torch.nn.Module):
 
     def density_on_rays(self, origins: Tensor, dirs: Tensor, near: Tensor, far: Tensor, bins: Tensor) -> Tensor:
         return proposal_density(origins, dirs, near, far, bins, self.table, self.scalings, self.log2_T, self.mlp_blob)
+
+
+def _accumulate_field_grads(field: "HashMLPDensityField", origins, dirs, near, far, bins, g_density: Tensor) -> None:
+    d_table, d_mlp = proposal_density_bwd(origins, dirs, near, far, bins, field.table, field.scalings, field.log2_T, field.mlp_blob, g_density)
+    grads = unpack_proposal_mlp_grad(d_mlp, field.num_levels)
+    grads["encoding.hash_table"] = d_table
+    for k, p in field.params.items():
+        g = grads[k].reshape(p.shape)
+        if p.grad is None:
+            p.grad = g
+        else:
+            p.grad.add_(g)          # in place: .grad may be a view into a GradBucketReducer communication bucket
 
 
 def _ray_samples(origins, dirs, euclid, spacing, near, far):

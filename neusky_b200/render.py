@@ -190,7 +190,7 @@ class RayRenderer:
     def __init__(self, sdf_params: Dict[str, Tensor], ddf_params: Dict[str, Tensor], reni_params: Dict[str, Tensor], device="cuda",
                  log2_T: int = 19, num_levels: int = 16, ddf_radius: float = 1.0, impl: str = "tc2", sdf_impl: str = "tc",
                  proposal_params: Optional[Sequence[Dict[str, Tensor]]] = None, proposal_max_res: Sequence[int] = (64, 256),
-                 num_proposal_samples_per_ray: Sequence[int] = (256, 96), proposal_log2_T: int = 17):
+                 num_proposal_samples_per_ray: Sequence[int] = (256, 96), proposal_log2_T: int = 17, ddf_log2_T: Optional[int] = None):
         """``proposal_params``: state of the two HashMLPDensityFields -> sample placement by the proposal-network sampler
         (the shipped NeuS-facto configuration, neusky_model.py:561); None -> uniform placement."""
         self.device = torch.device(device)
@@ -203,7 +203,9 @@ class RayRenderer:
             self._proposal_samplers = {}
         self.log2_T = log2_T
         self.sdf_impl = sdf_impl
-        self.shader = SkyShader(ddf_params, reni_params, device=device, ddf_radius=ddf_radius, log2_T=log2_T, num_levels=num_levels, impl=impl)
+        # the DDF's position encoding is always 16 x 2^19 in the reference (directional_distance_field.py:139-145); `ddf_log2_T` lets reduced tests shrink it
+        self.shader = SkyShader(ddf_params, reni_params, device=device, ddf_radius=ddf_radius, log2_T=log2_T if ddf_log2_T is None else ddf_log2_T,
+                                num_levels=num_levels, impl=impl)
         self.scalings = self.shader.scalings
         self.sdf_table = sdf_params["encoding.hash_table"].to(self.device, torch.float32).contiguous()
         self.set_sdf_weights(sdf_params)

@@ -441,7 +441,7 @@ class NeuSkyTrainStep(torch.nn.Module):
                  lower_hemisphere_visibility: float = 1.0, proposal_params: Optional[Sequence[Dict[str, Tensor]]] = None,
                  proposal_max_res: Sequence[int] = (64, 256), num_proposal_samples_per_ray: Sequence[int] = (256, 96), proposal_log2_T: int = 17,
                  share_params: bool = False, latents: Optional[torch.nn.Parameter] = None, scale: Optional[torch.nn.Parameter] = None,
-                 visibility_threshold: Optional[torch.nn.Parameter] = None, proposal_fields: Optional[Sequence] = None):
+                 visibility_threshold: Optional[torch.nn.Parameter] = None, proposal_fields: Optional[Sequence] = None, ddf_log2_T: Optional[int] = None):
         """``proposal_params``: state of the two HashMLPDensityFields -> the shipped NeuS-facto sample placement (proposal-network
         sampler, neusky_model.py:561) and its interlevel loss (:987-988, coefficient 1.0); None -> uniform placement.
         ``share_params``: register the ``nn.Parameter`` objects passed in ``sdf_params`` / ``ddf_params`` themselves instead of
@@ -473,7 +473,7 @@ class NeuSkyTrainStep(torch.nn.Module):
         self.reni_blob = packing.pack_reni(reni_params, device=self.dev)
         self.reni_blob_bwd = packing.pack_reni_bwd(reni_params, device=self.dev)
         self.sdf_cfg = SDFConfig(scalings=self.scalings, log2_T=log2_T, split_geo=split_geo, split_colour=split)
-        self.ddf_cfg = DDFConfig(scalings=self.scalings, log2_T=log2_T, radius=self.radius, sigmoid_scale=sigmoid_scale, split=split)
+        self.ddf_cfg = DDFConfig(scalings=self.scalings, log2_T=log2_T if ddf_log2_T is None else ddf_log2_T, radius=self.radius, sigmoid_scale=sigmoid_scale, split=split)
         self.cos_anneal_ratio = 1.0
         self.grid_resolution = 10                                                                  # neusky_config.py:127
         self.proposal_fields, self.proposal_sampler, self.proposal_anneal = None, None, 1.0

@@ -587,7 +587,7 @@ def uniform_samples(near: Tensor, far: Tensor, S: int) -> Tuple[Tensor, Tensor]:
 
 def render_rays(origins, directions, dnorm, S, sdf_p, ddf_p, reni_p, latent, scale, dirs, inv_s, log2_T=19,
                 ddf_radius=1.0, threshold=0.1, sigmoid_scale=25.0, rotation=None, chunk=256, proposal_nets=None, proposal_log2_T=17,
-                clip_per_chunk=False):
+                clip_per_chunk=False, steps_minmax=None):
     """Eval render of R rays of ONE camera.  Sample placement: uniform, or -- with ``proposal_nets`` = the state of the two
     HashMLPDensityFields -- the proposal-network sampler (neusky_model.py:561; oracle/sampler_oracle.py).  Returns the outputs
     dict of neusky_model.py:881-931 (rgb, albedo, accumulation, depth, p2p_dist, normal) plus visibility [R,D].
@@ -607,6 +607,8 @@ def render_rays(origins, directions, dnorm, S, sdf_p, ddf_p, reni_p, latent, sca
         starts_all, ends_all = uniform_samples(near, far, S)
     mids = (starts_all + ends_all) / 2
     smin, smax = mids.min(), mids.max()
+    if steps_minmax is not None:      # a sample of a larger bundle: clip to the range of the WHOLE bundle the sample was drawn from
+        smin, smax = torch.as_tensor(steps_minmax[0], dtype=mids.dtype), torch.as_tensor(steps_minmax[1], dtype=mids.dtype)
     for s in range(0, R, chunk):
         o, d, dn = origins[s:s + chunk], directions[s:s + chunk], dnorm[s:s + chunk]
         starts, ends = starts_all[s:s + chunk], ends_all[s:s + chunk]

@@ -22,3 +22,17 @@ def golden():
         return np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False)
 
     return load
+
+
+def log_err(name: str, **values) -> None:
+    """Append measured errors of a parity assertion to gpurun_out/test_errors.jsonl (read back after a GPU run to keep the asserted
+    tolerances at ~3x what is measured).  Never raises."""
+    import json
+
+    try:
+        d = os.path.join(ROOT, "gpurun_out")
+        os.makedirs(d, exist_ok=True)
+        with open(os.path.join(d, "test_errors.jsonl"), "a") as f:
+            f.write(json.dumps({"test": name, **{k: float(v) for k, v in values.items()}}) + "\n")
+    except Exception:
+        pass

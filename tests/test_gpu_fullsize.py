@@ -71,7 +71,10 @@ def test_full_size_matches_oracle_on_a_sample(full, dev):
         ref_lin, _ = O.shade_points(full["pts"][idx.to(dev)].cpu(), full["nrm"][idx.to(dev)].cpu(), full["alb"][idx.to(dev)].cpu(), full["dirs"], rad_cpu,
                                     full["ddf"], O.hash_scalings(), 19, 1.0, 0.1, 25.0)
         ref = O.linear_to_srgb(ref_lin)
-    assert float((rgb[idx.to(dev)].cpu() - ref).abs().max()) <= 5e-3
+    from conftest import log_err
+
+    log_err("fullsize_config2_sample", srgb=(rgb[idx.to(dev)].cpu() - ref).abs().max())
+    assert float((rgb[idx.to(dev)].cpu() - ref).abs().max()) <= 1.5e-4      # measured 3.4e-5 (fp16-operand K4, x8 stress gain)
     full["lin_full"] = lin
 
 

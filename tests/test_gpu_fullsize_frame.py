@@ -1,0 +1,116 @@
+"""BASELINE.json configs[2] and configs[4] at FULL size: one 1280x720 frame (921,600 rays, S = 128 uniform samples per ray, the
+642-direction icosphere, 2^19-entry hash tables) rendered through the throughput configuration (K2 + K4 on tcgen05, tiles of 16,384
+rays) and re-lit under other RENI++ latent codes / a rotation from the collapsed relighting cache; the CPU oracle renders a random
+sample of the frame's rays (the oracle needs ~0.1 s per ray at this size, so the whole frame is out of reach) with the frame-global
+depth clip range.  Tolerances: the tensor-core figures of tests/test_gpu_render.py (all inside north_star's 1e-3); the same rays
+through the exact fp32 kernels: 1e-3 relative on every output."""
+import math
+
+import pytest
+import torch
+
+from conftest import log_err
+from neusky_b200 import init as nb_init
+
+pytestmark = pytest.mark.gpu
+H, W, S, N_SAMPLE = 720, 1280, 128, 96
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from neusky_b200 import _lib
+
+    _lib.load()
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def frame(dev):
+    from neusky_b200 import samplers
+    from neusky_b200.render import RayRenderer, global_steps_minmax, pinhole_rays
+    from oracle import neusky_oracle as O
+
+    p = dict(sdf=nb_init.init_sdf_params(2, bias=0.45), ddf=nb_init.init_ddf_params(0, final_gain=8.0), reni=nb_init.init_reni_params(1))
+    p["sdf"]["deviation_network.variance"] = torch.tensor(0.3)
+    r = RayRenderer(p["sdf"], p["ddf"], p["reni"], device=dev)          # impl tc2 / sdf tc: the throughput configuration
+    dirs = samplers.IcosahedronSampler(512)().frustums.directions
+    r.set_directions(dirs)
+    fx = (W / 2) / math.tan(math.radians(30.0))
+    c2w = O.look_at_camera((0.0, -0.9, 0.25))
+    o, d, dn = pinhole_rays(H, W, fx, fx, W / 2, H / 2, c2w, dev)
+    Z = torch.randn(100, 3, generator=torch.Generator().manual_seed(3))
+    sc = torch.zeros((), device=dev)
+    mm = global_steps_minmax(o, d, S)
+    outs, caches = {k: [] for k in ("rgb", "albedo", "normal", "depth", "p2p_dist", "accumulation")}, []
+    rad, bg = r.illumination_for(Z.to(dev), sc, d)
+    tile = 16384
+    for a in range(0, H * W, tile):
+        out = r.render(o[a:a + tile].contiguous(), d[a:a + tile].contiguous(), dn[a:a + tile].contiguous(), S, Z.to(dev), sc, steps_minmax=mm,
+                       radiance=rad, background=bg[a:a + tile], want_cache=True, collapse_cache=True)
+        for k in outs:
+            outs[k].append(out[k])
+        caches.append(out["relight_cache"])
+    torch.cuda.synchronize()
+    outs = {k: torch.cat(v, 0) for k, v in outs.items()}
+    idx = torch.randint(0, H * W, (N_SAMPLE,), generator=torch.Generator().manual_seed(17))
+    idx[: N_SAMPLE // 3] = (torch.arange(N_SAMPLE // 3) * 3 + 355) * W + W // 2 - 40 + torch.arange(N_SAMPLE // 3)   # a column through the object: surface rays for sure
+    return dict(r=r, p=p, dirs=dirs, o=o, d=d, dn=dn, Z=Z, mm=mm, outs=outs, caches=caches, idx=idx, tile=tile, O=O)
+
+
+def _oracle(frame, Z, rotation=None):
+    O, p, idx = frame["O"], frame["p"], frame["idx"]
+    o, d, dn = (frame[k][idx.to(frame[k].device)].cpu() for k in ("o", "d", "dn"))
+    with torch.no_grad():
+        return O.render_rays(o, d, dn, S, p["sdf"], p["ddf"], p["reni"], Z, torch.zeros(()), frame["dirs"], float(torch.exp(torch.tensor(3.0))),
+                             rotation=rotation, chunk=32, steps_minmax=tuple(float(x) for x in frame["mm"].cpu()))
+
+
+def test_config3_full_frame_vs_oracle_sample(frame, dev):
+    ref = _oracle(frame, frame["Z"])
+    frame["ref0"] = ref
+    acc = ref["accumulation"]
+    assert float(acc.max()) > 0.9 and float(acc.min()) < 0.1                      # the sample holds surface AND sky rays
+    idx = frame["idx"].to(dev)
+    errs = {k: float((frame["outs"][k][idx].cpu().reshape(ref[k].shape) - ref[k]).abs().max()) for k in ("rgb", "albedo", "normal", "accumulation", "depth")}
+    log_err("config3_full_frame_tc", **errs)
+    assert errs["rgb"] <= 5e-4 and errs["normal"] <= 7e-4 and errs["albedo"] <= 4e-4 and errs["accumulation"] <= 6e-4, errs
+    assert errs["depth"] <= 3e-4 * float(ref["depth"].abs().max()), errs
+    # the same rays through the exact fp32 kernels (K2 and K4 SIMT): north_star's 1e-3 relative on every output
+    from neusky_b200.render import RayRenderer
+
+    p = frame["p"]
+    r32 = RayRenderer(p["sdf"], p["ddf"], p["reni"], device=dev, impl="simt", sdf_impl="simt")
+    r32.set_directions(frame["dirs"])
+    out = r32.render(frame["o"][idx].contiguous(), frame["d"][idx].contiguous(), frame["dn"][idx].contiguous(), S, frame["Z"].to(dev), torch.zeros((), device=dev),
+                     steps_minmax=frame["mm"])
+    rel = {k: float((out[k].cpu().reshape(ref[k].shape) - ref[k]).abs().max() / ref[k].abs().max().clamp_min(1e-6)) for k in ("rgb", "albedo", "normal", "accumulation", "depth", "p2p_dist")}
+    log_err("config3_sample_fp32", **rel)
+    assert all(v <= 1e-3 for v in rel.values()), rel
+
+
+def test_config5_relight_full_frame_vs_oracle_sample(frame, dev):
+    """configs[4]: fixed geometry, new latent codes -- relit from the collapsed cache (no SDF, no compositing, no DDF) and compared with
+    the ORACLE's full render of the sampled rays under that latent code, one of them with the latent rotated about z
+    (reni_illumination_field.py:517-519)."""
+    r, idx = frame["r"], frame["idx"].to(dev)
+    g = torch.Generator().manual_seed(29)
+    codes = torch.randn(3, 100, 3, generator=g)
+    ang = 0.9
+    rot = torch.tensor([[math.cos(ang), -math.sin(ang), 0.0], [math.sin(ang), math.cos(ang), 0.0], [0.0, 0.0, 1.0]])
+    sc = torch.zeros((), device=dev)
+    tile = frame["tile"]
+    for k, R in ((1, None), (2, rot)):
+        rad, bg = r.illumination_for(codes[k].to(dev), sc, frame["d"], rotation=None if R is None else R.to(dev))
+        rgb = torch.cat([r.relight(c, codes[k].to(dev), sc, radiance=rad, background=bg[i * tile:(i + 1) * tile]) for i, c in enumerate(frame["caches"])], 0)
+        ref = _oracle(frame, codes[k], rotation=R)
+        e = float((rgb[idx].cpu() - ref["rgb"]).abs().max())
+        log_err(f"config5_relight_full[{k}]", rgb=e)
+        assert e <= 5e-4, (k, e)
+        assert float((ref["rgb"] - frame["ref0"]["rgb"]).abs().max()) > 1e-2 if "ref0" in frame else True   # the illumination really changed
+    # four codes per pass over the cache == one by one
+    ill = [r.illumination_for(codes[i % 3].to(dev), sc, frame["d"][:tile].contiguous()) for i in range(4)]
+    many = r.relight_many(frame["caches"][0], torch.cat([a for a, _ in ill], 0), torch.stack([b for _, b in ill], 0))
+    one = r.relight(frame["caches"][0], codes[1].to(dev), sc, radiance=ill[1][0], background=ill[1][1])
+    assert float((many[1] - one).abs().max()) <= 1e-6

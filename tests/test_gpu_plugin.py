@@ -153,6 +153,9 @@ def test_sdf_albedo_field_forward(dev):
     rs.camera_indices = torch.zeros(R, S, 1, dtype=torch.long, device=dev)
     out = f(rs, return_alphas=True)
     assert float((out[FieldHeadNames.SDF].detach().cpu().reshape(-1, 1) - ref["sdf"]).abs().max()) <= 1e-4
+    with torch.no_grad():      # the geometric init zeroes the first layer's hash-feature columns (no table gradient at step 0): perturb them
+        f.glin0.weight_v[:, 39:] += 0.05 * torch.randn(256, 32, generator=g).to(dev)
+    out = f(rs, return_alphas=True)
     (out[FieldHeadNames.ALPHA].sum() + out[NeuSkyFieldHeadNames.ALBEDO].sum()).backward()
     for n in ("glin0.weight_v", "glin0.weight_g", "glin2.bias", "clin2.weight_v", "encoding.hash_table", "deviation_network.variance"):
         gr = f.get_parameter(n).grad
@@ -328,9 +331,10 @@ def test_model_training_forward_backward_on_reference_named_parameters(dev):
     assert set(m.state_dict().keys()) == keys_before
     # no_grad forward in training mode leaves every .grad untouched (the interlevel loss is an autograd node, not a side effect)
     snap = {n: q.grad.clone() for n, q in m.named_parameters() if q.grad is not None}
+    rb_eval = RayBundle(origins=rb.origins, directions=rb.directions, camera_indices=rb.camera_indices % 2, metadata=rb.metadata)   # 2 eval images
     with torch.no_grad():
         m.eval()
-        m(rb)
+        m(rb_eval)
         m.train()
     for n, q in m.named_parameters():
         if n in snap:

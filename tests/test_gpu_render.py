@@ -1,10 +1,13 @@
 """End-to-end eval render (BASELINE.json config 1 shape, reduced): sample placement -> K2 -> K3 -> RENI++ -> K4 -> sRGB
 on the GPU vs the CPU oracle's render_rays on the same seeded weights and camera.
-fp32 path (impl="simt" for K4): rgb / depth / normal / visibility within 1e-3 (north_star).  Tensor-core K4 path:
-stated separately (fp16 operands): rgb within 5e-3 absolute."""
+fp32 path (impl="simt" for K4): rgb / depth / normal / visibility within 1e-3 (north_star).  Tensor-core path (fp16 operands),
+stated separately and kept at ~3x the measured error (conftest.log_err -> profiles/r02_test_errors.jsonl): K4 on tensor cores:
+rgb <= 1e-4 absolute (measured 2.5e-5); K2 and K4 on tensor cores: rgb <= 5e-4, normal <= 7e-4, albedo <= 4e-4, accumulation <= 6e-4
+absolute, depth <= 3e-4 relative -- i.e. every rendered output of the throughput configuration is inside north_star's 1e-3."""
 import pytest
 import torch
 
+from conftest import log_err
 from neusky_b200 import init as nb_init
 
 pytestmark = pytest.mark.gpu
@@ -82,22 +85,23 @@ def test_render_fp32_path_vs_oracle(dev, scene):
 def test_render_tensor_core_path_vs_oracle(dev, scene, impl):
     _, _, _, out = _render(dev, scene, impl)
     ref = scene["ref"]
-    assert float((out["rgb"] - ref["rgb"]).abs().max()) <= 5e-3
-    assert float((out["visibility"] - ref["visibility"]).abs().max()) <= 2e-2
+    log_err(f"render_tc_path[{impl}]", rgb=(out["rgb"] - ref["rgb"]).abs().max(), vis=(out["visibility"] - ref["visibility"]).abs().max())
+    assert float((out["rgb"] - ref["rgb"]).abs().max()) <= (1e-4 if impl == "tc2" else 2e-4)                  # measured 2.5e-5 / 3.8e-5
+    assert float((out["visibility"] - ref["visibility"]).abs().max()) <= (8e-3 if impl == "tc2" else 2e-2)    # measured 2.4e-3 / 6.1e-3 (x8 stress gain)
     for k in ("accumulation", "depth", "normal", "albedo"):     # these do not go through the fp16 kernel
         err = (out[k] - ref[k]).abs().max() / ref[k].abs().max().clamp_min(1e-6)
         assert float(err) <= 1e-3, (k, float(err))
 
 
 def test_render_all_tensor_core_vs_oracle(dev, scene):
-    """K2 and K4 both on tcgen05 (fp16 operands): the throughput configuration.  Stated tolerances: rgb 1e-2 absolute,
-    accumulation / depth 5e-3 relative, rendered normal 1e-2 absolute."""
+    """K2 and K4 both on tcgen05 (fp16 operands): the throughput configuration.  Measured on B200: rgb 1.3e-4, normal 1.7e-4,
+    albedo 7e-5, accumulation 1.4e-4 absolute, depth 7e-5; asserted at ~3x that, all inside north_star's 1e-3."""
     _, _, _, out = _render(dev, scene, "tc2", "tc")
     ref = scene["ref"]
     errs = {k: float((out[k] - ref[k]).abs().max()) for k in ("rgb", "accumulation", "depth", "normal", "albedo")}
-    print(errs)
-    assert errs["rgb"] <= 1e-2 and errs["normal"] <= 1e-2 and errs["albedo"] <= 1e-2
-    assert errs["accumulation"] <= 5e-3 and errs["depth"] <= 5e-3 * float(ref["depth"].abs().max())
+    log_err("render_all_tc", **errs)
+    assert errs["rgb"] <= 5e-4 and errs["normal"] <= 7e-4 and errs["albedo"] <= 4e-4, errs
+    assert errs["accumulation"] <= 6e-4 and errs["depth"] <= 3e-4 * float(ref["depth"].abs().max()), errs
 
 
 def test_render_image_is_tile_invariant(dev, scene):
@@ -223,12 +227,16 @@ def test_baseline_config1_full_size_vs_oracle(dev):
             assert float((ev > 1e-3).float().mean()) <= 1e-4, float((ev > 1e-3).float().mean())
         else:
             errs = {k: float((out[k] - ref[k]).abs().max()) for k in ("rgb", "accumulation", "depth", "normal", "albedo")}
-            assert errs["rgb"] <= 1e-2 and errs["normal"] <= 1e-2 and errs["albedo"] <= 1e-2, errs
-            assert errs["accumulation"] <= 5e-3 and errs["depth"] <= 5e-3 * float(ref["depth"].abs().max()), errs
-            # fp16-operand DDF under the x8 stress gain of this random init: the per-pair visibility error has a heavy tail (the FiLM
-            # frequencies 15 f + 30 turn operand rounding into phase error), so over 1.26 M pairs it is bounded in distribution, and
-            # through what it feeds: the rendered colour above (1e-2 stated, ~2e-4 measured)
+            log_err("config1_full_tc", **errs)
+            # measured at the full config-1 size: rgb 1.5e-4, normal 2.2e-4, albedo 1.0e-4, accumulation 2.0e-4, depth 9e-5
+            assert errs["rgb"] <= 5e-4 and errs["normal"] <= 7e-4 and errs["albedo"] <= 4e-4, errs
+            assert errs["accumulation"] <= 6e-4 and errs["depth"] <= 3e-4 * float(ref["depth"].abs().max()), errs
+            # fp16-operand DDF under the x8 stress gain of this random init, evaluated at surface points that themselves moved by ~1e-4
+            # (K2 on tensor cores): the per-pair visibility error has a heavy tail (FiLM frequencies 15 f + 30 turn a displaced input
+            # into phase error), so over 1.26 M pairs it is bounded in distribution (measured mean 9.3e-5, 4e-5 of the pairs above
+            # 2e-2), and through what it feeds: the rendered colour above
             ev = (out["visibility"] - ref["visibility"]).abs()
             stats = (float(ev.mean()), float((ev > 2e-2).float().mean()), float(ev.max()))
+            log_err("config1_full_tc_vis", mean=stats[0], frac_gt_2e2=stats[1], max=stats[2])
             print("config 1, tensor-core path: max abs errors", errs, "visibility |err| mean / frac > 2e-2 / max:", stats)
-            assert stats[0] <= 3e-3 and stats[1] <= 2e-3, stats
+            assert stats[0] <= 3e-4 and stats[1] <= 2e-4, stats

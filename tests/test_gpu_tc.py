@@ -1,10 +1,17 @@
 """Tensor-core (tcgen05, fp16 operands / fp32 accumulate) shading path vs the exact fp32 CUDA path and
-the CPU oracle.  Tolerances for this path are stated here, separately from the fp32 path
-(BASELINE.json north_star): per-pair visibility |err| <= 2e-2 max and <= 3e-3 mean under a x8
-stress gain on the DDF output layer, DDF distance |err| <= 4e-3, shaded linear RGB <= 3e-3 relative."""
+the CPU oracle.  Tolerances for this path are stated here, separately from the fp32 path (BASELINE.json
+north_star), and kept at ~3x what the B200 measures (gpurun_out/test_errors.jsonl via conftest.log_err;
+profiles/r02_test_errors.jsonl is the committed copy):
+
+  default kernel `tc2` (CTA pairs; first trunk layer carried as an fp16 hi/lo split):
+    random-init DDF as the reference initialises it (gain 1): visibility |err| <= 1e-3 max  (measured 4.4e-4) -- north_star's bar
+    x8 stress gain on the DDF output layer (the goldens): visibility <= 1e-2 max / 3e-4 mean (measured 3.3e-3 / 8e-5),
+    DDF distance <= 2.5e-3 (7e-4), shaded linear RGB <= 1.5e-3 relative (4.4e-4)
+  single-CTA variant `tc` (no hi/lo split; kept as the bring-up kernel): 2e-2 / 5e-4 / 4e-3 / 3e-3."""
 import pytest
 import torch
 
+from conftest import log_err
 from neusky_b200 import init as nb_init
 
 pytestmark = pytest.mark.gpu
@@ -48,11 +55,15 @@ def test_tc_vs_simt(dev, R, D, S, gain, impl):
     assert torch.allclose(out["termination_dist"], ref["termination_dist"], rtol=1e-5, atol=2e-6)
     e_ddf = (out["expected_termination_dist"] - ref["expected_termination_dist"]).abs()
     e_vis = (out["visibility"] - ref["visibility"]).abs()
-    assert float(e_ddf.max()) <= 4e-3, float(e_ddf.max())
-    assert float(e_vis.max()) <= 2e-2 and float(e_vis.mean()) <= 3e-3, (float(e_vis.max()), float(e_vis.mean()))
     denom = ref["rgb_lin"].abs().clamp_min(1e-3)
     rel = ((out["rgb_lin"] - ref["rgb_lin"]).abs() / denom).max()
-    assert float(rel) <= 3e-3, float(rel)
+    log_err(f"tc_vs_simt[{impl},{R},{D},{S},{gain}]", ddf_max=e_ddf.max(), vis_max=e_vis.max(), vis_mean=e_vis.mean(), rgb_rel=rel)
+    t_ddf, t_vmax, t_vmean, t_rel = (2.5e-3, 1e-2, 3e-4, 1.5e-3) if impl == "tc2" else (4e-3, 2e-2, 5e-4, 3e-3)
+    if impl == "tc2" and gain == 1.0:
+        t_vmax = 1e-3          # north_star's visibility bar on the reference's own initialisation
+    assert float(e_ddf.max()) <= t_ddf, float(e_ddf.max())
+    assert float(e_vis.max()) <= t_vmax and float(e_vis.mean()) <= t_vmean, (float(e_vis.max()), float(e_vis.mean()))
+    assert float(rel) <= t_rel, float(rel)
 
 
 def test_tc_vs_reference_golden(dev, golden):
@@ -71,9 +82,10 @@ def test_tc_vs_reference_golden(dev, golden):
                    want_vis=True, want_ddf=True, threshold=float(g["threshold"]), sigmoid_scale=float(g["sigmoid_scale"]))
     ref = torch.from_numpy(g["visibility"])
     e = (out["visibility"].cpu() - ref).abs()
-    assert float(e.max()) <= 2e-2 and float(e.mean()) <= 3e-3, (float(e.max()), float(e.mean()))
     e_ddf = (out["expected_termination_dist"].cpu() - torch.from_numpy(g["expected_termination_dist"])).abs()
-    assert float(e_ddf.max()) <= 4e-3
+    log_err("tc_vs_reference_golden", vis_max=e.max(), vis_mean=e.mean(), ddf_max=e_ddf.max())
+    assert float(e.max()) <= 1e-2 and float(e.mean()) <= 1.5e-4, (float(e.max()), float(e.mean()))      # measured 3.0e-3 / 4.2e-5 (x8 stress gain)
+    assert float(e_ddf.max()) <= 2e-3                                                                       # measured 6.6e-4
 
 
 @pytest.mark.parametrize("impl", ["tc", "tc2"])
@@ -93,6 +105,7 @@ def test_tc_multi_tile_persistent_and_no_vis_buffer(dev, impl):
     torch.cuda.synchronize()
     assert "visibility" not in out
     rel = ((out["rgb_lin"] - ref["rgb_lin"]).abs() / ref["rgb_lin"].abs().clamp_min(1e-3)).max()
-    assert float(rel) <= 3e-3, float(rel)
+    log_err(f"tc_multi_tile[{impl}]", rgb_rel=rel)
+    assert float(rel) <= (1e-3 if impl == "tc2" else 3e-3), float(rel)      # measured 3.4e-4 / 7.2e-4
     # run-to-run: only the fp32 atomic summation order may differ
     assert torch.allclose(out["rgb_lin"], out2["rgb_lin"], rtol=1e-5, atol=1e-7)
