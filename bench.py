@@ -202,19 +202,51 @@ def _config(args, world):
             "k4_numerics": "fp16 operands, fp32 accumulate (tcgen05.mma.cta_group::2 kind::f16, CTA pairs), fp32 epilogues"}
 
 
+# ------------------------------------------------------------------------------------------ process / device context
+class Ctx:
+    """One process per GPU: rank / device / process group, initialised once per bench.py invocation."""
+
+    def __init__(self):
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=self.dev)
+            self.dist = dist
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(self, *xs):
+        if self.dist is None:
+            return xs if len(xs) > 1 else xs[0]
+        t = torch.tensor(list(xs), device=self.dev, dtype=torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        v = [float(x) for x in t]
+        return v if len(v) > 1 else v[0]
+
+    def close(self):
+        if self.dist is not None:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
 # ------------------------------------------------------------------------------------------ eval-render arm (configs[2])
-def eval_arm(args):
+def eval_arm(args, ctx):
     """Full-image eval render of a 1280x720 synthetic camera, S uniform samples per ray, D = 642 icosphere directions
     (308 through the DDF), ray tiles round-robin over the ranks, per-ray outputs gathered at the end (strong scaling:
     the image is fixed).  Supplementary line: the driver's headline is the default workload."""
-    rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+    rank, local, world, dev, dist = ctx.rank, ctx.local, ctx.world, ctx.dev, ctx.dist
     import math
     from neusky_b200 import _lib, init as nb_init, samplers
     from neusky_b200.render import RayRenderer, pinhole_rays, render_image
@@ -238,50 +270,46 @@ def eval_arm(args):
     def step():
         return render_image(r, o, d, dn, args.samples, Z[0], sc[0], tile=args.tile)
 
+    from neusky_b200 import parallel as _par
+
     for _ in range(args.warmup):
         step()
-    if dist is not None:
-        dist.barrier()
-    torch.cuda.synchronize()
+    ctx.barrier()
     l0 = _lib.launches
-    ts = []
+    ts, tg = [], []
     for _ in range(args.steps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        _par.GATHER_EVENTS = []
         e0.record(); out = step(); e1.record()
         torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1) / 1e3)
-    t = sum(ts)
-    if dist is not None:
-        tt = torch.tensor([t], device=dev, dtype=torch.float64); dist.all_reduce(tt, op=dist.ReduceOp.MAX); t = float(tt.item())
+        tg.append(sum(a.elapsed_time(b) for a, b in _par.GATHER_EVENTS) / 1e3)
+    _par.GATHER_EVENTS = None
+    t, t_gather = ctx.max_over_ranks(sum(ts), sum(tg))
+    line = None
     if rank == 0:
         n = H * W
         acc = out["accumulation"]
-        print(json.dumps({"metric": METRIC, "value": n * args.steps / t, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        line = ({"metric": METRIC, "value": n * args.steps / t, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                           "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f16xf16->f32", "data": "synthetic",
                           "config": {"workload": f"BASELINE.json configs[2]: full-image eval render {W}x{H}, {args.samples} {'proposal-network (256->96->' + str(args.samples) + ')' if args.sampler == 'proposal' else 'uniform'} samples/ray, 642 icosphere directions (D'={Dp}), "
                                                  f"ray tiles of {args.tile} round-robin over {world} GPU(s), outputs gathered", "parallelism": f"ray tiles x{world}, weights replicated",
                                      "l2": "inputs (118 M samples/frame) exceed L2", "surface_coverage": float((acc > 0.5).float().mean())},
-                          "gpu_launches": _lib.launches - l0, "pairs_per_frame": n * Dp, "samples_per_frame": n * args.samples}), flush=True)
-    if dist is not None:
-        dist.barrier(); dist.destroy_process_group()
+                          "gpu_launches": _lib.launches - l0, "pairs_per_frame": n * Dp, "samples_per_frame": n * args.samples,
+                          "gather_ms_per_step": 1e3 * t_gather / args.steps, "gather_bytes_per_step": n * 12 * 4 if world > 1 else 0,
+                          "collective": "all_gather_into_tensor of the per-ray outputs (12 floats/ray) + one indexed copy" if world > 1 else "none (single rank)"})
+    return line
 
 
 
 # ------------------------------------------------------------------------------------------ relighting sweep (configs[4])
-def relight_arm(args):
+def relight_arm(args, ctx):
     """BASELINE.json configs[4]: fixed geometry, 64 RENI++ latent codes re-shaded per view.  The frame is rendered once with
     `want_cache=True` (per-sample shading inputs + per-ray visibility of the D' DDF directions, kept in HBM), then every
     latent code is one RENI++ decode + one Lambertian pass over the cache per tile -- no SDF field, no compositing, no DDF.
     The timed region is the 64-code sweep; the cache build is reported separately.  Ray tiles are partitioned over the ranks
     (strong scaling), each rank relights its own tiles; no collective in the timed region."""
-    rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+    rank, local, world, dev, dist = ctx.rank, ctx.local, ctx.world, ctx.dev, ctx.dist
     import math
     from neusky_b200 import _lib, init as nb_init, samplers
     from neusky_b200.render import RayRenderer, global_steps_minmax, pinhole_rays
@@ -355,6 +383,7 @@ def relight_arm(args):
     t = sum(ts)
     if dist is not None:
         tt = torch.tensor([t, build_s], device=dev, dtype=torch.float64); dist.all_reduce(tt, op=dist.ReduceOp.MAX); t, build_s = (float(x) for x in tt)
+    line = None
     if rank == 0:
         peaks = _peaks()
         # bytes one relight pass must read per ray: the collapsed coefficients D x 3 x 4 (or, per-sample cache: normals 12 + wa 12 +
@@ -362,7 +391,7 @@ def relight_arm(args):
         Dp = int(r.shader.mask.sum())
         per_ray = (S * 28 + Dp * 4) if args.per_sample_cache else 642 * 12
         algo = n * (per_ray + 16 + 12) * NL * args.steps
-        print(json.dumps({"metric": "relit rays/s (fixed geometry, new RENI++ latent code per pass)", "value": n * NL * args.steps / t, "unit": UNIT, "n_gpus": world,
+        line = ({"metric": "relit rays/s (fixed geometry, new RENI++ latent code per pass)", "value": n * NL * args.steps / t, "unit": UNIT, "n_gpus": world,
                           "steps": args.steps, "warmup": max(1, args.warmup // 3), "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "strong",
                           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                           "config": {"workload": f"BASELINE.json configs[4]: relighting sweep, {W}x{H} frame, {S} samples/ray, {NL} latent codes per step, "
@@ -372,9 +401,8 @@ def relight_arm(args):
                           "roofline": {"kernel": "lambert_relight_kernel" if args.per_sample_cache else "relight_collapsed_kernel", "bound": "hbm", "achieved": algo / t / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                        "frac": algo / t / 1e9 / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
                                        "note": "whole-sweep rate over the cache bytes: includes the RENI++ decodes of the direction set and of the per-ray background"},
-                          "gpu_launches": _lib.launches - l0}), flush=True)
-    if dist is not None:
-        dist.barrier(); dist.destroy_process_group()
+                          "gpu_launches": _lib.launches - l0})
+    return line
 
 
 # ------------------------------------------------------------------------------------------ training-step arm (configs[3])
@@ -392,19 +420,12 @@ def _train_batch(R: int, K: int, seed: int):
             "sky": (torch.rand(R, generator=g) > 0.8).float()}
 
 
-def train_arm(args):
+def train_arm(args, ctx):
     """One `ns-train neusky` iteration per step at R = 1024 rays per GPU (README default): forward (uniform S = 48 samples,
     SDF/albedo field with analytic normals, NeuS compositing, RENI++ radiance, DDF visibility on the R x D' pairs of a randomly
     rotated 642-direction icosphere, sdf_at_termination, Lambertian shading), the reference's losses, backward into every
     parameter group, bucketed gradient all-reduce (NCCL) and a fused Adam step.  Weak scaling: every rank has its own R rays."""
-    rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+    rank, local, world, dev, dist = ctx.rank, ctx.local, ctx.world, ctx.dev, ctx.dist
     import numpy as np
     from scipy.spatial.transform import Rotation
     from neusky_b200 import _lib, init as nb_init, samplers
@@ -464,10 +485,8 @@ def train_arm(args):
 
     for _ in range(args.warmup):
         one_step()
-    if dist is not None:
-        dist.barrier()
-    torch.cuda.synchronize()
-    sampler = ClockSampler(local) if rank == 0 else None
+    ctx.barrier()
+    sampler = ClockSampler(local) if (rank == 0 and getattr(args, "sample_clocks", True)) else None
     if sampler:
         sampler.start()
     Dp_seen.clear()
@@ -481,14 +500,28 @@ def train_arm(args):
     host_launch = time.perf_counter() - wall0        # the loop never synchronises: time until the last launch of the last step was queued
     torch.cuda.synchronize()
     t = sum(a.elapsed_time(b) for a, b in evs) / 1e3
-    if dist is not None:
-        dist.barrier()
-    torch.cuda.synchronize()
+    ctx.barrier()
     wall = time.perf_counter() - wall0
     clocks = sampler.stop() if sampler else None
     launches = _lib.launches - l0
-    if dist is not None:
-        tt = torch.tensor([t, wall], device=dev, dtype=torch.float64); dist.all_reduce(tt, op=dist.ReduceOp.MAX); t, wall = (float(x) for x in tt)
+    t, wall = ctx.max_over_ranks(t, wall)
+    # exposed all-reduce time: the same steps with the collective switched off (every rank keeps its local gradients; identical compute)
+    exposed_ms = None
+    if world > 1:
+        red.on = False
+        n_off = max(2, args.steps // 2)
+        one_step()
+        ctx.barrier()
+        ev2 = []
+        for _ in range(n_off):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); one_step(); e1.record()
+            ev2.append((e0, e1))
+        torch.cuda.synchronize()
+        t_off = ctx.max_over_ranks(sum(a.elapsed_time(b) for a, b in ev2) / 1e3)
+        red.on = True
+        exposed_ms = 1e3 * (t / args.steps - t_off / n_off)
+    line = None
     if rank == 0:
         peaks = _peaks()
         Dp = sum(Dp_seen) / max(1, len(Dp_seen))
@@ -513,10 +546,59 @@ def train_arm(args):
                 "e2e": {"value": world * R * args.steps / wall, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                         "api": "neusky_b200.train.NeuSkyTrainStep + parallel.GradBucketReducer; e2e value is wall-clock over the timed steps (host work, h2d of the ray batch and d2h of the loss included); `value` is CUDA-event time of the same steps"},
                 "gpu_launches": launches, "algorithmic_tflops": flop * args.steps / t / 1e12, "tf32_peak_tflops_sustained": peaks["tf_sustained"] / 2,
+                "all_reduce_exposed_ms": exposed_ms, "all_reduce_bytes_per_step": red.bytes_per_step if world > 1 else 0,
                 "clocks": clocks, "loss": float(loss_h.item())}
-        print(json.dumps(line), flush=True)
-    if dist is not None:
-        dist.barrier(); dist.destroy_process_group()
+    return line
+
+
+# ------------------------------------------------------------------------------------------ fp32-parity figures for K4
+def fp32_parity_roofline(dev):
+    """The same (point, direction) pairs through the paths that meet north_star's 1e-3 on per-pair visibility WHATEVER the weights
+    (the default fp16-operand kernel meets it on the reference's initialisation, 4.4e-4 measured, and is at 3e-3 under the x8
+    stress gain of the goldens): the exact fp32 CUDA-core kernel, and the layer-wise 3xTF32 tcgen05 chain (fp32-accurate tensor-core
+    path, unfused: activations round-trip HBM).  Algorithmic FLOP per pair as for the headline; fractions against the same
+    sustained dense fp16/bf16 peak (a 3xTF32 contraction issues three half-rate MMAs per product: 1/6 of that peak at best)."""
+    from neusky_b200 import init as nb_init, train as T
+    from neusky_b200.render import SkyShader
+
+    peaks = _peaks()
+    ddf = nb_init.init_ddf_params(SEED_W)
+    sh = SkyShader(ddf, None, device=dev)
+    sh.set_directions(_equirect_directions(WIDTH))
+    Dp = int(sh.mask.sum())
+    out = {"peak": peaks["tf_sustained"], "unit": "TFLOP/s", "flop_per_pair": FLOP_PER_PAIR}
+
+    def run(fn, pairs, iters=3):
+        fn(); fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        ach = pairs * FLOP_PER_PAIR / (ms * 1e-3) / 1e12
+        return {"achieved": ach, "frac": ach / peaks["tf_sustained"], "ms_per_launch": ms, "pairs_per_launch": pairs}
+
+    P = 16384
+    pts, nrm, alb = (t.to(dev) for t in _inputs(P, SEED_P))
+    rad = torch.ones(1, sh.dirs.shape[0], 3, device=dev)
+    out["simt_fp32"] = {"kernel": "sky_shade_simt_kernel (fp32 FMA, fused)", "visibility_err_vs_reference": "<= 5e-4 (tests/test_gpu_parity.py)",
+                        **run(lambda: sh.shade(pts, nrm.reshape(P, 1, 3), alb.reshape(P, 1, 3), rad, impl="simt"), P * Dp)}
+    P2 = 512      # 524k rows: the [rows, 2560] FiLM tensor of the chain is 5.4 GB in fp32
+    p_dev = {k: v.to(dev) for k, v in ddf.items()}
+    cfg = T.DDFConfig(scalings=sh.scalings, log2_T=19, radius=1.0, sigmoid_scale=25.0, split=3)
+    thr = torch.tensor(0.1, device=dev)
+    mlp = T.ddf_param_list(p_dev)
+
+    def chain():
+        with torch.no_grad():
+            T.ddf_visibility(cfg, pts[:P2].contiguous(), sh.dirs_sel, thr, p_dev["position_encoding.hash_table"], p_dev["ddf.final_layer.weight"], p_dev["ddf.final_layer.bias"], mlp)
+
+    out["tc_3xtf32_chain"] = {"kernel": "gemm_tf32_kernel<3> x 11 + film_sin / ddf_head (tcgen05 kind::tf32, 3xTF32, layer-wise)",
+                              "visibility_err_vs_reference": "<= 2e-4 (tests/test_gpu_train.py, split=3)", **run(chain, P2 * Dp)}
+    return out
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
@@ -528,6 +610,9 @@ def main():
     ap.add_argument("--points", type=int, default=1_000_000)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the config-3 / config-4 runs (extra.eval, extra.train) after the headline")
+    ap.add_argument("--no-kernels", action="store_true", help="skip the per-kernel roofline microbenchmarks (kernels[], roofline_fp32_parity)")
+    ap.add_argument("--extra-steps", type=int, default=3, help="timed frames of the config-3 extra (the config-4 extra times twice as many steps)")
     ap.add_argument("--workload", default="shade", choices=["shade", "eval", "train", "relight"],
                     help="shade = BASELINE.json configs[1] (the headline line); eval = configs[2] full-image render, train = configs[3] training step (supplementary lines)")
     ap.add_argument("--height", type=int, default=720)
@@ -546,28 +631,14 @@ def main():
     if args.impl == "reference":
         reference_arm(args)
         return
-    if args.workload == "eval":
-        eval_arm(args)
+    ctx = Ctx()
+    if args.workload != "shade":
+        line = {"eval": eval_arm, "relight": relight_arm, "train": train_arm}[args.workload](args, ctx)
+        if line is not None:
+            print(json.dumps(line), flush=True)
+        ctx.close()
         return
-    if args.workload == "relight":
-        relight_arm(args)
-        return
-    if args.workload == "train":
-        train_arm(args)
-        return
-
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+    rank, local, world, dev, dist = ctx.rank, ctx.local, ctx.world, ctx.dev, ctx.dist
 
     from neusky_b200 import _lib, init as nb_init
     from neusky_b200.render import SkyShader
@@ -582,17 +653,7 @@ def main():
     Z, sc = (t.to(dev) for t in _latents())
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x: float) -> float:
-        if dist is None:
-            return x
-        t = torch.tensor([x], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+    barrier, max_over_ranks = ctx.barrier, ctx.max_over_ranks
 
     def timed(fn, steps):
         evs = []
@@ -627,7 +688,7 @@ def main():
     # ---- end to end from pinned host buffers -----------------------------------------------------
     out_h = torch.empty(P, 3, dtype=torch.float32).pin_memory()
     e2e_step = lambda: shader.shade_points_host(pts_h, nrm_h, alb_h, Z, sc, out_h=out_h)
-    e2e_steps = max(1, min(args.steps, 2))
+    e2e_steps = args.steps                 # the same K steps as the device-resident figure
     e2e_step()
     barrier()
     t_e2e = max_over_ranks(timed(e2e_step, e2e_steps))
@@ -654,10 +715,42 @@ def main():
         if not args.no_cpu_baseline and world == 1:
             r, cores, desc, t = cpu_oracle_rate()
             line["cpu_baseline"] = {"value": r, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc, "seconds": t}
+    else:
+        line = None
+    del pts, nrm, alb, pts_h, nrm_h, alb_h, out_h, shader
+    torch.cuda.empty_cache()
+
+    # ---- the splits that carry a collective, under the same clock: config 3 (eval frame, ray tiles over the ranks +
+    # ---- all-gather of the outputs, strong scaling) and config 4 (training step, data-parallel gradient all-reduce, weak scaling) ---------
+    if not args.no_extras:
+        import copy
+
+        ea = copy.copy(args); ea.steps, ea.warmup = args.extra_steps, 2
+        ev = eval_arm(ea, ctx)
+        torch.cuda.empty_cache()
+        ta = copy.copy(args); ta.steps, ta.warmup, ta.sample_clocks = max(4, 2 * args.extra_steps), 3, False
+        tr = train_arm(ta, ctx)
+        torch.cuda.empty_cache()
+        if line is not None:
+            keep = ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "dtype", "gpu_launches")
+            line["extra"] = {
+                "eval": {**{k: ev[k] for k in keep}, "workload": ev["config"]["workload"], "gather_ms_per_step": ev["gather_ms_per_step"],
+                         "gather_bytes_per_step": ev["gather_bytes_per_step"], "collective": ev["collective"]},
+                "train": {**{k: tr[k] for k in keep}, "workload": tr["config"]["workload"], "parallelism": tr["config"]["parallelism"],
+                          "all_reduce_exposed_ms": tr["all_reduce_exposed_ms"], "all_reduce_bytes_per_step": tr["all_reduce_bytes_per_step"],
+                          "algorithmic_tflops": tr["algorithmic_tflops"], "wall_ms_per_step": tr["wall_ms_per_step"]},
+            }
+    # ---- per-kernel rooflines of the rest of the path (K1, K2, K3, RENI++, proposal sampler): rank 0, the other ranks wait at the barrier ----
+    if not args.no_kernels:
+        if rank == 0:
+            from bench_kernels import kernel_rooflines
+
+            line["kernels"] = kernel_rooflines(dev, _peaks(), scale=0.25)
+            line["roofline_fp32_parity"] = fp32_parity_roofline(dev)
+        barrier()
+    if line is not None:
         print(json.dumps(line), flush=True)
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
+    ctx.close()
 
 
 if __name__ == "__main__":

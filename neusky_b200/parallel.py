@@ -34,6 +34,7 @@ def max_local_rays(n_rays: int, tile: int, world: int) -> int:
 
 
 _GATHER_MAP: Dict[tuple, Tensor] = {}
+GATHER_EVENTS = None      # bench hook: when a list, gather_rays appends a (start, end) CUDA event pair around the collective + reorder
 
 
 def _gather_map(n_rays: int, tile: int, world: int, device) -> Tensor:
@@ -70,8 +71,16 @@ def gather_rays(local: Tensor, n_rays: int, tile: int, group=None) -> Tensor:
         buf = torch.zeros((cap, C), dtype=local.dtype, device=local.device)
         buf[: local.shape[0]] = local
     out = torch.empty((world * cap, C), dtype=local.dtype, device=local.device)
+    ev = None
+    if GATHER_EVENTS is not None and local.is_cuda:
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
     dist.all_gather_into_tensor(out, buf, group=group)
-    return out.index_select(0, _gather_map(n_rays, tile, world, local.device))
+    full = out.index_select(0, _gather_map(n_rays, tile, world, local.device))
+    if ev is not None:
+        ev[1].record()
+        GATHER_EVENTS.append(ev)
+    return full
 
 
 def render_sharded(render_fn: Callable[[Tensor], Dict[str, Tensor]], n_rays: int, tile: int, keys: Tuple[str, ...], device=None, group=None) -> Dict[str, Tensor]:

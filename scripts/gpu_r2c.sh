@@ -1,3 +1,6 @@
 #!/bin/bash
+# round 2, call C: the default bench line (headline + extras + kernels) on 1 GPU
+cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_tf32 -s 2 -c 1 -o gpurun_out/r2c_gemm_nt_256_256_s3 -f python scripts/gemm_one.py 256 256 3 > gpurun_out/r2c_ncu.log 2>&1; echo "ncu exit=$?"
+( time timeout 900 python bench.py --steps 3 --warmup 3 ) > gpurun_out/r2c_bench.json 2> gpurun_out/r2c_bench.err; echo "bench rc=$?"
+tail -c 6000 gpurun_out/r2c_bench.json; tail -8 gpurun_out/r2c_bench.err
