@@ -143,6 +143,13 @@ int nsk_reni_decode_fwd(const float* dirs, int64_t D, const float* latents, cons
 int nsk_reni_decode_rows_fwd(const float* dirs, const int* row_cam, int64_t N, const float* latents, const float* scale, int64_t K,
                              const float* rotation, const float* weights, int latent_dim, int hidden, int num_layers,
                              int log_domain, float* workspace, float* out, void* stream);
+/* Fused tensor-core row decode (csrc/reni_fused_tc.cu): the whole decoder of the rows above in ONE tcgen05 kernel, fp16 operands, fp32
+ * accumulate and LayerNorm; for frame-sized batches (per-ray background of a render, relighting sweeps).  zxy [K,Ld,2] and attn [K,6,128]
+ * are the two halves of the nsk_reni_prep workspace; fused_weights = neusky_b200.packing.pack_reni_fused (nsk_reni_fused_weights_bytes()
+ * bytes, 16-byte aligned); row_cam NULL = one latent code; log_domain as for nsk_reni_decode_fwd. */
+int64_t nsk_reni_fused_weights_bytes(void);
+int nsk_reni_rows_fused_fwd(const float* dirs, const int* row_cam, int64_t N, const float* zxy, const float* attn, const float* scale,
+                            const void* fused_weights, int latent_dim, int log_domain, float* out, void* stream);
 /* Backward of both variants w.r.t. the latent codes and scales, decoder frozen: what torch autograd computes for the
  * per-image `illumination_latents` / `scale` parameters (neusky_model.py:261-269, 488-504) under
  * RENIField.hold_decoder_fixed (reni_illumination_field.py:157-196).  row_cam NULL = table mode (out, g_out [K,D,3]), else

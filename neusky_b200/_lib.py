@@ -33,7 +33,7 @@ def load() -> ctypes.CDLL:
             )
         lib = ctypes.CDLL(LIB_PATH)
         lib.nsk_last_error.restype = ctypes.c_char_p
-        for name in ("nsk_reni_weights_floats", "nsk_ddf_simt_weights_floats", "nsk_ddf_tc_weights_bytes", "nsk_sdf_simt_weights_floats", "nsk_sdf_tc_weights_bytes", "nsk_ddf_tc2_weights_bytes", "nsk_reni_bwd_weights_floats", "nsk_reni_bwd_workspace_floats", "nsk_proposal_mlp_floats"):
+        for name in ("nsk_reni_weights_floats", "nsk_ddf_simt_weights_floats", "nsk_ddf_tc_weights_bytes", "nsk_sdf_simt_weights_floats", "nsk_sdf_tc_weights_bytes", "nsk_ddf_tc2_weights_bytes", "nsk_reni_bwd_weights_floats", "nsk_reni_fused_weights_bytes", "nsk_reni_bwd_workspace_floats", "nsk_proposal_mlp_floats"):
             if hasattr(lib, name):
                 getattr(lib, name).restype = ctypes.c_int64
         _lib = lib

@@ -349,6 +349,40 @@ def reni_rows_tc(dirs: Tensor, latents: Tensor, scale: Optional[Tensor], packed:
     return out
 
 
+def reni_rows_fused(dirs: Tensor, latents: Tensor, scale: Optional[Tensor], packed: Tensor, fused_blob: Tensor, rotation: Optional[Tensor] = None,
+                    row_cam: Optional[Tensor] = None, log_domain=True) -> Tensor:
+    """dirs [N,3] (+ row_cam [N] int32 when K > 1), latents [K,L,3], scale [K] -> HDR radiance [N,3] through the FUSED tcgen05 kernel
+    (csrc/reni_fused_tc.cu: fp16 operands, fp32 accumulate / LayerNorm; a row's activations never leave the SM).  `packed` =
+    packing.pack_reni(...) (per-code prologue), `fused_blob` = packing.pack_reni_fused(...).  Meant for frame-sized N."""
+    N = dirs.shape[0]
+    K, L = latents.shape[0], latents.shape[1]
+    dirs = _chk("dirs", dirs, shape=(N, 3))
+    latents = _chk("latents", latents, shape=(K, L, 3))
+    if row_cam is not None:
+        row_cam = _chk("row_cam", row_cam, dtype=torch.int32, shape=(N,))
+    elif K != 1:
+        raise ValueError("reni_rows_fused: several latent codes need row_cam")
+    if scale is not None:
+        scale = _chk("scale", scale, shape=(K,))
+    if rotation is not None:
+        if rotation.dim() == 3:
+            raise NotImplementedError("Batched rotation not implemented yet")  # reni_illumination_field.py:520-521
+        rotation = _chk("rotation", rotation, shape=(3, 3))
+    lib = _lib.load()
+    hidden, num_layers = 128, 6
+    packed = _chk("packed", packed, shape=(lib.nsk_reni_weights_floats(c_int(L), c_int(hidden), c_int(num_layers)),))
+    fused_blob = _chk("fused_blob", fused_blob, dtype=torch.uint8, shape=(lib.nsk_reni_fused_weights_bytes(),))
+    dev = dirs.device
+    ws = torch.empty((K * num_layers * hidden + K * L * 2,), device=dev, dtype=torch.float32)
+    st = _stream(dirs)
+    _lib.check(lib.nsk_reni_prep(_ptr(latents), _ptr(rotation), c_int64(K), _ptr(packed), c_int(L), c_int(hidden), c_int(num_layers), _ptr(ws), st), "nsk_reni_prep")
+    attn, zxy = ws[:K * num_layers * hidden], ws[K * num_layers * hidden:]
+    out = torch.empty((N, 3), device=dev, dtype=torch.float32)
+    _lib.check(lib.nsk_reni_rows_fused_fwd(_ptr(dirs), _ptr(row_cam), c_int64(N), _ptr(zxy), _ptr(attn), _ptr(scale), _ptr(fused_blob), c_int(L), c_int(int(log_domain)),
+                                           _ptr(out), st), "nsk_reni_rows_fused_fwd")
+    return out
+
+
 def reni_radiance_rows(dirs: Tensor, row_cam: Tensor, latents: Tensor, scale: Optional[Tensor], packed: Tensor, rotation: Optional[Tensor] = None, hidden: int = 128, num_layers: int = 6, log_domain: bool = True) -> Tensor:
     """dirs [N,3], row_cam [N] int32 (latent code of each row), latents [K,L,3], scale [K] -> HDR radiance [N,3]
     (the per-ray background colours of a mixed-camera batch, neusky_model.py:535-549)."""

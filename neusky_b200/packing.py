@@ -313,3 +313,53 @@ def pack_sdf_tc(p: Dict[str, Tensor]) -> Tensor:
     vec[:256] = W2[0]
     vec[256] = b2[0]
     return torch.cat([stream, vec.view(torch.uint8)]).contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# Blob for csrc/reni_fused_tc.cu: 32 fp16 weight stages of [128 N][64 K] (first layer 510 -> 128 zero-padded to K = 512: 8 stages; then per
+# decoder layer fc.0 and fc.2, 2 stages each) in the order the MMA issuer consumes them, followed by the fp32 constants
+# (biases, LayerNorm weights, output head).  The attention constants a_i(k) come from nsk_reni_prep (per latent code).
+# ------------------------------------------------------------------------------------------------
+RENI_FUSED_WEIGHT_BYTES = 32 * 16384
+RENI_FUSED_CONST_FLOATS = 128 + 6 * 6 * 128 + 3 * 128 + 4
+
+
+@_host_packed
+def pack_reni_fused(p: Dict[str, Tensor], num_layers: int = 6) -> Tensor:
+    """uint8 blob [RENI_FUSED_WEIGHT_BYTES + RENI_FUSED_CONST_FLOATS * 4] for nsk_reni_rows_fused_fwd."""
+    if num_layers != 6:
+        raise ValueError("pack_reni_fused: the fused kernel implements the 6-layer RENI++ decoder NeuSky ships")
+    f = lambda k: p[k].to(torch.float32)
+    Wr = f("network.residual_projection.weight")
+    if Wr.shape[0] != 128 or Wr.shape[1] > 512:
+        raise ValueError("pack_reni_fused: expected a [128, 5 (L + 2) <= 512] residual projection")
+    if Wr.shape[1] != 510:
+        raise ValueError("pack_reni_fused: the fused kernel is specialised for latent_dim = 100 (a [128, 510] residual projection)")
+    nj = 102                                     # 100 latent inputs + d_z + |d_xy|: [sin a, sin 4a] x nj | [cos a, cos 4a] x nj | x x nj  (reni_illumination_field.py:345-348)
+    orig = lambda j: [2 * j, 2 * j + 1, 2 * nj + 2 * j, 2 * nj + 2 * j + 1, 4 * nj + j]       # sin a, sin 4a, cos a, cos 4a, x
+    extras = orig(100) + orig(101) + [-1, -1]
+    perm = []
+    for q in range(4):                           # the kernel's per-quarter layout (csrc/reni_fused_tc.cu, positional-encoding warps)
+        cols = []
+        for jj in range(25):
+            cols += orig(25 * q + jj)[:4]
+        cols += [orig(25 * q + jj)[4] for jj in range(25)]
+        cols += extras[3 * q:3 * q + 3]
+        perm += cols
+    assert len(perm) == 512 and sorted(c for c in perm if c >= 0) == list(range(510))
+    Wp = torch.zeros((128, 512), dtype=torch.float32)
+    idx = torch.tensor([c for c in perm if c >= 0])
+    Wp[:, torch.tensor([i for i, c in enumerate(perm) if c >= 0])] = Wr[:, idx]
+    st = _stages(Wp, 8, 64, 0)
+    consts = [f("network.residual_projection.bias")]
+    for i in range(num_layers):
+        pre = f"network.layers.{i}."
+        st += _stages(f(pre + "fc.0.weight"), 2, 64, 0) + _stages(f(pre + "fc.2.weight"), 2, 64, 0)
+        consts += [f(pre + "fc.0.bias"), f(pre + "fc.2.bias"), f(pre + "norm1.weight"), f(pre + "norm1.bias"), f(pre + "norm2.weight"), f(pre + "norm2.bias")]
+    fcb = torch.zeros(4, dtype=torch.float32)
+    fcb[:3] = f("network.fc.bias")
+    consts += [f("network.fc.weight").reshape(-1), fcb]
+    stream = torch.cat(st).contiguous().view(torch.uint8)
+    cvec = torch.cat([c.reshape(-1) for c in consts]).contiguous()
+    assert stream.numel() == RENI_FUSED_WEIGHT_BYTES and cvec.numel() == RENI_FUSED_CONST_FLOATS, (stream.numel(), cvec.numel())
+    return torch.cat([stream, cvec.view(torch.uint8)]).contiguous()

@@ -1,6 +1,6 @@
 #!/bin/bash
+# round 2, call D: the default bench line on 2 GPUs (extras exercise all-gather and the gradient all-reduce)
+cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
-timeout 600 python bench.py --workload train --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/r2d_bench_train.json 2> gpurun_out/r2d_train.err; echo "train exit=$?"; cut -c1-300 gpurun_out/r2d_bench_train.json; tail -3 gpurun_out/r2d_train.err
-timeout 600 python bench.py --workload train --steps 5 --warmup 3 --no-cpu-baseline --no-ddf-fit > gpurun_out/r2d_bench_train_nofit.json 2> gpurun_out/r2d_train2.err; echo "train exit=$?"; cut -c1-300 gpurun_out/r2d_bench_train_nofit.json
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2d_train_launches.csv python bench.py --workload train --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/r2d_train_under_ncu.log 2>&1; echo "ncu exit=$?"
-python scripts/summarise_launches.py gpurun_out/r2d_train_launches.csv gpurun_out/r2d_train_launch_summary.txt | head -30
+( time timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 2 --steps 3 --warmup 3 --no-kernels ) > gpurun_out/r2d_bench_n2.json 2> gpurun_out/r2d_bench_n2.err; echo "bench rc=$?"
+tail -c 3000 gpurun_out/r2d_bench_n2.json; tail -8 gpurun_out/r2d_bench_n2.err

@@ -1,12 +1,20 @@
 #!/bin/bash
-# round-1 closing measurement pass on the current tree: smoke, headline bench (+ reference arm), eval benches, per-kernel rooflines,
-# ncu launch list of the headline command
+# round 2, call E: ncu DRAM-traffic metrics for the bandwidth-bound kernels + compute-sanitizer runs
+cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2e_smoke.log 2>&1; echo "smoke exit=$?" >> gpurun_out/r2e_smoke.log; tail -2 gpurun_out/r2e_smoke.log
-timeout 900 python bench.py > gpurun_out/r2e_bench.json 2> gpurun_out/r2e_bench.err; echo "bench exit=$?"; cut -c1-300 gpurun_out/r2e_bench.json; tail -2 gpurun_out/r2e_bench.err
-timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r2e_bench_reference.json 2> gpurun_out/r2e_ref.err; echo "ref exit=$?"; cut -c1-200 gpurun_out/r2e_bench_reference.json
-timeout 600 python bench.py --workload eval --steps 3 --warmup 3 > gpurun_out/r2e_bench_eval.json 2> gpurun_out/r2e_e1.err; echo "eval exit=$?"; cut -c1-250 gpurun_out/r2e_bench_eval.json
-timeout 600 python bench.py --workload eval --samples 48 --sampler proposal --steps 3 --warmup 3 > gpurun_out/r2e_bench_eval_proposal48.json 2> gpurun_out/r2e_e2.err; echo "eval-prop exit=$?"; cut -c1-250 gpurun_out/r2e_bench_eval_proposal48.json
-timeout 600 python scripts/kernel_bench.py > gpurun_out/r2e_kernel_bench.jsonl 2> gpurun_out/r2e_kb.err; echo "kb exit=$?"; wc -l gpurun_out/r2e_kernel_bench.jsonl
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2e_launches_bench.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/r2e_bench_under_ncu.log 2>&1; echo "ncu exit=$?"
-python scripts/summarise_launches.py gpurun_out/r2e_launches_bench.csv gpurun_out/r2e_bench_launch_summary.txt | head -12
+M=dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,lts__t_sector_hit_rate.pct,gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed,sm__throughput.avg.pct_of_peak_sustained_elapsed
+timeout 900 ncu --metrics $M --clock-control none --csv --log-file gpurun_out/r02_ncu_hbm_kernels.csv \
+  -k regex:'hash_encode|neus_composite|proposal_density|pdf_resample|reni_|relight_collapsed|gemm_tf32' \
+  python scripts/ncu_kernels.py > gpurun_out/r02_ncu_hbm_kernels_algorithmic.jsonl 2> gpurun_out/r02_ncu_hbm.err
+echo "ncu rc=$?"; tail -3 gpurun_out/r02_ncu_hbm.err
+python scripts/summarise_ncu_metrics.py gpurun_out/r02_ncu_hbm_kernels.csv > gpurun_out/r02_ncu_hbm_kernels_summary.txt 2>&1; tail -n 40 gpurun_out/r02_ncu_hbm_kernels_summary.txt
+CS=/usr/local/cuda/bin/compute-sanitizer
+for tool in memcheck racecheck synccheck; do
+  timeout 600 $CS --tool $tool --error-exitcode 7 --print-limit 20 python -m pytest -q -x -p no:cacheprovider \
+     tests/test_gpu_parity.py tests/test_gpu_backward.py tests/test_gpu_sampler.py tests/test_gpu_shaders.py -m gpu > gpurun_out/r02_sanitizer_${tool}.log 2>&1
+  echo "$tool rc=$?"; grep -E "ERROR SUMMARY|passed|failed|RACECHECK SUMMARY" gpurun_out/r02_sanitizer_${tool}.log | tail -3
+done
+timeout 600 $CS --tool memcheck --error-exitcode 7 --print-limit 20 python -m pytest -q -x -p no:cacheprovider tests/test_gpu_train.py -m gpu -k "not proposal" > gpurun_out/r02_sanitizer_memcheck_train.log 2>&1
+echo "memcheck train rc=$?"; grep -E "ERROR SUMMARY|passed|failed" gpurun_out/r02_sanitizer_memcheck_train.log | tail -3
+timeout 600 $CS --tool initcheck --error-exitcode 7 --print-limit 20 python -m pytest -q -x -p no:cacheprovider tests/test_gpu_tc.py tests/test_gpu_sdf.py -m gpu > gpurun_out/r02_sanitizer_initcheck_tc.log 2>&1
+echo "initcheck tc rc=$?"; grep -E "ERROR SUMMARY|passed|failed" gpurun_out/r02_sanitizer_initcheck_tc.log | tail -3
