@@ -24,8 +24,9 @@
 //          ring 4 x 16 KB weight stages, 20 KB fp32 constants (biases, LayerNorm weights, output head)
 //   warp 0  weight producer (one lane)        warp 1  MMA issuer (one lane)        warp 2  TMEM allocator
 //   warps 4-7    positional encoding of the NEXT quarter / pair (thread = row; sin / cos on the MUFU after an exact range reduction)
-//   warps 8-11   epilogue of tile 0, warps 12-15 epilogue of tile 1 (thread = row: all 128 columns of a row live in one thread's
-//                registers, so LayerNorm needs no shuffles; the two epilogue warpgroups take 200 registers each via setmaxnreg)
+//   warps 8-15   epilogue of tile 0, warps 16-23 epilogue of tile 1: two threads per row (64 columns each, warps e and e + 4 share a TMEM
+//                lane quadrant); LayerNorm partial sums cross through shared memory under 64-thread named barriers; registers are moved
+//                from the service warps to the epilogue warpgroups with setmaxnreg
 #include "reni_common.cuh"
 #include "tc_util.cuh"
 
@@ -39,7 +40,7 @@ constexpr int STAGE_BYTES = 16384;                 // [128 N][64 K] fp16
 constexpr int NSLOT = 4;
 constexpr int NGROUP = 4 + 2 * NLAYER;             // 16 groups of K = 128 (2 stages each)
 constexpr int STAGES_PER_PAIR = 2 * NGROUP;        // 32
-constexpr int NUM_THREADS = 512;
+constexpr int NUM_THREADS = 768;                   // 8 service / encoding warps + 2 tiles x 8 epilogue warps
 constexpr int TILE_BYTES = TM * HID * 2;           // 32768
 constexpr int PE_LD = 512;
 
@@ -56,7 +57,8 @@ constexpr int64_t BLOB_BYTES = WEIGHT_BYTES + (int64_t)CB_FLOATS * 4;
 constexpr uint32_t OFF_A = 0;                                  // tile t: A_X at t * 65536, A_H at t * 65536 + 32768
 constexpr uint32_t OFF_RING = 4 * TILE_BYTES;                  // 131072
 constexpr uint32_t OFF_CONST = OFF_RING + NSLOT * STAGE_BYTES; // 196608
-constexpr uint32_t OFF_BAR = OFF_CONST + CB_FLOATS * 4;        // 217104
+constexpr uint32_t OFF_XCHG = OFF_CONST + CB_FLOATS * 4;       // 217104: LayerNorm partial sums [2 tiles][2 halves][128 rows] float4
+constexpr uint32_t OFF_BAR = OFF_XCHG + 2 * 2 * 128 * 16;      // 225296
 // A_X and A_H of a tile have a READY barrier each: with one shared barrier the positional-encoding warps (quarters 0 and 1 have no
 // dependency on the issuer) could complete two phases before the issuer consumed the first, and a parity wait cannot tell phase n from n + 2
 enum { B_WFULL = 0, B_WEMPTY = 4, B_AXREADY = 8, B_ACCREADY = 10, B_AXFREE = 12, B_AHFREE = 14, B_ACCFREE = 16, B_AHREADY = 18, B_COUNT = 20 };
@@ -86,67 +88,75 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
 template <int REGS> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS)); }
 template <int REGS> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS)); }
 
-// all 128 fp32 columns of this thread's TMEM lane starting at column `col`
-__device__ __forceinline__ void load_row128(uint32_t taddr, float (&v)[128]) {
+// 64 fp32 columns of this thread's TMEM lane starting at `taddr`
+__device__ __forceinline__ void load_row64(uint32_t taddr, float (&v)[64]) {
+  uint32_t u[4][16];
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    uint32_t u[16];
-    tmem_ld16(taddr + c * 16, u);
-    tmem_ld_wait();
+  for (int c = 0; c < 4; ++c) tmem_ld16(taddr + c * 16, u[c]);
+  tmem_ld_wait();
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[c * 16 + j] = __uint_as_float(u[j]);
-  }
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[c * 16 + j] = __uint_as_float(u[c][j]);
 }
 
-// v <- LayerNorm(v) * w + b (biased variance, eps 1e-5: torch.nn.LayerNorm), w / b in shared memory
-__device__ __forceinline__ void layernorm128(float (&v)[128], const float* __restrict__ w, const float* __restrict__ b) {
-  float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};        // eight independent partial sums: the 128-long dependent chain was the epilogue's critical path
-#pragma unroll
-  for (int j = 0; j < 128; ++j) s[j & 7] += v[j];
-  const float mean = (((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]))) * (1.0f / 128.0f);
-  float q[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-  for (int j = 0; j < 128; ++j) { const float d = v[j] - mean; q[j & 7] = fmaf(d, d, q[j & 7]); }
-  const float rstd = rsqrtf((((q[0] + q[1]) + (q[2] + q[3])) + ((q[4] + q[5]) + (q[6] + q[7]))) * (1.0f / 128.0f) + 1e-5f);
-  const float4* w4 = reinterpret_cast<const float4*>(w);      // 16-byte broadcast loads: the per-column constants were the epilogue's
-  const float4* b4 = reinterpret_cast<const float4*>(b);      // critical path as 4-byte loads (one warp per SM sub-partition, 128 live registers)
-#pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    const float4 ww = w4[j], bb = b4[j];
-    v[4 * j + 0] = fmaf((v[4 * j + 0] - mean) * rstd, ww.x, bb.x);
-    v[4 * j + 1] = fmaf((v[4 * j + 1] - mean) * rstd, ww.y, bb.y);
-    v[4 * j + 2] = fmaf((v[4 * j + 2] - mean) * rstd, ww.z, bb.z);
-    v[4 * j + 3] = fmaf((v[4 * j + 3] - mean) * rstd, ww.w, bb.w);
-  }
-}
-
-// v += a (+ b): per-column constants through 16-byte loads (shared or global)
-__device__ __forceinline__ void add128(float (&v)[128], const float* __restrict__ a) {
+// v += a: 64 per-column constants through 16-byte broadcast loads (shared memory) / read-only global loads
+__device__ __forceinline__ void add64(float (&v)[64], const float* __restrict__ a) {
   const float4* a4 = reinterpret_cast<const float4*>(a);
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
+  for (int j = 0; j < 16; ++j) {
     const float4 x = a4[j];
     v[4 * j + 0] += x.x; v[4 * j + 1] += x.y; v[4 * j + 2] += x.z; v[4 * j + 3] += x.w;
   }
 }
-__device__ __forceinline__ void add128_ldg(float (&v)[128], const float* __restrict__ a) {
+__device__ __forceinline__ void add64_ldg(float (&v)[64], const float* __restrict__ a) {
   const float4* a4 = reinterpret_cast<const float4*>(a);
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
+  for (int j = 0; j < 16; ++j) {
     const float4 x = __ldg(a4 + j);
     v[4 * j + 0] += x.x; v[4 * j + 1] += x.y; v[4 * j + 2] += x.z; v[4 * j + 3] += x.w;
   }
 }
 
-// fp16 image of a row of the next A operand + the fp32 residual base (x + bias) back into TMEM
-__device__ __forceinline__ void store_row(const float (&v)[128], uint8_t* a_dst /* tile base + row * 16 */, uint32_t tmem_x, const float* __restrict__ resid_bias) {
+// LayerNorm over a row of 128 held by TWO threads (64 columns each, same TMEM lane, warps w and w + 4 of the tile's epilogue group):
+// biased variance, eps 1e-5 (torch.nn.LayerNorm), two-pass like the reference; the partial sums cross through shared memory
+// (`mine` / `theirs`: this thread's and its partner's float4 slot) under a 64-thread named barrier.  w / b: this half's 64 columns.
+__device__ __forceinline__ void layernorm_half(float (&v)[64], const float* __restrict__ w, const float* __restrict__ b, float4* mine, const float4* theirs, int bar_id) {
+  // one exchange per LayerNorm: (sum, sum of squares) of this half; var = E[v^2] - mean^2 in fp32 (the rows here are O(1) with
+  // |mean| < std, so the cancellation costs ~1e-7 relative; the two-pass form needed a second named-barrier round trip)
+  float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-  for (int c = 0; c < 16; ++c)
+  for (int j = 0; j < 64; ++j) { s[j & 3] += v[j]; q[j & 3] = fmaf(v[j], v[j], q[j & 3]); }
+  const float s_mine = (s[0] + s[1]) + (s[2] + s[3]), q_mine = (q[0] + q[1]) + (q[2] + q[3]);
+  mine->x = s_mine; mine->y = q_mine;
+  asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+  const float mean = (s_mine + theirs->x) * (1.0f / 128.0f);
+  const float var = fmaxf(fmaf(-mean, mean, (q_mine + theirs->y) * (1.0f / 128.0f)), 0.f);
+  const float rstd = rsqrtf(var + 1e-5f);
+  const float shift = -mean * rstd;
+  asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");     // the partner has read this slot before the next LayerNorm rewrites it
+  const float4* w4 = reinterpret_cast<const float4*>(w);
+  const float4* b4 = reinterpret_cast<const float4*>(b);
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const float4 ww = w4[j], bb = b4[j];
+    v[4 * j + 0] = fmaf(fmaf(v[4 * j + 0], rstd, shift), ww.x, bb.x);
+    v[4 * j + 1] = fmaf(fmaf(v[4 * j + 1], rstd, shift), ww.y, bb.y);
+    v[4 * j + 2] = fmaf(fmaf(v[4 * j + 2], rstd, shift), ww.z, bb.z);
+    v[4 * j + 3] = fmaf(fmaf(v[4 * j + 3], rstd, shift), ww.w, bb.w);
+  }
+}
+
+// this thread's 64 columns of a row: fp16 image into the next A operand + the fp32 residual base (x + bias) back into TMEM
+__device__ __forceinline__ void store_half(const float (&v)[64], uint8_t* a_dst /* tile base + first chunk of this half + row * 16 */, uint32_t tmem_x,
+                                           const float* __restrict__ resid_bias) {
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
     *reinterpret_cast<uint4*>(a_dst + c * (TM * 16)) = make_uint4(pack_h2(v[c * 8], v[c * 8 + 1]), pack_h2(v[c * 8 + 2], v[c * 8 + 3]),
                                                                   pack_h2(v[c * 8 + 4], v[c * 8 + 5]), pack_h2(v[c * 8 + 6], v[c * 8 + 7]));
   const float4* r4 = reinterpret_cast<const float4*>(resid_bias);
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
+  for (int c = 0; c < 4; ++c) {
     uint32_t u[16];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -175,12 +185,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) reni_rows_fused_kernel(const P
   if (threadIdx.x == 0) {
     for (int i = 0; i < NSLOT; ++i) { mbar_init(bars + 8 * (B_WFULL + i), 1); mbar_init(bars + 8 * (B_WEMPTY + i), 1); }
     for (int t = 0; t < 2; ++t) {
-      mbar_init(bars + 8 * (B_AXREADY + t), 4);     // one arrival per producing warp (PE warps or the tile's epilogue warps)
-      mbar_init(bars + 8 * (B_AHREADY + t), 4);
+      mbar_init(bars + 8 * (B_AXREADY + t), 8);     // the tile's 8 epilogue warps arrive once each, the 4 encoding warps twice each
+      mbar_init(bars + 8 * (B_AHREADY + t), 8);
       mbar_init(bars + 8 * (B_ACCREADY + t), 1);    // tcgen05.commit
       mbar_init(bars + 8 * (B_AXFREE + t), 1);
       mbar_init(bars + 8 * (B_AHFREE + t), 1);
-      mbar_init(bars + 8 * (B_ACCFREE + t), 4);
+      mbar_init(bars + 8 * (B_ACCFREE + t), 8);
     }
     fence_barrier_init();
   }
@@ -284,7 +294,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) reni_rows_fused_kernel(const P
     //   cols 125 .. 127       = entries 3 q .. 3 q + 2 of [sin, sin4, cos, cos4, x](d_z) ++ [sin, sin4, cos, cos4, x](|d_xy|) ++ [0, 0]
     // so a thread loads the quarter's 25 (z_x, z_y) pairs up front (25 independent 8-byte loads in flight), and one input costs two
     // MUFU ops for its five columns.
-    reg_dec<88>();
     const int row = (warp - 4) * 32 + lane;
     uint32_t ph_ax[2] = {0, 0}, ph_ah[2] = {0, 0};
     long long t_pw = 0;
@@ -321,8 +330,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) reni_rows_fused_kernel(const P
           }
           // the buffer this quarter goes to must have been read by the MMAs that used it last
           const long long pc0 = RCLK();
-          if (q & 1) { mbar_wait(bars + 8 * (B_AHFREE + t), ph_ah[t] ^ 1u); ph_ah[t] ^= 1u; }
-          else { mbar_wait(bars + 8 * (B_AXFREE + t), ph_ax[t] ^ 1u); ph_ax[t] ^= 1u; }
+          if (q & 1) { mbar_wait_backoff(bars + 8 * (B_AHFREE + t), ph_ah[t] ^ 1u, 256); ph_ah[t] ^= 1u; }
+          else { mbar_wait_backoff(bars + 8 * (B_AXFREE + t), ph_ax[t] ^ 1u, 256); ph_ax[t] ^= 1u; }
           if (PROF) t_pw += RCLK() - pc0;
           uint8_t* dst = smem + OFF_A + t * (2 * TILE_BYTES) + ((q & 1) ? TILE_BYTES : 0) + row * 16;
 #pragma unroll
@@ -342,27 +351,36 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) reni_rows_fused_kernel(const P
           *reinterpret_cast<uint4*>(dst + 15 * (TM * 16)) = make_uint4(pack_h2(xj[20], xj[21]), pack_h2(xj[22], xj[23]), pack_h2(xj[24], ex[0]), pack_h2(ex[1], ex[2]));
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) mbar_arrive(bars + 8 * (((q & 1) ? B_AHREADY : B_AXREADY) + t));
+          if (lane == 0) { mbar_arrive(bars + 8 * (((q & 1) ? B_AHREADY : B_AXREADY) + t)); mbar_arrive(bars + 8 * (((q & 1) ? B_AHREADY : B_AXREADY) + t)); }
         }
       }
     }
     if (PROF && P.prof && row == 0) { P.prof[blockIdx.x * 16 + 6] = RCLK() - t_pbegin; P.prof[blockIdx.x * 16 + 7] = t_pw; }
   } else {
-    // ================================ epilogue (warps 8-11: tile 0, warps 12-15: tile 1) ================================
-    reg_inc<192>();
-    const int t = (warp - 8) >> 2;
+    // ================================ epilogue (warps 8-15: tile 0, warps 16-23: tile 1) ================================
+    // Two threads per row: warps e and e + 4 of a tile's group own the same TMEM lanes (lane quadrant = warp % 4) and split the 128
+    // columns.  With one thread per row (128 live registers, one epilogue warp per SM sub-partition and tile) the epilogue ran at an IPC
+    // of ~0.2 and was 2.5x longer than the MMAs it feeds (profiles/r02_reni_fused_phase_cycles.log).
+    reg_inc<88>();
+    const int e = warp - 8;
+    const int t = e >> 3, half = (e >> 2) & 1;
     const int row = (warp & 3) * 32 + lane;
     const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
-    const uint32_t tm_x = tmem + lane_off + (uint32_t)t * 256, tm_h = tm_x + 128;
-    uint8_t* ax = smem + OFF_A + t * (2 * TILE_BYTES) + row * 16;
+    const uint32_t tm_x = tmem + lane_off + (uint32_t)t * 256 + half * 64, tm_h = tm_x + 128;
+    uint8_t* ax = smem + OFF_A + t * (2 * TILE_BYTES) + (half * 8) * (TM * 16) + row * 16;      // this half's first 8-column chunk
     uint8_t* ah = ax + TILE_BYTES;
+    float4* xc = reinterpret_cast<float4*>(smem + OFF_XCHG);
+    float4* mine = xc + (t * 2 + half) * 128 + row;
+    const float4* theirs = xc + (t * 2 + (half ^ 1)) * 128 + row;
+    const int bar_id = 1 + t * 4 + (warp & 3);                                                  // the two warps sharing these 32 rows
+    const int co = half * 64;                                                                   // first column of this half
     const uint32_t bar_acc = bars + 8 * (B_ACCREADY + t), bar_ax = bars + 8 * (B_AXREADY + t), bar_ah = bars + 8 * (B_AHREADY + t);
     uint32_t ph_acc = 0;
     long long t_ew = 0;
     const long long t_ebegin = RCLK();
     auto wait_acc = [&]() {
       const long long c0 = RCLK();
-      mbar_wait(bar_acc, ph_acc); ph_acc ^= 1u;
+      mbar_wait_backoff(bar_acc, ph_acc); ph_acc ^= 1u;
       if (PROF) t_ew += RCLK() - c0;
       tc_fence_after();
     };
@@ -376,23 +394,23 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) reni_rows_fused_kernel(const P
       const int64_t grow_raw = pr * 256 + t * 128 + row;
       const int64_t grow = min(grow_raw, P.N - 1);
       const int k = P.row_cam ? __ldg(P.row_cam + grow) : 0;
-      const float* at = P.attn + (int64_t)k * (NLAYER * HID);
-      float v[128];
+      const float* at = P.attn + (int64_t)k * (NLAYER * HID) + co;
+      float v[64];
       // ---- first layer: x = LN1_0(W_r pe + b_r + a_0) ----
       wait_acc();
-      load_row128(tm_x, v);
-      add128(v, cb + CB_BR);
-      add128_ldg(v, at);
-      layernorm128(v, cb + CB_LAYER0 + CB_N1W, cb + CB_LAYER0 + CB_N1B);
-      store_row(v, ax, tm_x, cb + CB_LAYER0 + CB_F2B);
+      load_row64(tm_x, v);
+      add64(v, cb + CB_BR + co);
+      add64_ldg(v, at);
+      layernorm_half(v, cb + CB_LAYER0 + CB_N1W + co, cb + CB_LAYER0 + CB_N1B + co, mine, theirs, bar_id);
+      store_half(v, ax, tm_x, cb + CB_LAYER0 + CB_F2B + co);
       publish(bar_ax);
 #pragma unroll 1
       for (int i = 0; i < NLAYER; ++i) {
-        const float* cl = cb + CB_LAYER0 + i * CB_LAYER_STRIDE;
+        const float* cl = cb + CB_LAYER0 + i * CB_LAYER_STRIDE + co;
         // ---- h = relu(F0_i x + f0b_i) ----
         wait_acc();
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
+        for (int c = 0; c < 4; ++c) {
           uint32_t u[16];
           tmem_ld16(tm_h + c * 16, u);
           tmem_ld_wait();
@@ -410,18 +428,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) reni_rows_fused_kernel(const P
         publish(bar_ah);
         // ---- y = F2_i h + (x + f2b_i) (accumulated in TMEM);  x = LN2_i(y) ----
         wait_acc();
-        load_row128(tm_x, v);
+        load_row64(tm_x, v);
         if (i == NLAYER - 1) {        // X of this tile is free for the next pair's first layer
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bars + 8 * (B_ACCFREE + t));
         }
-        layernorm128(v, cl + CB_N2W, cl + CB_N2B);
+        layernorm_half(v, cl + CB_N2W, cl + CB_N2B, mine, theirs, bar_id);
         if (i + 1 < NLAYER) {
           const float* cn = cl + CB_LAYER_STRIDE;
-          add128_ldg(v, at + (i + 1) * HID);
-          layernorm128(v, cn + CB_N1W, cn + CB_N1B);
-          store_row(v, ax, tm_x, cn + CB_F2B);
+          add64_ldg(v, at + (i + 1) * HID);
+          layernorm_half(v, cn + CB_N1W, cn + CB_N1B, mine, theirs, bar_id);
+          store_half(v, ax, tm_x, cn + CB_F2B);
           publish(bar_ax);
         }
       }
@@ -429,26 +447,34 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) reni_rows_fused_kernel(const P
       float o[3];
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        float s4[4] = {cb[CB_BO + c], 0.f, 0.f, 0.f};
-        const float4* wo = reinterpret_cast<const float4*>(cb + CB_WO + c * 128);
+        float s4[4] = {0.f, 0.f, 0.f, 0.f};
+        const float4* wo = reinterpret_cast<const float4*>(cb + CB_WO + c * 128 + co);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
+        for (int j = 0; j < 16; ++j) {
           const float4 w = wo[j];
           s4[0] = fmaf(v[4 * j], w.x, s4[0]); s4[1] = fmaf(v[4 * j + 1], w.y, s4[1]); s4[2] = fmaf(v[4 * j + 2], w.z, s4[2]); s4[3] = fmaf(v[4 * j + 3], w.w, s4[3]);
         }
         o[c] = (s4[0] + s4[1]) + (s4[2] + s4[3]);
       }
-      if (P.scale) {
-        const float sc = expf(__ldg(P.scale + k));
+      if (half == 1) { mine->x = o[0]; mine->y = o[1]; mine->z = o[2]; }
+      asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+      if (half == 0) {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) o[c] = P.log_domain ? (o[c] + logf(sc)) : (o[c] * sc);
-      }
-      if (grow_raw < P.N) {
+        for (int c = 0; c < 3; ++c) o[c] += cb[CB_BO + c];
+        o[0] += theirs->x; o[1] += theirs->y; o[2] += theirs->z;
+        if (P.scale) {
+          const float sc = expf(__ldg(P.scale + k));
 #pragma unroll
-        for (int c = 0; c < 3; ++c) P.out[grow_raw * 3 + c] = P.log_domain == 1 ? expf(o[c]) : o[c];
+          for (int c = 0; c < 3; ++c) o[c] = P.log_domain ? (o[c] + logf(sc)) : (o[c] * sc);
+        }
+        if (grow_raw < P.N) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) P.out[grow_raw * 3 + c] = P.log_domain == 1 ? expf(o[c]) : o[c];
+        }
       }
+      asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");     // the partner has read the head partials before the next pair reuses the slot
     }
-    if (PROF && P.prof && row == 0) { P.prof[blockIdx.x * 16 + 8 + 2 * t] = RCLK() - t_ebegin; P.prof[blockIdx.x * 16 + 9 + 2 * t] = t_ew; }
+    if (PROF && P.prof && row == 0 && half == 0) { P.prof[blockIdx.x * 16 + 8 + 2 * t] = RCLK() - t_ebegin; P.prof[blockIdx.x * 16 + 9 + 2 * t] = t_ew; }
   }
 #undef RCLK
 

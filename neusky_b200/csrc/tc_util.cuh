@@ -48,6 +48,19 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// Same, for warps that expect to wait long (epilogue warps waiting for an accumulator): sleep between polls so that the polling
+// loop does not take issue slots from the warps doing the work on the same SM sub-partition.
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity, uint32_t ns = 64) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(ns);
+    if (++spins > NSK_MBAR_SPIN_LIMIT) {
+      printf("nsk: mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+
 // generic-proxy writes to shared memory -> visible to the async proxy (tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 

@@ -34,7 +34,11 @@ class SkyShader:
         self.set_ddf_weights(ddf_params)
         self.reni_blob = packing.pack_reni(reni_params, device=self.device) if reni_params is not None else None
         self.reni_gemm = packing.pack_reni_gemm(reni_params, device=self.device) if reni_params is not None else None
-        self.reni_tc_min_rows = 8192    # below this the fp32 SIMT decode wins (one launch instead of ~30)
+        self.reni_fused = packing.pack_reni_fused(reni_params, device=self.device) if (reni_params is not None and reni_params["network.residual_projection.weight"].shape[1] == 510) else None
+        self.reni_tc_min_rows = 8192    # below this the fp32 SIMT decode wins (one launch, exact fp32)
+        # frame-sized row batches: "fused" = one tcgen05 kernel, fp16 operands (radiance within 7e-4 relative of fp32, measured: mean 1e-4);
+        # "3xtf32" = the layer-wise fp32-accurate GEMM chain (6x slower)
+        self.reni_rows_impl = "fused" if self.reni_fused is not None else "3xtf32"
         # visibility sigmoid: bias and scale.  Defaults = the values the method config trains towards / fixes (target_min_bias 0.1,
         # target_max_scale 25: neusky_config.py:122-123); a model passes its learnable `visibility_threshold` (initialised to
         # 2 * ddf_radius, neusky_model.py:234) explicitly or sets these attributes from the checkpoint
@@ -81,6 +85,8 @@ class SkyShader:
         """HDR radiance [N,3] along N directions for ONE latent code [1,L,3] (per-ray background, neusky_model.py:535-549): the
         tensor-core GEMM chain for frame-sized batches, the fp32 SIMT decode for small ones."""
         if ray_directions.shape[0] >= self.reni_tc_min_rows:
+            if self.reni_rows_impl == "fused":
+                return ops.reni_rows_fused(ray_directions, latents, scale, self.reni_blob, self.reni_fused, rotation)
             return ops.reni_rows_tc(ray_directions, latents, scale, self.reni_blob, self.reni_gemm, rotation)
         return ops.reni_radiance_table(ray_directions, latents, scale, self.reni_blob, rotation)[0]
 
@@ -223,6 +229,8 @@ class RayRenderer:
         """Per-ray background radiance of a MIXED-camera batch: ray n is decoded with latent code cam[n] (neusky_model.py:535-549)."""
         sh = self.shader
         if ray_directions.shape[0] >= sh.reni_tc_min_rows:
+            if sh.reni_rows_impl == "fused":
+                return ops.reni_rows_fused(ray_directions, latents, scale, sh.reni_blob, sh.reni_fused, rotation, row_cam=cam)
             return ops.reni_rows_tc(ray_directions, latents, scale, sh.reni_blob, sh.reni_gemm, rotation, row_cam=cam)
         return ops.reni_radiance_rows(ray_directions, cam, latents, scale, sh.reni_blob, rotation)
 
