@@ -333,27 +333,34 @@ def relight_arm(args, ctx):
     for a, b in tiles:
         offs.append(offs[-1] + (b - a))
     mm = global_steps_minmax(o, d, S)
+    compact = not args.per_sample_cache and not args.fp32_cache
     if tiles:      # untimed warm-up of the render path (allocator, lazy kernel attributes) so that cache_build_s is a steady-state figure
         a, b = tiles[0]
         r.render(o[a:b].contiguous(), d[a:b].contiguous(), dn[a:b].contiguous(), S, Z0[0], sc[0], steps_minmax=mm, want_cache=True,
-                 collapse_cache=not args.per_sample_cache)
+                 collapse_cache=not args.per_sample_cache, compact_cache=compact)
         torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     caches = []
     for a, b in tiles:
         out = r.render(o[a:b].contiguous(), d[a:b].contiguous(), dn[a:b].contiguous(), S, Z0[0], sc[0], steps_minmax=mm, want_cache=True,
-                       collapse_cache=not args.per_sample_cache)
-        c = out["relight_cache"]
-        # keep what a new illumination needs; collapse nothing (parity with a full re-render is tested in tests/test_gpu_render.py)
-        caches.append(c)
+                       collapse_cache=not args.per_sample_cache, compact_cache=compact)
+        caches.append(out["relight_cache"])
+    del out
+    if compact and caches:
+        frame_cache = r.merge_caches(caches)      # one cache for this rank's rays: a sweep is a handful of launches, not one set per tile
+        caches = [frame_cache]
     e1.record()
     torch.cuda.synchronize()
     build_s = e0.elapsed_time(e1) / 1e3
-    cache_bytes = sum(sum(v.numel() * v.element_size() for v in c.values()) for c in caches)
+    cache_bytes = sum(sum(v.numel() * v.element_size() for v in c.values() if torch.is_tensor(v)) for c in caches)
+
+    sc_all = torch.zeros(NL, device=dev)
 
     def sweep():
         last = None
+        if compact:
+            return r.relight_sweep(caches[0], codes, sc_all) if caches else None
         if args.per_sample_cache:
             for k in range(NL):
                 rad, bg = r.illumination_for(codes[k], sc[0], my_dirs)          # two RENI++ decodes per latent, not per tile
@@ -381,6 +388,12 @@ def relight_arm(args, ctx):
         torch.cuda.synchronize()
         ts.append(s0.elapsed_time(s1) / 1e3)
     t = sum(ts)
+    stages = None
+    if compact and caches:      # one more sweep with per-stage CUDA events: where a latent code's time goes
+        r.sweep_events = {}
+        sweep(); torch.cuda.synchronize()
+        stages = {k: sum(a.elapsed_time(b) for a, b in v) / NL for k, v in r.sweep_events.items()}
+        r.sweep_events = None
     if dist is not None:
         tt = torch.tensor([t, build_s], device=dev, dtype=torch.float64); dist.all_reduce(tt, op=dist.ReduceOp.MAX); t, build_s = (float(x) for x in tt)
     line = None
@@ -391,14 +404,20 @@ def relight_arm(args, ctx):
         Dp = int(r.shader.mask.sum())
         per_ray = (S * 28 + Dp * 4) if args.per_sample_cache else 642 * 12
         algo = n * (per_ray + 16 + 12) * NL * args.steps
+        if compact:      # compact cache: 6 DP + 4 bytes per hit ray and pass of four codes; 12 B direction + 12 B result per ray and code
+            hit = float(caches[0]["rows"].shape[0]) if caches else 0.0
+            algo = (hit * world * (6 * 648 + 4) * ((NL + 3) // 4) + n * 24.0 * NL) * args.steps
         line = ({"metric": "relit rays/s (fixed geometry, new RENI++ latent code per pass)", "value": n * NL * args.steps / t, "unit": UNIT, "n_gpus": world,
                           "steps": args.steps, "warmup": max(1, args.warmup // 3), "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "strong",
                           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                           "config": {"workload": f"BASELINE.json configs[4]: relighting sweep, {W}x{H} frame, {S} samples/ray, {NL} latent codes per step, "
                                                  f"642 icosphere directions (D'={Dp} cached visibilities per ray), tiles of {args.tile} rays over {world} GPU(s)",
                                      "parallelism": f"ray tiles x{world}, weights replicated, no collective", "l2": f"relight cache {cache_bytes / 2**30:.2f} GiB per rank exceeds L2",
-                                     "cache_build_s": build_s, "ms_per_latent_frame": 1e3 * t / args.steps / NL},
-                          "roofline": {"kernel": "lambert_relight_kernel" if args.per_sample_cache else "relight_collapsed_kernel", "bound": "hbm", "achieved": algo / t / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                     "cache_build_s": build_s, "ms_per_latent_frame": 1e3 * t / args.steps / NL,
+                                     "ms_per_latent_by_stage": stages, "background_rows": int(caches[0]["bg_rows"].shape[0]) if (compact and caches) else None,
+                                     "cache_rows": int(caches[0]["rows"].shape[0]) if (compact and caches) else None},
+                          "cache_format": "compact: fp16 channel-planar rows for hit rays + per-row scale" if compact else ("per-sample fp32" if args.per_sample_cache else "collapsed fp32 [R,D,3]"),
+                          "roofline": {"kernel": "lambert_relight_kernel" if args.per_sample_cache else ("relight_h16_kernel" if compact else "relight_collapsed_kernel"), "bound": "hbm", "achieved": algo / t / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                        "frac": algo / t / 1e9 / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
                                        "note": "whole-sweep rate over the cache bytes: includes the RENI++ decodes of the direction set and of the per-ray background"},
                           "gpu_launches": _lib.launches - l0})
@@ -622,6 +641,7 @@ def main():
     ap.add_argument("--sampler", default="uniform", choices=["uniform", "proposal"], help="eval: sample placement (proposal = shipped NeuS-facto default, use --samples 48)")
     ap.add_argument("--latents", type=int, default=64, help="relight: latent codes per sweep")
     ap.add_argument("--per-sample-cache", action="store_true", help="relight: keep the per-sample cache instead of the collapsed [R,D,3] coefficients")
+    ap.add_argument("--fp32-cache", action="store_true", help="relight: the round-1 collapsed fp32 [R,D,3] cache instead of the compact fp16 one")
     ap.add_argument("--rays", type=int, default=1024, help="train: rays per GPU")
     ap.add_argument("--train-samples", type=int, default=48)
     ap.add_argument("--split", type=int, default=3, choices=[1, 3], help="train: 1 = tf32 GEMMs, 3 = 3xTF32 (fp32-accurate)")

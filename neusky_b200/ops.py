@@ -518,6 +518,33 @@ def relight_collapsed_multi(H: Tensor, radiance: Tensor) -> Tensor:
     return out
 
 
+def relight_pack_h16(H: Tensor, rows: Tensor) -> Tuple[Tensor, Tensor]:
+    """H [R,D,3] fp32 coefficients + rows [Rs] int32 (the rays that own a cache row) -> (H16 [Rs, 3*DP] fp16 channel-planar rows
+    normalised by their maximum, hscale [Rs]): the compact relighting cache (csrc/relight_compact.cu)."""
+    R, D = H.shape[0], H.shape[1]
+    H = _chk("H", H, shape=(R, D, 3))
+    rows = _chk("rows", rows, dtype=torch.int32, shape=(None,))
+    Rs, DP = rows.shape[0], (D + 7) // 8 * 8
+    H16 = torch.empty((Rs, 3 * DP), device=H.device, dtype=torch.float16)
+    hscale = torch.empty((Rs,), device=H.device, dtype=torch.float32)
+    _lib.check(_lib.load().nsk_relight_pack_h16(_ptr(H), _ptr(rows), c_int64(Rs), c_int(D), _ptr(H16), _ptr(hscale), _stream(H)), "nsk_relight_pack_h16")
+    return H16, hscale
+
+
+def relight_h16_multi(H16: Tensor, hscale: Tensor, rows: Tensor, R: int, D: int, radiance: Tensor) -> Tensor:
+    """Compact cache + radiance [NL,D,3] -> linear rgb [NL,R,3] (zero for rays without a cache row), four illuminations per pass."""
+    Rs, DP = rows.shape[0], (D + 7) // 8 * 8
+    H16 = _chk("H16", H16, dtype=torch.float16, shape=(Rs, 3 * DP))
+    hscale = _chk("hscale", hscale, shape=(Rs,))
+    rows = _chk("rows", rows, dtype=torch.int32, shape=(Rs,))
+    radiance = _chk("radiance", radiance, shape=(None, D, 3))
+    NL = radiance.shape[0]
+    out = torch.empty((NL, R, 3), device=radiance.device, dtype=torch.float32)
+    _lib.check(_lib.load().nsk_relight_h16_multi(_ptr(H16), _ptr(hscale), _ptr(rows), c_int64(Rs), c_int64(R), c_int(D), _ptr(radiance), c_int(NL), _ptr(out),
+                                                 _stream(radiance)), "nsk_relight_h16_multi")
+    return out
+
+
 def lambert_relight_bwd(normals, wa, inv_count, dirs, sel_index, radiance, vis_sel, g_rgb_lin, cam=None, unoccluded_vis: float = 1.0, want_vis: bool = True, want_radiance: bool = True):
     """-> (d_wa [R,S,3], d_normals [R,S,3], d_vis_sel [R,Dp] | None, d_radiance [K,D,3] | None)."""
     R, S = normals.shape[0], normals.shape[1]

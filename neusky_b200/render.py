@@ -213,6 +213,7 @@ class RayRenderer:
         self.shader = SkyShader(ddf_params, reni_params, device=device, ddf_radius=ddf_radius, log2_T=log2_T if ddf_log2_T is None else ddf_log2_T,
                                 num_levels=num_levels, impl=impl)
         self.scalings = self.shader.scalings
+        self.sweep_events = None
         self.sdf_table = sdf_params["encoding.hash_table"].to(self.device, torch.float32).contiguous()
         self.set_sdf_weights(sdf_params)
 
@@ -239,7 +240,7 @@ class RayRenderer:
                threshold: Optional[float] = None, sigmoid_scale: Optional[float] = None, cos_anneal_ratio: float = 1.0, want_vis: bool = False,
                steps_minmax: Optional[Tensor] = None, want_cache: bool = False, collapse_cache: bool = False,
                radiance: Optional[Tensor] = None, background: Optional[Tensor] = None, cam: Optional[Tensor] = None,
-               want_visibility_batch: bool = False, want_prop_depth: bool = False) -> Dict[str, Tensor]:
+               want_visibility_batch: bool = False, want_prop_depth: bool = False, compact_cache: bool = False) -> Dict[str, Tensor]:
         """origins/directions [R,3], dnorm [R,1].  One camera: latent [L,3], scale scalar tensor.  Mixed-camera batch (what
         torch.unique(camera_indices) handles in the reference, neusky_model.py:461): latent [K,L,3], scale [K] and `cam` [R]
         int32 = the latent row of every ray.
@@ -308,7 +309,15 @@ class RayRenderer:
                 # per ray, independent of S; a new illumination is one streaming pass over it
                 # G over ALL directions (block-per-ray kernel), then fold the per-ray visibility in (lower hemisphere = lower_vis)
                 H = ops.lambert_collapse_sel(c["normals"], c["wa"], s["inv_count"], sh.dirs) * s["visibility"][:, :, None]
-                out["relight_cache"] = {"H": H, "accumulation": c["accumulation"], "directions": directions}
+                if compact_cache:
+                    # compact form: fp16 rows only for rays that hit something, per-row scale; background rows only where 1 - accumulation > 0
+                    acc = c["accumulation"]
+                    rows = torch.nonzero(acc > 0).reshape(-1).to(torch.int32)
+                    H16, hscale = ops.relight_pack_h16(H, rows)
+                    out["relight_cache"] = {"H16": H16, "hscale": hscale, "rows": rows, "bg_rows": torch.nonzero(acc < 1).reshape(-1).to(torch.int32),
+                                            "accumulation": acc, "directions": directions, "n_dirs": sh.dirs.shape[0]}
+                else:
+                    out["relight_cache"] = {"H": H, "accumulation": c["accumulation"], "directions": directions}
             else:
                 out["relight_cache"] = {"normals": c["normals"], "wa": c["wa"], "inv_count": s["inv_count"], "visibility_sel": s["visibility_sel"],
                                         "accumulation": c["accumulation"], "directions": directions}
@@ -361,7 +370,9 @@ class RayRenderer:
             if background is None:
                 background = sh.radiance_rows(cache["directions"], Z, sc, rotation)
         bg = background
-        if "H" in cache:
+        if "H16" in cache:
+            lin = ops.relight_h16_multi(cache["H16"], cache["hscale"], cache["rows"], cache["accumulation"].shape[0], cache["n_dirs"], radiance)[0]
+        elif "H" in cache:
             lin = ops.relight_collapsed(cache["H"], radiance)
         else:
             lin = ops.lambert_relight(cache["normals"], cache["wa"], cache["inv_count"], sh.dirs, sh.sel_index, radiance, cache["visibility_sel"], None, sh.lower_vis)
@@ -371,12 +382,74 @@ class RayRenderer:
     def relight_many(self, cache: Dict[str, Tensor], radiance: Tensor, background: Tensor) -> Tensor:
         """sRGB [NL,R,3] of the cached rays (collapsed cache) under NL illuminations at once: radiance [NL,D,3] and background [NL,R,3]
         from `illumination_for`, one pass over the cache per four illuminations."""
-        if "H" not in cache:
+        if "H" not in cache and "H16" not in cache:
             raise ValueError("relight_many needs the collapsed cache (render(..., want_cache=True, collapse_cache=True))")
-        NL, R = radiance.shape[0], cache["H"].shape[0]
-        lin = ops.relight_collapsed_multi(cache["H"], radiance)
+        NL, R = radiance.shape[0], cache["accumulation"].shape[0]
+        if "H16" in cache:
+            lin = ops.relight_h16_multi(cache["H16"], cache["hscale"], cache["rows"], R, cache["n_dirs"], radiance)
+        else:
+            lin = ops.relight_collapsed_multi(cache["H"], radiance)
         rgb = ops.shade_finalize(lin.reshape(NL * R, 3), background.reshape(NL * R, 3).contiguous(), cache["accumulation"].repeat(NL))
         return rgb.reshape(NL, R, 3)
+
+    @staticmethod
+    def merge_caches(caches: Sequence[Dict[str, Tensor]]) -> Dict[str, Tensor]:
+        """Compact caches of consecutive ray tiles -> one cache of the whole bundle (row indices shifted by the tile offsets), so that
+        a sweep over a frame is a handful of launches instead of one set per tile."""
+        if not caches or "H16" not in caches[0]:
+            raise ValueError("merge_caches takes compact caches (render(..., want_cache=True, collapse_cache=True, compact_cache=True))")
+        off, rows, bg = 0, [], []
+        for c in caches:
+            rows.append(c["rows"] + off)
+            bg.append(c["bg_rows"] + off)
+            off += c["accumulation"].shape[0]
+        return {"H16": torch.cat([c["H16"] for c in caches], 0), "hscale": torch.cat([c["hscale"] for c in caches], 0), "rows": torch.cat(rows, 0),
+                "bg_rows": torch.cat(bg, 0), "accumulation": torch.cat([c["accumulation"] for c in caches], 0),
+                "directions": torch.cat([c["directions"] for c in caches], 0), "n_dirs": caches[0]["n_dirs"]}
+
+    @torch.no_grad()
+    def relight_sweep(self, cache: Dict[str, Tensor], latents: Tensor, scales: Tensor, rotation: Optional[Tensor] = None, group: int = 8) -> Tensor:
+        """sRGB [NL, R, 3] of the cached rays (compact cache) under NL latent codes [NL, L, 3] / scales [NL] (BASELINE.json configs[4]).
+        Per group of latent codes: ONE RENI++ table decode, ONE fused row decode of the background of the rays whose
+        1 - accumulation is not zero (every other ray gets no background: it is multiplied by 0), one streaming pass over the cache
+        per four codes, one finalize -- no per-tile, per-code Python loop."""
+        if "H16" not in cache:
+            raise ValueError("relight_sweep takes the compact cache")
+        sh = self.shader
+        NL, R = latents.shape[0], cache["accumulation"].shape[0]
+        Z = latents.to(self.device, torch.float32).contiguous()
+        sc = scales.reshape(-1).to(self.device, torch.float32).contiguous()
+        bg_rows = cache["bg_rows"].long()
+        Nb = bg_rows.shape[0]
+        dirs_b = cache["directions"][bg_rows].contiguous()
+        out = torch.empty((NL, R, 3), device=self.device, dtype=torch.float32)
+        ev = self.sweep_events          # bench hook: when a dict, CUDA-event pairs per stage ("table", "pass", "background", "finalize")
+
+        def timed(name, fn):
+            if ev is None:
+                return fn()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); r_ = fn(); e1.record()
+            ev.setdefault(name, []).append((e0, e1))
+            return r_
+
+        all_rows = Nb == R
+        for a in range(0, NL, group):
+            b = min(NL, a + group)
+            g = b - a
+            rad = timed("table", lambda: sh.radiance_table(Z[a:b], sc[a:b], rotation))                                # [g, D, 3]
+            lin = timed("pass", lambda: ops.relight_h16_multi(cache["H16"], cache["hscale"], cache["rows"], R, cache["n_dirs"], rad))      # [g, R, 3]
+            if Nb:
+                row_cam = torch.arange(g, device=self.device, dtype=torch.int32).repeat_interleave(Nb)
+                rows_rad = timed("background", lambda: self.radiance_rows_cam(dirs_b.repeat(g, 1), row_cam, Z[a:b], sc[a:b], rotation))    # [g * Nb, 3]
+            if all_rows:
+                bg = rows_rad.reshape(g, R, 3)
+            else:
+                bg = torch.zeros((g, R, 3), device=self.device, dtype=torch.float32)
+                if Nb:
+                    bg[:, bg_rows] = rows_rad.reshape(g, Nb, 3)
+            out[a:b] = timed("finalize", lambda: ops.shade_finalize(lin.reshape(g * R, 3), bg.reshape(g * R, 3), cache["accumulation"].repeat(g))).reshape(g, R, 3)
+        return out
 
     @torch.no_grad()
     def illumination_for(self, latent: Tensor, scale: Tensor, ray_directions: Tensor, rotation: Optional[Tensor] = None):

@@ -1,6 +1,7 @@
 #!/bin/bash
-mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/r2g_pytest_gpu.log 2>&1; echo "pytest exit=$?"; tail -3 gpurun_out/r2g_pytest_gpu.log | cut -c1-300
-timeout 600 python bench.py --workload train --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/r2g_bench_train.json 2> gpurun_out/r2g_train.err; echo "train exit=$?"; cut -c1-300 gpurun_out/r2g_bench_train.json; tail -3 gpurun_out/r2g_train.err
-timeout 600 python bench.py --workload train --steps 5 --warmup 3 --no-cpu-baseline --no-ddf-fit > gpurun_out/r2g_bench_train_nofit.json 2> gpurun_out/r2g_train2.err; echo "train exit=$?"; cut -c1-300 gpurun_out/r2g_bench_train_nofit.json
-timeout 300 python scripts/gemm_bench.py > gpurun_out/r2g_gemm_bench.jsonl 2> /dev/null
+cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
+mkdir -p gpurun_out; rm -f gpurun_out/test_errors.jsonl
+timeout 600 python -m pytest tests/test_gpu_fullsize_frame.py tests/test_gpu_render.py -m gpu -q --timeout 600 > gpurun_out/r2g_pytest.log 2>&1; echo "pytest rc=$?"
+grep -E "passed|failed|FAILED|ERROR|^E  " gpurun_out/r2g_pytest.log | head -30
+cat gpurun_out/test_errors.jsonl | grep config5
+timeout 600 python bench.py --workload relight --steps 2 --warmup 3 > gpurun_out/r2g_relight.json 2> gpurun_out/r2g_relight.err; tail -c 1700 gpurun_out/r2g_relight.json; tail -3 gpurun_out/r2g_relight.err

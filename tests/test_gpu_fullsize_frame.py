@@ -109,6 +109,32 @@ def test_config5_relight_full_frame_vs_oracle_sample(frame, dev):
         log_err(f"config5_relight_full[{k}]", rgb=e)
         assert e <= 5e-4, (k, e)
         assert float((ref["rgb"] - frame["ref0"]["rgb"]).abs().max()) > 1e-2 if "ref0" in frame else True   # the illumination really changed
+    # the COMPACT cache (fp16 rows for hit rays only, background decoded only where 1 - accumulation > 0) through relight_sweep: one call
+    # for all codes; against the oracle sample, and against the fp32 cache on every ray of the frame
+    compact = []
+    Z0, mm = frame["Z"].to(dev), frame["mm"]
+    for a in range(0, H * W, tile):
+        sl = slice(a, a + tile)
+        out = r.render(frame["o"][sl].contiguous(), frame["d"][sl].contiguous(), frame["dn"][sl].contiguous(), S, Z0, sc, steps_minmax=mm,
+                       want_cache=True, collapse_cache=True, compact_cache=True)
+        compact.append(out["relight_cache"])
+    cc = r.merge_caches(compact)
+    n_hit = int(cc["rows"].shape[0])
+    # rays with accumulation EXACTLY 0 own no row; this random-init scene (inv_s = e^3) leaves ~1e-2 of accumulation on sky rays, so every
+    # ray keeps its row here -- a trained scene (inv_s ~ 1e3) drops its sky
+    assert 0 < n_hit <= H * W and cc["H16"].shape == (n_hit, 3 * 648) and cc["H16"].dtype == torch.float16
+    full_bytes = sum(c["H"].numel() * 4 for c in frame["caches"])
+    comp_bytes = cc["H16"].numel() * 2 + cc["hscale"].numel() * 4 + cc["rows"].numel() * 4
+    assert comp_bytes < 0.52 * full_bytes
+    sweep = r.relight_sweep(cc, codes.to(dev), torch.zeros(3, device=dev))
+    assert sweep.shape == (3, H * W, 3)
+    ref1 = _oracle(frame, codes[1])
+    e = float((sweep[1][idx].cpu() - ref1["rgb"]).abs().max())
+    rad, bg = r.illumination_for(codes[1].to(dev), sc, frame["d"])
+    fp32 = torch.cat([r.relight(c, codes[1].to(dev), sc, radiance=rad, background=bg[i * tile:(i + 1) * tile]) for i, c in enumerate(frame["caches"])], 0)
+    e_all = float((sweep[1] - fp32).abs().max())
+    log_err("config5_compact_cache", rgb_vs_oracle=e, rgb_vs_fp32_cache_all_rays=e_all, bytes_ratio=comp_bytes / full_bytes)
+    assert e <= 5e-4 and e_all <= 5e-4, (e, e_all)
     # four codes per pass over the cache == one by one
     ill = [r.illumination_for(codes[i % 3].to(dev), sc, frame["d"][:tile].contiguous()) for i in range(4)]
     many = r.relight_many(frame["caches"][0], torch.cat([a for a, _ in ill], 0), torch.stack([b for _, b in ill], 0))
