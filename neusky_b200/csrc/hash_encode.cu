@@ -62,27 +62,50 @@ hash_encode_fwd_kernel(const float* __restrict__ x, int64_t n, const float2* __r
   }
 }
 
+// Backward (scatter): thread = point, a warp = 32 consecutive points walking the levels together, so all in-flight
+// reductions of a warp land in one level's table slice (coarse levels: a handful of L2 lines).  Each thread reads its
+// own contiguous 8 L-byte gradient row exactly once (16-byte loads, every fetched sector fully used) and x once.
+// The first version ran one thread per (point, level) with the level in blockIdx.y: every level re-read a 32-byte
+// sector of grad_out for 8 useful bytes, 18 GB of DRAM reads per 7.9 M points (profiles/r02_ncu_hbm_kernels_summary.txt).
 __global__ void __launch_bounds__(256)
 hash_encode_bwd_kernel(const float* __restrict__ x, int64_t n, const float* __restrict__ scalings, int L,
                        int log2_T, const float* __restrict__ grad_out, float* __restrict__ grad_table) {
-  // one thread per (point, level); d out / d table[corner] = trilinear weight of that corner
+  __shared__ float s_scale[HE_MAX_LEVELS];
+  if (threadIdx.x < L) s_scale[threadIdx.x] = scalings[threadIdx.x];
+  __syncthreads();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int lev = blockIdx.y;
   if (i >= n) return;
   const uint32_t mask = (1u << log2_T) - 1u;
-  const float s = scalings[lev];
-  uint32_t idx[8];
-  float ox, oy, oz;
-  hash_corners(__fmul_rn(x[i * 3], s), __fmul_rn(x[i * 3 + 1], s), __fmul_rn(x[i * 3 + 2], s), mask, idx, ox, oy, oz);
-  const float gx = grad_out[i * 2 * L + 2 * lev], gy = grad_out[i * 2 * L + 2 * lev + 1];
-  const float wx[2] = {ox, 1.f - ox}, wy[2] = {oy, 1.f - oy}, wz[2] = {oz, 1.f - oz};
+  const float px = x[i * 3], py = x[i * 3 + 1], pz = x[i * 3 + 2];
+  const float* grow = grad_out + i * 2 * L;
   // corner c uses (x: c or f, y: c or f, z: c or f) -> weight index 0 for "c" (offset), 1 for "f"
   const int ux[8] = {0, 0, 1, 1, 0, 0, 1, 1}, uy[8] = {0, 1, 1, 0, 0, 1, 1, 0}, uz[8] = {0, 0, 0, 0, 1, 1, 1, 1};
-  float2* tl = reinterpret_cast<float2*>(grad_table) + ((size_t)lev << log2_T);
+  auto scatter = [&](int lev, float gx, float gy) {
+    const float s = s_scale[lev];
+    uint32_t idx[8];
+    float ox, oy, oz;
+    hash_corners(__fmul_rn(px, s), __fmul_rn(py, s), __fmul_rn(pz, s), mask, idx, ox, oy, oz);
+    const float wx[2] = {ox, 1.f - ox}, wy[2] = {oy, 1.f - oy}, wz[2] = {oz, 1.f - oz};
+    float2* tl = reinterpret_cast<float2*>(grad_table) + ((size_t)lev << log2_T);
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    const float w = wx[ux[c]] * wy[uy[c]] * wz[uz[c]];
-    atomicAdd(tl + idx[c], make_float2(w * gx, w * gy));
+    for (int c = 0; c < 8; ++c) {
+      const float w = wx[ux[c]] * wy[uy[c]] * wz[uz[c]];
+      atomicAdd(tl + idx[c], make_float2(w * gx, w * gy));
+    }
+  };
+  if ((L & 1) == 0) {
+    // rows are 8 L bytes: 16-byte aligned when L is even
+#pragma unroll 2
+    for (int lev = 0; lev < L; lev += 2) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(grow) + (lev >> 1));
+      scatter(lev, g.x, g.y);
+      scatter(lev + 1, g.z, g.w);
+    }
+  } else {
+    for (int lev = 0; lev < L; ++lev) {
+      const float2 g = __ldg(reinterpret_cast<const float2*>(grow) + lev);
+      scatter(lev, g.x, g.y);
+    }
   }
 }
 
@@ -150,29 +173,51 @@ __global__ void __launch_bounds__(256)
 hash_encode_grad_x_bwd_kernel(const float* __restrict__ x, int64_t n, const float2* __restrict__ table, const float* __restrict__ scalings,
                               int L, int log2_T, const float* __restrict__ g, const float* __restrict__ cx, float* __restrict__ d_g,
                               float* __restrict__ d_table) {
+  // thread = point walking the levels (see hash_encode_bwd_kernel): the g / d_g rows are read / written once, contiguously
+  __shared__ float s_scale[HE_MAX_LEVELS];
+  if (threadIdx.x < L) s_scale[threadIdx.x] = scalings[threadIdx.x];
+  __syncthreads();
   const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int lev = blockIdx.y;
   if (p >= n) return;
   const uint32_t mask = (1u << log2_T) - 1u;
-  const float s = scalings[lev];
-  uint32_t idx[8];
-  float ox, oy, oz;
-  hash_corners(__fmul_rn(x[p * 3], s), __fmul_rn(x[p * 3 + 1], s), __fmul_rn(x[p * 3 + 2], s), mask, idx, ox, oy, oz);
-  float cf[3][8];
-  interp_grad_coefs(ox, oy, oz, cf);
+  const float px = x[p * 3], py = x[p * 3 + 1], pz = x[p * 3 + 2];
   const float c0 = cx[p * 3], c1 = cx[p * 3 + 1], c2 = cx[p * 3 + 2];
-  const float ga = g[p * 2 * L + 2 * lev], gb = g[p * 2 * L + 2 * lev + 1];
-  const float2* tl = table + ((size_t)lev << log2_T);
-  float2* dtl = reinterpret_cast<float2*>(d_table) + ((size_t)lev << log2_T);
-  float ja = 0.f, jb = 0.f;
+  auto level = [&](int lev, float ga, float gb, float& ja, float& jb) {
+    const float s = s_scale[lev];
+    uint32_t idx[8];
+    float ox, oy, oz;
+    hash_corners(__fmul_rn(px, s), __fmul_rn(py, s), __fmul_rn(pz, s), mask, idx, ox, oy, oz);
+    float cf[3][8];
+    interp_grad_coefs(ox, oy, oz, cf);
+    const float2* tl = table + ((size_t)lev << log2_T);
+    float2* dtl = reinterpret_cast<float2*>(d_table) + ((size_t)lev << log2_T);
+    ja = 0.f; jb = 0.f;
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    const float k = s * (c0 * cf[0][c] + c1 * cf[1][c] + c2 * cf[2][c]);
-    const float2 v = __ldg(tl + idx[c]);
-    ja = fmaf(k, v.x, ja); jb = fmaf(k, v.y, jb);
-    if (d_table) atomicAdd(dtl + idx[c], make_float2(k * ga, k * gb));
+    for (int c = 0; c < 8; ++c) {
+      const float k = s * (c0 * cf[0][c] + c1 * cf[1][c] + c2 * cf[2][c]);
+      const float2 v = __ldg(tl + idx[c]);
+      ja = fmaf(k, v.x, ja); jb = fmaf(k, v.y, jb);
+      if (d_table) atomicAdd(dtl + idx[c], make_float2(k * ga, k * gb));
+    }
+  };
+  const float* grow = g + p * 2 * L;
+  float* drow = d_g ? d_g + p * 2 * L : nullptr;
+  if ((L & 1) == 0) {
+    for (int lev = 0; lev < L; lev += 2) {
+      const float4 gg = __ldg(reinterpret_cast<const float4*>(grow) + (lev >> 1));
+      float4 j;
+      level(lev, gg.x, gg.y, j.x, j.y);
+      level(lev + 1, gg.z, gg.w, j.z, j.w);
+      if (drow) reinterpret_cast<float4*>(drow)[lev >> 1] = j;
+    }
+  } else {
+    for (int lev = 0; lev < L; ++lev) {
+      const float2 gg = __ldg(reinterpret_cast<const float2*>(grow) + lev);
+      float2 j;
+      level(lev, gg.x, gg.y, j.x, j.y);
+      if (drow) reinterpret_cast<float2*>(drow)[lev] = j;
+    }
   }
-  if (d_g) { d_g[p * 2 * L + 2 * lev] = ja; d_g[p * 2 * L + 2 * lev + 1] = jb; }
 }
 
 // ---- tcnn ("tiny-cuda-nn") grid semantics ---------------------------------------------------------------------------
@@ -234,7 +279,7 @@ extern "C" int nsk_hash_encode_grad_x_bwd(const float* x, int64_t n, const float
   NSK_REQUIRE(num_levels >= 1 && num_levels <= nsk::HE_MAX_LEVELS, "nsk_hash_encode_grad_x_bwd: num_levels out of range");
   if (n == 0) return 0;
   NSK_REQUIRE(x && table && scalings && grad_out && cot_x && (d_grad_out || d_table), "nsk_hash_encode_grad_x_bwd: null pointer");
-  dim3 grid((unsigned)((n + 255) / 256), num_levels);
+  const unsigned grid = (unsigned)((n + 255) / 256);
   nsk::hash_encode_grad_x_bwd_kernel<<<grid, 256, 0, nsk::as_stream(stream)>>>(x, n, reinterpret_cast<const float2*>(table), scalings,
                                                                               num_levels, log2_T, grad_out, cot_x, d_grad_out, d_table);
   return nsk::check_launch("hash_encode_grad_x_bwd_kernel");
@@ -259,7 +304,7 @@ extern "C" int nsk_hash_encode_bwd(const float* x, int64_t n, const float* scali
   NSK_REQUIRE(num_levels >= 1 && num_levels <= nsk::HE_MAX_LEVELS, "nsk_hash_encode_bwd: num_levels out of range");
   if (n == 0) return 0;
   NSK_REQUIRE(x && scalings && grad_out && grad_table, "nsk_hash_encode_bwd: null pointer");
-  dim3 grid((unsigned)((n + 255) / 256), num_levels);
+  const unsigned grid = (unsigned)((n + 255) / 256);
   nsk::hash_encode_bwd_kernel<<<grid, 256, 0, nsk::as_stream(stream)>>>(x, n, scalings, num_levels, log2_T, grad_out, grad_table);
   return nsk::check_launch("hash_encode_bwd_kernel");
 }
