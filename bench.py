@@ -404,9 +404,9 @@ def relight_arm(args, ctx):
         Dp = int(r.shader.mask.sum())
         per_ray = (S * 28 + Dp * 4) if args.per_sample_cache else 642 * 12
         algo = n * (per_ray + 16 + 12) * NL * args.steps
-        if compact:      # compact cache: 6 DP + 4 bytes per hit ray and pass of four codes; 12 B direction + 12 B result per ray and code
+        if compact:      # compact cache: 6 DP + 4 bytes per hit ray and pass of eight codes; 12 B direction + 12 B result per ray and code
             hit = float(caches[0]["rows"].shape[0]) if caches else 0.0
-            algo = (hit * world * (6 * 648 + 4) * ((NL + 3) // 4) + n * 24.0 * NL) * args.steps
+            algo = (hit * world * (6 * 648 + 4) * ((NL + 7) // 8) + n * 24.0 * NL) * args.steps
         line = ({"metric": "relit rays/s (fixed geometry, new RENI++ latent code per pass)", "value": n * NL * args.steps / t, "unit": UNIT, "n_gpus": world,
                           "steps": args.steps, "warmup": max(1, args.warmup // 3), "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "strong",
                           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -459,7 +459,7 @@ def train_arm(args, ctx):
     if args.train_sampler == "proposal":   # the shipped NeuS-facto placement: 256 -> 96 -> S samples through two HashMLPDensityFields + interlevel loss
         prop = [nb_init.init_proposal_params(SEED_W + 3, table_scale=1.0, density_bias=1.0), nb_init.init_proposal_params(SEED_W + 4, table_scale=1.0, density_bias=2.0)]
     step_mod = NeuSkyTrainStep(sdf_p, nb_init.init_ddf_params(SEED_W), nb_init.init_reni_params(SEED_W + 1), num_cameras=K, device=dev,
-                               num_samples=S, split_geo=3, split=args.split, threshold_init=0.4, proposal_params=prop)
+                               num_samples=S, split_geo=3, split=args.split, ddf_split_bwd=(args.ddf_split_bwd or None), threshold_init=0.4, proposal_params=prop)
     with torch.no_grad():
         step_mod.latents.copy_(torch.randn(K, 100, 3, generator=torch.Generator().manual_seed(3)).to(dev))
     params = [p for p in step_mod.parameters() if p.requires_grad]
@@ -553,7 +553,8 @@ def train_arm(args, ctx):
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "wall_ms_per_step": 1e3 * wall / args.steps,
                 "host_launch_ms_per_step": 1e3 * host_launch / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": f"tf32 operands (3xTF32 on the SDF geometry network, split={args.split} elsewhere), fp32 accumulate / activations / gradients", "data": "synthetic",
+                "dtype": f"tf32 operands (3xTF32 on the SDF geometry network, split={args.split} elsewhere"
+                         + (f", DDF backward contractions split={args.ddf_split_bwd}" if args.ddf_split_bwd else "") + "), fp32 accumulate / activations / gradients", "data": "synthetic",
                 "config": {"workload": f"BASELINE.json configs[3]: training step, {R} rays/GPU from {K} cameras, S={S} {'proposal-network (256->96->' + str(S) + ', interlevel loss)' if prop is not None else 'uniform'} samples/ray, 642-direction icosphere with a random "
                                        f"rotation per step (mean D'={Dp:.0f} through the DDF), sdf_at_termination branch, hashgrid density loss on {gres**3} grid points, "
                                        + ("DDF fitting pass (8 x 128 vMF rays rendered through the SDF field, DDF on 1024 + 1024 multi-view + 256 sky rows, gradients into both fields), " if fit is not None else "no DDF fitting pass, ")
@@ -645,6 +646,7 @@ def main():
     ap.add_argument("--rays", type=int, default=1024, help="train: rays per GPU")
     ap.add_argument("--train-samples", type=int, default=48)
     ap.add_argument("--split", type=int, default=3, choices=[1, 3], help="train: 1 = tf32 GEMMs, 3 = 3xTF32 (fp32-accurate)")
+    ap.add_argument("--ddf-split-bwd", type=int, default=0, choices=[0, 1, 3], help="train: precision of the DDF's backward contractions only (0 = same as --split)")
     ap.add_argument("--train-sampler", default="proposal", choices=["proposal", "uniform"], help="train: sample placement (proposal = shipped NeuS-facto default)")
     ap.add_argument("--no-ddf-fit", action="store_true", help="train: leave the DDF fitting pass (fit_visibility_field=True in the reference) out of the step")
     args = ap.parse_args()
@@ -751,6 +753,11 @@ def main():
         ta = copy.copy(args); ta.steps, ta.warmup, ta.sample_clocks = max(4, 2 * args.extra_steps), 3, False
         tr = train_arm(ta, ctx)
         torch.cuda.empty_cache()
+        # the same iteration with the DDF's backward contractions in single-pass tf32 (forward and every loss value stay 3xTF32):
+        # stated separately, tolerance in tests/test_gpu_train.py
+        tb = copy.copy(ta); tb.ddf_split_bwd = 1
+        trb = train_arm(tb, ctx)
+        torch.cuda.empty_cache()
         if line is not None:
             keep = ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "dtype", "gpu_launches")
             line["extra"] = {
@@ -758,7 +765,9 @@ def main():
                          "gather_bytes_per_step": ev["gather_bytes_per_step"], "collective": ev["collective"]},
                 "train": {**{k: tr[k] for k in keep}, "workload": tr["config"]["workload"], "parallelism": tr["config"]["parallelism"],
                           "all_reduce_exposed_ms": tr["all_reduce_exposed_ms"], "all_reduce_bytes_per_step": tr["all_reduce_bytes_per_step"],
-                          "algorithmic_tflops": tr["algorithmic_tflops"], "wall_ms_per_step": tr["wall_ms_per_step"]},
+                          "algorithmic_tflops": tr["algorithmic_tflops"], "wall_ms_per_step": tr["wall_ms_per_step"],
+                          "tf32_ddf_backward": {"value": trb["value"], "ms_per_step": trb["ms_per_step"], "dtype": trb["dtype"],
+                                                "all_reduce_exposed_ms": trb["all_reduce_exposed_ms"]}},
             }
     # ---- per-kernel rooflines of the rest of the path (K1, K2, K3, RENI++, proposal sampler): rank 0, the other ranks wait at the barrier ----
     if not args.no_kernels:

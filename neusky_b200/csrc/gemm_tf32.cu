@@ -47,11 +47,13 @@ constexpr uint32_t A_LBO = TM * 16, B_LBO = BN * 16;
 // by the issue rate of the 4 loader warps (ncu: loaders stalled issuing, epilogue warps 2/3 idle); the operands therefore
 // arrive as tensor-map TMA boxes (TMA = true: SWIZZLE_64B, one issuing thread), the LDGSTS loader stays as the fallback.
 template <int SPLIT, bool TN, bool TMA = false> struct Cfg {
-  static constexpr bool PAIR = (SPLIT == 3 && !TN);
-  static constexpr bool TNT = (SPLIT == 3 && TN && TMA);                       // 3xTF32 TN fed by MN-major tensor-map boxes
-  static constexpr bool ROLES = PAIR || TNT;                                   // loader + hi/lo splitter warps
+  static constexpr bool PAIR = !TN && (SPLIT == 3 || TMA);                     // plain tf32 takes the pair shape only with TMA operands
+  static constexpr bool TNT = TN && TMA;                                       // TN fed by MN-major tensor-map boxes
+  static constexpr bool ROLES = PAIR || TNT;                                   // loader (+ hi/lo splitter warps when SPLIT == 3)
   static constexpr int KC = (PAIR || TNT) ? 16 : 32;
-  static constexpr int ST = PAIR ? 3 : (TNT ? 4 : (TN ? (SPLIT == 3 ? 2 : 4) : 3));   // NT keeps 18 KB for the epilogue staging
+  // NT keeps 18 KB for the epilogue staging.  Plain tf32 (SPLIT == 1) has no lo planes: the same 192 KB hold twice the stages,
+  // and the MMA issuer waits on the TMA (RAW) barrier directly -- the variant is HBM-bound, ring depth is what it needs.
+  static constexpr int ST = PAIR ? (SPLIT == 3 ? 3 : 6) : (TNT ? (SPLIT == 3 ? 4 : 8) : (TN ? (SPLIT == 3 ? 2 : 4) : 3));
   static constexpr int TMI = PAIR ? 2 * TM : TM;                              // rows of the A operand per work item
   static constexpr uint32_t A_HALF = TM * KC * 4;
   static constexpr uint32_t A_BYTES = TMI * KC * 4;
@@ -288,7 +290,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32_kernel(const Params p, c
             if (++stage == ST) { stage = 0; phase ^= 1; }
           }
         }
-      } else if (warp >= 4) {
+      } else if (SPLIT == 3 && warp >= 4) {
         const uint32_t t128 = (uint32_t)(threadIdx.x & 127) * 16;
         for (int64_t w = blockIdx.x; w < p.n_items; w += gridDim.x) {
           const Item it = get_item<TN, TMI>(p, w);
@@ -373,7 +375,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32_kernel(const Params p, c
             if (++stage == ST) { stage = 0; phase ^= 1; }
           }
         }
-      } else {
+      } else if (SPLIT == 3) {
         for (int64_t w = blockIdx.x; w < p.n_items; w += gridDim.x) {
           for (int c = 0; c < spi; ++c) {
             mbar_wait(RAW + 8 * stage, phase);
@@ -530,7 +532,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32_kernel(const Params p, c
           for (int c = 0; c < nch; ++c) {
             const int64_t r = chunk_start<TN>(it, c, nch, KC);                  // same rotated order as the loader
             const int ksteps = (int)min((int64_t)(KC / 8), (it.r1 - r + 7) / 8);
-            mbar_wait(FULL + 8 * stage, phase);
+            mbar_wait((SPLIT == 1 ? RAW : FULL) + 8 * stage, phase);
             tc_fence_after();
             const uint32_t sa = smem_u32(smem + stage * STAGE), sb = sa + A_BYTES;
             for (int j = 0; j < ksteps; ++j) {
@@ -541,9 +543,13 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32_kernel(const Params p, c
                 const uint64_t ah = TMA ? make_smem_desc_sw64(sa + hf * A_HALF + j * 32) : make_smem_desc(sa + hf * A_HALF + j * 2 * A_LBO, A_LBO, 128);
                 const uint64_t al = TMA ? make_smem_desc_sw64(sa + LO_OFF + hf * A_HALF + j * 32)
                                         : make_smem_desc(sa + LO_OFF + hf * A_HALF + j * 2 * A_LBO, A_LBO, 128);
-                umma_tf32(d, al, bh, idesc, (c > 0 || j > 0) ? 1u : 0u);
-                umma_tf32(d, ah, bl, idesc, 1);
-                umma_tf32(d, ah, bh, idesc, 1);
+                if (SPLIT == 3) {
+                  umma_tf32(d, al, bh, idesc, (c > 0 || j > 0) ? 1u : 0u);
+                  umma_tf32(d, ah, bl, idesc, 1);
+                  umma_tf32(d, ah, bh, idesc, 1);
+                } else {
+                  umma_tf32(d, ah, bh, idesc, (c > 0 || j > 0) ? 1u : 0u);
+                }
               }
             }
             umma_commit(EMPTY + 8 * stage);
@@ -565,7 +571,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32_kernel(const Params p, c
         const int nch = it.r0 < it.r1 ? (int)((it.r1 - it.r0 + KC - 1) / KC) : 0;
         for (int c = 0; c < nch; ++c) {
           const int64_t r = chunk_start<TN>(it, c, nch, KC);
-          mbar_wait(FULL + 8 * stage, phase);
+          mbar_wait(((TNT && SPLIT == 1) ? RAW : FULL) + 8 * stage, phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * STAGE), sb = sa + A_BYTES;
           const int ksteps = (int)min((int64_t)(KC / 8), (it.r1 - r + 7) / 8);
@@ -802,21 +808,26 @@ static bool make_tensor_map_mn(CUtensorMap* m, const float* base, int64_t rows, 
 }
 
 template <int SPLIT, bool TN>
-static int launch(const Params& p, cudaStream_t st) {
+static int launch(Params p, cudaStream_t st) {
   CUtensorMap ma, mb;
   memset(&ma, 0, sizeof(ma));
   memset(&mb, 0, sizeof(mb));
+  // NT work items are TMI rows of A x one B tile; TMI depends on the variant that runs
+  auto nt_items = [&](int tmi) { return ((p.M + tmi - 1) / tmi) * p.n_btiles; };
   if (getenv("NSK_GEMM_NO_TMA") == nullptr) {
-    if constexpr (Cfg<SPLIT, TN>::PAIR) {
-      if (make_tensor_map(&ma, p.A, p.M, p.K, p.lda, Cfg<SPLIT, TN>::TMI) && make_tensor_map(&mb, p.B, p.N, p.K, p.ldb, BN))
+    if constexpr (!TN) {
+      if (make_tensor_map(&ma, p.A, p.M, p.K, p.lda, Cfg<SPLIT, TN, true>::TMI) && make_tensor_map(&mb, p.B, p.N, p.K, p.ldb, BN)) {
+        p.n_items = nt_items(Cfg<SPLIT, TN, true>::TMI);
         return launch_variant<SPLIT, TN, true>(p, ma, mb, st);
-    } else if constexpr (SPLIT == 3 && TN) {
+      }
+    } else {
       // TN: A [M, P = p.N] and B [M, Q = p.K]; the reduction index (rows) must fit the int32 TMA coordinate
-      if (p.M < (1ll << 31) && make_tensor_map_mn(&ma, p.A, p.M, p.N, p.lda, Cfg<3, true, true>::KC, TM / 32) &&
-          make_tensor_map_mn(&mb, p.B, p.M, p.K, p.ldb, Cfg<3, true, true>::KC, BN / 32))
+      if (p.M < (1ll << 31) && make_tensor_map_mn(&ma, p.A, p.M, p.N, p.lda, Cfg<SPLIT, true, true>::KC, TM / 32) &&
+          make_tensor_map_mn(&mb, p.B, p.M, p.K, p.ldb, Cfg<SPLIT, true, true>::KC, BN / 32))
         return launch_variant<SPLIT, TN, true>(p, ma, mb, st);
     }
   }
+  if constexpr (!TN) p.n_items = nt_items(Cfg<SPLIT, TN, false>::TMI);
   return launch_variant<SPLIT, TN, false>(p, ma, mb, st);
 }
 
@@ -846,8 +857,7 @@ extern "C" int nsk_gemm_tf32_nt(const float* A, int lda, const float* B, int ldb
   p.n_btiles = (N + BN - 1) / BN;
   p.n_atiles = 0;
   p.rows_per_split = 0;
-  const int tmi = split == 3 ? Cfg<3, false>::TMI : Cfg<1, false>::TMI;
-  p.n_items = ((M + tmi - 1) / tmi) * p.n_btiles;
+  p.n_items = 0;   // set by launch() once the variant (rows of A per work item) is known
   return split == 3 ? launch<3, false>(p, nsk::as_stream(stream)) : launch<1, false>(p, nsk::as_stream(stream));
 }
 

@@ -240,7 +240,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) sky_
     // The whole warp walks the schedule (warp-uniform control flow); one elected lane issues the
     // tcgen05.mma / tcgen05.commit instructions.  Descriptors are advanced by adding to their low words.
     uint32_t wst = 0, wph = 0, phases = 0;
-    long long t_dep = 0, t_w = 0, t_dep_map = 0;
+    long long t_dep = 0, t_w = 0, t_dep_map = 0, t_iss_map = 0, t_iss_fp = 0, t_iss_z = 0;
     const long long t_begin = NSK_CLK();
     const uint64_t desc_hi = ((uint64_t)1 << 46) | ((uint64_t)(128 >> 4) << 32);   // version 1, SBO = 128 B
     if (!leader) {
@@ -299,6 +299,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) sky_
               if (PROF) t_w += NSK_CLK() - c0;
             }
             tc_fence_after();
+            const long long ci0 = NSK_CLK();
             if (elect_one()) {
               uint64_t ad = ad0 + (uint64_t)kstep * 256u;   // one K=16 step = 2 chunks = 4096 B >> 4
               uint64_t bd = bd0 | (uint64_t)(((sbase + OFF_RING + wst * STAGE_BYTES) >> 4) & 0x3FFF);
@@ -313,6 +314,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) sky_
               umma_commit2(bars + 8 * (B_WEMPTY + wst));   // stage reusable in BOTH CTAs once these MMAs have read it
             }
             __syncwarp();
+            if (PROF) {
+              const long long dt = NSK_CLK() - ci0;
+              if (sh == SH_FP) t_iss_fp += dt; else if (sh == SH_Z || sh == SH_Z0) t_iss_z += dt; else t_iss_map += dt;
+            }
             kstep += nmma;
             acc = 1;
             if (++wst == NSTAGE) { wst = 0; wph ^= 1; }
@@ -329,6 +334,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) sky_
     if (PROF && P.prof && lane == 0) {
       P.prof[blockIdx.x * 16 + 2] = NSK_CLK() - t_begin; P.prof[blockIdx.x * 16 + 3] = t_dep; P.prof[blockIdx.x * 16 + 4] = t_w;
       P.prof[blockIdx.x * 16 + 5] = t_dep_map;
+      P.prof[blockIdx.x * 16 + 13] = t_iss_map; P.prof[blockIdx.x * 16 + 14] = t_iss_fp; P.prof[blockIdx.x * 16 + 15] = t_iss_z;
     }
   } else if (warp >= EPI_WARP0 && warp < PRO_WARP0) {
     // ================================ epilogue ================================

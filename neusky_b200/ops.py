@@ -532,7 +532,7 @@ def relight_pack_h16(H: Tensor, rows: Tensor) -> Tuple[Tensor, Tensor]:
 
 
 def relight_h16_multi(H16: Tensor, hscale: Tensor, rows: Tensor, R: int, D: int, radiance: Tensor) -> Tensor:
-    """Compact cache + radiance [NL,D,3] -> linear rgb [NL,R,3] (zero for rays without a cache row), four illuminations per pass."""
+    """Compact cache + radiance [NL,D,3] -> linear rgb [NL,R,3] (zero for rays without a cache row), eight illuminations per pass."""
     Rs, DP = rows.shape[0], (D + 7) // 8 * 8
     H16 = _chk("H16", H16, dtype=torch.float16, shape=(Rs, 3 * DP))
     hscale = _chk("hscale", hscale, shape=(Rs,))

@@ -36,6 +36,7 @@ class DDFConfig:
     radius: float = 1.0
     sigmoid_scale: float = 25.0
     split: int = 1
+    split_bwd: Optional[int] = None      # GEMM precision of the backward contractions (dX, dW); None = same as `split`
 
 
 def _pad_cols(W: Tensor, mult: int = 8) -> Tensor:
@@ -87,7 +88,7 @@ def _ddf_backward_core(cfg: DDFConfig, cond, xin, q, term, film, that, threshold
                        need_table: bool, need_xin: bool, b_shape):
     """Backward of `_ddf_forward_core`: gradients for threshold, hash table, final layer, every mapping / trunk weight and
     (optionally) the trunk input rows xin."""
-    sp = cfg.split
+    sp = cfg.split if cfg.split_bwd is None else cfg.split_bwd
     dev = cond.device
     zeros = lambda *s: torch.zeros(s, device=dev, dtype=torch.float32)
 
@@ -437,7 +438,7 @@ class NeuSkyTrainStep(torch.nn.Module):
 
     def __init__(self, sdf_params: Dict[str, Tensor], ddf_params: Dict[str, Tensor], reni_params: Dict[str, Tensor], num_cameras: int, device="cuda",
                  log2_T: int = 19, num_levels: int = 16, num_samples: int = 48, ddf_radius: float = 1.0, sigmoid_scale: float = 25.0,
-                 split_geo: int = 3, split: int = 3, threshold_init: Optional[float] = None, only_upper_hemisphere: bool = True,
+                 split_geo: int = 3, split: int = 3, ddf_split_bwd: Optional[int] = None, threshold_init: Optional[float] = None, only_upper_hemisphere: bool = True,
                  lower_hemisphere_visibility: float = 1.0, proposal_params: Optional[Sequence[Dict[str, Tensor]]] = None,
                  proposal_max_res: Sequence[int] = (64, 256), num_proposal_samples_per_ray: Sequence[int] = (256, 96), proposal_log2_T: int = 17,
                  share_params: bool = False, latents: Optional[torch.nn.Parameter] = None, scale: Optional[torch.nn.Parameter] = None,
@@ -446,7 +447,9 @@ class NeuSkyTrainStep(torch.nn.Module):
         sampler, neusky_model.py:561) and its interlevel loss (:987-988, coefficient 1.0); None -> uniform placement.
         ``share_params``: register the ``nn.Parameter`` objects passed in ``sdf_params`` / ``ddf_params`` themselves instead of
         copies (the drop-in model, neusky_b200/models.py, owns the parameters under the reference's module names and runs its
-        training forward through this class); ``latents`` / ``scale`` / ``visibility_threshold`` / ``proposal_fields`` likewise."""
+        training forward through this class); ``latents`` / ``scale`` / ``visibility_threshold`` / ``proposal_fields`` likewise.
+        ``ddf_split_bwd``: GEMM precision of the DDF's backward contractions only (1 = single-pass tf32 dX / dW with the forward
+        still at ``split``); None keeps them at ``split``."""
         super().__init__()
         from . import packing
         from .init import hash_scalings
@@ -473,7 +476,7 @@ class NeuSkyTrainStep(torch.nn.Module):
         self.reni_blob = packing.pack_reni(reni_params, device=self.dev)
         self.reni_blob_bwd = packing.pack_reni_bwd(reni_params, device=self.dev)
         self.sdf_cfg = SDFConfig(scalings=self.scalings, log2_T=log2_T, split_geo=split_geo, split_colour=split)
-        self.ddf_cfg = DDFConfig(scalings=self.scalings, log2_T=log2_T if ddf_log2_T is None else ddf_log2_T, radius=self.radius, sigmoid_scale=sigmoid_scale, split=split)
+        self.ddf_cfg = DDFConfig(scalings=self.scalings, log2_T=log2_T if ddf_log2_T is None else ddf_log2_T, radius=self.radius, sigmoid_scale=sigmoid_scale, split=split, split_bwd=ddf_split_bwd)
         self.cos_anneal_ratio = 1.0
         self.grid_resolution = 10                                                                  # neusky_config.py:127
         self.proposal_fields, self.proposal_sampler, self.proposal_anneal = None, None, 1.0

@@ -7,6 +7,8 @@ tf32 pass, 10-bit mantissa operands) is the throughput mode: 2e-3 on contraction
 import pytest
 import torch
 
+from conftest import log_err
+
 from neusky_b200 import init as nb_init
 
 pytestmark = pytest.mark.gpu
@@ -141,10 +143,12 @@ def _ddf_case(R, Dn, seed, log2_T=14):
     return p, pts, dirs
 
 
-@pytest.mark.parametrize("split,tol_fwd,tol_grad", [(3, 2e-4, 5e-3), (1, 2e-2, 8e-2)])
-def test_ddf_visibility_forward_backward_vs_oracle_autograd(dev, split, tol_fwd, tol_grad):
+@pytest.mark.parametrize("split,split_bwd,tol_fwd,tol_grad", [(3, None, 2e-4, 5e-3), (1, None, 2e-2, 8e-2), (3, 1, 2e-4, 1e-2)])
+def test_ddf_visibility_forward_backward_vs_oracle_autograd(dev, split, split_bwd, tol_fwd, tol_grad):
     """vis / expected termination distance and the gradients of every DDF parameter, the hash table and the threshold
-    against fp64 autograd through oracle.compute_visibility (neusky_model.py:1685-1740 + ddf_model.py + film_siren.py)."""
+    against fp64 autograd through oracle.compute_visibility (neusky_model.py:1685-1740 + ddf_model.py + film_siren.py).
+    (3, 1): fp32-accurate forward (3xTF32) with single-pass tf32 backward contractions -- the forward values keep the 3xTF32
+    tolerance, the gradients carry tf32 operand rounding (~1e-3 per contraction), stated separately here."""
     from neusky_b200 import train as T
     from oracle import neusky_oracle as O
 
@@ -171,7 +175,7 @@ def test_ddf_visibility_forward_backward_vs_oracle_autograd(dev, split, tol_fwd,
     cond = {k: _rel(p32[k].grad, pd[k].grad) for k in p if p32[k].grad is not None}
 
     # ---- CUDA ----
-    cfg = T.DDFConfig(scalings=O.hash_scalings().to(dev), log2_T=log2_T, radius=1.0, sigmoid_scale=scale, split=split)
+    cfg = T.DDFConfig(scalings=O.hash_scalings().to(dev), log2_T=log2_T, radius=1.0, sigmoid_scale=scale, split=split, split_bwd=split_bwd)
     pc = {k: v.to(dev).requires_grad_(True) for k, v in p.items()}
     thr = torch.tensor(thr0, device=dev, requires_grad=True)
     vis, that, q, term = T.ddf_visibility(cfg, pts.to(dev), dirs.to(dev), thr, pc["position_encoding.hash_table"], pc["ddf.final_layer.weight"], pc["ddf.final_layer.bias"],
@@ -185,6 +189,7 @@ def test_ddf_visibility_forward_backward_vs_oracle_autograd(dev, split, tol_fwd,
     for k in p:
         assert pc[k].grad is not None, k
         worst[k] = _rel(pc[k].grad, pd[k].grad)
+    log_err(f"ddf_train_grads[split={split},bwd={split_bwd}]", worst=max(worst.values()), median=sorted(worst.values())[len(worst) // 2])
     bad = {k: (v, cond.get(k)) for k, v in worst.items() if not v <= max(tol_grad, 2.0 * cond.get(k, 0.0))}
     assert not bad, f"split={split}: gradient mismatch (ours vs fp64, fp32 oracle vs fp64) {bad} (all: {worst})"
 
