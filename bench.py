@@ -266,11 +266,12 @@ def eval_arm(args, ctx):
     o, d, dn = pinhole_rays(H, W, fx, fx, W / 2, H / 2, c2w, dev)
     Z, sc = (t.to(dev) for t in _latents())
     Dp = int(r.shader.mask.sum())
+    from neusky_b200 import parallel as _par
+
+    tile = _par.balanced_tile(H * W, args.tile, world)      # equal ray counts per rank (N = 1 keeps --tile)
 
     def step():
-        return render_image(r, o, d, dn, args.samples, Z[0], sc[0], tile=args.tile)
-
-    from neusky_b200 import parallel as _par
+        return render_image(r, o, d, dn, args.samples, Z[0], sc[0], tile=tile)
 
     for _ in range(args.warmup):
         step()
@@ -293,7 +294,7 @@ def eval_arm(args, ctx):
         line = ({"metric": METRIC, "value": n * args.steps / t, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                           "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f16xf16->f32", "data": "synthetic",
                           "config": {"workload": f"BASELINE.json configs[2]: full-image eval render {W}x{H}, {args.samples} {'proposal-network (256->96->' + str(args.samples) + ')' if args.sampler == 'proposal' else 'uniform'} samples/ray, 642 icosphere directions (D'={Dp}), "
-                                                 f"ray tiles of {args.tile} round-robin over {world} GPU(s), outputs gathered", "parallelism": f"ray tiles x{world}, weights replicated",
+                                                 f"ray tiles of {tile} round-robin over {world} GPU(s), outputs gathered", "parallelism": f"ray tiles x{world}, weights replicated",
                                      "l2": "inputs (118 M samples/frame) exceed L2", "surface_coverage": float((acc > 0.5).float().mean())},
                           "gpu_launches": _lib.launches - l0, "pairs_per_frame": n * Dp, "samples_per_frame": n * args.samples,
                           "gather_ms_per_step": 1e3 * t_gather / args.steps, "gather_bytes_per_step": n * 12 * 4 if world > 1 else 0,

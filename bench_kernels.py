@@ -128,7 +128,25 @@ def kernel_rooflines(dev, peaks, scale: float = 1.0, emit=None):
     report("reni_rows_tc N=921600 (3xTF32 GEMM chain)", "tensor", ms, Nf * 524544.0, 524544, Nf, {"note": "algorithmic FLOP; 3xTF32 issues 3 tf32 MMAs per product"})
     ms = timeit(lambda: ops.reni_radiance_table(rows, Z1, s1, rblob), iters=3)
     report("reni_decode rows N=921600 (fp32 SIMT, same work)", "tensor", ms, Nf * 524544.0, 524544, Nf)
+    # the product path for frame-sized row batches since round 2: the whole decoder as ONE tcgen05 kernel (fp16 operands, fp32 LayerNorm)
+    rfused = packing.pack_reni_fused(rp, device=dev)
+    ms = timeit(lambda: ops.reni_rows_fused(rows, Z1, s1, rblob, rfused), iters=5)
+    report("reni_rows_fused N=921600 (one tcgen05 kernel, fp16 operands)", "tensor", ms, Nf * 524544.0, 524544, Nf,
+           {"note": "LayerNorm epilogues (two per decoder layer) bound it, not the tensor pipe: profiles/r02_reni_fused_phase_cycles.log"})
     del rows
+
+    # ---- relighting pass over the compact cache (8f row f3): 6 DP + 4 bytes per cached ray and pass of eight latent codes --------------
+    Rc, Dr = int(921_600 * scale), 642
+    DPr = (Dr + 7) // 8 * 8
+    H16 = (torch.rand(Rc, 3 * DPr, generator=g) * 0.9).to(torch.float16).to(dev)
+    hscale = torch.rand(Rc, generator=g).to(dev)
+    rws = torch.arange(Rc, dtype=torch.int32, device=dev)
+    rad8 = torch.rand(8, Dr, 3, generator=g).to(dev)
+    ms = timeit(lambda: ops.relight_h16_multi(H16, hscale, rws, Rc, Dr, rad8), iters=5)
+    byt = 6 * DPr + 8 + 8 * 12
+    report("relight_h16 (compact cache pass, 8 latent codes)", "hbm", ms, Rc * float(byt), byt, Rc,
+           {"note": "issue-bound (27 instructions per direction and row pair), not HBM-bound: fp16 -> fp32 conversions of the table entries"})
+    del H16, hscale, rws
 
     # ---- proposal-network sampler (8f row f1): density field 372 B/sample algorithmic (12 + 5*8*8 gather + 40 features);
     # ---- PDF resampling: reads bins (S+1)*4 + density S*4, writes weights S*4 + new bins/euclid 2*(N+1)*4 per ray --------------------

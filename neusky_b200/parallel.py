@@ -24,6 +24,16 @@ def tiles_of_rank(n_rays: int, tile: int, rank: int, world: int) -> List[Tuple[i
     return [(i * tile, min((i + 1) * tile, n_rays)) for i in range(rank, n_tiles, world)]
 
 
+def balanced_tile(n_rays: int, tile: int, world: int) -> int:
+    """Largest tile size <= `tile` that cuts `n_rays` into a multiple of `world` (almost) equal tiles, so that the round-robin
+    partition gives every rank the same number of rays (a 1280x720 frame is 56.25 tiles of 16384: with that size one rank carries
+    a quarter tile more than the others and everybody waits for it at the gather).  world == 1 keeps `tile`."""
+    if world <= 1 or n_rays <= 0:
+        return tile
+    k = (n_rays + world * tile - 1) // (world * tile)          # tiles per rank
+    return (n_rays + world * k - 1) // (world * k)
+
+
 def local_ray_indices(n_rays: int, tile: int, rank: int, world: int, device=None) -> Tensor:
     r = [torch.arange(a, b, device=device) for a, b in tiles_of_rank(n_rays, tile, rank, world)]
     return torch.cat(r) if r else torch.zeros(0, dtype=torch.long, device=device)

@@ -81,3 +81,19 @@ def test_sharded_render_gathers_identically_world2_gloo(n, tile):
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_balanced_tile_equalises_ranks():
+    """parallel.balanced_tile: the tile size the eval split uses at N > 1 gives every rank the same number of rays (+-1 tile rounding)
+    and never exceeds the requested tile; world 1 keeps the requested tile."""
+    from neusky_b200.parallel import balanced_tile, tiles_of_rank
+
+    assert balanced_tile(921600, 16384, 1) == 16384
+    for n, tile in ((921600, 16384), (230400, 16384), (1000, 64), (17, 4)):
+        for world in (2, 3, 4, 8):
+            t = balanced_tile(n, tile, world)
+            assert 0 < t <= tile
+            per_rank = [sum(b - a for a, b in tiles_of_rank(n, t, r, world)) for r in range(world)]
+            assert sum(per_rank) == n
+            assert max(per_rank) - min(per_rank) <= max(1, world * ((n + t - 1) // t) // world), (n, tile, world, per_rank)
+            assert max(per_rank) <= -(-n // world) + t            # nobody carries more than its share plus one tile's rounding
