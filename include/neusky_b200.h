@@ -212,8 +212,8 @@ int nsk_relight_collapsed(const float* H, int64_t R, int D, const float* radianc
  * by streaming H; NL = 4 reads it once for four latent codes). */
 int nsk_relight_collapsed_multi(const float* H, int64_t R, int D, const float* radiance, int NL, float* rgb_lin, void* stream);
 /* Compact relighting cache (csrc/relight_compact.cu): only rays with accumulation > 0 own a row (`rows` [Rs] int32 ->
- * ray index), a row is fp16, channel-planar [3][DP] (DP = D rounded up to 8), normalised by its own maximum (hscale [Rs]).
- * nsk_relight_pack_h16 builds it from the fp32 coefficients H [R,D,3]; nsk_relight_h16_multi streams it once per EIGHT illuminations:
+ * ray index), a row is fp16, channel-planar [3][DP] (DP = D rounded up to 16, directions in mma A-fragment order inside each block of 16), normalised by its own maximum (hscale [Rs]).
+ * nsk_relight_pack_h16 builds it from the fp32 coefficients H [R,D,3]; nsk_relight_h16_multi streams it once per 32 illuminations:
  * radiance [NL,D,3] -> rgb_lin [NL,R,3] (zero for rays without a row).  H16 must be 16-byte aligned. */
 int nsk_relight_pack_h16(const float* H, const int32_t* rows, int64_t Rs, int D, void* H16, float* hscale, void* stream);
 int nsk_relight_h16_multi(const void* H16, const float* hscale, const int32_t* rows, int64_t Rs, int64_t R, int D, const float* radiance,

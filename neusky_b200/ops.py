@@ -524,7 +524,7 @@ def relight_pack_h16(H: Tensor, rows: Tensor) -> Tuple[Tensor, Tensor]:
     R, D = H.shape[0], H.shape[1]
     H = _chk("H", H, shape=(R, D, 3))
     rows = _chk("rows", rows, dtype=torch.int32, shape=(None,))
-    Rs, DP = rows.shape[0], (D + 7) // 8 * 8
+    Rs, DP = rows.shape[0], (D + 15) // 16 * 16
     H16 = torch.empty((Rs, 3 * DP), device=H.device, dtype=torch.float16)
     hscale = torch.empty((Rs,), device=H.device, dtype=torch.float32)
     _lib.check(_lib.load().nsk_relight_pack_h16(_ptr(H), _ptr(rows), c_int64(Rs), c_int(D), _ptr(H16), _ptr(hscale), _stream(H)), "nsk_relight_pack_h16")
@@ -532,8 +532,8 @@ def relight_pack_h16(H: Tensor, rows: Tensor) -> Tuple[Tensor, Tensor]:
 
 
 def relight_h16_multi(H16: Tensor, hscale: Tensor, rows: Tensor, R: int, D: int, radiance: Tensor) -> Tensor:
-    """Compact cache + radiance [NL,D,3] -> linear rgb [NL,R,3] (zero for rays without a cache row), eight illuminations per pass."""
-    Rs, DP = rows.shape[0], (D + 7) // 8 * 8
+    """Compact cache + radiance [NL,D,3] -> linear rgb [NL,R,3] (zero for rays without a cache row), up to 32 illuminations per pass."""
+    Rs, DP = rows.shape[0], (D + 15) // 16 * 16
     H16 = _chk("H16", H16, dtype=torch.float16, shape=(Rs, 3 * DP))
     hscale = _chk("hscale", hscale, shape=(Rs,))
     rows = _chk("rows", rows, dtype=torch.int32, shape=(Rs,))

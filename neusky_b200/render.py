@@ -408,11 +408,11 @@ class RayRenderer:
                 "directions": torch.cat([c["directions"] for c in caches], 0), "n_dirs": caches[0]["n_dirs"]}
 
     @torch.no_grad()
-    def relight_sweep(self, cache: Dict[str, Tensor], latents: Tensor, scales: Tensor, rotation: Optional[Tensor] = None, group: int = 8) -> Tensor:
+    def relight_sweep(self, cache: Dict[str, Tensor], latents: Tensor, scales: Tensor, rotation: Optional[Tensor] = None, group: int = 32) -> Tensor:
         """sRGB [NL, R, 3] of the cached rays (compact cache) under NL latent codes [NL, L, 3] / scales [NL] (BASELINE.json configs[4]).
         Per group of latent codes: ONE RENI++ table decode, ONE fused row decode of the background of the rays whose
-        1 - accumulation is not zero (every other ray gets no background: it is multiplied by 0), one streaming pass over the cache
-        per four codes, one finalize -- no per-tile, per-code Python loop."""
+        1 - accumulation is not zero (every other ray gets no background: it is multiplied by 0), ONE streaming pass over the cache
+        (up to 32 codes per read), one finalize -- no per-tile, per-code Python loop."""
         if "H16" not in cache:
             raise ValueError("relight_sweep takes the compact cache")
         sh = self.shader

@@ -72,12 +72,12 @@ H = torch.rand(Rr, D, 3, device=dev)
 rad = torch.rand(4, D, 3, device=dev)
 twice(lambda: ops.relight_collapsed_multi(H, rad)); note("relight_collapsed_multi_kernel", Rr, D * 12 + 4 * 12, "config-5 pass: 4 latent codes per read of H [R,642,3] fp32")
 # round 2: compact cache pass (8 codes per read) and the fused RENI++ row kernel
-Rc, DPc = 921_600 // 2, 648
+Rc, DPc = 921_600 // 2, 656
 H16 = (torch.rand(Rc, 3 * DPc, device=dev) * 0.9).to(torch.float16)
 hs = torch.rand(Rc, device=dev)
 rws = torch.arange(Rc, dtype=torch.int32, device=dev)
-rad8 = torch.rand(8, D, 3, device=dev)
-twice(lambda: ops.relight_h16_multi(H16, hs, rws, Rc, D, rad8)); note("relight_h16_kernel", Rc, 6 * DPc + 8 + 8 * 12, "config-5 pass over the compact cache: 8 latent codes per read of fp16 rows [3][648]")
+rad8 = torch.rand(32, D, 3, device=dev)
+twice(lambda: ops.relight_h16_multi(H16, hs, rws, Rc, D, rad8)); note("relight_h16_kernel", Rc, 6 * DPc + 8 + 32 * 12, "config-5 pass over the compact cache: 32 latent codes per read of fp16 rows [3][656]")
 del H16, hs, rws
 rfused = packing.pack_reni_fused(rp, device=dev)
 rows = torch.nn.functional.normalize(torch.randn(Nf, 3, generator=g), dim=-1).to(dev)
