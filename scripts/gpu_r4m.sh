@@ -1,0 +1,6 @@
+#!/bin/bash
+cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
+mkdir -p gpurun_out
+nvcc -O3 -gencode arch=compute_100a,code=sm_100a -I neusky_b200/csrc -o /tmp/tc_probe tools/tc_probe.cu 2> gpurun_out/r4m_build.err || { tail gpurun_out/r4m_build.err; exit 1; }
+{ for n in 0 128 256; do for w in 8 16; do for d in 1 2 4; do timeout 60 /tmp/tc_probe ldtm3 $n $w $d | grep probe; done; done; done; } > gpurun_out/r4m_ldtm3.log 2>&1
+cat gpurun_out/r4m_ldtm3.log

@@ -387,6 +387,199 @@ static void probe_rate2(int N, int commit_every, int mode) {
          mean / iters, N / 2, ms, flops / (ms * 1e-3) / 1e12);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// probe 7: pure TMEM read throughput / latency: `warps` warps (warp w reads lane quadrant w % 4), 32x32b.xN loads, `depth` loads
+// in flight per warp before a tcgen05.wait::ld; no math beyond an xor fold.  Reports bytes per clock per SM and cycles per load group.
+// ------------------------------------------------------------------------------------------------
+template <int X>
+__global__ void __launch_bounds__(512) ldtm2_kernel(int iters, int depth, long long* cycles, unsigned* sink) {
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) tmem_alloc<512>(smem_u32(&tmem_base_s));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 64);
+  unsigned acc = 0;
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int i = 0; i < iters; ++i) {
+    uint32_t v[4][X];
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+      if (d < depth) {
+        if (X == 8) tmem_ld8(tmem + ((i + d) & 1) * 32 + d * 8, reinterpret_cast<uint32_t(&)[8]>(v[d]));
+        if (X == 16) tmem_ld16(tmem + ((i + d) & 1) * 32 + (d & 1) * 16, reinterpret_cast<uint32_t(&)[16]>(v[d]));
+        if (X == 32) tmem_ld32(tmem + ((i + d) & 1) * 32, reinterpret_cast<uint32_t(&)[32]>(v[d]));
+      }
+    }
+    tmem_ld_wait();
+#pragma unroll
+    for (int d = 0; d < 4; ++d)
+      if (d < depth) {
+#pragma unroll
+        for (int j = 0; j < X; ++j) acc ^= v[d][j];
+      }
+  }
+  const long long t1 = clock64();
+  __syncthreads();
+  if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+  if (acc == 0x12345678u) *sink = acc;
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tmem_base_s);
+}
+
+static void probe_ldtm2(int warps, int x, int depth) {
+  long long* d; unsigned* sink; CK(cudaMalloc(&d, 148 * 8)); CK(cudaMalloc(&sink, 4));
+  const int iters = 4000;
+  if (x == 8) ldtm2_kernel<8><<<148, warps * 32>>>(iters, depth, d, sink);
+  else if (x == 16) ldtm2_kernel<16><<<148, warps * 32>>>(iters, depth, d, sink);
+  else ldtm2_kernel<32><<<148, warps * 32>>>(iters, depth, d, sink);
+  CK(cudaDeviceSynchronize());
+  std::vector<long long> h(148);
+  CK(cudaMemcpy(h.data(), d, 148 * 8, cudaMemcpyDeviceToHost));
+  double mean = 0; for (auto v : h) mean += (double)v; mean /= 148;
+  const double bytes = (double)iters * depth * x * 4 * 32 * warps;
+  printf("probe ldtm2 warps=%d x%d depth=%d : %.1f cycles per group, %.1f B/clk per SM\n", warps, x, depth, mean / iters, bytes / mean);
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// probe 8: TMEM read latency / throughput UNDER a running MMA stream: thread 0 issues tcgen05.mma (M = 128, N, K = 16, accumulator in
+// columns [0, N)) back to back while warps 4.. read columns [256, 512) with 32x32b.x8 loads, `depth` loads in flight.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(640) ldtm3_kernel(int N, int mma_iters, int ld_iters, int depth, long long* cycles, unsigned* sink) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ int stop;
+  const int t = threadIdx.x, warp = t >> 5;
+  for (int e = t; e < (128 + 256) * 256 * 2 / 16; e += blockDim.x) reinterpret_cast<uint4*>(smem)[e] = make_uint4(0x3c003c00u, 0x3c003c00u, 0x3c003c00u, 0x3c003c00u);
+  if (t == 0) { mbar_init(smem_u32(&bar), 1); fence_barrier_init(); stop = 0; }
+  if (warp == 0) tmem_alloc<512>(smem_u32(&tmem_base_s));
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t sA = smem_u32(smem), sB = smem_u32(smem) + 128 * 256 * 2;
+  if (t == 0) {
+    const uint32_t idesc = make_idesc_f16(128, N);
+    for (int i = 0; i < mma_iters; ++i) {
+      const int k0 = (i & 15) * 16;
+      umma_ss(tmem, make_smem_desc(sA + (k0 / 8) * 128 * 16, 128 * 16, 128), make_smem_desc(sB + (k0 / 8) * N * 16, N * 16, 128), idesc, 1);
+    }
+    umma_commit(smem_u32(&bar));
+    mbar_wait(smem_u32(&bar), 0);
+  } else if (warp >= 4) {
+    const int w = warp - 4;
+    const uint32_t ta = tmem + ((uint32_t)((w & 3) * 32) << 16) + 256 + (uint32_t)((w >> 2) * 64);
+    unsigned acc = 0;
+    const long long t0 = clock64();
+    for (int i = 0; i < ld_iters; ++i) {
+      uint32_t v[4][8];
+#pragma unroll
+      for (int d = 0; d < 4; ++d)
+        if (d < depth) tmem_ld8(ta + ((i + d) & 1) * 32 + d * 8, v[d]);
+      tmem_ld_wait();
+#pragma unroll
+      for (int d = 0; d < 4; ++d)
+        if (d < depth) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc ^= v[d][j];
+        }
+    }
+    const long long t1 = clock64();
+    if (t == 128) cycles[blockIdx.x] = t1 - t0;
+    if (acc == 0x12345678u) *sink = acc;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
+static void probe_ldtm3(int N, int warps, int depth) {
+  long long* d; unsigned* sink; CK(cudaMalloc(&d, 148 * 8)); CK(cudaMalloc(&sink, 4));
+  const int ld_iters = 4000;
+  const size_t smem = (size_t)(128 + 256) * 256 * 2 + 1024;
+  CK(cudaFuncSetAttribute(ldtm3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // enough MMAs to outlast the loads: ~ld_iters * 400 cycles / (N / 2 cycles per MMA)
+  const int mma_iters = N > 0 ? (int)(ld_iters * 600.0 / (N / 2)) : 0;
+  ldtm3_kernel<<<148, (4 + warps) * 32, smem>>>(N > 0 ? N : 256, mma_iters, ld_iters, depth, d, sink);
+  CK(cudaDeviceSynchronize());
+  std::vector<long long> h(148);
+  CK(cudaMemcpy(h.data(), d, 148 * 8, cudaMemcpyDeviceToHost));
+  double mean = 0; for (auto v : h) mean += (double)v; mean /= 148;
+  printf("probe ldtm3 mma N=%d warps=%d depth=%d (x8) : %.1f cycles per group, %.1f B/clk per SM\n", N, warps, depth, mean / ld_iters,
+         (double)ld_iters * depth * 8 * 4 * 32 * warps / mean);
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// probe 9: throughput of the sine paths available to an epilogue: __sinf (FMUL + MUFU.SIN), a degree-11 odd polynomial after an exact
+// period reduction (FMA pipe only), and a 50/50 mix, with `warps` warps per SM (warps / 4 per scheduler), 32 independent values per thread.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sin_poly(float arg) {
+  // sin(arg) = sin(2 pi r), r = arg / 2 pi - rint(arg / 2 pi) in [-0.5, 0.5]; odd minimax-style polynomial in r (Taylor coefficients of sin(2 pi r)
+  // re-fitted would do better; Taylor to r^13 is ~2e-7 absolute on the interval after folding to [-0.25, 0.25])
+  float u = arg * 0.15915494309189535f;
+  float r = u - rintf(u);
+  // fold to [-0.25, 0.25]: sin(2 pi r) = sin(2 pi (0.5 sgn(r) - r))
+  float rf = copysignf(0.5f, r) - r;
+  r = fabsf(r) > 0.25f ? rf : r;
+  const float x = 6.283185307179586f * r, x2 = x * x;
+  float p = -2.5052108e-8f;
+  p = fmaf(p, x2, 2.7557319e-6f);
+  p = fmaf(p, x2, -1.9841270e-4f);
+  p = fmaf(p, x2, 8.3333333e-3f);
+  p = fmaf(p, x2, -1.6666667e-1f);
+  return fmaf(p * x2, x, x);
+}
+template <int MODE>
+__global__ void __launch_bounds__(512) sin_rate_kernel(int iters, long long* cycles, float* sink, float* err) {
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = 0.37f * (threadIdx.x + 1) + 1.7f * j;
+  float acc = 0.f, e = 0.f;
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float a = v[j] + (float)i * 0.01f;
+      float s;
+      if (MODE == 0) s = __sinf(a);
+      else if (MODE == 1) s = sin_poly(a);
+      else s = (j & 1) ? __sinf(a) : sin_poly(a);
+      acc += s;
+    }
+  }
+  const long long t1 = clock64();
+  if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+  // accuracy of the polynomial path against sinf on a sweep of arguments in the range the FiLM layers see (|arg| < 64)
+  for (int k = 0; k < 64; ++k) {
+    const float a = -64.f + (threadIdx.x * 64 + k) * (128.f / (512 * 64));
+    e = fmaxf(e, fabsf(sin_poly(a) - (float)sin((double)a)));
+  }
+  if (acc == 1234.5f) *sink = acc;
+  atomicMax(reinterpret_cast<int*>(err), __float_as_int(e));
+}
+static void probe_sin(int mode, int warps) {
+  long long* d; float* sink; float* err; CK(cudaMalloc(&d, 148 * 8)); CK(cudaMalloc(&sink, 4)); CK(cudaMalloc(&err, 4)); CK(cudaMemset(err, 0, 4));
+  const int iters = 2000;
+  if (mode == 0) sin_rate_kernel<0><<<148, warps * 32>>>(iters, d, sink, err);
+  else if (mode == 1) sin_rate_kernel<1><<<148, warps * 32>>>(iters, d, sink, err);
+  else sin_rate_kernel<2><<<148, warps * 32>>>(iters, d, sink, err);
+  CK(cudaDeviceSynchronize());
+  std::vector<long long> h(148); float herr = 0;
+  CK(cudaMemcpy(h.data(), d, 148 * 8, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(&herr, err, 4, cudaMemcpyDeviceToHost));
+  double mean = 0; for (auto v : h) mean += (double)v; mean /= 148;
+  printf("probe sin mode=%d (0 __sinf, 1 polynomial, 2 half/half) warps=%d : %.2f cycles per warp-sine per scheduler (%.1f sines/clk/SM), polynomial max |err| %.2e\n", mode, warps,
+         mean / iters / 32 / (warps / 4.0), 32.0 * warps * 32 * iters / mean, herr);
+}
+
 int main(int argc, char** argv) {
   const char* what = argc > 1 ? argv[1] : "all";
   int fails = 0;
@@ -397,6 +590,9 @@ int main(int argc, char** argv) {
   else if (!strcmp(what, "rate")) { probe_rate(atoi(argv[2]) != 0, atoi(argv[3]), atoi(argv[4]), argc > 5 ? atoi(argv[5]) : 0); }
   else if (!strcmp(what, "stream")) { fails += probe_stream(atoi(argv[2]), atoi(argv[3])); }
   else if (!strcmp(what, "ldtm")) { probe_ldtm(); }
+  else if (!strcmp(what, "sin")) { probe_sin(atoi(argv[2]), atoi(argv[3])); }
+  else if (!strcmp(what, "ldtm3")) { probe_ldtm3(atoi(argv[2]), atoi(argv[3]), atoi(argv[4])); }
+  else if (!strcmp(what, "ldtm2")) { probe_ldtm2(atoi(argv[2]), atoi(argv[3]), atoi(argv[4])); }
   else if (!strcmp(what, "rate2")) { probe_rate2(atoi(argv[2]), atoi(argv[3]), argc > 4 ? atoi(argv[4]) : 0); }
   else { printf("unknown probe %s\n", what); return 2; }
   return fails ? 1 : 0;
