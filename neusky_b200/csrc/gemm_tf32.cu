@@ -255,13 +255,13 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32_kernel(const Params p, c
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < ST; ++s) {
-      mbar_init(FULL + 8 * s, ROLES ? 128 : PROD_WARPS * 32);
+      mbar_init(FULL + 8 * s, ROLES ? 4 : PROD_WARPS * 32);      // ROLES: one arrival per splitter warp (lane 0 after __syncwarp)
       mbar_init(EMPTY + 8 * s, 1);
       if (ROLES) mbar_init(RAW + 8 * s, TMA ? 1 : 128);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(ACCF + 8 * b, 1);
-      mbar_init(ACCE + 8 * b, EPI_WARPS * 32);
+      mbar_init(ACCE + 8 * b, EPI_WARPS);                        // one arrival per epilogue warp
     }
     fence_barrier_init();
   }
@@ -300,7 +300,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32_kernel(const Params p, c
 #pragma unroll
             for (int j = 0; j < (int)((A_BYTES + B_BYTES) / 2048); ++j) fix_lo<LO_OFF>(sa, t128 + (uint32_t)j * 2048);
             fence_proxy_async_smem();
-            mbar_arrive(FULL + 8 * stage);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(FULL + 8 * stage);
             if (++stage == ST) { stage = 0; phase ^= 1; }
           }
         }
@@ -392,7 +393,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32_kernel(const Params p, c
               for (int j = 0; j < NP; ++j) fix_lo<LO_OFF>(sb, offB[j]);
             }
             fence_proxy_async_smem();
-            mbar_arrive(FULL + 8 * stage);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(FULL + 8 * stage);
             if (++stage == ST) { stage = 0; phase ^= 1; }
           }
         }
@@ -728,7 +730,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32_kernel(const Params p, c
         }
       }
       tc_fence_before();
-      mbar_arrive(ACCE + 8 * buf);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ACCE + 8 * buf);
      }
     }
   }

@@ -142,13 +142,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_field_tc_kernel(const Para
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NSTAGE; ++i) { mbar_init(bars + 8 * (B_WFULL + i), 1); mbar_init(bars + 8 * (B_WEMPTY + i), 1); }
-    mbar_init(bars + 8 * B_INFULL, PRO_THREADS);
+    mbar_init(bars + 8 * B_INFULL, PRO_THREADS / 32);      // one arrival per warp (lane 0 after __syncwarp): 512 per-thread arrivals on one
+                                                           // mbarrier serialise in shared memory, seven times per tile
     mbar_init(bars + 8 * B_INEMPTY, 1);
     mbar_init(bars + 8 * B_ACCA, 1);
     mbar_init(bars + 8 * B_ACCB, 1);
-    mbar_init(bars + 8 * B_EPI, EPI_THREADS);
+    mbar_init(bars + 8 * B_EPI, EPI_THREADS / 32);
     mbar_init(bars + 8 * B_B0DONE, 1);
-    mbar_init(bars + 8 * B_PGDONE, PRO_THREADS);
+    mbar_init(bars + 8 * B_PGDONE, PRO_THREADS / 32);
     fence_barrier_init();
   }
   // constant-1 columns (k = 256, 257) of X and Y, written once
@@ -262,7 +263,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_field_tc_kernel(const Para
 
     auto wait_a = [&]() { mbar_wait(bars + 8 * B_ACCA, ph_a); ph_a ^= 1; tc_fence_after(); };
     auto wait_b = [&]() { mbar_wait(bars + 8 * B_ACCB, ph_b); ph_b ^= 1; tc_fence_after(); };
-    auto done = [&]() { fence_proxy_async_smem(); tc_fence_before(); mbar_arrive(bars + 8 * B_EPI); };
+    auto done = [&]() { fence_proxy_async_smem(); tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(bars + 8 * B_EPI); };
     // generic 128-column pass: f(values of 16 columns, column base) -> 8 packed words -> two 16-byte chunks of `dst`
     auto store16 = [&](uint8_t* dst, int cb, const uint32_t (&pk)[8]) {
       *reinterpret_cast<uint4*>(dst + (cb * 2) * (TM * 16)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -483,7 +484,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_field_tc_kernel(const Para
 #pragma unroll
       for (int kc = 0; kc < 10; ++kc) *reinterpret_cast<uint4*>(d + kc * (TM * 16)) = make_uint4(w[kc * 4], w[kc * 4 + 1], w[kc * 4 + 2], w[kc * 4 + 3]);
       fence_proxy_async_smem();
-      mbar_arrive(bars + 8 * B_INFULL);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bars + 8 * B_INFULL);
     };
 
     uint32_t w[40];
@@ -525,7 +527,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_field_tc_kernel(const Para
       for (int i = 0; i < 4; ++i) tmem_ld8(tmem + TM_ACC_B + lane_off + 40 + i * 8, gfe[i]);
       tmem_ld_wait();
       tc_fence_before();
-      mbar_arrive(bars + 8 * B_PGDONE);     // the TMEM columns of B0 may be overwritten (C1)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bars + 8 * B_PGDONE);     // the TMEM columns of B0 may be overwritten (C1)
       // ---- hand the next tile's inputs over as soon as C0 of this tile has consumed IN ------------------------------
       if (next < P.n_tiles) {
         mbar_wait(bars + 8 * B_INEMPTY, ph_empty); ph_empty ^= 1;
