@@ -4,6 +4,7 @@ import numpy as np
 import pytest
 import torch
 
+from conftest import log_err
 from neusky_b200 import init as nb_init
 
 pytestmark = pytest.mark.gpu
@@ -298,3 +299,42 @@ def test_lambert_prep_thread_per_sample_matches_warp_per_ray(dev, R, S, D):
     unm = (mask == 0).double()
     ref = (wa.double() * (torch.einsum("rsd,dc->rsc", c * unm, rad[0].double()) / cnt[..., None]) * 0.75).sum(1)
     assert torch.allclose(lin_a.double(), ref, rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("Rs,R,D,NL", [(1, 3, 5, 1), (17, 40, 642, 9), (300, 300, 642, 20), (129, 500, 100, 33), (64, 64, 31, 70)])
+def test_compact_relight_cache_pass_vs_torch(dev, Rs, R, D, NL):
+    """csrc/relight_compact.cu: pack (fp16 rows in mma A-fragment order, per-row scale) + pass (warp-level mma, 8 / 16 / 32 codes per
+    read, several passes beyond 32) against an fp64 einsum on the SAME quantised operands (bit-level check of layout, fragment order,
+    tail tiles and the code-block templates; measured <= 4.8e-7 of the row scale) and against the unquantised product (fp16 operand rounding only)."""
+    from neusky_b200 import ops
+
+    g = torch.Generator().manual_seed(Rs * 7 + D + NL)
+    H = (torch.rand(R, D, 3, generator=g) ** 3) * torch.rand(R, 1, 1, generator=g) * 4.0
+    H[R // 2] = 0.0                                            # an all-zero row (scale 0) must shade to exactly 0
+    rows = torch.randperm(R, generator=g)[:Rs].sort().values.to(torch.int32)
+    rad = torch.exp(torch.randn(NL, D, 3, generator=g) * 1.5)          # HDR: several decades
+    H16, hscale = ops.relight_pack_h16(H.to(dev), rows.to(dev))
+    DP = (D + 15) // 16 * 16
+    assert H16.shape == (Rs, 3 * DP) and hscale.shape == (Rs,)
+    out = ops.relight_h16_multi(H16, hscale, rows.to(dev), R, D, rad.to(dev)).cpu().double()
+    assert out.shape == (NL, R, 3)
+    # rays without a cache row are exactly zero
+    mask = torch.ones(R, dtype=torch.bool); mask[rows.long()] = False
+    if mask.any():
+        assert float(out[:, mask].abs().max()) == 0.0
+    Hs = H[rows.long()].double()                                       # [Rs, D, 3]
+    exact = torch.einsum("rdc,ldc->lrc", Hs, rad.double())
+    # the kernel's own quantisation: rows scaled by their max, tables by theirs, both rounded to fp16
+    hmax = Hs.abs().amax(dim=(1, 2))
+    assert torch.allclose(hscale.cpu().double(), hmax, rtol=1e-6, atol=0)
+    Hq = torch.where(hmax[:, None, None] > 0, Hs / hmax[:, None, None].clamp_min(1e-300), torch.zeros_like(Hs)).float().half().double()
+    rmax = rad.double().abs().amax(dim=(1, 2))
+    rq = (rad.double() / rmax[:, None, None]).float().half().double()
+    quant = torch.einsum("rdc,ldc->lrc", Hq, rq) * hmax[None, :, None] * rmax[:, None, None]
+    got = out[:, rows.long()]
+    scale = (hmax[None, :, None] * rmax[:, None, None] * D).clamp_min(1e-30)
+    e_q = float(((got - quant).abs() / scale).max())
+    e_x = float(((got - exact).abs() / scale).max())
+    log_err(f"compact_relight_pass[{Rs},{D},{NL}]", vs_quantised=e_q, vs_exact=e_x)
+    assert e_q <= 2e-6, e_q              # fp32 accumulation of exact fp16 products: summation order / tensor-core accumulator rounding only
+    assert e_x <= 1e-4, e_x              # measured <= 1.9e-5
