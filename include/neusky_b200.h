@@ -90,6 +90,16 @@ int64_t nsk_sdf_simt_weights_floats(void);
 int nsk_sdf_field_simt_fwd(const float* x, int64_t n, const float* sdf_weights, const float* hash_table,
                            const float* scalings, int num_levels, int log2_T, float* sdf, float* grad, float* albedo,
                            float* geo, void* stream);
+/* The same two kernels on an IMPORTED tiny-cuda-nn grid (the reference's encodings are tcnn.Encoding modules, sdf_albedo_field.py:117-130;
+ * neusky_b200/tcnn_import.py): grid_meta [L][4] int32 = (float bits of scale, resolution, size, dense) per level, 16-byte aligned, NULL =
+ * the nerfstudio torch grid of the plain entry points; smoothstep = tcnn's interpolation flag (the analytic normal carries its derivative).
+ * tcnn semantics are restated from memory and pinned by self-consistency tests only. */
+int nsk_sdf_field_tc_fwd_ex(const float* x, int64_t n, const void* sdf_weights, const float* hash_table,
+                            const float* scalings, int num_levels, int log2_T, const int32_t* grid_meta, int smoothstep,
+                            float* sdf, float* grad, float* albedo, void* stream);
+int nsk_sdf_field_simt_fwd_ex(const float* x, int64_t n, const float* sdf_weights, const float* hash_table,
+                              const float* scalings, int num_levels, int log2_T, const int32_t* grid_meta, int smoothstep,
+                              float* sdf, float* grad, float* albedo, float* geo, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K3  NeuS logistic-CDF alpha + transmittance + compositing, one warp per ray.
@@ -275,6 +285,20 @@ int nsk_sky_shade_tc2_fwd(const float* points, int64_t R, const float* normals, 
                           const float* scalings, int num_levels, int log2_T, float radius, float threshold,
                           float sigmoid_scale, float* rgb_lin, float* vis_out, float* ddf_out, float* term_out,
                           void* stream);
+/* K4 on an imported tiny-cuda-nn position grid (directional_distance_field.py:139-156 builds a tcnn.Encoding): grid_meta / smoothstep as for
+ * nsk_sdf_field_tc_fwd_ex; NULL = the plain entry points above. */
+int nsk_sky_shade_tc2_fwd_ex(const float* points, int64_t R, const float* normals, const float* wa,
+                             const float* inv_count, int S, const float* dirs, int Dp, const float* radiance,
+                             const int32_t* cam, const void* ddf_weights, const float* hash_table,
+                             const float* scalings, int num_levels, int log2_T, const int32_t* grid_meta, int smoothstep,
+                             float radius, float threshold, float sigmoid_scale, float* rgb_lin, float* vis_out, float* ddf_out,
+                             float* term_out, void* stream);
+int nsk_sky_shade_simt_fwd_ex(const float* points, int64_t R, const float* normals, const float* wa,
+                              const float* inv_count, int S, const float* dirs, int Dp, const float* radiance,
+                              const int32_t* cam, const float* ddf_weights, const float* hash_table,
+                              const float* scalings, int num_levels, int log2_T, const int32_t* grid_meta, int smoothstep,
+                              float radius, float threshold, float sigmoid_scale, float* rgb_lin, float* vis_out, float* ddf_out,
+                              float* term_out, void* stream);
 int64_t nsk_ddf_tc2_weights_bytes(void);
 int64_t nsk_ddf_simt_weights_floats(void);
 int64_t nsk_ddf_tc_weights_bytes(void);

@@ -61,6 +61,52 @@ __device__ __forceinline__ void hash_corners(float sx, float sy, float sz, uint3
   idx[7] = hash3(fx, cy, fz, mask);
 }
 
+// ---- grid semantics switch (SURVEY A.3 "tcnn differences", neusky_b200/tcnn_import.py) ------------------------------------------------
+// meta == nullptr: the nerfstudio torch HashEncoding the rest of this file implements (scale from `scalings`, corners floor / ceil,
+// linear weights, prime hash & mask).  meta != nullptr: tiny-cuda-nn's grid as imported from a reference checkpoint: per level
+// (float bits of scale, resolution, size, dense) -- pos = x * scale + 0.5, corners floor / floor + 1, dense index x + y res + z res^2
+// or the same prime hash, both modulo the level's size, linear or smoothstep weights.  The table keeps our [L * T, F] layout.
+struct GridMode {
+  const int4* meta;
+  int smoothstep;
+};
+// Corners + interpolation weights of level `lev` at the (already normalised) position p.  `ox, oy, oz` are the weights of the UPPER corner
+// per axis in the corner order of hash_corners() (so hash_interp / hash_interp_grad apply unchanged); `dw` = d weight / d (grid
+// position) per axis (1 for linear weights) and `scale` = d (grid position) / d p: the chain rule factors of the analytic normal.
+__device__ __forceinline__ void grid_corners(const GridMode gm, int lev, float px, float py, float pz, float ns_scale, uint32_t mask, uint32_t idx[8],
+                                             float& ox, float& oy, float& oz, float (&dw)[3], float& scale) {
+  if (gm.meta == nullptr) {
+    hash_corners(__fmul_rn(px, ns_scale), __fmul_rn(py, ns_scale), __fmul_rn(pz, ns_scale), mask, idx, ox, oy, oz);
+    dw[0] = dw[1] = dw[2] = 1.0f;
+    scale = ns_scale;
+    return;
+  }
+  const int4 m = __ldg(gm.meta + lev);
+  scale = __int_as_float(m.x);
+  const uint32_t res = (uint32_t)m.y, size = (uint32_t)m.z;
+  const bool dense = m.w != 0;
+  const float p[3] = {px, py, pz};
+  uint32_t g[3];
+  float w[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const float pos = fmaf(p[d], scale, 0.5f);
+    const float fl = floorf(pos);
+    g[d] = (uint32_t)(int)fl;
+    const float t = pos - fl;
+    w[d] = gm.smoothstep ? t * t * (3.0f - 2.0f * t) : t;
+    dw[d] = gm.smoothstep ? 6.0f * t * (1.0f - t) : 1.0f;
+  }
+  ox = w[0]; oy = w[1]; oz = w[2];
+  // corner order of hash_corners(): "c" = upper corner (g + 1), "f" = lower corner (g)
+  const int ux[8] = {1, 1, 0, 0, 1, 1, 0, 0}, uy[8] = {1, 0, 0, 1, 1, 0, 0, 1}, uz[8] = {1, 1, 1, 1, 0, 0, 0, 0};
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const uint32_t gx = g[0] + ux[c], gy = g[1] + uy[c], gz = g[2] + uz[c];
+    idx[c] = (dense ? gx + gy * res + gz * res * res : (gx ^ (gy * 2654435761u) ^ (gz * 805459861u))) % size;
+  }
+}
+
 // Interpolation in the oracle's operation order, without FMA contraction (bit-exact vs torch).
 __device__ __forceinline__ float lerp_ns(float a, float b, float o) {
   // a*o + b*(1-o)

@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(FT, 1)
 sdf_field_simt_kernel(const float* __restrict__ x, int64_t n, const float* __restrict__ W, SdfLayout y,
                       const float2* __restrict__ table, const float* __restrict__ scalings, int log2_T, int flags,
                       float* __restrict__ sdf_out, float* __restrict__ grad_out, float* __restrict__ albedo_out,
-                      float* __restrict__ geo_out) {
+                      float* __restrict__ geo_out, const GridMode gm) {
   extern __shared__ __align__(16) float smem[];
   float* in = smem;                         // [72][FR]   x, PE, hash features
   float* bufA = in + 72 * FR;               // [256][FR]  a0 -> geo feature
@@ -120,10 +120,9 @@ sdf_field_simt_kernel(const float* __restrict__ x, int64_t n, const float* __res
       const int r = t % FR, sub = t / FR;
       const float px = posb[r], py = posb[FR + r], pz = posb[2 * FR + r];
       for (int lev = sub; lev < SDF_LEVELS; lev += FT / FR) {
-        const float s = scalings[lev];
         uint32_t idx[8];
-        float ox, oy, oz;
-        hash_corners(__fmul_rn(px, s), __fmul_rn(py, s), __fmul_rn(pz, s), mask, idx, ox, oy, oz);
+        float ox, oy, oz, dw[3], s;
+        grid_corners(gm, lev, px, py, pz, scalings[lev], mask, idx, ox, oy, oz, dw, s);
         const float2* tl = table + ((size_t)lev << log2_T);
         float2 f[8];
 #pragma unroll
@@ -205,10 +204,9 @@ sdf_field_simt_kernel(const float* __restrict__ x, int64_t n, const float* __res
         const float px = posb[r], py = posb[FR + r], pz = posb[2 * FR + r];
         float a0 = 0.f, a1 = 0.f, a2 = 0.f;    // d sdf / d pos accumulated over this thread's levels
         for (int lev = sub; lev < SDF_LEVELS; lev += FT / FR) {
-          const float s = scalings[lev];
           uint32_t idx[8];
-          float ox, oy, oz;
-          hash_corners(__fmul_rn(px, s), __fmul_rn(py, s), __fmul_rn(pz, s), mask, idx, ox, oy, oz);
+          float ox, oy, oz, dw[3], s;
+          grid_corners(gm, lev, px, py, pz, scalings[lev], mask, idx, ox, oy, oz, dw, s);
           const float2* tl = table + ((size_t)lev << log2_T);
           float fa[8], fb[8];
 #pragma unroll
@@ -217,9 +215,9 @@ sdf_field_simt_kernel(const float* __restrict__ x, int64_t n, const float* __res
           hash_interp_grad(fa, ox, oy, oz, da);
           hash_interp_grad(fb, ox, oy, oz, db);
           const float ga = g0[(39 + 2 * lev) * FR + r], gb = g0[(39 + 2 * lev + 1) * FR + r];
-          a0 += s * (da[0] * ga + db[0] * gb);
-          a1 += s * (da[1] * ga + db[1] * gb);
-          a2 += s * (da[2] * ga + db[2] * gb);
+          a0 += s * dw[0] * (da[0] * ga + db[0] * gb);
+          a1 += s * dw[1] * (da[1] * ga + db[1] * gb);
+          a2 += s * dw[2] * (da[2] * ga + db[2] * gb);
         }
         // d sdf / d x += J^T (d sdf / d pos)
         atomicAdd(&gx[0 * FR + r], jac[0 * FR + r] * a0 + jac[3 * FR + r] * a1 + jac[6 * FR + r] * a2);
@@ -285,7 +283,14 @@ extern "C" int64_t nsk_sdf_simt_weights_floats(void) { return nsk::sdf_layout().
 extern "C" int nsk_sdf_field_simt_fwd(const float* x, int64_t n, const float* sdf_weights, const float* hash_table,
                                       const float* scalings, int num_levels, int log2_T, float* sdf, float* grad,
                                       float* albedo, float* geo, void* stream) {
+  return nsk_sdf_field_simt_fwd_ex(x, n, sdf_weights, hash_table, scalings, num_levels, log2_T, nullptr, 0, sdf, grad, albedo, geo, stream);
+}
+
+extern "C" int nsk_sdf_field_simt_fwd_ex(const float* x, int64_t n, const float* sdf_weights, const float* hash_table,
+                                         const float* scalings, int num_levels, int log2_T, const int32_t* grid_meta, int smoothstep,
+                                         float* sdf, float* grad, float* albedo, float* geo, void* stream) {
   NSK_REQUIRE(num_levels == nsk::SDF_LEVELS, "nsk_sdf_field_simt_fwd: the SDF position encoding has 16 levels");
+  NSK_REQUIRE(grid_meta == nullptr || (reinterpret_cast<uintptr_t>(grid_meta) & 15) == 0, "nsk_sdf_field_simt_fwd_ex: grid_meta must be 16-byte aligned");
   if (n == 0) return 0;
   NSK_REQUIRE(x && sdf_weights && hash_table && scalings && sdf, "nsk_sdf_field_simt_fwd: null pointer");
   const size_t smem = (size_t)(72 + 4 * nsk::SDF_HID + 72 + 18) * nsk::FR * sizeof(float);
@@ -300,6 +305,6 @@ extern "C" int nsk_sdf_field_simt_fwd(const float* x, int64_t n, const float* sd
   const int flags = (grad ? 1 : 0) | (albedo ? 2 : 0);
   nsk::sdf_field_simt_kernel<<<(unsigned)grid, nsk::FT, smem, nsk::as_stream(stream)>>>(
       x, n, sdf_weights, nsk::sdf_layout(), reinterpret_cast<const float2*>(hash_table), scalings, log2_T, flags, sdf, grad,
-      albedo, geo);
+      albedo, geo, nsk::GridMode{reinterpret_cast<const int4*>(grid_meta), smoothstep});
   return nsk::check_launch("sdf_field_simt_kernel");
 }

@@ -107,6 +107,7 @@ struct Params {
   const uint8_t* blob; const float2* table; const float* scalings; int log2_T;
   float* sdf; float* grad; float* albedo;
   int64_t n_tiles;
+  GridMode gm;      // nerfstudio torch grid (meta == nullptr) or an imported tiny-cuda-nn grid (nsk_common.cuh)
 };
 
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
@@ -428,12 +429,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_field_tc_kernel(const Para
       __sincosf(TWO_PI * t, &sn, &cs);
     };
     // 4 hash levels per batch: 32 independent 8-byte gathers in flight per thread
-    auto gather4 = [&](const float (&pos)[3], int lev0, float2 (&f)[4][8], float (&o)[4][3]) {
+    auto gather4 = [&](const float (&pos)[3], int lev0, float2 (&f)[4][8], float (&o)[4][3], float (&dwv)[4][3], float (&scv)[4]) {
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const float sc = __ldg(P.scalings + lev0 + u);
         uint32_t idx[8];
-        hash_corners(__fmul_rn(pos[0], sc), __fmul_rn(pos[1], sc), __fmul_rn(pos[2], sc), mask, idx, o[u][0], o[u][1], o[u][2]);
+        grid_corners(P.gm, lev0 + u, pos[0], pos[1], pos[2], __ldg(P.scalings + lev0 + u), mask, idx, o[u][0], o[u][1], o[u][2], dwv[u], scv[u]);
         const float2* tl = P.table + ((size_t)(lev0 + u) << P.log2_T);
 #pragma unroll
         for (int c = 0; c < 8; ++c) f[u][c] = __ldg(tl + idx[c]);
@@ -461,8 +461,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_field_tc_kernel(const Para
 #pragma unroll
       for (int lev0 = 0; lev0 < SDF_LEVELS; lev0 += 4) {
         float2 f[4][8];
-        float o[4][3];
-        gather4(pos, lev0, f, o);
+        float o[4][3], dwv[4][3], scv[4];
+        gather4(pos, lev0, f, o, dwv, scv);
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const float2 r = hash_interp(f[u], o[u][0], o[u][1], o[u][2]);
@@ -542,12 +542,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_field_tc_kernel(const Para
 #pragma unroll
         for (int lev0 = 0; lev0 < SDF_LEVELS; lev0 += 4) {
           float2 f[4][8];
-          float o[4][3];
-          gather4(pos, lev0, f, o);
+          float o[4][3], dwv[4][3], scv[4];
+          gather4(pos, lev0, f, o, dwv, scv);
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             const int lev = lev0 + u;
-            const float sc = __ldg(P.scalings + lev);
+            const float sc = scv[u];
             float fa[8], fb[8];
 #pragma unroll
             for (int c = 0; c < 8; ++c) { fa[c] = f[u][c].x; fb[c] = f[u][c].y; }
@@ -555,9 +555,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) sdf_field_tc_kernel(const Para
             hash_interp_grad(fa, o[u][0], o[u][1], o[u][2], da);
             hash_interp_grad(fb, o[u][0], o[u][1], o[u][2], db);
             const float ga = __uint_as_float(gfe[(2 * lev) >> 3][(2 * lev) & 7]), gb = __uint_as_float(gfe[(2 * lev + 1) >> 3][(2 * lev + 1) & 7]);
-            a0 += sc * (da[0] * ga + db[0] * gb);
-            a1 += sc * (da[1] * ga + db[1] * gb);
-            a2 += sc * (da[2] * ga + db[2] * gb);
+            a0 += sc * dwv[u][0] * (da[0] * ga + db[0] * gb);
+            a1 += sc * dwv[u][1] * (da[1] * ga + db[1] * gb);
+            a2 += sc * dwv[u][2] * (da[2] * ga + db[2] * gb);
           }
         }
         gx[0] += J[0] * a0 + J[3] * a1 + J[6] * a2;
@@ -583,7 +583,14 @@ extern "C" int64_t nsk_sdf_tc_weights_bytes(void) { return nsk::sdftc::BLOB_BYTE
 extern "C" int nsk_sdf_field_tc_fwd(const float* x, int64_t n, const void* sdf_weights, const float* hash_table,
                                     const float* scalings, int num_levels, int log2_T, float* sdf, float* grad,
                                     float* albedo, void* stream) {
+  return nsk_sdf_field_tc_fwd_ex(x, n, sdf_weights, hash_table, scalings, num_levels, log2_T, nullptr, 0, sdf, grad, albedo, stream);
+}
+
+extern "C" int nsk_sdf_field_tc_fwd_ex(const float* x, int64_t n, const void* sdf_weights, const float* hash_table,
+                                       const float* scalings, int num_levels, int log2_T, const int32_t* grid_meta, int smoothstep,
+                                       float* sdf, float* grad, float* albedo, void* stream) {
   using namespace nsk::sdftc;
+  NSK_REQUIRE(grid_meta == nullptr || (reinterpret_cast<uintptr_t>(grid_meta) & 15) == 0, "nsk_sdf_field_tc_fwd_ex: grid_meta must be 16-byte aligned");
   NSK_REQUIRE(num_levels == nsk::SDF_LEVELS, "nsk_sdf_field_tc_fwd: the SDF position encoding has 16 levels");
   if (n == 0) return 0;
   NSK_REQUIRE(x && sdf_weights && hash_table && scalings && sdf && grad && albedo, "nsk_sdf_field_tc_fwd: null pointer");
@@ -598,6 +605,7 @@ extern "C" int nsk_sdf_field_tc_fwd(const float* x, int64_t n, const void* sdf_w
   P.x = x; P.n = n; P.blob = reinterpret_cast<const uint8_t*>(sdf_weights);
   P.table = reinterpret_cast<const float2*>(hash_table); P.scalings = scalings; P.log2_T = log2_T;
   P.sdf = sdf; P.grad = grad; P.albedo = albedo;
+  P.gm = nsk::GridMode{reinterpret_cast<const int4*>(grid_meta), smoothstep};
   P.n_tiles = (n + TM - 1) / TM;
   const int64_t grid = P.n_tiles < num_sms ? P.n_tiles : num_sms;
   sdf_field_tc_kernel<<<(unsigned)grid, NUM_THREADS, SMEM_BYTES, nsk::as_stream(stream)>>>(P);

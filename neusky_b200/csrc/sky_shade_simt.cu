@@ -68,7 +68,7 @@ sky_shade_simt_kernel(const float* __restrict__ points, int64_t R, const float* 
                       const int32_t* __restrict__ cam, const float* __restrict__ W, SimtLayout y,
                       const float2* __restrict__ table, const float* __restrict__ scalings, int L, int log2_T,
                       float radius, float thr, float sig_scale, float* __restrict__ rgb_lin, float* __restrict__ vis_out,
-                      float* __restrict__ ddf_out, float* __restrict__ term_out) {
+                      float* __restrict__ ddf_out, float* __restrict__ term_out, const GridMode gm) {
   extern __shared__ __align__(16) float smem[];
   float* bufM = smem;                        // [256][SR]  mapping activations (m5 at the end)
   float* bufA = bufM + DDF_HID * SR;         // [256][SR]
@@ -109,10 +109,9 @@ sky_shade_simt_kernel(const float* __restrict__ points, int64_t R, const float* 
       const int r = t % SR, sub = t / SR;  // 8 sub-groups x 2 levels
       const float qx = geo[r], qy = geo[SR + r], qz = geo[2 * SR + r];
       for (int lev = sub; lev < L; lev += ST / SR) {
-        const float s = scalings[lev];
         uint32_t idx[8];
-        float ox, oy, oz;
-        hash_corners(__fmul_rn(qx, s), __fmul_rn(qy, s), __fmul_rn(qz, s), mask, idx, ox, oy, oz);
+        float ox, oy, oz, dw_[3], sc_;
+        grid_corners(gm, lev, qx, qy, qz, scalings[lev], mask, idx, ox, oy, oz, dw_, sc_);
         const float2* tl = table + ((size_t)lev << log2_T);
         float2 f[8];
 #pragma unroll
@@ -213,6 +212,17 @@ extern "C" int nsk_sky_shade_simt_fwd(const float* points, int64_t R, const floa
                                       const float* scalings, int num_levels, int log2_T, float radius, float threshold,
                                       float sigmoid_scale, float* rgb_lin, float* vis_out, float* ddf_out,
                                       float* term_out, void* stream) {
+  return nsk_sky_shade_simt_fwd_ex(points, R, normals, wa, inv_count, S, dirs, Dp, radiance, cam, ddf_weights, hash_table, scalings, num_levels, log2_T,
+                                   nullptr, 0, radius, threshold, sigmoid_scale, rgb_lin, vis_out, ddf_out, term_out, stream);
+}
+
+extern "C" int nsk_sky_shade_simt_fwd_ex(const float* points, int64_t R, const float* normals, const float* wa,
+                                         const float* inv_count, int S, const float* dirs, int Dp, const float* radiance,
+                                         const int32_t* cam, const float* ddf_weights, const float* hash_table,
+                                         const float* scalings, int num_levels, int log2_T, const int32_t* grid_meta, int smoothstep,
+                                         float radius, float threshold, float sigmoid_scale, float* rgb_lin, float* vis_out, float* ddf_out,
+                                         float* term_out, void* stream) {
+  NSK_REQUIRE(grid_meta == nullptr || (reinterpret_cast<uintptr_t>(grid_meta) & 15) == 0, "nsk_sky_shade_simt_fwd_ex: grid_meta must be 16-byte aligned");
   NSK_REQUIRE(num_levels == nsk::DDF_LEVELS, "nsk_sky_shade_simt_fwd: the DDF position encoding has 16 levels");
   if (R == 0 || Dp == 0) return 0;
   NSK_REQUIRE(S >= 1, "nsk_sky_shade_simt_fwd: S must be >= 1");
@@ -230,6 +240,6 @@ extern "C" int nsk_sky_shade_simt_fwd(const float* points, int64_t R, const floa
   nsk::sky_shade_simt_kernel<<<(unsigned)grid, nsk::ST, smem, nsk::as_stream(stream)>>>(
       points, R, normals, wa, inv_count, S, dirs, Dp, radiance, cam, ddf_weights, nsk::simt_layout(),
       reinterpret_cast<const float2*>(hash_table), scalings, num_levels, log2_T, radius, threshold, sigmoid_scale, rgb_lin,
-      vis_out, ddf_out, term_out);
+      vis_out, ddf_out, term_out, nsk::GridMode{reinterpret_cast<const int4*>(grid_meta), smoothstep});
   return nsk::check_launch("sky_shade_simt_kernel");
 }

@@ -100,6 +100,7 @@ struct Params {
   float radius, thr, sig_scale;
   float* rgb_lin; float* vis_out; float* ddf_out; float* term_out;
   int64_t n_pairs, n_tiles, n_tp;   // n_tp = tile pairs
+  GridMode gm;                // DDF position grid: nerfstudio torch semantics (meta == nullptr) or an imported tiny-cuda-nn grid
   unsigned long long* prof;   // diagnostics: [grid][16] cycle counters (NULL = off)
   float* dbg;   // diagnostics: [10][128][256] activations of the first tile of CTA 0 (NULL = off)
 };
@@ -520,9 +521,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) sky_
         float ox[2], oy[2], oz[2];
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
-          const float s = __ldg(P.scalings + lev + u);
           uint32_t idx[8];
-          hash_corners(__fmul_rn(qv[0], s), __fmul_rn(qv[1], s), __fmul_rn(qv[2], s), mask, idx, ox[u], oy[u], oz[u]);
+          float dw_[3], sc_;
+          grid_corners(P.gm, lev + u, qv[0], qv[1], qv[2], __ldg(P.scalings + lev + u), mask, idx, ox[u], oy[u], oz[u], dw_, sc_);
           const float2* tl = P.table + ((size_t)(lev + u) << P.log2_T);
 #pragma unroll
           for (int c = 0; c < 8; ++c) f[u][c] = __ldg(tl + idx[c]);
@@ -600,7 +601,18 @@ extern "C" int nsk_sky_shade_tc2_fwd(const float* points, int64_t R, const float
                                     const float* scalings, int num_levels, int log2_T, float radius, float threshold,
                                     float sigmoid_scale, float* rgb_lin, float* vis_out, float* ddf_out, float* term_out,
                                     void* stream) {
+  return nsk_sky_shade_tc2_fwd_ex(points, R, normals, wa, inv_count, S, dirs, Dp, radiance, cam, ddf_weights, hash_table, scalings, num_levels, log2_T,
+                                  nullptr, 0, radius, threshold, sigmoid_scale, rgb_lin, vis_out, ddf_out, term_out, stream);
+}
+
+extern "C" int nsk_sky_shade_tc2_fwd_ex(const float* points, int64_t R, const float* normals, const float* wa,
+                                       const float* inv_count, int S, const float* dirs, int Dp, const float* radiance,
+                                       const int32_t* cam, const void* ddf_weights, const float* hash_table,
+                                       const float* scalings, int num_levels, int log2_T, const int32_t* grid_meta, int smoothstep,
+                                       float radius, float threshold, float sigmoid_scale, float* rgb_lin, float* vis_out, float* ddf_out,
+                                       float* term_out, void* stream) {
   using namespace nsk::tcs2;
+  NSK_REQUIRE(grid_meta == nullptr || (reinterpret_cast<uintptr_t>(grid_meta) & 15) == 0, "nsk_sky_shade_tc2_fwd_ex: grid_meta must be 16-byte aligned");
   NSK_REQUIRE(num_levels == nsk::DDF_LEVELS, "nsk_sky_shade_tc2_fwd: the DDF position encoding has 16 levels");
   if (R == 0 || Dp == 0) return 0;
   NSK_REQUIRE(S >= 0, "nsk_sky_shade_tc2_fwd: S must be >= 0");
@@ -622,6 +634,7 @@ extern "C" int nsk_sky_shade_tc2_fwd(const float* points, int64_t R, const float
   P.table = reinterpret_cast<const float2*>(hash_table); P.scalings = scalings; P.log2_T = log2_T;
   P.radius = radius; P.thr = threshold; P.sig_scale = sigmoid_scale;
   P.rgb_lin = rgb_lin; P.vis_out = vis_out; P.ddf_out = ddf_out; P.term_out = term_out;
+  P.gm = nsk::GridMode{reinterpret_cast<const int4*>(grid_meta), smoothstep};
   P.dbg = g_nsk_tc2_debug_dump;
   P.prof = g_nsk_tc2_prof;
   P.n_pairs = R * (int64_t)Dp;

@@ -181,9 +181,20 @@ class _HashGrid(nn.Module):
         self._tcnn_meta = None
 
     def require_native(self, who: str) -> None:
+        """Training paths only: the differentiable kernels (hash-encode backward, train.py) implement the nerfstudio torch grid."""
         if self.tcnn_levels is not None:
-            raise NotImplementedError(f"{who}: this hash grid was imported from a tiny-cuda-nn checkpoint; the fused field kernels evaluate the nerfstudio "
-                                      "torch-grid semantics only (DESIGN.md section 6).  The stand-alone encode (module call) supports the imported grid.")
+            raise NotImplementedError(f"{who}: this hash grid was imported from a tiny-cuda-nn checkpoint; it renders through the eval kernels "
+                                      "(K1 / K2 / K4 take the imported grid), but training from it is not supported (DESIGN.md section 6).")
+
+    def grid_args(self) -> Dict[str, Any]:
+        """kwargs for ops.sdf_field / ops.sky_shade: the per-level table of an imported tiny-cuda-nn grid (None = nerfstudio torch grid)."""
+        if self.tcnn_levels is None:
+            return {"grid_meta": None, "smoothstep": True}
+        from .tcnn_import import tcnn_level_meta
+
+        if self._tcnn_meta is None or self._tcnn_meta.device != self.hash_table.device:
+            self._tcnn_meta = tcnn_level_meta(self.tcnn_levels, self.hash_table.device)
+        return {"grid_meta": self._tcnn_meta, "smoothstep": bool(self.tcnn_smoothstep)}
 
     def forward(self, x: Tensor) -> Tensor:
         from . import autograd as nba
@@ -279,6 +290,7 @@ class SDFAlbedoField(nn.Module):
         self.use_average_appearance_embedding = use_average_appearance_embedding
         self.use_grid_feature, self.divide_factor = c.use_grid_feature, c.divide_factor
         self.encoding = _HashGrid(c.num_levels, c.log2_hashmap_size, c.features_per_level, c.base_res, c.max_res)   # :117-130
+        self.encoding.tcnn_smoothstep = bool(c.smoothstep)      # nerfstudio SDFField passes "interpolation": "Smoothstep" to tcnn when config.smoothstep
         in_dim = 3 + 36 + self.encoding.n_output_dims
         dims = [in_dim] + [c.hidden_dim] * c.num_layers + [1 + c.geo_feat_dim]
         self.num_layers = len(dims)
@@ -344,36 +356,36 @@ class SDFAlbedoField(nn.Module):
 
     def forward_geonetwork(self, inputs: Tensor) -> Tensor:
         """x [N,3] -> [N, 1 + geo_feat_dim] (sdf | geometry feature), nerfstudio SDFField.forward_geonetwork [A.4]: exact fp32 kernel."""
-        self.encoding.require_native("SDFAlbedoField.forward_geonetwork")
         x = inputs.reshape(-1, 3)
         f = ops.sdf_field(x, self._blob("simt"), self.encoding.hash_table.detach(), self.encoding.scalings, self.encoding.log2_T,
-                          want_grad=False, want_albedo=False, want_geo=True, impl="simt")
+                          want_grad=False, want_albedo=False, want_geo=True, impl="simt", **self.encoding.grid_args())
         return torch.cat([f["sdf"], f["geo"]], dim=-1)
 
     def get_sdf_at_pos(self, positions: Tensor) -> Tensor:
         """:169-174 -> [N,1].  Differentiable (w.r.t. positions to first order, the hash table and the weights) when autograd is on:
         DDFModel's sdf_at_termination branch trains through it (ddf_model.py:241-251)."""
-        self.encoding.require_native("SDFAlbedoField.get_sdf_at_pos")
         x = positions.reshape(-1, 3)
         if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
             from . import train
 
+            self.encoding.require_native("SDFAlbedoField.get_sdf_at_pos (differentiable)")
             sdf, _, _ = train.sdf_field(self._train_cfg(), x.contiguous(), self.encoding.hash_table, self._train_weights(), want_normals=False, want_albedo=False)
             return sdf[:, None]
         return ops.sdf_field(x, self._blob("simt"), self.encoding.hash_table.detach(), self.encoding.scalings, self.encoding.log2_T,
-                             want_grad=False, want_albedo=False, impl="simt")["sdf"]
+                             want_grad=False, want_albedo=False, impl="simt", **self.encoding.grid_args())["sdf"]
 
     def _field(self, x: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
         """x [...,3] -> (sdf [...,1], gradient [...,3], albedo [...,3])."""
-        self.encoding.require_native("SDFAlbedoField")
         lead = x.shape[:-1]
         if _need_autograd(list(self.parameters())):
             from . import train
 
+            self.encoding.require_native("SDFAlbedoField (training)")
             sdf, grad, alb = train.sdf_field(self._train_cfg(), x.reshape(-1, 3).contiguous(), self.encoding.hash_table, self._train_weights())
             return sdf.reshape(*lead, 1), grad.reshape(*lead, 3), alb.reshape(*lead, 3)
         impl = self.config.impl
-        f = ops.sdf_field(x, self._blob(impl), self.encoding.hash_table.detach(), self.encoding.scalings, self.encoding.log2_T, impl=impl)
+        f = ops.sdf_field(x, self._blob(impl), self.encoding.hash_table.detach(), self.encoding.scalings, self.encoding.log2_T, impl=impl,
+                          **self.encoding.grid_args())
         return f["sdf"], f["gradient"], f["albedo"]
 
     def get_alpha(self, ray_samples, sdf: Optional[Tensor] = None, gradients: Optional[Tensor] = None) -> Tensor:
@@ -499,6 +511,7 @@ class DirectionalDistanceField(nn.Module):
         self.config = c
         self.ddf_radius = float(ddf_radius)
         self.position_encoding = _HashGrid(16, 19, 2, 16, 2048)                                 # :138-156
+        self.position_encoding.tcnn_smoothstep = False          # no "interpolation" key in the reference's encoding_config: tcnn's default, linear
         self.direction_encoding = None                                                          # NeRFEncoding has no parameters (:189-192)
         self.num_depth_components = c.num_dirac_components
         self.num_weight_components = c.num_dirac_components - 1

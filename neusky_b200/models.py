@@ -320,8 +320,6 @@ class NeuSkyFactoModel(nn.Module):
 
         if self.visibility_field is None:
             raise ValueError("NeuSkyFactoModel: use_visibility needs a visibility_field (DDFModel)")
-        self.field.encoding.require_native("NeuSkyFactoModel")
-        self.visibility_field.field.position_encoding.require_native("NeuSkyFactoModel")
         mods = [self.field, self.visibility_field.field, self.illumination_field, self.proposal_networks]
         key = _versions([p for m in mods for p in m.parameters()])
         if self._renderer is None or self._renderer_key != key:
@@ -333,6 +331,9 @@ class NeuSkyFactoModel(nn.Module):
                             proposal_params=[{n: p.detach() for n, p in net.named_parameters()} for net in self.proposal_networks],
                             proposal_max_res=[net.max_res for net in self.proposal_networks], num_proposal_samples_per_ray=c.num_proposal_samples_per_ray,
                             proposal_log2_T=self.proposal_networks[0].log2_T, ddf_log2_T=self.visibility_field.field.position_encoding.log2_T)
+            ga, gd = self.field.encoding.grid_args(), self.visibility_field.field.position_encoding.grid_args()      # imported tcnn grids, if any
+            r.sdf_grid_meta, r.sdf_grid_smoothstep = ga["grid_meta"], ga["smoothstep"]
+            r.shader.grid_meta, r.shader.grid_smoothstep = gd["grid_meta"], gd["smoothstep"]
             r.shader.only_upper = c.only_upperhemisphere_visibility
             r.shader.lower_vis = 1.0 if c.lower_hermisphere_visibility else 0.0
             self._renderer, self._renderer_key = r, key

@@ -172,9 +172,11 @@ def hash_indices(x: Tensor, scalings: Tensor, log2_T: int) -> Tuple[Tensor, Tens
 
 # ------------------------------------------------------------------------------------------- K2
 def sdf_field(x: Tensor, blob: Tensor, hash_table: Tensor, scalings: Tensor, log2_T: int, want_grad: bool = True, want_albedo: bool = True,
-              want_geo: bool = False, impl: str = "simt") -> Dict[str, Tensor]:
+              want_geo: bool = False, impl: str = "simt", grid_meta: Optional[Tensor] = None, smoothstep: bool = True) -> Dict[str, Tensor]:
     """x [...,3] -> {"sdf" [...,1], "gradient" [...,3], "albedo" [...,3], "geo" [...,256]} (SDFAlbedoField.get_outputs
-    without alpha, neusky/fields/sdf_albedo_field.py:211-269; the gradient is analytic, not autograd)."""
+    without alpha, neusky/fields/sdf_albedo_field.py:211-269; the gradient is analytic, not autograd).
+    ``grid_meta`` (int32 [L,4], tcnn_import.tcnn_level_meta): evaluate the hash table with tiny-cuda-nn's grid semantics (imported
+    reference checkpoint) instead of the nerfstudio torch grid; ``smoothstep`` is tcnn's interpolation flag."""
     lead = x.shape[:-1]
     x2 = _chk("x", x.reshape(-1, 3), shape=(None, 3))
     n = x2.shape[0]
@@ -184,12 +186,15 @@ def sdf_field(x: Tensor, blob: Tensor, hash_table: Tensor, scalings: Tensor, log
     lib = _lib.load()
     f = dict(device=x.device, dtype=torch.float32)
     sdf = torch.empty((n,), **f)
+    if grid_meta is not None:
+        grid_meta = _chk("grid_meta", grid_meta, dtype=torch.int32, shape=(L, 4))
+    gm = (_ptr(grid_meta), c_int(int(smoothstep)))
     if impl == "tc":
         if want_geo:
             raise ValueError("sdf_field: the tensor-core path keeps the geometry feature on chip (want_geo needs impl='simt')")
         blob = _chk("blob", blob, dtype=torch.uint8, shape=(lib.nsk_sdf_tc_weights_bytes(),))
         grad, alb = torch.empty((n, 3), **f), torch.empty((n, 3), **f)
-        _lib.check(lib.nsk_sdf_field_tc_fwd(_ptr(x2), c_int64(n), _ptr(blob), _ptr(hash_table), _ptr(scalings), c_int(L), c_int(log2_T), _ptr(sdf), _ptr(grad), _ptr(alb), _stream(x)), "nsk_sdf_field_tc_fwd")
+        _lib.check(lib.nsk_sdf_field_tc_fwd_ex(_ptr(x2), c_int64(n), _ptr(blob), _ptr(hash_table), _ptr(scalings), c_int(L), c_int(log2_T), *gm, _ptr(sdf), _ptr(grad), _ptr(alb), _stream(x)), "nsk_sdf_field_tc_fwd_ex")
         return {"sdf": sdf.reshape(*lead, 1), "gradient": grad.reshape(*lead, 3), "albedo": alb.reshape(*lead, 3)}
     if impl != "simt":
         raise ValueError(f"impl must be 'tc' or 'simt', got {impl!r}")
@@ -197,7 +202,7 @@ def sdf_field(x: Tensor, blob: Tensor, hash_table: Tensor, scalings: Tensor, log
     grad = torch.empty((n, 3), **f) if want_grad else None
     alb = torch.empty((n, 3), **f) if want_albedo else None
     geo = torch.empty((n, 256), **f) if want_geo else None
-    _lib.check(lib.nsk_sdf_field_simt_fwd(_ptr(x2), c_int64(n), _ptr(blob), _ptr(hash_table), _ptr(scalings), c_int(L), c_int(log2_T), _ptr(sdf), _ptr(grad), _ptr(alb), _ptr(geo), _stream(x)), "nsk_sdf_field_simt_fwd")
+    _lib.check(lib.nsk_sdf_field_simt_fwd_ex(_ptr(x2), c_int64(n), _ptr(blob), _ptr(hash_table), _ptr(scalings), c_int(L), c_int(log2_T), *gm, _ptr(sdf), _ptr(grad), _ptr(alb), _ptr(geo), _stream(x)), "nsk_sdf_field_simt_fwd_ex")
     out = {"sdf": sdf.reshape(*lead, 1)}
     if grad is not None:
         out["gradient"] = grad.reshape(*lead, 3)
@@ -589,8 +594,10 @@ def shade_finalize(rgb_lin, bg, acc, training: bool = False) -> Tensor:
 COLLAPSE_MIN_SAMPLES = 8     # K4 (tc2): from this many samples per ray on, pre-collapse the Lambert coefficients
 
 
-def sky_shade(points, normals, wa, inv_count, dirs_sel, radiance_sel, ddf_blob, hash_table, scalings, log2_T: int, radius: float, threshold: float, sigmoid_scale: float, rgb_lin: Tensor, cam=None, want_vis: bool = False, want_ddf: bool = False, impl: str = "tc"):
-    """K4.  Accumulates into ``rgb_lin`` [R,3]; returns (vis [R,Dp] | None, ddf [R*Dp] | None, term | None)."""
+def sky_shade(points, normals, wa, inv_count, dirs_sel, radiance_sel, ddf_blob, hash_table, scalings, log2_T: int, radius: float, threshold: float, sigmoid_scale: float, rgb_lin: Tensor, cam=None, want_vis: bool = False, want_ddf: bool = False, impl: str = "tc",
+              grid_meta: Optional[Tensor] = None, smoothstep: bool = True):
+    """K4.  Accumulates into ``rgb_lin`` [R,3]; returns (vis [R,Dp] | None, ddf [R*Dp] | None, term | None).
+    ``grid_meta`` / ``smoothstep``: the DDF position grid is an imported tiny-cuda-nn grid (see ``sdf_field``; impl 'tc2' and 'simt')."""
     R, S = normals.shape[0], normals.shape[1]
     Dp = dirs_sel.shape[0]
     points = _chk("points", points, shape=(R, 3))
@@ -626,6 +633,13 @@ def sky_shade(points, normals, wa, inv_count, dirs_sel, radiance_sel, ddf_blob, 
         fn, name = lib.nsk_sky_shade_tc2_fwd, "nsk_sky_shade_tc2_fwd"
     else:
         raise ValueError(f"impl must be 'tc2', 'tc' or 'simt', got {impl!r}")
+    if grid_meta is not None:
+        if impl == "tc":
+            raise ValueError("sky_shade: an imported tiny-cuda-nn grid needs impl 'tc2' (default) or 'simt'")
+        grid_meta = _chk("grid_meta", grid_meta, dtype=torch.int32, shape=(L, 4))
+        fn, name = (lib.nsk_sky_shade_tc2_fwd_ex, "nsk_sky_shade_tc2_fwd_ex") if impl == "tc2" else (lib.nsk_sky_shade_simt_fwd_ex, "nsk_sky_shade_simt_fwd_ex")
+        _lib.check(fn(_ptr(points), c_int64(R), _ptr(normals), _ptr(wa), _ptr(inv_count), c_int(S), _ptr(dirs_sel), c_int(Dp), _ptr(radiance_sel), _ptr(cam), _ptr(blob), _ptr(hash_table), _ptr(scalings), c_int(L), c_int(log2_T), _ptr(grid_meta), c_int(int(smoothstep)), c_float(radius), c_float(threshold), c_float(sigmoid_scale), _ptr(rgb_lin), _ptr(vis), _ptr(ddf), _ptr(term), _stream(points)), name)
+        return vis, ddf, term
     _lib.check(fn(_ptr(points), c_int64(R), _ptr(normals), _ptr(wa), _ptr(inv_count), c_int(S), _ptr(dirs_sel), c_int(Dp), _ptr(radiance_sel), _ptr(cam), _ptr(blob), _ptr(hash_table), _ptr(scalings), c_int(L), c_int(log2_T), c_float(radius), c_float(threshold), c_float(sigmoid_scale), _ptr(rgb_lin), _ptr(vis), _ptr(ddf), _ptr(term), _stream(points)), name)
     return vis, ddf, term
 

@@ -31,6 +31,9 @@ class SkyShader:
         self.impl = impl
         self.scalings = hash_scalings(num_levels).to(self.device)
         self.hash_table = ddf_params["position_encoding.hash_table"].to(self.device, torch.float32).contiguous()
+        # imported tiny-cuda-nn position grid (tcnn_import): int32 [L,4] level table + tcnn's interpolation flag; None = nerfstudio torch grid
+        self.grid_meta: Optional[Tensor] = None
+        self.grid_smoothstep = True
         self.set_ddf_weights(ddf_params)
         self.reni_blob = packing.pack_reni(reni_params, device=self.device) if reni_params is not None else None
         self.reni_gemm = packing.pack_reni_gemm(reni_params, device=self.device) if reni_params is not None else None
@@ -106,7 +109,8 @@ class SkyShader:
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             ev[0].record()
         vis, ddf, term = ops.sky_shade(points, normals, wa, inv_count, self.dirs_sel, rad_sel, blob, self.hash_table, self.scalings,
-                                       self.log2_T, self.radius, threshold, sigmoid_scale, rgb_lin, cam, want_vis, want_ddf, impl)
+                                       self.log2_T, self.radius, threshold, sigmoid_scale, rgb_lin, cam, want_vis, want_ddf, impl,
+                                       grid_meta=self.grid_meta, smoothstep=self.grid_smoothstep)
         if self.k4_events is not None:
             ev[1].record()
             self.k4_events.append(ev)
@@ -215,6 +219,8 @@ class RayRenderer:
         self.scalings = self.shader.scalings
         self.sweep_events = None
         self.sdf_table = sdf_params["encoding.hash_table"].to(self.device, torch.float32).contiguous()
+        self.sdf_grid_meta: Optional[Tensor] = None       # imported tiny-cuda-nn grid of the SDF field (see SkyShader.grid_meta)
+        self.sdf_grid_smoothstep = True
         self.set_sdf_weights(sdf_params)
 
     def set_sdf_weights(self, sdf_params: Dict[str, Tensor]) -> None:
@@ -262,7 +268,8 @@ class RayRenderer:
         else:
             starts, ends = uniform_samples(near, far, S)
         x = origins[:, None, :] + directions[:, None, :] * starts[..., None]          # get_start_positions
-        f = ops.sdf_field(x, self.sdf_blob, self.sdf_table, self.scalings, self.log2_T, impl=self.sdf_impl)
+        f = ops.sdf_field(x, self.sdf_blob, self.sdf_table, self.scalings, self.log2_T, impl=self.sdf_impl, grid_meta=self.sdf_grid_meta,
+                          smoothstep=self.sdf_grid_smoothstep)
         c = ops.neus_composite(f["sdf"], f["gradient"], f["albedo"], directions, starts, ends, ends - starts, dnorm, self.inv_s, cos_anneal_ratio, False,
                                steps_minmax=steps_minmax)
         if cam is not None:

@@ -16,7 +16,10 @@ file is pinned by self-consistency tests only, tests/test_tcnn_import.py, and ma
 
 ``tcnn_levels`` computes the level geometry, ``tcnn_params_to_table`` re-lays the flat vector out as the fp32 ``[L * T, F]``
 table our fields hold (level l at rows ``[l T, l T + n_l)``, the rest zero) and ``nsk_hash_encode_tcnn_fwd``
-(``ops.hash_encode_tcnn``) evaluates it with tcnn's indexing, offset and interpolation.
+(``ops.hash_encode_tcnn``) evaluates it with tcnn's indexing, offset and interpolation.  The fused field kernels take the same
+per-level table through their ``*_fwd_ex`` entry points (``GridMode`` in csrc/nsk_common.cuh): K2 (``nsk_sdf_field_tc_fwd_ex`` /
+``_simt_fwd_ex``, incl. the smoothstep factor of the analytic normal) and K4 (``nsk_sky_shade_tc2_fwd_ex`` / ``_simt_fwd_ex``), so an
+imported checkpoint renders through the same eval path; training from an imported grid is not supported.
 """
 from __future__ import annotations
 
@@ -86,7 +89,8 @@ def tcnn_grid_encode_torch(x: Tensor, table: Tensor, levels: List[TcnnLevel], lo
     T = 1 << log2_hashmap_size
     outs = []
     for l, lv in enumerate(levels):
-        pos = x.to(torch.float32) * np.float32(lv.scale) + 0.5
+        # tcnn: fmaf(scale, x, 0.5f) -- one rounding; the fp64 product of two fp32 values is exact, so this is the same number
+        pos = (x.to(torch.float64) * float(np.float32(lv.scale)) + 0.5).to(torch.float32)
         g = torch.floor(pos)
         w = pos - g
         if smoothstep:
@@ -99,10 +103,10 @@ def tcnn_grid_encode_torch(x: Tensor, table: Tensor, levels: List[TcnnLevel], lo
             wc = torch.ones_like(w[:, 0])
             for d in range(3):
                 wc = wc * (w[:, d] if bit[d] else (1.0 - w[:, d]))
+            u = gc & 0xFFFFFFFF                      # grid coordinates as tcnn holds them: uint32 (negative positions wrap around)
             if lv.dense:
-                idx = gc[:, 0] + gc[:, 1] * lv.resolution + gc[:, 2] * lv.resolution * lv.resolution
+                idx = (u[:, 0] + ((u[:, 1] * lv.resolution) & 0xFFFFFFFF) + ((u[:, 2] * (lv.resolution * lv.resolution)) & 0xFFFFFFFF)) & 0xFFFFFFFF
             else:
-                u = gc & 0xFFFFFFFF
                 idx = (u[:, 0] * PRIMES[0]) ^ ((u[:, 1] * PRIMES[1]) & 0xFFFFFFFF) ^ ((u[:, 2] * PRIMES[2]) & 0xFFFFFFFF)
             idx = idx % lv.size
             acc = acc + wc[:, None] * table[l * T + idx]
