@@ -48,6 +48,7 @@
 #include "nsk_common.cuh"
 #include "tc_util.cuh"
 #include <stdlib.h>
+#include <type_traits>
 
 namespace nsk {
 namespace tcs2 {
@@ -164,6 +165,7 @@ template <int VARIANT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) sky_shade_tc2_kernel(const Params P) {
   // VARIANT bit0: epilogue math stripped (diagnostic), bit1: MMAs not issued (diagnostic)
   constexpr bool PROF = (VARIANT & 4) != 0;      // per-role cycle accounting (diagnostic instantiation only)
+  constexpr bool DBG = (VARIANT & 8) != 0;       // activation dump of the first tile (diagnostic instantiation only: keeps the stores out of the hot epilogue loops)
 #define NSK_CLK() (PROF ? clock64() : 0ll)
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
@@ -183,7 +185,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) sky_
   };
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < NSTAGE; ++i) { mbar_init(bars + 8 * (B_WFULL + i), 1); mbar_init(bars + 8 * (B_WEMPTY + i), 1); }
+    // WFULL of the LEADER counts two arrivals per use: its own producer's expect_tx and the peer's "my half has landed" relay, so the
+    // issuer polls ONE barrier per weight stage (147 stages per tile)
+    for (int i = 0; i < NSTAGE; ++i) { mbar_init(bars + 8 * (B_WFULL + i), leader ? 2 : 1); mbar_init(bars + 8 * (B_WEMPTY + i), 1); }
     mbar_init(bars + 8 * B_INFULL, 2 * (PRO_THREADS / 32));          // one arrival per prologue warp of both CTAs
     for (int i = 0; i < NSTAGE; ++i) mbar_init(bars + 8 * (B_PFULL + i), 1);
     mbar_init(bars + 8 * B_INEMPTY, 1);
@@ -255,7 +259,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) sky_
 #pragma unroll 1
           for (int sg = 0; sg < nst; ++sg) {
             mbar_wait(bars + 8 * (B_WFULL + wst), wph);
-            if (lane == 0) mbar_arrive_remote(bars + 8 * (B_PFULL + wst), 0);
+            if (lane == 0) mbar_arrive_remote(bars + 8 * (B_WFULL + wst), 0);
             __syncwarp();
             if (++wst == NSTAGE) { wst = 0; wph ^= 1; }
           }
@@ -295,8 +299,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) sky_
             const int nmma = (sg < nfull ? kps : ktail) >> 4;
             {
               const long long c0 = NSK_CLK();
-              mbar_wait(bars + 8 * (B_WFULL + wst), wph);                  // my half of the stage
-              mbar_wait(bars + 8 * (B_PFULL + wst), wph);                  // the peer's half
+              mbar_wait(bars + 8 * (B_WFULL + wst), wph);                  // my half of the stage AND the peer's (relayed arrival)
               if (PROF) t_w += NSK_CLK() - c0;
             }
             tc_fence_after();
@@ -371,7 +374,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) sky_
             const float a0 = __uint_as_float(v[cb & 1][j]), a1 = __uint_as_float(v[cb & 1][j + 1]);
             pk[j >> 1] = pack_h2(fmaxf(a0, 0.2f * a0), fmaxf(a1, 0.2f * a1));   // LeakyReLU(0.2)
           }
-          if (P.dbg && tile == 0) {
+          if (DBG && P.dbg && tile == 0) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const float a0 = __uint_as_float(v[cb & 1][j]);
@@ -387,7 +390,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) sky_
       }
       // ---- trunk: h = sin(freq' * z + phase') ----
       float fin = 0.f;
-      for (int l = 0; l < DDF_LAYERS; ++l) {
+      // one trunk layer; LAST (a compile-time tag) = the fifth layer, whose activations go into the 256 -> 1 dot product instead of
+      // shared memory: peeled so that neither path carries the other's branch and code in its 8-column blocks
+      auto trunk_layer = [&](auto last_tag, const int l) {
+        constexpr bool LAST = decltype(last_tag)::value;
         long long c0 = NSK_CLK();
         mbar_wait(bars + 8 * B_ACCA, ph_acca); ph_acca ^= 1;   // Z_l
         t_wz += NSK_CLK() - c0;
@@ -416,11 +422,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) sky_
               const float arg = fmaf(__uint_as_float(f[pc & 1][j]), __uint_as_float(z[pc & 1][j]), __uint_as_float(p[pc & 1][j]));
               h[j] = (VARIANT & 1) ? arg : __sinf(arg);
             }
-            if (P.dbg && tile == 0) {
+            if (DBG && P.dbg && tile == 0) {
 #pragma unroll
               for (int j = 0; j < 8; ++j) P.dbg[((5 + l) * 128 + row) * 256 + colw + pc * 8 + j] = h[j];
             }
-            if (l + 1 < DDF_LAYERS) {
+            if (!LAST) {
               uint8_t* dst = smem + OFF_ACT_H + (uint32_t)((colw >> 3) + pc) * (TM * 16) + row * 16;
               *reinterpret_cast<uint4*>(dst) = make_uint4(pack_h2(h[0], h[1]), pack_h2(h[2], h[3]), pack_h2(h[4], h[5]), pack_h2(h[6], h[7]));
             } else {
@@ -430,11 +436,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) sky_
               fin = fmaf(h[4], w1.x, fin); fin = fmaf(h[5], w1.y, fin); fin = fmaf(h[6], w1.z, fin); fin = fmaf(h[7], w1.w, fin);  // film_siren.py:147
             }
           }
-          if (l + 1 < DDF_LAYERS) fence_proxy_async_smem();
+          if (!LAST) fence_proxy_async_smem();
           tc_fence_before();
           arrive_leader(bars + 8 * (B_FPFREE + (c & 1)));
         }
-      }
+      };
+      for (int l = 0; l + 1 < DDF_LAYERS; ++l) trunk_layer(std::false_type{}, l);
+      trunk_layer(std::true_type{}, DDF_LAYERS - 1);
       // ---- tail: sigmoid, visibility, Lambertian accumulation ----
       const long long c_tail = NSK_CLK();
       if (hsel == 1) fin_part[row] = fin;
@@ -624,6 +632,7 @@ extern "C" int nsk_sky_shade_tc2_fwd_ex(const float* points, int64_t R, const fl
   if (int err = nsk::device_once(once, "nsk_sky_shade_tc2_fwd: device setup", &num_sms, [] {
         cudaError_t e = cudaFuncSetAttribute(sky_shade_tc2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(sky_shade_tc2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(sky_shade_tc2_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
         return e;
       }))
     return err;
@@ -643,6 +652,7 @@ extern "C" int nsk_sky_shade_tc2_fwd_ex(const float* points, int64_t R, const fl
   const int64_t clusters = P.n_tp < num_sms / 2 ? P.n_tp : num_sms / 2;
   const int64_t grid = 2 * clusters;
   if (P.prof) sky_shade_tc2_kernel<4><<<(unsigned)grid, NUM_THREADS, SMEM_BYTES, nsk::as_stream(stream)>>>(P);
+  else if (P.dbg) sky_shade_tc2_kernel<8><<<(unsigned)grid, NUM_THREADS, SMEM_BYTES, nsk::as_stream(stream)>>>(P);
   else sky_shade_tc2_kernel<0><<<(unsigned)grid, NUM_THREADS, SMEM_BYTES, nsk::as_stream(stream)>>>(P);
   return nsk::check_launch("sky_shade_tc2_kernel");
 }
