@@ -160,6 +160,17 @@ __constant__ int c_shape_N[6] = {256, 256, 128, 256, 256, 0};
 __constant__ int c_shape_nfull[6] = {0, 4, 2, 0, 4, 0};
 __constant__ int c_shape_kps[6] = {64, 64, 128, 64, 64, 0};
 __constant__ int c_shape_ktail[6] = {48, 16, 16, 48, 0, 0};
+// The same tables as compile-time constants: the MMA issuer is ONE thread and the serial resource of the kernel, so its walk over
+// the schedule is unrolled with every operand an immediate (no __constant__ lookups, no runtime shape arithmetic between MMAs).
+constexpr Schedule k_sched = Schedule();
+constexpr int k_shape_N[6] = {256, 256, 128, 256, 256, 0};
+constexpr int k_shape_nfull[6] = {0, 4, 2, 0, 4, 0};
+constexpr int k_shape_kps[6] = {64, 64, 128, 64, 64, 0};
+constexpr int k_shape_ktail[6] = {48, 16, 16, 48, 0, 0};
+template <class F, int... Os>
+__device__ __forceinline__ void for_each_op(F&& f, std::integer_sequence<int, Os...>) {
+  (f(std::integral_constant<int, Os>{}), ...);
+}
 
 template <int VARIANT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) sky_shade_tc2_kernel(const Params P) {
@@ -265,38 +276,34 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) sky_
           }
         }
       }
-    } else {
-    for (int64_t tp = tp0; tp < P.n_tp; tp += tp_step) {
-#pragma unroll 1
-      for (int o = 0; o < NUM_OPS; ++o) {
-        const Op op = c_sched.ops[o];
-        if (op.wait != NOB) {
+    } else if (lane == 0) {
+      // ---- leader CTA: one thread issues every MMA of the pair ---------------------------------------------------
+      auto issue_op = [&](auto o_tag) {
+        constexpr int O = decltype(o_tag)::value;
+        constexpr Op op = k_sched.ops[O];
+        if constexpr (op.wait != NOB) {
           const long long c0 = NSK_CLK();
           mbar_wait(bars + 8 * op.wait, (phases >> op.wait) & 1u);
           if (PROF) {
             const long long dt = NSK_CLK() - c0;
             t_dep += dt;
-            if (o < 6) t_dep_map += dt;
+            if (O < 6) t_dep_map += dt;
           }
           phases ^= 1u << op.wait;
           tc_fence_after();
         }
-        const int sh = op.shape;
-        if (sh != SH_NONE) {
-          const int N = c_shape_N[sh], nfull = c_shape_nfull[sh], kps = c_shape_kps[sh], ktail = c_shape_ktail[sh];
-          const int nst = nfull + (ktail ? 1 : 0);
-          const int Nh = N >> 1;                                  // B rows held by each CTA
-          const uint32_t idesc = make_idesc_f16(2 * TM, N);       // M = 256 across the pair
+        constexpr int sh = op.shape;
+        if constexpr (sh != SH_NONE) {
+          constexpr int N = k_shape_N[sh], nfull = k_shape_nfull[sh], kps = k_shape_kps[sh], ktail = k_shape_ktail[sh];
+          constexpr int Nh = N >> 1;                                  // B rows held by each CTA
+          constexpr uint32_t idesc = make_idesc_f16(2 * TM, N);       // M = 256 across the pair
           const uint32_t tmem_d = tmem + op.d_col;
           // A descriptor: LBO = 128 rows * 16 B; advancing one K=16 step moves 2 chunks = 4096 B
-          const uint64_t ad0 = desc_hi | ((uint64_t)((TM * 16) >> 4) << 16) | (uint64_t)(((sbase + op.a_off) >> 4) & 0x3FFF);
-          uint32_t kstep = 0;   // K=16 steps issued so far in this op (warp-uniform)
-          const uint64_t bd0 = desc_hi | ((uint64_t)((Nh * 16) >> 4) << 16);
-          const uint32_t b_step = (uint32_t)(2 * Nh * 16) >> 4;
-          uint32_t acc = 0;
-#pragma unroll 1
-          for (int sg = 0; sg < nst; ++sg) {
-            const int nmma = (sg < nfull ? kps : ktail) >> 4;
+          uint64_t ad = desc_hi | ((uint64_t)((TM * 16) >> 4) << 16) | (uint64_t)(((sbase + op.a_off) >> 4) & 0x3FFF);
+          constexpr uint64_t bd0 = ((uint64_t)1 << 46) | ((uint64_t)(128 >> 4) << 32) | ((uint64_t)((Nh * 16) >> 4) << 16);
+          constexpr uint32_t b_step = (uint32_t)(2 * Nh * 16) >> 4;
+          auto stage = [&](auto nmma_tag, const uint32_t first_acc) {
+            constexpr int NMMA = decltype(nmma_tag)::value;
             {
               const long long c0 = NSK_CLK();
               mbar_wait(bars + 8 * (B_WFULL + wst), wph);                  // my half of the stage AND the peer's (relayed arrival)
@@ -304,37 +311,30 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) sky_
             }
             tc_fence_after();
             const long long ci0 = NSK_CLK();
-            if (elect_one()) {
-              uint64_t ad = ad0 + (uint64_t)kstep * 256u;   // one K=16 step = 2 chunks = 4096 B >> 4
-              uint64_t bd = bd0 | (uint64_t)(((sbase + OFF_RING + wst * STAGE_BYTES) >> 4) & 0x3FFF);
-              uint32_t a = acc;
-#pragma unroll 1
-              for (int j = 0; j < nmma; ++j) {
-                umma_ss2(tmem_d, ad, bd, idesc, a);
-                a = 1;
-                ad += 256;
-                bd += b_step;
-              }
-              umma_commit2(bars + 8 * (B_WEMPTY + wst));   // stage reusable in BOTH CTAs once these MMAs have read it
+            uint64_t bd = bd0 | (uint64_t)(((sbase + OFF_RING + wst * STAGE_BYTES) >> 4) & 0x3FFF);
+#pragma unroll
+            for (int j = 0; j < NMMA; ++j) {
+              umma_ss2(tmem_d, ad, bd, idesc, j == 0 ? first_acc : 1u);
+              ad += 256;                                                   // one K=16 step = 2 chunks = 4096 B >> 4
+              bd += b_step;
             }
-            __syncwarp();
+            umma_commit2(bars + 8 * (B_WEMPTY + wst));   // stage reusable in BOTH CTAs once these MMAs have read it
             if (PROF) {
               const long long dt = NSK_CLK() - ci0;
               if (sh == SH_FP) t_iss_fp += dt; else if (sh == SH_Z || sh == SH_Z0) t_iss_z += dt; else t_iss_map += dt;
             }
-            kstep += nmma;
-            acc = 1;
             if (++wst == NSTAGE) { wst = 0; wph ^= 1; }
-          }
-          if (elect_one()) {
-            umma_commit2(bars + 8 * op.commit0);
-            if (op.commit1 != NOB) umma_commit2(bars + 8 * op.commit1);
-          }
-          __syncwarp();
+          };
+#pragma unroll 1
+          for (int sg = 0; sg < nfull; ++sg) stage(std::integral_constant<int, (kps >> 4)>{}, sg == 0 ? 0u : 1u);
+          if constexpr (ktail != 0) stage(std::integral_constant<int, (ktail >> 4)>{}, nfull == 0 ? 0u : 1u);
+          umma_commit2(bars + 8 * op.commit0);
+          if constexpr (op.commit1 != NOB) umma_commit2(bars + 8 * op.commit1);
         }
-      }
+      };
+      for (int64_t tp = tp0; tp < P.n_tp; tp += tp_step) for_each_op(issue_op, std::make_integer_sequence<int, NUM_OPS>{});
     }
-    }
+    __syncwarp();
     if (PROF && P.prof && lane == 0) {
       P.prof[blockIdx.x * 16 + 2] = NSK_CLK() - t_begin; P.prof[blockIdx.x * 16 + 3] = t_dep; P.prof[blockIdx.x * 16 + 4] = t_w;
       P.prof[blockIdx.x * 16 + 5] = t_dep_map;
