@@ -502,26 +502,24 @@ def train_arm(args, ctx):
         sky_o = (torch.tensor([0.0, -0.6, 0.1]).expand(256, 3) + 0.1 * torch.randn(256, 3, generator=gs)).to(dev)
         sky_d = torch.nn.functional.normalize(torch.randn(256, 3, generator=gs) + torch.tensor([0.0, 0.0, 1.0]), dim=-1).to(dev)
 
+    # zero-fill + forward + DDF fitting pass + backward as ONE CUDA graph after two eager iterations (neusky_b200/graphed.py); the host's
+    # random draws, the h2d of the batch, the gradient all-reduce and the optimizer step stay outside it.  --no-train-graph: all eager.
+    from neusky_b200.graphed import GraphedTrainIteration
+    iteration = GraphedTrainIteration(step_mod, red, opt, fit=fit, graph=not args.no_train_graph)
+
     def one_step():
         i = it["i"]; it["i"] += 1
         dirs = torch.from_numpy((base_dirs @ rots[i % len(rots)]).astype(np.float32))          # IcosahedronSampler random rotation (host, :339-341)
-        step_mod.set_directions(dirs)
+        gp = gpos0 + (torch.rand(gpos0.shape, generator=gg) - 0.5) * (2.0 / gres)
+        gd = torch.nn.functional.normalize(torch.randn(gpos0.shape, generator=gg), dim=-1)
+        loss = iteration(batch_h, dirs, gp, gd, sky_o if fit is not None else None, sky_d if fit is not None else None)   # h2d of the ray batch inside
         Dp_seen.append(int(step_mod.dirs_sel.shape[0]))
-        gp = (gpos0 + (torch.rand(gpos0.shape, generator=gg) - 0.5) * (2.0 / gres)).to(dev, non_blocking=True)
-        gd = torch.nn.functional.normalize(torch.randn(gpos0.shape, generator=gg), dim=-1).to(dev, non_blocking=True)
-        b = {k: v.to(dev, non_blocking=True) for k, v in batch_h.items()}                       # h2d of the ray batch inside the step
-        red.zero_grad()
-        loss, _, _ = step_mod(b, grid_positions=gp, grid_dirs=gd)
-        if fit is not None:
-            loss = loss + fit(sky_o, sky_d)[0]
-        loss.backward()
-        red.finish()
-        opt.step()
-        loss_h.copy_(loss.detach().reshape(1), non_blocking=True)                               # d2h of the step's result
+        loss_h.copy_(loss.reshape(1), non_blocking=True)                                        # d2h of the step's result
 
-    for _ in range(args.warmup):
+    for _ in range(max(args.warmup, 0 if args.no_train_graph else 3)):      # two eager iterations + the capture come before the timed region
         one_step()
     ctx.barrier()
+    replays0, eager0 = iteration.replays, iteration.eager_steps
     sampler = ClockSampler(local) if (rank == 0 and getattr(args, "sample_clocks", True)) else None
     if sampler:
         sampler.start()
@@ -581,7 +579,9 @@ def train_arm(args, ctx):
                                           + (" over NCCL" if world > 1 else " (single rank: no collective)"),
                            "l2": "per-step activations (~15 GB) exceed L2"},
                 "e2e": {"value": world * R * args.steps / wall, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                        "api": "neusky_b200.train.NeuSkyTrainStep + parallel.GradBucketReducer; e2e value is wall-clock over the timed steps (host work, h2d of the ray batch and d2h of the loss included); `value` is CUDA-event time of the same steps"},
+                        "api": "neusky_b200.graphed.GraphedTrainIteration (train.NeuSkyTrainStep + ddf_fit.DDFFit + parallel.GradBucketReducer + fused Adam); e2e value is wall-clock over the timed steps (host random draws, h2d of the ray batch, d2h of the loss included); `value` is CUDA-event time of the same steps"},
+                "cuda_graph": {"enabled": not args.no_train_graph, "replayed_steps": iteration.replays - replays0, "eager_steps": iteration.eager_steps - eager0,
+                               "abi_kernels_in_graph": iteration.kernels_in_graph, "captures": iteration.captures},
                 "gpu_launches": launches, "algorithmic_tflops": flop * args.steps / t / 1e12, "tf32_peak_tflops_sustained": peaks["tf_sustained"] / 2,
                 "all_reduce_exposed_ms": exposed_ms, "all_reduce_bytes_per_step": red.bytes_per_step if world > 1 else 0,
                 "clocks": clocks, "loss": float(loss_h.item())}
@@ -666,6 +666,7 @@ def main():
     ap.add_argument("--ddf-split-bwd", type=int, default=0, choices=[0, 1, 3], help="train: precision of the DDF's backward contractions only (0 = same as --split)")
     ap.add_argument("--train-sampler", default="proposal", choices=["proposal", "uniform"], help="train: sample placement (proposal = shipped NeuS-facto default)")
     ap.add_argument("--no-ddf-fit", action="store_true", help="train: leave the DDF fitting pass (fit_visibility_field=True in the reference) out of the step")
+    ap.add_argument("--no-train-graph", action="store_true", help="train: run every iteration eagerly (~2900 launches from the host) instead of replaying the captured CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

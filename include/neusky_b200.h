@@ -130,6 +130,20 @@ int nsk_neus_composite_bwd(const float* sdf, const float* grad, const float* alb
                            const float* g_normals, const float* g_acc, const float* g_p2p_raw,
                            const float* g_normal_out, const float* g_albedo_out, const float* g_bg_T,
                            float* d_sdf, float* d_grad, float* d_albedo, float* d_inv_s, void* stream);
+/* Device-scalar variants of the two calls above: inv_s is read from inv_s_dev [1] ON THE DEVICE.  The training step computes
+ * inv_s = exp(10 * variance) from a parameter the optimizer updates in HBM (nerfstudio LearnedVariance); reading it
+ * back for a by-value argument costs a host synchronisation per call and cannot be captured in a CUDA graph. */
+int nsk_neus_composite_fwd_dv(const float* sdf, const float* grad, const float* albedo, const float* ray_dirs,
+                              const float* starts, const float* ends, const float* deltas,
+                              int64_t R, int S, const float* inv_s_dev, float cos_anneal_ratio, int training,
+                              float* weights, float* wa, float* normals, float* acc, float* p2p_raw,
+                              float* normal_out, float* albedo_out, float* bg_T, float* steps_minmax, void* stream);
+int nsk_neus_composite_bwd_dv(const float* sdf, const float* grad, const float* albedo, const float* ray_dirs,
+                              const float* starts, const float* ends, const float* deltas, int64_t R, int S,
+                              const float* inv_s_dev, float cos_anneal_ratio, const float* g_weights, const float* g_wa,
+                              const float* g_normals, const float* g_acc, const float* g_p2p_raw,
+                              const float* g_normal_out, const float* g_albedo_out, const float* g_bg_T,
+                              float* d_sdf, float* d_grad, float* d_albedo, float* d_inv_s, void* stream);
 int nsk_neus_finalize_depth(const float* p2p_raw, const float* dnorm, const float* steps_minmax, int64_t R,
                             float* p2p, float* depth, void* stream);
 

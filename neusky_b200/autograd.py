@@ -66,7 +66,7 @@ class _NeusComposite(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, sdf, grad, albedo, inv_s, ray_dirs, starts, ends, deltas, dnorm, cos_anneal_ratio: float):
-        o = ops.neus_composite(sdf, grad, albedo, ray_dirs, starts, ends, deltas, dnorm, float(inv_s), cos_anneal_ratio, True)
+        o = ops.neus_composite(sdf, grad, albedo, ray_dirs, starts, ends, deltas, dnorm, inv_s, cos_anneal_ratio, True)     # inv_s read on the device: no host sync
         ctx.save_for_backward(sdf, grad, albedo, inv_s, ray_dirs, starts, ends, deltas)
         ctx.rho = cos_anneal_ratio
         return tuple(o[k] for k in _NeusComposite.OUT)
@@ -75,7 +75,7 @@ class _NeusComposite(torch.autograd.Function):
     def backward(ctx, *gs):
         sdf, grad, albedo, inv_s, ray_dirs, starts, ends, deltas = ctx.saved_tensors
         g = {k: (None if v is None else v.contiguous()) for k, v in zip(_NeusComposite.OUT, gs)}
-        d_sdf, d_grad, d_alb, d_inv = ops.neus_composite_bwd(sdf, grad, albedo, ray_dirs, starts, ends, deltas, float(inv_s), ctx.rho, g)
+        d_sdf, d_grad, d_alb, d_inv = ops.neus_composite_bwd(sdf, grad, albedo, ray_dirs, starts, ends, deltas, inv_s, ctx.rho, g)
         return d_sdf.reshape(sdf.shape), d_grad, d_alb, d_inv.reshape(inv_s.shape), None, None, None, None, None, None
 
 

@@ -24,13 +24,14 @@ constexpr int NC_WARPS = 8;
 __global__ void __launch_bounds__(NC_WARPS * 32)
 neus_composite_kernel(const float* __restrict__ sdf, const float* __restrict__ grad, const float* __restrict__ albedo,
                       const float* __restrict__ ray_dirs, const float* __restrict__ starts, const float* __restrict__ ends,
-                      const float* __restrict__ deltas, int64_t R, int S, float inv_s, float rho, int training,
+                      const float* __restrict__ deltas, int64_t R, int S, float inv_s, const float* __restrict__ inv_s_dev, float rho, int training,
                       float* __restrict__ weights, float* __restrict__ wa, float* __restrict__ normals,
                       float* __restrict__ acc_out, float* __restrict__ p2p_raw, float* __restrict__ normal_out,
                       float* __restrict__ albedo_out, float* __restrict__ bgT_out, float* __restrict__ steps_minmax) {
   const int lane = threadIdx.x & 31;
   const int64_t warp_global = (int64_t)blockIdx.x * NC_WARPS + (threadIdx.x >> 5);
   const int64_t warps_total = (int64_t)gridDim.x * NC_WARPS;
+  if (inv_s_dev) inv_s = __ldg(inv_s_dev);   // *_dv entry points: the scalar stays on the device (no host read-back; CUDA-graph capturable)
   float smin = FLT_MAX, smax = -FLT_MAX;
   for (int64_t r = warp_global; r < R; r += warps_total) {
     const float dx = ray_dirs[r * 3], dy = ray_dirs[r * 3 + 1], dz = ray_dirs[r * 3 + 2];
@@ -135,11 +136,11 @@ __global__ void surface_points_kernel(const float* __restrict__ o, const float* 
 
 }  // namespace nsk
 
-extern "C" int nsk_neus_composite_fwd(const float* sdf, const float* grad, const float* albedo, const float* ray_dirs,
-                                      const float* starts, const float* ends, const float* deltas, int64_t R, int S,
-                                      float inv_s, float cos_anneal_ratio, int training, float* weights, float* wa,
-                                      float* normals, float* acc, float* p2p_raw, float* normal_out, float* albedo_out,
-                                      float* bg_T, float* steps_minmax, void* stream) {
+static int neus_composite_fwd_impl(const float* sdf, const float* grad, const float* albedo, const float* ray_dirs,
+                                   const float* starts, const float* ends, const float* deltas, int64_t R, int S,
+                                   float inv_s, const float* inv_s_dev, float cos_anneal_ratio, int training, float* weights, float* wa,
+                                   float* normals, float* acc, float* p2p_raw, float* normal_out, float* albedo_out,
+                                   float* bg_T, float* steps_minmax, void* stream) {
   if (R == 0) return 0;
   NSK_REQUIRE(S >= 1, "nsk_neus_composite_fwd: S must be >= 1");
   NSK_REQUIRE(sdf && grad && albedo && ray_dirs && starts && ends && deltas && weights && wa && normals && acc &&
@@ -149,9 +150,28 @@ extern "C" int nsk_neus_composite_fwd(const float* sdf, const float* grad, const
   const int64_t cap = 148 * 8 * 8;
   if (blocks > cap) blocks = cap;
   nsk::neus_composite_kernel<<<(unsigned)blocks, nsk::NC_WARPS * 32, 0, nsk::as_stream(stream)>>>(
-      sdf, grad, albedo, ray_dirs, starts, ends, deltas, R, S, inv_s, cos_anneal_ratio, training, weights, wa, normals,
+      sdf, grad, albedo, ray_dirs, starts, ends, deltas, R, S, inv_s, inv_s_dev, cos_anneal_ratio, training, weights, wa, normals,
       acc, p2p_raw, normal_out, albedo_out, bg_T, steps_minmax);
   return nsk::check_launch("neus_composite_kernel");
+}
+
+extern "C" int nsk_neus_composite_fwd(const float* sdf, const float* grad, const float* albedo, const float* ray_dirs,
+                                      const float* starts, const float* ends, const float* deltas, int64_t R, int S,
+                                      float inv_s, float cos_anneal_ratio, int training, float* weights, float* wa,
+                                      float* normals, float* acc, float* p2p_raw, float* normal_out, float* albedo_out,
+                                      float* bg_T, float* steps_minmax, void* stream) {
+  return neus_composite_fwd_impl(sdf, grad, albedo, ray_dirs, starts, ends, deltas, R, S, inv_s, nullptr, cos_anneal_ratio, training, weights, wa,
+                                 normals, acc, p2p_raw, normal_out, albedo_out, bg_T, steps_minmax, stream);
+}
+
+extern "C" int nsk_neus_composite_fwd_dv(const float* sdf, const float* grad, const float* albedo, const float* ray_dirs,
+                                         const float* starts, const float* ends, const float* deltas, int64_t R, int S,
+                                         const float* inv_s_dev, float cos_anneal_ratio, int training, float* weights, float* wa,
+                                         float* normals, float* acc, float* p2p_raw, float* normal_out, float* albedo_out,
+                                         float* bg_T, float* steps_minmax, void* stream) {
+  NSK_REQUIRE(inv_s_dev || R == 0, "nsk_neus_composite_fwd_dv: inv_s_dev is NULL");
+  return neus_composite_fwd_impl(sdf, grad, albedo, ray_dirs, starts, ends, deltas, R, S, 0.f, inv_s_dev, cos_anneal_ratio, training, weights, wa,
+                                 normals, acc, p2p_raw, normal_out, albedo_out, bg_T, steps_minmax, stream);
 }
 
 extern "C" int nsk_neus_finalize_depth(const float* p2p_raw, const float* dnorm, const float* steps_minmax, int64_t R,
@@ -184,7 +204,7 @@ constexpr int NCB_MAX_CHUNKS = 32;   // S <= 1024
 __global__ void __launch_bounds__(NC_WARPS * 32)
 neus_composite_bwd_kernel(const float* __restrict__ sdf, const float* __restrict__ grad, const float* __restrict__ albedo,
                           const float* __restrict__ ray_dirs, const float* __restrict__ starts, const float* __restrict__ ends,
-                          const float* __restrict__ deltas, int64_t R, int S, float inv_s, float rho,
+                          const float* __restrict__ deltas, int64_t R, int S, float inv_s, const float* __restrict__ inv_s_dev, float rho,
                           const float* __restrict__ g_weights, const float* __restrict__ g_wa, const float* __restrict__ g_normals,
                           const float* __restrict__ g_acc, const float* __restrict__ g_p2p_raw, const float* __restrict__ g_normal_out,
                           const float* __restrict__ g_albedo_out, const float* __restrict__ g_bgT,
@@ -194,6 +214,7 @@ neus_composite_bwd_kernel(const float* __restrict__ sdf, const float* __restrict
   const int64_t warp_global = (int64_t)blockIdx.x * NC_WARPS + wib;
   const int64_t warps_total = (int64_t)gridDim.x * NC_WARPS;
   const int nchunks = (S + 31) / 32;
+  if (inv_s_dev) inv_s = __ldg(inv_s_dev);
   float dinv_acc = 0.f;
 
   for (int64_t r = warp_global; r < R; r += warps_total) {
@@ -304,12 +325,12 @@ neus_composite_bwd_kernel(const float* __restrict__ sdf, const float* __restrict
 
 }  // namespace nsk
 
-extern "C" int nsk_neus_composite_bwd(const float* sdf, const float* grad, const float* albedo, const float* ray_dirs,
-                                      const float* starts, const float* ends, const float* deltas, int64_t R, int S,
-                                      float inv_s, float cos_anneal_ratio, const float* g_weights, const float* g_wa,
-                                      const float* g_normals, const float* g_acc, const float* g_p2p_raw,
-                                      const float* g_normal_out, const float* g_albedo_out, const float* g_bg_T,
-                                      float* d_sdf, float* d_grad, float* d_albedo, float* d_inv_s, void* stream) {
+static int neus_composite_bwd_impl(const float* sdf, const float* grad, const float* albedo, const float* ray_dirs,
+                                   const float* starts, const float* ends, const float* deltas, int64_t R, int S,
+                                   float inv_s, const float* inv_s_dev, float cos_anneal_ratio, const float* g_weights, const float* g_wa,
+                                   const float* g_normals, const float* g_acc, const float* g_p2p_raw,
+                                   const float* g_normal_out, const float* g_albedo_out, const float* g_bg_T,
+                                   float* d_sdf, float* d_grad, float* d_albedo, float* d_inv_s, void* stream) {
   if (R == 0) return 0;
   NSK_REQUIRE(S >= 1 && S <= 32 * nsk::NCB_MAX_CHUNKS, "nsk_neus_composite_bwd: S must be in [1, 1024]");
   NSK_REQUIRE(sdf && grad && albedo && ray_dirs && starts && ends && deltas && d_sdf && d_grad && d_albedo && d_inv_s,
@@ -318,7 +339,28 @@ extern "C" int nsk_neus_composite_bwd(const float* sdf, const float* grad, const
   const int64_t cap = 148 * 8 * 8;
   if (blocks > cap) blocks = cap;
   nsk::neus_composite_bwd_kernel<<<(unsigned)blocks, nsk::NC_WARPS * 32, 0, nsk::as_stream(stream)>>>(
-      sdf, grad, albedo, ray_dirs, starts, ends, deltas, R, S, inv_s, cos_anneal_ratio, g_weights, g_wa, g_normals, g_acc,
+      sdf, grad, albedo, ray_dirs, starts, ends, deltas, R, S, inv_s, inv_s_dev, cos_anneal_ratio, g_weights, g_wa, g_normals, g_acc,
       g_p2p_raw, g_normal_out, g_albedo_out, g_bg_T, d_sdf, d_grad, d_albedo, d_inv_s);
   return nsk::check_launch("neus_composite_bwd_kernel");
+}
+
+extern "C" int nsk_neus_composite_bwd(const float* sdf, const float* grad, const float* albedo, const float* ray_dirs,
+                                      const float* starts, const float* ends, const float* deltas, int64_t R, int S,
+                                      float inv_s, float cos_anneal_ratio, const float* g_weights, const float* g_wa,
+                                      const float* g_normals, const float* g_acc, const float* g_p2p_raw,
+                                      const float* g_normal_out, const float* g_albedo_out, const float* g_bg_T,
+                                      float* d_sdf, float* d_grad, float* d_albedo, float* d_inv_s, void* stream) {
+  return neus_composite_bwd_impl(sdf, grad, albedo, ray_dirs, starts, ends, deltas, R, S, inv_s, nullptr, cos_anneal_ratio, g_weights, g_wa, g_normals,
+                                 g_acc, g_p2p_raw, g_normal_out, g_albedo_out, g_bg_T, d_sdf, d_grad, d_albedo, d_inv_s, stream);
+}
+
+extern "C" int nsk_neus_composite_bwd_dv(const float* sdf, const float* grad, const float* albedo, const float* ray_dirs,
+                                         const float* starts, const float* ends, const float* deltas, int64_t R, int S,
+                                         const float* inv_s_dev, float cos_anneal_ratio, const float* g_weights, const float* g_wa,
+                                         const float* g_normals, const float* g_acc, const float* g_p2p_raw,
+                                         const float* g_normal_out, const float* g_albedo_out, const float* g_bg_T,
+                                         float* d_sdf, float* d_grad, float* d_albedo, float* d_inv_s, void* stream) {
+  NSK_REQUIRE(inv_s_dev || R == 0, "nsk_neus_composite_bwd_dv: inv_s_dev is NULL");
+  return neus_composite_bwd_impl(sdf, grad, albedo, ray_dirs, starts, ends, deltas, R, S, 0.f, inv_s_dev, cos_anneal_ratio, g_weights, g_wa, g_normals,
+                                 g_acc, g_p2p_raw, g_normal_out, g_albedo_out, g_bg_T, d_sdf, d_grad, d_albedo, d_inv_s, stream);
 }

@@ -220,9 +220,27 @@ class DDFFit:
                 "mask": (accumulations > mask_threshold).float(), "termination_dist": p2p, "normals": normal.reshape(-1, 3)}
 
     # -- neusky_pipeline.py:493-515 --------------------------------------------------------------------------------
-    def generate_ddf_samples(self, sky_origins: Optional[Tensor] = None, sky_directions: Optional[Tensor] = None) -> Dict[str, Tensor]:
-        """Sampler -> ground truth (+ the sky-ray bundle the datamanager supplies, `get_sky_ray_bundle(256)`)."""
-        origins, directions = self.sampler()
+    def draw_host(self) -> Tuple[Tensor, Tensor, Optional[Tensor]]:
+        """The HOST random draws of one fitting pass, in the reference's order on torch's CPU generator: the sampler's rays
+        (ddf_sampler.py), then the multi-view sphere points (ddf_model.py:279-284) -> CPU tensors (origins [N,3], directions [N,3],
+        multi_view_points [N,3] or None).  `forward(..., rays=, multi_view_points=)` takes them back (on the device): a captured
+        iteration (graphed.py) cannot draw on the host, so it draws here, outside the graph, and copies into its static inputs."""
+        dev, self.sampler.device = self.sampler.device, torch.device("cpu")
+        try:
+            origins, directions = self.sampler()
+        finally:
+            self.sampler.device = dev
+        mv = None
+        if self.config.loss_inclusions.get("multi_view_loss") and self.training:
+            mv = random_points_on_unit_sphere(origins.shape[0])
+            mv[:, 2] = torch.abs(mv[:, 2])
+        return origins, directions, mv
+
+    def generate_ddf_samples(self, sky_origins: Optional[Tensor] = None, sky_directions: Optional[Tensor] = None,
+                             rays: Optional[Tuple[Tensor, Tensor]] = None) -> Dict[str, Tensor]:
+        """Sampler -> ground truth (+ the sky-ray bundle the datamanager supplies, `get_sky_ray_bundle(256)`).  `rays`: pre-drawn
+        (origins, directions) on the device instead of a fresh draw from the sampler (`draw_host`)."""
+        origins, directions = self.sampler() if rays is None else rays
         if self.stop_sdf_gradients:
             with torch.no_grad():
                 data = self.generate_ddf_ground_truth(origins, directions, self.accumulation_mask_threshold)
@@ -337,10 +355,12 @@ class DDFFit:
         return {k: v * cfg.loss_coefficients[k] for k, v in L.items() if k in cfg.loss_coefficients}
 
     # -- neusky_pipeline.py:272-289 --------------------------------------------------------------------------------
-    def forward(self, sky_origins: Optional[Tensor] = None, sky_directions: Optional[Tensor] = None):
-        """One fitting pass: (sum of losses, loss dict, outputs, batch).  Add the sum to the main step's loss before backward()."""
-        batch = self.generate_ddf_samples(sky_origins, sky_directions)
-        outputs = self.get_outputs(batch, stop_gradients=self.stop_sdf_gradients)
+    def forward(self, sky_origins: Optional[Tensor] = None, sky_directions: Optional[Tensor] = None,
+                rays: Optional[Tuple[Tensor, Tensor]] = None, multi_view_points: Optional[Tensor] = None):
+        """One fitting pass: (sum of losses, loss dict, outputs, batch).  Add the sum to the main step's loss before backward().
+        `rays` / `multi_view_points`: the host draws of `draw_host()`, already on the device (no host work inside the pass)."""
+        batch = self.generate_ddf_samples(sky_origins, sky_directions, rays=rays)
+        outputs = self.get_outputs(batch, stop_gradients=self.stop_sdf_gradients, multi_view_points=multi_view_points)
         losses = self.get_loss_dict(outputs, batch)
         return sum(losses.values()), losses, outputs, batch
 

@@ -214,9 +214,33 @@ def sdf_field(x: Tensor, blob: Tensor, hash_table: Tensor, scalings: Tensor, log
 
 
 # ------------------------------------------------------------------------------------------- K3
-def neus_composite(sdf, grad, albedo, ray_dirs, starts, ends, deltas, dnorm, inv_s: float, cos_anneal_ratio: float = 1.0, training: bool = False,
+_MINMAX_INIT: Dict[torch.device, Tensor] = {}
+
+
+def _minmax_init(dev) -> Tensor:
+    """A fresh {+inf, -inf} accumulator for the composite kernel's running min / max: cloned on the device from a per-device constant
+    (torch.tensor([...], device=cuda) would be a pageable host->device copy per call: a host sync, and illegal in a graph capture)."""
+    dev = torch.device(dev)
+    c = _MINMAX_INIT.get(dev)
+    if c is None:
+        c = _MINMAX_INIT[dev] = torch.tensor([float("inf"), float("-inf")], device=dev, dtype=torch.float32)
+    return c.clone()
+
+
+def _inv_s_arg(inv_s, dev):
+    """(by-value float, device pointer) for the composite calls: a tensor stays on the device (`*_dv` entry points)."""
+    if isinstance(inv_s, torch.Tensor):
+        t = _chk("inv_s", inv_s.detach().reshape(-1), shape=(1,))
+        if t.device != dev:
+            raise ValueError(f"inv_s: tensor on {t.device}, samples on {dev}")
+        return None, t
+    return float(inv_s), None
+
+
+def neus_composite(sdf, grad, albedo, ray_dirs, starts, ends, deltas, dnorm, inv_s, cos_anneal_ratio: float = 1.0, training: bool = False,
                    steps_minmax: Optional[Tensor] = None) -> Dict[str, Tensor]:
-    """sdf/starts/ends/deltas [R,S(,1)], grad/albedo [R,S,3], ray_dirs [R,3], dnorm [R(,1)].
+    """sdf/starts/ends/deltas [R,S(,1)], grad/albedo [R,S,3], ray_dirs [R,3], dnorm [R(,1)]; inv_s a float or a 1-element CUDA tensor
+    (read on the device: no host synchronisation).
     The expected depth is clipped to [min, max] of the sample mid-points like nerfstudio's DepthRenderer: over THIS
     batch by default (the reference renders 256-ray chunks, so its clip range is per chunk), or to the caller's
     ``steps_minmax`` [2] when given (tile- and rank-invariant eval renders)."""
@@ -235,10 +259,16 @@ def neus_composite(sdf, grad, albedo, ray_dirs, starts, ends, deltas, dnorm, inv
         "albedo": torch.empty((R, 3), **f), "bg_transmittance": torch.empty((R,), **f),
         "p2p_dist": torch.empty((R,), **f), "depth": torch.empty((R,), **f),
     }
-    mm = torch.tensor([float("inf"), float("-inf")], **f)
+    mm = _minmax_init(dev)
     lib = _lib.load()
     st = _stream(sdf)
-    _lib.check(lib.nsk_neus_composite_fwd(_ptr(sdf), _ptr(grad), _ptr(albedo), _ptr(ray_dirs), _ptr(starts), _ptr(ends), _ptr(deltas), c_int64(R), c_int(S), c_float(inv_s), c_float(cos_anneal_ratio), c_int(int(training)), _ptr(out["weights"]), _ptr(out["wa"]), _ptr(out["normals"]), _ptr(out["accumulation"]), _ptr(out["p2p_raw"]), _ptr(out["normal"]), _ptr(out["albedo"]), _ptr(out["bg_transmittance"]), _ptr(mm), st), "nsk_neus_composite_fwd")
+    inv_f, inv_t = _inv_s_arg(inv_s, dev)
+    tail = (c_float(cos_anneal_ratio), c_int(int(training)), _ptr(out["weights"]), _ptr(out["wa"]), _ptr(out["normals"]), _ptr(out["accumulation"]), _ptr(out["p2p_raw"]), _ptr(out["normal"]), _ptr(out["albedo"]), _ptr(out["bg_transmittance"]), _ptr(mm), st)
+    head = (_ptr(sdf), _ptr(grad), _ptr(albedo), _ptr(ray_dirs), _ptr(starts), _ptr(ends), _ptr(deltas), c_int64(R), c_int(S))
+    if inv_t is None:
+        _lib.check(lib.nsk_neus_composite_fwd(*head, c_float(inv_f), *tail), "nsk_neus_composite_fwd")
+    else:
+        _lib.check(lib.nsk_neus_composite_fwd_dv(*head, _ptr(inv_t), *tail), "nsk_neus_composite_fwd_dv")
     if steps_minmax is not None:
         mm = _chk("steps_minmax", steps_minmax, shape=(2,))
     _lib.check(lib.nsk_neus_finalize_depth(_ptr(out["p2p_raw"]), _ptr(dnorm), _ptr(mm), c_int64(R), _ptr(out["p2p_dist"]), _ptr(out["depth"]), st), "nsk_neus_finalize_depth")
@@ -246,7 +276,7 @@ def neus_composite(sdf, grad, albedo, ray_dirs, starts, ends, deltas, dnorm, inv
     return out
 
 
-def neus_composite_bwd(sdf, grad, albedo, ray_dirs, starts, ends, deltas, inv_s: float, cos_anneal_ratio: float, g: Dict[str, Optional[Tensor]]):
+def neus_composite_bwd(sdf, grad, albedo, ray_dirs, starts, ends, deltas, inv_s, cos_anneal_ratio: float, g: Dict[str, Optional[Tensor]]):
     """Cotangents g[{"weights","wa","normals","accumulation","p2p_raw","normal","albedo","bg_transmittance"}] (missing / None = 0)
     -> (d_sdf [R,S], d_grad [R,S,3], d_albedo [R,S,3], d_inv_s [1])."""
     R, S = sdf.shape[0], sdf.shape[1]
@@ -258,9 +288,14 @@ def neus_composite_bwd(sdf, grad, albedo, ray_dirs, starts, ends, deltas, inv_s:
     gg = {k: (None if g.get(k) is None else _chk("g_" + k, g[k].reshape(shp), shape=shp)) for k, shp in shapes.items()}
     f = dict(device=sdf.device, dtype=torch.float32)
     d_sdf, d_grad, d_alb, d_inv = torch.empty((R, S), **f), torch.empty((R, S, 3), **f), torch.empty((R, S, 3), **f), torch.zeros((1,), **f)
-    _lib.check(_lib.load().nsk_neus_composite_bwd(_ptr(sdf), _ptr(grad), _ptr(albedo), _ptr(ray_dirs), _ptr(starts), _ptr(ends), _ptr(deltas), c_int64(R), c_int(S), c_float(inv_s), c_float(cos_anneal_ratio),
-                                                  _ptr(gg["weights"]), _ptr(gg["wa"]), _ptr(gg["normals"]), _ptr(gg["accumulation"]), _ptr(gg["p2p_raw"]), _ptr(gg["normal"]), _ptr(gg["albedo"]), _ptr(gg["bg_transmittance"]),
-                                                  _ptr(d_sdf), _ptr(d_grad), _ptr(d_alb), _ptr(d_inv), _stream(sdf)), "nsk_neus_composite_bwd")
+    inv_f, inv_t = _inv_s_arg(inv_s, sdf.device)
+    head = (_ptr(sdf), _ptr(grad), _ptr(albedo), _ptr(ray_dirs), _ptr(starts), _ptr(ends), _ptr(deltas), c_int64(R), c_int(S))
+    tail = (c_float(cos_anneal_ratio), _ptr(gg["weights"]), _ptr(gg["wa"]), _ptr(gg["normals"]), _ptr(gg["accumulation"]), _ptr(gg["p2p_raw"]), _ptr(gg["normal"]), _ptr(gg["albedo"]), _ptr(gg["bg_transmittance"]),
+            _ptr(d_sdf), _ptr(d_grad), _ptr(d_alb), _ptr(d_inv), _stream(sdf))
+    if inv_t is None:
+        _lib.check(_lib.load().nsk_neus_composite_bwd(*head, c_float(inv_f), *tail), "nsk_neus_composite_bwd")
+    else:
+        _lib.check(_lib.load().nsk_neus_composite_bwd_dv(*head, _ptr(inv_t), *tail), "nsk_neus_composite_bwd_dv")
     return d_sdf, d_grad, d_alb, d_inv
 
 

@@ -175,6 +175,7 @@ class GradBucketReducer:
         self.launched_order: List[int] = []
         self._next = 0                      # first bucket not launched yet
         self._finished = False
+        self.capturing = False              # set by graphed.GraphedTrainIteration while it captures forward + backward
         for p in self.params:
             p.register_post_accumulate_grad_hook(self._hook)
 
@@ -186,6 +187,12 @@ class GradBucketReducer:
         """Zero the buckets in place (the .grad views stay attached) and re-arm the ready counters."""
         for b in self.buckets:
             b.zero_()
+        self.rearm()
+
+    def rearm(self) -> None:
+        """Re-arm the ready counters WITHOUT touching the buckets: what a replay of a captured iteration needs (the zero-fill and
+        the backward are inside the CUDA graph, `neusky_b200/graphed.py`; the hooks only ran while it was captured), followed by
+        `finish()`, which then launches every bucket in order."""
         self._left = list(self._sizes)
         self._work = []
         self.launched_order = []
@@ -203,6 +210,8 @@ class GradBucketReducer:
         bi = self._bucket_of[id(p)]
         if p.grad is None or p.grad.untyped_storage().data_ptr() != self.buckets[bi].untyped_storage().data_ptr():
             raise RuntimeError("GradBucketReducer: a parameter's .grad was replaced; use reducer.zero_grad(), not optimizer.zero_grad(set_to_none=True)")
+        if self.capturing:          # stream capture of the iteration: no collective inside the graph, `finish()` after each replay reduces
+            return
         if self._left[bi] <= 0 or self._finished:
             raise RuntimeError("GradBucketReducer: a gradient arrived for a bucket that is already being reduced -- call reducer.zero_grad() "
                                "before every backward() (one backward per step; accumulate micro-batches into the loss instead)")

@@ -183,10 +183,24 @@ def sphere_collider(origins: Tensor, directions: Tensor, radius: float = 1.0, ne
     return torch.nan_to_num(near, nan=0.0), torch.nan_to_num(far, nan=0.0)
 
 
+_UNIT_BINS: Dict[tuple, Tensor] = {}
+
+
+def _unit_bins(S: int, like: Tensor) -> Tensor:
+    """torch.linspace(0, 1, S + 1)[None] with the CPU kernel's rounding, built on the host ONCE per (S, dtype, device): a fresh
+    host tensor per call is a pageable host->device copy, i.e. a host synchronisation inside every placement (and illegal in a
+    CUDA-graph capture of the training iteration)."""
+    key = (int(S), like.dtype, str(like.device))
+    t = _UNIT_BINS.get(key)
+    if t is None:
+        t = _UNIT_BINS[key] = torch.linspace(0.0, 1.0, S + 1, dtype=like.dtype)[None].to(like.device)
+    return t
+
+
 def uniform_samples(near: Tensor, far: Tensor, S: int):
     """nerfstudio UniformSampler eval placement [SURVEY A.6]: same op sequence as the oracle so that starts / ends
     are bit-identical to the CPU reference."""
-    bins = torch.linspace(0.0, 1.0, S + 1, dtype=near.dtype)[None].to(near.device)   # built on the host: CPU linspace rounding
+    bins = _unit_bins(S, near)                                                        # built on the host: CPU linspace rounding
     e = bins * far + (1 - bins) * near
     return e[:, :-1].contiguous(), e[:, 1:].contiguous()
 
@@ -472,7 +486,7 @@ def global_steps_minmax(origins: Tensor, directions: Tensor, S: int) -> Tensor:
     bundle is rendered in one batch), from the first and last bins only -- same arithmetic as uniform_samples, so the
     values are bit-identical to a full placement.  Lets tiles / ranks clip to an image-global range."""
     near, far = sphere_collider(origins, directions)
-    bins = torch.linspace(0.0, 1.0, S + 1, dtype=near.dtype)[None].to(near.device)
+    bins = _unit_bins(S, near)
     sel = bins[:, [0, 1, S - 1, S]]
     e = sel * far + (1 - sel) * near
     return torch.stack([((e[:, 0] + e[:, 1]) / 2).min(), ((e[:, 2] + e[:, 3]) / 2).max()]).contiguous()

@@ -185,7 +185,8 @@ def ddf_row_features_torch(origins: Tensor, directions: Tensor) -> Tensor:
     z = torch.linalg.cross(y, x)
     z = z / z.norm(dim=-1, keepdim=True)
     dl = torch.stack([(x * directions).sum(-1), (y * directions).sum(-1), (z * directions).sum(-1)], dim=-1)
-    ang = (2.0 * torch.pi * dl)[:, :, None] * dl.new_tensor([1.0, 4.0])                      # [N,3,2]
+    a1 = 2.0 * torch.pi * dl
+    ang = torch.stack([a1 * 1.0, a1 * 4.0], dim=-1)                                          # [N,3,2]; no host-built constant tensor (a pageable h2d copy = a sync)
     ang = ang.reshape(-1, 6)
     return torch.cat([dl, torch.sin(ang), torch.sin(ang + torch.pi / 2.0)], dim=-1)
 
@@ -510,7 +511,7 @@ class NeuSkyTrainStep(torch.nn.Module):
         return self._sdf_w
 
     def _drop_sdf_weights(self, grad):
-        self._sdf_w_key = None
+        self._sdf_w_key, self._sdf_w = None, None          # also releases the fold's autograd nodes (they pin the parameters' AccumulateGrad nodes)
         return None
 
     def get_param_groups(self) -> Dict[str, List[torch.nn.Parameter]]:
@@ -522,14 +523,20 @@ class NeuSkyTrainStep(torch.nn.Module):
 
     def set_directions(self, dirs: Tensor) -> None:
         """Illumination directions of this iteration [D,3] (IcosahedronSampler with its random rotation, neusky_model.py:452-456)."""
+        d0, mask_u8, dirs_sel, sel = self.compact_directions(dirs)
+        nb = d0.device.type == "cpu"
+        self.dirs = d0.to(self.dev, non_blocking=nb)
+        self.mask_u8 = mask_u8.to(self.dev, non_blocking=nb)
+        self.dirs_sel = dirs_sel.to(self.dev, non_blocking=nb)
+        self.sel_index = sel.to(self.dev, non_blocking=nb)
+
+    def compact_directions(self, dirs: Tensor) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+        """dirs [D,3] -> (dirs fp32 [D,3], upper-hemisphere mask uint8 [D], the D' selected directions [D',3], index of every direction
+        in that selection or -1, int32 [D]) on the device `dirs` lives on (the host for the icosphere sampler: no sync)."""
         d0 = dirs.to(torch.float32).contiguous()          # mask / compaction on the device the sampler produced them on (host: no sync)
         m = (d0[:, 2] > 0) if self.only_upper else torch.ones(d0.shape[0], dtype=torch.bool, device=d0.device)
         sel = torch.where(m, torch.cumsum(m.to(torch.int32), 0, dtype=torch.int32) - 1, torch.full_like(m, -1, dtype=torch.int32)).to(torch.int32)
-        nb = d0.device.type == "cpu"
-        self.dirs = d0.to(self.dev, non_blocking=nb)
-        self.mask_u8 = m.to(torch.uint8).contiguous().to(self.dev, non_blocking=nb)
-        self.dirs_sel = d0[m].contiguous().to(self.dev, non_blocking=nb)
-        self.sel_index = sel.contiguous().to(self.dev, non_blocking=nb)
+        return d0, m.to(torch.uint8).contiguous(), d0[m].contiguous(), sel.contiguous()
 
     # -- forward ---------------------------------------------------------------------------------------------
     def forward(self, batch: Dict[str, Tensor], grid_positions: Optional[Tensor] = None, grid_dirs: Optional[Tensor] = None) -> Tuple[Tensor, Dict[str, Tensor], Dict[str, Tensor]]:
@@ -605,7 +612,8 @@ class NeuSkyTrainStep(torch.nn.Module):
         ws = out["accumulation"].clip(1e-3, 1.0 - 1e-3)
         L["fg_mask_loss"] = torch.nn.functional.binary_cross_entropy(ws, fg.to(ws.dtype))
         gm = ground.to(image.dtype)[:, None]
-        up = torch.tensor([0.0, 0.0, 1.0], device=image.device).expand_as(out["normal"])
+        up = torch.zeros_like(out["normal"])
+        up[:, 2] = 1.0                                                                  # built on the device: no pageable h2d copy (a host sync)
         L["ground_plane_loss"] = _monosdf_normal_loss(out["normal"] * gm, up * gm)
         srgb_bg = _linear_to_srgb(out["hdr_background_colours"])
         L["sky_pixel_loss"] = sky_pixel_loss(srgb_bg, image, sky.to(image.dtype)[:, None].expand_as(srgb_bg))

@@ -58,6 +58,25 @@ def _worker(rank, world, port, q):
         ok = ok and bool((params[3].grad == 0).all())
         ok = ok and sorted(red.launched_order) == [0, 1]
         ok = ok and params[0].grad.untyped_storage().data_ptr() == red.buckets[0].untyped_storage().data_ptr()
+    # graph-replay protocol (neusky_b200/graphed.py): while an iteration is CAPTURED the hooks must not launch a collective; after a
+    # replay (here: the same backward, run with `capturing` set) `rearm()` + `finish()` reduce every bucket in order
+    red.zero_grad()
+    red.capturing = True
+    idx, x = _data(500 + rank, 64)
+    _loss(params, idx, x).backward()
+    red.capturing = False
+    ok = ok and red.launched_order == []
+    red.rearm()
+    red.finish()
+    ref = _model(0)
+    tot = 0
+    for r in range(world):
+        i2, x2 = _data(500 + r, 64)
+        tot = tot + _loss(ref, i2, x2) / world
+    tot.backward()
+    for p, pr in zip(params[:3], ref[:3]):
+        ok = ok and torch.allclose(p.grad, pr.grad, rtol=1e-5, atol=1e-7)
+    ok = ok and red.launched_order == [0, 1]
     q.put((rank, bool(ok)))
     dist.destroy_process_group()
 
