@@ -369,6 +369,11 @@ int nsk_ddf_rows_fwd(const float* origins, const float* directions, int64_t N, c
 int nsk_film_sin_fwd(const float* z, const float* film, int ldf, int layer, int64_t N, float* a, void* stream);
 int nsk_film_sin_bwd(const float* da, const float* z, const float* film, int ldf, int layer, int64_t N, float* dz,
                      float* dfilm, void* stream);
+/* nsk_film_sin_bwd that ALSO accumulates (atomics; caller zero-fills) the column sums the bias gradients need:
+ * sum_dz [256] += sum_r dz[r, :] (trunk layer `layer`), sum_dfilm [ldf] += sum_r dfilm[r, :] on this layer's two column blocks
+ * (the last mapping layer's bias gradient): saves the separate column-sum passes over [N,256] per layer and [N,ldf]. */
+int nsk_film_sin_bwd_sums(const float* da, const float* z, const float* film, int ldf, int layer, int64_t N, float* dz,
+                          float* dfilm, float* sum_dz, float* sum_dfilm, void* stream);
 int nsk_ddf_head_fwd(const float* a5, const float* w_final, const float* b_final, const float* term_dist, int64_t N,
                      float radius, const float* threshold, float sigmoid_scale, float* that, float* vis, void* stream);
 int nsk_ddf_head_bwd(const float* a5, const float* w_final, const float* that, const float* term_dist, const float* d_vis,

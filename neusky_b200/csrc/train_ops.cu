@@ -108,11 +108,16 @@ film_sin_fwd_kernel(const float* __restrict__ z, const float* __restrict__ F, in
 }
 
 // du = da * cos(u); dz = du * freq; dF[:, l*H + c] = 15 * du * z; dF[:, half + l*H + c] = du
+// SUMS: also accumulate the column sums of dz (the trunk layer's bias gradient) and of the two dF column blocks (their share of the
+// last mapping layer's bias gradient) -- a thread keeps its 4 columns for the whole grid-stride loop (the grid is a multiple of 64
+// granules), so the sums ride in registers and the separate colsum passes over [N,256] x 5 and [N,2560] go away.
+template <bool SUMS>
 __global__ void __launch_bounds__(256)
 film_sin_bwd_kernel(const float* __restrict__ da, const float* __restrict__ z, const float* __restrict__ F, int ldf, int layer,
-                    int64_t N, float* __restrict__ dz, float* __restrict__ dF) {
+                    int64_t N, float* __restrict__ dz, float* __restrict__ dF, float* __restrict__ sum_dz, float* __restrict__ sum_dF) {
   const int64_t total = N * 64;
   const int half = ldf >> 1;
+  float4 s_z = make_float4(0.f, 0.f, 0.f, 0.f), s_f = s_z, s_p = s_z;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i >> 6;
     const int c = (int)(i & 63) * 4;
@@ -134,6 +139,26 @@ film_sin_bwd_kernel(const float* __restrict__ da, const float* __restrict__ z, c
     *reinterpret_cast<float4*>(dz + r * 256 + c) = odz;
     *reinterpret_cast<float4*>(dF + r * ldf + layer * 256 + c) = odf;
     *reinterpret_cast<float4*>(dF + r * ldf + half + layer * 256 + c) = odp;
+    if (SUMS) {
+      s_z.x += odz.x; s_z.y += odz.y; s_z.z += odz.z; s_z.w += odz.w;
+      s_f.x += odf.x; s_f.y += odf.y; s_f.z += odf.z; s_f.w += odf.w;
+      s_p.x += odp.x; s_p.y += odp.y; s_p.z += odp.z; s_p.w += odp.w;
+    }
+  }
+  if (SUMS) {
+    // 256 threads = 4 row groups x 64 column granules: fold the row groups through shared memory, one atomic per column and block
+    __shared__ float4 sh[3][4][64];
+    const int cg = threadIdx.x & 63, rg = threadIdx.x >> 6;
+    sh[0][rg][cg] = s_z; sh[1][rg][cg] = s_f; sh[2][rg][cg] = s_p;
+    __syncthreads();
+    if (threadIdx.x < 192) {
+      const int which = threadIdx.x >> 6;
+      float4 t = sh[which][0][cg];
+#pragma unroll
+      for (int g2 = 1; g2 < 4; ++g2) { const float4 u = sh[which][g2][cg]; t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w; }
+      float* dst = which == 0 ? sum_dz + cg * 4 : which == 1 ? sum_dF + layer * 256 + cg * 4 : sum_dF + half + layer * 256 + cg * 4;
+      atomicAdd(dst, t.x); atomicAdd(dst + 1, t.y); atomicAdd(dst + 2, t.z); atomicAdd(dst + 3, t.w);
+    }
   }
 }
 
@@ -271,7 +296,17 @@ extern "C" int nsk_film_sin_bwd(const float* da, const float* z, const float* fi
   NSK_REQUIRE(da && z && film && dz && dfilm, "nsk_film_sin_bwd: null pointer");
   NSK_REQUIRE((ldf & 7) == 0 && layer >= 0 && (layer + 1) * 256 <= ldf / 2, "nsk_film_sin_bwd: layer / ldf");
   if (N == 0) return 0;
-  film_sin_bwd_kernel<<<grid_for(N * 64, 256), 256, 0, as_stream(stream)>>>(da, z, film, ldf, layer, N, dz, dfilm);
+  film_sin_bwd_kernel<false><<<grid_for(N * 64, 256), 256, 0, as_stream(stream)>>>(da, z, film, ldf, layer, N, dz, dfilm, nullptr, nullptr);
+  return check_launch("film_sin_bwd_kernel");
+}
+
+extern "C" int nsk_film_sin_bwd_sums(const float* da, const float* z, const float* film, int ldf, int layer, int64_t N, float* dz,
+                                     float* dfilm, float* sum_dz, float* sum_dfilm, void* stream) {
+  NSK_REQUIRE(da && z && film && dz && dfilm && sum_dz && sum_dfilm, "nsk_film_sin_bwd_sums: null pointer");
+  NSK_REQUIRE((ldf & 7) == 0 && layer >= 0 && (layer + 1) * 256 <= ldf / 2, "nsk_film_sin_bwd_sums: layer / ldf");
+  if (N == 0) return 0;
+  // block = 256 threads = 4 rows of 64 granules, so every thread keeps its column granule across the grid-stride loop for any grid size
+  film_sin_bwd_kernel<true><<<grid_for(N * 64, 256), 256, 0, as_stream(stream)>>>(da, z, film, ldf, layer, N, dz, dfilm, sum_dz, sum_dfilm);
   return check_launch("film_sin_bwd_kernel");
 }
 

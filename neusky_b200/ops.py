@@ -775,14 +775,23 @@ def film_sin(z: Tensor, film: Tensor, layer: int) -> Tensor:
     return a
 
 
-def film_sin_bwd(da: Tensor, z: Tensor, film: Tensor, layer: int, dfilm: Tensor) -> Tensor:
-    """Returns d z [N,256]; writes the layer's frequency / phase column blocks of ``dfilm`` [N, ldf]."""
+def film_sin_bwd(da: Tensor, z: Tensor, film: Tensor, layer: int, dfilm: Tensor, sum_dz: Optional[Tensor] = None, sum_dfilm: Optional[Tensor] = None) -> Tensor:
+    """Returns d z [N,256]; writes the layer's frequency / phase column blocks of ``dfilm`` [N, ldf].  With ``sum_dz`` [256] and
+    ``sum_dfilm`` [ldf] (both or neither; ACCUMULATED INTO, caller zero-fills) the column sums of d z and of those ``dfilm`` blocks
+    come out of the same pass (the bias gradients of the trunk layer and of the last mapping layer)."""
     N = z.shape[0]
     da, z, film = _chk("da", da, shape=(N, 256)), _chk("z", z, shape=(N, 256)), _chk("film", film, shape=(N, None))
     if not (dfilm.is_cuda and dfilm.dtype == torch.float32 and dfilm.is_contiguous() and dfilm.shape == film.shape):
         raise ValueError("dfilm: expected a contiguous CUDA fp32 tensor shaped like film")
     dz = torch.empty_like(z)
-    _lib.check(_lib.load().nsk_film_sin_bwd(_ptr(da), _ptr(z), _ptr(film), c_int(film.shape[1]), c_int(layer), c_int64(N), _ptr(dz), _ptr(dfilm), _stream(z)), "nsk_film_sin_bwd")
+    if (sum_dz is None) != (sum_dfilm is None):
+        raise ValueError("film_sin_bwd: pass both sum_dz and sum_dfilm or neither")
+    if sum_dz is None:
+        _lib.check(_lib.load().nsk_film_sin_bwd(_ptr(da), _ptr(z), _ptr(film), c_int(film.shape[1]), c_int(layer), c_int64(N), _ptr(dz), _ptr(dfilm), _stream(z)), "nsk_film_sin_bwd")
+    else:
+        sum_dz, sum_dfilm = _chk_out("sum_dz", sum_dz, shape=(256,)), _chk_out("sum_dfilm", sum_dfilm, shape=(film.shape[1],))
+        _lib.check(_lib.load().nsk_film_sin_bwd_sums(_ptr(da), _ptr(z), _ptr(film), c_int(film.shape[1]), c_int(layer), c_int64(N), _ptr(dz), _ptr(dfilm),
+                                                     _ptr(sum_dz), _ptr(sum_dfilm), _stream(z)), "nsk_film_sin_bwd_sums")
     return dz
 
 

@@ -99,13 +99,14 @@ def _ddf_backward_core(cfg: DDFConfig, cond, xin, q, term, film, that, threshold
     dWt: List[Optional[Tensor]] = [None] * DDF_TRUNK_LAYERS
     dbt: List[Optional[Tensor]] = [None] * DDF_TRUNK_LAYERS
     d_xin = None
+    db_film = zeros(film.shape[1])          # column sums of dfilm (bias gradient of the last mapping layer): filled block by block below
     for l in reversed(range(DDF_TRUNK_LAYERS)):
-        dz = ops.film_sin_bwd(da, zs[l], film, l, dfilm)
+        dbt[l] = zeros(256)
+        dz = ops.film_sin_bwd(da, zs[l], film, l, dfilm, sum_dz=dbt[l], sum_dfilm=db_film)      # bias column sums in the same pass
         a_prev = acts[l - 1] if l > 0 else xin
         g = zeros(256, a_prev.shape[1])
         ops.gemm_tn(dz, a_prev, g, split=sp)
         dWt[l] = g[:, :Wt[l].shape[1]]
-        dbt[l] = ops.colsum(dz, zeros(256))
         if l > 0:
             da = ops.gemm_nt(dz, Wt[l].t().contiguous(), split=sp)
         elif need_xin:
@@ -115,7 +116,7 @@ def _ddf_backward_core(cfg: DDFConfig, cond, xin, q, term, film, that, threshold
     g = zeros(*Wm[-1].shape)
     ops.gemm_tn(dfilm, hs[-1], g, split=sp)
     dWm[-1] = g
-    dbm[-1] = ops.colsum(dfilm, zeros(film.shape[1]))
+    dbm[-1] = db_film
     dz = ops.gemm_nt(dfilm, Wm[-1].t().contiguous(), aux=hs[-1], dact="leaky", split=sp)
     del dfilm
     d_table = None
