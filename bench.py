@@ -505,7 +505,7 @@ def train_arm(args, ctx):
     # zero-fill + forward + DDF fitting pass + backward as ONE CUDA graph after two eager iterations (neusky_b200/graphed.py); the host's
     # random draws, the h2d of the batch, the gradient all-reduce and the optimizer step stay outside it.  --no-train-graph: all eager.
     from neusky_b200.graphed import GraphedTrainIteration
-    iteration = GraphedTrainIteration(step_mod, red, opt, fit=fit, graph=not args.no_train_graph)
+    iteration = GraphedTrainIteration(step_mod, red, opt, fit=fit, graph=not args.no_train_graph, overlap_fit=not args.no_fit_overlap)
 
     def one_step():
         i = it["i"]; it["i"] += 1
@@ -539,6 +539,14 @@ def train_arm(args, ctx):
     clocks = sampler.stop() if sampler else None
     launches = _lib.launches - l0
     t, wall = ctx.max_over_ranks(t, wall)
+    if os.environ.get("NSK_TRAIN_PROFILE") and rank == 0:
+        # diagnostics: per-kernel device time of two more iterations (graph replays) through CUPTI, NOT part of any reported number
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            one_step(); one_step()
+            torch.cuda.synchronize()
+        with open(os.environ["NSK_TRAIN_PROFILE"], "w") as f:
+            f.write(prof.key_averages().table(sort_by="cuda_time_total", row_limit=60, max_name_column_width=90))
     # exposed all-reduce time: the same steps with the collective switched off (every rank keeps its local gradients; identical compute)
     exposed_ms = None
     if world > 1:
@@ -666,6 +674,7 @@ def main():
     ap.add_argument("--ddf-split-bwd", type=int, default=0, choices=[0, 1, 3], help="train: precision of the DDF's backward contractions only (0 = same as --split)")
     ap.add_argument("--train-sampler", default="proposal", choices=["proposal", "uniform"], help="train: sample placement (proposal = shipped NeuS-facto default)")
     ap.add_argument("--no-ddf-fit", action="store_true", help="train: leave the DDF fitting pass (fit_visibility_field=True in the reference) out of the step")
+    ap.add_argument("--no-fit-overlap", action="store_true", help="train: run the DDF fitting pass after the main pass on the same stream instead of as a parallel branch")
     ap.add_argument("--no-train-graph", action="store_true", help="train: run every iteration eagerly (~2900 launches from the host) instead of replaying the captured CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -30,10 +30,11 @@ Tensor = torch.Tensor
 
 
 class GraphedTrainIteration:
-    def __init__(self, step, reducer, optimizer, fit=None, graph: bool = True, eager_warmup: int = 2):
+    def __init__(self, step, reducer, optimizer, fit=None, graph: bool = True, eager_warmup: int = 2, overlap_fit: bool = True):
         """`step`: train.NeuSkyTrainStep; `reducer`: parallel.GradBucketReducer over its parameters (the .grad views are the
         graph's static gradient buffers); `optimizer`: stepped after the reduce; `fit`: ddf_fit.DDFFit or None.
-        `graph=False` runs every iteration eagerly through the same code (the comparison arm of bench.py and the tests)."""
+        `graph=False` runs every iteration eagerly through the same code (the comparison arm of bench.py and the tests).
+        `overlap_fit`: run the DDF fitting pass as a parallel branch of the iteration (second stream) instead of after the main pass."""
         if not torch.cuda.is_available():
             raise RuntimeError("GraphedTrainIteration needs a CUDA device (neusky_b200 has no CPU path)")
         self.step, self.red, self.opt, self.fit = step, reducer, optimizer, fit
@@ -48,6 +49,8 @@ class GraphedTrainIteration:
         # were created on, and a node created by an eager iteration on the legacy default stream that is still alive when the capture
         # starts makes the capture depend on the default stream (cudaErrorStreamCaptureImplicit).
         self._stream = torch.cuda.Stream(device=step.dev)
+        self._fit_stream = torch.cuda.Stream(device=step.dev)
+        self.overlap_fit = bool(overlap_fit)
 
     # ------------------------------------------------------------------------------------------ host side of an iteration
     def _host_inputs(self, batch, dirs, grid_positions, grid_dirs, sky_origins, sky_directions) -> Dict[str, Tensor]:
@@ -91,10 +94,31 @@ class GraphedTrainIteration:
             else:
                 batch[name] = s[k]
         self.red.zero_grad()
+        run_fit = lambda: self.fit(s.get("fit.sky_origins"), s.get("fit.sky_directions"), rays=(s["fit.origins"], s["fit.directions"]),
+                                   multi_view_points=s.get("fit.multi_view_points"))
+        fit_res = None
+        if self.fit is not None and self.overlap_fit:
+            # The DDF fitting pass is independent of the main pass until the two losses are added, and its kernels are small (1024 rays,
+            # 2304 DDF rows): it runs as a second BRANCH (its own stream; a fork / join inside the captured graph) next to the main
+            # pass's 328k-row kernels instead of in front of them.  Autograd runs each branch's backward on the branch's stream.
+            cur = torch.cuda.current_stream()
+            shared = list(st.sdf_weights())                       # what both branches read is produced before the fork
+            for f in st.proposal_fields or ():
+                f.refresh()
+            self._fit_stream.wait_stream(cur)
+            with torch.cuda.stream(self._fit_stream):
+                fit_res = run_fit()
+            for t in shared:
+                t.record_stream(self._fit_stream)
         loss, losses, _out = st(batch, grid_positions=s.get("grid_positions"), grid_dirs=s.get("grid_dirs"))
         if self.fit is not None:
-            fl, fls, _, _ = self.fit(s.get("fit.sky_origins"), s.get("fit.sky_directions"), rays=(s["fit.origins"], s["fit.directions"]),
-                                     multi_view_points=s.get("fit.multi_view_points"))
+            if fit_res is None:
+                fit_res = run_fit()
+            else:
+                torch.cuda.current_stream().wait_stream(self._fit_stream)
+                for t in (fit_res[0], *fit_res[1].values()):
+                    t.record_stream(torch.cuda.current_stream())
+            fl, fls = fit_res[0], fit_res[1]
             loss = loss + fl
             losses = {**losses, **{"ddf_fit." + k: v for k, v in fls.items()}}
         loss.backward()

@@ -57,7 +57,9 @@ def _build(dev, proposal, with_fit, graph):
     fit = None
     if with_fit:
         fit = DDFFit(step, sampler=VMFDDFSampler(DDFSamplerConfig(num_samples_on_sphere=2, num_rays_per_sample=8), ddf_sphere_radius=step.radius, device=dev))
-    return step, red, GraphedTrainIteration(step, red, opt, fit=fit, graph=graph, eager_warmup=1)
+    # the eager arm also keeps the DDF fitting pass AFTER the main pass on one stream (the reference's order); the graphed arm runs it as
+    # a parallel branch on a second stream, so the comparison covers the fork / join as well as the capture
+    return step, red, GraphedTrainIteration(step, red, opt, fit=fit, graph=graph, eager_warmup=1, overlap_fit=graph)
 
 
 def _run(dev, proposal, with_fit, graph, n_iter, anneal_change_at=None, repeat_inputs=False):
