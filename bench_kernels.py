@@ -161,9 +161,12 @@ def kernel_rooflines(dev, peaks, scale: float = 1.0, emit=None):
         f = P.HashMLPDensityField(nb_init.init_proposal_params(mr, table_scale=1.0, density_bias=1.0), mr, device=dev)
         bins = P.uniform_bins(R, S, dev, torch.rand(R, device=dev))
         ms = timeit(lambda: f.density_on_rays(o, d, near, far, bins))
+        # NOT an HBM kernel: the 5 MB table is L2 / L1 resident, so its 372 algorithmic bytes per sample are cache traffic (1.2-1.7x the HBM
+        # peak) and no HBM fraction is claimed; the DRAM side is ~8 B per sample (ncu: profiles/r02_ncu_hbm_kernels_summary.txt)
         report(f"proposal_density_fwd (P1) S={S} max_res={mr}", "hbm", ms, R * S * 372.0, 372, R * S,
-               {"note": "table 5 MB: gathers are L2/L1 hits; actual HBM traffic is ~8 B/sample", "achieved_actual_GBps": R * S * 8.0 / (ms * 1e-3) / 1e9,
-                "Gsamples_per_s": R * S / (ms * 1e-3) / 1e9})
+               {"bound": "l2 (5 MB table is cache resident)", "frac": None, "peak": None, "achieved_is": "algorithmic gather + stream bytes per second (cache traffic)",
+                "note": "table 5 MB: gathers are L2/L1 hits; actual HBM traffic is ~8 B/sample", "achieved_actual_GBps": R * S * 8.0 / (ms * 1e-3) / 1e9,
+                "frac_hbm_actual": R * S * 8.0 / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "Gsamples_per_s": R * S / (ms * 1e-3) / 1e9})
         dens = f.density_on_rays(o, d, near, far, bins)
         ms = timeit(lambda: P.pdf_resample(bins, near, far, N, density=dens))
         byt = (S + 1) * 4 + S * 4 + S * 4 + 2 * (N + 1) * 4 + 8

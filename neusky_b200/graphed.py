@@ -34,7 +34,8 @@ class GraphedTrainIteration:
         """`step`: train.NeuSkyTrainStep; `reducer`: parallel.GradBucketReducer over its parameters (the .grad views are the
         graph's static gradient buffers); `optimizer`: stepped after the reduce; `fit`: ddf_fit.DDFFit or None.
         `graph=False` runs every iteration eagerly through the same code (the comparison arm of bench.py and the tests).
-        `overlap_fit`: run the DDF fitting pass as a parallel branch of the iteration (second stream) instead of after the main pass."""
+        `overlap_fit`: run the DDF fitting pass and the RENI++ radiance decodes as parallel branches of the iteration (side streams,
+        fork / join inside the captured graph) instead of in line with the main pass."""
         if not torch.cuda.is_available():
             raise RuntimeError("GraphedTrainIteration needs a CUDA device (neusky_b200 has no CPU path)")
         self.step, self.red, self.opt, self.fit = step, reducer, optimizer, fit
@@ -50,6 +51,7 @@ class GraphedTrainIteration:
         # starts makes the capture depend on the default stream (cudaErrorStreamCaptureImplicit).
         self._stream = torch.cuda.Stream(device=step.dev)
         self._fit_stream = torch.cuda.Stream(device=step.dev)
+        self._aux_stream = torch.cuda.Stream(device=step.dev)
         self.overlap_fit = bool(overlap_fit)
 
     # ------------------------------------------------------------------------------------------ host side of an iteration
@@ -93,6 +95,7 @@ class GraphedTrainIteration:
                 batch.setdefault(name, []).append(s[k])              # keys sort as #0, #1, ... (fewer than ten levels)
             else:
                 batch[name] = s[k]
+        st.aux_stream = self._aux_stream if self.overlap_fit else None      # RENI++ radiance as a parallel branch of the main forward
         self.red.zero_grad()
         run_fit = lambda: self.fit(s.get("fit.sky_origins"), s.get("fit.sky_directions"), rays=(s["fit.origins"], s["fit.directions"]),
                                    multi_view_points=s.get("fit.multi_view_points"))

@@ -16,6 +16,7 @@ There is no torch fallback: every op raises without the CUDA library.
 """
 from __future__ import annotations
 
+import contextlib
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -480,6 +481,7 @@ class NeuSkyTrainStep(torch.nn.Module):
         self.sdf_cfg = SDFConfig(scalings=self.scalings, log2_T=log2_T, split_geo=split_geo, split_colour=split)
         self.ddf_cfg = DDFConfig(scalings=self.scalings, log2_T=log2_T if ddf_log2_T is None else ddf_log2_T, radius=self.radius, sigmoid_scale=sigmoid_scale, split=split, split_bwd=ddf_split_bwd)
         self.cos_anneal_ratio = 1.0
+        self.aux_stream: Optional[torch.cuda.Stream] = None      # side stream for the RENI++ branch of forward (None = in line)
         self.grid_resolution = 10                                                                  # neusky_config.py:127
         self.proposal_fields, self.proposal_sampler, self.proposal_anneal = None, None, 1.0
         if proposal_params is not None or proposal_fields is not None:
@@ -551,6 +553,29 @@ class NeuSkyTrainStep(torch.nn.Module):
         sdf_w = self.sdf_weights()
         table = sdf_p["encoding.hash_table"]
 
+        # RENI++ radiance of every (camera, light direction) pair and along each camera ray; differentiable w.r.t. the per-image
+        # latent codes and scales, decoder frozen (neusky_model.py:261-269, 488-504, 535-549; neusky_config.py:94).  Independent of the
+        # geometry until the shading sum, and small (K x D + R rows on fp32 SIMT kernels: one wave of 128 blocks for the per-ray rows):
+        # with `aux_stream` set (graphed.GraphedTrainIteration) it runs as a parallel branch next to the SDF field instead of in line.
+        inv_s = torch.exp(sdf_p["deviation_network.variance"] * 10.0).clip(1e-6, 1e6)
+        aux, cur = self.aux_stream, None
+        if aux is not None:
+            cur = torch.cuda.current_stream()
+            aux.wait_stream(cur)
+        grid_density = None
+        with torch.cuda.stream(aux) if aux is not None else contextlib.nullcontext():
+            radiance = nba.reni_radiance(self.dirs, self.latents, self.scale, self.reni_blob, self.reni_blob_bwd)                 # [K,D,3]
+            bg = nba.reni_radiance(d.contiguous(), self.latents, self.scale, self.reni_blob, self.reni_blob_bwd, row_cam=cam)     # [R,3]
+            if grid_positions is not None:
+                # hashgrid density probe (neusky_model.py:675-734): 1000 grid points through the geometry network, ~30 tiny kernels forward
+                # + backward -- the same branch
+                gs, gg, _ = sdf_field(self.sdf_cfg, grid_positions, table, sdf_w, want_normals=True, want_albedo=False)
+                gap = 2.0 / self.grid_resolution
+                grid_density = _neus_alpha(gs[:, None], gg, grid_dirs, torch.full_like(gs[:, None], gap), inv_s, self.cos_anneal_ratio)
+        if aux is not None:
+            for t in (inv_s, *sdf_w):
+                t.record_stream(aux)
+
         near, far = sphere_collider(o, d, radius=1.0, training=True)
         rs = None
         if self.proposal_fields is not None:
@@ -567,7 +592,6 @@ class NeuSkyTrainStep(torch.nn.Module):
             starts, ends = uniform_samples(near, far, S)                               # [R,S]
         x = (o[:, None, :] + d[:, None, :] * starts[:, :, None]).reshape(-1, 3)
         sdf, grad, alb = sdf_field(self.sdf_cfg, x, table, sdf_w)
-        inv_s = torch.exp(sdf_p["deviation_network.variance"] * 10.0).clip(1e-6, 1e6)
         starts2, ends2 = starts.reshape(R, S), ends.reshape(R, S)
         weights, wa, normals, acc, p2p_raw, normal, _albedo, _bgT = nba.neus_composite(
             sdf.reshape(R, S), grad.reshape(R, S, 3), alb.reshape(R, S, 3), inv_s, d, starts2, ends2, ends2 - starts2, dn.reshape(R), self.cos_anneal_ratio)
@@ -575,10 +599,10 @@ class NeuSkyTrainStep(torch.nn.Module):
         p2p = torch.clip(p2p_raw.detach(), steps.min(), steps.max())                   # DepthRenderer clip; detached (stop-gradients "depth")
         pts = ops.surface_points(o, d, p2p, self.radius)
 
-        # RENI++ radiance of every (camera, light direction) pair and along each camera ray; differentiable w.r.t. the per-image
-        # latent codes and scales, decoder frozen (neusky_model.py:261-269, 488-504, 535-549; neusky_config.py:94)
-        radiance = nba.reni_radiance(self.dirs, self.latents, self.scale, self.reni_blob, self.reni_blob_bwd)                 # [K,D,3]
-        bg = nba.reni_radiance(d.contiguous(), self.latents, self.scale, self.reni_blob, self.reni_blob_bwd, row_cam=cam)     # [R,3]
+        if aux is not None:                                        # join the RENI++ branch before its results are read on this stream
+            cur.wait_stream(aux)
+            for t in (radiance, bg) + (() if grid_density is None else (grid_density,)):
+                t.record_stream(cur)
 
         vis, that, q, _term = ddf_visibility(self.ddf_cfg, pts, self.dirs_sel, self.visibility_threshold, ddf_p["position_encoding.hash_table"],
                                              ddf_p["ddf.final_layer.weight"], ddf_p["ddf.final_layer.bias"], ddf_param_list(ddf_p))
@@ -596,10 +620,8 @@ class NeuSkyTrainStep(torch.nn.Module):
             # proposal networks (weights -> density -> MLP + hash table; the fine histogram is detached)
             out["interlevel_loss"] = self.proposal_sampler.interlevel_loss(weights.detach(), rs, o, d, near, far)
             out["starts"], out["ends"] = starts, ends
-        if grid_positions is not None:
-            gs, gg, _ = sdf_field(self.sdf_cfg, grid_positions, table, sdf_w, want_normals=True, want_albedo=False)
-            gap = 2.0 / self.grid_resolution
-            out["grid_density"] = _neus_alpha(gs[:, None], gg, grid_dirs, torch.full_like(gs[:, None], gap), inv_s, self.cos_anneal_ratio)
+        if grid_density is not None:
+            out["grid_density"] = grid_density
         losses = self.get_loss_dict(out, batch)
         return sum(losses.values()), losses, out
 
