@@ -50,9 +50,14 @@ class GraphedTrainIteration:
         # were created on, and a node created by an eager iteration on the legacy default stream that is still alive when the capture
         # starts makes the capture depend on the default stream (cudaErrorStreamCaptureImplicit).
         self._stream = torch.cuda.Stream(device=step.dev)
-        self._fit_stream = torch.cuda.Stream(device=step.dev)
-        self._aux_stream = torch.cuda.Stream(device=step.dev)
         self.overlap_fit = bool(overlap_fit)
+        self._fit_stream = torch.cuda.Stream(device=step.dev)
+        # parameters used by several branches get their gradient contributions from several streams: intended here (the engine orders
+        # them); silence torch's per-backward warning about it
+        _quiet = getattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch", None)
+        if _quiet is not None and self.overlap_fit:
+            _quiet(False)
+        self._aux_stream = torch.cuda.Stream(device=step.dev)
 
     # ------------------------------------------------------------------------------------------ host side of an iteration
     def _host_inputs(self, batch, dirs, grid_positions, grid_dirs, sky_origins, sky_directions) -> Dict[str, Tensor]:
