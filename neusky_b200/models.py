@@ -383,6 +383,15 @@ class NeuSkyFactoModel(nn.Module):
 
     def _train_outputs(self, ray_bundle, batch, rotation, step) -> Dict[str, Any]:
         """Training forward + the tensors get_loss_dict needs, through neusky_b200/train.py on the SAME nn.Parameter objects."""
+        ts = self.train_step()
+        ts.cos_anneal_ratio = self._cos_anneal_ratio
+        ts.set_directions(self._illumination_directions())
+        if rotation is not None:
+            raise NotImplementedError("rotation is an eval-time option (fit / relight); the training forward takes none, like ns-train")
+        return self._train_outputs_with(ts, ray_bundle, batch)
+
+    def train_step(self):
+        """The training-path engine (neusky_b200/train.py:NeuSkyTrainStep) over THIS model's nn.Parameter objects (built once per device)."""
         from . import train
 
         if self.visibility_field is None:
@@ -399,11 +408,20 @@ class NeuSkyFactoModel(nn.Module):
                 share_params=True, latents=self.train_illumination_latents, scale=self.train_scale, visibility_threshold=self.visibility_threshold,
                 proposal_fields=list(self.proposal_networks), ddf_log2_T=self.visibility_field.field.position_encoding.log2_T)
             object.__setattr__(self, "_train_step", ts)      # NOT a registered sub-module: its parameters are ours already (state_dict stays the reference's)
-        ts = self._train_step
+        return self._train_step
+
+    def graphed_iteration(self, reducer, optimizer, fit=None, **kwargs):
+        """One whole training iteration of this model (zero-fill, forward, optional DDF fitting pass, backward, gradient all-reduce,
+        optimizer step) replayed as a CUDA graph: neusky_b200/graphed.py.  `reducer`: parallel.GradBucketReducer over
+        `list(model.train_step().parameters())`; `optimizer`: anything with `.step()` over the same parameters.  For loops that own
+        the iteration (nerfstudio's Trainer calls forward / backward / step separately and stays on the eager path)."""
+        from .graphed import GraphedTrainIteration
+
+        ts = self.train_step()
         ts.cos_anneal_ratio = self._cos_anneal_ratio
-        ts.set_directions(self._illumination_directions())
-        if rotation is not None:
-            raise NotImplementedError("rotation is an eval-time option (fit / relight); the training forward takes none, like ns-train")
+        return GraphedTrainIteration(ts, reducer, optimizer, fit=fit, **kwargs)
+
+    def _train_outputs_with(self, ts, ray_bundle, batch) -> Dict[str, Any]:
         b = {"origins": ray_bundle.origins.reshape(-1, 3).contiguous(), "directions": ray_bundle.directions.reshape(-1, 3).contiguous(),
              "dnorm": ray_bundle.metadata["directions_norm"].reshape(-1, 1).contiguous(), "cam": ray_bundle.camera_indices.reshape(-1)}
         grid = None

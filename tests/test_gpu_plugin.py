@@ -339,3 +339,35 @@ def test_model_training_forward_backward_on_reference_named_parameters(dev):
     for n, q in m.named_parameters():
         if n in snap:
             assert torch.equal(q.grad, snap[n]), n
+
+
+def test_model_graphed_iteration_trains_the_models_own_parameters(dev):
+    """NeuSkyFactoModel.graphed_iteration: the whole iteration replayed as a CUDA graph (neusky_b200/graphed.py) over the model's own
+    nn.Parameter objects -- after one eager and two replayed iterations the module's parameters have moved, the loss is finite and the
+    state_dict still has the reference's layout."""
+    from neusky_b200.parallel import GradBucketReducer
+
+    m, p = _build_model(dev, S=16)
+    m.train()
+    ts = m.train_step()
+    params = [q for q in ts.parameters() if q.requires_grad]
+    red = GradBucketReducer(params, big_bytes=64 << 10)
+    it = m.graphed_iteration(red, torch.optim.SGD(params, lr=1e-4), eager_warmup=1)
+    R = 96
+    g = torch.Generator().manual_seed(4)
+    o = torch.tensor([0.0, -0.9, 0.25]).expand(R, 3) + 0.02 * torch.randn(R, 3, generator=g)
+    d = torch.nn.functional.normalize(-o + 0.4 * torch.randn(R, 3, generator=g), dim=-1)
+    batch = {"origins": o.contiguous(), "directions": d.contiguous(), "dnorm": torch.ones(R, 1), "cam": torch.randint(0, 3, (R,), generator=g).to(torch.int32),
+             "image": torch.rand(R, 3, generator=g), "fg": (torch.rand(R, generator=g) > 0.3).float(), "ground": (torch.rand(R, generator=g) > 0.7).float(),
+             "sky": (torch.rand(R, generator=g) > 0.8).float()}
+    keys_before = set(m.state_dict().keys())
+    w0 = m.field.glin1.weight_v.detach().clone()
+    t0 = m.visibility_field.field.ddf.net[2].layer.weight.detach().clone()
+    losses = []
+    for _ in range(3):
+        gp, gd = torch.rand(27, 3, generator=g) * 2 - 1, torch.nn.functional.normalize(torch.randn(27, 3, generator=g), dim=-1)
+        losses.append(float(it(batch, m._illumination_directions().cpu(), gp, gd)))
+    assert it.captures == 1 and it.eager_steps == 1 and it.replays == 2
+    assert all(l == l and abs(l) < 1e6 for l in losses), losses
+    assert not torch.equal(w0, m.field.glin1.weight_v) and not torch.equal(t0, m.visibility_field.field.ddf.net[2].layer.weight)
+    assert set(m.state_dict().keys()) == keys_before

@@ -346,6 +346,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128) mma_rate2_kerne
     const long long t0 = clock64();
     for (int i = 0; i < iters; ++i) {
       const int k0 = (i & 15) * 16;
+      if (mode == 3) {
+        // A operand from TMEM (columns [256, 384): K = 256 halves of each CTA's 128 rows), B from shared memory: the ".ts" form of the pair MMA
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem),
+            "r"(tmem + 256 + k0 / 2), "l"(make_smem_desc(sB + (k0 / 8) * Nh * 16, Nh * 16, 128)), "r"(idesc), "r"(1)
+            : "memory");
+      } else
       umma_ss2(tmem, make_smem_desc(sA + (k0 / 8) * 128 * 16, 128 * 16, 128), make_smem_desc(sB + (k0 / 8) * Nh * 16, Nh * 16, 128), idesc, 1);
       if (commit_every > 0 && ((i + 1) & (commit_every - 1)) == 0) {
         if (mode == 0) umma_commit2(smem_u32(&bar2));                 // multicast to both CTAs
