@@ -756,7 +756,7 @@ def main():
                     "api": "neusky_b200.render.SkyShader.shade_points_host", "steps": e2e_steps},
             "gpu_launches": launches,
             "roofline": {"kernel": "sky_shade_tc2_kernel", "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": _ncu_traffic(pairs), "traffic_source": "committed ncu capture of this command, not measured in the run: profiles/k4_ncu_summary.json (r01_k4_tc2_dram_full.csv)",
+                         "traffic": _ncu_traffic(pairs), "traffic_source": "committed ncu capture of this command, not measured in the run: profiles/k4_ncu_summary.json (r02_k4_tc2_dram_full_final.csv)",
                          "peak_source": f"{peaks['source']} dense bf16/fp16 cuBLAS, sustained ({peaks['tf_burst']:.0f} burst)",
                          "frac_of_burst": achieved / peaks["tf_burst"], "pairs_per_launch": pairs, "flop_per_pair": FLOP_PER_PAIR,
                          "ms_per_launch": 1e3 * k4_s, "k4_share_of_step": k4_s * args.steps / t_dev if world == 1 else None},
