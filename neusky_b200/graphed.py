@@ -32,7 +32,8 @@ Tensor = torch.Tensor
 class GraphedTrainIteration:
     def __init__(self, step, reducer, optimizer, fit=None, graph: bool = True, eager_warmup: int = 2, overlap_fit: bool = True):
         """`step`: train.NeuSkyTrainStep; `reducer`: parallel.GradBucketReducer over its parameters (the .grad views are the
-        graph's static gradient buffers); `optimizer`: stepped after the reduce; `fit`: ddf_fit.DDFFit or None.
+        graph's static gradient buffers); `optimizer`: anything with `.step()`, stepped after the reduce (None: the caller steps);
+        `fit`: ddf_fit.DDFFit or None.  Training only: every call runs a backward, so gradients must be enabled.
         `graph=False` runs every iteration eagerly through the same code (the comparison arm of bench.py and the tests).
         `overlap_fit`: run the DDF fitting pass and the RENI++ radiance decodes as parallel branches of the iteration (side streams,
         fork / join inside the captured graph) instead of in line with the main pass."""
@@ -159,6 +160,8 @@ class GraphedTrainIteration:
         illumination directions (host).  Returns the iteration's total loss (a device scalar, overwritten by the next call); the
         parameters have been updated when it returns (asynchronously, on the current stream)."""
         st = self.step
+        if not torch.is_grad_enabled():
+            raise RuntimeError("GraphedTrainIteration: called under torch.no_grad(); an iteration includes the backward pass")
         inp = self._host_inputs(batch, dirs, grid_positions, grid_dirs, sky_origins, sky_directions)
         key = self._key_of(inp)
         if key != self._key:
@@ -182,6 +185,7 @@ class GraphedTrainIteration:
                     self._seen += 1
                     self.eager_steps += 1
                 self.red.finish()
-                self.opt.step()
+                if self.opt is not None:
+                    self.opt.step()
             caller.wait_stream(self._stream)                 # the caller's stream sees the updated parameters and the loss
         return self.loss

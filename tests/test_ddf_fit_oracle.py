@@ -93,3 +93,29 @@ def test_host_loss_dict_matches_reference_on_golden_outputs(golden):
         assert abs(float(v) - float(g["loss_" + k])) <= 1e-6 * max(1.0, abs(float(g["loss_" + k]))), k
     m = fit.get_metrics_dict(out, batch)
     assert np.isfinite(float(m["depth_psnr"]))
+
+
+def test_draw_host_consumes_the_cpu_generator_like_the_in_line_pass():
+    """DDFFit.draw_host (the host half of a fitting pass, hoisted out of the captured iteration: neusky_b200/graphed.py) must draw
+    exactly what the in-line pass draws, in the same order on torch's CPU generator: the sampler's rays (ddf_sampler.py), then the
+    multi-view sphere points with |z| (ddf_model.py:279-284) -- so a graphed training run sees the reference's random sequence."""
+    fit = F.DDFFit.__new__(F.DDFFit)                      # host logic only: no NeuSkyTrainStep (that needs the CUDA library's device)
+    fit.config, fit.training = F.DDFModelConfig(), True
+    fit.sampler = F.VMFDDFSampler(F.DDFSamplerConfig(), ddf_sphere_radius=1.0, device="cpu")
+    torch.manual_seed(11)
+    o, d, mv = fit.draw_host()
+    torch.manual_seed(11)
+    o2, d2 = fit.sampler()
+    mv2 = F.random_points_on_unit_sphere(o2.shape[0])
+    mv2[:, 2] = torch.abs(mv2[:, 2])
+    assert torch.equal(o, o2) and torch.equal(d, d2) and torch.equal(mv, mv2)
+    assert o.device.type == "cpu" and o.shape == (1024, 3) and bool((mv[:, 2] >= 0).all())
+    assert str(fit.sampler.device) == "cpu"
+    # without the multi-view loss (or in eval mode) no extra draw is consumed
+    fit.training = False
+    torch.manual_seed(11)
+    _, _, mv3 = fit.draw_host()
+    nxt = torch.rand(1)
+    torch.manual_seed(11)
+    fit.sampler()
+    assert mv3 is None and torch.equal(nxt, torch.rand(1))

@@ -32,3 +32,27 @@ def test_equirect_matches_oracle_and_bench():
     assert d.shape == (2048, 3) and int((d[:, 2] > 0).sum()) == 1024 and int((d[:, 2] == 0).sum()) == 0
     assert torch.equal(d, O.equirect_directions(64))
     assert torch.equal(d, bench._equirect_directions(64))
+
+
+def test_icosphere_upper_hemisphere_count_is_rotation_invariant():
+    """The subdivided icosahedron is centrally symmetric (v in the set <=> -v in the set), so under ANY rotation exactly half of its
+    directions have z > 0 (up to vertices exactly on the equator, a measure-zero event).  The training iteration's shapes are therefore
+    static -- D' = D / 2 -- which is what lets neusky_b200/graphed.py capture it once as a CUDA graph."""
+    from scipy.spatial.transform import Rotation
+
+    base = samplers.IcosahedronSampler(512)().frustums.directions.to(torch.float64).numpy()      # [642, 3]
+    assert base.shape == (642, 3)
+    # central symmetry: every direction has its antipode in the set
+    d = np.abs(base[:, None, :] + base[None, :, :]).max(-1)                                       # |v_i + v_j|
+    assert float(d.min(axis=1).max()) < 1e-6
+    rots = Rotation.random(50, random_state=np.random.RandomState(3)).as_matrix()
+    for Rm in rots:
+        z = (base @ Rm).astype(np.float32)[:, 2]
+        assert int((z > 0).sum()) == 321
+    # the sampler's own rotated draws (what the training loop consumes)
+    smp = samplers.IcosahedronSampler(512, apply_random_rotation=True, seed=5)
+    for _ in range(10):
+        dirs = smp().frustums.directions
+        assert int((dirs[:, 2] > 0).sum()) == 321
+    # the UN-rotated set has 26 vertices exactly on the equator: 308 strictly above it (the eval configuration's D')
+    assert int((samplers.IcosahedronSampler(512)().frustums.directions[:, 2] > 0).sum()) == 308
