@@ -101,12 +101,17 @@ class GraphedTrainIteration:
                 batch.setdefault(name, []).append(s[k])              # keys sort as #0, #1, ... (fewer than ten levels)
             else:
                 batch[name] = s[k]
-        st.aux_stream = self._aux_stream if self.overlap_fit else None      # RENI++ radiance as a parallel branch of the main forward
+        # Branches only where no collective is launched from inside the backward: an EAGER multi-GPU iteration all-reduces each bucket
+        # from a gradient hook, and NCCL orders that collective after the hook's stream only -- gradients of the same bucket written
+        # by another branch's stream would race with it.  Captured iterations (hooks silent, buckets reduced after the replay) and
+        # single-GPU runs have no such collective.
+        overlap = self.overlap_fit and (self.red.capturing or self.red.world == 1)
+        st.aux_stream = self._aux_stream if overlap else None               # RENI++ radiance as a parallel branch of the main forward
         self.red.zero_grad()
         run_fit = lambda: self.fit(s.get("fit.sky_origins"), s.get("fit.sky_directions"), rays=(s["fit.origins"], s["fit.directions"]),
                                    multi_view_points=s.get("fit.multi_view_points"))
         fit_res = None
-        if self.fit is not None and self.overlap_fit:
+        if self.fit is not None and overlap:
             # The DDF fitting pass is independent of the main pass until the two losses are added, and its kernels are small (1024 rays,
             # 2304 DDF rows): it runs as a second BRANCH (its own stream; a fork / join inside the captured graph) next to the main
             # pass's 328k-row kernels instead of in front of them.  Autograd runs each branch's backward on the branch's stream.
